@@ -1,0 +1,111 @@
+"""Generate tests/golden/*.npz by executing the UNMODIFIED reference under oracle/shim (build container only).
+
+TEST INFRASTRUCTURE.  Run:  python oracle/make_golden.py
+Requires /root/reference (absent on the GPU box, which only consumes the committed fixtures).  The reference has no
+tests or golden vectors of its own, so these fixtures are the parity pins: outputs of
+reference CRN_ELU.TemporalCRN / distillation_crn.TemporalCRN / utility.{segmentation,over_add,decompress_cIRM,
+cal_si_snr} on deterministic synthetic weights and mixtures from oracle/synth.py.
+"""
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path[:0] = [os.path.join(HERE, "shim"), "/root/reference", REPO]
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torchaudio  # noqa: E402
+
+torchaudio.set_audio_backend = lambda *a, **k: None  # API removed in torchaudio 2.x (reference utility.py:475-476)
+
+import CRN_ELU  # noqa: E402  (reference, unmodified)
+import distillation_crn  # noqa: E402  (reference, unmodified)
+import utility  # noqa: E402  (reference, unmodified)
+
+from oracle import synth  # noqa: E402
+
+OUT = os.path.join(REPO, "tests", "golden")
+
+TEACHER = dict(num_channels=[16, 32, 64, 128], num_freqs=201, hidden=512, num_layers=2, num_inputs=3, kernel_size=3)
+STUDENT = dict(num_channels=[16, 32, 64, 64], num_freqs=201, hidden=128, num_layers=2, num_inputs=3, kernel_size=3)
+SMALL = dict(num_channels=[8, 8, 16, 16], num_freqs=201, hidden=32, num_layers=2, num_inputs=3, kernel_size=3)
+
+
+def load_into(model, weights):
+    sd = {k: torch.from_numpy(v) for k, v in synth.with_alias_keys(weights).items()}
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return model.eval()
+
+
+def run_model(cls, cfg, seed, B, L, tag, continuation=False):
+    weights = synth.make_crn_weights(seed=seed, **cfg)
+    model = load_into(cls(segment_length=3200, dropout=0.0, **cfg), weights)
+    mix, _ = synth.make_mixture(B, L)
+    x = torch.from_numpy(mix)
+    res = {}
+    with torch.no_grad():
+        y = model.realtime_process(x)
+        y = y[0] if isinstance(y, tuple) else y
+        res["out"] = y.numpy()
+        if continuation:
+            mix2, _ = synth.make_mixture(B, L // 2, first_stream=100)
+            y2 = model.realtime_process(torch.from_numpy(mix2), True)
+            y2 = y2[0] if isinstance(y2, tuple) else y2
+            res["out_cont"] = y2.numpy()
+        # one isolated forward on the first chunk (fresh state): spectrum in -> enhanced spectrum out
+        model.reset()
+        seg, gap = model.segmentation(torch.cat([torch.zeros(B, 3, 1600), x], dim=-1))
+        N = seg.shape[0] // B
+        spec = model.stft_trans(seg).reshape(B, N, 3, 201, -1, 2)
+        f0 = model.forward(spec[:, 1].contiguous())
+        f0 = f0[0] if isinstance(f0, tuple) else f0
+        res["spec_chunk1"] = spec[:, 1].numpy()
+        res["fwd_chunk1"] = f0.numpy()
+        res["istft_chunk1"] = model.istft_trans(f0).numpy()
+        res["gap"] = np.array([gap])
+        res["n_chunks"] = np.array([N])
+    res["meta"] = np.array([seed, B, L])
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **res)
+    print(tag, {k: v.shape for k, v in res.items()}, "peak", float(np.abs(res["out"]).max()))
+
+
+def framing():
+    """Integer-exact fixtures: segmentation of an index ramp, over_add of chunk ids, gap / N for several lengths."""
+    res = {}
+    lengths = [1, 1599, 1600, 1601, 3199, 3200, 3201, 4000, 9600, 48000, 65600]
+    gaps, ns = [], []
+    for L in lengths:
+        ramp = torch.arange(1, L + 1, dtype=torch.float32).reshape(1, 1, L).repeat(2, 3, 1)
+        ramp[1] += 100000
+        ramp[:, 1] += 0.25
+        ramp[:, 2] += 0.5
+        seg, gap = utility.segmentation(ramp, 3200)
+        gaps.append(gap)
+        ns.append(seg.shape[0] // 2)
+        if L in (1601, 4000):
+            res[f"seg_{L}"] = seg.numpy()
+            chunks = seg[:, 0].reshape(2, -1, 3200)
+            res[f"ola_{L}"] = utility.over_add(chunks, gap).numpy()
+    res["lengths"], res["gaps"], res["n_chunks"] = np.array(lengths), np.array(gaps), np.array(ns)
+    m = torch.linspace(-12, 12, 4001)
+    res["cirm_in"] = m.numpy()
+    res["cirm_out"] = utility.decompress_cIRM(m).numpy()
+    mix, src = synth.make_mixture(3, 5000)
+    est = torch.from_numpy(mix[:, 0])
+    res["sisnr"] = utility.cal_si_snr(est, torch.from_numpy(src), torch.tensor([5000, 4000, 3000])).numpy()
+    np.savez_compressed(os.path.join(OUT, "framing.npz"), **res)
+    print("framing", gaps, ns)
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    framing()
+    run_model(CRN_ELU.TemporalCRN, SMALL, 7, 2, 4000, "crn_small", continuation=True)
+    run_model(CRN_ELU.TemporalCRN, TEACHER, 0, 2, 8000, "crn_teacher", continuation=True)
+    run_model(distillation_crn.TemporalCRN, STUDENT, 3, 2, 8000, "crn_student")
+    n_t = sum(int(np.prod(s)) for s in synth.crn_param_shapes(**TEACHER).values())
+    n_s = sum(int(np.prod(s)) for s in synth.crn_param_shapes(**STUDENT).values())
+    print("param counts (README.md:56,58 say 6.16 / 0.81 M):", n_t, n_s)
