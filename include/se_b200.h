@@ -1,0 +1,129 @@
+/*
+ * se_b200.h -- C-ABI of the B200-native streaming speech-enhancement hot path.
+ *
+ * Drop-in boundary for the chunked `realtime_process` path of KI-D/Speech-Enhancement-Mi's CRN_ELU.TemporalCRN
+ * (and the distilled student of distillation_crn.py).  The reference has no native code: each entry point below
+ * replaces a PyTorch call site of the reference, cited as file:line into the reference tree.  No torch types cross
+ * this boundary: plain pointers (device pointers unless the name ends in `_host`), sizes and an opaque CUDA stream
+ * handle (`void*` = cudaStream_t, NULL = default stream).
+ *
+ * Every function returns 0 on success and a non-zero status on failure; the message is available from
+ * se_last_error() (thread-local).  Nothing throws across the ABI.  There is no CPU fallback: without a CUDA device
+ * se_ctx_create fails.
+ */
+#ifndef SE_B200_H
+#define SE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SE_MAX_LEVELS 8
+
+/* numerics variants: CRN_ELU.py (teacher) vs distillation_crn.py:51,340 (student) */
+#define SE_VARIANT_CRN_ELU 0
+#define SE_VARIANT_DISTILLED 1
+
+/* arithmetic of the dense contractions */
+#define SE_PRECISION_FP32 0 /* fp32 FMA on CUDA cores (exact mode)                     */
+#define SE_PRECISION_TF32 1 /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (fast)  */
+
+/* Mirrors the kwargs of CRN_ELU.TemporalCRN.__init__ (CRN_ELU.py:321-323; config.yaml:205-217), with
+ * win_length / hop_length already converted from milliseconds to samples (speechbrain STFT: round(sr/1000*ms)). */
+typedef struct se_crn_config {
+    int32_t num_inputs;                  /* microphones M (3)                              */
+    int32_t num_freqs;                   /* F = n_fft/2+1 (201)                            */
+    int32_t num_levels;                  /* len(num_channels) (4)                          */
+    int32_t num_channels[SE_MAX_LEVELS]; /* [16,32,64,128] teacher / [16,32,64,64] student */
+    int32_t hidden;                      /* GRU hidden (512 / 128)                         */
+    int32_t num_layers;                  /* GRU layers (2)                                 */
+    int32_t kernel_size;                 /* temporal kernel of encoder/decoder (3)         */
+    int32_t segment_length;              /* chunk K (3200); hop is K/2                     */
+    int32_t n_fft;                       /* 400                                            */
+    int32_t win_length;                  /* samples (400)                                  */
+    int32_t hop_length;                  /* samples (160)                                  */
+    int32_t variant;                     /* SE_VARIANT_*                                   */
+    int32_t precision;                   /* SE_PRECISION_*                                 */
+    int32_t max_streams;                 /* capacity of the per-stream state arena         */
+} se_crn_config;
+
+typedef struct se_ctx se_ctx;
+
+/* ---- lifetime / errors ------------------------------------------------------------------------------------ */
+/* replaces: TemporalCRN.__init__ + .to(device)  (CRN_ELU.py:321-365; train.py:58,72; predict.py:45-48) */
+int se_ctx_create(se_ctx** out, int device, const se_crn_config* cfg);
+int se_ctx_destroy(se_ctx* ctx);
+/* thread-local message of the last failing call (the reference raises Python exceptions) */
+const char* se_last_error(void);
+/* library / build identification, e.g. "se_b200 0.1 sm_100a" */
+const char* se_version(void);
+
+/* ---- parameters --------------------------------------------------------------------------------------------- */
+/* The DISTINCT parameter tensors of TemporalCRN.state_dict() in a fixed order (alias keys `net.0.*` excluded;
+ * CRN_ELU.py:225,282).  replaces: nn.Module parameter registration / load_state_dict (train.py:110; predict.py:47). */
+int se_crn_num_params(const se_ctx* ctx);
+const char* se_crn_param_name(const se_ctx* ctx, int index);
+int64_t se_crn_param_numel(const se_ctx* ctx, int index);
+/* ptrs[i] -> contiguous fp32 tensor i (device or host memory, reference layout).  The library re-lays the
+ * weights out for its kernels; call again after every change of the parameters. */
+int se_crn_bind_weights(se_ctx* ctx, const float* const* ptrs, int n, void* stream);
+
+/* ---- per-stream state (CRN_ELU.py:158,228 buffers + GRU h; reset: CRN_ELU.py:408-415) ------------------------ */
+/* zero the causal-conv buffers, GRU state and overlap-add carry of streams [first, first+count) */
+int se_crn_state_reset(se_ctx* ctx, int first, int count, void* stream);
+/* bytes of carried state per stream */
+int64_t se_crn_state_bytes_per_stream(const se_ctx* ctx);
+
+/* ---- the fused hot path: one chunk step for B streams --------------------------------------------------------
+ * replaces one iteration of the loop CRN_ELU.py:485-489 plus its share of preprocessing/postprocessing
+ * (stft_trans :417-424, forward :367-406, istft_trans :426-432, over_add utility.py:393-403).
+ *   in  : chunk of K samples per stream and microphone: in[b*in_stream_stride + m*in_mic_stride + n]
+ *   out : K/2 samples per stream: (first half of this chunk's iSTFT + carried second half of the previous)/2
+ * The carry is always updated.  Streams are rows [0,B) of the state arena.                                      */
+int se_crn_process_chunk(se_ctx* ctx, const float* in, int64_t in_stream_stride, int64_t in_mic_stride,
+                         float* out, int64_t out_stream_stride, int B, void* stream);
+
+/* replaces: TemporalCRN.realtime_process(mixture[B,M,L], flag) -> [B,L]  (CRN_ELU.py:472-509) on device memory.
+ * mixture and out are contiguous [B,M,L] / [B,L].  flag=0 prepends K/2 zeros, resets state and strips the pad.    */
+int se_crn_realtime_process(se_ctx* ctx, const float* mixture, int B, int64_t L, int flag, float* out,
+                            void* stream);
+/* same with HOST buffers: host->device and device->host copies happen inside (this is what predict.py:48,92 times,
+ * where model and tensors sit on the CPU). Synchronous. */
+int se_crn_realtime_process_host(se_ctx* ctx, const float* mixture, int B, int64_t L, int flag, float* out);
+
+/* ---- the pieces, for callers that use the reference's finer-grained methods ----------------------------------- */
+/* replaces: TemporalCRN.stft_trans (CRN_ELU.py:417-424): chunks [R,M,K] -> spectrum [R,M,F,T,2] (reference layout) */
+int se_stft_trans(se_ctx* ctx, const float* chunks, int R, float* spec, void* stream);
+/* replaces: TemporalCRN.istft_trans (CRN_ELU.py:426-432): spectrum [R,F,T,2] -> [R,K] */
+int se_istft_trans(se_ctx* ctx, const float* spec, int R, float* out, void* stream);
+/* replaces: TemporalCRN.forward (CRN_ELU.py:367-406): x [B,M,F,T,2] -> enhanced spectrum [B,F,T,2]; advances state */
+int se_crn_forward_chunk(se_ctx* ctx, const float* spec_in, float* spec_out, int B, void* stream);
+/* replaces: utility.segmentation (utility.py:339-370): [B,C,L] -> [B*N,C,K]; *gap / *n_chunks as the reference */
+int se_segmentation(const float* x, int B, int C, int64_t L, int K, float* out, int* gap, int* n_chunks,
+                    void* stream);
+/* chunk-grid arithmetic only (host, no GPU): gap and N for a signal of L samples (utility.py:325-327,357-368) */
+int se_chunk_grid(int64_t L, int K, int* gap, int* n_chunks);
+/* replaces: utility.over_add (utility.py:373-403): [C,N,K] -> [C, N*K/2 - K/2 - gap] */
+int se_over_add(const float* chunks, int C, int N, int K, int gap, float* out, void* stream);
+
+/* ---- introspection used by bench.py --------------------------------------------------------------------------- */
+/* number of kernel launches one se_crn_process_chunk issues (graph nodes included) */
+int se_crn_launches_per_chunk(const se_ctx* ctx);
+/* enable (1) / disable (0) CUDA-graph replay of the chunk step; default 1 */
+int se_crn_set_graph(se_ctx* ctx, int enable);
+/* time one named stage of the chunk step in isolation: runs it `iters` times on B streams and returns the average
+ * device time in milliseconds in *ms.  Stages: "stft", "mask_istft", "step".  Used for the roofline report. */
+int se_crn_time_stage(se_ctx* ctx, const char* stage, int B, int iters, float* ms);
+
+/* ---- test hook ------------------------------------------------------------------------------------------------- */
+/* Copy the logical interior of a named internal activation of stream b to HOST memory as [T][F][C] (channels-last),
+ * dims = {T, F, C}.  Names: "pre_in<i>", "enc_in<i>", "dec_in<j>", "xg", "fcraw", "hseq<l>", "ylast", "noisy".
+ * Synchronises the device.  Used by tests/ to localise a parity failure to one layer (CRN_ELU.py:375-399). */
+int se_debug_read(se_ctx* ctx, const char* name, int b, float* host_dst, int64_t max_floats, int* dims);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SE_B200_H */

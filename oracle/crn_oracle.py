@@ -216,23 +216,36 @@ class CRNOracle:
         return torch.cat([mag, ipd], dim=1)
 
     # -- forward (CRN_ELU.py:367-406) ------------------------------------------------------------------------
-    def forward(self, x, return_mask=False):
-        """x [B, M, F, T, 2] (STFT of one chunk) -> enhanced spectrum [B, F, T, 2]."""
+    def forward(self, x, return_mask=False, trace=None):
+        """x [B, M, F, T, 2] (STFT of one chunk) -> enhanced spectrum [B, F, T, 2].
+
+        ``trace``: optional dict that receives the activation entering every block ([B, C, F, T]), keyed like the
+        CUDA path's internal buffers (pre_in<i>, enc_in<i>, xg, dec_in<j>) -- used to localise parity failures."""
         noisy = x[:, 0]
         y = self.features(x)
         for i, d in enumerate((1, 2, 4)):
+            if trace is not None:
+                trace[f"pre_in{i}"] = y
             y = self._tconv(f"preconvlist.{i}", y, (1, 1), (d, 1), 2 * d, 4) + y
         residuals = [y]
         for i in range(self.L):
             d = 2 ** i
+            if trace is not None:
+                trace[f"enc_in{i}"] = y
             y = self._tconv(f"convlist.{i}", y, (2, 1), (1, d), 2, (self.kernel_size - 1) * d)
             residuals.append(y)
         B, C, Fq, T = y.shape
+        if trace is not None:
+            trace["xg"] = y
         y = self._gru(y.reshape(B, C * Fq, T)).reshape(B, C, Fq, T)
         idx = -2
         for j in range(self.L - 1):
+            if trace is not None:
+                trace[f"dec_in{j}"] = y
             y = self._tdeconv(f"deconvlist.{j}", y, 2 ** j, residuals[idx])
             idx -= 1
+        if trace is not None:
+            trace[f"dec_in{self.L - 1}"] = y
         y = self._tdeconv(f"deconvlist.{self.L - 1}", y, 2 ** (self.L - 1)).permute(0, 2, 3, 1)
         m = decompress_cirm(y)
         er = m[..., 0] * noisy[..., 0] - m[..., 1] * noisy[..., 1]

@@ -1,0 +1,1264 @@
+// Context, weight re-layout, chunk-step program and the C-ABI of the CRN_ELU streaming path (include/se_b200.h).
+//
+// Data layout in HBM (per stream, fp32, channels-last): every tensor that feeds a convolution lives in a physically
+// zero-bordered buffer [Tp][Fp][C] so that the implicit-GEMM gather (GemmParams::koff) never needs a bounds check:
+//   * causal convs (CRN_ELU.py:230-247): `pad` leading frames hold the carried state (= last `pad` frames of the
+//     previous chunk's block input), F is bordered by the conv's frequency padding;
+//   * transposed convs (CRN_ELU.py:290-307): 2*d trailing zero frames (the `[..., -T:]` crop turns the time taps into
+//     look-ahead inside the chunk) and one zero row on each side of F (stride-2 phase split, taps {0,2,4} / {1,3}).
+// The carried state of a stream is therefore the leading frames of its conv-input buffers, slot 0 of the two GRU
+// hidden sequences and the K/2 overlap-add carry; "roll" moves the trailing frames to the front after each chunk.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/se_b200.h"
+#include "se_internal.h"
+
+namespace se {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+namespace {
+
+constexpr int T = kFramesPerChunk;
+constexpr int NBIN = 201;
+constexpr int KCHUNK = 3200;
+constexpr int PHOP = KCHUNK / 2;
+
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
+    float* base = nullptr;
+    int C = 0, F = 0;
+    int padT0 = 0, padT1 = 0, padF0 = 0, padF1 = 0;
+    int Tp = 0, Fp = 0;
+    long long sB = 0, sT = 0, sF = 0;
+    float* interior() const { return base + padT0 * sT + padF0 * sF; }
+    long long per_stream() const { return sB; }
+};
+
+enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW };
+enum Stage { ST_STFT = 0, ST_PRECONV, ST_ENCODER, ST_GRU, ST_DECODER, ST_MASK, ST_ROLL, ST_COUNT };
+const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"};
+
+struct Op {
+    OpKind kind;
+    int stage;
+    GemmParams g;
+    int rows_per_stream = 0;
+    NormApplyParams n;
+    // GRU pointwise
+    const float* gi = nullptr;
+    long long giB = 0;
+    const float* gh = nullptr;
+    const float* hprev = nullptr;
+    long long hB = 0;
+    float* hout = nullptr;
+    int H = 0;
+};
+
+struct ParamInfo {
+    std::string name;
+    std::vector<int> shape;
+    int64_t numel() const {
+        int64_t n = 1;
+        for (int s : shape) n *= s;
+        return n;
+    }
+};
+
+using HostParams = std::map<std::string, std::vector<float>>;
+using PackFn = std::function<void(const HostParams&, float*)>;  // fills a host mirror of the packed-weight arena
+
+}  // namespace
+}  // namespace se
+
+using namespace se;
+
+struct se_ctx {
+    se_crn_config cfg;
+    int device = 0;
+    int maxB = 0;
+    int L = 0;        // levels
+    int C0 = 0;       // 2M-1 real input channels
+    int student = 0;
+    std::vector<int> encF;  // F after each encoder level
+    int Fg = 0, Cg = 0, feat = 0, H = 0;
+
+    std::vector<ParamInfo> params;
+    std::vector<void*> allocs;
+
+    // activations
+    std::vector<Act> pre_in;  // 3 preconv inputs
+    std::vector<Act> enc_in;  // L encoder inputs
+    std::vector<Act> dec_in;  // L decoder inputs
+    float *xg = nullptr, *gi = nullptr, *gh = nullptr, *hseq[2] = {nullptr, nullptr}, *fcraw = nullptr;
+    float *tmp_e = nullptr, *tmp_y = nullptr, *tmp_rm = nullptr, *tmp_rr = nullptr;
+    float *noisy = nullptr, *ylast = nullptr, *carry = nullptr;
+    double* stats = nullptr;
+    int n_stats = 0;
+    int stats_last = -1;  // slot of the last deconv's statistics
+    const float *w_last = nullptr, *b_last = nullptr;
+
+    // packed weights
+    float* warena = nullptr;
+    size_t warena_floats = 0;
+    int* karena = nullptr;
+    std::vector<int> khost;
+    std::vector<PackFn> packers;
+    bool weights_bound = false;
+
+    std::vector<Op> ops;
+    RollTable roll{};
+    RollTable zero_tab{};
+
+    IoDesc* io_dev = nullptr;
+    bool use_graph = true;
+    std::map<int, cudaGraphExec_t> graphs;  // keyed by B
+    cudaStream_t own_stream = nullptr;
+
+    // staging for the host variant
+    float *h_in = nullptr, *h_out = nullptr;
+    size_t h_in_floats = 0, h_out_floats = 0;
+
+    size_t reserve_w(size_t n) {
+        size_t off = warena_floats;
+        warena_floats += (n + 3) / 4 * 4;
+        return off;
+    }
+    int reserve_k(const std::vector<int>& v) {
+        int off = (int)khost.size();
+        khost.insert(khost.end(), v.begin(), v.end());
+        return off;
+    }
+};
+
+namespace {
+
+template <typename Tp>
+int dev_alloc(se_ctx* c, Tp** out, size_t count) {
+    void* p = nullptr;
+    SE_CUDA_OK(cudaMalloc(&p, count * sizeof(Tp)));
+    SE_CUDA_OK(cudaMemset(p, 0, count * sizeof(Tp)));
+    c->allocs.push_back(p);
+    *out = reinterpret_cast<Tp*>(p);
+    return 0;
+}
+
+int make_act(se_ctx* c, Act& a, int C, int F, int Tn, int padT0, int padT1, int padF0, int padF1) {
+    a.C = C;
+    a.F = F;
+    a.padT0 = padT0;
+    a.padT1 = padT1;
+    a.padF0 = padF0;
+    a.padF1 = padF1;
+    a.Tp = padT0 + Tn + padT1;
+    a.Fp = padF0 + F + padF1;
+    a.sF = C;
+    a.sT = (long long)a.Fp * C;
+    a.sB = a.sT * a.Tp;
+    return dev_alloc(c, &a.base, (size_t)a.sB * c->maxB);
+}
+
+// ---- parameter registry (order of TemporalCRN.state_dict() without the `net.0` aliases; CRN_ELU.py:335-365) -------
+void register_params(se_ctx* c) {
+    auto add = [&](const std::string& n, std::vector<int> s) { c->params.push_back({n, std::move(s)}); };
+    const se_crn_config& g = c->cfg;
+    auto conv_block = [&](const std::string& p, int ci, int co, int kf, int kt) {
+        add(p + ".conv.weight", {co, ci, kf, kt});
+        add(p + ".conv.bias", {co});
+        add(p + ".conv_trans.weight", {co, co, 1, 1});
+        add(p + ".conv_trans.bias", {co});
+        add(p + ".conv_gated.weight", {co, co, 1, 1});
+        add(p + ".conv_gated.bias", {co});
+        add(p + ".norm.weight", {1, co, 1, 1});
+        add(p + ".norm.bias", {1, co, 1, 1});
+    };
+    for (int i = 0; i < 3; ++i) conv_block("preconvlist." + std::to_string(i), c->C0, c->C0, 5, 5);
+    for (int i = 0; i < c->L; ++i)
+        conv_block("convlist." + std::to_string(i), i == 0 ? c->C0 : g.num_channels[i - 1], g.num_channels[i], 5,
+                   g.kernel_size);
+    for (int j = 0; j < c->L; ++j) {
+        const int ci = g.num_channels[c->L - 1 - j];
+        const int co = j < c->L - 1 ? g.num_channels[c->L - 2 - j] : 2;
+        const std::string p = "deconvlist." + std::to_string(j);
+        add(p + ".conv.weight", {ci, co, 5, g.kernel_size});
+        add(p + ".conv.bias", {co});
+        add(p + ".residualmask.weight", {co, co, 1, 1});
+        add(p + ".residualmask.bias", {co});
+        add(p + ".residualnorm.weight", {1, co, 1, 1});
+        add(p + ".residualnorm.bias", {1, co, 1, 1});
+        add(p + ".residual.weight", {co, co, 1, 1});
+        add(p + ".residual.bias", {co});
+        add(p + ".norm.weight", {1, co, 1, 1});
+        add(p + ".norm.bias", {1, co, 1, 1});
+    }
+    for (int l = 0; l < g.num_layers; ++l) {
+        const std::string s = std::to_string(l);
+        add("gru.sequence_model.weight_ih_l" + s, {3 * c->H, l == 0 ? c->feat : c->H});
+        add("gru.sequence_model.weight_hh_l" + s, {3 * c->H, c->H});
+        add("gru.sequence_model.bias_ih_l" + s, {3 * c->H});
+        add("gru.sequence_model.bias_hh_l" + s, {3 * c->H});
+    }
+    add("gru.fc_output_layer.weight", {c->feat, c->H});
+    add("gru.fc_output_layer.bias", {c->feat});
+    add("gru.norm.weight", {1, 1, 1, c->feat});
+    add("gru.norm.bias", {1, 1, 1, c->feat});
+}
+
+// A packed GEMM weight: W[Npad][K] followed by bias[Npad]
+struct PackedW {
+    size_t w_off, b_off;
+    int Npad, K;
+};
+PackedW reserve_packed(se_ctx* c, int N, int K) {
+    PackedW pw;
+    pw.Npad = round_up(N, 16);
+    pw.K = K;
+    pw.w_off = c->reserve_w((size_t)pw.Npad * K);
+    pw.b_off = c->reserve_w(pw.Npad);
+    return pw;
+}
+
+void fill_gemm_common(se_ctx* c, GemmParams& g, const PackedW& pw, int N, int koff_off) {
+    g.W = nullptr;  // patched after arena allocation (offsets kept in out-of-band vectors)
+    g.K = pw.K;
+    g.N = N;
+    g.Npad = pw.Npad;
+    (void)c;
+    (void)koff_off;
+}
+
+}  // namespace
+
+// The program builder keeps arena offsets until the arenas exist; these two vectors remember, per op, where its
+// packed weights / koff table start.
+struct OpFix {
+    size_t w_off, b_off;
+    int k_off;
+    size_t nw_off, nb_off, nwr_off, nbr_off;  // norm affine offsets (SIZE_MAX = unused)
+};
+
+namespace {
+
+constexpr size_t NONE = (size_t)-1;
+
+struct Builder {
+    se_ctx* c;
+    std::vector<OpFix> fix;
+
+    // identity koff for a dense K-contiguous operand
+    int koff_dense(int K) {
+        std::vector<int> v(K / 4);
+        for (int u = 0; u < K / 4; ++u) v[u] = 4 * u;
+        return c->reserve_k(v);
+    }
+
+    void push_gemm(int stage, GemmParams g, int rows_per_stream, const PackedW& pw, int k_off) {
+        Op op{};
+        op.kind = OP_GEMM;
+        op.stage = stage;
+        op.g = g;
+        op.rows_per_stream = rows_per_stream;
+        c->ops.push_back(op);
+        fix.push_back({pw.w_off, pw.b_off, k_off, NONE, NONE, NONE, NONE});
+    }
+    void push_norm(int stage, NormApplyParams n, size_t w_off, size_t b_off, size_t wr_off = NONE,
+                   size_t br_off = NONE) {
+        Op op{};
+        op.kind = OP_NORM;
+        op.stage = stage;
+        op.n = n;
+        c->ops.push_back(op);
+        fix.push_back({NONE, NONE, -1, w_off, b_off, wr_off, br_off});
+    }
+    void push_gru_pw(const float* gi, long long giB, const float* gh, const float* hprev, long long hB, float* hout,
+                     int H) {
+        Op op{};
+        op.kind = OP_GRU_PW;
+        op.stage = ST_GRU;
+        op.gi = gi;
+        op.giB = giB;
+        op.gh = gh;
+        op.hprev = hprev;
+        op.hB = hB;
+        op.hout = hout;
+        op.H = H;
+        c->ops.push_back(op);
+        fix.push_back({NONE, NONE, -1, NONE, NONE, NONE, NONE});
+    }
+
+    // per-channel affine [Cp] (zero beyond the real channels) -> arena
+    size_t pack_affine(const std::string& key, int Creal, int Cp) {
+        const size_t off = c->reserve_w(Cp);
+        c->packers.push_back([=](const HostParams& hp, float* arena) {
+            const std::vector<float>& v = hp.at(key);
+            for (int i = 0; i < Cp; ++i) arena[off + i] = i < Creal ? v[i] : 0.f;
+        });
+        return off;
+    }
+
+    // ---- causal gated conv block (CRN_ELU.py:230-247) ---------------------------------------------------------
+    // in: padded input; dst/dstB..: where the normalised output goes; residual: add the block input (preconv)
+    void conv_block(int stage, const std::string& name, const Act& in, int Cin_real, int Cout_real, int KF, int KT,
+                    int strideF, int dilF, int dilT, int Fo, float* dst, long long dB, long long dT, long long dF,
+                    bool residual, int stats_slot) {
+        const int Cp_in = in.C;
+        const int Cp_out = round_up(Cout_real, 4);
+        const int rows = T * Fo;
+        // (1) conv + ELU -> tmp_e [B][T][Fo][Cp_out]
+        {
+            const int K = KT * KF * Cp_in;
+            std::vector<int> koff(K / 4);
+            for (int kt = 0; kt < KT; ++kt)
+                for (int kf = 0; kf < KF; ++kf)
+                    for (int c4 = 0; c4 < Cp_in / 4; ++c4)
+                        koff[((kt * KF + kf) * Cp_in) / 4 + c4] =
+                            (int)(kt * dilT * in.sT + kf * dilF * in.sF + 4 * c4);
+            const int k_off = c->reserve_k(koff);
+            PackedW pw = reserve_packed(c, Cout_real, K);
+            c->packers.push_back([=](const HostParams& hp, float* arena) {
+                const std::vector<float>& w = hp.at(name + ".conv.weight");  // [Co][Ci][KF][KT]
+                const std::vector<float>& b = hp.at(name + ".conv.bias");
+                for (int n = 0; n < Cout_real; ++n) {
+                    for (int kt = 0; kt < KT; ++kt)
+                        for (int kf = 0; kf < KF; ++kf)
+                            for (int ci = 0; ci < Cin_real; ++ci)
+                                arena[pw.w_off + (size_t)n * K + (kt * KF + kf) * Cp_in + ci] =
+                                    w[((n * Cin_real + ci) * KF + kf) * KT + kt];
+                    arena[pw.b_off + n] = b[n];
+                }
+            });
+            GemmParams g{};
+            g.A = in.base;
+            g.sB = in.sB;
+            g.sT = in.sT;
+            g.sF = (long long)strideF * in.sF;
+            g.Tn = T;
+            g.Fo = Fo;
+            fill_gemm_common(c, g, pw, Cout_real, k_off);
+            g.epi = EPI_ELU;
+            g.out = c->tmp_e;
+            g.oB = (long long)rows * Cp_out;
+            g.oT = (long long)Fo * Cp_out;
+            g.oF = Cp_out;
+            push_gemm(stage, g, rows, pw, k_off);
+        }
+        // (2) gated 1x1 pair + statistics -> tmp_y [B][T][Fo][Cp_out]
+        {
+            const int K = Cp_out;
+            const int k_off = koff_dense(K);
+            PackedW pw = reserve_packed(c, 2 * Cout_real, K);
+            c->packers.push_back([=](const HostParams& hp, float* arena) {
+                const std::vector<float>& wt = hp.at(name + ".conv_trans.weight");
+                const std::vector<float>& bt = hp.at(name + ".conv_trans.bias");
+                const std::vector<float>& wg = hp.at(name + ".conv_gated.weight");
+                const std::vector<float>& bg = hp.at(name + ".conv_gated.bias");
+                for (int co = 0; co < Cout_real; ++co) {
+                    for (int ci = 0; ci < Cout_real; ++ci) {
+                        arena[pw.w_off + (size_t)(2 * co) * K + ci] = wt[co * Cout_real + ci];
+                        arena[pw.w_off + (size_t)(2 * co + 1) * K + ci] = wg[co * Cout_real + ci];
+                    }
+                    arena[pw.b_off + 2 * co] = bt[co];
+                    arena[pw.b_off + 2 * co + 1] = bg[co];
+                }
+            });
+            GemmParams g{};
+            g.A = c->tmp_e;
+            g.sB = (long long)rows * Cp_out;
+            g.sT = (long long)Fo * Cp_out;
+            g.sF = Cp_out;
+            g.Tn = T;
+            g.Fo = Fo;
+            fill_gemm_common(c, g, pw, 2 * Cout_real, k_off);
+            g.epi = EPI_GATE_STATS;
+            g.out = c->tmp_y;
+            g.oB = g.sB;
+            g.oT = g.sT;
+            g.oF = g.sF;
+            g.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
+            push_gemm(stage, g, rows, pw, k_off);
+        }
+        // (3) GlobalLayerNorm (+ residual) -> destination
+        {
+            NormApplyParams n{};
+            n.mode = residual ? 1 : 0;
+            n.T = T;
+            n.F = Fo;
+            n.C = Cp_out;
+            n.student = c->student;
+            n.y = c->tmp_y;
+            n.Fy = Fo;
+            n.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
+            n.count = (double)Cout_real * Fo * T;
+            n.per_feature = 0;
+            if (residual) {
+                n.res = in.interior();
+                n.rB = in.sB;
+                n.rT = in.sT;
+                n.rF = in.sF;
+            }
+            n.out = dst;
+            n.oB = dB;
+            n.oT = dT;
+            n.oF = dF;
+            const size_t w_off = pack_affine(name + ".norm.weight", Cout_real, Cp_out);
+            const size_t b_off = pack_affine(name + ".norm.bias", Cout_real, Cp_out);
+            push_norm(stage, n, w_off, b_off);
+        }
+    }
+
+    // ---- transposed conv block (CRN_ELU.py:290-307) ---------------------------------------------------------
+    // in: [T + 2d][Fin + 2][Cin]; skip: padded encoder-input buffer whose interior is the skip tensor (or null)
+    void deconv_block(const std::string& name, const Act& in, int Cin, int Cout_real, int KT, int d, const Act* skip,
+                      float* dst, long long dB, long long dT, long long dF, int stats_slot, int stats_slot_r) {
+        const int Fin = in.F;
+        const int Fy = 2 * Fin - 1;
+        const int Cop = Cout_real < 4 ? Cout_real : round_up(Cout_real, 4);  // last layer keeps 2 (float2 consumer)
+        float* y = skip ? c->tmp_y : c->ylast;
+        for (int parity = 0; parity < 2; ++parity) {
+            const int nkf = parity == 0 ? 3 : 2;
+            const int Fo = parity == 0 ? Fin : Fin - 1;
+            const int K = KT * nkf * Cin;
+            std::vector<int> koff(K / 4);
+            for (int kt = 0; kt < KT; ++kt)
+                for (int j = 0; j < nkf; ++j)
+                    for (int c4 = 0; c4 < Cin / 4; ++c4) {
+                        // even rows (phi = 2f'): taps kf = 2j -> padded input row f' + 2 - j
+                        // odd rows (phi = 2f'+1): taps kf = 2j+1 -> padded input row f' + 2 - j
+                        const long long frame = (long long)(KT - 1 - kt) * d;
+                        koff[((kt * nkf + j) * Cin) / 4 + c4] = (int)(frame * in.sT + (2 - j) * in.sF + 4 * c4);
+                    }
+            const int k_off = c->reserve_k(koff);
+            PackedW pw = reserve_packed(c, Cout_real, K);
+            const int KF = 5;
+            c->packers.push_back([=](const HostParams& hp, float* arena) {
+                const std::vector<float>& w = hp.at(name + ".conv.weight");  // [Ci][Co][KF][KT]
+                const std::vector<float>& b = hp.at(name + ".conv.bias");
+                for (int n = 0; n < Cout_real; ++n) {
+                    for (int kt = 0; kt < KT; ++kt)
+                        for (int j = 0; j < nkf; ++j) {
+                            const int kf = 2 * j + parity;
+                            for (int ci = 0; ci < Cin; ++ci)
+                                arena[pw.w_off + (size_t)n * K + (kt * nkf + j) * Cin + ci] =
+                                    w[((ci * Cout_real + n) * KF + kf) * KT + kt];
+                        }
+                    arena[pw.b_off + n] = b[n];
+                }
+            });
+            GemmParams g{};
+            g.A = in.base;  // padded row 0, frame 0
+            g.sB = in.sB;
+            g.sT = in.sT;
+            g.sF = in.sF;
+            g.Tn = T;
+            g.Fo = Fo;
+            fill_gemm_common(c, g, pw, Cout_real, k_off);
+            g.epi = EPI_ELU_STATS;
+            g.out = y + (parity ? Cop : 0);
+            g.oB = (long long)T * Fy * Cop;
+            g.oT = (long long)Fy * Cop;
+            g.oF = 2 * Cop;
+            g.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
+            push_gemm(ST_DECODER, g, T * Fo, pw, k_off);
+        }
+        if (!skip) return;
+        const int Fs = skip->F;
+        const int rows = T * Fs;
+        {  // residual mask / residual 1x1 pair on the skip tensor
+            const int K = skip->C;
+            const int k_off = koff_dense(K);
+            PackedW pw = reserve_packed(c, 2 * Cout_real, K);
+            c->packers.push_back([=](const HostParams& hp, float* arena) {
+                const std::vector<float>& wm = hp.at(name + ".residualmask.weight");
+                const std::vector<float>& bm = hp.at(name + ".residualmask.bias");
+                const std::vector<float>& wr = hp.at(name + ".residual.weight");
+                const std::vector<float>& br = hp.at(name + ".residual.bias");
+                for (int co = 0; co < Cout_real; ++co) {
+                    for (int ci = 0; ci < Cout_real; ++ci) {
+                        arena[pw.w_off + (size_t)(2 * co) * K + ci] = wm[co * Cout_real + ci];
+                        arena[pw.w_off + (size_t)(2 * co + 1) * K + ci] = wr[co * Cout_real + ci];
+                    }
+                    arena[pw.b_off + 2 * co] = bm[co];
+                    arena[pw.b_off + 2 * co + 1] = br[co];
+                }
+            });
+            GemmParams g{};
+            g.A = skip->interior();
+            g.sB = skip->sB;
+            g.sT = skip->sT;
+            g.sF = skip->sF;
+            g.Tn = T;
+            g.Fo = Fs;
+            fill_gemm_common(c, g, pw, 2 * Cout_real, k_off);
+            g.epi = EPI_SKIP;
+            g.out = c->tmp_rm;
+            g.oB = (long long)rows * Cop;
+            g.oT = (long long)Fs * Cop;
+            g.oF = Cop;
+            g.out2 = c->tmp_rr;
+            g.o2B = g.oB;
+            g.o2T = g.oT;
+            g.o2F = g.oF;
+            g.stats = c->stats + (size_t)stats_slot_r * 2 * c->maxB;
+            push_gemm(ST_DECODER, g, rows, pw, k_off);
+        }
+        {
+            NormApplyParams n{};
+            n.mode = 2;
+            n.T = T;
+            n.F = Fs;
+            n.C = Cop;
+            n.student = c->student;
+            n.y = y;
+            n.Fy = Fy;
+            n.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
+            n.count = (double)Cout_real * Fy * T;
+            n.rm = c->tmp_rm;
+            n.rr = c->tmp_rr;
+            n.stats_r = c->stats + (size_t)stats_slot_r * 2 * c->maxB;
+            n.count_r = (double)Cout_real * Fs * T;
+            n.out = dst;
+            n.oB = dB;
+            n.oT = dT;
+            n.oF = dF;
+            const size_t w_off = pack_affine(name + ".norm.weight", Cout_real, Cop);
+            const size_t b_off = pack_affine(name + ".norm.bias", Cout_real, Cop);
+            const size_t wr_off = pack_affine(name + ".residualnorm.weight", Cout_real, Cop);
+            const size_t br_off = pack_affine(name + ".residualnorm.bias", Cout_real, Cop);
+            push_norm(ST_DECODER, n, w_off, b_off, wr_off, br_off);
+        }
+    }
+};
+
+int build_ctx(se_ctx* c) {
+    const se_crn_config& g = c->cfg;
+    SE_REQUIRE(g.num_inputs == 3, "num_inputs must be 3 (features of CRN_ELU.py:369-373 are built for 3 microphones)");
+    SE_REQUIRE(g.num_freqs == NBIN && g.n_fft == 400 && g.win_length == 400 && g.hop_length == 160,
+               "STFT kernel is built for n_fft=win=400, hop=160, 201 bins (config.yaml:214-217)");
+    SE_REQUIRE(g.segment_length == KCHUNK, "segment_length must be 3200 (config.yaml:209)");
+    SE_REQUIRE(g.num_levels >= 2 && g.num_levels <= 4, "num_levels must be 2..4 (state pad 2*2^i must stay < 21 frames)");
+    SE_REQUIRE(g.kernel_size == 3, "kernel_size must be 3 (config.yaml:211)");
+    SE_REQUIRE(g.num_layers == 2, "num_layers must be 2 (config.yaml:210)");
+    SE_REQUIRE(g.hidden % 16 == 0 && g.hidden > 0, "hidden must be a positive multiple of 16");
+    SE_REQUIRE(g.max_streams > 0, "max_streams must be positive");
+    SE_REQUIRE(g.precision == SE_PRECISION_FP32 || g.precision == SE_PRECISION_TF32, "unknown precision");
+    SE_REQUIRE(g.variant == SE_VARIANT_CRN_ELU || g.variant == SE_VARIANT_DISTILLED, "unknown variant");
+    c->maxB = g.max_streams;
+    c->L = g.num_levels;
+    c->C0 = 2 * g.num_inputs - 1;
+    c->student = g.variant == SE_VARIANT_DISTILLED;
+    c->H = g.hidden;
+    for (int i = 0; i < c->L; ++i)
+        SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
+    int F = NBIN;
+    for (int i = 0; i < c->L; ++i) {
+        F = (F - 1) / 2 + 1;
+        c->encF.push_back(F);
+    }
+    c->Fg = F;
+    c->Cg = g.num_channels[c->L - 1];
+    c->feat = c->Fg * c->Cg;
+    SE_REQUIRE(c->Fg == NBIN / (1 << c->L) + 1, "frequency pyramid does not match CRN_ELU.py:364");
+    register_params(c);
+
+    const int maxB = c->maxB;
+    const int C0p = 8;
+    const int H = c->H;
+    // ---- activations ------------------------------------------------------------------------------------------
+    c->pre_in.resize(3);
+    for (int i = 0; i < 3; ++i) {
+        const int d = 1 << i;
+        if (make_act(c, c->pre_in[i], C0p, NBIN, T, 4, 0, 2 * d, 2 * d)) return 1;
+    }
+    c->enc_in.resize(c->L);
+    for (int i = 0; i < c->L; ++i) {
+        const int Cin = i == 0 ? C0p : g.num_channels[i - 1];
+        const int Fin = i == 0 ? NBIN : c->encF[i - 1];
+        if (make_act(c, c->enc_in[i], Cin, Fin, T, 2 * (1 << i), 0, 2, 2)) return 1;
+    }
+    c->dec_in.resize(c->L);
+    for (int j = 0; j < c->L; ++j) {
+        const int Cin = g.num_channels[c->L - 1 - j];
+        const int Fin = j == 0 ? c->Fg : c->encF[c->L - 1 - j];
+        const int d = 1 << j;
+        if (make_act(c, c->dec_in[j], Cin, Fin, T, 0, 2 * d, 1, 1)) return 1;
+    }
+    size_t tmp = 0;
+    auto upd = [&](size_t v) { tmp = v > tmp ? v : tmp; };
+    upd((size_t)T * NBIN * C0p);
+    for (int i = 0; i < c->L; ++i) upd((size_t)T * c->encF[i] * g.num_channels[i]);
+    for (int j = 0; j + 1 < c->L; ++j) {
+        const int Fin = c->dec_in[j].F;
+        const int Co = g.num_channels[c->L - 2 - j];
+        upd((size_t)T * (2 * Fin) * Co);
+    }
+    if (dev_alloc(c, &c->tmp_e, tmp * maxB)) return 1;
+    if (dev_alloc(c, &c->tmp_y, tmp * maxB)) return 1;
+    if (dev_alloc(c, &c->tmp_rm, tmp * maxB)) return 1;
+    if (dev_alloc(c, &c->tmp_rr, tmp * maxB)) return 1;
+    if (dev_alloc(c, &c->xg, (size_t)T * c->feat * maxB)) return 1;
+    if (dev_alloc(c, &c->fcraw, (size_t)T * c->feat * maxB)) return 1;
+    if (dev_alloc(c, &c->gi, (size_t)T * 3 * H * maxB)) return 1;
+    if (dev_alloc(c, &c->gh, (size_t)3 * H * maxB)) return 1;
+    for (int l = 0; l < 2; ++l)
+        if (dev_alloc(c, &c->hseq[l], (size_t)(T + 1) * H * maxB)) return 1;
+    if (dev_alloc(c, &c->noisy, (size_t)T * NBIN * 2 * maxB)) return 1;
+    if (dev_alloc(c, &c->ylast, (size_t)T * NBIN * 2 * maxB)) return 1;
+    if (dev_alloc(c, &c->carry, (size_t)PHOP * maxB)) return 1;
+    c->n_stats = 3 + c->L + 1 + 2 * c->L;
+    if (dev_alloc(c, &c->stats, (size_t)c->n_stats * 2 * maxB)) return 1;
+    if (dev_alloc(c, &c->io_dev, 1)) return 1;
+
+    // ---- program ----------------------------------------------------------------------------------------------
+    Builder b{c, {}};
+    int slot = 0;
+    for (int i = 0; i < 3; ++i) {
+        const Act& in = c->pre_in[i];
+        const Act& nx = i < 2 ? c->pre_in[i + 1] : c->enc_in[0];
+        b.conv_block(ST_PRECONV, "preconvlist." + std::to_string(i), in, c->C0, c->C0, 5, 5, 1, 1 << i, 1, NBIN,
+                     nx.interior(), nx.sB, nx.sT, nx.sF, true, slot++);
+    }
+    for (int i = 0; i < c->L; ++i) {
+        const Act& in = c->enc_in[i];
+        const int Cin_real = i == 0 ? c->C0 : g.num_channels[i - 1];
+        float* dst;
+        long long dB, dT, dF;
+        if (i + 1 < c->L) {
+            const Act& nx = c->enc_in[i + 1];
+            dst = nx.interior();
+            dB = nx.sB;
+            dT = nx.sT;
+            dF = nx.sF;
+        } else {
+            dst = c->xg;
+            dB = (long long)T * c->feat;
+            dT = c->feat;
+            dF = c->Cg;
+        }
+        b.conv_block(ST_ENCODER, "convlist." + std::to_string(i), in, Cin_real, g.num_channels[i], 5, 3, 2, 1, 1 << i,
+                     c->encF[i], dst, dB, dT, dF, false, slot++);
+    }
+    // ---- GRU + Linear + ELU + GLN(last) (CRN_ELU.py:160-186) --------------------------------------------------
+    // feature index: reference c*Fg + f  ->  ours f*Cg + c (channels-last)
+    const int Fg = c->Fg, Cg = c->Cg, feat = c->feat;
+    auto perm = [=](int ours) { return (ours % Cg) * Fg + ours / Cg; };
+    const int gru_slot = slot++;
+    for (int l = 0; l < 2; ++l) {
+        const int Kin = l == 0 ? feat : H;
+        const std::string s = std::to_string(l);
+        {  // input projection for all T frames at once
+            const int k_off = b.koff_dense(Kin);
+            PackedW pw = reserve_packed(c, 3 * H, Kin);
+            c->packers.push_back([=](const HostParams& hp, float* arena) {
+                const std::vector<float>& w = hp.at("gru.sequence_model.weight_ih_l" + s);
+                const std::vector<float>& bi = hp.at("gru.sequence_model.bias_ih_l" + s);
+                for (int n = 0; n < 3 * H; ++n) {
+                    for (int k = 0; k < Kin; ++k)
+                        arena[pw.w_off + (size_t)n * Kin + k] = w[(size_t)n * Kin + (l == 0 ? perm(k) : k)];
+                    arena[pw.b_off + n] = bi[n];
+                }
+            });
+            GemmParams gp{};
+            if (l == 0) {
+                gp.A = c->xg;
+                gp.sB = (long long)T * feat;
+                gp.sT = feat;
+            } else {
+                gp.A = c->hseq[0] + H;
+                gp.sB = (long long)(T + 1) * H;
+                gp.sT = H;
+            }
+            gp.sF = 0;
+            gp.Tn = T;
+            gp.Fo = 1;
+            fill_gemm_common(c, gp, pw, 3 * H, k_off);
+            gp.epi = EPI_BIAS;
+            gp.out = c->gi;
+            gp.oB = (long long)T * 3 * H;
+            gp.oT = 3 * H;
+            gp.oF = 0;
+            b.push_gemm(ST_GRU, gp, T, pw, k_off);
+        }
+        const int k_off = b.koff_dense(H);
+        PackedW pw = reserve_packed(c, 3 * H, H);
+        c->packers.push_back([=](const HostParams& hp, float* arena) {
+            const std::vector<float>& w = hp.at("gru.sequence_model.weight_hh_l" + s);
+            const std::vector<float>& bh = hp.at("gru.sequence_model.bias_hh_l" + s);
+            for (int n = 0; n < 3 * H; ++n) {
+                for (int k = 0; k < H; ++k) arena[pw.w_off + (size_t)n * H + k] = w[(size_t)n * H + k];
+                arena[pw.b_off + n] = bh[n];
+            }
+        });
+        for (int t = 0; t < T; ++t) {
+            GemmParams gp{};
+            gp.A = c->hseq[l] + (long long)t * H;
+            gp.sB = (long long)(T + 1) * H;
+            gp.sT = 0;
+            gp.sF = 0;
+            gp.Tn = 1;
+            gp.Fo = 1;
+            fill_gemm_common(c, gp, pw, 3 * H, k_off);
+            gp.epi = EPI_BIAS;
+            gp.out = c->gh;
+            gp.oB = 3 * H;
+            gp.oT = 0;
+            gp.oF = 0;
+            b.push_gemm(ST_GRU, gp, 1, pw, k_off);
+            b.push_gru_pw(c->gi + (long long)t * 3 * H, (long long)T * 3 * H, c->gh, c->hseq[l] + (long long)t * H,
+                          (long long)(T + 1) * H, c->hseq[l] + (long long)(t + 1) * H, H);
+        }
+    }
+    {  // fc + ELU + stats, then per-feature GLN into the first decoder input
+        const int k_off = b.koff_dense(H);
+        PackedW pw = reserve_packed(c, feat, H);
+        c->packers.push_back([=](const HostParams& hp, float* arena) {
+            const std::vector<float>& w = hp.at("gru.fc_output_layer.weight");
+            const std::vector<float>& bb = hp.at("gru.fc_output_layer.bias");
+            for (int n = 0; n < feat; ++n) {
+                const int r = perm(n);
+                for (int k = 0; k < H; ++k) arena[pw.w_off + (size_t)n * H + k] = w[(size_t)r * H + k];
+                arena[pw.b_off + n] = bb[r];
+            }
+        });
+        GemmParams gp{};
+        gp.A = c->hseq[1] + H;
+        gp.sB = (long long)(T + 1) * H;
+        gp.sT = H;
+        gp.sF = 0;
+        gp.Tn = T;
+        gp.Fo = 1;
+        fill_gemm_common(c, gp, pw, feat, k_off);
+        gp.epi = EPI_ELU_STATS;
+        gp.out = c->fcraw;
+        gp.oB = (long long)T * feat;
+        gp.oT = feat;
+        gp.oF = 0;
+        gp.stats = c->stats + (size_t)gru_slot * 2 * maxB;
+        b.push_gemm(ST_GRU, gp, T, pw, k_off);
+
+        const Act& nx = c->dec_in[0];
+        NormApplyParams n{};
+        n.mode = 0;
+        n.T = T;
+        n.F = Fg;
+        n.C = Cg;
+        n.student = c->student;
+        n.y = c->fcraw;
+        n.Fy = Fg;
+        n.stats = gp.stats;
+        n.count = (double)feat * T;
+        n.per_feature = 1;
+        n.out = nx.interior();
+        n.oB = nx.sB;
+        n.oT = nx.sT;
+        n.oF = nx.sF;
+        const size_t w_off = c->reserve_w(feat), b_off = c->reserve_w(feat);
+        c->packers.push_back([=](const HostParams& hp, float* arena) {
+            const std::vector<float>& w = hp.at("gru.norm.weight");
+            const std::vector<float>& bb = hp.at("gru.norm.bias");
+            for (int n2 = 0; n2 < feat; ++n2) {
+                arena[w_off + n2] = w[perm(n2)];
+                arena[b_off + n2] = bb[perm(n2)];
+            }
+        });
+        b.push_norm(ST_GRU, n, w_off, b_off);
+    }
+    // ---- decoder ----------------------------------------------------------------------------------------------
+    size_t wl_off = NONE, bl_off = NONE;
+    for (int j = 0; j < c->L; ++j) {
+        const Act& in = c->dec_in[j];
+        const int Cin = g.num_channels[c->L - 1 - j];
+        const std::string name = "deconvlist." + std::to_string(j);
+        if (j + 1 < c->L) {
+            const int Co = g.num_channels[c->L - 2 - j];
+            const Act* skip = &c->enc_in[c->L - 1 - j];  // interior = output of encoder level L-2-j
+            const Act& nx = c->dec_in[j + 1];
+            const int s0 = slot++, s1 = slot++;
+            b.deconv_block(name, in, Cin, Co, 3, 1 << j, skip, nx.interior(), nx.sB, nx.sT, nx.sF, s0, s1);
+        } else {
+            c->stats_last = slot++;
+            b.deconv_block(name, in, Cin, 2, 3, 1 << j, nullptr, nullptr, 0, 0, 0, c->stats_last, -1);
+            wl_off = b.pack_affine(name + ".norm.weight", 2, 4);
+            bl_off = b.pack_affine(name + ".norm.bias", 2, 4);
+        }
+    }
+    SE_REQUIRE(slot <= c->n_stats, "internal: statistics slots");
+
+    // ---- arenas -------------------------------------------------------------------------------------------------
+    if (dev_alloc(c, &c->warena, c->warena_floats)) return 1;
+    if (dev_alloc(c, &c->karena, c->khost.size())) return 1;
+    SE_CUDA_OK(cudaMemcpy(c->karena, c->khost.data(), c->khost.size() * sizeof(int), cudaMemcpyHostToDevice));
+    for (size_t i = 0; i < c->ops.size(); ++i) {
+        Op& op = c->ops[i];
+        const OpFix& f = b.fix[i];
+        if (op.kind == OP_GEMM) {
+            op.g.W = c->warena + f.w_off;
+            op.g.bias = c->warena + f.b_off;
+            op.g.koff = c->karena + f.k_off;
+        } else if (op.kind == OP_NORM) {
+            op.n.w = c->warena + f.nw_off;
+            op.n.b = c->warena + f.nb_off;
+            if (f.nwr_off != NONE) {
+                op.n.wr = c->warena + f.nwr_off;
+                op.n.br = c->warena + f.nbr_off;
+            }
+        }
+    }
+    c->w_last = c->warena + wl_off;
+    c->b_last = c->warena + bl_off;
+
+    // ---- state tables -------------------------------------------------------------------------------------------
+    auto add_state = [&](float* base, long long sB, long long src, int count) {
+        RollEntry e{base, sB, src, 0, count};
+        c->roll.e[c->roll.n++] = e;
+        c->zero_tab.e[c->zero_tab.n++] = e;
+    };
+    for (const Act& a : c->pre_in) add_state(a.base, a.sB, (long long)T * a.sT, (int)(a.padT0 * a.sT));
+    for (const Act& a : c->enc_in) add_state(a.base, a.sB, (long long)T * a.sT, (int)(a.padT0 * a.sT));
+    for (int l = 0; l < 2; ++l) add_state(c->hseq[l], (long long)(T + 1) * H, (long long)T * H, H);
+    {
+        RollEntry e{c->carry, PHOP, 0, 0, PHOP};
+        c->zero_tab.e[c->zero_tab.n++] = e;
+    }
+    if (init_fft_tables()) return 1;
+    return 0;
+}
+
+int launch_op(const Op& op, int B, cudaStream_t st) {
+    switch (op.kind) {
+        case OP_GEMM: {
+            GemmParams g = op.g;
+            g.M = B * op.rows_per_stream;
+            return launch_gemm_fp32(g, st);
+        }
+        case OP_NORM: {
+            NormApplyParams n = op.n;
+            n.B = B;
+            return launch_norm_apply(n, st);
+        }
+        case OP_GRU_PW:
+            return launch_gru_pointwise(op.gi, op.giB, op.gh, op.hprev, op.hB, op.hout, B, op.H, st);
+    }
+    return 0;
+}
+
+// stage_filter < 0: everything
+int enqueue_net(se_ctx* c, int B, cudaStream_t st, int stage_filter) {
+    for (const Op& op : c->ops) {
+        if (stage_filter >= 0 && op.stage != stage_filter) continue;
+        if (launch_op(op, B, st)) return 1;
+    }
+    return 0;
+}
+
+int enqueue_stream_step(se_ctx* c, int B, cudaStream_t st, int stage_filter = -1) {
+    auto want = [&](int s) { return stage_filter < 0 || stage_filter == s; };
+    if (want(ST_STFT)) {
+        SE_CUDA_OK(cudaMemsetAsync(c->stats, 0, (size_t)c->n_stats * 2 * c->maxB * sizeof(double), st));
+        StftParams sp{};
+        sp.io = c->io_dev;
+        sp.B = B;
+        sp.M = 3;
+        sp.student = c->student;
+        const Act& a = c->pre_in[0];
+        sp.feat = a.interior();
+        sp.fB = a.sB;
+        sp.fT = a.sT;
+        sp.fF = a.sF;
+        sp.noisy = c->noisy;
+        if (launch_stft_features(sp, st)) return 1;
+    }
+    if (enqueue_net(c, B, st, stage_filter)) return 1;
+    if (want(ST_MASK)) {
+        MaskIstftParams mp{};
+        mp.io = c->io_dev;
+        mp.B = B;
+        mp.student = c->student;
+        mp.y = c->ylast;
+        mp.stats = c->stats + (size_t)c->stats_last * 2 * c->maxB;
+        mp.count = 2.0 * NBIN * T;
+        mp.w = c->w_last;
+        mp.b = c->b_last;
+        mp.noisy = c->noisy;
+        mp.carry = c->carry;
+        if (launch_mask_istft(mp, st)) return 1;
+    }
+    if (want(ST_ROLL)) {
+        if (launch_roll(c->roll, 0, B, st)) return 1;
+    }
+    return 0;
+}
+
+int count_launches(const se_ctx* c) {
+    // memset + stft + ops + mask + roll
+    return 1 + 1 + (int)c->ops.size() + 1 + 1;
+}
+
+int run_stream_step(se_ctx* c, const IoDesc& io, int B, cudaStream_t st) {
+    if (launch_set_io(c->io_dev, io, st)) return 1;
+    if (!c->use_graph) return enqueue_stream_step(c, B, st);
+    auto it = c->graphs.find(B);
+    if (it == c->graphs.end()) {
+        // capture on a private stream so that the caller's stream is not put into capture mode
+        if (!c->own_stream) SE_CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        SE_CUDA_OK(cudaStreamBeginCapture(c->own_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue_stream_step(c, B, c->own_stream);
+        cudaError_t e = cudaStreamEndCapture(c->own_stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return 1;
+        }
+        SE_CUDA_OK(e);
+        cudaGraphExec_t exec = nullptr;
+        SE_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+        SE_CUDA_OK(cudaGraphDestroy(graph));
+        it = c->graphs.emplace(B, exec).first;
+    }
+    SE_CUDA_OK(cudaGraphLaunch(it->second, st));
+    return 0;
+}
+
+int check_ready(se_ctx* c, int B) {
+    SE_REQUIRE(c != nullptr, "null context");
+    SE_REQUIRE(c->weights_bound, "se_crn_bind_weights has not been called");
+    SE_REQUIRE(B >= 0 && B <= c->maxB, "B exceeds max_streams of the context");
+    SE_CUDA_OK(cudaSetDevice(c->device));
+    return 0;
+}
+
+}  // namespace
+
+// ======================================================================================================================
+// C-ABI
+// ======================================================================================================================
+extern "C" {
+
+const char* se_last_error(void) { return g_err.c_str(); }
+const char* se_version(void) { return "se_b200 0.1 sm_100a"; }
+
+int se_ctx_create(se_ctx** out, int device, const se_crn_config* cfg) {
+    if (!out || !cfg) {
+        set_error("se_ctx_create: null argument");
+        return 2;
+    }
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        set_error("se_ctx_create: no CUDA device (this library has no CPU fallback)");
+        return 3;
+    }
+    SE_REQUIRE(device >= 0 && device < n, "se_ctx_create: bad device index");
+    SE_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SE_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    SE_REQUIRE(prop.major == 10, "se_ctx_create: kernels are built for sm_100a (Blackwell B200) only");
+    se_ctx* c = new se_ctx();
+    c->cfg = *cfg;
+    c->device = device;
+    if (build_ctx(c)) {
+        se_ctx_destroy(c);
+        return 1;
+    }
+    *out = c;
+    return 0;
+}
+
+int se_ctx_destroy(se_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->h_in) cudaFree(c->h_in);
+    if (c->h_out) cudaFree(c->h_out);
+    delete c;
+    return 0;
+}
+
+int se_crn_num_params(const se_ctx* c) { return c ? (int)c->params.size() : 0; }
+const char* se_crn_param_name(const se_ctx* c, int i) {
+    return (c && i >= 0 && i < (int)c->params.size()) ? c->params[i].name.c_str() : nullptr;
+}
+int64_t se_crn_param_numel(const se_ctx* c, int i) {
+    return (c && i >= 0 && i < (int)c->params.size()) ? c->params[i].numel() : -1;
+}
+
+int se_crn_bind_weights(se_ctx* c, const float* const* ptrs, int n, void* stream) {
+    SE_REQUIRE(c != nullptr && ptrs != nullptr, "se_crn_bind_weights: null argument");
+    SE_REQUIRE(n == (int)c->params.size(), "se_crn_bind_weights: wrong number of tensors");
+    SE_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_OK(cudaStreamSynchronize(st));
+    HostParams hp;
+    for (int i = 0; i < n; ++i) {
+        SE_REQUIRE(ptrs[i] != nullptr, "se_crn_bind_weights: null tensor " + c->params[i].name);
+        std::vector<float> v((size_t)c->params[i].numel());
+        SE_CUDA_OK(cudaMemcpy(v.data(), ptrs[i], v.size() * sizeof(float), cudaMemcpyDefault));
+        hp.emplace(c->params[i].name, std::move(v));
+    }
+    std::vector<float> arena(c->warena_floats, 0.f);
+    for (const PackFn& f : c->packers) f(hp, arena.data());
+    SE_CUDA_OK(cudaDeviceSynchronize());  // no step may still read the old weights
+    SE_CUDA_OK(cudaMemcpy(c->warena, arena.data(), arena.size() * sizeof(float), cudaMemcpyHostToDevice));
+    c->weights_bound = true;
+    return 0;
+}
+
+int se_crn_state_reset(se_ctx* c, int first, int count, void* stream) {
+    SE_REQUIRE(c != nullptr, "null context");
+    SE_REQUIRE(first >= 0 && count >= 0 && first + count <= c->maxB, "se_crn_state_reset: stream range");
+    SE_CUDA_OK(cudaSetDevice(c->device));
+    return launch_zero(c->zero_tab, first, count, (cudaStream_t)stream);
+}
+
+int64_t se_crn_state_bytes_per_stream(const se_ctx* c) {
+    if (!c) return -1;
+    int64_t n = 0;
+    for (int i = 0; i < c->zero_tab.n; ++i) n += c->zero_tab.e[i].count;
+    return n * 4;
+}
+
+int se_crn_process_chunk(se_ctx* c, const float* in, int64_t in_stream_stride, int64_t in_mic_stride, float* out,
+                         int64_t out_stream_stride, int B, void* stream) {
+    if (check_ready(c, B)) return 1;
+    SE_REQUIRE(in != nullptr && out != nullptr, "se_crn_process_chunk: null buffer");
+    if (B == 0) return 0;
+    IoDesc io{in, in_stream_stride, in_mic_stride, 0, KCHUNK, out, out_stream_stride, PHOP};
+    return run_stream_step(c, io, B, (cudaStream_t)stream);
+}
+
+int se_chunk_grid(int64_t L, int K, int* gap, int* n_chunks) {
+    SE_REQUIRE(L >= 0 && K > 0 && K % 2 == 0, "se_chunk_grid: bad arguments");
+    const int P = K / 2;
+    const int g = K - (int)((P + L % K) % K);  // utility.py:325
+    if (gap) *gap = g;
+    if (n_chunks) *n_chunks = (int)(2 * (L + g + P) / K);  // utility.py:357-368
+    return 0;
+}
+
+int se_crn_realtime_process(se_ctx* c, const float* mixture, int B, int64_t L, int flag, float* out, void* stream) {
+    if (check_ready(c, B)) return 1;
+    SE_REQUIRE(mixture != nullptr && out != nullptr, "se_crn_realtime_process: null buffer");
+    SE_REQUIRE(L > 0, "se_crn_realtime_process: empty signal");
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int front = flag ? 0 : PHOP;  // CRN_ELU.py:474-476
+    int gap = 0, N = 0;
+    se_chunk_grid(L + front, KCHUNK, &gap, &N);
+    if (!flag) {
+        if (se_crn_state_reset(c, 0, B, stream)) return 1;  // CRN_ELU.py:480-481
+    }
+    // chunk n covers samples [n*P - P - front, ... + K) of the caller's signal; its step emits the overlap-added
+    // samples [n*P - P - front, n*P - front) (utility.py:393-403), of which [0, L) are kept.
+    for (int n = 0; n < N; ++n) {
+        IoDesc io{};
+        io.in = mixture;
+        io.in_stream_stride = 3 * L;
+        io.in_mic_stride = L;
+        io.in_offset = (long long)n * PHOP - PHOP - front;
+        io.in_len = L;
+        const long long o0 = (long long)n * PHOP - PHOP - front;
+        long long nv = 0;
+        if (o0 >= 0) nv = (L - o0) < PHOP ? (L - o0) : PHOP;
+        if (nv < 0) nv = 0;
+        io.out = out + (o0 >= 0 ? o0 : 0);
+        io.out_stream_stride = L;
+        io.n_valid = (int)nv;
+        if (run_stream_step(c, io, B, st)) return 1;
+    }
+    return 0;
+}
+
+int se_crn_realtime_process_host(se_ctx* c, const float* mixture, int B, int64_t L, int flag, float* out) {
+    if (check_ready(c, B)) return 1;
+    const size_t nin = (size_t)B * 3 * L, nout = (size_t)B * L;
+    if (c->h_in_floats < nin) {
+        if (c->h_in) cudaFree(c->h_in);
+        SE_CUDA_OK(cudaMalloc(&c->h_in, nin * sizeof(float)));
+        c->h_in_floats = nin;
+    }
+    if (c->h_out_floats < nout) {
+        if (c->h_out) cudaFree(c->h_out);
+        SE_CUDA_OK(cudaMalloc(&c->h_out, nout * sizeof(float)));
+        c->h_out_floats = nout;
+    }
+    SE_CUDA_OK(cudaMemcpy(c->h_in, mixture, nin * sizeof(float), cudaMemcpyHostToDevice));
+    if (se_crn_realtime_process(c, c->h_in, B, L, flag, c->h_out, nullptr)) return 1;
+    SE_CUDA_OK(cudaMemcpy(out, c->h_out, nout * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int se_stft_trans(se_ctx* c, const float* chunks, int R, float* spec, void* stream) {
+    SE_REQUIRE(c != nullptr && chunks != nullptr && spec != nullptr, "se_stft_trans: null argument");
+    SE_CUDA_OK(cudaSetDevice(c->device));
+    if (R == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    IoDesc io{chunks, 3LL * KCHUNK, KCHUNK, 0, KCHUNK, nullptr, 0, 0};
+    if (launch_set_io(c->io_dev, io, st)) return 1;
+    StftParams sp{};
+    sp.io = c->io_dev;
+    sp.B = R;
+    sp.M = 3;
+    sp.student = c->student;
+    sp.spec_ref = spec;
+    return launch_stft_features(sp, st);
+}
+
+int se_istft_trans(se_ctx* c, const float* spec, int R, float* out, void* stream) {
+    SE_REQUIRE(c != nullptr && spec != nullptr && out != nullptr, "se_istft_trans: null argument");
+    SE_CUDA_OK(cudaSetDevice(c->device));
+    if (R == 0) return 0;
+    MaskIstftParams mp{};
+    mp.B = R;
+    mp.spec_in = spec;
+    mp.out_chunk = out;
+    return launch_mask_istft(mp, (cudaStream_t)stream);
+}
+
+int se_crn_forward_chunk(se_ctx* c, const float* spec_in, float* spec_out, int B, void* stream) {
+    if (check_ready(c, B)) return 1;
+    SE_REQUIRE(spec_in != nullptr && spec_out != nullptr, "se_crn_forward_chunk: null buffer");
+    if (B == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_OK(cudaMemsetAsync(c->stats, 0, (size_t)c->n_stats * 2 * c->maxB * sizeof(double), st));
+    const Act& a = c->pre_in[0];
+    if (launch_features_from_spec(spec_in, B, 3, c->student, a.interior(), a.sB, a.sT, a.sF, c->noisy, st)) return 1;
+    if (enqueue_net(c, B, st, -1)) return 1;
+    MaskIstftParams mp{};
+    mp.B = B;
+    mp.student = c->student;
+    mp.y = c->ylast;
+    mp.stats = c->stats + (size_t)c->stats_last * 2 * c->maxB;
+    mp.count = 2.0 * NBIN * T;
+    mp.w = c->w_last;
+    mp.b = c->b_last;
+    mp.noisy = c->noisy;
+    mp.spec_ref = spec_out;
+    if (launch_mask_istft(mp, st)) return 1;
+    return launch_roll(c->roll, 0, B, st);
+}
+
+int se_segmentation(const float* x, int B, int C, int64_t L, int K, float* out, int* gap, int* n_chunks,
+                    void* stream) {
+    SE_REQUIRE(x != nullptr && out != nullptr, "se_segmentation: null buffer");
+    int g = 0, N = 0;
+    if (se_chunk_grid(L, K, &g, &N)) return 1;
+    if (gap) *gap = g;
+    if (n_chunks) *n_chunks = N;
+    return launch_segmentation(x, B, C, L, K, g, N, out, (cudaStream_t)stream);
+}
+
+int se_over_add(const float* chunks, int C, int N, int K, int gap, float* out, void* stream) {
+    SE_REQUIRE(chunks != nullptr && out != nullptr, "se_over_add: null buffer");
+    SE_REQUIRE(N >= 2 && K > 0 && K % 2 == 0 && gap >= 0, "se_over_add: bad arguments");
+    return launch_over_add(chunks, C, N, K, gap, out, (cudaStream_t)stream);
+}
+
+int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t max_floats, int* dims) {
+    SE_REQUIRE(c != nullptr && name != nullptr && host_dst != nullptr && dims != nullptr, "se_debug_read: null argument");
+    SE_REQUIRE(b >= 0 && b < c->maxB, "se_debug_read: stream index");
+    SE_CUDA_OK(cudaSetDevice(c->device));
+    SE_CUDA_OK(cudaDeviceSynchronize());
+    const std::string n(name);
+    const float* src = nullptr;
+    int t = T, f = 1, ch = 1;
+    long long sT = 0, sF = 0;
+    auto from_act = [&](const Act& a) {
+        src = a.interior() + (long long)b * a.sB;
+        f = a.F;
+        ch = a.C;
+        sT = a.sT;
+        sF = a.sF;
+    };
+    auto compact = [&](const float* base, int F_, int C_, int T_ = T) {
+        t = T_;
+        f = F_;
+        ch = C_;
+        sF = C_;
+        sT = (long long)F_ * C_;
+        src = base + (long long)b * T_ * sT;
+    };
+    auto idx_of = [&](const char* prefix, int limit) -> int {
+        const size_t len = strlen(prefix);
+        if (n.compare(0, len, prefix) != 0 || n.size() != len + 1) return -1;
+        const int i = n[len] - '0';
+        return (i >= 0 && i < limit) ? i : -1;
+    };
+    int i;
+    if ((i = idx_of("pre_in", 3)) >= 0) from_act(c->pre_in[i]);
+    else if ((i = idx_of("enc_in", c->L)) >= 0) from_act(c->enc_in[i]);
+    else if ((i = idx_of("dec_in", c->L)) >= 0) from_act(c->dec_in[i]);
+    else if ((i = idx_of("hseq", 2)) >= 0) compact(c->hseq[i], 1, c->H, T + 1);
+    else if (n == "xg") compact(c->xg, c->Fg, c->Cg);
+    else if (n == "fcraw") compact(c->fcraw, c->Fg, c->Cg);
+    else if (n == "ylast") compact(c->ylast, NBIN, 2);
+    else if (n == "noisy") compact(c->noisy, NBIN, 2);
+    else SE_REQUIRE(false, "se_debug_read: unknown tensor " + n);
+    dims[0] = t;
+    dims[1] = f;
+    dims[2] = ch;
+    SE_REQUIRE((int64_t)t * f * ch <= max_floats, "se_debug_read: destination too small");
+    SE_CUDA_OK(cudaMemcpy2D(host_dst, (size_t)f * ch * sizeof(float), src, (size_t)sT * sizeof(float),
+                            (size_t)f * ch * sizeof(float), t, cudaMemcpyDeviceToHost));
+    (void)sF;
+    return 0;
+}
+
+int se_crn_launches_per_chunk(const se_ctx* c) { return c ? count_launches(c) : 0; }
+
+int se_crn_set_graph(se_ctx* c, int enable) {
+    SE_REQUIRE(c != nullptr, "null context");
+    c->use_graph = enable != 0;
+    return 0;
+}
+
+int se_crn_time_stage(se_ctx* c, const char* stage, int B, int iters, float* ms) {
+    if (check_ready(c, B)) return 1;
+    SE_REQUIRE(stage != nullptr && ms != nullptr && iters > 0 && B > 0, "se_crn_time_stage: bad arguments");
+    int filter = -2;
+    if (strcmp(stage, "step") == 0) filter = -1;
+    for (int s = 0; s < ST_COUNT; ++s)
+        if (strcmp(stage, kStageNames[s]) == 0) filter = s;
+    SE_REQUIRE(filter != -2, std::string("se_crn_time_stage: unknown stage ") + stage);
+    cudaStream_t st = nullptr;
+    // a self-contained chunk source so that the stage can run without caller buffers: the carry/out of the previous
+    // run are reused as scratch (timing only; state is garbage afterwards -> caller must reset)
+    static thread_local float* scratch = nullptr;
+    static thread_local size_t scratch_floats = 0;
+    const size_t need = (size_t)B * (3 * KCHUNK + PHOP);
+    if (scratch_floats < need) {
+        if (scratch) cudaFree(scratch);
+        SE_CUDA_OK(cudaMalloc(&scratch, need * sizeof(float)));
+        SE_CUDA_OK(cudaMemset(scratch, 0, need * sizeof(float)));
+        scratch_floats = need;
+    }
+    IoDesc io{scratch, 3LL * KCHUNK, KCHUNK, 0, KCHUNK, scratch + (size_t)B * 3 * KCHUNK, PHOP, PHOP};
+    if (launch_set_io(c->io_dev, io, st)) return 1;
+    cudaEvent_t e0, e1;
+    SE_CUDA_OK(cudaEventCreate(&e0));
+    SE_CUDA_OK(cudaEventCreate(&e1));
+    if (enqueue_stream_step(c, B, st, filter)) return 1;  // warm-up
+    SE_CUDA_OK(cudaEventRecord(e0, st));
+    for (int i = 0; i < iters; ++i)
+        if (enqueue_stream_step(c, B, st, filter)) return 1;
+    SE_CUDA_OK(cudaEventRecord(e1, st));
+    SE_CUDA_OK(cudaEventSynchronize(e1));
+    float t = 0.f;
+    SE_CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t / iters;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return 0;
+}
+
+}  // extern "C"

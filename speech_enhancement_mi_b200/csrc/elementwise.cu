@@ -1,0 +1,218 @@
+// HBM-bound elementwise kernels of the CRN path: GlobalLayerNorm application fused with the residual add / gated
+// skip blend that follows it, the fp32-path GRU cell update, the causal-state roll, framing and overlap-add.
+#include "se_internal.h"
+
+namespace se {
+
+namespace {
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// mean / inverse denominator of GlobalLayerNorm from the accumulated (sum, sum of squares) in double
+// teacher: (x-mean)/(sqrt(var+1e-8)+1e-8)  (CRN_ELU.py:51);  student: (x-mean)/(sqrt(var)+1e-8) (distillation_crn.py:51)
+__device__ __forceinline__ void gln_coeffs(const double* stats, int b, double count, int student, float& mean,
+                                           float& inv) {
+    const double s = stats[2 * b], ss = stats[2 * b + 1];
+    const double mu = s / count;
+    double var = ss / count - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float varf = (float)var;
+    const float den = student ? (sqrtf(varf) + 1e-8f) : (sqrtf(varf + 1e-8f) + 1e-8f);
+    mean = (float)mu;
+    inv = 1.0f / den;
+}
+
+// one thread per 4 channels (C % 4 == 0); grid-stride over B*T*F*C/4
+__global__ void __launch_bounds__(256) norm_apply_kernel(NormApplyParams p) {
+    const int C4 = p.C >> 2;
+    const long long total = (long long)p.B * p.T * p.F * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % C4);
+        long long r = i / C4;
+        const int f = (int)(r % p.F);
+        r /= p.F;
+        const int t = (int)(r % p.T);
+        const int b = (int)(r / p.T);
+        const int c = c4 * 4;
+
+        float mean, inv;
+        gln_coeffs(p.stats, b, p.count, p.student, mean, inv);
+
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (f < p.Fy) {
+            const float4 y = *reinterpret_cast<const float4*>(p.y + (((long long)b * p.T + t) * p.Fy + f) * p.C + c);
+            const int wi = p.per_feature ? (f * p.C + c) : c;
+            const float4 w = *reinterpret_cast<const float4*>(p.w + wi);
+            const float4 bb = *reinterpret_cast<const float4*>(p.b + wi);
+            // same operation order as the reference: (x - mean) / den * w + b; the division is done as a multiply by
+            // the reciprocal (<= 1 ulp difference, inside the stated fp tolerance)
+            o.x = (y.x - mean) * inv * w.x + bb.x;
+            o.y = (y.y - mean) * inv * w.y + bb.y;
+            o.z = (y.z - mean) * inv * w.z + bb.z;
+            o.w = (y.w - mean) * inv * w.w + bb.w;
+        }
+        if (p.mode == 1) {
+            const float4 x = *reinterpret_cast<const float4*>(p.res + b * p.rB + t * p.rT + f * p.rF + c);
+            o.x += x.x;
+            o.y += x.y;
+            o.z += x.z;
+            o.w += x.w;
+        } else if (p.mode == 2) {
+            float mr, ir;
+            gln_coeffs(p.stats_r, b, p.count_r, p.student, mr, ir);
+            const long long ri = (((long long)b * p.T + t) * p.F + f) * p.C + c;
+            const float4 rm = *reinterpret_cast<const float4*>(p.rm + ri);
+            const float4 rr = *reinterpret_cast<const float4*>(p.rr + ri);
+            const float4 w = *reinterpret_cast<const float4*>(p.wr + c);
+            const float4 bb = *reinterpret_cast<const float4*>(p.br + c);
+            const float m0 = sigmoidf_((rm.x - mr) * ir * w.x + bb.x);
+            const float m1 = sigmoidf_((rm.y - mr) * ir * w.y + bb.y);
+            const float m2 = sigmoidf_((rm.z - mr) * ir * w.z + bb.z);
+            const float m3 = sigmoidf_((rm.w - mr) * ir * w.w + bb.w);
+            o.x = m0 * rr.x + (1.0f - m0) * o.x;
+            o.y = m1 * rr.y + (1.0f - m1) * o.y;
+            o.z = m2 * rr.z + (1.0f - m2) * o.z;
+            o.w = m3 * rr.w + (1.0f - m3) * o.w;
+        }
+        *reinterpret_cast<float4*>(p.out + b * p.oB + t * p.oT + f * p.oF + c) = o;
+    }
+}
+
+__global__ void __launch_bounds__(256) gru_pointwise_kernel(const float* __restrict__ gi, long long giB,
+                                                            const float* __restrict__ gh,
+                                                            const float* __restrict__ hprev, long long hB,
+                                                            float* __restrict__ hout, int B, int H) {
+    const long long total = (long long)B * H;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % H);
+        const int b = (int)(i / H);
+        const float* g = gi + b * giB;
+        const float* h = gh + (long long)b * 3 * H;
+        const float r = sigmoidf_(g[j] + h[j]);
+        const float z = sigmoidf_(g[H + j] + h[H + j]);
+        const float n = tanhf(g[2 * H + j] + r * h[2 * H + j]);
+        const float hp = hprev[b * hB + j];
+        hout[b * hB + j] = (1.0f - z) * n + z * hp;
+    }
+}
+
+__global__ void __launch_bounds__(256) roll_kernel(RollTable tab, int first, int zero) {
+    const RollEntry e = tab.e[blockIdx.y];
+    const int b = first + blockIdx.z;
+    float* base = e.base + b * e.sB;
+    const int n4 = e.count >> 2;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!zero) v = *reinterpret_cast<const float4*>(base + e.src_off + 4 * i);
+        *reinterpret_cast<float4*>(base + e.dst_off + 4 * i) = v;
+    }
+}
+
+__global__ void set_io_kernel(IoDesc* dst, IoDesc v) { *dst = v; }
+
+// utility.py:339-370 -- chunk n of stream b is row b*N+n = padded[n*P : n*P+K], padded = [P zeros | x | gap | P zeros]
+__global__ void __launch_bounds__(256) segmentation_kernel(const float* __restrict__ x, int B, int C, long long L,
+                                                           int K, int N, float* __restrict__ out) {
+    const int P = K / 2;
+    const long long total = (long long)B * N * C * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K);
+        long long r = i / K;
+        const int c = (int)(r % C);
+        r /= C;
+        const int n = (int)(r % N);
+        const int b = (int)(r / N);
+        const long long src = (long long)n * P + k - P;
+        out[i] = (src >= 0 && src < L) ? x[((long long)b * C + c) * L + src] : 0.f;
+    }
+}
+
+// utility.py:373-403 -- y[q] = (even(q) + odd(q)) / 2 for q in [P, N*P), then drop `gap` samples of tail
+__global__ void __launch_bounds__(256) over_add_kernel(const float* __restrict__ chunks, int C, int N, int K, int gap,
+                                                       float* __restrict__ out) {
+    const int P = K / 2;
+    const long long Lout = (long long)N * P - P - gap;
+    const long long total = (long long)C * Lout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long q = i % Lout + P;
+        const int c = (int)(i / Lout);
+        const int n1 = (int)(q / P);  // chunk starting at n1*P: offset q - n1*P in [0,P)
+        const int n0 = n1 - 1;        // chunk starting at n0*P: offset in [P, K)
+        const float a = chunks[((long long)c * N + n0) * K + (q - (long long)n0 * P)];
+        const float b = chunks[((long long)c * N + n1) * K + (q - (long long)n1 * P)];
+        // reference adds input1 (even chunks) + input2 (odd chunks): fp add is commutative, so order is immaterial
+        out[i] = (a + b) / 2;
+    }
+}
+
+inline int grid_for(long long n, int block = 256) {
+    long long g = (n + block - 1) / block;
+    const long long cap = 148LL * 16;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int launch_norm_apply(const NormApplyParams& p, cudaStream_t st) {
+    SE_REQUIRE(p.C % 4 == 0, "norm_apply: C must be a multiple of 4");
+    const long long total = (long long)p.B * p.T * p.F * (p.C / 4);
+    if (total == 0) return 0;
+    norm_apply_kernel<<<grid_for(total), 256, 0, st>>>(p);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_gru_pointwise(const float* gi, long long giB, const float* gh, const float* hprev, long long hB,
+                         float* hout, int B, int H, cudaStream_t st) {
+    if (B == 0) return 0;
+    gru_pointwise_kernel<<<grid_for((long long)B * H), 256, 0, st>>>(gi, giB, gh, hprev, hB, hout, B, H);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int roll_or_zero(const RollTable& tab, int first, int B, int zero, cudaStream_t st) {
+    if (B == 0 || tab.n == 0) return 0;
+    int maxc = 0;
+    for (int i = 0; i < tab.n; ++i) maxc = tab.e[i].count > maxc ? tab.e[i].count : maxc;
+    int gx = (maxc / 4 + 255) / 256;
+    gx = gx < 1 ? 1 : (gx > 32 ? 32 : gx);
+    // gridDim.z is limited to 65535 streams per launch
+    for (int off = 0; off < B; off += 65535) {
+        const int nb = (B - off) < 65535 ? (B - off) : 65535;
+        roll_kernel<<<dim3(gx, tab.n, nb), 256, 0, st>>>(tab, first + off, zero);
+        SE_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+int launch_roll(const RollTable& tab, int first, int B, cudaStream_t st) { return roll_or_zero(tab, first, B, 0, st); }
+int launch_zero(const RollTable& tab, int first, int B, cudaStream_t st) { return roll_or_zero(tab, first, B, 1, st); }
+
+int launch_set_io(IoDesc* dst, const IoDesc& v, cudaStream_t st) {
+    set_io_kernel<<<1, 1, 0, st>>>(dst, v);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_segmentation(const float* x, int B, int C, long long L, int K, int gap, int N, float* out,
+                        cudaStream_t st) {
+    (void)gap;
+    const long long total = (long long)B * N * C * K;
+    if (total == 0) return 0;
+    segmentation_kernel<<<grid_for(total), 256, 0, st>>>(x, B, C, L, K, N, out);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_over_add(const float* chunks, int C, int N, int K, int gap, float* out, cudaStream_t st) {
+    const long long total = (long long)C * ((long long)N * (K / 2) - K / 2 - gap);
+    if (total <= 0) return 0;
+    over_add_kernel<<<grid_for(total), 256, 0, st>>>(chunks, C, N, K, gap, out);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace se

@@ -1,0 +1,413 @@
+// STFT framing + Hamming window + real FFT-400 + input features, and its inverse: cIRM mask application + inverse
+// real FFT-400 + window + intra-chunk overlap-add + envelope division + 50 % chunk overlap-add with a carried half.
+//
+// n_fft = 400 = 20 x 20 is not a power of two: both transforms are four-step (20-point DFT, twiddle, 20-point DFT)
+// Cooley-Tukey factorizations staged entirely in shared memory, exploiting the Hermitian symmetry of a real signal.
+//   forward : n = 20*n1 + n2, k = k1 + 20*k2 :  X[k] = sum_n2 W20^(n2 k2) * W400^(n2 k1) * sum_n1 x[n] W20^(n1 k1)
+//   inverse : same indices, conjugate twiddles, X[400-k] = conj X[k], imag of DC / Nyquist ignored (C2R semantics
+//             of torch.fft.irfft inside torch.istft).
+// Reference call sites: CRN_ELU.py:417-424 (stft_trans), :369-373 (features), :401-405 + utility.py:439-442 (mask),
+// CRN_ELU.py:426-432 (istft_trans), utility.py:393-403 (over_add).
+#include <math.h>
+
+#include <vector>
+
+#include "se_internal.h"
+
+namespace se {
+
+namespace {
+
+constexpr int NFFT = 400;
+constexpr int HOP = 160;
+constexpr int NBIN = 201;
+constexpr int T = kFramesPerChunk;  // 21
+constexpr int K = 3200;             // chunk
+constexpr int GROUP = 7;            // frames handled per pass
+constexpr int ROW = 21;             // padded row length (float2) of the 20x20 intermediate
+
+__constant__ float2 c_w20[20];    // exp(-2 pi i j / 20)
+__constant__ float2 c_w400[400];  // exp(-2 pi i j / 400)
+__constant__ float c_window[NFFT];
+__constant__ float c_env[K];  // sum_t w^2 at output positions (istft window envelope, trimmed)
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
+    return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// STFT + features.  grid = (B, 3): block (b, g) handles frames [7g, 7g+7) of all microphones of stream b.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SPAN = (GROUP - 1) * HOP + NFFT;  // 1360 padded samples cover 7 frames
+
+struct StftSmem {
+    float xs[3][SPAN];              // raw samples (zero outside the chunk), up to 3 mics per pass set
+    float win[NFFT];
+    float2 w20[20];
+    float2 w400[400];
+    float2 y[GROUP][20][ROW];       // stage-1 output after twiddle
+    float2 spec[3][GROUP][NBIN + 1];
+};
+
+__global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+    const int t0 = blockIdx.y * GROUP;
+    const int M = p.M;  // <= 3 per pass set (host guarantees M == 3 for the feature path)
+
+    for (int i = tid; i < NFFT; i += blockDim.x) {
+        s.win[i] = c_window[i];
+        s.w400[i] = c_w400[i];
+    }
+    if (tid < 20) s.w20[tid] = c_w20[tid];
+    const float* in = p.io->in + b * p.io->in_stream_stride;
+    const long long mic_stride = p.io->in_mic_stride;
+    const long long in_off = p.io->in_offset, in_len = p.io->in_len;
+    for (int m = 0; m < M; ++m) {
+        for (int i = tid; i < SPAN; i += blockDim.x) {
+            const int n = t0 * HOP + i - NFFT / 2;  // sample index inside the chunk (center=True zero padding)
+            const long long j = in_off + n;         // index inside the caller's signal (segmentation zero padding)
+            s.xs[m][i] = (n >= 0 && n < K && j >= 0 && j < in_len) ? in[m * mic_stride + j] : 0.f;
+        }
+    }
+    __syncthreads();
+
+    for (int m = 0; m < M; ++m) {
+        // ---- stage 1: 20-point DFT over n1 of real data, k1 = 0..10, then twiddle W400^(n2 k1) -----------------
+        for (int o = tid; o < GROUP * 11 * 20; o += blockDim.x) {
+            const int n2 = o % 20;
+            const int k1 = (o / 20) % 11;
+            const int fr = o / 220;
+            const float* x = &s.xs[m][fr * HOP];
+            float re = 0.f, im = 0.f;
+            int idx = 0;
+#pragma unroll 5
+            for (int n1 = 0; n1 < 20; ++n1) {
+                const int n = 20 * n1 + n2;
+                const float v = x[n] * s.win[n];
+                const float2 w = s.w20[idx];
+                re = fmaf(v, w.x, re);
+                im = fmaf(v, w.y, im);
+                idx += k1;
+                if (idx >= 20) idx -= 20;
+            }
+            const float2 yv = make_float2(re, im);
+            s.y[fr][k1][n2] = cmul(yv, s.w400[n2 * k1]);
+            if (k1 >= 1 && k1 <= 9) {  // Hermitian partner row 20-k1
+                const float2 yc = make_float2(re, -im);
+                s.y[fr][20 - k1][n2] = cmul(yc, s.w400[n2 * (20 - k1)]);
+            }
+        }
+        __syncthreads();
+        // ---- stage 2: 20-point DFT over n2 -> bins k = k1 + 20 k2, k <= 200 ------------------------------------
+        for (int o = tid; o < GROUP * NBIN; o += blockDim.x) {
+            const int k = o % NBIN;
+            const int fr = o / NBIN;
+            const int k1 = k % 20, k2 = k / 20;
+            const float2* yr = s.y[fr][k1];
+            float re = 0.f, im = 0.f;
+            int idx = 0;
+#pragma unroll 5
+            for (int n2 = 0; n2 < 20; ++n2) {
+                const float2 v = yr[n2];
+                const float2 w = s.w20[idx];
+                re = fmaf(v.x, w.x, re);
+                re = fmaf(-v.y, w.y, re);
+                im = fmaf(v.x, w.y, im);
+                im = fmaf(v.y, w.x, im);
+                idx += k2;
+                if (idx >= 20) idx -= 20;
+            }
+            // DC and Nyquist bins of a real signal are exactly real (pocketfft r2c returns +0 there)
+            if (k == 0 || k == NBIN - 1) im = 0.f;
+            s.spec[m][fr][k] = make_float2(re, im);
+        }
+        __syncthreads();
+    }
+
+    // ---- outputs ---------------------------------------------------------------------------------------------
+    if (p.spec_ref != nullptr) {  // reference layout [R][M][F][T][2]
+        for (int o = tid; o < M * GROUP * NBIN; o += blockDim.x) {
+            const int fr = o % GROUP;
+            const int k = (o / GROUP) % NBIN;
+            const int m = o / (GROUP * NBIN);
+            const float2 v = s.spec[m][fr][k];
+            float2* dst = reinterpret_cast<float2*>(p.spec_ref) + (((long long)b * M + m) * NBIN + k) * T + t0 + fr;
+            *dst = v;
+        }
+    }
+    if (p.feat != nullptr) {
+        for (int o = tid; o < GROUP * NBIN; o += blockDim.x) {
+            const int k = o % NBIN;
+            const int fr = o / NBIN;
+            const int t = t0 + fr;
+            float mag[3], ph[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                const float2 v = s.spec[m][fr][k];
+                mag[m] = sqrtf(v.x * v.x + v.y * v.y + 1e-10f);  // CRN_ELU.py:372
+                ph[m] = p.student ? atanf(v.y / (v.x + 1e-8f) + 1e-8f)  // distillation_crn.py:340
+                                  : atan2f(v.y, v.x);                   // CRN_ELU.py:370
+            }
+            float* f = p.feat + b * p.fB + t * p.fT + k * p.fF;
+            *reinterpret_cast<float4*>(f) = make_float4(mag[0], mag[1], mag[2], ph[0] - ph[1]);
+            *reinterpret_cast<float4*>(f + 4) = make_float4(ph[0] - ph[2], 0.f, 0.f, 0.f);
+            reinterpret_cast<float2*>(p.noisy)[((long long)b * T + t) * NBIN + k] = s.spec[0][fr][k];
+        }
+    }
+}
+
+// features from a reference-layout spectrum (TemporalCRN.forward entry, CRN_ELU.py:369-373)
+__global__ void __launch_bounds__(256) features_from_spec_kernel(const float* __restrict__ spec, int B, int M,
+                                                                 int student, float* __restrict__ feat, long long fB,
+                                                                 long long fT, long long fF,
+                                                                 float* __restrict__ noisy) {
+    const long long total = (long long)B * T * NBIN;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % NBIN);
+        const int t = (int)((i / NBIN) % T);
+        const int b = (int)(i / ((long long)NBIN * T));
+        float mag[3], ph[3];
+        float2 v0 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int m = 0; m < 3; ++m) {
+            const float2 v = reinterpret_cast<const float2*>(spec)[(((long long)b * M + m) * NBIN + k) * T + t];
+            if (m == 0) v0 = v;
+            mag[m] = sqrtf(v.x * v.x + v.y * v.y + 1e-10f);
+            ph[m] = student ? atanf(v.y / (v.x + 1e-8f) + 1e-8f) : atan2f(v.y, v.x);
+        }
+        float* f = feat + b * fB + t * fT + k * fF;
+        *reinterpret_cast<float4*>(f) = make_float4(mag[0], mag[1], mag[2], ph[0] - ph[1]);
+        *reinterpret_cast<float4*>(f + 4) = make_float4(ph[0] - ph[2], 0.f, 0.f, 0.f);
+        reinterpret_cast<float2*>(noisy)[((long long)b * T + t) * NBIN + k] = v0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// mask + iSTFT + overlap-add.  grid = B, one block per stream; frames processed in 3 groups of 7.
+// ------------------------------------------------------------------------------------------------------------
+struct IstftSmem {
+    float2 spec[GROUP][NBIN + 1];
+    float2 z[GROUP][11][ROW];
+    float frames[GROUP][NFFT];
+    float ola[NFFT + HOP * (T - 1)];  // 3600
+    float win[NFFT];
+    float2 w20[20];
+    float2 w400[400];
+};
+
+__device__ __forceinline__ float decompress_cirm(float m) {  // utility.py:439-442
+    const float limit = 9.9f;
+    const float ge = (m >= limit) ? 1.f : 0.f;
+    const float le = (m <= -limit) ? 1.f : 0.f;
+    const float in = (fabsf(m) < limit) ? 1.f : 0.f;
+    m = limit * ge - limit * le + m * in;
+    return -10.f * logf((10.f - m) / (10.f + m));
+}
+
+__global__ void __launch_bounds__(256) mask_istft_kernel(MaskIstftParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    IstftSmem& s = *reinterpret_cast<IstftSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x;
+
+    for (int i = tid; i < NFFT; i += blockDim.x) {
+        s.win[i] = c_window[i];
+        s.w400[i] = c_w400[i];
+    }
+    if (tid < 20) s.w20[tid] = c_w20[tid];
+    for (int i = tid; i < NFFT + HOP * (T - 1); i += blockDim.x) s.ola[i] = 0.f;
+
+    float mean = 0.f, inv = 0.f, w0 = 0.f, w1 = 0.f, b0 = 0.f, b1 = 0.f;
+    if (p.spec_in == nullptr) {
+        const double sum = p.stats[2 * b], ssq = p.stats[2 * b + 1];
+        const double mu = sum / p.count;
+        double var = ssq / p.count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const float varf = (float)var;
+        const float den = p.student ? (sqrtf(varf) + 1e-8f) : (sqrtf(varf + 1e-8f) + 1e-8f);
+        mean = (float)mu;
+        inv = 1.f / den;
+        w0 = p.w[0];
+        w1 = p.w[1];
+        b0 = p.b[0];
+        b1 = p.b[1];
+    }
+    __syncthreads();
+
+    for (int g = 0; g < T / GROUP; ++g) {
+        const int t0 = g * GROUP;
+        // ---- enhanced spectrum of this frame group -----------------------------------------------------------
+        for (int o = tid; o < GROUP * NBIN; o += blockDim.x) {
+            const int k = o % NBIN;
+            const int fr = o / NBIN;
+            const int t = t0 + fr;
+            float2 e;
+            if (p.spec_in != nullptr) {
+                e = reinterpret_cast<const float2*>(p.spec_in)[((long long)b * NBIN + k) * T + t];
+            } else {
+                const long long idx = ((long long)b * T + t) * NBIN + k;
+                const float2 y = reinterpret_cast<const float2*>(p.y)[idx];
+                const float2 x = reinterpret_cast<const float2*>(p.noisy)[idx];
+                const float mr = decompress_cirm((y.x - mean) * inv * w0 + b0);
+                const float mi = decompress_cirm((y.y - mean) * inv * w1 + b1);
+                e = make_float2(mr * x.x - mi * x.y, mi * x.x + mr * x.y);  // CRN_ELU.py:402-403
+                if (p.spec_ref != nullptr)
+                    reinterpret_cast<float2*>(p.spec_ref)[((long long)b * NBIN + k) * T + t] = e;
+            }
+            if (k == 0 || k == NBIN - 1) e.y = 0.f;  // C2R: imaginary parts of DC / Nyquist are ignored
+            s.spec[fr][k] = e;
+        }
+        __syncthreads();
+        if (p.spec_ref != nullptr && p.out_chunk == nullptr && p.carry == nullptr) continue;  // forward(): no iSTFT
+
+        // ---- stage A: z[k1][n2] = sum_k2 Xfull[k1 + 20 k2] * conj(W20)^(n2 k2), then * conj(W400)^(n2 k1) -------
+        for (int o = tid; o < GROUP * 11 * 20; o += blockDim.x) {
+            const int n2 = o % 20;
+            const int k1 = (o / 20) % 11;
+            const int fr = o / 220;
+            float re = 0.f, im = 0.f;
+            int idx = 0;
+#pragma unroll 5
+            for (int k2 = 0; k2 < 20; ++k2) {
+                const int k = k1 + 20 * k2;
+                float2 v;
+                if (k <= 200) {
+                    v = s.spec[fr][k];
+                } else {
+                    v = s.spec[fr][NFFT - k];
+                    v.y = -v.y;
+                }
+                const float2 w = s.w20[idx];  // conj applied below
+                re = fmaf(v.x, w.x, re);
+                re = fmaf(v.y, w.y, re);
+                im = fmaf(v.y, w.x, im);
+                im = fmaf(-v.x, w.y, im);
+                idx += n2;
+                if (idx >= 20) idx -= 20;
+            }
+            s.z[fr][k1][n2] = cmul_conj(make_float2(re, im), s.w400[n2 * k1]);
+        }
+        __syncthreads();
+        // ---- stage C: x[20 n1 + n2] = (z0 + (-1)^n1 z10 + 2 sum_{k1=1..9} Re(z[k1] conj(W20)^(n1 k1))) / 400 ----
+        for (int o = tid; o < GROUP * NFFT; o += blockDim.x) {
+            const int n = o % NFFT;
+            const int fr = o / NFFT;
+            const int n1 = n / 20, n2 = n % 20;
+            float acc = 0.f;
+            int idx = n1;
+#pragma unroll
+            for (int k1 = 1; k1 <= 9; ++k1) {
+                const float2 v = s.z[fr][k1][n2];
+                const float2 w = s.w20[idx];
+                acc = fmaf(v.x, w.x, acc);
+                acc = fmaf(v.y, w.y, acc);  // Re(v * conj(w))
+                idx += n1;
+                if (idx >= 20) idx -= 20;
+            }
+            const float z0 = s.z[fr][0][n2].x;
+            const float z10 = s.z[fr][10][n2].x;
+            const float x = (z0 + ((n1 & 1) ? -z10 : z10) + 2.f * acc) * (1.0f / NFFT);
+            s.frames[fr][n] = x * s.win[n];
+        }
+        __syncthreads();
+        // ---- overlap-add of this group's frames (deterministic order: ascending frame) ---------------------------
+        for (int pos = tid; pos < NFFT + HOP * (T - 1); pos += blockDim.x) {
+            float acc = s.ola[pos];
+#pragma unroll
+            for (int fr = 0; fr < GROUP; ++fr) {
+                const int n = pos - (t0 + fr) * HOP;
+                if (n >= 0 && n < NFFT) acc += s.frames[fr][n];
+            }
+            s.ola[pos] = acc;
+        }
+        __syncthreads();
+    }
+    if (p.spec_ref != nullptr && p.out_chunk == nullptr && p.carry == nullptr) return;
+
+    // ---- envelope division, trim n_fft/2, chunk-level 50 % overlap-add with the carried half ---------------------
+    constexpr int P = K / 2;
+    if (p.out_chunk != nullptr) {
+        for (int n = tid; n < K; n += blockDim.x) p.out_chunk[(long long)b * K + n] = s.ola[NFFT / 2 + n] / c_env[n];
+    }
+    if (p.carry != nullptr) {
+        float* out = p.io->out + b * p.io->out_stream_stride;
+        const int n_valid = p.io->n_valid;
+        float* carry = p.carry + (long long)b * P;
+        for (int n = tid; n < P; n += blockDim.x) {
+            const float first = s.ola[NFFT / 2 + n] / c_env[n];
+            const float second = s.ola[NFFT / 2 + P + n] / c_env[P + n];
+            if (n < n_valid) out[n] = (first + carry[n]) / 2;  // utility.py:397-399
+            carry[n] = second;
+        }
+    }
+}
+
+}  // namespace
+
+int init_fft_tables() {
+    std::vector<float2> w20(20), w400(400);
+    std::vector<float> win(NFFT), env(K);
+    const double pi = 3.14159265358979323846;
+    for (int j = 0; j < 20; ++j) w20[j] = make_float2((float)cos(2 * pi * j / 20), (float)(-sin(2 * pi * j / 20)));
+    for (int j = 0; j < 400; ++j) w400[j] = make_float2((float)cos(2 * pi * j / 400), (float)(-sin(2 * pi * j / 400)));
+    // exact quadrant values (avoid 6e-17 residues turning into sign noise)
+    w20[0] = make_float2(1.f, 0.f);
+    w20[5] = make_float2(0.f, -1.f);
+    w20[10] = make_float2(-1.f, 0.f);
+    w20[15] = make_float2(0.f, 1.f);
+    w400[0] = make_float2(1.f, 0.f);
+    w400[100] = make_float2(0.f, -1.f);
+    w400[200] = make_float2(-1.f, 0.f);
+    w400[300] = make_float2(0.f, 1.f);
+    for (int n = 0; n < NFFT; ++n) win[n] = (float)(0.54 - 0.46 * cos(2 * pi * n / NFFT));  // periodic Hamming
+    std::vector<double> full(NFFT + HOP * (T - 1), 0.0);
+    for (int t = 0; t < T; ++t)
+        for (int n = 0; n < NFFT; ++n) full[t * HOP + n] += (double)win[n] * (double)win[n];
+    for (int n = 0; n < K; ++n) env[n] = (float)full[NFFT / 2 + n];
+    SE_CUDA_OK(cudaMemcpyToSymbol(c_w20, w20.data(), sizeof(float2) * 20));
+    SE_CUDA_OK(cudaMemcpyToSymbol(c_w400, w400.data(), sizeof(float2) * 400));
+    SE_CUDA_OK(cudaMemcpyToSymbol(c_window, win.data(), sizeof(float) * NFFT));
+    SE_CUDA_OK(cudaMemcpyToSymbol(c_env, env.data(), sizeof(float) * K));
+    SE_CUDA_OK(cudaFuncSetAttribute(stft_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(StftSmem)));
+    SE_CUDA_OK(cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)sizeof(IstftSmem)));
+    return 0;
+}
+
+int launch_stft_features(const StftParams& p, cudaStream_t st) {
+    SE_REQUIRE(p.M >= 1 && p.M <= 3, "stft: at most 3 microphones per launch");
+    SE_REQUIRE(p.feat == nullptr || p.M == 3, "stft features need exactly 3 microphones (CRN_ELU.py:369-373)");
+    if (p.B == 0) return 0;
+    stft_features_kernel<<<dim3(p.B, T / GROUP), 256, sizeof(StftSmem), st>>>(p);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_features_from_spec(const float* spec, int B, int M, int student, float* feat, long long fB, long long fT,
+                              long long fF, float* noisy, cudaStream_t st) {
+    SE_REQUIRE(M == 3, "features need exactly 3 microphones (CRN_ELU.py:369-373)");
+    if (B == 0) return 0;
+    const long long total = (long long)B * T * NBIN;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    features_from_spec_kernel<<<grid, 256, 0, st>>>(spec, B, M, student, feat, fB, fT, fF, noisy);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_mask_istft(const MaskIstftParams& p, cudaStream_t st) {
+    if (p.B == 0) return 0;
+    mask_istft_kernel<<<p.B, 256, sizeof(IstftSmem), st>>>(p);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace se

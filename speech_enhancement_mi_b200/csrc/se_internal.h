@@ -1,0 +1,172 @@
+// Internal declarations shared by the .cu translation units of libse_b200.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace se {
+
+constexpr int kFramesPerChunk = 21;  // T = 1 + K/hop for K=3200, hop=160 (reference: torch.stft center=True)
+
+// ---------------------------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+#define SE_CUDA_OK(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            se::set_error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" +      \
+                          __FILE__ + ":" + std::to_string(__LINE__) + ")");                       \
+            return 1;                                                                             \
+        }                                                                                         \
+    } while (0)
+#define SE_REQUIRE(cond, msg)                       \
+    do {                                            \
+        if (!(cond)) {                              \
+            se::set_error(std::string(msg));        \
+            return 2;                               \
+        }                                           \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// gathered GEMM:  C[m][n] = sum_k A(m,k) * W[n][k],  m = (b*Tn + t)*Fo + f
+//   A(m,k) = A[b*sB + t*sT + f*sF + koff[k/4] + k%4]          (implicit im2col over channels-last activations)
+// Used for every dense contraction of the path: causal convs (CRN_ELU.py:239), 1x1 gate pairs (:240), transposed
+// convs (:294), skip 1x1s (:305-306), GRU input / recurrent projections (:173) and the output Linear (:175).
+// ---------------------------------------------------------------------------------------------------------------
+enum Epilogue : int {
+    EPI_BIAS = 0,        // out[n] = acc + bias[n]
+    EPI_ELU = 1,         // out[n] = elu(acc + bias[n])
+    EPI_ELU_STATS = 2,   // as EPI_ELU, and accumulate per-stream sum / sum-of-squares of out
+    EPI_GATE_STATS = 3,  // columns interleaved (trans_c, gated_c): out[c] = (a0+b0)*sigmoid(a1+b1); stats of out
+    EPI_SKIP = 4,        // columns interleaved (mask_c, resid_c): out[c] = a0+b0 (stats); out2[c] = elu(a1+b1)
+    EPI_GRU = 5,         // TF32 path only: columns per 32-unit group [r|z|n]; fused GRU cell update
+};
+
+struct GemmParams {
+    const float* A;
+    long long sB, sT, sF;  // element strides of the row decomposition
+    int Tn, Fo, M;
+    const int* koff;  // [K/4] element offset of every 4-float unit of a row
+    int K;            // multiple of 4 (fp32 path) / padded to a multiple of 32 (tf32 path)
+    const float* W;   // [Npad][K] packed weights, rows >= N are zero
+    int N;            // logical columns
+    int Npad;         // rows available in W / bias (multiple of 16)
+    const float* bias;
+    int epi;
+    float* out;
+    long long oB, oT, oF;
+    float* out2;
+    long long o2B, o2T, o2F;
+    double* stats;  // [B][2] (sum, sum of squares)
+    // EPI_GRU extras: gi = input projection (b_ih included) [B][Tn_gi][3H]; h_prev/h_out rows [B][.][H]
+    const float* gi;
+    long long giB;
+    const float* hprev;
+    long long hB;
+    int H;
+};
+
+int launch_gemm_fp32(const GemmParams& p, cudaStream_t st);
+int launch_gemm_tf32(const GemmParams& p, cudaStream_t st);  // tcgen05 path (gemm_tc.cu)
+
+// ---------------------------------------------------------------------------------------------------------------
+// GlobalLayerNorm application (CRN_ELU.py:37-56), fused with what follows it in the graph
+// ---------------------------------------------------------------------------------------------------------------
+struct NormApplyParams {
+    int mode;  // 0: plain, 1: + residual (preconv, CRN_ELU.py:376), 2: gated skip blend (CRN_ELU.py:297-306)
+    int B, T, F, C;         // logical extent of the output
+    int student;            // distillation_crn.py:51 denominator
+    const float* y;         // raw (pre-norm) tensor, [B][T][Fy][C] compact; rows f >= Fy read as post-norm 0 (mode 2)
+    int Fy;
+    const double* stats;    // [B][2] of y
+    double count;           // number of real elements per stream in the statistics
+    const float* w;         // per-channel [C] (or per-feature [F*C] when per_feature)
+    const float* b;
+    int per_feature;
+    // mode 1: residual source (block input), mode 2 unused
+    const float* res;
+    long long rB, rT, rF;
+    // mode 2: rm = raw residual mask [B][T][F][C] compact, rr = elu(residual) compact, stats/affine of rm
+    const float* rm;
+    const float* rr;
+    const double* stats_r;
+    double count_r;
+    const float* wr;
+    const float* br;
+    // destination (channels-last, strided)
+    float* out;
+    long long oB, oT, oF;
+};
+int launch_norm_apply(const NormApplyParams& p, cudaStream_t st);
+
+// GRU cell pointwise update for the fp32 path (PyTorch nn.GRU gate order r,z,n; CRN_ELU.py:127-133)
+int launch_gru_pointwise(const float* gi, long long giB, const float* gh, const float* hprev, long long hB,
+                         float* hout, int B, int H, cudaStream_t st);
+
+// state roll: copy `count` floats from src_off to dst_off inside each stream's slab of up to 16 buffers
+struct RollEntry {
+    float* base;
+    long long sB;
+    long long src_off, dst_off;
+    int count;  // multiple of 4
+};
+struct RollTable {
+    RollEntry e[16];
+    int n;
+};
+int launch_roll(const RollTable& tab, int first, int B, cudaStream_t st);
+int launch_zero(const RollTable& tab, int first, int B, cudaStream_t st);  // zero [dst_off, dst_off+count)
+
+// ---------------------------------------------------------------------------------------------------------------
+// STFT / features / mask / iSTFT / overlap-add
+// ---------------------------------------------------------------------------------------------------------------
+struct IoDesc {  // written by a 1-thread kernel before each step so that a captured graph can stay static
+    const float* in;  // sample n of the chunk = in[b*in_stream_stride + m*in_mic_stride + in_offset + n] when that index
+    long long in_stream_stride, in_mic_stride;  // lies in [0, in_len), else 0 (the zero padding of utility.py:327-336)
+    long long in_offset, in_len;
+    float* out;  // K/2 samples per stream; only the first n_valid are written (gap trimming, CRN_ELU.py:507-508)
+    long long out_stream_stride;
+    int n_valid;
+};
+
+struct StftParams {
+    const IoDesc* io;  // chunk source
+    int B, M;          // streams, microphones (3)
+    int student;       // phase formula of distillation_crn.py:340
+    float* feat;       // preconv-0 input buffer interior, channels-last C=8: [b][t][f][c]
+    long long fB, fT, fF;
+    float* noisy;  // mic-0 spectrum [B][T][F][2]
+    // optional full spectrum in the reference layout [R][M][F][T][2] (se_stft_trans); feat/noisy may be null
+    float* spec_ref;
+};
+int launch_stft_features(const StftParams& p, cudaStream_t st);
+// features from a spectrum in the reference layout [B][M][F][T][2] (for TemporalCRN.forward, CRN_ELU.py:369-373)
+int launch_features_from_spec(const float* spec, int B, int M, int student, float* feat, long long fB, long long fT,
+                              long long fF, float* noisy, cudaStream_t st);
+
+struct MaskIstftParams {
+    const IoDesc* io;     // out pointer for the fused streaming path (may be null when out_chunk is set)
+    int B;
+    int student;
+    const float* y;       // raw last-deconv output [B][T][F][2]
+    const double* stats;  // its statistics
+    double count;
+    const float* w;  // norm affine, 2 channels
+    const float* b;
+    const float* noisy;  // mic-0 spectrum [B][T][F][2]
+    float* carry;        // [B][K/2] overlap-add carry (null: no streaming OLA)
+    float* out_chunk;    // optional [B][K] full per-chunk iSTFT output
+    float* spec_ref;     // optional enhanced spectrum in the reference layout [B][F][T][2] (forward()); skips iSTFT
+    const float* spec_in;  // optional: take the enhanced spectrum [B][F][T][2] from here instead (se_istft_trans)
+};
+int launch_mask_istft(const MaskIstftParams& p, cudaStream_t st);
+int init_fft_tables();  // uploads twiddles / window / envelope to constant memory of the current device
+
+int launch_set_io(IoDesc* dst, const IoDesc& v, cudaStream_t st);
+int launch_segmentation(const float* x, int B, int C, long long L, int K, int gap, int N, float* out, cudaStream_t st);
+int launch_over_add(const float* chunks, int C, int N, int K, int gap, float* out, cudaStream_t st);
+
+}  // namespace se

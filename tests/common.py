@@ -1,0 +1,57 @@
+"""Shared helpers for the parity tests (test infrastructure; may import oracle/)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+from oracle import synth  # noqa: E402
+from oracle.crn_oracle import CRNOracle, si_sdr_db  # noqa: E402
+
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+TEACHER = dict(num_channels=[16, 32, 64, 128], num_freqs=201, hidden=512, num_layers=2, num_inputs=3, kernel_size=3)
+STUDENT = dict(num_channels=[16, 32, 64, 64], num_freqs=201, hidden=128, num_layers=2, num_inputs=3, kernel_size=3)
+SMALL = dict(num_channels=[8, 8, 16, 16], num_freqs=201, hidden=32, num_layers=2, num_inputs=3, kernel_size=3)
+CONFIGS = {"crn_small": (SMALL, 7, False), "crn_teacher": (TEACHER, 0, False), "crn_student": (STUDENT, 3, True)}
+
+# Stated floating-point tolerances of the CUDA path against the reference (north_star: "max-abs error on the waveform
+# plus an SI-SDR delta").  fp32 mode re-associates sums (tiled GEMM, four-step FFT) but keeps fp32 everywhere.
+TOL = {
+    "fp32": dict(wave_max_abs=2e-4, spec_rel=2e-4, si_sdr_vs_ref_db=70.0),
+    "tf32": dict(wave_max_abs=2e-2, spec_rel=2e-2, si_sdr_vs_ref_db=40.0),
+}
+
+
+def load_golden(tag):
+    z = np.load(os.path.join(GOLDEN, f"{tag}.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def make_oracle(tag):
+    cfg, seed, student = CONFIGS[tag]
+    w = synth.make_crn_weights(seed=seed, **cfg)
+    return CRNOracle({k: torch.from_numpy(v) for k, v in w.items()}, segment_length=3200, student=student, **cfg), w
+
+
+def make_model(tag, precision="fp32", **kw):
+    """The product model with the deterministic synthetic weights of `tag` loaded through load_state_dict."""
+    from speech_enhancement_mi_b200 import CRN_ELU, distillation_crn
+    cfg, seed, student = CONFIGS[tag]
+    cls = distillation_crn.TemporalCRN if student else CRN_ELU.TemporalCRN
+    model = cls(segment_length=3200, dropout=0.0, precision=precision, **cfg, **kw)
+    w = synth.make_crn_weights(seed=seed, **cfg)
+    sd = {k: torch.from_numpy(v) for k, v in synth.with_alias_keys(w).items()}
+    missing, unexpected = model.load_state_dict(sd, strict=True)
+    assert not missing and not unexpected
+    return model.eval()
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
