@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""Headline benchmark: enhanced audio-seconds per wall-second of the CRN_ELU streaming path (BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--streams B] [--precision fp32|tf32]
+
+A step advances every concurrent stream by one 3200-sample chunk at hop 1600 (0.1 s of new audio per stream):
+STFT -> features -> preconv/encoder -> GRU -> decoder -> cIRM mask -> iSTFT -> overlap-add, with the per-stream causal
+state carried in HBM.  Workload = BASELINE.json configs[1]: teacher CRN_ELU, 1024 concurrent synthetic streams per GPU.
+Streams are independent, so N GPUs run N x 1024 streams with no data-path collective ("weak" scaling); NCCL is used
+only to take the max of the device time over ranks.
+
+`--impl reference` times the reference algorithm's CPU restatement (oracle/, torch CPU ops = the kernels the reference
+runs in predict.py:48) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "enhanced audio-sec/sec (CRN_ELU streaming)"
+UNIT = "audio-s/s"
+RING = 16  # distinct hops of input per stream kept in HBM (input ring 1024*3*27200*4 B = 334 MB > 126 MB L2)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--streams", type=int, default=1024, help="concurrent streams per GPU")
+    ap.add_argument("--precision", default=os.environ.get("SE_B200_PRECISION", "fp32"))
+    ap.add_argument("--model", default="teacher", choices=["teacher", "student"])
+    ap.add_argument("--cpu-streams", type=int, default=16, help="streams in the CPU baseline sample")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(int(float(s[0])))
+                mx = max(mx, int(float(s[1])))
+                for n, v in zip(names, s[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic input
+# ----------------------------------------------------------------------------------------------------------------
+def synthetic_signal(n_streams, n_samples):
+    """[n_streams, 3, n_samples] float32 noisy 3-mic streams: 32 base mixtures from synth, tiled with per-stream gains."""
+    import numpy as np
+    from speech_enhancement_mi_b200 import synth
+    base, _ = synth.make_mixture(min(n_streams, 32), n_samples)
+    reps = (n_streams + base.shape[0] - 1) // base.shape[0]
+    sig = np.tile(base, (reps, 1, 1))[:n_streams].copy()
+    gains = 0.5 + 0.5 * synth.uniform01(2021, n_streams, stream=7).astype(np.float32)
+    sig *= gains[:, None, None]
+    return sig
+
+
+def build_model(args, max_streams):
+    import torch
+    from speech_enhancement_mi_b200 import CRN_ELU, distillation_crn, synth, workload
+    cfg = workload.TEACHER if args.model == "teacher" else workload.STUDENT
+    cls = CRN_ELU.TemporalCRN if args.model == "teacher" else distillation_crn.TemporalCRN
+    model = cls(segment_length=3200, dropout=0.0, precision=args.precision, max_streams=max_streams, **cfg)
+    w = synth.make_crn_weights(seed=0, **cfg)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.with_alias_keys(w).items()}, strict=True)
+    return model.eval(), cfg
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU baseline (oracle port) -- the only place bench.py touches oracle/
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_baseline(args, n_streams, budget_s, min_steps=3):
+    import torch
+    from oracle.crn_oracle import CRNOracle  # checker / baseline only
+    from speech_enhancement_mi_b200 import synth, workload
+    cfg = workload.TEACHER if args.model == "teacher" else workload.STUDENT
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = synth.make_crn_weights(seed=0, **cfg)
+    oracle = CRNOracle({k: torch.from_numpy(v) for k, v in w.items()}, segment_length=3200,
+                       student=args.model == "student", **cfg)
+    sig = torch.from_numpy(synthetic_signal(n_streams, (RING + 1) * 1600))
+    carry = None
+    times = []
+    with torch.no_grad():
+        oracle.stream_step(sig[:, :, :3200], None)  # warm-up (thread pool, allocator)
+        oracle.reset()
+        t_start = time.perf_counter()
+        n = 0
+        while True:
+            off = (n % RING) * 1600
+            t0 = time.perf_counter()
+            _, carry = oracle.stream_step(sig[:, :, off:off + 3200], carry)
+            times.append(time.perf_counter() - t0)
+            n += 1
+            if n >= min_steps and time.perf_counter() - t_start > budget_s:
+                break
+    mean = sum(times) / len(times)
+    return {"value": n_streams * workload.AUDIO_SEC_PER_STEP / mean, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_streams} of the workload's streams x {len(times)} chunk steps, teacher fp32, torch CPU ops "
+                      f"with {cores} threads (oracle/crn_oracle.py stream_step)",
+            "ms_per_step": mean * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from speech_enhancement_mi_b200 import workload
+    n = args.cpu_streams
+    # warm-up + exactly K timed steps of the bounded sample
+    import torch
+    from oracle.crn_oracle import CRNOracle
+    from speech_enhancement_mi_b200 import synth
+    cfg = workload.TEACHER if args.model == "teacher" else workload.STUDENT
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w = synth.make_crn_weights(seed=0, **cfg)
+    oracle = CRNOracle({k: torch.from_numpy(v) for k, v in w.items()}, segment_length=3200,
+                       student=args.model == "student", **cfg)
+    sig = torch.from_numpy(synthetic_signal(n, (RING + 1) * 1600))
+    carry = None
+    steps = min(args.steps, 40)
+    with torch.no_grad():
+        for i in range(max(args.warmup, 1)):
+            off = (i % RING) * 1600
+            _, carry = oracle.stream_step(sig[:, :, off:off + 3200], carry)
+        t0 = time.perf_counter()
+        for i in range(steps):
+            off = (i % RING) * 1600
+            _, carry = oracle.stream_step(sig[:, :, off:off + 3200], carry)
+        dt = time.perf_counter() - t0
+    ms = dt / steps * 1e3
+    value = n * workload.AUDIO_SEC_PER_STEP / (dt / steps)
+    sample = (f"{n} of the {args.streams} streams per step, {steps} steps, torch CPU ops with {cores} threads "
+              f"(oracle/crn_oracle.py, restating CRN_ELU.py:367-509)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"CRN_ELU {args.model} batched streaming inference, {args.streams} concurrent "
+                               f"synthetic streams per GPU, 3200-sample chunks at hop 1600", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+    from speech_enhancement_mi_b200 import workload
+    from speech_enhancement_mi_b200._native import check, lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200 (no CPU fallback); use --impl reference for the CPU baseline")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.streams
+    model, cfg = build_model(args, B)
+    sig_host = synthetic_signal(B, (RING + 1) * 1600)
+    sig = torch.from_numpy(sig_host).to(dev)
+    out = torch.empty((B, 1600), dtype=torch.float32, device=dev)
+
+    def chunk_view(i):
+        off = (i % RING) * 1600
+        return sig[:, :, off:off + 3200]  # strided view: the kernel reads it in place
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K, W = args.steps, max(args.warmup, 3)
+    for i in range(W):
+        model.process_chunk(chunk_view(i), out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    barrier()
+    events[0].record()
+    for k in range(K):
+        model.process_chunk(chunk_view(W + k), out)
+        events[k + 1].record()
+    barrier()
+    total_ms = events[0].elapsed_time(events[K])
+    lat = sorted(events[k].elapsed_time(events[k + 1]) for k in range(K))
+    clocks = sampler.stop()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = world * B * workload.AUDIO_SEC_PER_STEP / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed region ------------
+    e2e = None
+    if not args.no_e2e:
+        host_in = [torch.from_numpy(sig_host[:, :, (i % RING) * 1600:(i % RING) * 1600 + 3200].copy()).pin_memory()
+                   for i in range(4)]
+        host_out = torch.empty((B, 1600), dtype=torch.float32).pin_memory()
+        dchunk = torch.empty((B, 3, 3200), dtype=torch.float32, device=dev)
+        model.reset()
+
+        def e2e_step(i):
+            dchunk.copy_(host_in[i % 4], non_blocking=True)
+            model.process_chunk(dchunk, out)
+            host_out.copy_(out, non_blocking=True)
+
+        for i in range(W):
+            e2e_step(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(K):
+            e2e_step(i)
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * workload.AUDIO_SEC_PER_STEP / (float(te.item()) / K * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": B * 3 * 3200 * 4, "d2h_bytes_per_step": B * 1600 * 4,
+               "ms_per_step": float(te.item()) / K}
+
+    # ---- per-stage device times (CUDA events inside the library, on the launching stream) and rooflines -------------
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            mp = json.load(f)
+        peaks.update({k: mp[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in mp})
+        peaks["src"] = "measured"
+    except Exception:
+        pass
+    stages = {}
+    roofline = None
+    if rank == 0:
+        fl = workload.algorithmic_flops(**cfg)
+        by = workload.algorithmic_bytes()
+        for st in ("stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"):
+            ms = C.c_float(0)
+            check(lib().se_crn_time_stage(model._ctx, st.encode(), B, 5, C.byref(ms)), "se_crn_time_stage")
+            stages[st] = {"ms": ms.value}
+        model.reset()
+        tot = sum(s["ms"] for s in stages.values())
+        for st, s in stages.items():
+            s["share"] = s["ms"] / tot
+            if st in by:
+                a = by[st] * B / (s["ms"] * 1e-3) / 1e9
+                s.update(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"])
+            elif st in fl:
+                a = fl[st] * B / (s["ms"] * 1e-3) / 1e12
+                s.update(bound="tensor", achieved=a, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
+                         frac=a / peaks["bf16_tflops_sustained"])
+        top = max((s for s in stages if "bound" in stages[s]), key=lambda s: stages[s]["ms"])
+        roofline = {"kernel": top, "bound": stages[top]["bound"], "achieved": stages[top]["achieved"],
+                    "peak": stages[top]["peak"], "unit": stages[top]["unit"], "frac": stages[top]["frac"],
+                    "traffic": None, "peak_source": peaks["src"] + " (sustained bf16)" if stages[top]["bound"] == "tensor"
+                    else peaks["src"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, args.cpu_streams, args.cpu_seconds)
+
+    if rank == 0:
+        launches = lib().se_crn_launches_per_chunk(model._ctx) + 1  # + the io-descriptor kernel
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+            "config": {"workload": f"CRN_ELU {args.model} batched streaming inference, {B} concurrent synthetic "
+                                   f"streams per GPU, 3200-sample chunks at hop 1600 (BASELINE.json configs[1])",
+                       "streams_per_gpu": B, "precision": args.precision,
+                       "l2": f"inputs larger than L2: {RING}-hop input ring of {sig.numel() * 4 / 1e6:.0f} MB and a "
+                             f"per-step working set of several GB, both > 126 MB L2"},
+            "p99_chunk_latency_ms": lat[min(K - 1, int(0.99 * K))], "p50_chunk_latency_ms": lat[K // 2],
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * K, "roofline": roofline, "stages": stages,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
