@@ -10,6 +10,7 @@
 // hidden sequences and the K/2 overlap-add carry; "roll" moves the trailing frames to the front after each chunk.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -121,6 +122,8 @@ struct se_ctx {
 
     IoDesc* io_dev = nullptr;
     bool use_graph = true;
+    bool tf32 = false;
+    unsigned tc_mask = 0xffffffffu;  // SE_B200_TC_MASK: bit per Stage that may use the tensor-core GEMM (debug)
     std::map<int, cudaGraphExec_t> graphs;  // keyed by B
     cudaStream_t own_stream = nullptr;
 
@@ -556,6 +559,8 @@ int build_ctx(se_ctx* c) {
     c->C0 = 2 * g.num_inputs - 1;
     c->student = g.variant == SE_VARIANT_DISTILLED;
     c->H = g.hidden;
+    c->tf32 = g.precision == SE_PRECISION_TF32;
+    if (const char* e = getenv("SE_B200_TC_MASK")) c->tc_mask = (unsigned)strtoul(e, nullptr, 0);
     for (int i = 0; i < c->L; ++i)
         SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
     int F = NBIN;
@@ -689,15 +694,35 @@ int build_ctx(se_ctx* c) {
         }
         const int k_off = b.koff_dense(H);
         PackedW pw = reserve_packed(c, 3 * H, H);
+        const bool fused = c->tf32 && ((c->tc_mask >> ST_GRU) & 1u) && H % 32 == 0;
         c->packers.push_back([=](const HostParams& hp, float* arena) {
             const std::vector<float>& w = hp.at("gru.sequence_model.weight_hh_l" + s);
             const std::vector<float>& bh = hp.at("gru.sequence_model.bias_hh_l" + s);
             for (int n = 0; n < 3 * H; ++n) {
-                for (int k = 0; k < H; ++k) arena[pw.w_off + (size_t)n * H + k] = w[(size_t)n * H + k];
-                arena[pw.b_off + n] = bh[n];
+                // fused tensor-core cell: tile y holds [r | z | n] of hidden units 32y .. 32y+31 (gemm_tc.cu EPI_GRU)
+                const int src = fused ? ((n % 96) / 32) * H + (n / 96) * 32 + n % 32 : n;
+                for (int k = 0; k < H; ++k) arena[pw.w_off + (size_t)n * H + k] = w[(size_t)src * H + k];
+                arena[pw.b_off + n] = bh[src];
             }
         });
-        for (int t = 0; t < T; ++t) {
+        for (int t = 0; t < T && fused; ++t) {
+            GemmParams gp{};
+            gp.A = c->hseq[l] + (long long)t * H;
+            gp.sB = (long long)(T + 1) * H;
+            gp.Tn = 1;
+            gp.Fo = 1;
+            fill_gemm_common(c, gp, pw, 3 * H, k_off);
+            gp.epi = EPI_GRU;
+            gp.out = c->hseq[l] + (long long)(t + 1) * H;
+            gp.oB = (long long)(T + 1) * H;
+            gp.gi = c->gi + (long long)t * 3 * H;
+            gp.giB = (long long)T * 3 * H;
+            gp.hprev = c->hseq[l] + (long long)t * H;
+            gp.hB = (long long)(T + 1) * H;
+            gp.H = H;
+            b.push_gemm(ST_GRU, gp, 1, pw, k_off);
+        }
+        for (int t = 0; t < T && !fused; ++t) {
             GemmParams gp{};
             gp.A = c->hseq[l] + (long long)t * H;
             gp.sB = (long long)(T + 1) * H;
@@ -832,11 +857,13 @@ int build_ctx(se_ctx* c) {
     return 0;
 }
 
-int launch_op(const Op& op, int B, cudaStream_t st) {
+int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st) {
     switch (op.kind) {
         case OP_GEMM: {
             GemmParams g = op.g;
             g.M = B * op.rows_per_stream;
+            if (g.epi == EPI_GRU) return launch_gemm_tf32(g, st);
+            if (c->tf32 && ((c->tc_mask >> op.stage) & 1u) && gemm_tf32_supported(g)) return launch_gemm_tf32(g, st);
             return launch_gemm_fp32(g, st);
         }
         case OP_NORM: {
@@ -854,7 +881,7 @@ int launch_op(const Op& op, int B, cudaStream_t st) {
 int enqueue_net(se_ctx* c, int B, cudaStream_t st, int stage_filter) {
     for (const Op& op : c->ops) {
         if (stage_filter >= 0 && op.stage != stage_filter) continue;
-        if (launch_op(op, B, st)) return 1;
+        if (launch_op(c, op, B, st)) return 1;
     }
     return 0;
 }

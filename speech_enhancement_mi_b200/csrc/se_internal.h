@@ -71,6 +71,7 @@ struct GemmParams {
 
 int launch_gemm_fp32(const GemmParams& p, cudaStream_t st);
 int launch_gemm_tf32(const GemmParams& p, cudaStream_t st);  // tcgen05 path (gemm_tc.cu)
+bool gemm_tf32_supported(const GemmParams& p);
 
 // ---------------------------------------------------------------------------------------------------------------
 // GlobalLayerNorm application (CRN_ELU.py:37-56), fused with what follows it in the graph
