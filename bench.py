@@ -38,7 +38,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=1024, help="concurrent streams per GPU")
-    ap.add_argument("--precision", default=os.environ.get("SE_B200_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("SE_B200_PRECISION", "tf32"))
     ap.add_argument("--model", default="teacher", choices=["teacher", "student"])
     ap.add_argument("--cpu-streams", type=int, default=16, help="streams in the CPU baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of the cpu_baseline leg")

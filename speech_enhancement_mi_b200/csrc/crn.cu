@@ -247,6 +247,7 @@ struct OpFix {
     size_t w_off, b_off;
     int k_off;
     size_t nw_off, nb_off, nwr_off, nbr_off;  // norm affine offsets (SIZE_MAX = unused)
+    size_t w2_off = (size_t)-1, b2_off = (size_t)-1;  // fused gate weights of EPI_ELU_GATE
 };
 
 namespace {
@@ -264,15 +265,17 @@ struct Builder {
         return c->reserve_k(v);
     }
 
-    void push_gemm(int stage, GemmParams g, int rows_per_stream, const PackedW& pw, int k_off) {
+    void push_gemm(int stage, GemmParams g, int rows_per_stream, const PackedW& pw, int k_off, size_t w2_off = NONE,
+                   size_t b2_off = NONE) {
         Op op{};
         op.kind = OP_GEMM;
         op.stage = stage;
         op.g = g;
         op.rows_per_stream = rows_per_stream;
         c->ops.push_back(op);
-        fix.push_back({pw.w_off, pw.b_off, k_off, NONE, NONE, NONE, NONE});
+        fix.push_back({pw.w_off, pw.b_off, k_off, NONE, NONE, NONE, NONE, w2_off, b2_off});
     }
+    bool tc_stage(int stage) const { return c->tf32 && ((c->tc_mask >> stage) & 1u); }
     void push_norm(int stage, NormApplyParams n, size_t w_off, size_t b_off, size_t wr_off = NONE,
                    size_t br_off = NONE) {
         Op op{};
@@ -316,7 +319,9 @@ struct Builder {
         const int Cp_in = in.C;
         const int Cp_out = round_up(Cout_real, 4);
         const int rows = T * Fo;
-        // (1) conv + ELU -> tmp_e [B][T][Fo][Cp_out]
+        const bool fuse_gate = tc_stage(stage) && Cp_out <= 16;
+        double* stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
+        // (1) conv + ELU -> tmp_e [B][T][Fo][Cp_out]   (fuse_gate: + gated 1x1 pair + statistics -> tmp_y, skipping 2)
         {
             const int K = KT * KF * Cp_in;
             std::vector<int> koff(K / 4);
@@ -339,6 +344,25 @@ struct Builder {
                     arena[pw.b_off + n] = b[n];
                 }
             });
+            size_t w2_off = NONE, b2_off = NONE;
+            if (fuse_gate) {
+                w2_off = c->reserve_w((size_t)2 * Cout_real * 16);
+                b2_off = c->reserve_w((size_t)2 * Cout_real);
+                c->packers.push_back([=](const HostParams& hp, float* arena) {
+                    const std::vector<float>& wt = hp.at(name + ".conv_trans.weight");
+                    const std::vector<float>& bt = hp.at(name + ".conv_trans.bias");
+                    const std::vector<float>& wg = hp.at(name + ".conv_gated.weight");
+                    const std::vector<float>& bg = hp.at(name + ".conv_gated.bias");
+                    for (int co = 0; co < Cout_real; ++co) {
+                        for (int ci = 0; ci < Cout_real; ++ci) {
+                            arena[w2_off + (size_t)(2 * co) * 16 + ci] = wt[co * Cout_real + ci];
+                            arena[w2_off + (size_t)(2 * co + 1) * 16 + ci] = wg[co * Cout_real + ci];
+                        }
+                        arena[b2_off + 2 * co] = bt[co];
+                        arena[b2_off + 2 * co + 1] = bg[co];
+                    }
+                });
+            }
             GemmParams g{};
             g.A = in.base;
             g.sB = in.sB;
@@ -347,15 +371,20 @@ struct Builder {
             g.Tn = T;
             g.Fo = Fo;
             fill_gemm_common(c, g, pw, Cout_real, k_off);
-            g.epi = EPI_ELU;
-            g.out = c->tmp_e;
+            g.epi = fuse_gate ? EPI_ELU_GATE : EPI_ELU;
+            g.out = fuse_gate ? c->tmp_y : c->tmp_e;
             g.oB = (long long)rows * Cp_out;
             g.oT = (long long)Fo * Cp_out;
             g.oF = Cp_out;
-            push_gemm(stage, g, rows, pw, k_off);
+            g.vec4 = 1;
+            if (fuse_gate) {
+                g.C2 = Cout_real;
+                g.stats = stats;
+            }
+            push_gemm(stage, g, rows, pw, k_off, w2_off, b2_off);
         }
         // (2) gated 1x1 pair + statistics -> tmp_y [B][T][Fo][Cp_out]
-        {
+        if (!fuse_gate) {
             const int K = Cp_out;
             const int k_off = koff_dense(K);
             PackedW pw = reserve_packed(c, 2 * Cout_real, K);
@@ -386,7 +415,8 @@ struct Builder {
             g.oB = g.sB;
             g.oT = g.sT;
             g.oF = g.sF;
-            g.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
+            g.vec4 = 1;
+            g.stats = stats;
             push_gemm(stage, g, rows, pw, k_off);
         }
         // (3) GlobalLayerNorm (+ residual) -> destination
@@ -470,6 +500,7 @@ struct Builder {
             g.oT = (long long)Fy * Cop;
             g.oF = 2 * Cop;
             g.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
+            g.vec4 = Cop % 4 == 0;
             push_gemm(ST_DECODER, g, T * Fo, pw, k_off);
         }
         if (!skip) return;
@@ -511,6 +542,7 @@ struct Builder {
             g.o2T = g.oT;
             g.o2F = g.oF;
             g.stats = c->stats + (size_t)stats_slot_r * 2 * c->maxB;
+            g.vec4 = 1;
             push_gemm(ST_DECODER, g, rows, pw, k_off);
         }
         {
@@ -690,6 +722,7 @@ int build_ctx(se_ctx* c) {
             gp.oB = (long long)T * 3 * H;
             gp.oT = 3 * H;
             gp.oF = 0;
+            gp.vec4 = 1;
             b.push_gemm(ST_GRU, gp, T, pw, k_off);
         }
         const int k_off = b.koff_dense(H);
@@ -767,6 +800,7 @@ int build_ctx(se_ctx* c) {
         gp.oT = feat;
         gp.oF = 0;
         gp.stats = c->stats + (size_t)gru_slot * 2 * maxB;
+        gp.vec4 = 1;
         b.push_gemm(ST_GRU, gp, T, pw, k_off);
 
         const Act& nx = c->dec_in[0];
@@ -828,6 +862,10 @@ int build_ctx(se_ctx* c) {
             op.g.W = c->warena + f.w_off;
             op.g.bias = c->warena + f.b_off;
             op.g.koff = c->karena + f.k_off;
+            if (f.w2_off != NONE) {
+                op.g.W2 = c->warena + f.w2_off;
+                op.g.bias2 = c->warena + f.b2_off;
+            }
         } else if (op.kind == OP_NORM) {
             op.n.w = c->warena + f.nw_off;
             op.n.b = c->warena + f.nb_off;
@@ -862,7 +900,7 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st) {
         case OP_GEMM: {
             GemmParams g = op.g;
             g.M = B * op.rows_per_stream;
-            if (g.epi == EPI_GRU) return launch_gemm_tf32(g, st);
+            if (g.epi == EPI_GRU || g.epi == EPI_ELU_GATE) return launch_gemm_tf32(g, st);
             if (c->tf32 && ((c->tc_mask >> op.stage) & 1u) && gemm_tf32_supported(g)) return launch_gemm_tf32(g, st);
             return launch_gemm_fp32(g, st);
         }

@@ -3,11 +3,13 @@
 // table (implicit im2col over zero-bordered channels-last activations) -- plus the fused GRU cell epilogue.
 //
 // One CTA computes a 128 x BN tile:
-//   warps 0-3 : producers.  Thread r owns tile row r: per 32-float k-block it issues 8 x 16-byte cp.async gathers into
-//               the canonical K-major SWIZZLE_128B layout (row r at (r/8)*1024 + (r%8)*128, 16-byte chunk j stored at
-//               j ^ (r%8)) and the same for its share of the weight rows, then arrives on the stage's "full" mbarrier
-//               through cp.async.mbarrier.arrive.noinc.  After the k loop the same threads run the epilogue: thread r
-//               reads accumulator row r from TMEM (tcgen05.ld 32x32b) and writes its N outputs channels-last.
+//   warps 0-3 : producers.  Per 32-float k-block, 8 consecutive lanes issue the 8 x 16-byte cp.async gathers of one
+//               128-byte tile row (a warp instruction touches 4 rows = 4 cache lines) into the canonical K-major
+//               SWIZZLE_128B layout (row r at (r/8)*1024 + (r%8)*128, 16-byte chunk j stored at j ^ (r%8)), the same
+//               for the weight rows, then arrive on the stage's "full" mbarrier through
+//               cp.async.mbarrier.arrive.noinc.  After the k loop the same threads run the epilogue: thread r reads
+//               accumulator row r from TMEM (tcgen05.ld 32x32b), applies the epilogue function and parks the row in
+//               the idle pipeline stages; each warp then writes its 32 rows out with coalesced 16-byte stores.
 //   warp 4    : allocates TMEM; lane 0 issues the tcgen05.mma chain (4 MMAs of K=8 per k-block), commits each stage
 //               to its "empty" mbarrier and the last one to the accumulator barrier.
 // Every mbarrier wait is bounded (trap after ~2 s) so that a protocol bug cannot hang the GPU.
@@ -103,47 +105,90 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 __device__ __forceinline__ float elu1(float x) { return x > 0.f ? x : expm1f(x); }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// accumulate (s, ss) of one tile row group into the per-stream statistics with as few atomics as possible
+// per-stream (sum, sum of squares) of the rows a warp owns: rows are ordered by stream, so the warp holds a short
+// monotone run of stream indices; one shuffle reduction and one pair of double atomics per distinct stream
 __device__ __forceinline__ void stats_commit(double* stats, int b, float s, float ss) {
     const unsigned full = 0xffffffffu;
-    const int b0 = __shfl_sync(full, b, 0);
-    const bool uniform = __all_sync(full, b == b0);
-    if (uniform) {
-        if (b0 < 0) return;
+    int lo = b < 0 ? 0x7fffffff : b, hi = b;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(full, lo, off));
+        hi = max(hi, __shfl_xor_sync(full, hi, off));
+    }
+    for (int bb = lo; bb <= hi; ++bb) {  // hi < 0 (no valid row): lo = INT_MAX, loop does not run
+        float a = b == bb ? s : 0.f, c = b == bb ? ss : 0.f;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
-            s += __shfl_xor_sync(full, s, off);
-            ss += __shfl_xor_sync(full, ss, off);
+            a += __shfl_xor_sync(full, a, off);
+            c += __shfl_xor_sync(full, c, off);
         }
         if ((threadIdx.x & 31) == 0) {
-            atomicAdd(stats + 2 * b0, (double)s);
-            atomicAdd(stats + 2 * b0 + 1, (double)ss);
+            atomicAdd(stats + 2 * bb, (double)a);
+            atomicAdd(stats + 2 * bb + 1, (double)c);
         }
-    } else if (b >= 0) {
-        atomicAdd(stats + 2 * b, (double)s);
-        atomicAdd(stats + 2 * b + 1, (double)ss);
     }
 }
+
+constexpr int kW2Floats = 32 * 16 + 32;  // fused small gate: W2 [2*C2][16] + bias2 [2*C2], C2 <= 16
 
 template <int BN, int STAGES>
 struct TcSmem {
     static constexpr int B_STAGE_BYTES = BN * BK * 4;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int SP = BN + 4;     // pitch (floats) of the epilogue staging rows
     static constexpr int KOFF_MAX = 512;  // K <= 2048
-    static constexpr int BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + KOFF_MAX * 4 + 256;
+    static constexpr int OFF_KOFF = TILE_BYTES;
+    static constexpr int OFF_BAR = OFF_KOFF + KOFF_MAX * 4;
+    static constexpr int OFF_TMEM = OFF_BAR + (2 * STAGES + 1) * 8;
+    static constexpr int OFF_AOFF = OFF_TMEM + 8;             // long long [BM] gather base offset of a row (-1: none)
+    static constexpr int OFF_OOFF = OFF_AOFF + BM * 8;        // long long [BM] output offset of a row (-1: none)
+    static constexpr int OFF_W2 = OFF_OOFF + BM * 8;          // float [kW2Floats]
+    static constexpr int BYTES = 1024 /*align slack*/ + OFF_W2 + kW2Floats * 4;
+    static_assert(BM * SP * 4 <= TILE_BYTES, "epilogue staging must fit in the pipeline stages");
+    static_assert(STAGE_BYTES % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
 };
+
+// coalesced write-out of the 32 staging rows a warp owns: consecutive lanes write consecutive float4 of a row
+template <int C4, int SP>
+__device__ __forceinline__ void store_rows(const float* stg, int col0, const long long* s_ooff, float* out, int cnt,
+                                           bool vec4, int warp, int lane) {
+    if (vec4) {
+        const int cnt4 = (cnt + 3) >> 2;
+#pragma unroll 4
+        for (int i = lane; i < 32 * C4; i += 32) {
+            const int r = warp * 32 + i / C4;
+            const int c4 = i % C4;
+            const long long off = s_ooff[r];
+            if (off >= 0 && c4 < cnt4)
+                *reinterpret_cast<float4*>(out + off + 4 * c4) =
+                    *reinterpret_cast<const float4*>(stg + r * SP + col0 + 4 * c4);
+        }
+    } else {
+        for (int i = lane; i < 32 * C4 * 4; i += 32) {
+            const int r = warp * 32 + i / (C4 * 4);
+            const int c = i % (C4 * 4);
+            const long long off = s_ooff[r];
+            if (off >= 0 && c < cnt) out[off + c] = stg[r * SP + col0 + c];
+        }
+    }
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(GemmParams p) {
     using S = TcSmem<BN, STAGES>;
+    constexpr int SP = S::SP;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
     unsigned char* tiles_ptr = smem_raw + (tiles - raw);
-    int* s_koff = reinterpret_cast<int*>(tiles_ptr + STAGES * S::STAGE_BYTES);
-    uint64_t* s_bar = reinterpret_cast<uint64_t*>(tiles_ptr + STAGES * S::STAGE_BYTES + S::KOFF_MAX * 4);
-    // barriers: [0,STAGES) full, [STAGES,2*STAGES) empty, [2*STAGES] accumulator; then the TMEM base address
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * STAGES + 1);
+    int* s_koff = reinterpret_cast<int*>(tiles_ptr + S::OFF_KOFF);
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(tiles_ptr + S::OFF_BAR);
+    // barriers: [0,STAGES) full, [STAGES,2*STAGES) empty, [2*STAGES] accumulator
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(tiles_ptr + S::OFF_TMEM);
+    long long* s_aoff = reinterpret_cast<long long*>(tiles_ptr + S::OFF_AOFF);
+    long long* s_ooff = reinterpret_cast<long long*>(tiles_ptr + S::OFF_OOFF);
+    float* s_w2 = reinterpret_cast<float*>(tiles_ptr + S::OFF_W2);
     const uint32_t bar0 = smem_u32(s_bar);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
@@ -151,12 +196,35 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(GemmParams p) {
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    const int lane = tid & 31;
     const int m0 = blockIdx.x * BM;
     const int n0 = blockIdx.y * BN;
     const int nkb = (p.K + BK - 1) / BK;
     constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
 
     for (int i = tid; i < p.K / 4; i += kThreads) s_koff[i] = __ldg(p.koff + i);
+    if (BN == 16 && p.epi == EPI_ELU_GATE) {
+        const int nw = 2 * p.C2 * 16;
+        for (int i = tid; i < nw; i += kThreads) s_w2[i] = __ldg(p.W2 + i);
+        for (int i = tid; i < 2 * p.C2; i += kThreads) s_w2[32 * 16 + i] = __ldg(p.bias2 + i);
+    }
+    // row r = tid of the tile: where it gathers from and where it writes to
+    int b = -1;
+    if (tid < BM) {
+        const int m = m0 + tid;
+        long long ao = -1, oo = -1;
+        if (m < p.M) {
+            const int rowsPerStream = p.Tn * p.Fo;
+            b = m / rowsPerStream;
+            const int rr = m - b * rowsPerStream;
+            const int t = rr / p.Fo;
+            const int f = rr - t * p.Fo;
+            ao = b * p.sB + t * p.sT + f * p.sF;
+            oo = b * p.oB + t * p.oT + f * p.oF;
+        }
+        s_aoff[tid] = ao;
+        s_ooff[tid] = oo;
+    }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full_bar(s), kProducerThreads);
@@ -178,167 +246,191 @@ __global__ void __launch_bounds__(kThreads) gemm_tf32_kernel(GemmParams p) {
 
     if (warp < 4) {
         // ============================ producers ============================
-        const int r = tid;  // tile row
-        const int m = m0 + r;
-        const int rowsPerStream = p.Tn * p.Fo;
-        int b = -1, t = 0, f = 0;
-        const float* a_row = p.A;
-        uint32_t a_ok = 0;
-        if (m < p.M) {
-            b = m / rowsPerStream;
-            const int rr = m - b * rowsPerStream;
-            t = rr / p.Fo;
-            f = rr - t * p.Fo;
-            a_row = p.A + b * p.sB + t * p.sT + f * p.sF;
-            a_ok = 16;
+        // 8 consecutive lanes fetch the 8 x 16-byte chunks of one 128-byte tile row (coalesced: a warp instruction
+        // touches 4 rows = 4 lines instead of 32); thread (g = tid/8, j = tid%8) serves rows g, g+16, g+32, ...
+        const int j = tid & 7;
+        const int g = tid >> 3;
+        const uint32_t dst_gj = (uint32_t)((g >> 3) * 1024 + (g & 7) * 128 + ((j ^ (g & 7)) << 4));
+        const float* arow[BM / 16];
+        uint32_t avalid = 0;
+#pragma unroll
+        for (int i = 0; i < BM / 16; ++i) {
+            const long long ao = s_aoff[i * 16 + g];
+            arow[i] = p.A + (ao >= 0 ? ao : 0);
+            avalid |= (ao >= 0 ? 1u : 0u) << i;
         }
-        const uint32_t sw = (uint32_t)(r & 7);
-        const uint32_t a_dst_row = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-        constexpr int B_ROWS_PER_THREAD = (BN + kProducerThreads - 1) / kProducerThreads;
+        constexpr int B_ITERS = BN / 16;
+        const float* wbase = p.W + (long long)(n0 + g) * p.K + 4 * j;
 
         for (int kb = 0; kb < nkb; ++kb) {
             const int s = kb % STAGES;
             mbar_wait(empty_bar(s), ((kb / STAGES) & 1) ^ 1);
-            const uint32_t stage = tiles + (uint32_t)s * S::STAGE_BYTES;
-            const int k0 = kb * BK;
+            const uint32_t stage = tiles + (uint32_t)s * S::STAGE_BYTES + dst_gj;
+            const int k = kb * BK + 4 * j;
+            const bool kin = k < p.K;
+            const int ko = kin ? s_koff[k >> 2] : 0;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int k = k0 + 4 * j;
-                const bool kin = k < p.K;
-                const float* src = kin ? a_row + s_koff[k >> 2] : p.A;
-                cp_async16(stage + a_dst_row + ((j ^ sw) << 4), src, kin ? a_ok : 0u);
-            }
+            for (int i = 0; i < BM / 16; ++i)
+                cp_async16(stage + (uint32_t)i * 2048u, arow[i] + ko, (kin && ((avalid >> i) & 1u)) ? 16u : 0u);
 #pragma unroll
-            for (int i = 0; i < B_ROWS_PER_THREAD; ++i) {
-                const int nl = r + i * kProducerThreads;  // row inside the weight tile
-                if (nl < BN) {
-                    const int n = n0 + nl;
-                    const bool nin = n < p.Npad;
-                    const float* wrow = p.W + (long long)(nin ? n : 0) * p.K;
-                    const uint32_t dst_row =
-                        stage + A_STAGE_BYTES + (uint32_t)((nl >> 3) * 1024 + (nl & 7) * 128);
-                    const uint32_t swb = (uint32_t)(nl & 7);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = k0 + 4 * j;
-                        const bool ok = nin && k < p.K;
-                        cp_async16(dst_row + ((j ^ swb) << 4), ok ? wrow + k : p.W, ok ? 16u : 0u);
-                    }
-                }
+            for (int i = 0; i < B_ITERS; ++i) {
+                const bool ok = kin && (n0 + i * 16 + g) < p.Npad;
+                cp_async16(stage + A_STAGE_BYTES + (uint32_t)i * 2048u,
+                           ok ? wbase + (long long)i * 16 * p.K + kb * BK : p.W, ok ? 16u : 0u);
             }
             cp_async_mbar_arrive_noinc(full_bar(s));
         }
 
         // ============================ epilogue ============================
+        // phase 1: thread r reads accumulator row r from TMEM, applies the epilogue function and parks the result in
+        //          the (now idle) pipeline stages; phase 2: each warp writes its 32 rows out with coalesced stores.
         mbar_wait(acc_bar, 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const bool row_ok = m < p.M;
+        float* stg = reinterpret_cast<float*>(tiles_ptr);
+        float* srow = stg + tid * SP;
+        const bool row_ok = b >= 0;
         float s_acc = 0.f, ss_acc = 0.f;
 
         if (p.epi == EPI_GRU) {
-            // tile columns: [r | z | n] of hidden units j0 .. j0+BN/3
-            constexpr int U = BN / 3;
-            const int j0 = blockIdx.y * U;
-            const float* gi = p.gi + (row_ok ? (long long)m * p.giB : 0);
-            const float* hp = p.hprev + (row_ok ? (long long)m * p.hB : 0);
-            float* ho = p.out + (row_ok ? (long long)m * p.oB : 0);
-            const float* bias = p.bias + (long long)blockIdx.y * BN;
 #pragma unroll 1
-            for (int u0 = 0; u0 < U; u0 += 8) {
-                float ar[8], az[8], an[8];
-                tmem_ld8(trow + u0, ar);
-                tmem_ld8(trow + U + u0, az);
-                tmem_ld8(trow + 2 * U + u0, an);
-                if (row_ok) {
-                    float hn[8];
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + c0, v);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int j = j0 + u0 + i;
-                        const float rg = sigmoidf_(gi[j] + ar[i] + __ldg(bias + u0 + i));
-                        const float zg = sigmoidf_(gi[p.H + j] + az[i] + __ldg(bias + U + u0 + i));
-                        const float ng = tanhf(gi[2 * p.H + j] + rg * (an[i] + __ldg(bias + 2 * U + u0 + i)));
-                        hn[i] = (1.0f - zg) * ng + zg * hp[j];
+                for (int i = 0; i < 16; i += 4)
+                    *reinterpret_cast<float4*>(srow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+            __syncwarp();
+            // tile columns: [r | z | n] of hidden units j0 .. j0+U; lane = unit, one row per iteration
+            constexpr int U = BN / 3;
+            if (lane < U) {
+                const int ju = blockIdx.y * U + lane;
+                const float* bias = p.bias + (long long)blockIdx.y * BN;
+                const float br = __ldg(bias + lane), bz = __ldg(bias + U + lane), bn = __ldg(bias + 2 * U + lane);
+#pragma unroll 4
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int r = warp * 32 + rr;
+                    const int m = m0 + r;
+                    if (m < p.M) {
+                        const float* gi = p.gi + (long long)m * p.giB;
+                        const float hp = p.hprev[(long long)m * p.hB + ju];
+                        const float* sr = stg + r * SP;
+                        const float rg = sigmoidf_(gi[ju] + sr[lane] + br);
+                        const float zg = sigmoidf_(gi[p.H + ju] + sr[U + lane] + bz);
+                        const float ng = tanhf(gi[2 * p.H + ju] + rg * (sr[2 * U + lane] + bn));
+                        p.out[(long long)m * p.oB + ju] = (1.0f - zg) * ng + zg * hp;
                     }
-                    *reinterpret_cast<float4*>(ho + j0 + u0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    *reinterpret_cast<float4*>(ho + j0 + u0 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
                 }
             }
+        } else if (BN == 16 && p.epi == EPI_ELU_GATE) {
+            // conv + ELU, then the gated 1x1 pair of CRN_ELU.py:240 in registers (C2 <= 16 channels), + statistics
+            float e[16];
+            tmem_ld16(trow, e);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) e[i] = elu1(e[i] + __ldg(p.bias + i));
+            const float* b2 = s_w2 + 32 * 16;
+            float y[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                float a = 0.f, gt = 0.f;
+                if (c < p.C2) {
+                    a = b2[2 * c];
+                    gt = b2[2 * c + 1];
+                    const float4* wa = reinterpret_cast<const float4*>(s_w2 + (2 * c) * 16);
+                    const float4* wg = reinterpret_cast<const float4*>(s_w2 + (2 * c + 1) * 16);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 x = wa[q], z = wg[q];
+                        a += x.x * e[4 * q] + x.y * e[4 * q + 1] + x.z * e[4 * q + 2] + x.w * e[4 * q + 3];
+                        gt += z.x * e[4 * q] + z.y * e[4 * q + 1] + z.z * e[4 * q + 2] + z.w * e[4 * q + 3];
+                    }
+                    a *= sigmoidf_(gt);
+                }
+                y[c] = a;
+                if (row_ok) {
+                    s_acc += a;
+                    ss_acc += a * a;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(srow + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+            __syncwarp();
+            store_rows<4, SP>(stg, 0, s_ooff, p.out, p.C2, p.vec4 != 0, warp, lane);
+            stats_commit(p.stats, b, s_acc, ss_acc);
         } else {
             const bool paired = (p.epi == EPI_GATE_STATS || p.epi == EPI_SKIP);
             const bool want_stats = (p.epi == EPI_ELU_STATS || p.epi == EPI_GATE_STATS || p.epi == EPI_SKIP);
-            float* o = row_ok ? p.out + b * p.oB + t * p.oT + f * p.oF : p.out;
-            float* o2 = (p.epi == EPI_SKIP && row_ok) ? p.out2 + b * p.o2B + t * p.o2T + f * p.o2F : p.out2;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 float v[16];
                 tmem_ld16(trow + c0, v);
                 const int n = n0 + c0;
-                if (row_ok && n < p.N) {
+                if (n < p.Npad) {  // bias is zero beyond N, weight rows beyond N are zero: padded columns come out 0
 #pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n + i);
+                    for (int i = 0; i < 16; ++i) v[i] += __ldg(p.bias + n + i);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+                }
                 if (!paired) {
                     if (p.epi != EPI_BIAS) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) v[i] = elu1(v[i]);
                     }
-                    if (n + 16 <= p.N) {
 #pragma unroll
-                        for (int i = 0; i < 16; i += 4)
-                            *reinterpret_cast<float4*>(o + n + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(srow + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    if (row_ok) {
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             s_acc += v[i];
                             ss_acc += v[i] * v[i];
                         }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (n + i < p.N) {
-                                o[n + i] = v[i];
-                                s_acc += v[i];
-                                ss_acc += v[i] * v[i];
-                            }
                     }
                 } else {
                     float w[8];
-                    const int c = n >> 1;
-                    const int nc = (p.N - n) >> 1;  // valid output channels in this group (>= 1)
                     if (p.epi == EPI_GATE_STATS) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) w[i] = v[2 * i] * sigmoidf_(v[2 * i + 1]);
                     } else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) w[i] = v[2 * i];
+                        const bool live = n < p.N;  // elu(0) = 0 for the padded pairs anyway
+                        float* s2 = srow + BN / 2 + (c0 >> 1);
+                        *reinterpret_cast<float4*>(s2) = make_float4(live ? elu1(v[1]) : 0.f, live ? elu1(v[3]) : 0.f,
+                                                                      live ? elu1(v[5]) : 0.f, live ? elu1(v[7]) : 0.f);
+                        *reinterpret_cast<float4*>(s2 + 4) =
+                            make_float4(live ? elu1(v[9]) : 0.f, live ? elu1(v[11]) : 0.f, live ? elu1(v[13]) : 0.f,
+                                        live ? elu1(v[15]) : 0.f);
                     }
-                    if (nc >= 8) {
-                        *reinterpret_cast<float4*>(o + c) = make_float4(w[0], w[1], w[2], w[3]);
-                        *reinterpret_cast<float4*>(o + c + 4) = make_float4(w[4], w[5], w[6], w[7]);
-                        if (p.epi == EPI_SKIP) {
-                            *reinterpret_cast<float4*>(o2 + c) =
-                                make_float4(elu1(v[1]), elu1(v[3]), elu1(v[5]), elu1(v[7]));
-                            *reinterpret_cast<float4*>(o2 + c + 4) =
-                                make_float4(elu1(v[9]), elu1(v[11]), elu1(v[13]), elu1(v[15]));
-                        }
+                    float* s1 = srow + (c0 >> 1);
+                    *reinterpret_cast<float4*>(s1) = make_float4(w[0], w[1], w[2], w[3]);
+                    *reinterpret_cast<float4*>(s1 + 4) = make_float4(w[4], w[5], w[6], w[7]);
+                    if (row_ok) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             s_acc += w[i];
                             ss_acc += w[i] * w[i];
                         }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i)
-                            if (i < nc) {
-                                o[c + i] = w[i];
-                                if (p.epi == EPI_SKIP) o2[c + i] = elu1(v[2 * i + 1]);
-                                s_acc += w[i];
-                                ss_acc += w[i] * w[i];
-                            }
                     }
                 }
-                }  // row_ok && n < N
             }
-            if (want_stats) stats_commit(p.stats, row_ok ? b : -1, s_acc, ss_acc);
+            __syncwarp();
+            const bool vec4 = p.vec4 != 0;
+            if (!paired) {
+                const int cnt = min(BN, p.N - n0);
+                store_rows<BN / 4, SP>(stg, 0, s_ooff, p.out + n0, cnt, vec4, warp, lane);
+            } else {
+                const int cnt = min(BN / 2, (p.N - n0) >> 1);
+                store_rows<BN / 8, SP>(stg, 0, s_ooff, p.out + (n0 >> 1), cnt, vec4, warp, lane);
+                if (p.epi == EPI_SKIP) {
+                    // out2 shares the row decomposition of out when its strides are equal (the only use: tmp_rm/tmp_rr)
+                    store_rows<BN / 8, SP>(stg, BN / 2, s_ooff, p.out2 + (n0 >> 1), cnt, vec4, warp, lane);
+                }
+            }
+            if (want_stats) stats_commit(p.stats, b, s_acc, ss_acc);
         }
         tc_fence_before();
     } else {
@@ -393,10 +485,12 @@ int launch_tc(const GemmParams& p, cudaStream_t st) {
 }  // namespace
 
 bool gemm_tf32_supported(const GemmParams& p) {
-    if (p.epi == EPI_GRU) return p.H % 32 == 0 && p.K % 4 == 0 && p.K <= 2048;
-    // tiny contractions stay on the CUDA-core kernel: tile set-up would dominate
-    return p.K % 4 == 0 && p.K >= 32 && p.K <= 2048 && p.N >= 8 && (p.oF % 4 == 0) && (p.oT % 4 == 0) &&
-           (p.oB % 4 == 0);
+    if (p.K % 4 != 0 || p.K < 8 || p.K > 2048) return false;
+    if (p.epi == EPI_GRU) return p.H % 32 == 0;
+    if (p.epi == EPI_ELU_GATE) return p.Npad == 16 && p.C2 >= 1 && p.C2 <= 16 && p.W2 && p.bias2;
+    if (p.epi == EPI_SKIP && (p.o2B != p.oB || p.o2T != p.oT || p.o2F != p.oF)) return false;
+    if (p.vec4 && ((p.oF % 4) || (p.oT % 4) || (p.oB % 4))) return false;
+    return p.N >= 1;
 }
 
 int launch_gemm_tf32(const GemmParams& p, cudaStream_t st) {

@@ -43,6 +43,8 @@ enum Epilogue : int {
     EPI_GATE_STATS = 3,  // columns interleaved (trans_c, gated_c): out[c] = (a0+b0)*sigmoid(a1+b1); stats of out
     EPI_SKIP = 4,        // columns interleaved (mask_c, resid_c): out[c] = a0+b0 (stats); out2[c] = elu(a1+b1)
     EPI_GRU = 5,         // TF32 path only: columns per 32-unit group [r|z|n]; fused GRU cell update
+    EPI_ELU_GATE = 6,    // TF32 path only, N <= 16: e = elu(acc + bias), then the gated 1x1 pair of CRN_ELU.py:240 in
+                         // registers: out[c] = (W2[2c].e + b2[2c]) * sigmoid(W2[2c+1].e + b2[2c+1]); stats of out
 };
 
 struct GemmParams {
@@ -67,6 +69,13 @@ struct GemmParams {
     const float* hprev;
     long long hB;
     int H;
+    // EPI_ELU_GATE extras: W2 [2*C2][16] (rows interleaved trans/gated, zero beyond C2 columns), bias2 [2*C2]
+    const float* W2;
+    const float* bias2;
+    int C2;
+    // tf32 path: rows may be written with 16-byte stores up to the next multiple of 4 columns (the destination pitch
+    // is padded and aligned); 0 = element-wise stores of exactly the valid columns
+    int vec4;
 };
 
 int launch_gemm_fp32(const GemmParams& p, cudaStream_t st);
