@@ -136,9 +136,10 @@ struct se_ctx {
         warena_floats += (n + 3) / 4 * 4;
         return off;
     }
-    int reserve_k(const std::vector<int>& v) {
+    int reserve_k(const std::vector<int>& v) {  // padded with offset-0 units to whole 32-float k-blocks (weights there: 0)
         int off = (int)khost.size();
         khost.insert(khost.end(), v.begin(), v.end());
+        while ((khost.size() - off) % 8) khost.push_back(0);
         return off;
     }
 };
@@ -221,11 +222,13 @@ struct PackedW {
     size_t w_off, b_off;
     int Npad, K;
 };
+// Rows are padded to the output-tile width the tensor-core kernel will pick for N (gemm_tf32_tile_n) and the row
+// pitch to whole 32-float k-blocks, all zero-filled, so that the kernels need no bounds checks on the weight operand.
 PackedW reserve_packed(se_ctx* c, int N, int K) {
     PackedW pw;
-    pw.Npad = round_up(N, 16);
-    pw.K = K;
-    pw.w_off = c->reserve_w((size_t)pw.Npad * K);
+    pw.Npad = round_up(N, gemm_tf32_tile_n(N));
+    pw.K = round_up(K, 32);
+    pw.w_off = c->reserve_w((size_t)pw.Npad * pw.K);
     pw.b_off = c->reserve_w(pw.Npad);
     return pw;
 }
@@ -339,7 +342,7 @@ struct Builder {
                     for (int kt = 0; kt < KT; ++kt)
                         for (int kf = 0; kf < KF; ++kf)
                             for (int ci = 0; ci < Cin_real; ++ci)
-                                arena[pw.w_off + (size_t)n * K + (kt * KF + kf) * Cp_in + ci] =
+                                arena[pw.w_off + (size_t)n * pw.K + (kt * KF + kf) * Cp_in + ci] =
                                     w[((n * Cin_real + ci) * KF + kf) * KT + kt];
                     arena[pw.b_off + n] = b[n];
                 }
@@ -395,8 +398,8 @@ struct Builder {
                 const std::vector<float>& bg = hp.at(name + ".conv_gated.bias");
                 for (int co = 0; co < Cout_real; ++co) {
                     for (int ci = 0; ci < Cout_real; ++ci) {
-                        arena[pw.w_off + (size_t)(2 * co) * K + ci] = wt[co * Cout_real + ci];
-                        arena[pw.w_off + (size_t)(2 * co + 1) * K + ci] = wg[co * Cout_real + ci];
+                        arena[pw.w_off + (size_t)(2 * co) * pw.K + ci] = wt[co * Cout_real + ci];
+                        arena[pw.w_off + (size_t)(2 * co + 1) * pw.K + ci] = wg[co * Cout_real + ci];
                     }
                     arena[pw.b_off + 2 * co] = bt[co];
                     arena[pw.b_off + 2 * co + 1] = bg[co];
@@ -480,7 +483,7 @@ struct Builder {
                         for (int j = 0; j < nkf; ++j) {
                             const int kf = 2 * j + parity;
                             for (int ci = 0; ci < Cin; ++ci)
-                                arena[pw.w_off + (size_t)n * K + (kt * nkf + j) * Cin + ci] =
+                                arena[pw.w_off + (size_t)n * pw.K + (kt * nkf + j) * Cin + ci] =
                                     w[((ci * Cout_real + n) * KF + kf) * KT + kt];
                         }
                     arena[pw.b_off + n] = b[n];
@@ -517,8 +520,8 @@ struct Builder {
                 const std::vector<float>& br = hp.at(name + ".residual.bias");
                 for (int co = 0; co < Cout_real; ++co) {
                     for (int ci = 0; ci < Cout_real; ++ci) {
-                        arena[pw.w_off + (size_t)(2 * co) * K + ci] = wm[co * Cout_real + ci];
-                        arena[pw.w_off + (size_t)(2 * co + 1) * K + ci] = wr[co * Cout_real + ci];
+                        arena[pw.w_off + (size_t)(2 * co) * pw.K + ci] = wm[co * Cout_real + ci];
+                        arena[pw.w_off + (size_t)(2 * co + 1) * pw.K + ci] = wr[co * Cout_real + ci];
                     }
                     arena[pw.b_off + 2 * co] = bm[co];
                     arena[pw.b_off + 2 * co + 1] = br[co];
@@ -699,7 +702,7 @@ int build_ctx(se_ctx* c) {
                 const std::vector<float>& bi = hp.at("gru.sequence_model.bias_ih_l" + s);
                 for (int n = 0; n < 3 * H; ++n) {
                     for (int k = 0; k < Kin; ++k)
-                        arena[pw.w_off + (size_t)n * Kin + k] = w[(size_t)n * Kin + (l == 0 ? perm(k) : k)];
+                        arena[pw.w_off + (size_t)n * pw.K + k] = w[(size_t)n * Kin + (l == 0 ? perm(k) : k)];
                     arena[pw.b_off + n] = bi[n];
                 }
             });
@@ -734,7 +737,7 @@ int build_ctx(se_ctx* c) {
             for (int n = 0; n < 3 * H; ++n) {
                 // fused tensor-core cell: tile y holds [r | z | n] of hidden units 32y .. 32y+31 (gemm_tc.cu EPI_GRU)
                 const int src = fused ? ((n % 96) / 32) * H + (n / 96) * 32 + n % 32 : n;
-                for (int k = 0; k < H; ++k) arena[pw.w_off + (size_t)n * H + k] = w[(size_t)src * H + k];
+                for (int k = 0; k < H; ++k) arena[pw.w_off + (size_t)n * pw.K + k] = w[(size_t)src * H + k];
                 arena[pw.b_off + n] = bh[src];
             }
         });
@@ -782,7 +785,7 @@ int build_ctx(se_ctx* c) {
             const std::vector<float>& bb = hp.at("gru.fc_output_layer.bias");
             for (int n = 0; n < feat; ++n) {
                 const int r = perm(n);
-                for (int k = 0; k < H; ++k) arena[pw.w_off + (size_t)n * H + k] = w[(size_t)r * H + k];
+                for (int k = 0; k < H; ++k) arena[pw.w_off + (size_t)n * pw.K + k] = w[(size_t)r * H + k];
                 arena[pw.b_off + n] = bb[r];
             }
         });

@@ -22,26 +22,28 @@ __device__ __forceinline__ void gln_coeffs(const double* stats, int b, double co
     inv = 1.0f / den;
 }
 
-// one thread per 4 channels (C % 4 == 0); grid-stride over B*T*F*C/4
+// grid (T, B): one block per frame of one stream, one thread per 4 channels (C % 4 == 0).  The per-stream
+// coefficients (double arithmetic) are computed once per block, and no 64-bit index division is left per element.
 __global__ void __launch_bounds__(256) norm_apply_kernel(NormApplyParams p) {
+    const int t = blockIdx.x;
+    const int b = p.b0 + blockIdx.y;
+    __shared__ float s_co[4];
+    if (threadIdx.x == 0) {
+        gln_coeffs(p.stats, b, p.count, p.student, s_co[0], s_co[1]);
+        if (p.mode == 2) gln_coeffs(p.stats_r, b, p.count_r, p.student, s_co[2], s_co[3]);
+    }
+    __syncthreads();
+    const float mean = s_co[0], inv = s_co[1];
     const int C4 = p.C >> 2;
-    const long long total = (long long)p.B * p.T * p.F * C4;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        const int c4 = (int)(i % C4);
-        long long r = i / C4;
-        const int f = (int)(r % p.F);
-        r /= p.F;
-        const int t = (int)(r % p.T);
-        const int b = (int)(r / p.T);
-        const int c = c4 * 4;
-
-        float mean, inv;
-        gln_coeffs(p.stats, b, p.count, p.student, mean, inv);
-
+    const int n4 = p.F * C4;
+    const float* yrow = p.y + ((long long)b * p.T + t) * p.Fy * p.C;
+    float* orow = p.out + b * p.oB + t * p.oT;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        const int f = i / C4;
+        const int c = (i - f * C4) * 4;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (f < p.Fy) {
-            const float4 y = *reinterpret_cast<const float4*>(p.y + (((long long)b * p.T + t) * p.Fy + f) * p.C + c);
+            const float4 y = *reinterpret_cast<const float4*>(yrow + f * p.C + c);
             const int wi = p.per_feature ? (f * p.C + c) : c;
             const float4 w = *reinterpret_cast<const float4*>(p.w + wi);
             const float4 bb = *reinterpret_cast<const float4*>(p.b + wi);
@@ -59,8 +61,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(NormApplyParams p) {
             o.z += x.z;
             o.w += x.w;
         } else if (p.mode == 2) {
-            float mr, ir;
-            gln_coeffs(p.stats_r, b, p.count_r, p.student, mr, ir);
+            const float mr = s_co[2], ir = s_co[3];
             const long long ri = (((long long)b * p.T + t) * p.F + f) * p.C + c;
             const float4 rm = *reinterpret_cast<const float4*>(p.rm + ri);
             const float4 rr = *reinterpret_cast<const float4*>(p.rr + ri);
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(NormApplyParams p) {
             o.z = m2 * rr.z + (1.0f - m2) * o.z;
             o.w = m3 * rr.w + (1.0f - m3) * o.w;
         }
-        *reinterpret_cast<float4*>(p.out + b * p.oB + t * p.oT + f * p.oF + c) = o;
+        *reinterpret_cast<float4*>(orow + f * p.oF + c) = o;
     }
 }
 
@@ -159,9 +160,11 @@ inline int grid_for(long long n, int block = 256) {
 
 int launch_norm_apply(const NormApplyParams& p, cudaStream_t st) {
     SE_REQUIRE(p.C % 4 == 0, "norm_apply: C must be a multiple of 4");
-    const long long total = (long long)p.B * p.T * p.F * (p.C / 4);
-    if (total == 0) return 0;
-    norm_apply_kernel<<<grid_for(total), 256, 0, st>>>(p);
+    if (p.B <= 0 || p.T <= 0 || p.F <= 0) return 0;
+    SE_REQUIRE(p.B <= 65535, "norm_apply: at most 65535 streams per launch");
+    const int n4 = p.F * (p.C / 4);
+    const int threads = n4 >= 256 ? 256 : (n4 >= 128 ? 128 : 64);
+    norm_apply_kernel<<<dim3(p.T, p.B), threads, 0, st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -51,6 +51,7 @@ struct GemmParams {
     const float* A;
     long long sB, sT, sF;  // element strides of the row decomposition
     int Tn, Fo, M;
+    int b0;  // first stream of this launch: row m belongs to stream b0 + m / (Tn*Fo)  (tf32 path)
     const int* koff;  // [K/4] element offset of every 4-float unit of a row
     int K;            // multiple of 4 (fp32 path) / padded to a multiple of 32 (tf32 path)
     const float* W;   // [Npad][K] packed weights, rows >= N are zero
@@ -81,6 +82,7 @@ struct GemmParams {
 int launch_gemm_fp32(const GemmParams& p, cudaStream_t st);
 int launch_gemm_tf32(const GemmParams& p, cudaStream_t st);  // tcgen05 path (gemm_tc.cu)
 bool gemm_tf32_supported(const GemmParams& p);
+int gemm_tf32_tile_n(int N);  // output-tile width (BN) the tcgen05 kernel uses for N logical columns
 
 // ---------------------------------------------------------------------------------------------------------------
 // GlobalLayerNorm application (CRN_ELU.py:37-56), fused with what follows it in the graph
@@ -88,6 +90,7 @@ bool gemm_tf32_supported(const GemmParams& p);
 struct NormApplyParams {
     int mode;  // 0: plain, 1: + residual (preconv, CRN_ELU.py:376), 2: gated skip blend (CRN_ELU.py:297-306)
     int B, T, F, C;         // logical extent of the output
+    int b0;                 // first stream of this launch
     int student;            // distillation_crn.py:51 denominator
     const float* y;         // raw (pre-norm) tensor, [B][T][Fy][C] compact; rows f >= Fy read as post-norm 0 (mode 2)
     int Fy;
