@@ -45,7 +45,7 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
     long long per_stream() const { return sB; }
 };
 
-enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW };
+enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV };
 enum Stage { ST_STFT = 0, ST_PRECONV, ST_ENCODER, ST_GRU, ST_DECODER, ST_MASK, ST_ROLL, ST_COUNT };
 const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"};
 
@@ -55,6 +55,7 @@ struct Op {
     GemmParams g;
     int rows_per_stream = 0;
     NormApplyParams n;
+    PreconvParams pc;
     // GRU pointwise
     const float* gi = nullptr;
     long long giB = 0;
@@ -63,6 +64,13 @@ struct Op {
     long long hB = 0;
     float* hout = nullptr;
     int H = 0;
+};
+
+struct PreBuf {  // channel-planar preconv input [maxB][5][25][Fpp] (se_internal.h: PRECONV_FPP)
+    float* base = nullptr;
+    int d = 1, Fpp = 0;
+    long long sB = 0, sC = 0;
+    float* interior() const { return base + 4 * Fpp + 2 * d; }  // frame 4 (first new frame), bin 0
 };
 
 struct ParamInfo {
@@ -97,7 +105,7 @@ struct se_ctx {
     std::vector<void*> allocs;
 
     // activations
-    std::vector<Act> pre_in;  // 3 preconv inputs
+    std::vector<PreBuf> pre_in;  // 3 preconv inputs
     std::vector<Act> enc_in;  // L encoder inputs
     std::vector<Act> dec_in;  // L decoder inputs
     float *xg = nullptr, *gi = nullptr, *gh = nullptr, *hseq[2] = {nullptr, nullptr}, *fcraw = nullptr;
@@ -119,6 +127,7 @@ struct se_ctx {
     std::vector<Op> ops;
     RollTable roll{};
     RollTable zero_tab{};
+    int64_t state_floats = 0;  // carried state per stream (allocated extents, incl. zero borders of the GEMM-path buffers)
 
     IoDesc* io_dev = nullptr;
     bool use_graph = true;
@@ -615,8 +624,12 @@ int build_ctx(se_ctx* c) {
     // ---- activations ------------------------------------------------------------------------------------------
     c->pre_in.resize(3);
     for (int i = 0; i < 3; ++i) {
-        const int d = 1 << i;
-        if (make_act(c, c->pre_in[i], C0p, NBIN, T, 4, 0, 2 * d, 2 * d)) return 1;
+        PreBuf& pb = c->pre_in[i];
+        pb.d = 1 << i;
+        pb.Fpp = PRECONV_FPP(pb.d);
+        pb.sC = (long long)PRECONV_TP * pb.Fpp;
+        pb.sB = 5 * pb.sC;
+        if (dev_alloc(c, &pb.base, (size_t)pb.sB * maxB)) return 1;
     }
     c->enc_in.resize(c->L);
     for (int i = 0; i < c->L; ++i) {
@@ -660,11 +673,56 @@ int build_ctx(se_ctx* c) {
     // ---- program ----------------------------------------------------------------------------------------------
     Builder b{c, {}};
     int slot = 0;
-    for (int i = 0; i < 3; ++i) {
-        const Act& in = c->pre_in[i];
-        const Act& nx = i < 2 ? c->pre_in[i + 1] : c->enc_in[0];
-        b.conv_block(ST_PRECONV, "preconvlist." + std::to_string(i), in, c->C0, c->C0, 5, 5, 1, 1 << i, 1, NBIN,
-                     nx.interior(), nx.sB, nx.sT, nx.sF, true, slot++);
+    for (int i = 0; i < 3; ++i) {  // pre-convolutions: one fused kernel per layer (preconv.cu), exact fp32 in both modes
+        const PreBuf& in = c->pre_in[i];
+        const std::string name = "preconvlist." + std::to_string(i);
+        const size_t w_off = c->reserve_w(PRECONV_W_FLOATS);
+        c->packers.push_back([=](const HostParams& hp, float* arena) {
+            const std::vector<float>& w = hp.at(name + ".conv.weight");  // [Co][Ci][KF][KT]
+            float* a = arena + w_off;
+            for (int kt = 0; kt < 5; ++kt)
+                for (int ci = 0; ci < 5; ++ci)
+                    for (int kf = 0; kf < 5; ++kf)
+                        for (int co = 0; co < 5; ++co)
+                            a[(kt * 5 + ci) * 28 + kf * 5 + co] = w[((co * 5 + ci) * 5 + kf) * 5 + kt];
+            for (int co = 0; co < 5; ++co) {
+                a[PRECONV_W_BIAS + co] = hp.at(name + ".conv.bias")[co];
+                for (int k = 0; k < 5; ++k) {
+                    a[PRECONV_W_WT + co * 5 + k] = hp.at(name + ".conv_trans.weight")[co * 5 + k];
+                    a[PRECONV_W_WG + co * 5 + k] = hp.at(name + ".conv_gated.weight")[co * 5 + k];
+                }
+                a[PRECONV_W_BT + co] = hp.at(name + ".conv_trans.bias")[co];
+                a[PRECONV_W_BG + co] = hp.at(name + ".conv_gated.bias")[co];
+                a[PRECONV_W_NW + co] = hp.at(name + ".norm.weight")[co];
+                a[PRECONV_W_NB + co] = hp.at(name + ".norm.bias")[co];
+            }
+        });
+        Op op{};
+        op.kind = OP_PRECONV;
+        op.stage = ST_PRECONV;
+        op.pc.in = in.base;
+        op.pc.in_sB = in.sB;
+        op.pc.d = in.d;
+        op.pc.student = c->student;
+        if (i < 2) {
+            const PreBuf& nx = c->pre_in[i + 1];
+            op.pc.out = nx.interior();
+            op.pc.oB = nx.sB;
+            op.pc.oC = nx.sC;
+            op.pc.oT = nx.Fpp;
+            op.pc.oF = 1;
+        } else {
+            const Act& nx = c->enc_in[0];
+            op.pc.out = nx.interior();
+            op.pc.oB = nx.sB;
+            op.pc.oC = 1;
+            op.pc.oT = nx.sT;
+            op.pc.oF = nx.sF;
+            op.pc.out_vec8 = 1;
+        }
+        c->ops.push_back(op);
+        b.fix.push_back({NONE, NONE, -1, w_off, NONE, NONE, NONE});
+        slot++;
     }
     for (int i = 0; i < c->L; ++i) {
         const Act& in = c->enc_in[i];
@@ -869,6 +927,8 @@ int build_ctx(se_ctx* c) {
                 op.g.W2 = c->warena + f.w2_off;
                 op.g.bias2 = c->warena + f.b2_off;
             }
+        } else if (op.kind == OP_PRECONV) {
+            op.pc.w = c->warena + f.nw_off;
         } else if (op.kind == OP_NORM) {
             op.n.w = c->warena + f.nw_off;
             op.n.b = c->warena + f.nb_off;
@@ -886,13 +946,19 @@ int build_ctx(se_ctx* c) {
         RollEntry e{base, sB, src, 0, count};
         c->roll.e[c->roll.n++] = e;
         c->zero_tab.e[c->zero_tab.n++] = e;
+        c->state_floats += count;
     };
-    for (const Act& a : c->pre_in) add_state(a.base, a.sB, (long long)T * a.sT, (int)(a.padT0 * a.sT));
+    for (const PreBuf& pb : c->pre_in) {  // rolled by the preconv kernel itself; a reset clears the whole slab
+        RollEntry e{pb.base, pb.sB, 0, 0, (int)pb.sB};
+        c->zero_tab.e[c->zero_tab.n++] = e;
+        c->state_floats += 5 * 4 * NBIN;
+    }
     for (const Act& a : c->enc_in) add_state(a.base, a.sB, (long long)T * a.sT, (int)(a.padT0 * a.sT));
     for (int l = 0; l < 2; ++l) add_state(c->hseq[l], (long long)(T + 1) * H, (long long)T * H, H);
     {
         RollEntry e{c->carry, PHOP, 0, 0, PHOP};
         c->zero_tab.e[c->zero_tab.n++] = e;
+        c->state_floats += PHOP;
     }
     if (init_fft_tables()) return 1;
     return 0;
@@ -911,6 +977,12 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st) {
             NormApplyParams n = op.n;
             n.B = B;
             return launch_norm_apply(n, st);
+        }
+        case OP_PRECONV: {
+            PreconvParams pc = op.pc;
+            pc.b0 = 0;
+            pc.B = B;
+            return launch_preconv(pc, st);
         }
         case OP_GRU_PW:
             return launch_gru_pointwise(op.gi, op.giB, op.gh, op.hprev, op.hB, op.hout, B, op.H, st);
@@ -936,11 +1008,12 @@ int enqueue_stream_step(se_ctx* c, int B, cudaStream_t st, int stage_filter = -1
         sp.B = B;
         sp.M = 3;
         sp.student = c->student;
-        const Act& a = c->pre_in[0];
+        const PreBuf& a = c->pre_in[0];
         sp.feat = a.interior();
         sp.fB = a.sB;
-        sp.fT = a.sT;
-        sp.fF = a.sF;
+        sp.fC = a.sC;
+        sp.fT = a.Fpp;
+        sp.fF = 1;
         sp.noisy = c->noisy;
         if (launch_stft_features(sp, st)) return 1;
     }
@@ -1091,9 +1164,7 @@ int se_crn_state_reset(se_ctx* c, int first, int count, void* stream) {
 
 int64_t se_crn_state_bytes_per_stream(const se_ctx* c) {
     if (!c) return -1;
-    int64_t n = 0;
-    for (int i = 0; i < c->zero_tab.n; ++i) n += c->zero_tab.e[i].count;
-    return n * 4;
+    return c->state_floats * 4;
 }
 
 int se_crn_process_chunk(se_ctx* c, const float* in, int64_t in_stream_stride, int64_t in_mic_stride, float* out,
@@ -1199,8 +1270,8 @@ int se_crn_forward_chunk(se_ctx* c, const float* spec_in, float* spec_out, int B
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     SE_CUDA_OK(cudaMemsetAsync(c->stats, 0, (size_t)c->n_stats * 2 * c->maxB * sizeof(double), st));
-    const Act& a = c->pre_in[0];
-    if (launch_features_from_spec(spec_in, B, 3, c->student, a.interior(), a.sB, a.sT, a.sF, c->noisy, st)) return 1;
+    const PreBuf& a = c->pre_in[0];
+    if (launch_features_from_spec(spec_in, B, 3, c->student, a.interior(), a.sB, a.sC, a.Fpp, 1, c->noisy, st)) return 1;
     if (enqueue_net(c, B, st, -1)) return 1;
     MaskIstftParams mp{};
     mp.B = B;
@@ -1263,8 +1334,22 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
         return (i >= 0 && i < limit) ? i : -1;
     };
     int i;
-    if ((i = idx_of("pre_in", 3)) >= 0) from_act(c->pre_in[i]);
-    else if ((i = idx_of("enc_in", c->L)) >= 0) from_act(c->enc_in[i]);
+    if ((i = idx_of("pre_in", 3)) >= 0) {  // planar -> [T][F][5] on the host
+        const PreBuf& pb = c->pre_in[i];
+        dims[0] = T;
+        dims[1] = NBIN;
+        dims[2] = 5;
+        SE_REQUIRE((int64_t)T * NBIN * 5 <= max_floats, "se_debug_read: destination too small");
+        std::vector<float> slab((size_t)pb.sB);
+        SE_CUDA_OK(cudaMemcpy(slab.data(), pb.base + (long long)b * pb.sB, slab.size() * sizeof(float),
+                              cudaMemcpyDeviceToHost));
+        for (int tt = 0; tt < T; ++tt)
+            for (int ff = 0; ff < NBIN; ++ff)
+                for (int cc = 0; cc < 5; ++cc)
+                    host_dst[((size_t)tt * NBIN + ff) * 5 + cc] =
+                        slab[(size_t)cc * pb.sC + (size_t)(tt + 4) * pb.Fpp + ff + 2 * pb.d];
+        return 0;
+    } else if ((i = idx_of("enc_in", c->L)) >= 0) from_act(c->enc_in[i]);
     else if ((i = idx_of("dec_in", c->L)) >= 0) from_act(c->dec_in[i]);
     else if ((i = idx_of("hseq", 2)) >= 0) compact(c->hseq[i], 1, c->H, T + 1);
     else if (n == "xg") compact(c->xg, c->Fg, c->Cg);

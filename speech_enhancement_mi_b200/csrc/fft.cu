@@ -155,8 +155,11 @@ __global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
                                   : atan2f(v.y, v.x);                   // CRN_ELU.py:370
             }
             float* f = p.feat + b * p.fB + t * p.fT + k * p.fF;
-            *reinterpret_cast<float4*>(f) = make_float4(mag[0], mag[1], mag[2], ph[0] - ph[1]);
-            *reinterpret_cast<float4*>(f + 4) = make_float4(ph[0] - ph[2], 0.f, 0.f, 0.f);
+            f[0] = mag[0];
+            f[p.fC] = mag[1];
+            f[2 * p.fC] = mag[2];
+            f[3 * p.fC] = ph[0] - ph[1];
+            f[4 * p.fC] = ph[0] - ph[2];
             reinterpret_cast<float2*>(p.noisy)[((long long)b * T + t) * NBIN + k] = s.spec[0][fr][k];
         }
     }
@@ -165,7 +168,7 @@ __global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
 // features from a reference-layout spectrum (TemporalCRN.forward entry, CRN_ELU.py:369-373)
 __global__ void __launch_bounds__(256) features_from_spec_kernel(const float* __restrict__ spec, int B, int M,
                                                                  int student, float* __restrict__ feat, long long fB,
-                                                                 long long fT, long long fF,
+                                                                 long long fC, long long fT, long long fF,
                                                                  float* __restrict__ noisy) {
     const long long total = (long long)B * T * NBIN;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -183,8 +186,11 @@ __global__ void __launch_bounds__(256) features_from_spec_kernel(const float* __
             ph[m] = student ? atanf(v.y / (v.x + 1e-8f) + 1e-8f) : atan2f(v.y, v.x);
         }
         float* f = feat + b * fB + t * fT + k * fF;
-        *reinterpret_cast<float4*>(f) = make_float4(mag[0], mag[1], mag[2], ph[0] - ph[1]);
-        *reinterpret_cast<float4*>(f + 4) = make_float4(ph[0] - ph[2], 0.f, 0.f, 0.f);
+        f[0] = mag[0];
+        f[fC] = mag[1];
+        f[2 * fC] = mag[2];
+        f[3 * fC] = ph[0] - ph[1];
+        f[4 * fC] = ph[0] - ph[2];
         reinterpret_cast<float2*>(noisy)[((long long)b * T + t) * NBIN + k] = v0;
     }
 }
@@ -391,14 +397,14 @@ int launch_stft_features(const StftParams& p, cudaStream_t st) {
     return 0;
 }
 
-int launch_features_from_spec(const float* spec, int B, int M, int student, float* feat, long long fB, long long fT,
-                              long long fF, float* noisy, cudaStream_t st) {
+int launch_features_from_spec(const float* spec, int B, int M, int student, float* feat, long long fB, long long fC,
+                              long long fT, long long fF, float* noisy, cudaStream_t st) {
     SE_REQUIRE(M == 3, "features need exactly 3 microphones (CRN_ELU.py:369-373)");
     if (B == 0) return 0;
     const long long total = (long long)B * T * NBIN;
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    features_from_spec_kernel<<<grid, 256, 0, st>>>(spec, B, M, student, feat, fB, fT, fF, noisy);
+    features_from_spec_kernel<<<grid, 256, 0, st>>>(spec, B, M, student, feat, fB, fC, fT, fF, noisy);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }

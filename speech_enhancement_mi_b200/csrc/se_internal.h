@@ -115,6 +115,28 @@ struct NormApplyParams {
 };
 int launch_norm_apply(const NormApplyParams& p, cudaStream_t st);
 
+// ---------------------------------------------------------------------------------------------------------------
+// pre-convolution block (CRN_ELU.py:337-339,375-376), one fused kernel per layer (preconv.cu).  Activations of this
+// chain are channel-planar per stream: [5][25 frames: 4 carried + 21 new][FPP bins: 2d zero | 201 | 2d zero | pad]
+// ---------------------------------------------------------------------------------------------------------------
+#define PRECONV_FPP(D) ((204 + 4 * (D) + 3) / 4 * 4)
+constexpr int PRECONV_TP = kFramesPerChunk + 4;
+// packed weights: conv [(kt*5+ci)*28 + kf*5 + co], then bias, conv_trans, conv_gated, their biases, norm affine
+constexpr int PRECONV_W_BIAS = 700, PRECONV_W_WT = 708, PRECONV_W_WG = 736, PRECONV_W_BT = 764, PRECONV_W_BG = 772,
+              PRECONV_W_NW = 780, PRECONV_W_NB = 788, PRECONV_W_FLOATS = 800;
+struct PreconvParams {
+    float* in;           // planar input of this layer (frames 0..3 are rewritten with the carried state)
+    long long in_sB;
+    int d;               // frequency dilation 1 / 2 / 4
+    const float* w;      // packed weights
+    float* out;          // out(b, c, t, f) = out[b*oB + c*oC + t*oT + f*oF]  (interior of the next layer's input)
+    long long oB, oC, oT, oF;
+    int out_vec8;        // destination is channels-last with 8 channels: two 16-byte stores per position
+    int student;
+    int b0, B;
+};
+int launch_preconv(const PreconvParams& p, cudaStream_t st);
+
 // GRU cell pointwise update for the fp32 path (PyTorch nn.GRU gate order r,z,n; CRN_ELU.py:127-133)
 int launch_gru_pointwise(const float* gi, long long giB, const float* gh, const float* hprev, long long hB,
                          float* hout, int B, int H, cudaStream_t st);
@@ -127,7 +149,7 @@ struct RollEntry {
     int count;  // multiple of 4
 };
 struct RollTable {
-    RollEntry e[16];
+    RollEntry e[24];
     int n;
 };
 int launch_roll(const RollTable& tab, int first, int B, cudaStream_t st);
@@ -149,16 +171,16 @@ struct StftParams {
     const IoDesc* io;  // chunk source
     int B, M;          // streams, microphones (3)
     int student;       // phase formula of distillation_crn.py:340
-    float* feat;       // preconv-0 input buffer interior, channels-last C=8: [b][t][f][c]
-    long long fB, fT, fF;
+    float* feat;       // preconv-0 input buffer interior: feat[b*fB + c*fC + t*fT + f*fF], c < 5
+    long long fB, fC, fT, fF;
     float* noisy;  // mic-0 spectrum [B][T][F][2]
     // optional full spectrum in the reference layout [R][M][F][T][2] (se_stft_trans); feat/noisy may be null
     float* spec_ref;
 };
 int launch_stft_features(const StftParams& p, cudaStream_t st);
 // features from a spectrum in the reference layout [B][M][F][T][2] (for TemporalCRN.forward, CRN_ELU.py:369-373)
-int launch_features_from_spec(const float* spec, int B, int M, int student, float* feat, long long fB, long long fT,
-                              long long fF, float* noisy, cudaStream_t st);
+int launch_features_from_spec(const float* spec, int B, int M, int student, float* feat, long long fB, long long fC,
+                              long long fT, long long fF, float* noisy, cudaStream_t st);
 
 struct MaskIstftParams {
     const IoDesc* io;     // out pointer for the fused streaming path (may be null when out_chunk is set)
