@@ -468,35 +468,40 @@ struct Builder {
         const int Fy = 2 * Fin - 1;
         const int Cop = Cout_real < 4 ? Cout_real : round_up(Cout_real, 4);  // last layer keeps 2 (float2 consumer)
         float* y = skip ? c->tmp_y : c->ylast;
-        for (int parity = 0; parity < 2; ++parity) {
-            const int nkf = parity == 0 ? 3 : 2;
-            const int Fo = parity == 0 ? Fin : Fin - 1;
+        {
+            // Both output parities in one GEMM.  Output bin phi = 2f' (even) uses taps kf = 0,2,4 and phi = 2f'+1 (odd)
+            // taps kf = 1,3, all on the padded input rows f'+2-j (j = kf/2): the odd half re-uses the rows gathered for
+            // the even half.  Columns: [even channels | odd channels] = 2*Cout contiguous floats of y at bin 2f'.  The
+            // odd half of the last row (phi = 2*Fin-1 = Fy) does not exist: GemmParams::odd_tail masks it.
+            const int nkf = 3;
+            const int Fo = Fin;
             const int K = KT * nkf * Cin;
             std::vector<int> koff(K / 4);
             for (int kt = 0; kt < KT; ++kt)
                 for (int j = 0; j < nkf; ++j)
                     for (int c4 = 0; c4 < Cin / 4; ++c4) {
-                        // even rows (phi = 2f'): taps kf = 2j -> padded input row f' + 2 - j
-                        // odd rows (phi = 2f'+1): taps kf = 2j+1 -> padded input row f' + 2 - j
                         const long long frame = (long long)(KT - 1 - kt) * d;
                         koff[((kt * nkf + j) * Cin) / 4 + c4] = (int)(frame * in.sT + (2 - j) * in.sF + 4 * c4);
                     }
             const int k_off = c->reserve_k(koff);
-            PackedW pw = reserve_packed(c, Cout_real, K);
+            PackedW pw = reserve_packed(c, 2 * Cout_real, K);
             const int KF = 5;
             c->packers.push_back([=](const HostParams& hp, float* arena) {
                 const std::vector<float>& w = hp.at(name + ".conv.weight");  // [Ci][Co][KF][KT]
                 const std::vector<float>& b = hp.at(name + ".conv.bias");
-                for (int n = 0; n < Cout_real; ++n) {
-                    for (int kt = 0; kt < KT; ++kt)
-                        for (int j = 0; j < nkf; ++j) {
-                            const int kf = 2 * j + parity;
-                            for (int ci = 0; ci < Cin; ++ci)
-                                arena[pw.w_off + (size_t)n * pw.K + (kt * nkf + j) * Cin + ci] =
-                                    w[((ci * Cout_real + n) * KF + kf) * KT + kt];
-                        }
-                    arena[pw.b_off + n] = b[n];
-                }
+                for (int parity = 0; parity < 2; ++parity)
+                    for (int co = 0; co < Cout_real; ++co) {
+                        const int n = parity * Cout_real + co;
+                        for (int kt = 0; kt < KT; ++kt)
+                            for (int j = 0; j < nkf; ++j) {
+                                const int kf = 2 * j + parity;
+                                if (kf >= KF) continue;  // odd rows have no third tap: weights stay zero
+                                for (int ci = 0; ci < Cin; ++ci)
+                                    arena[pw.w_off + (size_t)n * pw.K + (kt * nkf + j) * Cin + ci] =
+                                        w[((ci * Cout_real + co) * KF + kf) * KT + kt];
+                            }
+                        arena[pw.b_off + n] = b[co];
+                    }
             });
             GemmParams g{};
             g.A = in.base;  // padded row 0, frame 0
@@ -505,12 +510,13 @@ struct Builder {
             g.sF = in.sF;
             g.Tn = T;
             g.Fo = Fo;
-            fill_gemm_common(c, g, pw, Cout_real, k_off);
+            fill_gemm_common(c, g, pw, 2 * Cout_real, k_off);
             g.epi = EPI_ELU_STATS;
-            g.out = y + (parity ? Cop : 0);
+            g.out = y;
             g.oB = (long long)T * Fy * Cop;
             g.oT = (long long)Fy * Cop;
             g.oF = 2 * Cop;
+            g.odd_tail = 1;
             g.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
             g.vec4 = Cop % 4 == 0;
             push_gemm(ST_DECODER, g, T * Fo, pw, k_off);

@@ -124,10 +124,11 @@ __global__ void __launch_bounds__(kThreads) gemm_fp32_kernel(GemmParams p) {
             const int t = r / p.Fo;
             const int f = r - t * p.Fo;
             float* o = p.out + b * p.oB + t * p.oT + f * p.oF;
+            const int nlim = (p.odd_tail && f == p.Fo - 1) ? p.N / 2 : p.N;
             if (!paired) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    if (n + j < p.N) {
+                    if (n + j < nlim) {
                         float v = acc[i][j] + bias[j];
                         if (p.epi != EPI_BIAS) v = elu1(v);
                         o[n + j] = v;

@@ -175,9 +175,10 @@ struct Cfg {
 
 // coalesced write-out of a staged chunk: W columns (8, 16 or 32) of the warp's 32 rows; consecutive lanes write
 // consecutive float4 of a row.  `cnt` = valid columns of the chunk (<= W), `ooff` = this lane's row offset (-1: none)
-template <int W>
+template <int W, bool ROWCNT = false>
 __device__ __forceinline__ void store_chunk(const float* stg, int col0, float* out, long long ooff, int cnt, bool vec4,
                                             int lane) {
+    // ROWCNT: `cnt` is this lane's (= row's) own limit instead of a warp-uniform one
     const unsigned full = 0xffffffffu;
     if (vec4) {
         constexpr int C4 = W / 4;     // float4 per row
@@ -187,7 +188,8 @@ __device__ __forceinline__ void store_chunk(const float* stg, int col0, float* o
         for (int i = 0; i < 32 / RPI; ++i) {
             const int r = i * RPI + lane / C4;
             const long long off = __shfl_sync(full, ooff, r);
-            if (off >= 0 && 4 * c4 < cnt)
+            const int rc = ROWCNT ? __shfl_sync(full, cnt, r) : cnt;
+            if (off >= 0 && 4 * c4 < rc)
                 *reinterpret_cast<float4*>(out + off + 4 * c4) =
                     *reinterpret_cast<const float4*>(stg + r * SPW + col0 + 4 * c4);
         }
@@ -198,7 +200,8 @@ __device__ __forceinline__ void store_chunk(const float* stg, int col0, float* o
         for (int i = 0; i < 32 / RPI; ++i) {
             const int r = i * RPI + lane / W;
             const long long off = __shfl_sync(full, ooff, r);
-            if (off >= 0 && c < cnt) out[off + c] = stg[r * SPW + col0 + c];
+            const int rc = ROWCNT ? __shfl_sync(full, cnt, r) : cnt;
+            if (off >= 0 && c < rc) out[off + c] = stg[r * SPW + col0 + c];
         }
     }
 }
@@ -406,6 +409,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
             const int m = m0 + q * 32 + lane;
             int b = -1;
             long long ooff = -1;
+            int nlim = p.N;  // columns this row owns (merged-parity transposed conv: half of them on the last bin)
             if (m < p.M) {
                 const int bl = m / rowsPerStream;
                 const int rr = m - bl * rowsPerStream;
@@ -413,6 +417,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
                 const int f = rr - t * p.Fo;
                 b = p.b0 + bl;
                 ooff = b * p.oB + t * p.oT + f * p.oF;
+                if (p.odd_tail && f == p.Fo - 1) nlim = p.N >> 1;
             }
             const bool row_ok = b >= 0;
             // this tile's bias row, warp-private (zero beyond Npad)
@@ -532,14 +537,24 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
                         for (int i = 0; i < CH; i += 4)
                             *reinterpret_cast<float4*>(srow + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                         if (want_stats && row_ok) {
+                            if (n + CH <= nlim) {
 #pragma unroll
-                            for (int i = 0; i < CH; ++i) {
-                                s_acc += v[i];
-                                ss_acc += v[i] * v[i];
+                                for (int i = 0; i < CH; ++i) {
+                                    s_acc += v[i];
+                                    ss_acc += v[i] * v[i];
+                                }
+                            } else {  // padded columns are 0 anyway; this only matters for the odd_tail rows
+#pragma unroll
+                                for (int i = 0; i < CH; ++i)
+                                    if (n + i < nlim) {
+                                        s_acc += v[i];
+                                        ss_acc += v[i] * v[i];
+                                    }
                             }
                         }
                         __syncwarp();
-                        store_chunk<CH>(stg, 0, p.out + n, ooff, min(CH, p.N - n), vec4, lane);
+                        if (p.odd_tail) store_chunk<CH, true>(stg, 0, p.out + n, ooff, min(CH, nlim - n), vec4, lane);
+                        else store_chunk<CH>(stg, 0, p.out + n, ooff, min(CH, p.N - n), vec4, lane);
                     } else {
                         constexpr int CO = CH / 2;  // output channels per pass
                         float w[CO];

@@ -77,6 +77,8 @@ struct GemmParams {
     // tf32 path: rows may be written with 16-byte stores up to the next multiple of 4 columns (the destination pitch
     // is padded and aligned); 0 = element-wise stores of exactly the valid columns
     int vec4;
+    // merged-parity transposed conv: rows with f == Fo-1 own only the first N/2 columns (nothing stored / counted beyond)
+    int odd_tail;
 };
 
 int launch_gemm_fp32(const GemmParams& p, cudaStream_t st);
