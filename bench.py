@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="warm up, then run ONE chunk step inside cudaProfilerStart/Stop (for ncu --profile-from-start off) "
+                         "and write the kernel labels of that step to gpurun_out/kernel_labels.json")
     return ap.parse_args()
 
 
@@ -241,6 +244,21 @@ def main():
     for i in range(W):
         model.process_chunk(chunk_view(i), out)
     barrier()
+    if args.profile_step:
+        L = lib()
+        labels = ["set_io"]
+        for i in range(L.se_crn_num_kernels(model._ctx)):
+            name = C.create_string_buffer(96)
+            check(L.se_crn_kernel_info(model._ctx, i, name, 96, None, None, None), "kernel_info")
+            labels.append(name.value.decode())
+        os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(REPO, "gpurun_out", "kernel_labels.json"), "w") as f:
+            json.dump({"streams": B, "precision": args.precision, "labels": labels}, f)
+        torch.cuda.profiler.start()
+        model.process_chunk(chunk_view(W), out)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
@@ -291,7 +309,10 @@ def main():
                "h2d_bytes_per_step": B * 3 * 3200 * 4, "d2h_bytes_per_step": B * 1600 * 4,
                "ms_per_step": float(te.item()) / K}
 
-    # ---- per-stage device times (CUDA events inside the library, on the launching stream) and rooflines -------------
+    # ---- per-kernel device times (CUDA events inside the library, on the launching stream) and rooflines ------------
+    # Every kernel of the chunk step is timed alone (burst: back-to-back launches), with its ALGORITHMIC flops / bytes
+    #  from the library's op table.  Kernels of one class (e.g. the 21
+    # recurrent steps of a GRU layer) are grouped; `roofline` is the class with the largest share of the step.
     peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "src": "fallback"}
     try:
         with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
@@ -300,31 +321,56 @@ def main():
         peaks["src"] = "measured"
     except Exception:
         pass
-    stages = {}
-    roofline = None
+    traffic = {}
+    try:
+        with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch", {})
+    except Exception:
+        pass
+    stages, kernels, roofline = {}, [], None
     if rank == 0:
-        fl = workload.algorithmic_flops(**cfg)
-        by = workload.algorithmic_bytes()
-        for st in ("stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"):
+        import re
+        L = lib()
+        stage_names = ("stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll")
+        groups = {}
+        for i in range(L.se_crn_num_kernels(model._ctx)):
+            name = C.create_string_buffer(96)
+            fl, by, stg = C.c_double(0), C.c_double(0), C.c_int(0)
+            check(L.se_crn_kernel_info(model._ctx, i, name, 96, C.byref(fl), C.byref(by), C.byref(stg)), "kernel_info")
             ms = C.c_float(0)
-            check(lib().se_crn_time_stage(model._ctx, st.encode(), B, 5, C.byref(ms)), "se_crn_time_stage")
-            stages[st] = {"ms": ms.value}
+            check(L.se_crn_time_kernel(model._ctx, i, B, 5, C.byref(ms)), "se_crn_time_kernel")
+            key = re.sub(r"step\d+", "step", name.value.decode())
+            g = groups.setdefault(key, {"name": key, "stage": stage_names[stg.value], "launches": 0, "ms_total": 0.0,
+                                        "flops": fl.value * B, "bytes": by.value * B})
+            g["launches"] += 1
+            g["ms_total"] += ms.value
         model.reset()
-        tot = sum(s["ms"] for s in stages.values())
-        for st, s in stages.items():
-            s["share"] = s["ms"] / tot
-            if st in by:
-                a = by[st] * B / (s["ms"] * 1e-3) / 1e9
-                s.update(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"])
-            elif st in fl:
-                a = fl[st] * B / (s["ms"] * 1e-3) / 1e12
-                s.update(bound="tensor", achieved=a, peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s",
-                         frac=a / peaks["bf16_tflops_sustained"])
-        top = max((s for s in stages if "bound" in stages[s]), key=lambda s: stages[s]["ms"])
-        roofline = {"kernel": top, "bound": stages[top]["bound"], "achieved": stages[top]["achieved"],
-                    "peak": stages[top]["peak"], "unit": stages[top]["unit"], "frac": stages[top]["frac"],
-                    "traffic": None, "peak_source": peaks["src"] + " (sustained bf16)" if stages[top]["bound"] == "tensor"
-                    else peaks["src"]}
+        tot = sum(g["ms_total"] for g in groups.values())
+        tensor_peak = peaks["bf16_tflops"]  # kernels are timed alone: burst figure
+        for g in groups.values():
+            ms = g["ms_total"] / g["launches"]
+            k = {"name": g["name"], "stage": g["stage"], "launches": g["launches"], "ms": ms,
+                 "share": g["ms_total"] / tot}
+            if g["flops"] > 0 and g["stage"] != "preconv":
+                a = g["flops"] / (ms * 1e-3) / 1e12
+                k.update(bound="tensor", achieved=a, peak=tensor_peak, unit="TFLOP/s", frac=a / tensor_peak,
+                         frac_of_tf32_rate=a / (0.5 * tensor_peak))
+            else:
+                a = g["bytes"] / (ms * 1e-3) / 1e9
+                k.update(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"])
+            k["traffic"] = traffic.get(g["name"])
+            kernels.append(k)
+            st = stages.setdefault(g["stage"], {"ms": 0.0})
+            st["ms"] += g["ms_total"]
+        for st in stages.values():
+            st["share"] = st["ms"] / tot
+        top = max(kernels, key=lambda k: k["share"])
+        roofline = {"kernel": top["name"], "launches_per_step": top["launches"], "ms_per_launch": top["ms"],
+                    "share_of_step": top["share"], "bound": top["bound"], "achieved": top["achieved"],
+                    "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": top["traffic"],
+                    "peak_source": f"{peaks['src']} ({'bf16 dense burst; tf32 math runs at half that rate' if top['bound'] == 'tensor' else 'copy bandwidth'})"}
+        if "frac_of_tf32_rate" in top:
+            roofline["frac_of_tf32_rate"] = top["frac_of_tf32_rate"]
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -342,7 +388,7 @@ def main():
                        "l2": f"inputs larger than L2: {RING}-hop input ring of {sig.numel() * 4 / 1e6:.0f} MB and a "
                              f"per-step working set of several GB, both > 126 MB L2"},
             "p99_chunk_latency_ms": lat[min(K - 1, int(0.99 * K))], "p50_chunk_latency_ms": lat[K // 2],
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * K, "roofline": roofline, "stages": stages,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * K, "roofline": roofline, "stages": stages, "kernels": kernels,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

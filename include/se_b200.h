@@ -117,6 +117,14 @@ int se_crn_set_graph(se_ctx* ctx, int enable);
  * device time in milliseconds in *ms.  Stages: "stft", "mask_istft", "step".  Used for the roofline report. */
 int se_crn_time_stage(se_ctx* ctx, const char* stage, int B, int iters, float* ms);
 
+/* Kernel-level view of one chunk step, in launch order (the evidence behind bench.py's roofline object):
+ * name, algorithmic FLOPs and algorithmic HBM bytes per stream and chunk, stage index. */
+int se_crn_num_kernels(const se_ctx* ctx);
+int se_crn_kernel_info(const se_ctx* ctx, int index, char* name, int name_cap, double* flops_per_stream,
+                       double* bytes_per_stream, int* stage);
+/* average device time (CUDA events on the launching stream) of kernel `index` alone, launched `iters` times on B streams */
+int se_crn_time_kernel(se_ctx* ctx, int index, int B, int iters, float* ms);
+
 /* ---- test hook ------------------------------------------------------------------------------------------------- */
 /* Copy the logical interior of a named internal activation of stream b to HOST memory as [T][F][C] (channels-last),
  * dims = {T, F, C}.  Names: "pre_in<i>", "enc_in<i>", "dec_in<j>", "xg", "fcraw", "hseq<l>", "ylast", "noisy".

@@ -65,6 +65,9 @@ SIGNATURES = {
     "se_crn_launches_per_chunk": (_I, [_P]),
     "se_crn_set_graph": (_I, [_P, _I]),
     "se_crn_time_stage": (_I, [_P, C.c_char_p, _I, _I, C.POINTER(C.c_float)]),
+    "se_crn_num_kernels": (_I, [_P]),
+    "se_crn_kernel_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _PI]),
+    "se_crn_time_kernel": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float)]),
     "se_debug_read": (_I, [_P, C.c_char_p, _I, _P, _L, C.POINTER(C.c_int)]),
 }
 

@@ -52,6 +52,9 @@ const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decod
 struct Op {
     OpKind kind;
     int stage;
+    std::string label;      // kernel name for reports (se_crn_kernel_info)
+    double alg_flops = 0;   // algorithmic FLOPs (2*MACs of the reference op) per stream and chunk
+    double alg_bytes = 0;   // algorithmic HBM bytes per stream and chunk: every operand read once, every result written once
     GemmParams g;
     int rows_per_stream = 0;
     NormApplyParams n;
@@ -127,6 +130,7 @@ struct se_ctx {
     std::vector<Op> ops;
     RollTable roll{};
     RollTable zero_tab{};
+    int64_t roll_floats = 0;   // floats moved per stream by the roll kernel
     int64_t state_floats = 0;  // carried state per stream (allocated extents, incl. zero borders of the GEMM-path buffers)
 
     IoDesc* io_dev = nullptr;
@@ -269,6 +273,20 @@ constexpr size_t NONE = (size_t)-1;
 struct Builder {
     se_ctx* c;
     std::vector<OpFix> fix;
+    std::string m_label;  // meta of the next pushed op
+    double m_flops = 0, m_bytes = 0;
+    void meta(const std::string& label, double flops, double bytes) {
+        m_label = label;
+        m_flops = flops;
+        m_bytes = bytes;
+    }
+    void take_meta(Op& op) {
+        op.label = m_label;
+        op.alg_flops = m_flops;
+        op.alg_bytes = m_bytes;
+        m_label.clear();
+        m_flops = m_bytes = 0;
+    }
 
     // identity koff for a dense K-contiguous operand
     int koff_dense(int K) {
@@ -284,6 +302,7 @@ struct Builder {
         op.stage = stage;
         op.g = g;
         op.rows_per_stream = rows_per_stream;
+        take_meta(op);
         c->ops.push_back(op);
         fix.push_back({pw.w_off, pw.b_off, k_off, NONE, NONE, NONE, NONE, w2_off, b2_off});
     }
@@ -294,6 +313,7 @@ struct Builder {
         op.kind = OP_NORM;
         op.stage = stage;
         op.n = n;
+        take_meta(op);
         c->ops.push_back(op);
         fix.push_back({NONE, NONE, -1, w_off, b_off, wr_off, br_off});
     }
@@ -309,6 +329,7 @@ struct Builder {
         op.hB = hB;
         op.hout = hout;
         op.H = H;
+        take_meta(op);
         c->ops.push_back(op);
         fix.push_back({NONE, NONE, -1, NONE, NONE, NONE, NONE});
     }
@@ -393,6 +414,13 @@ struct Builder {
                 g.C2 = Cout_real;
                 g.stats = stats;
             }
+            {
+                const double in_b = 4.0 * Cin_real * in.Tp * in.F, conv_fl = 2.0 * rows * Cout_real * (KT * KF * Cin_real);
+                if (fuse_gate)
+                    meta(name + ".conv+elu+gate", conv_fl + 4.0 * rows * Cout_real * Cout_real, in_b + 4.0 * rows * Cout_real);
+                else
+                    meta(name + ".conv+elu", conv_fl, in_b + 4.0 * rows * Cout_real);
+            }
             push_gemm(stage, g, rows, pw, k_off, w2_off, b2_off);
         }
         // (2) gated 1x1 pair + statistics -> tmp_y [B][T][Fo][Cp_out]
@@ -429,6 +457,7 @@ struct Builder {
             g.oF = g.sF;
             g.vec4 = 1;
             g.stats = stats;
+            meta(name + ".gate1x1", 4.0 * rows * Cout_real * Cout_real, 8.0 * rows * Cout_real);
             push_gemm(stage, g, rows, pw, k_off);
         }
         // (3) GlobalLayerNorm (+ residual) -> destination
@@ -456,6 +485,7 @@ struct Builder {
             n.oF = dF;
             const size_t w_off = pack_affine(name + ".norm.weight", Cout_real, Cp_out);
             const size_t b_off = pack_affine(name + ".norm.bias", Cout_real, Cp_out);
+            meta(name + ".gln" + (residual ? "+residual" : ""), 0, (residual ? 12.0 : 8.0) * rows * Cout_real);
             push_norm(stage, n, w_off, b_off);
         }
     }
@@ -519,6 +549,9 @@ struct Builder {
             g.odd_tail = 1;
             g.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
             g.vec4 = Cop % 4 == 0;
+            // ConvTranspose2d counted over the T kept frames: even bins 3 taps, odd bins 2 taps
+            meta(name + ".deconv+elu", 2.0 * T * (3.0 * Fin + 2.0 * (Fin - 1)) * KT * Cin * Cout_real,
+                 4.0 * Cin * T * Fin + 4.0 * T * Fy * Cout_real);
             push_gemm(ST_DECODER, g, T * Fo, pw, k_off);
         }
         if (!skip) return;
@@ -561,6 +594,7 @@ struct Builder {
             g.o2F = g.oF;
             g.stats = c->stats + (size_t)stats_slot_r * 2 * c->maxB;
             g.vec4 = 1;
+            meta(name + ".skip1x1", 4.0 * rows * Cout_real * Cout_real, 12.0 * rows * Cout_real);
             push_gemm(ST_DECODER, g, rows, pw, k_off);
         }
         {
@@ -586,6 +620,7 @@ struct Builder {
             const size_t b_off = pack_affine(name + ".norm.bias", Cout_real, Cop);
             const size_t wr_off = pack_affine(name + ".residualnorm.weight", Cout_real, Cop);
             const size_t br_off = pack_affine(name + ".residualnorm.bias", Cout_real, Cop);
+            meta(name + ".gln+skipblend", 0, 4.0 * T * Cout_real * (Fy + 3.0 * Fs));
             push_norm(ST_DECODER, n, w_off, b_off, wr_off, br_off);
         }
     }
@@ -726,6 +761,9 @@ int build_ctx(se_ctx* c) {
             op.pc.oF = nx.sF;
             op.pc.out_vec8 = 1;
         }
+        op.label = name + ".fused";
+        op.alg_flops = 2.0 * T * NBIN * 5 * (125 + 10);
+        op.alg_bytes = 4.0 * 5 * NBIN * (PRECONV_TP + T);
         c->ops.push_back(op);
         b.fix.push_back({NONE, NONE, -1, w_off, NONE, NONE, NONE});
         slot++;
@@ -790,6 +828,7 @@ int build_ctx(se_ctx* c) {
             gp.oT = 3 * H;
             gp.oF = 0;
             gp.vec4 = 1;
+            b.meta("gru.l" + s + ".input_proj", 2.0 * T * 3 * H * Kin, 4.0 * T * (Kin + 3 * H));
             b.push_gemm(ST_GRU, gp, T, pw, k_off);
         }
         const int k_off = b.koff_dense(H);
@@ -820,6 +859,7 @@ int build_ctx(se_ctx* c) {
             gp.hprev = c->hseq[l] + (long long)t * H;
             gp.hB = (long long)(T + 1) * H;
             gp.H = H;
+            b.meta("gru.l" + s + ".step" + std::to_string(t), 2.0 * 3 * H * H, 4.0 * (3 * H + 2 * H));
             b.push_gemm(ST_GRU, gp, 1, pw, k_off);
         }
         for (int t = 0; t < T && !fused; ++t) {
@@ -836,7 +876,9 @@ int build_ctx(se_ctx* c) {
             gp.oB = 3 * H;
             gp.oT = 0;
             gp.oF = 0;
+            b.meta("gru.l" + s + ".step" + std::to_string(t) + ".hh", 2.0 * 3 * H * H, 4.0 * (H + 3 * H));
             b.push_gemm(ST_GRU, gp, 1, pw, k_off);
+            b.meta("gru.l" + s + ".step" + std::to_string(t) + ".cell", 0, 4.0 * (6 * H + 2 * H));
             b.push_gru_pw(c->gi + (long long)t * 3 * H, (long long)T * 3 * H, c->gh, c->hseq[l] + (long long)t * H,
                           (long long)(T + 1) * H, c->hseq[l] + (long long)(t + 1) * H, H);
         }
@@ -868,6 +910,7 @@ int build_ctx(se_ctx* c) {
         gp.oF = 0;
         gp.stats = c->stats + (size_t)gru_slot * 2 * maxB;
         gp.vec4 = 1;
+        b.meta("gru.fc+elu", 2.0 * T * feat * H, 4.0 * T * (H + feat));
         b.push_gemm(ST_GRU, gp, T, pw, k_off);
 
         const Act& nx = c->dec_in[0];
@@ -895,6 +938,7 @@ int build_ctx(se_ctx* c) {
                 arena[b_off + n2] = bb[perm(n2)];
             }
         });
+        b.meta("gru.gln", 0, 8.0 * T * feat);
         b.push_norm(ST_GRU, n, w_off, b_off);
     }
     // ---- decoder ----------------------------------------------------------------------------------------------
@@ -953,6 +997,7 @@ int build_ctx(se_ctx* c) {
         c->roll.e[c->roll.n++] = e;
         c->zero_tab.e[c->zero_tab.n++] = e;
         c->state_floats += count;
+        c->roll_floats += count;
     };
     for (const PreBuf& pb : c->pre_in) {  // rolled by the preconv kernel itself; a reset clears the whole slab
         RollEntry e{pb.base, pb.sB, 0, 0, (int)pb.sB};
@@ -1042,6 +1087,17 @@ int enqueue_stream_step(se_ctx* c, int B, cudaStream_t st, int stage_filter = -1
         if (launch_roll(c->roll, 0, B, st)) return 1;
     }
     return 0;
+}
+
+// kernels of one chunk step, in launch order: 0 = STFT + features, 1..n = network ops, n+1 = mask + iSTFT + OLA, n+2 = roll
+int num_kernels(const se_ctx* c) { return (int)c->ops.size() + 3; }
+
+int enqueue_kernel(se_ctx* c, int idx, int B, cudaStream_t st) {
+    const int n = (int)c->ops.size();
+    if (idx == 0) return enqueue_stream_step(c, B, st, ST_STFT);
+    if (idx <= n) return launch_op(c, c->ops[idx - 1], B, st);
+    if (idx == n + 1) return enqueue_stream_step(c, B, st, ST_MASK);
+    return enqueue_stream_step(c, B, st, ST_ROLL);
 }
 
 int count_launches(const se_ctx* c) {
@@ -1381,6 +1437,54 @@ int se_crn_set_graph(se_ctx* c, int enable) {
     return 0;
 }
 
+int se_crn_num_kernels(const se_ctx* c) { return c ? num_kernels(c) : 0; }
+
+int se_crn_kernel_info(const se_ctx* c, int index, char* name, int name_cap, double* flops_per_stream,
+                       double* bytes_per_stream, int* stage) {
+    SE_REQUIRE(c != nullptr && index >= 0 && index < num_kernels(c), "se_crn_kernel_info: bad index");
+    const int n = (int)c->ops.size();
+    std::string label;
+    double fl = 0, by = 0;
+    int stg = 0;
+    if (index == 0) {
+        label = "stft+features";
+        fl = 0;
+        by = 4.0 * (3 * KCHUNK + 5 * NBIN * T + 2 * NBIN * T);
+        stg = ST_STFT;
+    } else if (index <= n) {
+        const Op& op = c->ops[index - 1];
+        label = op.label;
+        fl = op.alg_flops;
+        by = op.alg_bytes;
+        stg = op.stage;
+    } else if (index == n + 1) {
+        label = "mask+istft+ola";
+        by = 4.0 * (2 * 2 * NBIN * T + PHOP + 2 * PHOP);
+        stg = ST_MASK;
+    } else {
+        label = "state_roll";
+        by = 2.0 * 4.0 * (double)c->roll_floats;
+        stg = ST_ROLL;
+    }
+    if (name && name_cap > 0) {
+        strncpy(name, label.c_str(), (size_t)name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    if (flops_per_stream) *flops_per_stream = fl;
+    if (bytes_per_stream) *bytes_per_stream = by;
+    if (stage) *stage = stg;
+    return 0;
+}
+
+static int time_filter(se_ctx* c, int filter, int kernel, int B, int iters, float* ms);
+
+int se_crn_time_kernel(se_ctx* c, int index, int B, int iters, float* ms) {
+    if (check_ready(c, B)) return 1;
+    SE_REQUIRE(ms != nullptr && iters > 0 && B > 0 && index >= 0 && index < num_kernels(c),
+               "se_crn_time_kernel: bad arguments");
+    return time_filter(c, -2, index, B, iters, ms);
+}
+
 int se_crn_time_stage(se_ctx* c, const char* stage, int B, int iters, float* ms) {
     if (check_ready(c, B)) return 1;
     SE_REQUIRE(stage != nullptr && ms != nullptr && iters > 0 && B > 0, "se_crn_time_stage: bad arguments");
@@ -1389,6 +1493,11 @@ int se_crn_time_stage(se_ctx* c, const char* stage, int B, int iters, float* ms)
     for (int s = 0; s < ST_COUNT; ++s)
         if (strcmp(stage, kStageNames[s]) == 0) filter = s;
     SE_REQUIRE(filter != -2, std::string("se_crn_time_stage: unknown stage ") + stage);
+    return time_filter(c, filter, -1, B, iters, ms);
+}
+
+// filter >= -1: a stage (or the whole step); filter == -2: the single kernel `kernel`
+static int time_filter(se_ctx* c, int filter, int kernel, int B, int iters, float* ms) {
     cudaStream_t st = nullptr;
     // a self-contained chunk source so that the stage can run without caller buffers: the carry/out of the previous
     // run are reused as scratch (timing only; state is garbage afterwards -> caller must reset)
@@ -1406,10 +1515,11 @@ int se_crn_time_stage(se_ctx* c, const char* stage, int B, int iters, float* ms)
     cudaEvent_t e0, e1;
     SE_CUDA_OK(cudaEventCreate(&e0));
     SE_CUDA_OK(cudaEventCreate(&e1));
-    if (enqueue_stream_step(c, B, st, filter)) return 1;  // warm-up
+    auto run = [&]() { return filter == -2 ? enqueue_kernel(c, kernel, B, st) : enqueue_stream_step(c, B, st, filter); };
+    if (run()) return 1;  // warm-up
     SE_CUDA_OK(cudaEventRecord(e0, st));
     for (int i = 0; i < iters; ++i)
-        if (enqueue_stream_step(c, B, st, filter)) return 1;
+        if (run()) return 1;
     SE_CUDA_OK(cudaEventRecord(e1, st));
     SE_CUDA_OK(cudaEventSynchronize(e1));
     float t = 0.f;

@@ -48,7 +48,7 @@ struct StftSmem {
     float win[NFFT];
     float2 w20[20];
     float2 w400[400];
-    float2 y[GROUP][20][ROW];       // stage-1 output after twiddle
+    float2 y[3][GROUP][20][ROW];    // stage-1 output after twiddle
     float2 spec[3][GROUP][NBIN + 1];
 };
 
@@ -77,58 +77,61 @@ __global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
     }
     __syncthreads();
 
-    for (int m = 0; m < M; ++m) {
-        // ---- stage 1: 20-point DFT over n1 of real data, k1 = 0..10, then twiddle W400^(n2 k1) -----------------
-        for (int o = tid; o < GROUP * 11 * 20; o += blockDim.x) {
-            const int n2 = o % 20;
-            const int k1 = (o / 20) % 11;
-            const int fr = o / 220;
-            const float* x = &s.xs[m][fr * HOP];
+    // exp(-2 pi i j / 20) = (kC20[j], kS20[j]); both DFT stages are fully unrolled so that every twiddle is an immediate
+    constexpr float kC20[20] = {1.0f, 0.951056516f, 0.809016994f, 0.587785252f, 0.309016994f, 0.0f, -0.309016994f, -0.587785252f, -0.809016994f, -0.951056516f, -1.0f, -0.951056516f, -0.809016994f, -0.587785252f, -0.309016994f, 0.0f, 0.309016994f, 0.587785252f, 0.809016994f, 0.951056516f};
+    constexpr float kS20[20] = {0.0f, -0.309016994f, -0.587785252f, -0.809016994f, -0.951056516f, -1.0f, -0.951056516f, -0.809016994f, -0.587785252f, -0.309016994f, 0.0f, 0.309016994f, 0.587785252f, 0.809016994f, 0.951056516f, 1.0f, 0.951056516f, 0.809016994f, 0.587785252f, 0.309016994f};
+    // ---- stage 1: per (mic, frame, n2) the 20-point DFT over n1 of the windowed real samples, k1 = 0..10 (the rest by
+    //      Hermitian symmetry), then the twiddle W400^(n2 k1).  20 loads feed 440 FMAs held in registers.
+    for (int u = tid; u < M * GROUP * 20; u += blockDim.x) {
+        const int n2 = u % 20;
+        const int fr = (u / 20) % GROUP;
+        const int m = u / (20 * GROUP);
+        const float* x = &s.xs[m][fr * HOP];
+        float v[20];
+#pragma unroll
+        for (int n1 = 0; n1 < 20; ++n1) v[n1] = x[20 * n1 + n2] * s.win[20 * n1 + n2];
+#pragma unroll
+        for (int k1 = 0; k1 <= 10; ++k1) {
             float re = 0.f, im = 0.f;
-            int idx = 0;
-#pragma unroll 5
+#pragma unroll
             for (int n1 = 0; n1 < 20; ++n1) {
-                const int n = 20 * n1 + n2;
-                const float v = x[n] * s.win[n];
-                const float2 w = s.w20[idx];
-                re = fmaf(v, w.x, re);
-                im = fmaf(v, w.y, im);
-                idx += k1;
-                if (idx >= 20) idx -= 20;
+                re = fmaf(v[n1], kC20[(n1 * k1) % 20], re);
+                im = fmaf(v[n1], kS20[(n1 * k1) % 20], im);
             }
-            const float2 yv = make_float2(re, im);
-            s.y[fr][k1][n2] = cmul(yv, s.w400[n2 * k1]);
-            if (k1 >= 1 && k1 <= 9) {  // Hermitian partner row 20-k1
-                const float2 yc = make_float2(re, -im);
-                s.y[fr][20 - k1][n2] = cmul(yc, s.w400[n2 * (20 - k1)]);
-            }
+            s.y[m][fr][k1][n2] = cmul(make_float2(re, im), s.w400[n2 * k1]);
+            if (k1 >= 1 && k1 <= 9)  // Hermitian partner row 20-k1
+                s.y[m][fr][20 - k1][n2] = cmul(make_float2(re, -im), s.w400[n2 * (20 - k1)]);
         }
-        __syncthreads();
-        // ---- stage 2: 20-point DFT over n2 -> bins k = k1 + 20 k2, k <= 200 ------------------------------------
-        for (int o = tid; o < GROUP * NBIN; o += blockDim.x) {
-            const int k = o % NBIN;
-            const int fr = o / NBIN;
-            const int k1 = k % 20, k2 = k / 20;
-            const float2* yr = s.y[fr][k1];
-            float re = 0.f, im = 0.f;
-            int idx = 0;
-#pragma unroll 5
-            for (int n2 = 0; n2 < 20; ++n2) {
-                const float2 v = yr[n2];
-                const float2 w = s.w20[idx];
-                re = fmaf(v.x, w.x, re);
-                re = fmaf(-v.y, w.y, re);
-                im = fmaf(v.x, w.y, im);
-                im = fmaf(v.y, w.x, im);
-                idx += k2;
-                if (idx >= 20) idx -= 20;
-            }
-            // DC and Nyquist bins of a real signal are exactly real (pocketfft r2c returns +0 there)
-            if (k == 0 || k == NBIN - 1) im = 0.f;
-            s.spec[m][fr][k] = make_float2(re, im);
-        }
-        __syncthreads();
     }
+    __syncthreads();
+    // ---- stage 2: per (mic, frame, k1) the 20-point DFT over n2 -> bins k = k1 + 20 k2 <= 200 -------------------------
+    for (int u = tid; u < M * GROUP * 20; u += blockDim.x) {
+        const int k1 = u % 20;
+        const int fr = (u / 20) % GROUP;
+        const int m = u / (20 * GROUP);
+        float2 yr[20];
+#pragma unroll
+        for (int n2 = 0; n2 < 20; ++n2) yr[n2] = s.y[m][fr][k1][n2];
+#pragma unroll
+        for (int k2 = 0; k2 <= 10; ++k2) {
+            const int k = k1 + 20 * k2;
+            if (k < NBIN) {
+                float re = 0.f, im = 0.f;
+#pragma unroll
+                for (int n2 = 0; n2 < 20; ++n2) {
+                    const float wc = kC20[(n2 * k2) % 20], ws = kS20[(n2 * k2) % 20];
+                    re = fmaf(yr[n2].x, wc, re);
+                    re = fmaf(-yr[n2].y, ws, re);
+                    im = fmaf(yr[n2].x, ws, im);
+                    im = fmaf(yr[n2].y, wc, im);
+                }
+                // DC and Nyquist bins of a real signal are exactly real (pocketfft r2c returns +0 there)
+                if (k == 0 || k == NBIN - 1) im = 0.f;
+                s.spec[m][fr][k] = make_float2(re, im);
+            }
+        }
+    }
+    __syncthreads();
 
     // ---- outputs ---------------------------------------------------------------------------------------------
     if (p.spec_ref != nullptr) {  // reference layout [R][M][F][T][2]
@@ -392,7 +395,7 @@ int launch_stft_features(const StftParams& p, cudaStream_t st) {
     SE_REQUIRE(p.M >= 1 && p.M <= 3, "stft: at most 3 microphones per launch");
     SE_REQUIRE(p.feat == nullptr || p.M == 3, "stft features need exactly 3 microphones (CRN_ELU.py:369-373)");
     if (p.B == 0) return 0;
-    stft_features_kernel<<<dim3(p.B, T / GROUP), 256, sizeof(StftSmem), st>>>(p);
+    stft_features_kernel<<<dim3(p.B, T / GROUP), 224, sizeof(StftSmem), st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
