@@ -193,8 +193,9 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"CRN_ELU {args.model} batched streaming inference, {args.streams} concurrent "
-                               f"synthetic streams per GPU, 3200-sample chunks at hop 1600", "sample": sample},
+        "config": {"workload": f"CRN_ELU {args.model} batched streaming inference, {args.streams} concurrent synthetic "
+                               f"streams per GPU, 3200-sample chunks at hop 1600 (BASELINE.json configs[1])",
+                   "streams_per_gpu": args.streams, "precision": "fp32", "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
