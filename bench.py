@@ -26,6 +26,7 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+_REAL_STDOUT = sys.stdout
 METRIC = "enhanced audio-sec/sec (CRN_ELU streaming)"
 UNIT = "audio-s/s"
 RING = 16  # distinct hops of input per stream kept in HBM (input ring 1024*3*27200*4 B = 334 MB > 126 MB L2)
@@ -200,12 +201,18 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: anything a library prints to fd 1 (e.g. the "NCCL version" banner) goes to
+    # stderr instead; the result line is written to the saved descriptor
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -392,7 +399,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * K, "roofline": roofline, "stages": stages, "kernels": kernels,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
