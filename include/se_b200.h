@@ -94,7 +94,8 @@ int se_crn_realtime_process(se_ctx* ctx, const float* mixture, int B, int64_t L,
 int se_crn_realtime_process_host(se_ctx* ctx, const float* mixture, int B, int64_t L, int flag, float* out);
 
 /* ---- the pieces, for callers that use the reference's finer-grained methods ----------------------------------- */
-/* replaces: TemporalCRN.stft_trans (CRN_ELU.py:417-424): chunks [R,M,K] -> spectrum [R,M,F,T,2] (reference layout) */
+/* replaces: TemporalCRN.stft_trans (CRN_ELU.py:417-424; fullsubnet.py:835-844): chunks [R,M,K] -> spectrum [R,M,F,T,2]
+ * (reference layout).  The transforms do not depend on a model: ctx may be NULL (current device). */
 int se_stft_trans(se_ctx* ctx, const float* chunks, int R, float* spec, void* stream);
 /* replaces: TemporalCRN.istft_trans (CRN_ELU.py:426-432): spectrum [R,F,T,2] -> [R,K] */
 int se_istft_trans(se_ctx* ctx, const float* spec, int R, float* out, void* stream);
@@ -107,6 +108,40 @@ int se_segmentation(const float* x, int B, int C, int64_t L, int K, float* out, 
 int se_chunk_grid(int64_t L, int K, int* gap, int* n_chunks);
 /* replaces: utility.over_add (utility.py:373-403): [C,N,K] -> [C, N*K/2 - K/2 - gap] */
 int se_over_add(const float* chunks, int C, int N, int K, int gap, float* out, void* stream);
+
+/* ==== FullSubNet (fullsubnet.py:685-961; config.yaml:153-172) ==================================================== */
+typedef struct se_fsn_config {
+    int32_t num_freqs;        /* 201                                   */
+    int32_t num_mics;         /* 3                                     */
+    int32_t fb_hidden;        /* fb_model_hidden_size (512)            */
+    int32_t sb_hidden;        /* sb_model_hidden_size (384)            */
+    int32_t num_layers;       /* 2                                     */
+    int32_t sb_num_neighbors; /* 15                                    */
+    int32_t fb_num_neighbors; /* 0                                     */
+    int32_t max_streams;      /* capacity of the per-stream LSTM state */
+} se_fsn_config;
+typedef struct se_fsn se_fsn;
+
+/* replaces: FullSubNet.__init__ + .cuda() (fullsubnet.py:686-767; predict_fullsubnet.py:31-33) */
+int se_fsn_create(se_fsn** out, int device, const se_fsn_config* cfg);
+int se_fsn_destroy(se_fsn* ctx);
+/* the 20 parameter tensors of FullSubNet.state_dict() (fb_model.*, sb_model.*) in a fixed order */
+int se_fsn_num_params(const se_fsn* ctx);
+const char* se_fsn_param_name(const se_fsn* ctx, int index);
+int64_t se_fsn_param_numel(const se_fsn* ctx, int index);
+int se_fsn_bind_weights(se_fsn* ctx, const float* const* ptrs, int n, void* stream);
+/* replaces: FullSubNet.reset_state (fullsubnet.py:826-832): zero LSTM states, reset both CumLayerNorms */
+int se_fsn_reset_state(se_fsn* ctx, int first, int count, void* stream);
+/* replaces: FullSubNet.forward on one chunk (fullsubnet.py:769-824), T = 21 frames:
+ *   x [B, 2M, F, T] (M real planes then M imaginary planes, fullsubnet.py:835-844) -> compressed cIRM [B, 2, F, T];
+ *   advances the LSTM states fh / sh and the CumLayerNorm running means of streams [0, B). */
+int se_fsn_forward_chunk(se_fsn* ctx, const float* x, float* out, int B, void* stream);
+/* replaces: decompress_cIRM + complex multiply with mic 0 (fullsubnet.py:949-953):
+ *   crm [R, 2, F, T], x [R, 2, F, T] (mic-0 real / imaginary) -> enhanced spectrum [R, F, T, 2] */
+int se_fsn_apply_mask(const float* crm, const float* x, float* out, int R, int F, int T, void* stream);
+/* replaces: BaseModel.unfold (fullsubnet.py:299-331): [B, C, F, T] -> [B, F, C, 2n+1, T], reflect padding (n >= 1),
+ * n = 0 is the plain permutation */
+int se_unfold(const float* in, int B, int C, int F, int T, int num_neighbor, float* out, void* stream);
 
 /* ---- introspection used by bench.py --------------------------------------------------------------------------- */
 /* number of kernel launches one se_crn_process_chunk issues (graph nodes included) */

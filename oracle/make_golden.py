@@ -22,6 +22,7 @@ torchaudio.set_audio_backend = lambda *a, **k: None  # API removed in torchaudio
 import CRN_ELU  # noqa: E402  (reference, unmodified)
 import distillation_crn  # noqa: E402  (reference, unmodified)
 import utility  # noqa: E402  (reference, unmodified)
+import fullsubnet  # noqa: E402  (reference, unmodified)
 
 from oracle import synth  # noqa: E402
 
@@ -99,13 +100,65 @@ def framing():
     print("framing", gaps, ns)
 
 
+FSN_SMALL = dict(num_freqs=201, num_mics=3, fb_hidden=64, sb_hidden=32, sb_num_neighbors=15, fb_num_neighbors=0,
+                 num_layers=2)
+FSN_FULL = dict(num_freqs=201, num_mics=3, fb_hidden=512, sb_hidden=384, sb_num_neighbors=15, fb_num_neighbors=0,
+                num_layers=2)
+
+
+def run_fsn(cfg, seed, B, L, tag, continuation=False):
+    """Reference FullSubNet.realtime_process(train=False) (fullsubnet.py:903-961) + one isolated forward + unfold."""
+    weights = synth.make_fsn_weights(seed=seed, **cfg)
+    model = fullsubnet.FullSubNet(
+        num_freqs=cfg["num_freqs"], look_ahead=0, sequence_model="LSTM", fb_num_neighbors=cfg["fb_num_neighbors"],
+        sb_num_neighbors=cfg["sb_num_neighbors"], fb_output_activate_function="ReLU", sb_output_activate_function=False,
+        fb_model_hidden_size=cfg["fb_hidden"], sb_model_hidden_size=cfg["sb_hidden"], num_mics=cfg["num_mics"],
+        norm_type="offline_laplace_norm", num_groups_in_drop_band=2, num_layers=cfg["num_layers"], weight_init=False,
+        sample_rate=16000, segment_length=3200, win_length=25, hop_length=10, n_fft=400)
+    missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=True)
+    assert not missing and not unexpected
+    model.eval()
+    mix, src = synth.make_mixture(B, L)
+    x = torch.from_numpy(mix)
+    s3 = torch.from_numpy(np.repeat(src[:, None, :], 3, axis=1).copy())  # source [B, M, L] (only mic 0 is used)
+    res = {}
+    with torch.no_grad():
+        pred, crm, sf, xf = model.realtime_process(x, s3, flag=False, train=False)
+        res["out"], res["crm"], res["sf"], res["xf"] = pred.numpy(), crm.numpy(), sf.numpy(), xf.numpy()
+        if continuation:
+            mix2, src2 = synth.make_mixture(B, L // 2, first_stream=100)
+            s32 = torch.from_numpy(np.repeat(src2[:, None, :], 3, axis=1).copy())
+            pred2 = model.realtime_process(torch.from_numpy(mix2), s32, flag=True, train=False)[0]
+            res["out_cont"] = pred2.numpy()
+        # isolated forward on chunk 1 with fresh state
+        seg, gap = model.segmentation(torch.cat([torch.zeros(B, 3, 1600), x], dim=-1))
+        spec = model.stft_trans(seg)  # [B*N, 2M, F, T]
+        N = spec.shape[0] // B
+        x1 = spec.reshape(B, N, 6, 201, -1)[:, 1].contiguous()
+        model.reset_state(B, x1.dtype, x1.device)
+        res["x_chunk1"] = x1.numpy().copy()
+        res["fwd_chunk1"] = model.forward(x1.clone()).numpy()
+        res["fwd_chunk1_again"] = model.forward(x1.clone()).numpy()  # second call: running CumLayerNorm mean + LSTM state
+        small = torch.arange(2 * 2 * 7 * 3, dtype=torch.float32).reshape(2, 2, 7, 3)
+        res["unfold_in"], res["unfold_out"] = small.numpy(), fullsubnet.BaseModel.unfold(small, 2).numpy()
+        res["unfold0_out"] = fullsubnet.BaseModel.unfold(small, 0).numpy()
+    res["meta"] = np.array([seed, B, L])
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **res)
+    n = sum(int(np.prod(s)) for s in synth.fsn_param_shapes(**cfg).values())
+    print(tag, {k: v.shape for k, v in res.items()}, "peak", float(np.abs(res["out"]).max()), "params", n)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
-    framing()
-    run_model(CRN_ELU.TemporalCRN, SMALL, 7, 2, 4000, "crn_small", continuation=True)
-    run_model(CRN_ELU.TemporalCRN, TEACHER, 0, 2, 8000, "crn_teacher", continuation=True)
-    run_model(distillation_crn.TemporalCRN, STUDENT, 3, 2, 8000, "crn_student")
+    if "fsn" not in sys.argv[1:]:
+        framing()
+        run_model(CRN_ELU.TemporalCRN, SMALL, 7, 2, 4000, "crn_small", continuation=True)
+        run_model(CRN_ELU.TemporalCRN, TEACHER, 0, 2, 8000, "crn_teacher", continuation=True)
+        run_model(distillation_crn.TemporalCRN, STUDENT, 3, 2, 8000, "crn_student")
+    if "fsn" in sys.argv[1:] or len(sys.argv) == 1:
+        run_fsn(FSN_SMALL, 11, 2, 4000, "fsn_small", continuation=True)
+        run_fsn(FSN_FULL, 5, 1, 2400, "fsn_full")
     n_t = sum(int(np.prod(s)) for s in synth.crn_param_shapes(**TEACHER).values())
     n_s = sum(int(np.prod(s)) for s in synth.crn_param_shapes(**STUDENT).values())
     print("param counts (README.md:56,58 say 6.16 / 0.81 M):", n_t, n_s)

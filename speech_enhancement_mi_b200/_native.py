@@ -36,6 +36,11 @@ class SeCrnConfig(C.Structure):
     ]
 
 
+class SeFsnConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_freqs", "num_mics", "fb_hidden", "sb_hidden", "num_layers",
+                                         "sb_num_neighbors", "fb_num_neighbors", "max_streams")]
+
+
 _P = C.c_void_p
 _I = C.c_int
 _L = C.c_int64
@@ -65,6 +70,16 @@ SIGNATURES = {
     "se_crn_launches_per_chunk": (_I, [_P]),
     "se_crn_set_graph": (_I, [_P, _I]),
     "se_crn_time_stage": (_I, [_P, C.c_char_p, _I, _I, C.POINTER(C.c_float)]),
+    "se_fsn_create": (_I, [C.POINTER(_P), _I, C.POINTER(SeFsnConfig)]),
+    "se_fsn_destroy": (_I, [_P]),
+    "se_fsn_num_params": (_I, [_P]),
+    "se_fsn_param_name": (C.c_char_p, [_P, _I]),
+    "se_fsn_param_numel": (_L, [_P, _I]),
+    "se_fsn_bind_weights": (_I, [_P, C.POINTER(_P), _I, _P]),
+    "se_fsn_reset_state": (_I, [_P, _I, _I, _P]),
+    "se_fsn_forward_chunk": (_I, [_P, _P, _P, _I, _P]),
+    "se_fsn_apply_mask": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "se_unfold": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "se_crn_num_kernels": (_I, [_P]),
     "se_crn_kernel_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _PI]),
     "se_crn_time_kernel": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float)]),

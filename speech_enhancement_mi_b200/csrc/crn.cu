@@ -1299,25 +1299,52 @@ int se_crn_realtime_process_host(se_ctx* c, const float* mixture, int B, int64_t
     return 0;
 }
 
+// STFT / iSTFT do not depend on a model: with ctx == NULL they run on the current device with a per-device descriptor cell
+static int fft_cell(IoDesc** cell) {
+    static std::map<int, IoDesc*> cells;
+    int dev = 0;
+    SE_CUDA_OK(cudaGetDevice(&dev));
+    auto it = cells.find(dev);
+    if (it == cells.end()) {
+        void* p = nullptr;
+        SE_CUDA_OK(cudaMalloc(&p, sizeof(IoDesc)));
+        if (init_fft_tables()) return 1;
+        it = cells.emplace(dev, reinterpret_cast<IoDesc*>(p)).first;
+    }
+    *cell = it->second;
+    return 0;
+}
+
 int se_stft_trans(se_ctx* c, const float* chunks, int R, float* spec, void* stream) {
-    SE_REQUIRE(c != nullptr && chunks != nullptr && spec != nullptr, "se_stft_trans: null argument");
-    SE_CUDA_OK(cudaSetDevice(c->device));
+    SE_REQUIRE(chunks != nullptr && spec != nullptr, "se_stft_trans: null argument");
+    IoDesc* cell = nullptr;
+    if (c) {
+        SE_CUDA_OK(cudaSetDevice(c->device));
+        cell = c->io_dev;
+    } else if (fft_cell(&cell)) {
+        return 1;
+    }
     if (R == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     IoDesc io{chunks, 3LL * KCHUNK, KCHUNK, 0, KCHUNK, nullptr, 0, 0};
-    if (launch_set_io(c->io_dev, io, st)) return 1;
+    if (launch_set_io(cell, io, st)) return 1;
     StftParams sp{};
-    sp.io = c->io_dev;
+    sp.io = cell;
     sp.B = R;
     sp.M = 3;
-    sp.student = c->student;
+    sp.student = c ? c->student : 0;
     sp.spec_ref = spec;
     return launch_stft_features(sp, st);
 }
 
 int se_istft_trans(se_ctx* c, const float* spec, int R, float* out, void* stream) {
-    SE_REQUIRE(c != nullptr && spec != nullptr && out != nullptr, "se_istft_trans: null argument");
-    SE_CUDA_OK(cudaSetDevice(c->device));
+    SE_REQUIRE(spec != nullptr && out != nullptr, "se_istft_trans: null argument");
+    if (c) {
+        SE_CUDA_OK(cudaSetDevice(c->device));
+    } else {
+        IoDesc* cell = nullptr;
+        if (fft_cell(&cell)) return 1;  // constant tables of this device
+    }
     if (R == 0) return 0;
     MaskIstftParams mp{};
     mp.B = R;

@@ -121,7 +121,7 @@ __device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2
 
 // per-stream (sum, sum of squares) of the rows a warp owns: rows are ordered by stream, so the warp holds a short
 // monotone run of stream indices; one shuffle reduction and one pair of double atomics per distinct stream
-__device__ __forceinline__ void stats_commit(double* stats, int b, float s, float ss) {
+__device__ __forceinline__ void stats_commit(double* stats, int stride, int b, float s, float ss) {
     const unsigned full = 0xffffffffu;
     int lo = b < 0 ? 0x7fffffff : b, hi = b;
 #pragma unroll
@@ -137,8 +137,8 @@ __device__ __forceinline__ void stats_commit(double* stats, int b, float s, floa
             c += __shfl_xor_sync(full, c, off);
         }
         if ((threadIdx.x & 31) == 0) {
-            atomicAdd(stats + 2 * bb, (double)a);
-            atomicAdd(stats + 2 * bb + 1, (double)c);
+            atomicAdd(stats + (long long)stride * bb, (double)a);
+            atomicAdd(stats + (long long)stride * bb + 1, (double)c);
         }
     }
 }
@@ -480,6 +480,56 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
                     }
                 }
                 __syncwarp();
+            } else if (BN == 128 && p.epi == EPI_LSTM) {
+                // tile columns: [i | f | g | o] of hidden units j0 .. j0+32 (nn.LSTM gate order); 8 units per pass.
+                // c_prev = hprev (row stride hB), h' -> out (oB), c' -> out2 (o2B); Tn = Fo = 1: row = sequence
+                constexpr int U = BN / 4;
+                const int j0 = (tile % ntn) * U;
+                const int ul = lane & 7;
+                wait_acc();
+#pragma unroll 1
+                for (int u0 = 0; u0 < U; u0 += 8) {
+                    const int ju = j0 + u0 + ul;
+                    float pc[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int mm = m0 + q * 32 + i * 4 + (lane >> 3);
+                        pc[i] = mm < p.M ? p.hprev[(long long)(p.b0 + mm) * p.hB + ju] : 0.f;
+                    }
+                    uint32_t v[32];
+                    tmem_ld8_nowait(tlane + u0, v);
+                    tmem_ld8_nowait(tlane + U + u0, v + 8);
+                    tmem_ld8_nowait(tlane + 2 * U + u0, v + 16);
+                    tmem_ld8_nowait(tlane + 3 * U + u0, v + 24);
+                    tmem_ld_wait();
+                    if (u0 + 8 == U) {
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        *reinterpret_cast<uint4*>(srow + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    __syncwarp();
+                    const float bi = sbias[u0 + ul], bf = sbias[U + u0 + ul], bg = sbias[2 * U + u0 + ul],
+                                bo = sbias[3 * U + u0 + ul];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int r = i * 4 + (lane >> 3);
+                        const int mm = m0 + q * 32 + r;
+                        if (mm < p.M) {
+                            const float* sr = stg + r * SPW;
+                            const float ig = fast_sigmoid(sr[ul] + bi);
+                            const float fg = fast_sigmoid(sr[8 + ul] + bf);
+                            const float gg = fast_tanh(sr[16 + ul] + bg);
+                            const float og = fast_sigmoid(sr[24 + ul] + bo);
+                            const float cn = fg * pc[i] + ig * gg;
+                            const long long bb = p.b0 + mm;
+                            p.out2[bb * p.o2B + ju] = cn;
+                            p.out[bb * p.oB + ju] = og * fast_tanh(cn);
+                        }
+                    }
+                    __syncwarp();
+                }
             } else if (BN == 16 && p.epi == EPI_ELU_GATE) {
                 // conv + ELU, then the gated 1x1 pair of CRN_ELU.py:240 in registers (C2 <= 16 channels), + statistics
                 uint32_t vr[16];
@@ -506,10 +556,11 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
                 __syncwarp();
                 store_chunk<16>(stg, 0, p.out, ooff, p.C2, vec4, lane);
                 __syncwarp();
-                stats_commit(p.stats, b, s_acc, ss_acc);
+                stats_commit(p.stats, p.stats_stride ? p.stats_stride : 2, b, s_acc, ss_acc);
             } else {
                 const bool paired = (p.epi == EPI_GATE_STATS || p.epi == EPI_SKIP);
-                const bool want_stats = (p.epi == EPI_ELU_STATS || p.epi == EPI_GATE_STATS || p.epi == EPI_SKIP);
+                const bool want_stats = (p.epi == EPI_ELU_STATS || p.epi == EPI_GATE_STATS || p.epi == EPI_SKIP ||
+                                         p.epi == EPI_RELU_STATS);
                 constexpr int CH = BN < 32 ? 16 : 32;  // accumulator columns per pass
                 wait_acc();
 #pragma unroll 1
@@ -529,7 +580,10 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
 #pragma unroll
                     for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(vr[i]) + sbias[c0 + i];
                     if (!paired) {
-                        if (p.epi != EPI_BIAS) {
+                        if (p.epi == EPI_RELU_STATS) {
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) v[i] = fmaxf(v[i], 0.f);
+                        } else if (p.epi != EPI_BIAS) {
 #pragma unroll
                             for (int i = 0; i < CH; ++i) v[i] = fast_elu(v[i]);
                         }
@@ -588,7 +642,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
                     }
                     __syncwarp();
                 }
-                if (want_stats) stats_commit(p.stats, b, s_acc, ss_acc);
+                if (want_stats) stats_commit(p.stats, p.stats_stride ? p.stats_stride : 2, b, s_acc, ss_acc);
             }
         }
         tc_fence_before();
@@ -628,6 +682,7 @@ int launch_tc(const GemmParams& p, cudaStream_t st) {
 bool gemm_tf32_supported(const GemmParams& p) {
     if (p.K % 32 != 0 || p.K < 32 || p.K > 2048) return false;  // whole k-blocks (host pads with zero weights)
     if (p.epi == EPI_GRU) return p.H % 32 == 0 && p.Tn == 1 && p.Fo == 1 && p.N == 3 * p.H;
+    if (p.epi == EPI_LSTM) return p.H % 32 == 0 && p.Tn == 1 && p.Fo == 1 && p.N == 4 * p.H && p.Npad == p.N;
     if (p.Npad % gemm_tf32_tile_n(p.N) != 0) return false;
     if (p.epi == EPI_ELU_GATE) return p.Npad == 16 && p.C2 >= 1 && p.C2 <= 16 && p.W2 && p.bias2;
     if (p.epi == EPI_SKIP && (p.o2B != p.oB || p.o2T != p.oT || p.o2F != p.oF)) return false;
@@ -647,6 +702,7 @@ int launch_gemm_tf32(const GemmParams& p, cudaStream_t st) {
     SE_REQUIRE(gemm_tf32_supported(p), "gemm_tf32: unsupported shape");
     if (p.M <= 0) return 0;
     if (p.epi == EPI_GRU) return launch_tc<96>(p, st);
+    if (p.epi == EPI_LSTM) return launch_tc<128>(p, st);
     switch (gemm_tf32_tile_n(p.N)) {
         case 16: return launch_tc<16>(p, st);
         case 32: return launch_tc<32>(p, st);

@@ -43,6 +43,8 @@ enum Epilogue : int {
     EPI_GATE_STATS = 3,  // columns interleaved (trans_c, gated_c): out[c] = (a0+b0)*sigmoid(a1+b1); stats of out
     EPI_SKIP = 4,        // columns interleaved (mask_c, resid_c): out[c] = a0+b0 (stats); out2[c] = elu(a1+b1)
     EPI_GRU = 5,         // TF32 path only: columns per 32-unit group [r|z|n]; fused GRU cell update
+    EPI_LSTM = 7,        // TF32 path only: columns per 32-unit group [i|f|g|o]; fused LSTM cell (c in hprev, c' in out2)
+    EPI_RELU_STATS = 8,  // out[n] = relu(acc + bias[n]); stats accumulate the sum (and sum of squares) of out
     EPI_ELU_GATE = 6,    // TF32 path only, N <= 16: e = elu(acc + bias), then the gated 1x1 pair of CRN_ELU.py:240 in
                          // registers: out[c] = (W2[2c].e + b2[2c]) * sigmoid(W2[2c+1].e + b2[2c+1]); stats of out
 };
@@ -64,6 +66,7 @@ struct GemmParams {
     float* out2;
     long long o2B, o2T, o2F;
     double* stats;  // [B][2] (sum, sum of squares)
+    int stats_stride;  // doubles per stream in `stats` (0 = 2)
     // EPI_GRU extras: gi = input projection (b_ih included) [B][Tn_gi][3H]; h_prev/h_out rows [B][.][H]
     const float* gi;
     long long giB;

@@ -178,3 +178,42 @@ def make_mixture(num_streams: int, length: int, num_mics: int = 3, first_stream:
             mix[b] *= np.float32(0.95 / peak)
             src[b] *= np.float32(0.95 / peak)
     return mix, src
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# FullSubNet weights (reference fullsubnet.py:729-747: two SequenceModels = nn.LSTM + nn.Linear)
+# ----------------------------------------------------------------------------------------------------------------
+def fsn_param_shapes(num_freqs=201, num_mics=3, fb_hidden=512, sb_hidden=384, sb_num_neighbors=15, fb_num_neighbors=0,
+                     num_layers=2):
+    shapes = OrderedDict()
+
+    def seq(prefix, isz, hidden, osz):
+        for l in range(num_layers):
+            shapes[f"{prefix}.sequence_model.weight_ih_l{l}"] = (4 * hidden, isz if l == 0 else hidden)
+            shapes[f"{prefix}.sequence_model.weight_hh_l{l}"] = (4 * hidden, hidden)
+            shapes[f"{prefix}.sequence_model.bias_ih_l{l}"] = (4 * hidden,)
+            shapes[f"{prefix}.sequence_model.bias_hh_l{l}"] = (4 * hidden,)
+        shapes[f"{prefix}.fc_output_layer.weight"] = (osz, hidden)
+        shapes[f"{prefix}.fc_output_layer.bias"] = (osz,)
+
+    seq("fb_model", num_freqs * num_mics, fb_hidden, num_freqs)
+    seq("sb_model", (2 * sb_num_neighbors + 1) + (2 * fb_num_neighbors + 1), sb_hidden, 2)
+    return shapes
+
+
+def make_fsn_weights(seed: int = 0, **cfg):
+    """Deterministic float32 FullSubNet parameters at PyTorch-default scales (U(+-1/sqrt(hidden)) / U(+-1/sqrt(fan_in)))."""
+    out = OrderedDict()
+    for key, shape in fsn_param_shapes(**cfg).items():
+        n = int(np.prod(shape))
+        u = uniform01(seed, n, stream=zlib.crc32(key.encode())) * 2.0 - 1.0
+        if "sequence_model" in key:
+            fi = shape[0] // 4
+        else:
+            fi = shape[-1] if key.endswith("weight") else cfg_hidden_of(key, cfg)
+        out[key] = (u / np.sqrt(fi)).astype(np.float32).reshape(shape)
+    return out
+
+
+def cfg_hidden_of(key, cfg):
+    return cfg.get("fb_hidden", 512) if key.startswith("fb_model") else cfg.get("sb_hidden", 384)

@@ -1,0 +1,96 @@
+"""GPU parity of the FullSubNet chunk path (se_fsn_* behind speech_enhancement_mi_b200.fullsubnet) against fixtures of
+the unmodified reference (fp32 CPU run) and the oracle.  The LSTM GEMMs run on TF32 tensor cores (fp32 accumulate, fp32
+cell state): stated tolerance = 2e-2 x peak on mask / waveform and >= 40 dB SI-SDR against the reference waveform; the
+integer index work (unfold) is bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from common import GOLDEN, rel_err, si_sdr_db
+from oracle import synth
+from oracle.fsn_oracle import FSNOracle, unfold
+
+pytestmark = pytest.mark.gpu
+
+FSN_SMALL = dict(num_freqs=201, num_mics=3, fb_hidden=64, sb_hidden=32, sb_num_neighbors=15, fb_num_neighbors=0,
+                 num_layers=2)
+FSN_FULL = dict(num_freqs=201, num_mics=3, fb_hidden=512, sb_hidden=384, sb_num_neighbors=15, fb_num_neighbors=0,
+                num_layers=2)
+TOL_REL, TOL_DB = 2e-2, 40.0
+
+
+def load(tag):
+    z = np.load(os.path.join(GOLDEN, f"{tag}.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def make(cfg, seed, **kw):
+    from speech_enhancement_mi_b200 import fullsubnet
+    m = fullsubnet.FullSubNet(
+        num_freqs=cfg["num_freqs"], look_ahead=0, sequence_model="LSTM", fb_num_neighbors=cfg["fb_num_neighbors"],
+        sb_num_neighbors=cfg["sb_num_neighbors"], fb_output_activate_function="ReLU", sb_output_activate_function=False,
+        fb_model_hidden_size=cfg["fb_hidden"], sb_model_hidden_size=cfg["sb_hidden"], num_mics=cfg["num_mics"],
+        num_layers=cfg["num_layers"], weight_init=False, sample_rate=16000, segment_length=3200, win_length=25,
+        hop_length=10, n_fft=400, **kw)
+    w = synth.make_fsn_weights(seed=seed, **cfg)
+    missing, unexpected = m.load_state_dict({k: torch.from_numpy(v) for k, v in w.items()}, strict=True)
+    assert not missing and not unexpected
+    return m.eval()
+
+
+def test_unfold_bit_exact():
+    from speech_enhancement_mi_b200.fullsubnet import BaseModel
+    g = load("fsn_small")
+    x = torch.from_numpy(g["unfold_in"]).cuda()
+    assert np.array_equal(BaseModel.unfold(x, 2).cpu().numpy(), g["unfold_out"])
+    assert np.array_equal(BaseModel.unfold(x, 0).cpu().numpy(), g["unfold0_out"])
+    big = torch.randn(2, 1, 201, 21)
+    assert np.array_equal(BaseModel.unfold(big.cuda(), 15).cpu().numpy(), unfold(big, 15).numpy())
+
+
+@pytest.mark.parametrize("tag,cfg,seed", [("fsn_small", FSN_SMALL, 11), ("fsn_full", FSN_FULL, 5)])
+def test_forward_chunk_matches_reference(tag, cfg, seed):
+    g = load(tag)
+    m = make(cfg, seed)
+    x1 = torch.from_numpy(g["x_chunk1"]).cuda()
+    m.reset_state(x1.shape[0])
+    f1 = m.forward(x1).cpu().numpy()
+    f2 = m.forward(x1).cpu().numpy()  # running CumLayerNorm mean + carried LSTM state
+    assert rel_err(f1, g["fwd_chunk1"]) < TOL_REL
+    assert rel_err(f2, g["fwd_chunk1_again"]) < TOL_REL
+
+
+def test_realtime_process_matches_reference():
+    g = load("fsn_small")
+    m = make(FSN_SMALL, 11)
+    B, L = int(g["meta"][1]), int(g["meta"][2])
+    mix, src = synth.make_mixture(B, L)
+    s3 = torch.from_numpy(np.repeat(src[:, None, :], 3, axis=1).copy())
+    pred, crm, sf, xf = m.realtime_process(torch.from_numpy(mix).cuda(), s3.cuda(), flag=False, train=False)
+    pred = pred.cpu().numpy()
+    assert pred.shape == g["out"].shape
+    assert rel_err(crm.cpu().numpy(), g["crm"]) < TOL_REL
+    assert rel_err(sf.cpu().numpy(), g["sf"]) < 1e-5 and rel_err(xf.cpu().numpy(), g["xf"]) < 1e-5
+    assert np.abs(pred - g["out"]).max() < TOL_REL * max(1.0, np.abs(g["out"]).max())
+    assert si_sdr_db(pred, g["out"]) > TOL_DB
+    mix2, _ = synth.make_mixture(B, L // 2, first_stream=100)
+    p2 = m.realtime_process(torch.from_numpy(mix2).cuda(), None, flag=True, train=False).cpu().numpy()
+    assert np.abs(p2 - g["out_cont"]).max() < TOL_REL * max(1.0, np.abs(g["out_cont"]).max())
+    # CPU tensors in, CPU tensors out (predict_fullsubnet.py uses .cuda(); the drop-in accepts both)
+    p3 = m.realtime_process(torch.from_numpy(mix), None, flag=False, train=False)
+    assert not p3.is_cuda and np.abs(p3.numpy() - pred).max() < 1e-5
+
+
+def test_streams_independent_and_oracle_agrees():
+    m = make(FSN_SMALL, 11)
+    o = FSNOracle(synth.make_fsn_weights(seed=11, **FSN_SMALL), **FSN_SMALL)
+    mix, _ = synth.make_mixture(4, 5000)
+    x = torch.from_numpy(mix)
+    y = m.realtime_process(x.cuda(), None, flag=False, train=False).cpu().numpy()
+    with torch.no_grad():
+        want, _ = o.realtime_process(x)
+    assert np.abs(y - want.numpy()).max() < TOL_REL * max(1.0, float(want.abs().max()))
+    yb = m.realtime_process(x[2:3].cuda(), None, flag=False, train=False).cpu().numpy()
+    assert np.abs(yb[0] - y[2]).max() < 1e-4
