@@ -29,6 +29,8 @@ extern "C" {
 /* arithmetic of the dense contractions */
 #define SE_PRECISION_FP32 0 /* fp32 FMA on CUDA cores (exact mode)                     */
 #define SE_PRECISION_TF32 1 /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM (fast)  */
+#define SE_PRECISION_FP16 2 /* tcgen05.mma kind::f16: GEMM operands (activations between layers, weights) stored as
+                               fp16 (same 11-bit significand as tf32), fp32 accumulate, fp32 statistics / state / I/O */
 
 /* Mirrors the kwargs of CRN_ELU.TemporalCRN.__init__ (CRN_ELU.py:321-323; config.yaml:205-217), with
  * win_length / hop_length already converted from milliseconds to samples (speechbrain STFT: round(sr/1000*ms)). */

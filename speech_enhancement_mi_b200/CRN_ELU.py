@@ -89,8 +89,8 @@ class SequenceModel(nn.Module):
 class TemporalCRN(nn.Module):
     """B200-native ``CRN_ELU.TemporalCRN`` (reference CRN_ELU.py:314-535).
 
-    Extra keyword arguments (not in the reference, all optional): ``precision`` ("fp32" exact CUDA-core arithmetic or
-    "tf32" tcgen05 tensor cores), ``max_streams`` (capacity of the per-stream state arena; grows on demand),
+    Extra keyword arguments (not in the reference, all optional): ``precision`` ("fp32" exact CUDA-core arithmetic,
+    "tf32" tcgen05 tensor cores on fp32 storage, "fp16" tcgen05 tensor cores with fp16 operand storage and fp32 accumulation), ``max_streams`` (capacity of the per-stream state arena; grows on demand),
     ``device`` (CUDA device index used when tensors arrive on the CPU, as in predict.py:48).
     """
 
@@ -143,8 +143,8 @@ class TemporalCRN(nn.Module):
         # ---- native side -----------------------------------------------------------------------------------
         if precision is None:
             precision = os.environ.get("SE_B200_PRECISION", "fp32")
-        if precision not in ("fp32", "tf32"):
-            raise ValueError(f"precision must be 'fp32' or 'tf32', got {precision!r}")
+        if precision not in ("fp32", "tf32", "fp16"):
+            raise ValueError(f"precision must be 'fp32', 'tf32' or 'fp16', got {precision!r}")
         self.precision = precision
         self._max_streams = int(max_streams) if max_streams else 0
         self._device_index = device
@@ -172,7 +172,8 @@ class TemporalCRN(nn.Module):
         cfg.win_length = self.win_samples
         cfg.hop_length = self.hop_samples
         cfg.variant = self._variant
-        cfg.precision = _native.SE_PRECISION_TF32 if self.precision == "tf32" else _native.SE_PRECISION_FP32
+        cfg.precision = {"fp32": _native.SE_PRECISION_FP32, "tf32": _native.SE_PRECISION_TF32,
+                         "fp16": _native.SE_PRECISION_FP16}[self.precision]
         cfg.max_streams = capacity
         return cfg
 

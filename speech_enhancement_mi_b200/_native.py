@@ -15,6 +15,7 @@ SE_VARIANT_CRN_ELU = 0
 SE_VARIANT_DISTILLED = 1
 SE_PRECISION_FP32 = 0
 SE_PRECISION_TF32 = 1
+SE_PRECISION_FP16 = 2
 
 
 class SeCrnConfig(C.Structure):

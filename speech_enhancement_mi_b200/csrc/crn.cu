@@ -8,6 +8,7 @@
 //     look-ahead inside the chunk) and one zero row on each side of F (stride-2 phase split, taps {0,2,4} / {1,3}).
 // The carried state of a stream is therefore the leading frames of its conv-input buffers, slot 0 of the two GRU
 // hidden sequences and the K/2 overlap-add carry; "roll" moves the trailing frames to the front after each chunk.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdlib.h>
@@ -40,8 +41,10 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
     int C = 0, F = 0;
     int padT0 = 0, padT1 = 0, padF0 = 0, padF1 = 0;
     int Tp = 0, Fp = 0;
-    long long sB = 0, sT = 0, sF = 0;
-    float* interior() const { return base + padT0 * sT + padF0 * sF; }
+    long long sB = 0, sT = 0, sF = 0;  // strides in ELEMENTS
+    int esz = 4;                       // element size: 4 (fp32) or 2 (fp16 operand storage, SE_PRECISION_FP16)
+    float* at(long long elems) const { return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + elems * esz); }
+    float* interior() const { return at(padT0 * sT + padF0 * sF); }
     long long per_stream() const { return sB; }
 };
 
@@ -135,7 +138,16 @@ struct se_ctx {
 
     IoDesc* io_dev = nullptr;
     bool use_graph = true;
-    bool tf32 = false;
+    bool tf32 = false;  // tensor-core path (tf32 or fp16 operands)
+    bool half = false;  // operands of the tensor-core GEMMs are stored as fp16 (SE_PRECISION_FP16)
+    int esz = 4;        // element size of the GEMM-operand activations
+    int ue = 4;         // elements per 16-byte gather unit
+    int kblock = 32;    // elements per k-block
+    float* h32[2] = {nullptr, nullptr};  // fp16 mode: fp32 master copy of the GRU state [maxB][H] per layer
+    void* warena_h = nullptr;            // fp16 mode: the weight arena converted to fp16 (same indexing)
+    float* E(float* base, long long elems) const {  // element offset into an operand buffer
+        return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + elems * esz);
+    }
     unsigned tc_mask = 0xffffffffu;  // SE_B200_TC_MASK: bit per Stage that may use the tensor-core GEMM (debug)
     std::map<int, cudaGraphExec_t> graphs;  // keyed by B
     cudaStream_t own_stream = nullptr;
@@ -181,7 +193,8 @@ int make_act(se_ctx* c, Act& a, int C, int F, int Tn, int padT0, int padT1, int 
     a.sF = C;
     a.sT = (long long)a.Fp * C;
     a.sB = a.sT * a.Tp;
-    return dev_alloc(c, &a.base, (size_t)a.sB * c->maxB);
+    a.esz = c->esz;
+    return dev_alloc(c, reinterpret_cast<char**>(&a.base), (size_t)a.sB * c->maxB * a.esz);
 }
 
 // ---- parameter registry (order of TemporalCRN.state_dict() without the `net.0` aliases; CRN_ELU.py:335-365) -------
@@ -240,7 +253,7 @@ struct PackedW {
 PackedW reserve_packed(se_ctx* c, int N, int K) {
     PackedW pw;
     pw.Npad = round_up(N, gemm_tf32_tile_n(N));
-    pw.K = round_up(K, 32);
+    pw.K = round_up(K, c->kblock);
     pw.w_off = c->reserve_w((size_t)pw.Npad * pw.K);
     pw.b_off = c->reserve_w(pw.Npad);
     return pw;
@@ -251,7 +264,7 @@ void fill_gemm_common(se_ctx* c, GemmParams& g, const PackedW& pw, int N, int ko
     g.K = pw.K;
     g.N = N;
     g.Npad = pw.Npad;
-    (void)c;
+    g.a_half = c->half ? 1 : 0;
     (void)koff_off;
 }
 
@@ -290,8 +303,9 @@ struct Builder {
 
     // identity koff for a dense K-contiguous operand
     int koff_dense(int K) {
-        std::vector<int> v(K / 4);
-        for (int u = 0; u < K / 4; ++u) v[u] = 4 * u;
+        const int U = c->ue;
+        std::vector<int> v(K / U);
+        for (int u = 0; u < K / U; ++u) v[u] = U * u;
         return c->reserve_k(v);
     }
 
@@ -313,6 +327,7 @@ struct Builder {
         op.kind = OP_NORM;
         op.stage = stage;
         op.n = n;
+        op.n.out_half = c->half ? 1 : 0;  // every normalised tensor is the operand of a following GEMM
         take_meta(op);
         c->ops.push_back(op);
         fix.push_back({NONE, NONE, -1, w_off, b_off, wr_off, br_off});
@@ -357,12 +372,13 @@ struct Builder {
         // (1) conv + ELU -> tmp_e [B][T][Fo][Cp_out]   (fuse_gate: + gated 1x1 pair + statistics -> tmp_y, skipping 2)
         {
             const int K = KT * KF * Cp_in;
-            std::vector<int> koff(K / 4);
+            const int U = c->ue;
+            std::vector<int> koff(K / U);
             for (int kt = 0; kt < KT; ++kt)
                 for (int kf = 0; kf < KF; ++kf)
-                    for (int c4 = 0; c4 < Cp_in / 4; ++c4)
-                        koff[((kt * KF + kf) * Cp_in) / 4 + c4] =
-                            (int)(kt * dilT * in.sT + kf * dilF * in.sF + 4 * c4);
+                    for (int cu = 0; cu < Cp_in / U; ++cu)
+                        koff[((kt * KF + kf) * Cp_in) / U + cu] =
+                            (int)(kt * dilT * in.sT + kf * dilF * in.sF + U * cu);
             const int k_off = c->reserve_k(koff);
             PackedW pw = reserve_packed(c, Cout_real, K);
             c->packers.push_back([=](const HostParams& hp, float* arena) {
@@ -413,6 +429,8 @@ struct Builder {
             if (fuse_gate) {
                 g.C2 = Cout_real;
                 g.stats = stats;
+            } else {
+                g.out_half = c->half ? 1 : 0;  // tmp_e is the operand of the gate GEMM
             }
             {
                 const double in_b = 4.0 * Cin_real * in.Tp * in.F, conv_fl = 2.0 * rows * Cout_real * (KT * KF * Cin_real);
@@ -506,12 +524,13 @@ struct Builder {
             const int nkf = 3;
             const int Fo = Fin;
             const int K = KT * nkf * Cin;
-            std::vector<int> koff(K / 4);
+            const int U = c->ue;
+            std::vector<int> koff(K / U);
             for (int kt = 0; kt < KT; ++kt)
                 for (int j = 0; j < nkf; ++j)
-                    for (int c4 = 0; c4 < Cin / 4; ++c4) {
+                    for (int cu = 0; cu < Cin / U; ++cu) {
                         const long long frame = (long long)(KT - 1 - kt) * d;
-                        koff[((kt * nkf + j) * Cin) / 4 + c4] = (int)(frame * in.sT + (2 - j) * in.sF + 4 * c4);
+                        koff[((kt * nkf + j) * Cin) / U + cu] = (int)(frame * in.sT + (2 - j) * in.sF + U * cu);
                     }
             const int k_off = c->reserve_k(koff);
             PackedW pw = reserve_packed(c, 2 * Cout_real, K);
@@ -637,17 +656,25 @@ int build_ctx(se_ctx* c) {
     SE_REQUIRE(g.num_layers == 2, "num_layers must be 2 (config.yaml:210)");
     SE_REQUIRE(g.hidden % 16 == 0 && g.hidden > 0, "hidden must be a positive multiple of 16");
     SE_REQUIRE(g.max_streams > 0, "max_streams must be positive");
-    SE_REQUIRE(g.precision == SE_PRECISION_FP32 || g.precision == SE_PRECISION_TF32, "unknown precision");
+    SE_REQUIRE(g.precision == SE_PRECISION_FP32 || g.precision == SE_PRECISION_TF32 || g.precision == SE_PRECISION_FP16,
+               "unknown precision");
     SE_REQUIRE(g.variant == SE_VARIANT_CRN_ELU || g.variant == SE_VARIANT_DISTILLED, "unknown variant");
     c->maxB = g.max_streams;
     c->L = g.num_levels;
     c->C0 = 2 * g.num_inputs - 1;
     c->student = g.variant == SE_VARIANT_DISTILLED;
     c->H = g.hidden;
-    c->tf32 = g.precision == SE_PRECISION_TF32;
+    c->tf32 = g.precision != SE_PRECISION_FP32;
+    c->half = g.precision == SE_PRECISION_FP16;
+    c->esz = c->half ? 2 : 4;
+    c->ue = 16 / c->esz;
+    c->kblock = 128 / c->esz;
     if (const char* e = getenv("SE_B200_TC_MASK")) c->tc_mask = (unsigned)strtoul(e, nullptr, 0);
-    for (int i = 0; i < c->L; ++i)
+    for (int i = 0; i < c->L; ++i) {
         SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
+        SE_REQUIRE(!c->half || g.num_channels[i] % 8 == 0, "fp16 mode: num_channels must be multiples of 8");
+    }
+    SE_REQUIRE(!c->half || g.hidden % 32 == 0, "fp16 mode: hidden must be a multiple of 32");
     int F = NBIN;
     for (int i = 0; i < c->L; ++i) {
         F = (F - 1) / 2 + 1;
@@ -694,16 +721,19 @@ int build_ctx(se_ctx* c) {
         const int Co = g.num_channels[c->L - 2 - j];
         upd((size_t)T * (2 * Fin) * Co);
     }
-    if (dev_alloc(c, &c->tmp_e, tmp * maxB)) return 1;
+    if (dev_alloc(c, reinterpret_cast<char**>(&c->tmp_e), tmp * maxB * c->esz)) return 1;
     if (dev_alloc(c, &c->tmp_y, tmp * maxB)) return 1;
     if (dev_alloc(c, &c->tmp_rm, tmp * maxB)) return 1;
     if (dev_alloc(c, &c->tmp_rr, tmp * maxB)) return 1;
-    if (dev_alloc(c, &c->xg, (size_t)T * c->feat * maxB)) return 1;
+    if (dev_alloc(c, reinterpret_cast<char**>(&c->xg), (size_t)T * c->feat * maxB * c->esz)) return 1;
     if (dev_alloc(c, &c->fcraw, (size_t)T * c->feat * maxB)) return 1;
     if (dev_alloc(c, &c->gi, (size_t)T * 3 * H * maxB)) return 1;
     if (dev_alloc(c, &c->gh, (size_t)3 * H * maxB)) return 1;
     for (int l = 0; l < 2; ++l)
-        if (dev_alloc(c, &c->hseq[l], (size_t)(T + 1) * H * maxB)) return 1;
+        if (dev_alloc(c, reinterpret_cast<char**>(&c->hseq[l]), (size_t)(T + 1) * H * maxB * c->esz)) return 1;
+    if (c->half)
+        for (int l = 0; l < 2; ++l)
+            if (dev_alloc(c, &c->h32[l], (size_t)H * maxB)) return 1;
     if (dev_alloc(c, &c->noisy, (size_t)T * NBIN * 2 * maxB)) return 1;
     if (dev_alloc(c, &c->ylast, (size_t)T * NBIN * 2 * maxB)) return 1;
     if (dev_alloc(c, &c->carry, (size_t)PHOP * maxB)) return 1;
@@ -760,6 +790,7 @@ int build_ctx(se_ctx* c) {
             op.pc.oT = nx.sT;
             op.pc.oF = nx.sF;
             op.pc.out_vec8 = 1;
+            op.pc.out_half = c->half ? 1 : 0;
         }
         op.label = name + ".fused";
         op.alg_flops = 2.0 * T * NBIN * 5 * (125 + 10);
@@ -814,7 +845,7 @@ int build_ctx(se_ctx* c) {
                 gp.sB = (long long)T * feat;
                 gp.sT = feat;
             } else {
-                gp.A = c->hseq[0] + H;
+                gp.A = c->E(c->hseq[0], H);
                 gp.sB = (long long)(T + 1) * H;
                 gp.sT = H;
             }
@@ -833,7 +864,7 @@ int build_ctx(se_ctx* c) {
         }
         const int k_off = b.koff_dense(H);
         PackedW pw = reserve_packed(c, 3 * H, H);
-        const bool fused = c->tf32 && ((c->tc_mask >> ST_GRU) & 1u) && H % 32 == 0;
+        const bool fused = c->half || (c->tf32 && ((c->tc_mask >> ST_GRU) & 1u) && H % 32 == 0);
         c->packers.push_back([=](const HostParams& hp, float* arena) {
             const std::vector<float>& w = hp.at("gru.sequence_model.weight_hh_l" + s);
             const std::vector<float>& bh = hp.at("gru.sequence_model.bias_hh_l" + s);
@@ -846,18 +877,27 @@ int build_ctx(se_ctx* c) {
         });
         for (int t = 0; t < T && fused; ++t) {
             GemmParams gp{};
-            gp.A = c->hseq[l] + (long long)t * H;
+            gp.A = c->E(c->hseq[l], (long long)t * H);
             gp.sB = (long long)(T + 1) * H;
             gp.Tn = 1;
             gp.Fo = 1;
             fill_gemm_common(c, gp, pw, 3 * H, k_off);
             gp.epi = EPI_GRU;
-            gp.out = c->hseq[l] + (long long)(t + 1) * H;
-            gp.oB = (long long)(T + 1) * H;
             gp.gi = c->gi + (long long)t * 3 * H;
             gp.giB = (long long)T * 3 * H;
-            gp.hprev = c->hseq[l] + (long long)t * H;
-            gp.hB = (long long)(T + 1) * H;
+            if (c->half) {  // fp32 master state updated in place + fp16 history = operand of the following GEMMs
+                gp.hprev = c->h32[l];
+                gp.hB = H;
+                gp.out = c->h32[l];
+                gp.oB = H;
+                gp.out_h2 = c->E(c->hseq[l], (long long)(t + 1) * H);
+                gp.o2B = (long long)(T + 1) * H;
+            } else {
+                gp.out = c->hseq[l] + (long long)(t + 1) * H;
+                gp.oB = (long long)(T + 1) * H;
+                gp.hprev = c->hseq[l] + (long long)t * H;
+                gp.hB = (long long)(T + 1) * H;
+            }
             gp.H = H;
             b.meta("gru.l" + s + ".step" + std::to_string(t), 2.0 * 3 * H * H, 4.0 * (3 * H + 2 * H));
             b.push_gemm(ST_GRU, gp, 1, pw, k_off);
@@ -896,7 +936,7 @@ int build_ctx(se_ctx* c) {
             }
         });
         GemmParams gp{};
-        gp.A = c->hseq[1] + H;
+        gp.A = c->E(c->hseq[1], H);
         gp.sB = (long long)(T + 1) * H;
         gp.sT = H;
         gp.sF = 0;
@@ -964,13 +1004,15 @@ int build_ctx(se_ctx* c) {
 
     // ---- arenas -------------------------------------------------------------------------------------------------
     if (dev_alloc(c, &c->warena, c->warena_floats)) return 1;
+    if (c->half && dev_alloc(c, reinterpret_cast<char**>(&c->warena_h), c->warena_floats * 2)) return 1;
     if (dev_alloc(c, &c->karena, c->khost.size())) return 1;
     SE_CUDA_OK(cudaMemcpy(c->karena, c->khost.data(), c->khost.size() * sizeof(int), cudaMemcpyHostToDevice));
     for (size_t i = 0; i < c->ops.size(); ++i) {
         Op& op = c->ops[i];
         const OpFix& f = b.fix[i];
         if (op.kind == OP_GEMM) {
-            op.g.W = c->warena + f.w_off;
+            op.g.W = (c->half && op.g.a_half) ? static_cast<const void*>(reinterpret_cast<const unsigned short*>(c->warena_h) + f.w_off)
+                                              : static_cast<const void*>(c->warena + f.w_off);
             op.g.bias = c->warena + f.b_off;
             op.g.koff = c->karena + f.k_off;
             if (f.w2_off != NONE) {
@@ -1004,8 +1046,15 @@ int build_ctx(se_ctx* c) {
         c->zero_tab.e[c->zero_tab.n++] = e;
         c->state_floats += 5 * 4 * NBIN;
     }
-    for (const Act& a : c->enc_in) add_state(a.base, a.sB, (long long)T * a.sT, (int)(a.padT0 * a.sT));
-    for (int l = 0; l < 2; ++l) add_state(c->hseq[l], (long long)(T + 1) * H, (long long)T * H, H);
+    const int fpe = 4 / c->esz;  // operand elements per float: the roll / zero kernels move 4-byte units
+    for (const Act& a : c->enc_in)
+        add_state(a.base, a.sB / fpe, (long long)T * a.sT / fpe, (int)(a.padT0 * a.sT / fpe));
+    for (int l = 0; l < 2; ++l) add_state(c->hseq[l], (long long)(T + 1) * H / fpe, (long long)T * H / fpe, H / fpe);
+    if (c->half)
+        for (int l = 0; l < 2; ++l) {
+            RollEntry e{c->h32[l], H, 0, 0, H};
+            c->zero_tab.e[c->zero_tab.n++] = e;
+        }
     {
         RollEntry e{c->carry, PHOP, 0, 0, PHOP};
         c->zero_tab.e[c->zero_tab.n++] = e;
@@ -1021,7 +1070,9 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st) {
             GemmParams g = op.g;
             g.M = B * op.rows_per_stream;
             if (g.epi == EPI_GRU || g.epi == EPI_ELU_GATE) return launch_gemm_tf32(g, st);
-            if (c->tf32 && ((c->tc_mask >> op.stage) & 1u) && gemm_tf32_supported(g)) return launch_gemm_tf32(g, st);
+            if (c->tf32 && (c->half || ((c->tc_mask >> op.stage) & 1u)) && gemm_tf32_supported(g))
+                return launch_gemm_tf32(g, st);
+            SE_REQUIRE(!c->half, "internal: fp16 operands need the tensor-core GEMM (" + op.label + ")");
             return launch_gemm_fp32(g, st);
         }
         case OP_NORM: {
@@ -1213,6 +1264,11 @@ int se_crn_bind_weights(se_ctx* c, const float* const* ptrs, int n, void* stream
     for (const PackFn& f : c->packers) f(hp, arena.data());
     SE_CUDA_OK(cudaDeviceSynchronize());  // no step may still read the old weights
     SE_CUDA_OK(cudaMemcpy(c->warena, arena.data(), arena.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (c->half) {  // fp16 copy of the whole arena (same indexing): the GEMM weight operands are read from it
+        std::vector<__half> ah(arena.size());
+        for (size_t i = 0; i < arena.size(); ++i) ah[i] = __float2half_rn(arena[i]);
+        SE_CUDA_OK(cudaMemcpy(c->warena_h, ah.data(), ah.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    }
     c->weights_bound = true;
     return 0;
 }
@@ -1400,9 +1456,11 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
     const std::string n(name);
     const float* src = nullptr;
     int t = T, f = 1, ch = 1;
+    int src_esz = 4;
     long long sT = 0, sF = 0;
     auto from_act = [&](const Act& a) {
-        src = a.interior() + (long long)b * a.sB;
+        src_esz = a.esz;
+        src = a.at(a.padT0 * a.sT + a.padF0 * a.sF + (long long)b * a.sB);
         f = a.F;
         ch = a.C;
         sT = a.sT;
@@ -1440,8 +1498,15 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
         return 0;
     } else if ((i = idx_of("enc_in", c->L)) >= 0) from_act(c->enc_in[i]);
     else if ((i = idx_of("dec_in", c->L)) >= 0) from_act(c->dec_in[i]);
-    else if ((i = idx_of("hseq", 2)) >= 0) compact(c->hseq[i], 1, c->H, T + 1);
-    else if (n == "xg") compact(c->xg, c->Fg, c->Cg);
+    else if ((i = idx_of("hseq", 2)) >= 0) {
+        compact(c->hseq[i], 1, c->H, T + 1);
+        src_esz = c->esz;
+        src = c->E(c->hseq[i], (long long)b * (T + 1) * c->H);
+    } else if (n == "xg") {
+        compact(c->xg, c->Fg, c->Cg);
+        src_esz = c->esz;
+        src = c->E(c->xg, (long long)b * T * c->feat);
+    }
     else if (n == "fcraw") compact(c->fcraw, c->Fg, c->Cg);
     else if (n == "ylast") compact(c->ylast, NBIN, 2);
     else if (n == "noisy") compact(c->noisy, NBIN, 2);
@@ -1450,6 +1515,13 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
     dims[1] = f;
     dims[2] = ch;
     SE_REQUIRE((int64_t)t * f * ch <= max_floats, "se_debug_read: destination too small");
+    if (src_esz == 2) {  // fp16 operand buffer: convert on the host
+        std::vector<__half> tmp((size_t)t * f * ch);
+        SE_CUDA_OK(cudaMemcpy2D(tmp.data(), (size_t)f * ch * 2, src, (size_t)sT * 2, (size_t)f * ch * 2, t,
+                                cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < tmp.size(); ++i) host_dst[i] = __half2float(tmp[i]);
+        return 0;
+    }
     SE_CUDA_OK(cudaMemcpy2D(host_dst, (size_t)f * ch * sizeof(float), src, (size_t)sT * sizeof(float),
                             (size_t)f * ch * sizeof(float), t, cudaMemcpyDeviceToHost));
     (void)sF;

@@ -1,5 +1,7 @@
 // HBM-bound elementwise kernels of the CRN path: GlobalLayerNorm application fused with the residual add / gated
 // skip blend that follows it, the fp32-path GRU cell update, the causal-state roll, framing and overlap-add.
+#include <cuda_fp16.h>
+
 #include "se_internal.h"
 
 namespace se {
@@ -76,7 +78,16 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(NormApplyParams p) {
             o.z = m2 * rr.z + (1.0f - m2) * o.z;
             o.w = m3 * rr.w + (1.0f - m3) * o.w;
         }
-        *reinterpret_cast<float4*>(orow + f * p.oF + c) = o;
+        if (p.out_half) {
+            __half* oh = reinterpret_cast<__half*>(p.out) + b * p.oB + t * p.oT + f * p.oF + c;
+            const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+            uint2 u;
+            u.x = *reinterpret_cast<const unsigned*>(&lo);
+            u.y = *reinterpret_cast<const unsigned*>(&hi);
+            *reinterpret_cast<uint2*>(oh) = u;
+        } else {
+            *reinterpret_cast<float4*>(orow + f * p.oF + c) = o;
+        }
     }
 }
 

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(kThreads) gemm_fp32_kernel(GemmParams p) {
             const int r = m - b * rowsPerStream;
             const int t = r / p.Fo;
             const int f = r - t * p.Fo;
-            a_base[i] = p.A + b * p.sB + t * p.sT + f * p.sF;
+            a_base[i] = reinterpret_cast<const float*>(p.A) + b * p.sB + t * p.sT + f * p.sF;
         }
     }
 
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(kThreads) gemm_fp32_kernel(GemmParams p) {
                 const int row = u / (BK / 4), ku = u % (BK / 4);
                 const int n = n0 + row, k = k0 + ku * 4;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (n < p.Npad && k < p.K) v = *reinterpret_cast<const float4*>(p.W + (long long)n * p.K + k);
+                if (n < p.Npad && k < p.K)
+                    v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.W) + (long long)n * p.K + k);
                 Ws[ku * 4 + 0][row] = v.x;
                 Ws[ku * 4 + 1][row] = v.y;
                 Ws[ku * 4 + 2][row] = v.z;

@@ -18,6 +18,7 @@
 //                      epilogue function, parks the chunk in a warp-private staging buffer and the warp writes it out
 //                      with coalesced 16-byte stores.
 // Every mbarrier wait is bounded (trap after ~2 s) so that a protocol bug cannot hang the GPU.
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #include "se_internal.h"
@@ -26,8 +27,8 @@ namespace se {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BK = 32;  // floats per k-block = one 128-byte swizzle atom
-constexpr int A_STAGE_BYTES = BM * BK * 4;
+constexpr int BKB = 128;  // bytes per k-block row = one 128-byte swizzle atom: 32 tf32 (fp32 storage) or 64 fp16
+constexpr int A_STAGE_BYTES = BM * BKB;
 constexpr int kProducerThreads = 128;
 constexpr int kFirstEpiWarp = 5;
 constexpr int SPW = 36;  // pitch (floats) of a warp-private staging row: 32 columns + 4 (conflict-free float4 rows)
@@ -83,14 +84,25 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+// one M128 x N x K(32 bytes) MMA; operands: fp32 storage read as TF32 (K = 8) or fp16 (K = 16), fp32 accumulate
+template <typename AT>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+    if (sizeof(AT) == 4) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
 }
 // 16 / 8 consecutive fp32 accumulator columns of this thread's TMEM lane (issue only; tmem_ld_wait before use)
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t* r) {
@@ -155,7 +167,7 @@ struct Cfg {
     static constexpr uint32_t TMEM_COLS =
         TMEM_COLS_RAW <= 32 ? 32
                             : (TMEM_COLS_RAW <= 64 ? 64 : (TMEM_COLS_RAW <= 128 ? 128 : (TMEM_COLS_RAW <= 256 ? 256 : 512)));
-    static constexpr int B_STAGE_BYTES = BN * BK * 4;
+    static constexpr int B_STAGE_BYTES = BN * BKB;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int KOFF_MAX = 512;  // K <= 2048
@@ -177,9 +189,42 @@ struct Cfg {
 // consecutive float4 of a row.  `cnt` = valid columns of the chunk (<= W), `ooff` = this lane's row offset (-1: none)
 template <int W, bool ROWCNT = false>
 __device__ __forceinline__ void store_chunk(const float* stg, int col0, float* out, long long ooff, int cnt, bool vec4,
-                                            int lane) {
+                                            int lane, bool out_half = false) {
     // ROWCNT: `cnt` is this lane's (= row's) own limit instead of a warp-uniform one
     const unsigned full = 0xffffffffu;
+    if (out_half) {  // fp16 destination (operand of the next GEMM): `out` is a __half*, offsets are in halves
+        __half* oh = reinterpret_cast<__half*>(out);
+        if (vec4) {
+            constexpr int C4 = W / 4;
+            constexpr int RPI = 32 / C4;
+            const int c4 = lane % C4;
+#pragma unroll
+            for (int i = 0; i < 32 / RPI; ++i) {
+                const int r = i * RPI + lane / C4;
+                const long long off = __shfl_sync(full, ooff, r);
+                const int rc = ROWCNT ? __shfl_sync(full, cnt, r) : cnt;
+                if (off >= 0 && 4 * c4 < rc) {
+                    const float4 v = *reinterpret_cast<const float4*>(stg + r * SPW + col0 + 4 * c4);
+                    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+                    uint2 u;
+                    u.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    u.y = *reinterpret_cast<const uint32_t*>(&hi);
+                    *reinterpret_cast<uint2*>(oh + off + 4 * c4) = u;
+                }
+            }
+        } else {
+            constexpr int RPI = 32 / W;
+            const int c = lane % W;
+#pragma unroll 4
+            for (int i = 0; i < 32 / RPI; ++i) {
+                const int r = i * RPI + lane / W;
+                const long long off = __shfl_sync(full, ooff, r);
+                const int rc = ROWCNT ? __shfl_sync(full, cnt, r) : cnt;
+                if (off >= 0 && c < rc) oh[off + c] = __float2half_rn(stg[r * SPW + col0 + c]);
+            }
+        }
+        return;
+    }
     if (vec4) {
         constexpr int C4 = W / 4;     // float4 per row
         constexpr int RPI = 32 / C4;  // rows per warp instruction
@@ -230,8 +275,10 @@ __device__ __forceinline__ void small_gate(const float* s_w2, const float* e, in
     }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const GemmParams p) {
+template <int BN, typename AT>
+__global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const GemmParams p) {
+    constexpr int BKE = BKB / (int)sizeof(AT);  // elements per k-block
+    constexpr int UE = 16 / (int)sizeof(AT);    // elements per 16-byte gather unit
     using S = Cfg<BN>;
     constexpr int STAGES = S::STAGES;
     constexpr int NACC = S::NACC;
@@ -253,12 +300,15 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
     const int lane = tid & 31;
-    const int nkb = p.K / BK;  // K and Npad are padded by the host (zero weights): no bounds checks on either operand
+    const int nkb = p.K / BKE;  // K and Npad are padded by the host (zero weights): no bounds checks on either operand
     const int ntn = (p.epi == EPI_GRU ? p.N : p.Npad) / BN;
     const int ntiles = ((p.M + BM - 1) / BM) * ntn;
     const int rowsPerStream = p.Tn * p.Fo;
 
-    for (int i = tid; i < p.K / 4; i += S::THREADS) s_koff[i] = __ldg(p.koff + i);
+    for (int i = tid; i < p.K / UE; i += S::THREADS) s_koff[i] = __ldg(p.koff + i);
+    const AT* const Abase = reinterpret_cast<const AT*>(p.A);
+    const AT* const Wbase = reinterpret_cast<const AT*>(p.W);
+    const bool out_half = p.out_half != 0;
     if (BN == 16 && p.epi == EPI_ELU_GATE) {
         for (int i = tid; i < 2 * p.C2 * 16; i += S::THREADS) s_w2[i] = __ldg(p.W2 + i);
         for (int i = tid; i < 2 * p.C2; i += S::THREADS) s_w2[32 * 16 + i] = __ldg(p.bias2 + i);
@@ -297,7 +347,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const int m0 = (tile / ntn) * BM;
             const int n0 = (tile % ntn) * BN;
-            const float* arow[BM / 16];
+            const AT* arow[BM / 16];
             uint32_t avalid = 0;
             {
                 // rows m0 + g + 16 i: one division for the first row, then (q16 frames, r16 bins) steps
@@ -308,9 +358,9 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
                 int f = rr - t * p.Fo;
 #pragma unroll
                 for (int i = 0; i < BM / 16; ++i) {
-                    arow[i] = p.A;
+                    arow[i] = Abase;
                     if (m < p.M) {
-                        arow[i] = p.A + (p.b0 + bl) * p.sB + t * p.sT + f * p.sF;
+                        arow[i] = Abase + (p.b0 + bl) * p.sB + t * p.sT + f * p.sF;
                         avalid |= 1u << i;
                     }
                     m += 16;
@@ -329,7 +379,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
             uint32_t asz[BM / 16];
 #pragma unroll
             for (int i = 0; i < BM / 16; ++i) asz[i] = ((avalid >> i) & 1u) ? 16u : 0u;  // 0: zero-fill the row
-            const float* wptr = p.W + (long long)(n0 + g) * p.K + 4 * j;
+            const AT* wptr = Wbase + (long long)(n0 + g) * p.K + UE * j;
             const long long wstep = 16LL * p.K;
             const int* kptr = s_koff + j;
             for (int kb = 0; kb < nkb; ++kb) {
@@ -338,13 +388,13 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
                 const int ko = kptr[kb * 8];
 #pragma unroll
                 for (int i = 0; i < BM / 16; ++i) cp_async16(stage + (uint32_t)i * 2048u, arow[i] + ko, asz[i]);
-                const float* wp = wptr;
+                const AT* wp = wptr;
 #pragma unroll
                 for (int i = 0; i < B_ITERS; ++i) {
                     cp_async16(stage + A_STAGE_BYTES + (uint32_t)i * 2048u, wp, 16u);
                     wp += wstep;
                 }
-                wptr += BK;
+                wptr += BKE;
                 cp_async_mbar_arrive_noinc(full_bar(ps));
                 if (++ps == STAGES) {
                     ps = 0;
@@ -354,8 +404,9 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
         }
     } else if (warp == 4) {
         // ============================ MMA issuer ============================
-        // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 @17, M>>4 @24
-        constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+        // instruction descriptor: D=f32 (1<<4), A/B format @7/@10 (tf32 = 2, f16 = 0), K-major both, N>>3 @17, M>>4 @24
+        constexpr uint32_t fmt = sizeof(AT) == 4 ? 2u : 0u;
+        constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(BM >> 4) << 24);
         if (lane == 0) {
             uint32_t ms = 0, mphase = 0, it = 0;
@@ -372,9 +423,9 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
                     const uint64_t adesc = make_desc(tiles + ms * (uint32_t)S::STAGE_BYTES);
                     const uint64_t bdesc = adesc + (uint64_t)(A_STAGE_BYTES >> 4);
 #pragma unroll
-                    for (int kk = 0; kk < BK / 8; ++kk) {
-                        // advance 8 tf32 = 32 bytes inside the swizzle atom: +2 in the (addr >> 4) field
-                        tc_mma_tf32(tacc, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
+                    for (int kk = 0; kk < 4; ++kk) {
+                        // one MMA consumes 32 bytes of K (8 tf32 / 16 fp16): +2 in the (addr >> 4) field of the atom
+                        tc_mma<AT>(tacc, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
                         acc = 1;
                     }
                     tc_commit(empty_bar(ms));
@@ -476,7 +527,10 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
                         const float rg = fast_sigmoid(pr[i] + sr[ul] + br);
                         const float zg = fast_sigmoid(pz[i] + sr[8 + ul] + bz);
                         const float ng = fast_tanh(pn[i] + rg * (sr[16 + ul] + bn));
-                        p.out[(p.b0 + mm) * p.oB + ju] = (1.0f - zg) * ng + zg * ph[i];
+                        const float hn = (1.0f - zg) * ng + zg * ph[i];
+                        p.out[(p.b0 + mm) * p.oB + ju] = hn;
+                        // fp16 copy = operand of the next step / the next layer's projection
+                        if (p.out_h2) reinterpret_cast<__half*>(p.out_h2)[(p.b0 + mm) * p.o2B + ju] = __float2half_rn(hn);
                     }
                 }
                 __syncwarp();
@@ -607,8 +661,9 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
                             }
                         }
                         __syncwarp();
-                        if (p.odd_tail) store_chunk<CH, true>(stg, 0, p.out + n, ooff, min(CH, nlim - n), vec4, lane);
-                        else store_chunk<CH>(stg, 0, p.out + n, ooff, min(CH, p.N - n), vec4, lane);
+                        float* outp = out_half ? reinterpret_cast<float*>(reinterpret_cast<__half*>(p.out) + n) : p.out + n;
+                        if (p.odd_tail) store_chunk<CH, true>(stg, 0, outp, ooff, min(CH, nlim - n), vec4, lane, out_half);
+                        else store_chunk<CH>(stg, 0, outp, ooff, min(CH, p.N - n), vec4, lane, out_half);
                     } else {
                         constexpr int CO = CH / 2;  // output channels per pass
                         float w[CO];
@@ -657,12 +712,12 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tf32_kernel(const Ge
 
 int g_num_sms = 0;
 
-template <int BN>
+template <int BN, typename AT>
 int launch_tc(const GemmParams& p, cudaStream_t st) {
     using S = Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        SE_CUDA_OK(cudaFuncSetAttribute(gemm_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+        SE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
         configured = true;
     }
     if (g_num_sms == 0) {
@@ -672,15 +727,29 @@ int launch_tc(const GemmParams& p, cudaStream_t st) {
     }
     const int ntiles = ((p.M + BM - 1) / BM) * ((p.epi == EPI_GRU ? p.N : p.Npad) / BN);
     const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;  // persistent: one CTA per SM
-    gemm_tf32_kernel<BN><<<grid, S::THREADS, S::BYTES, st>>>(p);
+    gemm_tc_kernel<BN, AT><<<grid, S::THREADS, S::BYTES, st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+template <typename AT>
+int launch_elem(const GemmParams& p, cudaStream_t st) {
+    if (p.epi == EPI_GRU) return launch_tc<96, AT>(p, st);
+    if (p.epi == EPI_LSTM) return launch_tc<128, AT>(p, st);
+    switch (gemm_tf32_tile_n(p.N)) {
+        case 16: return launch_tc<16, AT>(p, st);
+        case 32: return launch_tc<32, AT>(p, st);
+        case 64: return launch_tc<64, AT>(p, st);
+        case 128: return launch_tc<128, AT>(p, st);
+        default: return launch_tc<256, AT>(p, st);
+    }
 }
 
 }  // namespace
 
 bool gemm_tf32_supported(const GemmParams& p) {
-    if (p.K % 32 != 0 || p.K < 32 || p.K > 2048) return false;  // whole k-blocks (host pads with zero weights)
+    const int bke = p.a_half ? 64 : 32, ue = p.a_half ? 8 : 4;  // elements per k-block / per 16-byte gather unit
+    if (p.K % bke != 0 || p.K < bke || p.K / ue > 512) return false;  // whole k-blocks (host pads with zero weights)
     if (p.epi == EPI_GRU) return p.H % 32 == 0 && p.Tn == 1 && p.Fo == 1 && p.N == 3 * p.H;
     if (p.epi == EPI_LSTM) return p.H % 32 == 0 && p.Tn == 1 && p.Fo == 1 && p.N == 4 * p.H && p.Npad == p.N;
     if (p.Npad % gemm_tf32_tile_n(p.N) != 0) return false;
@@ -699,17 +768,9 @@ int gemm_tf32_tile_n(int N) {
 }
 
 int launch_gemm_tf32(const GemmParams& p, cudaStream_t st) {
-    SE_REQUIRE(gemm_tf32_supported(p), "gemm_tf32: unsupported shape");
+    SE_REQUIRE(gemm_tf32_supported(p), "gemm_tc: unsupported shape");
     if (p.M <= 0) return 0;
-    if (p.epi == EPI_GRU) return launch_tc<96>(p, st);
-    if (p.epi == EPI_LSTM) return launch_tc<128>(p, st);
-    switch (gemm_tf32_tile_n(p.N)) {
-        case 16: return launch_tc<16>(p, st);
-        case 32: return launch_tc<32>(p, st);
-        case 64: return launch_tc<64>(p, st);
-        case 128: return launch_tc<128>(p, st);
-        default: return launch_tc<256>(p, st);
-    }
+    return p.a_half ? launch_elem<__half>(p, st) : launch_elem<float>(p, st);
 }
 
 }  // namespace se

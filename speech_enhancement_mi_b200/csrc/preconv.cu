@@ -7,6 +7,8 @@
 // each thread computes 4 adjacent bins x 5 output channels per pass in registers with fp32 FMAs (exact mode: no TF32
 // rounding in this block), the per-stream normalisation statistics are reduced inside the CTA (no atomics, no second
 // pass over HBM) and the normalised output + residual is written straight into the next layer's input buffer.
+#include <cuda_fp16.h>
+
 #include "se_internal.h"
 
 namespace se {
@@ -178,7 +180,17 @@ __global__ void __launch_bounds__(kThreads, 1) preconv_kernel(PreconvParams p) {
                         o[c] = (yv[pass][q][c] - mean) * inv * nw[c] + nb[c] +
                                s_in[(c * TP + t + KT - 1) * FPP + f + 2 * D];
                     float* dst = gout + t * p.oT + f * p.oF;
-                    if (p.out_vec8) {  // channels-last C = 8 destination (first encoder input)
+                    if (p.out_vec8 && p.out_half) {  // ... stored as fp16: 8 halves = one 16-byte store
+                        __half* dh = reinterpret_cast<__half*>(p.out) + (long long)b * p.oB + t * p.oT + f * p.oF;
+                        const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]),
+                                      h2 = __floats2half2_rn(o[4], 0.f);
+                        uint4 u;
+                        u.x = *reinterpret_cast<const unsigned*>(&h0);
+                        u.y = *reinterpret_cast<const unsigned*>(&h1);
+                        u.z = *reinterpret_cast<const unsigned*>(&h2);
+                        u.w = 0u;
+                        *reinterpret_cast<uint4*>(dh) = u;
+                    } else if (p.out_vec8) {  // channels-last C = 8 destination (first encoder input)
                         *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
                         *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], 0.f, 0.f, 0.f);
                     } else {

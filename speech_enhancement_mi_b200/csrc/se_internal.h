@@ -50,19 +50,22 @@ enum Epilogue : int {
 };
 
 struct GemmParams {
-    const float* A;
+    const void* A;         // fp32 (exact / tf32 path) or fp16 (a_half) activations
+    int a_half;            // tensor-core path: operands A and W are fp16 (kind::f16), else fp32 read as tf32
     long long sB, sT, sF;  // element strides of the row decomposition
     int Tn, Fo, M;
     int b0;  // first stream of this launch: row m belongs to stream b0 + m / (Tn*Fo)  (tf32 path)
-    const int* koff;  // [K/4] element offset of every 4-float unit of a row
-    int K;            // multiple of 4 (fp32 path) / padded to a multiple of 32 (tf32 path)
-    const float* W;   // [Npad][K] packed weights, rows >= N are zero
+    const int* koff;  // element offset of every 16-byte unit (4 floats / 8 halves) of a row
+    int K;            // padded to whole k-blocks (32 floats / 64 halves), weights zero there
+    const void* W;    // [Npad][K] packed weights (same element type as A), rows >= N are zero
     int N;            // logical columns
     int Npad;         // rows available in W / bias (multiple of 16)
     const float* bias;
     int epi;
-    float* out;
+    float* out;    // with out_half: a __half* (operand of a following GEMM), strides in halves
+    int out_half;
     long long oB, oT, oF;
+    void* out_h2;  // EPI_GRU: optional fp16 copy of h' (row stride o2B halves)
     float* out2;
     long long o2B, o2T, o2F;
     double* stats;  // [B][2] (sum, sum of squares)
@@ -114,8 +117,9 @@ struct NormApplyParams {
     double count_r;
     const float* wr;
     const float* br;
-    // destination (channels-last, strided)
+    // destination (channels-last, strided); out_half: a __half* (fp16 operand storage), strides in halves
     float* out;
+    int out_half;
     long long oB, oT, oF;
 };
 int launch_norm_apply(const NormApplyParams& p, cudaStream_t st);
@@ -137,6 +141,7 @@ struct PreconvParams {
     float* out;          // out(b, c, t, f) = out[b*oB + c*oC + t*oT + f*oF]  (interior of the next layer's input)
     long long oB, oC, oT, oF;
     int out_vec8;        // destination is channels-last with 8 channels: two 16-byte stores per position
+    int out_half;        // ... stored as fp16 (one 16-byte store per position); only with out_vec8
     int student;
     int b0, B;
 };

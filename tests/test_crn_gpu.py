@@ -64,7 +64,7 @@ def test_stft_istft_against_reference_fixture():
     assert np.all(z == 0)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp16"])
 @pytest.mark.parametrize("tag", list(CONFIGS))
 def test_forward_chunk_matches_reference(tag, precision):
     g = load_golden(tag)
@@ -75,7 +75,7 @@ def test_forward_chunk_matches_reference(tag, precision):
     assert rel_err(out.cpu().numpy(), g["fwd_chunk1"]) < tol["spec_rel"]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp16"])
 @pytest.mark.parametrize("tag", list(CONFIGS))
 def test_realtime_process_matches_reference(tag, precision):
     """fp32: CUDA-core exact mode.  tf32: tcgen05 tensor cores (operands truncated to TF32, fp32 accumulate in TMEM);
@@ -115,9 +115,10 @@ def test_streams_are_independent_and_shardable():
         assert np.abs(yb[0] - y[b]).max() < 2e-5
 
 
-def test_true_streaming_steps_equal_realtime_process():
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_true_streaming_steps_equal_realtime_process(precision):
     """process_chunk (the streaming step the bench times) reproduces realtime_process sample for sample."""
-    model = make_model("crn_small")
+    model = make_model("crn_small", precision)
     B, L = 3, 8000
     mix, _ = synth.make_mixture(B, L)
     x = torch.from_numpy(mix).cuda()
