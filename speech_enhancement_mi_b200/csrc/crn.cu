@@ -328,6 +328,7 @@ struct Builder {
         op.stage = stage;
         op.n = n;
         op.n.out_half = c->half ? 1 : 0;  // every normalised tensor is the operand of a following GEMM
+        op.n.in_half = c->half ? 1 : 0;   // ... and the pre-norm tensors are stored as fp16 too
         take_meta(op);
         c->ops.push_back(op);
         fix.push_back({NONE, NONE, -1, w_off, b_off, wr_off, br_off});
@@ -429,9 +430,8 @@ struct Builder {
             if (fuse_gate) {
                 g.C2 = Cout_real;
                 g.stats = stats;
-            } else {
-                g.out_half = c->half ? 1 : 0;  // tmp_e is the operand of the gate GEMM
             }
+            g.out_half = c->half ? 1 : 0;  // tmp_e (operand of the gate GEMM) / tmp_y (pre-norm tensor) are fp16 then
             {
                 const double in_b = 4.0 * Cin_real * in.Tp * in.F, conv_fl = 2.0 * rows * Cout_real * (KT * KF * Cin_real);
                 if (fuse_gate)
@@ -475,6 +475,7 @@ struct Builder {
             g.oF = g.sF;
             g.vec4 = 1;
             g.stats = stats;
+            g.out_half = c->half ? 1 : 0;
             meta(name + ".gate1x1", 4.0 * rows * Cout_real * Cout_real, 8.0 * rows * Cout_real);
             push_gemm(stage, g, rows, pw, k_off);
         }
@@ -566,6 +567,7 @@ struct Builder {
             g.oT = (long long)Fy * Cop;
             g.oF = 2 * Cop;
             g.odd_tail = 1;
+            g.out_half = (c->half && skip) ? 1 : 0;  // the last layer's output feeds the mask kernel in fp32
             g.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
             g.vec4 = Cop % 4 == 0;
             // ConvTranspose2d counted over the T kept frames: even bins 3 taps, odd bins 2 taps
@@ -613,6 +615,7 @@ struct Builder {
             g.o2F = g.oF;
             g.stats = c->stats + (size_t)stats_slot_r * 2 * c->maxB;
             g.vec4 = 1;
+            g.out_half = c->half ? 1 : 0;
             meta(name + ".skip1x1", 4.0 * rows * Cout_real * Cout_real, 12.0 * rows * Cout_real);
             push_gemm(ST_DECODER, g, rows, pw, k_off);
         }
@@ -722,11 +725,11 @@ int build_ctx(se_ctx* c) {
         upd((size_t)T * (2 * Fin) * Co);
     }
     if (dev_alloc(c, reinterpret_cast<char**>(&c->tmp_e), tmp * maxB * c->esz)) return 1;
-    if (dev_alloc(c, &c->tmp_y, tmp * maxB)) return 1;
-    if (dev_alloc(c, &c->tmp_rm, tmp * maxB)) return 1;
-    if (dev_alloc(c, &c->tmp_rr, tmp * maxB)) return 1;
+    if (dev_alloc(c, reinterpret_cast<char**>(&c->tmp_y), tmp * maxB * c->esz)) return 1;
+    if (dev_alloc(c, reinterpret_cast<char**>(&c->tmp_rm), tmp * maxB * c->esz)) return 1;
+    if (dev_alloc(c, reinterpret_cast<char**>(&c->tmp_rr), tmp * maxB * c->esz)) return 1;
     if (dev_alloc(c, reinterpret_cast<char**>(&c->xg), (size_t)T * c->feat * maxB * c->esz)) return 1;
-    if (dev_alloc(c, &c->fcraw, (size_t)T * c->feat * maxB)) return 1;
+    if (dev_alloc(c, reinterpret_cast<char**>(&c->fcraw), (size_t)T * c->feat * maxB * c->esz)) return 1;
     if (dev_alloc(c, &c->gi, (size_t)T * 3 * H * maxB)) return 1;
     if (dev_alloc(c, &c->gh, (size_t)3 * H * maxB)) return 1;
     for (int l = 0; l < 2; ++l)
@@ -950,6 +953,7 @@ int build_ctx(se_ctx* c) {
         gp.oF = 0;
         gp.stats = c->stats + (size_t)gru_slot * 2 * maxB;
         gp.vec4 = 1;
+        gp.out_half = c->half ? 1 : 0;
         b.meta("gru.fc+elu", 2.0 * T * feat * H, 4.0 * T * (H + feat));
         b.push_gemm(ST_GRU, gp, T, pw, k_off);
 
@@ -1507,7 +1511,11 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
         src_esz = c->esz;
         src = c->E(c->xg, (long long)b * T * c->feat);
     }
-    else if (n == "fcraw") compact(c->fcraw, c->Fg, c->Cg);
+    else if (n == "fcraw") {
+        compact(c->fcraw, c->Fg, c->Cg);
+        src_esz = c->esz;
+        src = c->E(c->fcraw, (long long)b * T * c->feat);
+    }
     else if (n == "ylast") compact(c->ylast, NBIN, 2);
     else if (n == "noisy") compact(c->noisy, NBIN, 2);
     else SE_REQUIRE(false, "se_debug_read: unknown tensor " + n);

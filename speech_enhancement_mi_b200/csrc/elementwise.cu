@@ -24,10 +24,19 @@ __device__ __forceinline__ void gln_coeffs(const double* stats, int b, double co
     inv = 1.0f / den;
 }
 
-// grid (T, B): one block per frame of one stream, one thread per 4 channels (C % 4 == 0).  The per-stream
-// coefficients (double arithmetic) are computed once per block, and no 64-bit index division is left per element.
+__device__ __forceinline__ float4 load4(const float* base, long long idx, bool is_half) {
+    if (!is_half) return *reinterpret_cast<const float4*>(base + idx);
+    const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(base) + idx);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// grid (ceil(T / kNormFrames), B): one block per group of frames of one stream, one thread per 4 channels (C % 4 == 0).
+// The per-stream coefficients (double arithmetic) are computed once per block; no 64-bit division per element.
+constexpr int kNormFrames = 7;
 __global__ void __launch_bounds__(256) norm_apply_kernel(NormApplyParams p) {
-    const int t = blockIdx.x;
+    const int t0 = blockIdx.x * kNormFrames;
     const int b = p.b0 + blockIdx.y;
     __shared__ float s_co[4];
     if (threadIdx.x == 0) {
@@ -38,14 +47,19 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(NormApplyParams p) {
     const float mean = s_co[0], inv = s_co[1];
     const int C4 = p.C >> 2;
     const int n4 = p.F * C4;
-    const float* yrow = p.y + ((long long)b * p.T + t) * p.Fy * p.C;
-    float* orow = p.out + b * p.oB + t * p.oT;
-    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-        const int f = i / C4;
-        const int c = (i - f * C4) * 4;
+    const bool ih = p.in_half != 0;
+    const int nt = min(kNormFrames, p.T - t0);
+    for (int i = threadIdx.x; i < n4 * nt; i += blockDim.x) {
+        const int tl = i / n4;
+        const int j = i - tl * n4;
+        const int t = t0 + tl;
+        const int f = j / C4;
+        const int c = (j - f * C4) * 4;
+        const long long yrow = ((long long)b * p.T + t) * p.Fy * p.C;
+        float* orow = p.out + b * p.oB + t * p.oT;
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
         if (f < p.Fy) {
-            const float4 y = *reinterpret_cast<const float4*>(yrow + f * p.C + c);
+            const float4 y = load4(p.y, yrow + f * p.C + c, ih);
             const int wi = p.per_feature ? (f * p.C + c) : c;
             const float4 w = *reinterpret_cast<const float4*>(p.w + wi);
             const float4 bb = *reinterpret_cast<const float4*>(p.b + wi);
@@ -65,8 +79,8 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(NormApplyParams p) {
         } else if (p.mode == 2) {
             const float mr = s_co[2], ir = s_co[3];
             const long long ri = (((long long)b * p.T + t) * p.F + f) * p.C + c;
-            const float4 rm = *reinterpret_cast<const float4*>(p.rm + ri);
-            const float4 rr = *reinterpret_cast<const float4*>(p.rr + ri);
+            const float4 rm = load4(p.rm, ri, ih);
+            const float4 rr = load4(p.rr, ri, ih);
             const float4 w = *reinterpret_cast<const float4*>(p.wr + c);
             const float4 bb = *reinterpret_cast<const float4*>(p.br + c);
             const float m0 = sigmoidf_((rm.x - mr) * ir * w.x + bb.x);
@@ -175,7 +189,7 @@ int launch_norm_apply(const NormApplyParams& p, cudaStream_t st) {
     SE_REQUIRE(p.B <= 65535, "norm_apply: at most 65535 streams per launch");
     const int n4 = p.F * (p.C / 4);
     const int threads = n4 >= 256 ? 256 : (n4 >= 128 ? 128 : 64);
-    norm_apply_kernel<<<dim3(p.T, p.B), threads, 0, st>>>(p);
+    norm_apply_kernel<<<dim3((p.T + kNormFrames - 1) / kNormFrames, p.B), threads, 0, st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }

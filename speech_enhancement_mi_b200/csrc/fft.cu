@@ -48,7 +48,7 @@ struct StftSmem {
     float win[NFFT];
     float2 w20[20];
     float2 w400[400];
-    float2 y[3][GROUP][20][ROW];    // stage-1 output after twiddle
+    float2 y[3][GROUP][11][ROW];    // stage-1 output rows k1 = 0..10 (the rest by Hermitian symmetry), before the twiddle
     float2 spec[3][GROUP][NBIN + 1];
 };
 
@@ -98,9 +98,7 @@ __global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
                 re = fmaf(v[n1], kC20[(n1 * k1) % 20], re);
                 im = fmaf(v[n1], kS20[(n1 * k1) % 20], im);
             }
-            s.y[m][fr][k1][n2] = cmul(make_float2(re, im), s.w400[n2 * k1]);
-            if (k1 >= 1 && k1 <= 9)  // Hermitian partner row 20-k1
-                s.y[m][fr][20 - k1][n2] = cmul(make_float2(re, -im), s.w400[n2 * (20 - k1)]);
+            s.y[m][fr][k1][n2] = make_float2(re, im);
         }
     }
     __syncthreads();
@@ -110,8 +108,13 @@ __global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
         const int fr = (u / 20) % GROUP;
         const int m = u / (20 * GROUP);
         float2 yr[20];
+        const int kr = k1 <= 10 ? k1 : 20 - k1;  // row 20-k1 is the conjugate of row k1 (real input)
+        const float sg = k1 <= 10 ? 1.f : -1.f;
 #pragma unroll
-        for (int n2 = 0; n2 < 20; ++n2) yr[n2] = s.y[m][fr][k1][n2];
+        for (int n2 = 0; n2 < 20; ++n2) {
+            const float2 v = s.y[m][fr][kr][n2];
+            yr[n2] = cmul(make_float2(v.x, sg * v.y), s.w400[n2 * k1]);  // twiddle W400^(n2 k1)
+        }
 #pragma unroll
         for (int k2 = 0; k2 <= 10; ++k2) {
             const int k = k1 + 20 * k2;

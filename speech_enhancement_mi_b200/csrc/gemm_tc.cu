@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
                 for (int i = 0; i < 16; i += 4)
                     *reinterpret_cast<float4*>(srow + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
                 __syncwarp();
-                store_chunk<16>(stg, 0, p.out, ooff, p.C2, vec4, lane);
+                store_chunk<16>(stg, 0, p.out, ooff, p.C2, vec4, lane, out_half);
                 __syncwarp();
                 stats_commit(p.stats, p.stats_stride ? p.stats_stride : 2, b, s_acc, ss_acc);
             } else {
@@ -691,9 +691,15 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
                         }
                         __syncwarp();
                         const int cnt = min(CO, (p.N - n) >> 1);
-                        store_chunk<CO>(stg, 0, p.out + (n >> 1), ooff, cnt, vec4, lane);
+                        const int co0 = n >> 1;
+                        float* o1 = out_half ? reinterpret_cast<float*>(reinterpret_cast<__half*>(p.out) + co0) : p.out + co0;
+                        store_chunk<CO>(stg, 0, o1, ooff, cnt, vec4, lane, out_half);
                         // out2 shares the row decomposition of out (gemm_tf32_supported checks the strides are equal)
-                        if (p.epi == EPI_SKIP) store_chunk<CO>(stg, CO, p.out2 + (n >> 1), ooff, cnt, vec4, lane);
+                        if (p.epi == EPI_SKIP) {
+                            float* o2 = out_half ? reinterpret_cast<float*>(reinterpret_cast<__half*>(p.out2) + co0)
+                                                 : p.out2 + co0;
+                            store_chunk<CO>(stg, CO, o2, ooff, cnt, vec4, lane, out_half);
+                        }
                     }
                     __syncwarp();
                 }

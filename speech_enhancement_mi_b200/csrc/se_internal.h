@@ -100,6 +100,7 @@ struct NormApplyParams {
     int B, T, F, C;         // logical extent of the output
     int b0;                 // first stream of this launch
     int student;            // distillation_crn.py:51 denominator
+    int in_half;            // y, rm, rr are stored as fp16 (SE_PRECISION_FP16)
     const float* y;         // raw (pre-norm) tensor, [B][T][Fy][C] compact; rows f >= Fy read as post-norm 0 (mode 2)
     int Fy;
     const double* stats;    // [B][2] of y
