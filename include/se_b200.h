@@ -145,6 +145,16 @@ int se_fsn_apply_mask(const float* crm, const float* x, float* out, int R, int F
  * n = 0 is the plain permutation */
 int se_unfold(const float* in, int B, int C, int F, int T, int num_neighbor, float* out, void* stream);
 
+/* ==== loss terms of compute_loss, forward only (CRN_ELU.py:513-535; fullsubnet.py:964-987) ======================== */
+/* replaces: utility.cal_si_snr (utility.py:207-223): separated, source [B, L] and length [B] (int32, DEVICE memory,
+ * may be NULL = full length) -> *out (device scalar) = mean over the batch of the SI-SNR in dB */
+int se_cal_si_snr(const float* separated, const float* source, const int32_t* length_dev, int B, int64_t L, float* out,
+                  void* stream);
+/* replaces: utility.stoi_loss (utility.py:821-916, reduction="mean"): y_true, y_pred [B, L], lens [B] (int32, device)
+ * -> *out (device scalar) = -mean(STOI-like score); items whose silent-frame-removed length is <= 512 score 0.99 */
+int se_stoi_loss(const float* y_true, const float* y_pred, const int32_t* lens_dev, int B, int64_t L, float* out,
+                 void* stream);
+
 /* ---- introspection used by bench.py --------------------------------------------------------------------------- */
 /* number of kernel launches one se_crn_process_chunk issues (graph nodes included) */
 int se_crn_launches_per_chunk(const se_ctx* ctx);

@@ -316,3 +316,79 @@ def si_sdr_db(estimate, reference):
     target = alpha * r
     noise = e - target
     return float(10 * torch.log10((target * target).sum() / ((noise * noise).sum() + 1e-30)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# a13: STOI-like loss (utility.py:821-916 with thirdoct :480-518 and removeSilentFrames :521-571), restated with the
+# same torch / torchaudio CPU operators the reference calls
+# ---------------------------------------------------------------------------------------------------------------
+def thirdoct(fs=10000, nfft=512, num_bands=15, min_freq=150):
+    import numpy as np
+    f = torch.linspace(0, fs, nfft + 1)[: nfft // 2 + 1]
+    k = torch.arange(num_bands, dtype=torch.float64)
+    lo = min_freq * torch.pow(2.0, (2 * k - 1) / 6)
+    hi = min_freq * torch.pow(2.0, (2 * k + 1) / 6)
+    obm = torch.zeros(num_bands, len(f))
+    for i in range(num_bands):
+        a = int(torch.argmin(torch.square(f - lo[i])))
+        b = int(torch.argmin(torch.square(f - hi[i])))
+        obm[i, a:b] = 1
+    return obm
+
+
+def remove_silent_frames(x, y, dyn_range=40, N=256):
+    import numpy as np
+    w = torch.from_numpy(np.hanning(256)).to(torch.float)
+    nf = x.shape[0] // N + (x.shape[0] - 128) // N
+    starts = [128 * m for m in range(nf)]
+    X = torch.stack([x[s:s + N] for s in starts], dim=1)
+    Y = torch.stack([y[s:s + N] for s in starts], dim=1)
+    energy = 20 * torch.log10(torch.sqrt((w[:, None] ** 2 * X ** 2).sum(0)) / 16.0 + np.finfo("float").eps)
+    msk = energy - energy.max() + dyn_range > 0
+    xs, ys = w[:, None] * X[:, msk], w[:, None] * Y[:, msk]
+
+    def ola(z):
+        return torch.cat((z[:128, 0], (z[:128, 1:] + z[128:, :-1]).T.flatten(), z[128:, -1]))
+
+    return ola(xs), ola(ys)
+
+
+def stoi_loss(y_true, y_pred, lens):
+    import numpy as np
+    import torchaudio
+    eps = np.finfo("float").eps
+    obm, c, Nseg = thirdoct(), 5.62341325, 30
+    resampler = torchaudio.transforms.Resample(16000, 10000)
+    spec = torchaudio.transforms.Spectrogram(n_fft=512, win_length=256, hop_length=128, power=2)
+    D = torch.zeros(y_true.shape[0])
+    for i in range(y_true.shape[0]):
+        t, p = resampler(y_true[i, :int(lens[i])]), resampler(y_pred[i, :int(lens[i])])
+        try:
+            t, p = remove_silent_frames(t, p)
+        except Exception:
+            pass
+        if t.shape[-1] <= 512:
+            D[i] = 0.99
+            continue
+        ot, op = torch.sqrt(obm @ spec(t) + 1e-14), torch.sqrt(obm @ spec(p) + 1e-14)
+        M = ot.shape[-1] - (Nseg - 1)
+        if M <= 0:
+            X, Y, M = ot, op, 1
+        else:
+            X = torch.cat([ot[:, m:m + Nseg] for m in range(M)], dim=0)
+            Y = torch.cat([op[:, m:m + Nseg] for m in range(M)], dim=0)
+        alpha = X.norm(dim=-1, keepdim=True) / (Y.norm(dim=-1, keepdim=True) + eps)
+        y = torch.min(Y * alpha, X + X * c)
+        xn = X - X.mean(-1, keepdim=True)
+        xn = xn / (xn.norm(dim=-1, keepdim=True) + eps)
+        yn = y - y.mean(-1, keepdim=True)
+        yn = yn / (yn.norm(dim=-1, keepdim=True) + eps)
+        D[i] = (xn * yn).sum() / (15.0 * M)
+    return -D.mean()
+
+
+def compute_loss(source, pred, length):
+    """CRN_ELU.py:513-535 (without the print): (loss, mae, sisnr)."""
+    mae = stoi_loss(source, pred, length)
+    sisnr = -cal_si_snr(pred, source, length)
+    return 0.7 * mae + 0.3 * sisnr, mae, sisnr

@@ -100,6 +100,28 @@ def framing():
     print("framing", gaps, ns)
 
 
+def losses():
+    """compute_loss of the reference (CRN_ELU.py:513-535 -> utility.stoi_loss / cal_si_snr) on synthetic pairs."""
+    import contextlib
+    import io
+    model = CRN_ELU.TemporalCRN(segment_length=3200, dropout=0.0, **SMALL)
+    res = {}
+    cases = {"a": (3, 24000, [24000, 20000, 9000]), "b": (2, 6000, [6000, 700]), "c": (1, 40000, [40000])}
+    for tag, (B, L, lens) in cases.items():
+        mix, src = synth.make_mixture(B, L)
+        source = torch.from_numpy(src)
+        pred = 0.8 * source + 0.2 * torch.from_numpy(mix[:, 0])  # an "enhanced" signal between clean and noisy
+        length = torch.tensor(lens)
+        with contextlib.redirect_stdout(io.StringIO()):
+            loss, mae, sisnr = model.compute_loss(source, pred, length)
+        res[f"{tag}_lens"] = np.array(lens)
+        res[f"{tag}_stoi"] = np.array(float(utility.stoi_loss(source, pred, length)))
+        res[f"{tag}_sisnr"] = utility.cal_si_snr(pred, source, length).numpy()
+        res[f"{tag}_loss"] = np.array([float(loss), float(mae), float(sisnr)])
+    np.savez_compressed(os.path.join(OUT, "losses.npz"), **res)
+    print("losses", {k: v for k, v in res.items() if not k.endswith("lens")})
+
+
 FSN_SMALL = dict(num_freqs=201, num_mics=3, fb_hidden=64, sb_hidden=32, sb_num_neighbors=15, fb_num_neighbors=0,
                  num_layers=2)
 FSN_FULL = dict(num_freqs=201, num_mics=3, fb_hidden=512, sb_hidden=384, sb_num_neighbors=15, fb_num_neighbors=0,
@@ -151,8 +173,12 @@ def run_fsn(cfg, seed, B, L, tag, continuation=False):
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "loss" in sys.argv[1:]:
+        losses()
+        sys.exit(0)
     if "fsn" not in sys.argv[1:]:
         framing()
+        losses()
         run_model(CRN_ELU.TemporalCRN, SMALL, 7, 2, 4000, "crn_small", continuation=True)
         run_model(CRN_ELU.TemporalCRN, TEACHER, 0, 2, 8000, "crn_teacher", continuation=True)
         run_model(distillation_crn.TemporalCRN, STUDENT, 3, 2, 8000, "crn_student")

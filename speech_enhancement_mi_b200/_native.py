@@ -81,6 +81,8 @@ SIGNATURES = {
     "se_fsn_forward_chunk": (_I, [_P, _P, _P, _I, _P]),
     "se_fsn_apply_mask": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "se_unfold": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
+    "se_cal_si_snr": (_I, [_P, _P, _P, _I, _L, _P, _P]),
+    "se_stoi_loss": (_I, [_P, _P, _P, _I, _L, _P, _P]),
     "se_crn_num_kernels": (_I, [_P]),
     "se_crn_kernel_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _PI]),
     "se_crn_time_kernel": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float)]),

@@ -57,9 +57,38 @@ def over_add(x, gap):
     return out.to(x.device)
 
 
+def _loss_args(a, b, length):
+    dev = _device_of(a if a.is_cuda else b)
+    ad = a.detach().to(device=f"cuda:{dev}", dtype=torch.float32).contiguous()
+    bd = b.detach().to(device=f"cuda:{dev}", dtype=torch.float32).contiguous()
+    if ad.dim() == 3:  # stoi_loss squeezes a trailing singleton (utility.py:845-846)
+        ad, bd = ad.squeeze(-1), bd.squeeze(-1)
+    B, L = ad.shape
+    if length is None:
+        ld = None
+    else:
+        ld = torch.as_tensor(length).to(device=ad.device, dtype=torch.int32).contiguous()
+    return dev, ad, bd, ld, B, L
+
+
 def cal_si_snr(separated, source, length=None, eps=1e-8):
-    raise NotImplementedError("cal_si_snr (utility.py:207-223): training-loss kernels are not built yet (DESIGN.md)")
+    """Mean SI-SNR in dB over the batch (utility.py:207-223).  Forward only (no autograd graph)."""
+    dev, sd, td, ld, B, L = _loss_args(separated, source, length)
+    with torch.cuda.device(dev):
+        out = torch.empty((), dtype=torch.float32, device=sd.device)
+        check(lib().se_cal_si_snr(sd.data_ptr(), td.data_ptr(), None if ld is None else ld.data_ptr(), B, L,
+                                  out.data_ptr(), _stream(dev)), "se_cal_si_snr")
+    return out.reshape(1)  # the reference accumulates [1]-shaped terms (keepdim sums)
 
 
-def stoi_loss(source, pred, length):
-    raise NotImplementedError("stoi_loss (utility.py:821-916): training-loss kernels are not built yet (DESIGN.md)")
+def stoi_loss(y_true_batch, y_pred_batch, lens, reduction="mean"):
+    """-mean(STOI-like score) (utility.py:821-916).  Forward only.  The reference moves everything to the CPU and returns
+    a CPU scalar; this returns a CUDA scalar."""
+    if reduction != "mean":
+        raise NotImplementedError("only reduction='mean' (the only use: CRN_ELU.py:526) is built")
+    dev, td, pd, ld, B, L = _loss_args(y_true_batch, y_pred_batch, lens)
+    with torch.cuda.device(dev):
+        out = torch.empty((), dtype=torch.float32, device=td.device)
+        check(lib().se_stoi_loss(td.data_ptr(), pd.data_ptr(), ld.data_ptr(), B, L, out.data_ptr(), _stream(dev)),
+              "se_stoi_loss")
+    return out
