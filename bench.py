@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--streams", type=int, default=1024, help="concurrent streams per GPU")
-    ap.add_argument("--precision", default=os.environ.get("SE_B200_PRECISION", "tf32"))
+    ap.add_argument("--precision", default=os.environ.get("SE_B200_PRECISION", "fp16"))
     ap.add_argument("--model", default="teacher", choices=["teacher", "student"])
     ap.add_argument("--cpu-streams", type=int, default=16, help="streams in the CPU baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of the cpu_baseline leg")
@@ -361,8 +361,9 @@ def main():
                  "share": g["ms_total"] / tot}
             if g["flops"] > 0 and g["stage"] != "preconv":
                 a = g["flops"] / (ms * 1e-3) / 1e12
-                k.update(bound="tensor", achieved=a, peak=tensor_peak, unit="TFLOP/s", frac=a / tensor_peak,
-                         frac_of_tf32_rate=a / (0.5 * tensor_peak))
+                k.update(bound="tensor", achieved=a, peak=tensor_peak, unit="TFLOP/s", frac=a / tensor_peak)
+                if args.precision == "tf32":
+                    k["frac_of_tf32_rate"] = a / (0.5 * tensor_peak)
             else:
                 a = g["bytes"] / (ms * 1e-3) / 1e9
                 k.update(bound="hbm", achieved=a, peak=peaks["hbm_gbs"], unit="GB/s", frac=a / peaks["hbm_gbs"])
@@ -376,7 +377,7 @@ def main():
         roofline = {"kernel": top["name"], "launches_per_step": top["launches"], "ms_per_launch": top["ms"],
                     "share_of_step": top["share"], "bound": top["bound"], "achieved": top["achieved"],
                     "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": top["traffic"],
-                    "peak_source": f"{peaks['src']} ({'bf16 dense burst; tf32 math runs at half that rate' if top['bound'] == 'tensor' else 'copy bandwidth'})"}
+                    "peak_source": f"{peaks['src']} ({'bf16/fp16 dense burst; tf32 math runs at half that rate' if top['bound'] == 'tensor' else 'copy bandwidth'})"}
         if "frac_of_tf32_rate" in top:
             roofline["frac_of_tf32_rate"] = top["frac_of_tf32_rate"]
 
@@ -389,7 +390,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+            "dtype": {"fp32": "f32", "tf32": "tf32", "fp16": "f16"}[args.precision], "data": "synthetic",
             "config": {"workload": f"CRN_ELU {args.model} batched streaming inference, {B} concurrent synthetic "
                                    f"streams per GPU, 3200-sample chunks at hop 1600 (BASELINE.json configs[1])",
                        "streams_per_gpu": B, "precision": args.precision,

@@ -4,6 +4,7 @@
 // The generic implicit-GEMM path would fetch every input value 25 times through L2 for this layer (K = 25 taps x 5
 // channels, N = 5): it is bound by L2 bandwidth, not by math.  Here one CTA owns one stream: the whole zero-bordered
 // input of the chunk (5 channels x 25 frames x <=220 bins, channel-planar, ~105 KB) is staged in shared memory once,
+// (persistent CTAs prefetch the next stream's input with cp.async while computing the current one),
 // each thread computes 4 adjacent bins x 5 output channels per pass in registers with fp32 FMAs (exact mode: no TF32
 // rounding in this block), the per-stream normalisation statistics are reduced inside the CTA (no atomics, no second
 // pass over HBM) and the normalised output + residual is written straight into the next layer's input buffer.
@@ -32,19 +33,32 @@ __global__ void __launch_bounds__(kThreads, 1) preconv_kernel(PreconvParams p) {
     constexpr int FPP = PRECONV_FPP(D);
     constexpr int NV4 = 1 + D;  // float4 loads that cover the 4 + 4*D input bins one group needs per (frame, channel)
     extern __shared__ __align__(16) float sm[];
-    float* s_in = sm;                       // [CH][TP][FPP]
-    float* s_w = sm + CH * TP * FPP;        // packed weights (PRECONV_W_FLOATS)
+    constexpr int NIN = CH * TP * FPP;      // floats of one stream's input
+    float* s_w = sm + 2 * NIN;              // packed weights (PRECONV_W_FLOATS) behind the two input buffers
     double* s_red = reinterpret_cast<double*>(s_w + PRECONV_W_FLOATS);  // [2][warps]
     const int tid = threadIdx.x;
-    const int b = p.b0 + blockIdx.x;
-    float* gin = p.in + (long long)b * p.in_sB;
+    for (int i = tid; i < PRECONV_W_FLOATS; i += kThreads) s_w[i] = __ldg(p.w + i);
 
-    // ---- stage the stream's input and the weights --------------------------------------------------------------
-    {
-        const float4* src = reinterpret_cast<const float4*>(gin);
-        float4* dst = reinterpret_cast<float4*>(s_in);
-        for (int i = tid; i < CH * TP * FPP / 4; i += kThreads) dst[i] = __ldg(src + i);
-        for (int i = tid; i < PRECONV_W_FLOATS; i += kThreads) s_w[i] = __ldg(p.w + i);
+    // Persistent CTA: streams blockIdx.x, blockIdx.x + gridDim.x, ...  The input of the NEXT stream is fetched with
+    // cp.async into the other shared-memory buffer while this one is computed (the load phase was 19 % of the kernel).
+    auto prefetch = [&](int stream, float* dst) {
+        const float* src = p.in + (long long)(p.b0 + stream) * p.in_sB;
+        const uint32_t d0 = (uint32_t)__cvta_generic_to_shared(dst);
+        for (int i = tid; i < NIN / 4; i += kThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u * i), "l"(src + 4 * i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    int cur = 0;
+    if ((int)blockIdx.x < p.B) prefetch(blockIdx.x, sm);
+  for (int stream = blockIdx.x; stream < p.B; stream += gridDim.x, cur ^= 1) {
+    float* s_in = sm + cur * NIN;           // [CH][TP][FPP]
+    const int b = p.b0 + stream;
+    float* gin = p.in + (long long)b * p.in_sB;
+    if (stream + (int)gridDim.x < p.B) {
+        prefetch(stream + gridDim.x, sm + (cur ^ 1) * NIN);
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     // ---- causal state: the last 4 frames of this chunk's input become frames 0..3 of the next chunk (CRN_ELU.py:246)
@@ -201,18 +215,27 @@ __global__ void __launch_bounds__(kThreads, 1) preconv_kernel(PreconvParams p) {
             }
         }
     }
+    __syncthreads();  // everyone is done with s_in before it is refilled two iterations later
+  }
 }
 
 template <int D>
 int launch_d(const PreconvParams& p, cudaStream_t st) {
-    constexpr size_t bytes = (size_t)(CH * TP * PRECONV_FPP(D) + PRECONV_W_FLOATS) * sizeof(float) +
+    constexpr size_t bytes = (size_t)(2 * CH * TP * PRECONV_FPP(D) + PRECONV_W_FLOATS) * sizeof(float) +
                              2 * (kThreads / 32) * sizeof(double);
+    static_assert(bytes <= 227 * 1024, "two input buffers must fit in shared memory");
     static bool configured = false;
     if (!configured) {
         SE_CUDA_OK(cudaFuncSetAttribute(preconv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
         configured = true;
     }
-    preconv_kernel<D><<<p.B, kThreads, bytes, st>>>(p);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        SE_CUDA_OK(cudaGetDevice(&dev));
+        SE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    preconv_kernel<D><<<p.B < num_sms ? p.B : num_sms, kThreads, bytes, st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -4,7 +4,7 @@ methods, the arithmetic running in the sm_100a kernels behind include/se_b200.h 
 
 Reference: fullsubnet.py:299-331 (unfold), :685-961 (FullSubNet).  Only the chunked loop the trainers and predictors
 use (``train=False``: train_fullsubnet.py:138,151; predict_fullsubnet.py:75) is built; ``train=True`` (all chunks
-concatenated into one forward) and ``compute_loss`` raise NotImplementedError.  The reference runs this loop under fp16
+concatenated into one forward) raises NotImplementedError; ``compute_loss`` is forward only (no autograd graph).  The reference runs this loop under fp16
 autocast on CUDA (fullsubnet.py:943) and in fp32 on the CPU; this path uses TF32 tensor cores with fp32 accumulation
 and fp32 cell state, checked against the fp32 CPU run.  No PyTorch / CPU compute fallback.
 """
@@ -266,4 +266,13 @@ class FullSubNet(BaseModel):
         return pred, pred_crm.to(mixture.device), s.to(mixture.device), x0.to(mixture.device)
 
     def compute_loss(self, source, pred_source, xf, sf, cIRM, length):
-        raise NotImplementedError("compute_loss (fullsubnet.py:964-987): the training-loss kernels are not built yet")
+        """fullsubnet.py:964-987 (forward only): loss = 0.7 * stoi_loss + 0.3 * (-SI-SNR); NaN => zero-filled."""
+        mae = utility.stoi_loss(source, pred_source, length)
+        sisnr = -utility.cal_si_snr(pred_source, source, length)
+        loss = 0.7 * mae + 0.3 * sisnr
+        print(sisnr, "\n")
+        if torch.isnan(loss):
+            mae = mae.fill_(0.0)
+            sisnr = sisnr.fill_(0.0)
+            loss = loss.fill_(0.0)
+        return loss, mae, sisnr
