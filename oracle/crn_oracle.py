@@ -152,7 +152,7 @@ class CRNOracle:
             F.conv2d(o, w[f"{name}.conv_gated.weight"], w[f"{name}.conv_gated.bias"]))
         o = gln(o, w[f"{name}.norm.weight"], w[f"{name}.norm.bias"], self.student)
         assert T > pad_t
-        self.buf[name] = x[..., -pad_t:].clone()
+        self.buf[name] = x[..., -pad_t:].detach().clone()  # CRN_ELU.py:243: detached
         return o
 
     # -- a8: TemporalConvTranspose2d (CRN_ELU.py:290-307) -----------------------------------------------------
@@ -199,7 +199,7 @@ class CRNOracle:
                 outs.append(h)
             seq = torch.stack(outs, dim=1)
             h_out.append(h)
-        self.h = torch.stack(h_out, dim=0)
+        self.h = torch.stack(h_out, dim=0).detach()  # CRN_ELU.py:185: detached
         o = F.elu(seq @ w["gru.fc_output_layer.weight"].t() + w["gru.fc_output_layer.bias"])
         o = gln(o.unsqueeze(1), w["gru.norm.weight"], w["gru.norm.bias"], self.student).squeeze(1)
         return o.permute(0, 2, 1)
@@ -392,3 +392,31 @@ def compute_loss(source, pred, length):
     mae = stoi_loss(source, pred, length)
     sisnr = -cal_si_snr(pred, source, length)
     return 0.7 * mae + 0.3 * sisnr, mae, sisnr
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# training micro-step (train.py:195-198): realtime_process -> compute_loss -> backward, by autograd through the
+# restatement above.  The carried conv buffers / GRU state are detached exactly where the reference detaches them
+# (CRN_ELU.py:185,243), so the gradient of every chunk stops at its own inputs.
+# ---------------------------------------------------------------------------------------------------------------
+def train_step_grads(oracle: "CRNOracle", mixture, source, lens, flag=False):
+    """Returns (pred [B,L], d loss/d pred [B,L], (loss, mae, sisnr) floats, {name: grad}) for the weights of ``oracle``."""
+    leaves = {}
+    for k, v in oracle.w.items():
+        if ".net.0." in k:
+            continue
+        leaves[k] = v.detach().clone().requires_grad_(True)
+    saved = oracle.w
+    oracle.w = dict(leaves)
+    for k in saved:
+        if ".net.0." in k:
+            oracle.w[k] = leaves[k.replace(".net.0.", ".conv.")]
+    try:
+        pred = oracle.realtime_process(torch.as_tensor(mixture, dtype=torch.float32), flag)
+        pred.retain_grad()
+        loss, mae, sisnr = compute_loss(torch.as_tensor(source, dtype=torch.float32), pred, torch.as_tensor(lens))
+        loss.backward()
+    finally:
+        oracle.w = saved
+    grads = {k: v.grad.detach() for k, v in leaves.items() if v.grad is not None}
+    return pred.detach(), pred.grad.detach(), (float(loss), float(mae), float(sisnr)), grads

@@ -122,6 +122,52 @@ def losses():
     print("losses", {k: v for k, v in res.items() if not k.endswith("lens")})
 
 
+def train_grads():
+    """One training micro-step of the UNMODIFIED reference (train.py:195-198): realtime_process -> compute_loss ->
+    backward, on seeded weights / mixtures.  Stores pred, d loss / d pred, the three loss scalars and the gradient of
+    every parameter (SMALL: full tensors; TEACHER: per-tensor L2 norm and the first 64 entries)."""
+    import contextlib
+    import io
+
+    def step(model, mix, src, lens, flag):
+        model.zero_grad()
+        pred = model.realtime_process(torch.from_numpy(mix), flag)
+        pred.retain_grad()
+        with contextlib.redirect_stdout(io.StringIO()):
+            loss, mae, sisnr = model.compute_loss(torch.from_numpy(src), pred, torch.tensor(lens))
+        loss.backward()
+        grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+        return pred.detach().numpy(), pred.grad.numpy(), np.array([float(loss), float(mae), float(sisnr)]), grads
+
+    res = {}
+    weights = synth.make_crn_weights(seed=7, **SMALL)
+    model = load_into(CRN_ELU.TemporalCRN(segment_length=3200, dropout=0.0, **SMALL), weights).train()
+    mix, src = synth.make_mixture(2, 8000)
+    pred, dpred, losses_, grads = step(model, mix, src, [8000, 6500], False)
+    res["small_pred"], res["small_dpred"], res["small_loss"] = pred, dpred, losses_
+    for k, g in grads.items():
+        res["small_grad/" + k] = g.numpy()
+    mix2, src2 = synth.make_mixture(2, 4800, first_stream=100)
+    pred, dpred, losses_, grads = step(model, mix2, src2, [4800, 4800], True)  # flag=True: state carried (data_c.py:61-63)
+    res["small_cont_pred"], res["small_cont_loss"] = pred, losses_
+    for k, g in grads.items():
+        res["small_cont_grad/" + k] = g.numpy()
+    res["small_meta"] = np.array([7, 2, 8000, 4800])
+
+    weights = synth.make_crn_weights(seed=0, **TEACHER)
+    model = load_into(CRN_ELU.TemporalCRN(segment_length=3200, dropout=0.0, **TEACHER), weights).train()
+    mix, src = synth.make_mixture(1, 6400)
+    pred, dpred, losses_, grads = step(model, mix, src, [6400], False)
+    res["teacher_pred"], res["teacher_dpred"], res["teacher_loss"] = pred, dpred, losses_
+    for k, g in grads.items():
+        res["teacher_gnorm/" + k] = np.array(float(g.norm()))
+        res["teacher_ghead/" + k] = g.flatten()[:64].numpy()
+    res["teacher_meta"] = np.array([0, 1, 6400])
+    np.savez_compressed(os.path.join(OUT, "train_grads.npz"), **res)
+    print("train_grads", res["small_loss"], res["small_cont_loss"], res["teacher_loss"],
+          "n grads", sum(1 for k in res if k.startswith("small_grad/")))
+
+
 FSN_SMALL = dict(num_freqs=201, num_mics=3, fb_hidden=64, sb_hidden=32, sb_num_neighbors=15, fb_num_neighbors=0,
                  num_layers=2)
 FSN_FULL = dict(num_freqs=201, num_mics=3, fb_hidden=512, sb_hidden=384, sb_num_neighbors=15, fb_num_neighbors=0,
@@ -176,9 +222,13 @@ if __name__ == "__main__":
     if "loss" in sys.argv[1:]:
         losses()
         sys.exit(0)
+    if "train" in sys.argv[1:]:
+        train_grads()
+        sys.exit(0)
     if "fsn" not in sys.argv[1:]:
         framing()
         losses()
+        train_grads()
         run_model(CRN_ELU.TemporalCRN, SMALL, 7, 2, 4000, "crn_small", continuation=True)
         run_model(CRN_ELU.TemporalCRN, TEACHER, 0, 2, 8000, "crn_teacher", continuation=True)
         run_model(distillation_crn.TemporalCRN, STUDENT, 3, 2, 8000, "crn_student")
