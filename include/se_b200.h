@@ -49,6 +49,9 @@ typedef struct se_crn_config {
     int32_t variant;                     /* SE_VARIANT_*                                   */
     int32_t precision;                   /* SE_PRECISION_*                                 */
     int32_t max_streams;                 /* capacity of the per-stream state arena         */
+    int32_t training;                    /* 0: streaming inference context; 1: training context (se_crn_train_*):
+                                            max_streams then counts chunk-streams = chunks * utterances per step,
+                                            every layer keeps its activations, precision must be FP32 or TF32      */
 } se_crn_config;
 
 typedef struct se_ctx se_ctx;
@@ -154,6 +157,36 @@ int se_cal_si_snr(const float* separated, const float* source, const int32_t* le
  * -> *out (device scalar) = -mean(STOI-like score); items whose silent-frame-removed length is <= 512 score 0.99 */
 int se_stoi_loss(const float* y_true, const float* y_pred, const int32_t* lens_dev, int B, int64_t L, float* out,
                  void* stream);
+
+/* ==== training micro-step (train.py:195-204; CRN_ELU.py:472-535) =================================================
+ * The reference trains through PyTorch autograd: realtime_process (serial chunk loop) -> compute_loss -> backward ->
+ * clip_grad_norm_(5) -> Adam.  Here the forward runs batched over all chunks of all utterances (only the GRU
+ * recurrence is serial over chunks), every adjoint is a hand-written kernel, and parameters / gradients cross the
+ * ABI as ONE flat fp32 vector: the tensors of se_crn_param_name() order, each in the reference layout, concatenated
+ * (tensor i starts at se_crn_param_offset(i); se_crn_num_theta() elements in total). */
+int64_t se_crn_num_theta(const se_ctx* ctx);
+int64_t se_crn_param_offset(const se_ctx* ctx, int index);
+/* re-lay the weights out from the flat DEVICE vector (no host round trip; after an optimizer step) */
+int se_crn_bind_weights_flat(se_ctx* ctx, const float* theta, void* stream);
+/* replaces: model.realtime_process(mixture[B,M,L], flag) in train mode (train.py:195; CRN_ELU.py:472-509):
+ * pred [B,L]; keeps what the backward needs.  flag=1 continues the previous piece (state carried, no front pad). */
+int se_crn_train_forward(se_ctx* ctx, const float* mixture, int B, int64_t L, int flag, float* pred, void* stream);
+/* replaces: the autograd backward from pred to the parameters (train.py:198): dpred [B,L] = d loss / d pred ->
+ * grad_flat [num_theta] (overwritten; parameters the graph does not reach, CRN_ELU.py:394-397, get 0) */
+int se_crn_train_backward(se_ctx* ctx, const float* dpred, float* grad_flat, void* stream);
+/* replaces: compute_loss (CRN_ELU.py:513-535) with its backward: source, pred [B,L], length [B] (int32, device) ->
+ * out3 (device) = {stoi_loss, cal_si_snr} = {-mean STOI-like score, mean SI-SNR dB} and their gradients w.r.t. pred
+ * (d_stoi, d_sisnr: [B,L] each, device).  The caller forms loss = 0.7 * stoi + 0.3 * (-sisnr). */
+int se_loss_terms_grad(const float* source, const float* pred, const int32_t* length_dev, int B, int64_t L,
+                       float* out2, float* d_stoi, float* d_sisnr, void* stream);
+/* out[i] = a * x[i] + b * y[i] with DEVICE scalars *a, *b (combines the two loss gradients with autograd's weights) */
+int se_axpby_dev(const float* a, const float* x, const float* b, const float* y, float* out, int64_t n, void* stream);
+/* replaces: clip_grad_norm_(params, max_norm) + Adam.step (train.py:200-204; config.yaml:10,99-100) on the flat
+ * vectors: *norm_out (device, may be NULL) = total L2 norm before clipping; grad is scaled by
+ * min(1, max_norm / (norm + 1e-6)) (max_norm <= 0: no clipping) and `grad_scale` (1 / world size after a summing
+ * all-reduce), then theta, m, v are updated in place with bias correction for step `step` (1-based). */
+int se_clip_adam_step(float* theta, float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                      float eps, int step, float max_norm, float grad_scale, float* norm_out, void* stream);
 
 /* ---- introspection used by bench.py --------------------------------------------------------------------------- */
 /* number of kernel launches one se_crn_process_chunk issues (graph nodes included) */

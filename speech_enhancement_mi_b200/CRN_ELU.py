@@ -86,6 +86,56 @@ class SequenceModel(nn.Module):
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# autograd plumbing of the training micro-step (train.py:195-198).  No arithmetic happens in PyTorch: the two graph
+# nodes below only hand device pointers to se_crn_train_forward / se_crn_train_backward and se_loss_terms_grad.
+# ----------------------------------------------------------------------------------------------------------------
+class _RealtimeTrainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, mixture, flag, *params):
+        ctx.model = model
+        ctx.shapes = [p.shape for p in params]
+        return model._train_forward(mixture, flag)
+
+    @staticmethod
+    def backward(ctx, dpred):
+        flat, offsets = ctx.model._train_backward(dpred)
+        grads = [flat[o:o + s.numel()].view(s) for o, s in zip(offsets, ctx.shapes)]
+        return (None, None, None, *grads)
+
+
+class _LossTermsFn(torch.autograd.Function):
+    """(stoi_loss, cal_si_snr) of utility.py:821-916,207-223 with their hand-written backward."""
+
+    @staticmethod
+    def forward(ctx, source, pred, length):
+        dev = pred.device
+        B, L = pred.shape
+        src = source.detach().to(device=dev, dtype=torch.float32).contiguous()
+        prd = pred.detach().to(torch.float32).contiguous()
+        lens = torch.as_tensor(length).to(device=dev, dtype=torch.int32).contiguous()
+        out2 = torch.empty(2, dtype=torch.float32, device=dev)
+        d_stoi = torch.empty((B, L), dtype=torch.float32, device=dev)
+        d_sisnr = torch.empty((B, L), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib().se_loss_terms_grad(src.data_ptr(), prd.data_ptr(), lens.data_ptr(), B, L, out2.data_ptr(),
+                                           d_stoi.data_ptr(), d_sisnr.data_ptr(),
+                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "se_loss_terms_grad")
+        ctx.save_for_backward(d_stoi, d_sisnr)
+        return out2[0].clone(), out2[1:2].clone()
+
+    @staticmethod
+    def backward(ctx, g_stoi, g_sisnr):
+        d_stoi, d_sisnr = ctx.saved_tensors
+        dev = d_stoi.device
+        a = g_stoi.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        b = g_sisnr.detach().to(device=dev, dtype=torch.float32).reshape(1).contiguous()
+        out = torch.empty_like(d_stoi)
+        with torch.cuda.device(dev):
+            check(lib().se_axpby_dev(a.data_ptr(), d_stoi.data_ptr(), b.data_ptr(), d_sisnr.data_ptr(), out.data_ptr(),
+                                     out.numel(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "se_axpby_dev")
+        return None, out, None
+
+
 class TemporalCRN(nn.Module):
     """B200-native ``CRN_ELU.TemporalCRN`` (reference CRN_ELU.py:314-535).
 
@@ -153,12 +203,19 @@ class TemporalCRN(nn.Module):
         self._ctx_capacity = 0
         self._bound_versions = None
         self._fresh = True  # no chunk processed since the last reset
+        # training context (chunk-major batch; created on the first realtime_process under autograd)
+        self._tctx = None
+        self._tctx_device = None
+        self._tctx_capacity = 0
+        self._tbound_versions = None
+        self._t_offsets = None
 
     # ------------------------------------------------------------------------------------------------------------
     # native context management
     # ------------------------------------------------------------------------------------------------------------
-    def _config(self, capacity):
+    def _config(self, capacity, training=False):
         cfg = SeCrnConfig()
+        cfg.training = 1 if training else 0
         cfg.num_inputs = self.num_inputs
         cfg.num_freqs = self.num_freqs
         cfg.num_levels = len(self.num_channels)
@@ -174,6 +231,8 @@ class TemporalCRN(nn.Module):
         cfg.variant = self._variant
         cfg.precision = {"fp32": _native.SE_PRECISION_FP32, "tf32": _native.SE_PRECISION_TF32,
                          "fp16": _native.SE_PRECISION_FP16}[self.precision]
+        if training and self.precision == "fp16":
+            cfg.precision = _native.SE_PRECISION_TF32  # training keeps fp32 activations (tensor cores on fp32 storage)
         cfg.max_streams = capacity
         return cfg
 
@@ -192,6 +251,10 @@ class TemporalCRN(nn.Module):
             lib().se_ctx_destroy(self._ctx)
             self._ctx = None
             self._bound_versions = None
+        if getattr(self, "_tctx", None) is not None:
+            lib().se_ctx_destroy(self._tctx)
+            self._tctx = None
+            self._tbound_versions = None
 
     def __del__(self):
         try:
@@ -320,13 +383,77 @@ class TemporalCRN(nn.Module):
         sp = sp.reshape(N, B, -1).permute(1, 0, 2)
         return self.overadd(sp, gap)
 
+    # ------------------------------------------------------------------------------------------------------------
+    # training micro-step (train.py:195-198): realtime_process under autograd
+    # ------------------------------------------------------------------------------------------------------------
+    def _train_params(self):
+        params = self._named_param_map()
+        n = lib().se_crn_num_params(self._tctx)
+        return [params[lib().se_crn_param_name(self._tctx, i).decode()] for i in range(n)]
+
+    def _ensure_train_ctx(self, n_streams, device, keep_state):
+        need = max(n_streams, self._max_streams, 1)
+        if self._tctx is not None and (device != self._tctx_device or need > self._tctx_capacity):
+            if keep_state:
+                raise RuntimeError("flag=True continues a previous piece, but the training context must be re-created "
+                                   "(more chunk-streams than before); construct TemporalCRN(max_streams=...) larger")
+            lib().se_ctx_destroy(self._tctx)
+            self._tctx = None
+            self._tbound_versions = None
+        if self._tctx is None:
+            ctx = C.c_void_p()
+            cfg = self._config(need, training=True)
+            check(lib().se_ctx_create(C.byref(ctx), device, C.byref(cfg)), "se_ctx_create(training)")
+            self._tctx, self._tctx_device, self._tctx_capacity = ctx, device, need
+            n = lib().se_crn_num_params(ctx)
+            self._t_offsets = [lib().se_crn_param_offset(ctx, i) for i in range(n)]
+        tensors = self._train_params()
+        versions = tuple((t.data_ptr(), t._version) for t in tensors)
+        if versions != self._tbound_versions:  # parameters changed (optimizer step / load_state_dict): re-lay out
+            with torch.cuda.device(device):
+                theta = torch.cat([t.detach().to(device=f"cuda:{device}", dtype=torch.float32).reshape(-1)
+                                   for t in tensors])
+                check(lib().se_crn_bind_weights_flat(self._tctx, theta.data_ptr(), self._stream_ptr(device)),
+                      "se_crn_bind_weights_flat")
+            self._tbound_versions = versions
+        return self._tctx
+
+    def _train_forward(self, mixture, flag):
+        B, _, L = mixture.shape
+        dev = self._pick_device(mixture)
+        _, n_chunks = _native.chunk_grid(L + (0 if flag else self.segment_length // 2), self.segment_length)
+        ctx = self._ensure_train_ctx(B * n_chunks, dev, keep_state=bool(flag))
+        with torch.cuda.device(dev):
+            xd = self._to_device(mixture, dev)
+            pred = torch.empty((B, L), dtype=torch.float32, device=xd.device)
+            check(lib().se_crn_train_forward(ctx, xd.data_ptr(), B, L, int(bool(flag)), pred.data_ptr(),
+                                             self._stream_ptr(dev)), "se_crn_train_forward")
+        return pred
+
+    def _train_backward(self, dpred):
+        dev = self._tctx_device
+        with torch.cuda.device(dev):
+            dp = dpred.detach().to(device=f"cuda:{dev}", dtype=torch.float32).contiguous()
+            flat = torch.empty(lib().se_crn_num_theta(self._tctx), dtype=torch.float32, device=dp.device)
+            check(lib().se_crn_train_backward(self._tctx, dp.data_ptr(), flat.data_ptr(), self._stream_ptr(dev)),
+                  "se_crn_train_backward")
+        return flat, self._t_offsets
+
     def realtime_process(self, mixture, flag=False):
         """[B, M, L] -> [B, L] (CRN_ELU.py:472-509).  One fused native call: padding, chunk grid, per-chunk STFT,
         network, mask, iSTFT and both overlap-adds happen on the device; with CPU tensors (predict.py:48,59-62) the
-        host<->device copies are inside the native call as well."""
+        host<->device copies are inside the native call as well.
+
+        Under autograd in train mode (train.py:195) the result carries a graph node whose backward is the native
+        backward pass; the forward then runs batched over all chunks (se_crn_train_forward)."""
         B, Cm, L = mixture.shape
         if Cm != self.num_inputs:
             raise ValueError(f"mixture must be [B, {self.num_inputs}, L]")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            dev = self._pick_device(mixture)
+            _, n_chunks = _native.chunk_grid(L + (0 if flag else self.segment_length // 2), self.segment_length)
+            self._ensure_train_ctx(B * n_chunks, dev, keep_state=bool(flag))
+            return _RealtimeTrainFn.apply(self, mixture, bool(flag), *self._train_params())
         dev = self._pick_device(mixture)
         ctx = self._ensure_ctx(B, dev, keep_state=bool(flag))
         with torch.cuda.device(dev):
@@ -362,8 +489,12 @@ class TemporalCRN(nn.Module):
     def compute_loss(self, source, pred_source, length):
         """CRN_ELU.py:513-535: loss = 0.7 * stoi_loss + 0.3 * (-SI-SNR); NaN => zero-filled; prints sisnr."""
         from .utility import cal_si_snr, stoi_loss
-        mae = stoi_loss(source, pred_source, length)
-        sisnr = -cal_si_snr(pred_source, source, length)
+        if pred_source.requires_grad:  # training: both terms and their backward in one native call
+            mae, sisnr_db = _LossTermsFn.apply(source, pred_source, length)
+            sisnr = -sisnr_db
+        else:
+            mae = stoi_loss(source, pred_source, length)
+            sisnr = -cal_si_snr(pred_source, source, length)
         loss = 0.7 * mae + 0.3 * sisnr
         print(sisnr)
         if torch.isnan(loss):

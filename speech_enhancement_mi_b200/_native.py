@@ -34,6 +34,7 @@ class SeCrnConfig(C.Structure):
         ("variant", C.c_int32),
         ("precision", C.c_int32),
         ("max_streams", C.c_int32),
+        ("training", C.c_int32),
     ]
 
 
@@ -86,6 +87,15 @@ SIGNATURES = {
     "se_crn_num_kernels": (_I, [_P]),
     "se_crn_kernel_info": (_I, [_P, _I, C.c_char_p, _I, C.POINTER(C.c_double), C.POINTER(C.c_double), _PI]),
     "se_crn_time_kernel": (_I, [_P, _I, _I, _I, C.POINTER(C.c_float)]),
+    "se_crn_num_theta": (_L, [_P]),
+    "se_crn_param_offset": (_L, [_P, _I]),
+    "se_crn_bind_weights_flat": (_I, [_P, _P, _P]),
+    "se_crn_train_forward": (_I, [_P, _P, _I, _L, _I, _P, _P]),
+    "se_crn_train_backward": (_I, [_P, _P, _P, _P]),
+    "se_loss_terms_grad": (_I, [_P, _P, _P, _I, _L, _P, _P, _P, _P]),
+    "se_axpby_dev": (_I, [_P, _P, _P, _P, _P, _L, _P]),
+    "se_clip_adam_step": (_I, [_P, _P, _P, _P, _L, C.c_float, C.c_float, C.c_float, C.c_float, _I, C.c_float,
+                               C.c_float, _P, _P]),
     "se_debug_read": (_I, [_P, C.c_char_p, _I, _P, _L, C.POINTER(C.c_int)]),
 }
 

@@ -43,6 +43,8 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
     int Tp = 0, Fp = 0;
     long long sB = 0, sT = 0, sF = 0;  // strides in ELEMENTS
     int esz = 4;                       // element size: 4 (fp32) or 2 (fp16 operand storage, SE_PRECISION_FP16)
+    float* dbase = nullptr;            // training: gradient twin with the same layout (fp32)
+    float* dinterior() const { return dbase + padT0 * sT + padF0 * sF; }
     float* at(long long elems) const { return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + elems * esz); }
     float* interior() const { return at(padT0 * sT + padF0 * sF); }
     long long per_stream() const { return sB; }
@@ -70,6 +72,34 @@ struct Op {
     long long hB = 0;
     float* hout = nullptr;
     int H = 0;
+    // training forward (chunk-major batch): state_entry >= 0 -> the carried frames of this op's input come from the
+    // previous chunk and are copied in right before the op; chunk_serial -> the op runs chunk by chunk (GRU recurrence)
+    int state_entry = -1;
+    int chunk_serial = 0;
+    int gru_layer = 0;
+};
+
+// ---- training: what the backward needs to know about each block (indices into se_ctx::ops) ---------------------
+struct ConvRec {
+    int op_conv = -1, op_gate = -1, op_norm = -1;
+    const Act* in = nullptr;
+    float *e = nullptr, *y = nullptr;  // saved elu(conv) and gate output (pre-norm)
+    int Cp_out = 0, Fo = 0;
+    bool residual = false, need_dgrad = true;
+    float* gout = nullptr;  // where d loss / d block output accumulates
+    StridedRows gs{};
+};
+struct DeconvRec {
+    int op_deconv = -1, op_skip = -1, op_norm = -1;
+    const Act* in = nullptr;
+    const Act* skip = nullptr;
+    float *y = nullptr, *rm = nullptr, *rr = nullptr;
+    int Cop = 0, Fy = 0, Fs = 0;
+    float* gout = nullptr;
+    StridedRows gs{};
+};
+struct GruRec {
+    int op_in[2] = {-1, -1}, op_hh[2] = {-1, -1}, op_fc = -1, op_norm = -1;
 };
 
 struct PreBuf {  // channel-planar preconv input [maxB][5][25][Fpp] (se_internal.h: PRECONV_FPP)
@@ -151,6 +181,29 @@ struct se_ctx {
     unsigned tc_mask = 0xffffffffu;  // SE_B200_TC_MASK: bit per Stage that may use the tensor-core GEMM (debug)
     std::map<int, cudaGraphExec_t> graphs;  // keyed by B
     cudaStream_t own_stream = nullptr;
+
+    // ---- training (se_crn_config.training): chunk-major batch, activations of every layer kept, gradient twins --------
+    bool train = false;
+    bool alloc_failed = false;
+    std::vector<Act> pre_act;  // the three pre-convolution inputs as zero-bordered channels-last buffers (GEMM path)
+    float* gi_l[2] = {nullptr, nullptr};  // per-layer GRU input projections (kept for the backward)
+    std::vector<ConvRec> conv_recs;       // preconv 0..2, encoder 0..L-1
+    std::vector<DeconvRec> deconv_recs;   // decoder 0..L-1
+    GruRec gru_rec;
+    float* garena = nullptr;  // gradient twin of warena
+    int* wmap = nullptr;      // warena position -> 1 + index into the flat parameter vector (0: padding)
+    std::vector<int64_t> param_off;
+    int64_t n_theta = 0;
+    float *dxg = nullptr, *dH[2] = {nullptr, nullptr}, *dhrec = nullptr, *dgi = nullptr, *dgh = nullptr, *gh_all = nullptr;
+    float* sc[4] = {nullptr, nullptr, nullptr, nullptr};  // scratch, 2 * tmp_floats * maxB each
+    double* red = nullptr;                                 // [maxB][2]
+    float *chunks = nullptr, *dchunks = nullptr, *dspec = nullptr;
+    std::vector<std::pair<void*, size_t>> twins;  // zeroed at the start of every backward
+    std::vector<float*> carry_store;              // per state entry: [maxB][count] state kept between flag=True pieces
+    int t_nb = 0, t_N = 0, t_front = 0;
+    long long t_L = 0;
+    bool t_have_fwd = false;
+    size_t tmp_floats = 0;
 
     // staging for the host variant
     float *h_in = nullptr, *h_out = nullptr;
@@ -321,6 +374,13 @@ struct Builder {
         fix.push_back({pw.w_off, pw.b_off, k_off, NONE, NONE, NONE, NONE, w2_off, b2_off});
     }
     bool tc_stage(int stage) const { return c->tf32 && ((c->tc_mask >> stage) & 1u); }
+    // inference: the per-layer temporaries share four buffers; training: every layer keeps its own (saved for backward)
+    float* tmp_buf(float* shared, size_t floats_per_stream) {
+        if (!c->train) return shared;
+        float* p = nullptr;
+        if (dev_alloc(c, &p, floats_per_stream * c->maxB)) c->alloc_failed = true;
+        return p;
+    }
     void push_norm(int stage, NormApplyParams n, size_t w_off, size_t b_off, size_t wr_off = NONE,
                    size_t br_off = NONE) {
         Op op{};
@@ -364,12 +424,23 @@ struct Builder {
     // in: padded input; dst/dstB..: where the normalised output goes; residual: add the block input (preconv)
     void conv_block(int stage, const std::string& name, const Act& in, int Cin_real, int Cout_real, int KF, int KT,
                     int strideF, int dilF, int dilT, int Fo, float* dst, long long dB, long long dT, long long dF,
-                    bool residual, int stats_slot) {
+                    bool residual, int stats_slot, int state_entry = -1, float* dgrad_dst = nullptr) {
         const int Cp_in = in.C;
         const int Cp_out = round_up(Cout_real, 4);
         const int rows = T * Fo;
-        const bool fuse_gate = tc_stage(stage) && Cp_out <= 16;
+        const bool fuse_gate = tc_stage(stage) && Cp_out <= 16 && !c->train;
         double* stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
+        float* const tmp_e = tmp_buf(c->tmp_e, (size_t)rows * Cp_out);
+        float* const tmp_y = tmp_buf(c->tmp_y, (size_t)rows * Cp_out);
+        ConvRec rec;
+        rec.in = &in;
+        rec.e = tmp_e;
+        rec.y = tmp_y;
+        rec.Cp_out = Cp_out;
+        rec.Fo = Fo;
+        rec.residual = residual;
+        rec.gout = dgrad_dst;
+        rec.gs = StridedRows{dB, dT, dF};
         // (1) conv + ELU -> tmp_e [B][T][Fo][Cp_out]   (fuse_gate: + gated 1x1 pair + statistics -> tmp_y, skipping 2)
         {
             const int K = KT * KF * Cp_in;
@@ -422,7 +493,7 @@ struct Builder {
             g.Fo = Fo;
             fill_gemm_common(c, g, pw, Cout_real, k_off);
             g.epi = fuse_gate ? EPI_ELU_GATE : EPI_ELU;
-            g.out = fuse_gate ? c->tmp_y : c->tmp_e;
+            g.out = fuse_gate ? tmp_y : tmp_e;
             g.oB = (long long)rows * Cp_out;
             g.oT = (long long)Fo * Cp_out;
             g.oF = Cp_out;
@@ -440,6 +511,8 @@ struct Builder {
                     meta(name + ".conv+elu", conv_fl, in_b + 4.0 * rows * Cout_real);
             }
             push_gemm(stage, g, rows, pw, k_off, w2_off, b2_off);
+            rec.op_conv = (int)c->ops.size() - 1;
+            c->ops.back().state_entry = state_entry;
         }
         // (2) gated 1x1 pair + statistics -> tmp_y [B][T][Fo][Cp_out]
         if (!fuse_gate) {
@@ -461,7 +534,7 @@ struct Builder {
                 }
             });
             GemmParams g{};
-            g.A = c->tmp_e;
+            g.A = tmp_e;
             g.sB = (long long)rows * Cp_out;
             g.sT = (long long)Fo * Cp_out;
             g.sF = Cp_out;
@@ -469,7 +542,7 @@ struct Builder {
             g.Fo = Fo;
             fill_gemm_common(c, g, pw, 2 * Cout_real, k_off);
             g.epi = EPI_GATE_STATS;
-            g.out = c->tmp_y;
+            g.out = tmp_y;
             g.oB = g.sB;
             g.oT = g.sT;
             g.oF = g.sF;
@@ -478,6 +551,7 @@ struct Builder {
             g.out_half = c->half ? 1 : 0;
             meta(name + ".gate1x1", 4.0 * rows * Cout_real * Cout_real, 8.0 * rows * Cout_real);
             push_gemm(stage, g, rows, pw, k_off);
+            rec.op_gate = (int)c->ops.size() - 1;
         }
         // (3) GlobalLayerNorm (+ residual) -> destination
         {
@@ -487,7 +561,7 @@ struct Builder {
             n.F = Fo;
             n.C = Cp_out;
             n.student = c->student;
-            n.y = c->tmp_y;
+            n.y = tmp_y;
             n.Fy = Fo;
             n.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
             n.count = (double)Cout_real * Fo * T;
@@ -506,17 +580,29 @@ struct Builder {
             const size_t b_off = pack_affine(name + ".norm.bias", Cout_real, Cp_out);
             meta(name + ".gln" + (residual ? "+residual" : ""), 0, (residual ? 12.0 : 8.0) * rows * Cout_real);
             push_norm(stage, n, w_off, b_off);
+            rec.op_norm = (int)c->ops.size() - 1;
         }
+        if (c->train) c->conv_recs.push_back(rec);
     }
 
     // ---- transposed conv block (CRN_ELU.py:290-307) ---------------------------------------------------------
     // in: [T + 2d][Fin + 2][Cin]; skip: padded encoder-input buffer whose interior is the skip tensor (or null)
     void deconv_block(const std::string& name, const Act& in, int Cin, int Cout_real, int KT, int d, const Act* skip,
-                      float* dst, long long dB, long long dT, long long dF, int stats_slot, int stats_slot_r) {
+                      float* dst, long long dB, long long dT, long long dF, int stats_slot, int stats_slot_r,
+                      float* dgrad_dst = nullptr) {
         const int Fin = in.F;
         const int Fy = 2 * Fin - 1;
         const int Cop = Cout_real < 4 ? Cout_real : round_up(Cout_real, 4);  // last layer keeps 2 (float2 consumer)
-        float* y = skip ? c->tmp_y : c->ylast;
+        float* y = skip ? tmp_buf(c->tmp_y, (size_t)T * Fy * Cop) : c->ylast;
+        DeconvRec rec;
+        rec.in = &in;
+        rec.skip = skip;
+        rec.y = y;
+        rec.Cop = Cop;
+        rec.Fy = Fy;
+        rec.Fs = skip ? skip->F : Fy;
+        rec.gout = dgrad_dst;
+        rec.gs = StridedRows{dB, dT, dF};
         {
             // Both output parities in one GEMM.  Output bin phi = 2f' (even) uses taps kf = 0,2,4 and phi = 2f'+1 (odd)
             // taps kf = 1,3, all on the padded input rows f'+2-j (j = kf/2): the odd half re-uses the rows gathered for
@@ -574,10 +660,18 @@ struct Builder {
             meta(name + ".deconv+elu", 2.0 * T * (3.0 * Fin + 2.0 * (Fin - 1)) * KT * Cin * Cout_real,
                  4.0 * Cin * T * Fin + 4.0 * T * Fy * Cout_real);
             push_gemm(ST_DECODER, g, T * Fo, pw, k_off);
+            rec.op_deconv = (int)c->ops.size() - 1;
         }
-        if (!skip) return;
+        if (!skip) {
+            if (c->train) c->deconv_recs.push_back(rec);
+            return;
+        }
         const int Fs = skip->F;
         const int rows = T * Fs;
+        float* const tmp_rm = tmp_buf(c->tmp_rm, (size_t)rows * Cop);
+        float* const tmp_rr = tmp_buf(c->tmp_rr, (size_t)rows * Cop);
+        rec.rm = tmp_rm;
+        rec.rr = tmp_rr;
         {  // residual mask / residual 1x1 pair on the skip tensor
             const int K = skip->C;
             const int k_off = koff_dense(K);
@@ -605,11 +699,11 @@ struct Builder {
             g.Fo = Fs;
             fill_gemm_common(c, g, pw, 2 * Cout_real, k_off);
             g.epi = EPI_SKIP;
-            g.out = c->tmp_rm;
+            g.out = tmp_rm;
             g.oB = (long long)rows * Cop;
             g.oT = (long long)Fs * Cop;
             g.oF = Cop;
-            g.out2 = c->tmp_rr;
+            g.out2 = tmp_rr;
             g.o2B = g.oB;
             g.o2T = g.oT;
             g.o2F = g.oF;
@@ -618,6 +712,7 @@ struct Builder {
             g.out_half = c->half ? 1 : 0;
             meta(name + ".skip1x1", 4.0 * rows * Cout_real * Cout_real, 12.0 * rows * Cout_real);
             push_gemm(ST_DECODER, g, rows, pw, k_off);
+            rec.op_skip = (int)c->ops.size() - 1;
         }
         {
             NormApplyParams n{};
@@ -630,8 +725,8 @@ struct Builder {
             n.Fy = Fy;
             n.stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
             n.count = (double)Cout_real * Fy * T;
-            n.rm = c->tmp_rm;
-            n.rr = c->tmp_rr;
+            n.rm = tmp_rm;
+            n.rr = tmp_rr;
             n.stats_r = c->stats + (size_t)stats_slot_r * 2 * c->maxB;
             n.count_r = (double)Cout_real * Fs * T;
             n.out = dst;
@@ -644,7 +739,9 @@ struct Builder {
             const size_t br_off = pack_affine(name + ".residualnorm.bias", Cout_real, Cop);
             meta(name + ".gln+skipblend", 0, 4.0 * T * Cout_real * (Fy + 3.0 * Fs));
             push_norm(ST_DECODER, n, w_off, b_off, wr_off, br_off);
+            rec.op_norm = (int)c->ops.size() - 1;
         }
+        if (c->train) c->deconv_recs.push_back(rec);
     }
 };
 
@@ -669,6 +766,8 @@ int build_ctx(se_ctx* c) {
     c->H = g.hidden;
     c->tf32 = g.precision != SE_PRECISION_FP32;
     c->half = g.precision == SE_PRECISION_FP16;
+    c->train = g.training != 0;
+    SE_REQUIRE(!(c->train && c->half), "training keeps fp32 activations: use precision fp32 or tf32");
     c->esz = c->half ? 2 : 4;
     c->ue = 16 / c->esz;
     c->kblock = 128 / c->esz;
@@ -693,8 +792,8 @@ int build_ctx(se_ctx* c) {
     const int C0p = 8;
     const int H = c->H;
     // ---- activations ------------------------------------------------------------------------------------------
-    c->pre_in.resize(3);
-    for (int i = 0; i < 3; ++i) {
+    c->pre_in.resize(c->train ? 0 : 3);
+    for (int i = 0; i < (int)c->pre_in.size(); ++i) {
         PreBuf& pb = c->pre_in[i];
         pb.d = 1 << i;
         pb.Fpp = PRECONV_FPP(pb.d);
@@ -702,11 +801,26 @@ int build_ctx(se_ctx* c) {
         pb.sB = 5 * pb.sC;
         if (dev_alloc(c, &pb.base, (size_t)pb.sB * maxB)) return 1;
     }
+    auto make_twin = [&](Act& a) -> int {
+        if (!c->train) return 0;
+        if (dev_alloc(c, &a.dbase, (size_t)a.sB * maxB)) return 1;
+        c->twins.push_back({a.dbase, (size_t)a.sB * maxB * sizeof(float)});
+        return 0;
+    };
+    if (c->train) {  // training: the pre-convolutions run on the generic GEMM path so that one backward serves all convs
+        c->pre_act.resize(3);
+        for (int i = 0; i < 3; ++i) {
+            const int d = 1 << i;
+            if (make_act(c, c->pre_act[i], C0p, NBIN, T, 4, 0, 2 * d, 2 * d)) return 1;
+            if (make_twin(c->pre_act[i])) return 1;
+        }
+    }
     c->enc_in.resize(c->L);
     for (int i = 0; i < c->L; ++i) {
         const int Cin = i == 0 ? C0p : g.num_channels[i - 1];
         const int Fin = i == 0 ? NBIN : c->encF[i - 1];
         if (make_act(c, c->enc_in[i], Cin, Fin, T, 2 * (1 << i), 0, 2, 2)) return 1;
+        if (make_twin(c->enc_in[i])) return 1;
     }
     c->dec_in.resize(c->L);
     for (int j = 0; j < c->L; ++j) {
@@ -714,6 +828,7 @@ int build_ctx(se_ctx* c) {
         const int Fin = j == 0 ? c->Fg : c->encF[c->L - 1 - j];
         const int d = 1 << j;
         if (make_act(c, c->dec_in[j], Cin, Fin, T, 0, 2 * d, 1, 1)) return 1;
+        if (make_twin(c->dec_in[j])) return 1;
     }
     size_t tmp = 0;
     auto upd = [&](size_t v) { tmp = v > tmp ? v : tmp; };
@@ -730,7 +845,28 @@ int build_ctx(se_ctx* c) {
     if (dev_alloc(c, reinterpret_cast<char**>(&c->tmp_rr), tmp * maxB * c->esz)) return 1;
     if (dev_alloc(c, reinterpret_cast<char**>(&c->xg), (size_t)T * c->feat * maxB * c->esz)) return 1;
     if (dev_alloc(c, reinterpret_cast<char**>(&c->fcraw), (size_t)T * c->feat * maxB * c->esz)) return 1;
+    c->tmp_floats = tmp;
     if (dev_alloc(c, &c->gi, (size_t)T * 3 * H * maxB)) return 1;
+    c->gi_l[0] = c->gi_l[1] = c->gi;
+    if (c->train) {
+        if (dev_alloc(c, &c->gi_l[1], (size_t)T * 3 * H * maxB)) return 1;
+        if (dev_alloc(c, &c->gh_all, (size_t)T * 3 * H * maxB)) return 1;
+        if (dev_alloc(c, &c->dgi, (size_t)T * 3 * H * maxB)) return 1;
+        if (dev_alloc(c, &c->dgh, (size_t)T * 3 * H * maxB)) return 1;
+        if (dev_alloc(c, &c->dhrec, (size_t)H * maxB)) return 1;
+        if (dev_alloc(c, &c->dxg, (size_t)T * c->feat * maxB)) return 1;
+        c->twins.push_back({c->dxg, (size_t)T * c->feat * maxB * sizeof(float)});
+        for (int l = 0; l < 2; ++l) {
+            if (dev_alloc(c, &c->dH[l], (size_t)(T + 1) * H * maxB)) return 1;
+            c->twins.push_back({c->dH[l], (size_t)(T + 1) * H * maxB * sizeof(float)});
+        }
+        for (int i = 0; i < 4; ++i)
+            if (dev_alloc(c, &c->sc[i], 2 * tmp * maxB)) return 1;
+        if (dev_alloc(c, &c->red, (size_t)2 * maxB)) return 1;
+        if (dev_alloc(c, &c->chunks, (size_t)KCHUNK * maxB)) return 1;
+        if (dev_alloc(c, &c->dchunks, (size_t)KCHUNK * maxB)) return 1;
+        if (dev_alloc(c, &c->dspec, (size_t)T * NBIN * 2 * maxB)) return 1;
+    }
     if (dev_alloc(c, &c->gh, (size_t)3 * H * maxB)) return 1;
     for (int l = 0; l < 2; ++l)
         if (dev_alloc(c, reinterpret_cast<char**>(&c->hseq[l]), (size_t)(T + 1) * H * maxB * c->esz)) return 1;
@@ -747,7 +883,14 @@ int build_ctx(se_ctx* c) {
     // ---- program ----------------------------------------------------------------------------------------------
     Builder b{c, {}};
     int slot = 0;
-    for (int i = 0; i < 3; ++i) {  // pre-convolutions: one fused kernel per layer (preconv.cu), exact fp32 in both modes
+    for (int i = 0; i < 3 && c->train; ++i) {  // training: generic conv blocks with the residual add (CRN_ELU.py:376)
+        const Act& in = c->pre_act[i];
+        const Act& nx = i < 2 ? c->pre_act[i + 1] : c->enc_in[0];
+        b.conv_block(ST_PRECONV, "preconvlist." + std::to_string(i), in, c->C0, c->C0, 5, 5, 1, 1 << i, 1, NBIN,
+                     nx.interior(), nx.sB, nx.sT, nx.sF, true, slot++, i, nx.dinterior());
+        c->conv_recs.back().need_dgrad = i > 0;
+    }
+    for (int i = 0; i < 3 && !c->train; ++i) {  // pre-convolutions: one fused kernel per layer (preconv.cu), exact fp32 in both modes
         const PreBuf& in = c->pre_in[i];
         const std::string name = "preconvlist." + std::to_string(i);
         const size_t w_off = c->reserve_w(PRECONV_W_FLOATS);
@@ -805,22 +948,24 @@ int build_ctx(se_ctx* c) {
     for (int i = 0; i < c->L; ++i) {
         const Act& in = c->enc_in[i];
         const int Cin_real = i == 0 ? c->C0 : g.num_channels[i - 1];
-        float* dst;
+        float *dst, *gdst = nullptr;
         long long dB, dT, dF;
         if (i + 1 < c->L) {
             const Act& nx = c->enc_in[i + 1];
             dst = nx.interior();
+            if (c->train) gdst = nx.dinterior();
             dB = nx.sB;
             dT = nx.sT;
             dF = nx.sF;
         } else {
             dst = c->xg;
+            gdst = c->dxg;
             dB = (long long)T * c->feat;
             dT = c->feat;
             dF = c->Cg;
         }
         b.conv_block(ST_ENCODER, "convlist." + std::to_string(i), in, Cin_real, g.num_channels[i], 5, 3, 2, 1, 1 << i,
-                     c->encF[i], dst, dB, dT, dF, false, slot++);
+                     c->encF[i], dst, dB, dT, dF, false, slot++, c->train ? 3 + i : -1, gdst);
     }
     // ---- GRU + Linear + ELU + GLN(last) (CRN_ELU.py:160-186) --------------------------------------------------
     // feature index: reference c*Fg + f  ->  ours f*Cg + c (channels-last)
@@ -857,17 +1002,18 @@ int build_ctx(se_ctx* c) {
             gp.Fo = 1;
             fill_gemm_common(c, gp, pw, 3 * H, k_off);
             gp.epi = EPI_BIAS;
-            gp.out = c->gi;
+            gp.out = c->gi_l[l];
             gp.oB = (long long)T * 3 * H;
             gp.oT = 3 * H;
             gp.oF = 0;
             gp.vec4 = 1;
             b.meta("gru.l" + s + ".input_proj", 2.0 * T * 3 * H * Kin, 4.0 * T * (Kin + 3 * H));
             b.push_gemm(ST_GRU, gp, T, pw, k_off);
+            c->gru_rec.op_in[l] = (int)c->ops.size() - 1;
         }
         const int k_off = b.koff_dense(H);
         PackedW pw = reserve_packed(c, 3 * H, H);
-        const bool fused = c->half || (c->tf32 && ((c->tc_mask >> ST_GRU) & 1u) && H % 32 == 0);
+        const bool fused = !c->train && (c->half || (c->tf32 && ((c->tc_mask >> ST_GRU) & 1u) && H % 32 == 0));
         c->packers.push_back([=](const HostParams& hp, float* arena) {
             const std::vector<float>& w = hp.at("gru.sequence_model.weight_hh_l" + s);
             const std::vector<float>& bh = hp.at("gru.sequence_model.bias_hh_l" + s);
@@ -886,7 +1032,7 @@ int build_ctx(se_ctx* c) {
             gp.Fo = 1;
             fill_gemm_common(c, gp, pw, 3 * H, k_off);
             gp.epi = EPI_GRU;
-            gp.gi = c->gi + (long long)t * 3 * H;
+            gp.gi = c->gi_l[l] + (long long)t * 3 * H;
             gp.giB = (long long)T * 3 * H;
             if (c->half) {  // fp32 master state updated in place + fp16 history = operand of the following GEMMs
                 gp.hprev = c->h32[l];
@@ -921,9 +1067,14 @@ int build_ctx(se_ctx* c) {
             gp.oF = 0;
             b.meta("gru.l" + s + ".step" + std::to_string(t) + ".hh", 2.0 * 3 * H * H, 4.0 * (H + 3 * H));
             b.push_gemm(ST_GRU, gp, 1, pw, k_off);
+            if (t == 0) c->gru_rec.op_hh[l] = (int)c->ops.size() - 1;
+            c->ops.back().chunk_serial = 1;
+            c->ops.back().gru_layer = l;
             b.meta("gru.l" + s + ".step" + std::to_string(t) + ".cell", 0, 4.0 * (6 * H + 2 * H));
-            b.push_gru_pw(c->gi + (long long)t * 3 * H, (long long)T * 3 * H, c->gh, c->hseq[l] + (long long)t * H,
+            b.push_gru_pw(c->gi_l[l] + (long long)t * 3 * H, (long long)T * 3 * H, c->gh, c->hseq[l] + (long long)t * H,
                           (long long)(T + 1) * H, c->hseq[l] + (long long)(t + 1) * H, H);
+            c->ops.back().chunk_serial = 1;
+            c->ops.back().gru_layer = l;
         }
     }
     {  // fc + ELU + stats, then per-feature GLN into the first decoder input
@@ -956,6 +1107,7 @@ int build_ctx(se_ctx* c) {
         gp.out_half = c->half ? 1 : 0;
         b.meta("gru.fc+elu", 2.0 * T * feat * H, 4.0 * T * (H + feat));
         b.push_gemm(ST_GRU, gp, T, pw, k_off);
+        c->gru_rec.op_fc = (int)c->ops.size() - 1;
 
         const Act& nx = c->dec_in[0];
         NormApplyParams n{};
@@ -984,6 +1136,7 @@ int build_ctx(se_ctx* c) {
         });
         b.meta("gru.gln", 0, 8.0 * T * feat);
         b.push_norm(ST_GRU, n, w_off, b_off);
+        c->gru_rec.op_norm = (int)c->ops.size() - 1;
     }
     // ---- decoder ----------------------------------------------------------------------------------------------
     size_t wl_off = NONE, bl_off = NONE;
@@ -996,7 +1149,8 @@ int build_ctx(se_ctx* c) {
             const Act* skip = &c->enc_in[c->L - 1 - j];  // interior = output of encoder level L-2-j
             const Act& nx = c->dec_in[j + 1];
             const int s0 = slot++, s1 = slot++;
-            b.deconv_block(name, in, Cin, Co, 3, 1 << j, skip, nx.interior(), nx.sB, nx.sT, nx.sF, s0, s1);
+            b.deconv_block(name, in, Cin, Co, 3, 1 << j, skip, nx.interior(), nx.sB, nx.sT, nx.sF, s0, s1,
+                           c->train ? nx.dinterior() : nullptr);
         } else {
             c->stats_last = slot++;
             b.deconv_block(name, in, Cin, 2, 3, 1 << j, nullptr, nullptr, 0, 0, 0, c->stats_last, -1);
@@ -1005,10 +1159,33 @@ int build_ctx(se_ctx* c) {
         }
     }
     SE_REQUIRE(slot <= c->n_stats, "internal: statistics slots");
+    SE_REQUIRE(!c->alloc_failed, "out of device memory while allocating the per-layer training buffers");
 
     // ---- arenas -------------------------------------------------------------------------------------------------
     if (dev_alloc(c, &c->warena, c->warena_floats)) return 1;
     if (c->half && dev_alloc(c, reinterpret_cast<char**>(&c->warena_h), c->warena_floats * 2)) return 1;
+    if (c->train) {
+        // position map of the packed arena: run the packers on index-coded parameters (value = 1 + flat index; every
+        // packer only copies values, and 6.2 M indices are exact in fp32)
+        if (dev_alloc(c, &c->garena, c->warena_floats)) return 1;
+        if (dev_alloc(c, &c->wmap, c->warena_floats)) return 1;
+        HostParams hp;
+        int64_t off = 0;
+        for (const ParamInfo& pi : c->params) {
+            c->param_off.push_back(off);
+            std::vector<float> v((size_t)pi.numel());
+            for (size_t i = 0; i < v.size(); ++i) v[i] = (float)(off + (int64_t)i + 1);
+            hp.emplace(pi.name, std::move(v));
+            off += pi.numel();
+        }
+        c->n_theta = off;
+        SE_REQUIRE(off < (1 << 24), "internal: parameter count exceeds the exact-integer range of the index coding");
+        std::vector<float> arena(c->warena_floats, 0.f);
+        for (const PackFn& f : c->packers) f(hp, arena.data());
+        std::vector<int> map(c->warena_floats);
+        for (size_t i = 0; i < arena.size(); ++i) map[i] = (int)arena[i];
+        SE_CUDA_OK(cudaMemcpy(c->wmap, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     if (dev_alloc(c, &c->karena, c->khost.size())) return 1;
     SE_CUDA_OK(cudaMemcpy(c->karena, c->khost.data(), c->khost.size() * sizeof(int), cudaMemcpyHostToDevice));
     for (size_t i = 0; i < c->ops.size(); ++i) {
@@ -1045,6 +1222,8 @@ int build_ctx(se_ctx* c) {
         c->state_floats += count;
         c->roll_floats += count;
     };
+    if (c->train)
+        for (const Act& a : c->pre_act) add_state(a.base, a.sB, (long long)T * a.sT, (int)(a.padT0 * a.sT));
     for (const PreBuf& pb : c->pre_in) {  // rolled by the preconv kernel itself; a reset clears the whole slab
         RollEntry e{pb.base, pb.sB, 0, 0, (int)pb.sB};
         c->zero_tab.e[c->zero_tab.n++] = e;
@@ -1064,15 +1243,41 @@ int build_ctx(se_ctx* c) {
         c->zero_tab.e[c->zero_tab.n++] = e;
         c->state_floats += PHOP;
     }
+    if (c->train) {
+        SE_REQUIRE(c->roll.n == 3 + c->L + 2, "internal: training state table");
+        for (int e = 0; e < c->roll.n; ++e) {
+            float* p = nullptr;
+            if (dev_alloc(c, &p, (size_t)c->roll.e[e].count * maxB)) return 1;
+            c->carry_store.push_back(p);
+        }
+    }
     if (init_fft_tables()) return 1;
     return 0;
 }
 
-int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st) {
+int run_gemm(const se_ctx* c, const GemmParams& g, int stage, const std::string& label, cudaStream_t st) {
+    if (g.epi == EPI_GRU || g.epi == EPI_ELU_GATE) return launch_gemm_tf32(g, st);
+    if (c->tf32 && (c->half || ((c->tc_mask >> stage) & 1u)) && gemm_tf32_supported(g)) return launch_gemm_tf32(g, st);
+    SE_REQUIRE(!c->half, "internal: fp16 operands need the tensor-core GEMM (" + label + ")");
+    return launch_gemm_fp32(g, st);
+}
+
+// s0: first stream of the launch (training forward runs the recurrent ops chunk by chunk on a slice of the batch)
+int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0) {
     switch (op.kind) {
         case OP_GEMM: {
             GemmParams g = op.g;
             g.M = B * op.rows_per_stream;
+            if (s0) {
+                SE_REQUIRE(!g.a_half && !g.out_half, "internal: stream-offset launches are fp32 only");
+                g.A = reinterpret_cast<const float*>(g.A) + (long long)s0 * g.sB;
+                g.out += (long long)s0 * g.oB;
+                if (g.out2) g.out2 += (long long)s0 * g.o2B;
+                if (g.gi) g.gi += (long long)s0 * g.giB;
+                if (g.hprev) g.hprev += (long long)s0 * g.hB;
+                g.b0 = s0;
+                return run_gemm(c, g, op.stage, op.label, st);
+            }
             if (g.epi == EPI_GRU || g.epi == EPI_ELU_GATE) return launch_gemm_tf32(g, st);
             if (c->tf32 && (c->half || ((c->tc_mask >> op.stage) & 1u)) && gemm_tf32_supported(g))
                 return launch_gemm_tf32(g, st);
@@ -1091,7 +1296,9 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st) {
             return launch_preconv(pc, st);
         }
         case OP_GRU_PW:
-            return launch_gru_pointwise(op.gi, op.giB, op.gh, op.hprev, op.hB, op.hout, B, op.H, st);
+            return launch_gru_pointwise(op.gi + (long long)s0 * op.giB, op.giB, op.gh + (long long)s0 * 3 * op.H,
+                                        op.hprev + (long long)s0 * op.hB, op.hB, op.hout + (long long)s0 * op.hB, B, op.H,
+                                        st);
     }
     return 0;
 }
@@ -1185,12 +1392,327 @@ int run_stream_step(se_ctx* c, const IoDesc& io, int B, cudaStream_t st) {
     return 0;
 }
 
-int check_ready(se_ctx* c, int B) {
+int check_ready(se_ctx* c, int B, bool want_train = false) {
     SE_REQUIRE(c != nullptr, "null context");
+    SE_REQUIRE(c->train == want_train, want_train ? "this entry point needs a context created with training = 1"
+                                                  : "training context: use the se_crn_train_* entry points");
     SE_REQUIRE(c->weights_bound, "se_crn_bind_weights has not been called");
     SE_REQUIRE(B >= 0 && B <= c->maxB, "B exceeds max_streams of the context");
     SE_CUDA_OK(cudaSetDevice(c->device));
     return 0;
+}
+
+
+// ======================================================================================================================
+// training micro-step (train.py:195-198).  Batch layout: stream s = n * nb + i is chunk n of utterance i ("chunk-major").
+// The convolutional layers and all batched GEMMs run once over all N * nb chunk-streams: the carried frames of chunk n
+// are the trailing frames of chunk n-1's block input (CRN_ELU.py:243), copied in front of the op that consumes them.
+// Only the GRU recurrence is serial over chunks (its hidden state crosses chunk boundaries, CRN_ELU.py:173,185).
+// ======================================================================================================================
+int train_forward(se_ctx* c, const float* mixture, int nb, long long L, int flag, float* pred, cudaStream_t st) {
+    const int front = flag ? 0 : PHOP;  // CRN_ELU.py:474-476
+    int gap = 0, N = 0;
+    se_chunk_grid(L + front, KCHUNK, &gap, &N);
+    const int Bp = N * nb;
+    SE_REQUIRE(Bp <= c->maxB, "se_crn_train_forward: chunks * utterances = " + std::to_string(Bp) +
+                                  " exceeds max_streams = " + std::to_string(c->maxB) + " of the training context");
+    SE_REQUIRE(!flag || (c->t_have_fwd && c->t_nb == nb), "se_crn_train_forward: flag=1 needs a previous piece of the same batch");
+    c->t_nb = nb;
+    c->t_N = N;
+    c->t_L = L;
+    c->t_front = front;
+    SE_CUDA_OK(cudaMemsetAsync(c->stats, 0, (size_t)c->n_stats * 2 * c->maxB * sizeof(double), st));
+    // chunk 0: zero state (CRN_ELU.py:480-481) or the state carried from the previous piece (flag=True)
+    for (int e = 0; e < c->roll.n; ++e) {
+        const RollEntry& r = c->roll.e[e];
+        if (launch_copy_rows(r.base + r.dst_off, r.sB, flag ? c->carry_store[e] : nullptr, r.count, r.count, nb, st)) return 1;
+    }
+    IoDesc io{mixture, 3 * L, L, -(long long)PHOP - front, L, nullptr, 0, 0};
+    if (launch_set_io(c->io_dev, io, st)) return 1;
+    {
+        StftParams sp{};
+        sp.io = c->io_dev;
+        sp.B = Bp;
+        sp.M = 3;
+        sp.student = c->student;
+        const Act& a = c->pre_act[0];
+        sp.feat = a.interior();
+        sp.fB = a.sB;
+        sp.fC = 1;
+        sp.fT = a.sT;
+        sp.fF = a.sF;
+        sp.noisy = c->noisy;
+        sp.nb = nb;
+        sp.hop_chunk = PHOP;
+        if (launch_stft_features(sp, st)) return 1;
+    }
+    auto shift_state = [&](int e) -> int {  // chunk n (n >= 1) <- trailing frames of chunk n-1
+        const RollEntry& r = c->roll.e[e];
+        return launch_copy_rows(r.base + (long long)nb * r.sB + r.dst_off, r.sB, r.base + r.src_off, r.sB, r.count,
+                                Bp - nb, st);
+    };
+    for (size_t i = 0; i < c->ops.size();) {
+        const Op& op = c->ops[i];
+        if (op.chunk_serial) {
+            size_t j = i;
+            while (j < c->ops.size() && c->ops[j].chunk_serial && c->ops[j].gru_layer == op.gru_layer) ++j;
+            const RollEntry& r = c->roll.e[3 + c->L + op.gru_layer];
+            for (int n = 0; n < N; ++n) {
+                if (n > 0 && launch_copy_rows(r.base + (long long)n * nb * r.sB + r.dst_off, r.sB,
+                                              r.base + (long long)(n - 1) * nb * r.sB + r.src_off, r.sB, r.count, nb, st))
+                    return 1;
+                for (size_t k = i; k < j; ++k)
+                    if (launch_op(c, c->ops[k], nb, st, n * nb)) return 1;
+            }
+            i = j;
+            continue;
+        }
+        if (op.state_entry >= 0 && N > 1 && shift_state(op.state_entry)) return 1;
+        if (launch_op(c, op, Bp, st)) return 1;
+        ++i;
+    }
+    {
+        MaskIstftParams mp{};
+        mp.B = Bp;
+        mp.student = c->student;
+        mp.y = c->ylast;
+        mp.stats = c->stats + (size_t)c->stats_last * 2 * c->maxB;
+        mp.count = 2.0 * NBIN * T;
+        mp.w = c->w_last;
+        mp.b = c->b_last;
+        mp.noisy = c->noisy;
+        mp.out_chunk = c->chunks;
+        if (launch_mask_istft(mp, st)) return 1;
+    }
+    if (launch_over_add_cm(c->chunks, nb, N, KCHUNK, front, L, pred, st)) return 1;
+    // state carried to a following flag=True piece: trailing frames / last hidden state of the last chunk
+    for (int e = 0; e < c->roll.n; ++e) {
+        const RollEntry& r = c->roll.e[e];
+        if (launch_copy_rows(c->carry_store[e], r.count, r.base + (long long)(N - 1) * nb * r.sB + r.src_off, r.sB, r.count,
+                             nb, st))
+            return 1;
+    }
+    c->t_have_fwd = true;
+    return 0;
+}
+
+float* garena_of(const se_ctx* c, const void* w) {
+    return c->garena + (reinterpret_cast<const float*>(w) - c->warena);
+}
+
+// weight + data gradient of one forward GEMM op.  G: d loss / d (pre-activation output), rows addressed by `gs`.
+int dense_bwd(se_ctx* c, const Op& op, int B, const float* G, StridedRows gs, float* dA, cudaStream_t st) {
+    GemmParams g = op.g;
+    g.M = B * op.rows_per_stream;
+    if (launch_wgrad(g, G, gs, garena_of(c, g.W), garena_of(c, g.bias), st)) return 1;
+    if (dA != nullptr && launch_dgrad(g, G, gs, dA, st)) return 1;
+    return 0;
+}
+
+int gln_bwd(se_ctx* c, const NormApplyParams& n, int B, int F, const float* y, const double* stats, double count,
+            const float* w, const float* g, StridedRows gs, float* dy, int oC, int ostep, int ooff, int elu,
+            cudaStream_t st) {
+    GlnBwdParams p{};
+    p.B = B;
+    p.T = T;
+    p.F = F;
+    p.C = n.C;
+    p.student = c->student;
+    p.per_feature = n.per_feature;
+    p.elu = elu;
+    p.y = y;
+    p.stats = stats;
+    p.count = count;
+    p.w = w;
+    p.g = g;
+    p.gB = gs.sB;
+    p.gT = gs.sT;
+    p.gF = gs.sF;
+    p.dw = garena_of(c, w);
+    p.db = garena_of(c, w == n.w ? n.b : n.br);
+    p.red = c->red;
+    p.dy = dy;
+    p.oC = oC;
+    p.ostep = ostep;
+    p.ooff = ooff;
+    return launch_gln_bwd(p, st);
+}
+
+int train_backward(se_ctx* c, const float* dpred, float* grad_flat, cudaStream_t st) {
+    SE_REQUIRE(c->t_have_fwd, "se_crn_train_backward: no forward pass to differentiate");
+    const int nb = c->t_nb, N = c->t_N, Bp = N * nb, H = c->H, L = c->L, feat = c->feat;
+    SE_CUDA_OK(cudaMemsetAsync(c->garena, 0, c->warena_floats * sizeof(float), st));
+    for (auto& tw : c->twins) SE_CUDA_OK(cudaMemsetAsync(tw.first, 0, tw.second, st));
+    float *s0 = c->sc[0], *s1 = c->sc[1], *s2 = c->sc[2], *s3 = c->sc[3];
+
+    // ---- over_add / iSTFT adjoint / mask -> gradient w.r.t. the normalised last deconv output ------------------------
+    if (launch_over_add_cm_bwd(dpred, nb, N, KCHUNK, c->t_front, c->t_L, c->dchunks, st)) return 1;
+    {
+        IoDesc io{c->dchunks, (long long)KCHUNK, 0, 0, KCHUNK, nullptr, 0, 0};
+        if (launch_set_io(c->io_dev, io, st)) return 1;
+        StftParams sp{};
+        sp.io = c->io_dev;
+        sp.B = Bp;
+        sp.M = 1;
+        sp.spec_ref = c->dspec;
+        if (launch_stft_features(sp, st)) return 1;
+        MaskBwdParams mb{};
+        mb.B = Bp;
+        mb.student = c->student;
+        mb.dspec = c->dspec;
+        mb.y = c->ylast;
+        mb.stats = c->stats + (size_t)c->stats_last * 2 * c->maxB;
+        mb.count = 2.0 * NBIN * T;
+        mb.w = c->w_last;
+        mb.b = c->b_last;
+        mb.noisy = c->noisy;
+        mb.g = s0;  // [Bp][T][201][2]
+        if (launch_mask_bwd(mb, st)) return 1;
+    }
+    // ---- decoder, last block first --------------------------------------------------------------------------------
+    for (int j = L - 1; j >= 0; --j) {
+        const DeconvRec& r = c->deconv_recs[j];
+        const Op& dop = c->ops[r.op_deconv];
+        const int C = r.Cop;
+        const StridedRows ys{(long long)T * r.Fy * C, (long long)r.Fy * C, 2LL * C};  // rows of the merged-parity GEMM in y
+        if (r.skip == nullptr) {
+            NormApplyParams n{};
+            n.C = C;
+            n.w = c->w_last;
+            n.b = c->b_last;
+            const StridedRows gs{(long long)T * r.Fy * C, (long long)r.Fy * C, C};
+            if (gln_bwd(c, n, Bp, r.Fy, r.y, c->stats + (size_t)c->stats_last * 2 * c->maxB, 2.0 * NBIN * T, n.w, s0, gs, s1,
+                        C, 1, 0, 1, st))
+                return 1;
+        } else {
+            const Op& nop = c->ops[r.op_norm];
+            const Op& sop = c->ops[r.op_skip];
+            const NormApplyParams& n = nop.n;
+            BlendBwdParams bp{};
+            bp.B = Bp;
+            bp.T = T;
+            bp.Fs = r.Fs;
+            bp.Fy = r.Fy;
+            bp.C = C;
+            bp.student = c->student;
+            bp.g = r.gout;
+            bp.gB = r.gs.sB;
+            bp.gT = r.gs.sT;
+            bp.gF = r.gs.sF;
+            bp.y = r.y;
+            bp.rm = r.rm;
+            bp.rr = r.rr;
+            bp.stats = n.stats;
+            bp.stats_r = n.stats_r;
+            bp.count = n.count;
+            bp.count_r = n.count_r;
+            bp.w = n.w;
+            bp.b = n.b;
+            bp.wr = n.wr;
+            bp.br = n.br;
+            bp.g_o = s0;  // [Bp][T][Fy][C]
+            bp.g_r = s2;  // [Bp][T][Fs][C]
+            bp.G2 = s3;   // [Bp*T*Fs][2C]
+            if (launch_blend_bwd(bp, st)) return 1;
+            // residual-mask norm backward -> even columns of G2, then the skip 1x1 pair (dgrad into the skip tensor)
+            const StridedRows rs{(long long)T * r.Fs * C, (long long)r.Fs * C, C};
+            if (gln_bwd(c, n, Bp, r.Fs, r.rm, n.stats_r, n.count_r, n.wr, s2, rs, s3, 2 * C, 2, 0, 0, st)) return 1;
+            const StridedRows g2s{(long long)T * r.Fs * 2 * C, (long long)r.Fs * 2 * C, 2LL * C};
+            if (dense_bwd(c, sop, Bp, s3, g2s, r.skip->dbase + (r.skip->interior() - r.skip->base), st)) return 1;
+            // main norm backward fused with the ELU backward -> s1 = d loss / d deconv pre-activation
+            const StridedRows os{(long long)T * r.Fy * C, (long long)r.Fy * C, C};
+            if (gln_bwd(c, n, Bp, r.Fy, r.y, n.stats, n.count, n.w, s0, os, s1, C, 1, 0, 1, st)) return 1;
+        }
+        if (dense_bwd(c, dop, Bp, s1, ys, r.in->dbase, st)) return 1;
+    }
+    // ---- GRU + Linear + ELU + GLN(last) -----------------------------------------------------------------------------
+    {
+        const GruRec& gr = c->gru_rec;
+        const Op& nop = c->ops[gr.op_norm];
+        const Op& fop = c->ops[gr.op_fc];
+        const Act& d0 = c->dec_in[0];
+        const StridedRows gs{d0.sB, d0.sT, d0.sF};
+        if (gln_bwd(c, nop.n, Bp, c->Fg, c->fcraw, nop.n.stats, nop.n.count, nop.n.w, d0.dinterior(), gs, s1, c->Cg, 1, 0, 1,
+                    st))
+            return 1;
+        const StridedRows fs{(long long)T * feat, feat, 0};
+        if (dense_bwd(c, fop, Bp, s1, fs, c->dH[1] + H, st)) return 1;
+        const StridedRows g3{(long long)T * 3 * H, 3LL * H, 0};
+        for (int l = 1; l >= 0; --l) {
+            const Op& hop = c->ops[gr.op_hh[l]];
+            const Op& iop = c->ops[gr.op_in[l]];
+            // recurrent projections of all T steps at once: gh[t] = W_hh h[t-1] + b_hh  (h[0..T-1] are saved in hseq)
+            GemmParams gh = hop.g;
+            gh.A = c->hseq[l];
+            gh.sB = (long long)(T + 1) * H;
+            gh.sT = H;
+            gh.Tn = T;
+            gh.M = Bp * T;
+            gh.epi = EPI_BIAS;
+            gh.out = c->gh_all;
+            gh.oB = (long long)T * 3 * H;
+            gh.oT = 3 * H;
+            gh.vec4 = 1;
+            if (run_gemm(c, gh, ST_GRU, "gru.bwd.hh", st)) return 1;
+            SE_CUDA_OK(cudaMemsetAsync(c->dhrec, 0, (size_t)Bp * H * sizeof(float), st));
+            GemmParams rec = hop.g;  // dhrec[b][:] += dgh_t . W_hh
+            rec.A = c->dhrec;
+            rec.sB = H;
+            rec.sT = 0;
+            rec.sF = 0;
+            rec.Tn = 1;
+            rec.M = Bp;
+            for (int t = T - 1; t >= 0; --t) {
+                if (launch_gru_bwd_pw(c->gi_l[l] + (long long)t * 3 * H, (long long)T * 3 * H,
+                                      c->gh_all + (long long)t * 3 * H, (long long)T * 3 * H,
+                                      c->hseq[l] + (long long)t * H, (long long)(T + 1) * H,
+                                      c->dH[l] + (long long)(t + 1) * H, (long long)(T + 1) * H, c->dhrec,
+                                      c->dgi + (long long)t * 3 * H, c->dgh + (long long)t * 3 * H, (long long)T * 3 * H, Bp,
+                                      H, st))
+                    return 1;
+                if (t > 0 && launch_dgrad(rec, c->dgh + (long long)t * 3 * H, StridedRows{(long long)T * 3 * H, 0, 0},
+                                          c->dhrec, st))
+                    return 1;
+            }
+            gh.out = nullptr;
+            if (launch_wgrad(gh, c->dgh, g3, garena_of(c, gh.W), garena_of(c, gh.bias), st)) return 1;
+            if (dense_bwd(c, iop, Bp, c->dgi, g3, l == 1 ? c->dH[0] + H : c->dxg, st)) return 1;
+        }
+    }
+    // ---- encoder and pre-convolutions, last block first ------------------------------------------------------------
+    for (int i = (int)c->conv_recs.size() - 1; i >= 0; --i) {
+        const ConvRec& r = c->conv_recs[i];
+        const Op& cop = c->ops[r.op_conv];
+        const Op& gop = c->ops[r.op_gate];
+        const Op& nop = c->ops[r.op_norm];
+        const int C = r.Cp_out;
+        const long long rows = (long long)Bp * T * r.Fo;
+        if (r.residual)  // out = GLN(..) + x: the block input receives the output gradient as well (CRN_ELU.py:376)
+            if (launch_add_strided(r.in->dinterior(), StridedRows{r.in->sB, r.in->sT, r.in->sF}, r.gout, r.gs, Bp, T, r.Fo,
+                                   r.in->C, st))
+                return 1;
+        if (gln_bwd(c, nop.n, Bp, r.Fo, r.y, nop.n.stats, nop.n.count, nop.n.w, r.gout, r.gs, s0, C, 1, 0, 0, st)) return 1;
+        GemmParams uv = gop.g;  // recompute the two 1x1 pre-activations (u, v) from the saved elu(conv)
+        uv.M = (int)rows;
+        uv.epi = EPI_BIAS;
+        uv.out = s1;
+        uv.oB = (long long)T * r.Fo * 2 * C;
+        uv.oT = (long long)r.Fo * 2 * C;
+        uv.oF = 2 * C;
+        uv.stats = nullptr;
+        uv.vec4 = 1;
+        if (run_gemm(c, uv, gop.stage, "gate.bwd.uv", st)) return 1;
+        if (launch_gate_bwd(s1, s0, rows, C, st)) return 1;
+        SE_CUDA_OK(cudaMemsetAsync(s2, 0, (size_t)rows * C * sizeof(float), st));
+        const StridedRows g2{(long long)T * r.Fo * 2 * C, (long long)r.Fo * 2 * C, 2LL * C};
+        if (dense_bwd(c, gop, Bp, s1, g2, s2, st)) return 1;
+        if (launch_elu_bwd(s2, r.e, rows * C, st)) return 1;
+        const StridedRows g1{(long long)T * r.Fo * C, (long long)r.Fo * C, C};
+        if (dense_bwd(c, cop, Bp, s2, g1, r.need_dgrad ? r.in->dbase : nullptr, st)) return 1;
+    }
+    // ---- packed-arena gradients -> flat vector in the reference layout (registry order) --------------------------------
+    SE_CUDA_OK(cudaMemsetAsync(grad_flat, 0, (size_t)c->n_theta * sizeof(float), st));
+    return launch_arena_scatter_add(c->garena, c->wmap, grad_flat, (long long)c->warena_floats, st);
 }
 
 }  // namespace
@@ -1485,7 +2007,9 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
         return (i >= 0 && i < limit) ? i : -1;
     };
     int i;
-    if ((i = idx_of("pre_in", 3)) >= 0) {  // planar -> [T][F][5] on the host
+    if ((i = idx_of("pre_in", 3)) >= 0 && c->train) {
+        from_act(c->pre_act[i]);
+    } else if ((i = idx_of("pre_in", 3)) >= 0) {  // planar -> [T][F][5] on the host
         const PreBuf& pb = c->pre_in[i];
         dims[0] = T;
         dims[1] = NBIN;
@@ -1534,6 +2058,35 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
                             (size_t)f * ch * sizeof(float), t, cudaMemcpyDeviceToHost));
     (void)sF;
     return 0;
+}
+
+
+// ---- training ---------------------------------------------------------------------------------------------------
+int64_t se_crn_num_theta(const se_ctx* c) { return c ? c->n_theta : -1; }
+int64_t se_crn_param_offset(const se_ctx* c, int i) {
+    return (c && c->train && i >= 0 && i < (int)c->param_off.size()) ? c->param_off[i] : -1;
+}
+
+int se_crn_bind_weights_flat(se_ctx* c, const float* theta, void* stream) {
+    SE_REQUIRE(c != nullptr && theta != nullptr, "se_crn_bind_weights_flat: null argument");
+    SE_REQUIRE(c->train, "se_crn_bind_weights_flat needs a context created with training = 1");
+    SE_CUDA_OK(cudaSetDevice(c->device));
+    if (launch_arena_gather(c->warena, c->wmap, theta, (long long)c->warena_floats, (cudaStream_t)stream)) return 1;
+    c->weights_bound = true;
+    return 0;
+}
+
+int se_crn_train_forward(se_ctx* c, const float* mixture, int B, int64_t L, int flag, float* pred, void* stream) {
+    if (check_ready(c, 0, true)) return 1;
+    SE_REQUIRE(mixture != nullptr && pred != nullptr, "se_crn_train_forward: null buffer");
+    SE_REQUIRE(B > 0 && L > 0, "se_crn_train_forward: empty batch");
+    return train_forward(c, mixture, B, L, flag, pred, (cudaStream_t)stream);
+}
+
+int se_crn_train_backward(se_ctx* c, const float* dpred, float* grad_flat, void* stream) {
+    if (check_ready(c, 0, true)) return 1;
+    SE_REQUIRE(dpred != nullptr && grad_flat != nullptr, "se_crn_train_backward: null buffer");
+    return train_backward(c, dpred, grad_flat, (cudaStream_t)stream);
 }
 
 int se_crn_launches_per_chunk(const se_ctx* c) { return c ? count_launches(c) : 0; }

@@ -65,9 +65,10 @@ __global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
         s.w400[i] = c_w400[i];
     }
     if (tid < 20) s.w20[tid] = c_w20[tid];
-    const float* in = p.io->in + b * p.io->in_stream_stride;
+    const int brow = p.nb > 0 ? b % p.nb : b;  // training layout: stream = chunk * nb + utterance
+    const float* in = p.io->in + brow * p.io->in_stream_stride;
     const long long mic_stride = p.io->in_mic_stride;
-    const long long in_off = p.io->in_offset, in_len = p.io->in_len;
+    const long long in_off = p.io->in_offset + (p.nb > 0 ? (long long)(b / p.nb) * p.hop_chunk : 0), in_len = p.io->in_len;
     for (int m = 0; m < M; ++m) {
         for (int i = tid; i < SPAN; i += blockDim.x) {
             const int n = t0 * HOP + i - NFFT / 2;  // sample index inside the chunk (center=True zero padding)
@@ -361,6 +362,78 @@ __global__ void __launch_bounds__(256) mask_istft_kernel(MaskIstftParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// training layout (stream s = n*nb + i = chunk n of utterance i): chunk-level overlap-add and the adjoints of
+// over_add / iSTFT / mask (the adjoint of the iSTFT is the STFT of dchunk / envelope scaled by c_k / n_fft)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) over_add_cm_kernel(const float* __restrict__ chunks, int nb, int N, int front,
+                                                          long long L, float* __restrict__ pred) {
+    constexpr int P = K / 2;
+    const long long total = (long long)nb * L;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int u = (int)(i / L);
+        const long long q = i - (long long)u * L + P + front;  // position on the padded grid (utility.py:393-403)
+        const int n1 = (int)(q / P);
+        float a = 0.f, b = 0.f;
+        if (n1 >= 1 && n1 - 1 < N) a = chunks[((long long)(n1 - 1) * nb + u) * K + (q - (long long)(n1 - 1) * P)];
+        if (n1 < N) b = chunks[((long long)n1 * nb + u) * K + (q - (long long)n1 * P)];
+        pred[i] = (a + b) / 2;
+    }
+}
+
+__global__ void __launch_bounds__(256) over_add_cm_bwd_kernel(const float* __restrict__ dpred, int nb, int N, int front,
+                                                              long long L, float* __restrict__ dchunks) {
+    constexpr int P = K / 2;
+    const long long total = (long long)nb * N * K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % K);
+        const long long s = i / K;
+        const int u = (int)(s % nb), n = (int)(s / nb);
+        const long long q = (long long)n * P + j;
+        const long long jj = q - P - front;
+        float v = 0.f;
+        if (q >= P && q < (long long)N * P && jj >= 0 && jj < L) v = 0.5f * dpred[(long long)u * L + jj] / c_env[j];
+        dchunks[i] = v;
+    }
+}
+
+__device__ __forceinline__ float decompress_cirm_grad(float m) {  // d/dm of utility.py:439-442
+    return fabsf(m) < 9.9f ? 200.f / (100.f - m * m) : 0.f;
+}
+
+__global__ void __launch_bounds__(256) mask_bwd_kernel(MaskBwdParams p) {
+    const long long per = (long long)T * NBIN;
+    const long long total = per * p.B;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per);
+        const int r = (int)(i - b * per);
+        const int t = r / NBIN, k = r - t * NBIN;
+        const double sum = p.stats[2 * b], ssq = p.stats[2 * b + 1];
+        const double mu = sum / p.count;
+        double var = ssq / p.count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const float varf = (float)var;
+        const float den = p.student ? (sqrtf(varf) + 1e-8f) : (sqrtf(varf + 1e-8f) + 1e-8f);
+        const float mean = (float)mu, inv = 1.f / den;
+        float2 d = reinterpret_cast<const float2*>(p.dspec)[((long long)b * NBIN + k) * T + t];
+        const bool edge = (k == 0 || k == NBIN - 1);
+        const float ck = (edge ? 1.f : 2.f) / NFFT;  // adjoint of the C2R transform
+        d.x *= ck;
+        d.y = edge ? 0.f : d.y * ck;
+        const float2 y = reinterpret_cast<const float2*>(p.y)[i];
+        const float2 x = reinterpret_cast<const float2*>(p.noisy)[i];
+        const float m0 = (y.x - mean) * inv * p.w[0] + p.b[0];
+        const float m1 = (y.y - mean) * inv * p.w[1] + p.b[1];
+        const float dmr = d.x * x.x + d.y * x.y;   // E = M * X (complex): dM = dE * conj(X)
+        const float dmi = -d.x * x.y + d.y * x.x;
+        reinterpret_cast<float2*>(p.g)[i] = make_float2(dmr * decompress_cirm_grad(m0), dmi * decompress_cirm_grad(m1));
+    }
+}
+
 }  // namespace
 
 int init_fft_tables() {
@@ -418,6 +491,36 @@ int launch_features_from_spec(const float* spec, int B, int M, int student, floa
 int launch_mask_istft(const MaskIstftParams& p, cudaStream_t st) {
     if (p.B == 0) return 0;
     mask_istft_kernel<<<p.B, 256, sizeof(IstftSmem), st>>>(p);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_over_add_cm(const float* chunks, int nb, int N, int Kc, int front, long long L, float* pred, cudaStream_t st) {
+    SE_REQUIRE(Kc == K, "over_add_cm: chunk length must be 3200");
+    const long long total = (long long)nb * L;
+    if (total <= 0) return 0;
+    long long g = (total + 255) / 256;
+    over_add_cm_kernel<<<(int)(g > 2368 ? 2368 : g), 256, 0, st>>>(chunks, nb, N, front, L, pred);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_over_add_cm_bwd(const float* dpred, int nb, int N, int Kc, int front, long long L, float* dchunks,
+                           cudaStream_t st) {
+    SE_REQUIRE(Kc == K, "over_add_cm_bwd: chunk length must be 3200");
+    const long long total = (long long)nb * N * K;
+    if (total <= 0) return 0;
+    long long g = (total + 255) / 256;
+    over_add_cm_bwd_kernel<<<(int)(g > 2368 ? 2368 : g), 256, 0, st>>>(dpred, nb, N, front, L, dchunks);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_mask_bwd(const MaskBwdParams& p, cudaStream_t st) {
+    if (p.B <= 0) return 0;
+    const long long total = (long long)p.B * T * NBIN;
+    long long g = (total + 255) / 256;
+    mask_bwd_kernel<<<(int)(g > 2368 ? 2368 : g), 256, 0, st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -1,4 +1,4 @@
-// Loss terms of compute_loss (CRN_ELU.py:513-535; fullsubnet.py:964-987), forward only:
+// Loss terms of compute_loss (CRN_ELU.py:513-535; fullsubnet.py:964-987), forward and (se_loss_terms_grad) backward:
 //   se_cal_si_snr  = utility.cal_si_snr (utility.py:207-223)
 //   se_stoi_loss   = utility.stoi_loss (utility.py:821-916): torchaudio Resample 16k -> 10k (polyphase windowed sinc),
 //                    removeSilentFrames (utility.py:521-571), Spectrogram(512, win 256, hop 128, power 2), 15 one-third
@@ -43,7 +43,7 @@ __device__ __forceinline__ float block_max(float v, float* red) {
 // ---- SI-SNR --------------------------------------------------------------------------------------------------------
 // out[i] = 20 log10(eps + |proj| / (|est_c - proj| + eps)), proj = <est_c, src_c> src_c / (|src_c|^2 + eps)
 __global__ void __launch_bounds__(kThreads) si_snr_kernel(const float* est, const float* src, const int* len, long long L,
-                                                          float eps, float* per_item) {
+                                                          float eps, float* per_item, float* grad, float gscale) {
     __shared__ double red[kThreads / 32];
     const int i = blockIdx.x;
     const int n = len ? min((long long)len[i], L) : L;
@@ -73,6 +73,26 @@ __global__ void __launch_bounds__(kThreads) si_snr_kernel(const float* est, cons
     }
     const float fp = sqrtf((float)block_sum(np, red)), fr = sqrtf((float)block_sum(nr, red));
     if (threadIdx.x == 0) per_item[i] = 20.f * log10f(eps + fp / (fr + eps));
+    if (grad == nullptr) return;
+    // backward: val = 20 log10(eps + q), q = fp / (fr + eps), tr = alpha sc, r = ec - tr, alpha = <ec, sc> / (nss + eps)
+    const float q = fp / (fr + eps);
+    const float dq = 20.f / (2.302585093f * (eps + q)) * gscale;
+    const float dfp = dq / (fr + eps), dfr = -dq * fp / ((fr + eps) * (fr + eps));
+    const float a_r = fr > 0.f ? dfr / fr : 0.f;                      // d val / d r[k] = a_r * r[k]
+    const float tr_sc = alpha * fnss, r_sc = fdot - alpha * fnss;     // <tr, sc>, <r, sc>
+    const float dalpha = (fp > 0.f ? dfp * tr_sc / fp : 0.f) - a_r * r_sc;
+    const float a_s = dalpha / (fnss + eps);                          // + a_s * sc[k]
+    double gs = 0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const float ec = e[k] - me, sc = s[k] - ms;
+        gs += (double)(a_r * (ec - alpha * sc) + a_s * sc);
+    }
+    const float gmean = (float)(block_sum(gs, red) / n);             // ec = e - mean(e)
+    float* g = grad + (long long)i * L;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const float ec = e[k] - me, sc = s[k] - ms;
+        g[k] = a_r * (ec - alpha * sc) + a_s * sc - gmean;
+    }
 }
 
 __global__ void mean_kernel(const float* v, int n, float scale, float* out) {
@@ -98,6 +118,15 @@ struct StoiWork {
     float* oct;     // [B][2][15][NSmax]
     long long L10max, Lsmax;
     int NFmax, NSmax;
+    // backward (null: forward only)
+    float* spec;    // [B][NSmax][NBmax][2] spectrum of the prediction, then 2 dP re / 2 dP im
+    float* doct;    // [B][15][NSmax]
+    float* dsil;    // [B][Lsmax]
+    float* dr10;    // [B][L10max]
+    int* rank;      // [B][NFmax] position of frame m among the kept frames, -1 = silent
+    float* dpred;   // [B][L] d (-mean D) / d pred
+    int NBmax;
+    float gscale;   // -1 / B
 };
 
 __global__ void __launch_bounds__(kThreads) stoi_kernel(const float* y_true, const float* y_pred, const int* lens,
@@ -195,6 +224,11 @@ __global__ void __launch_bounds__(kThreads) stoi_kernel(const float* y_true, con
                 im = fmaf(v, t.y, im);
             }
             const float pw = re * re + im * im;
+            if (sgl == 1 && w.spec != nullptr) {
+                float* sp = w.spec + (((long long)item * w.NSmax + r) * w.NBmax + (k - klo)) * 2;
+                sp[0] = re;
+                sp[1] = im;
+            }
             for (int j = 0; j < 15; ++j)
                 if (k >= c_st.band_lo[j] && k < c_st.band_hi[j]) atomicAdd(&oct[sgl][j * w.NSmax + r], pw);
         }
@@ -241,6 +275,115 @@ __global__ void __launch_bounds__(kThreads) stoi_kernel(const float* y_true, con
     }
     const double tot = block_sum(dsum, red);
     if (tid == 0) D[item] = (float)(tot / (15.0 * M));
+    if (w.dpred == nullptr) return;
+
+    // ================= backward: d (-mean_B D) / d pred, stage by stage in reverse =====================================
+    float* doct = w.doct + (long long)item * 15 * w.NSmax;
+    float* dsil = w.dsil + (long long)item * w.Lsmax;
+    float* dr10 = w.dr10 + (long long)item * w.L10max;
+    int* rank = w.rank + (long long)item * w.NFmax;
+    float* spec = w.spec + (long long)item * w.NSmax * w.NBmax * 2;
+    for (int i = tid; i < 15 * w.NSmax; i += blockDim.x) doct[i] = 0.f;
+    for (long long i = tid; i < Ls; i += blockDim.x) dsil[i] = 0.f;
+    for (int m = tid; m < NF; m += blockDim.x) rank[m] = -1;
+    __syncthreads();
+    for (int k = tid; k < ns; k += blockDim.x) rank[sel[k]] = k;
+    // (4') correlation rows -> d oct_pred
+    const float wrow = w.gscale / (15.0f * M);
+    for (int row = tid; row < 15 * M; row += blockDim.x) {
+        const int m = row / 15, j = row % 15;
+        const float* X = oct[0] + j * w.NSmax + m;
+        const float* Y = oct[1] + j * w.NSmax + m;
+        float nx = 0.f, ny = 0.f, mx = 0.f;
+        for (int i = 0; i < seglen; ++i) {
+            nx = fmaf(X[i], X[i], nx);
+            ny = fmaf(Y[i], Y[i], ny);
+            mx += X[i];
+        }
+        const float sny = sqrtf(ny), snx = sqrtf(nx);
+        const float alpha = snx / (sny + (float)kEps64);
+        mx /= seglen;
+        float my = 0.f;
+        for (int i = 0; i < seglen; ++i) my += fminf(Y[i] * alpha, X[i] + X[i] * c);
+        my /= seglen;
+        float sxx = 0.f, syy = 0.f, sxy = 0.f;
+        for (int i = 0; i < seglen; ++i) {
+            const float xc = X[i] - mx, yc = fminf(Y[i] * alpha, X[i] + X[i] * c) - my;
+            sxx = fmaf(xc, xc, sxx);
+            syy = fmaf(yc, yc, syy);
+            sxy = fmaf(xc, yc, sxy);
+        }
+        const float ssy = sqrtf(syy);
+        const float dx = sqrtf(sxx) + (float)kEps64, dy = ssy + (float)kEps64;
+        const float c1 = 1.f / (dx * dy), c2 = ssy > 0.f ? sxy / (dx * dy * dy * ssy) : 0.f;
+        // d value / d y_i = c1 xc_i - c2 yc_i (its mean over i vanishes because xc and yc are centred)
+        float dalpha = 0.f;
+        for (int i = 0; i < seglen; ++i) {
+            const float ay = Y[i] * alpha, lim = X[i] + X[i] * c;
+            if (ay < lim) dalpha += (c1 * (X[i] - mx) - c2 * (ay - my)) * Y[i];
+        }
+        const float da = sny > 0.f ? -dalpha * snx / ((sny + (float)kEps64) * (sny + (float)kEps64) * sny) : 0.f;
+        for (int i = 0; i < seglen; ++i) {
+            const float ay = Y[i] * alpha, lim = X[i] + X[i] * c;
+            float g = da * Y[i];
+            if (ay < lim) g += alpha * (c1 * (X[i] - mx) - c2 * (ay - my));
+            atomicAdd(&doct[j * w.NSmax + m + i], wrow * g);
+        }
+    }
+    __syncthreads();
+    // (3') band energies -> power spectrum -> frames of the silent-frame-removed signal
+    {
+        const int nb = khi - klo;
+        for (int o = tid; o < NS * nb; o += blockDim.x) {
+            const int r = o / nb, k = klo + o % nb;
+            float dP = 0.f;
+            for (int j = 0; j < 15; ++j)
+                if (k >= c_st.band_lo[j] && k < c_st.band_hi[j]) dP += doct[j * w.NSmax + r] / (2.f * oct[1][j * w.NSmax + r]);
+            float* sp = spec + ((long long)r * w.NBmax + (k - klo)) * 2;
+            sp[0] *= 2.f * dP;
+            sp[1] *= 2.f * dP;
+        }
+        __syncthreads();
+        for (int o = tid; o < NS * 256; o += blockDim.x) {
+            const int r = o >> 8, n = o & 255;
+            float dv = 0.f;
+            const float* sp = spec + (long long)r * w.NBmax * 2;
+            for (int kk = 0; kk < nb; ++kk) {
+                const float2 t = tw[((klo + kk) * (n + 128)) & 511];
+                dv = fmaf(sp[2 * kk], t.x, dv);
+                dv = fmaf(sp[2 * kk + 1], t.y, dv);
+            }
+            long long pos = 128LL * r + 128 + n - 256;
+            if (pos < 0) pos = -pos;
+            if (pos >= Ls) pos = 2 * (Ls - 1) - pos;
+            atomicAdd(&dsil[pos], dv * c_st.hann_per[n]);
+        }
+        __syncthreads();
+    }
+    // (2') overlap-add of the kept frames -> resampled signal
+    for (long long p = tid; p < L10; p += blockDim.x) {
+        const int m = (int)(p / 128), i = (int)(p % 128);
+        float v = 0.f;
+        if (m < NF && rank[m] >= 0) v += c_st.hann_sym[i] * dsil[128LL * rank[m] + i];
+        if (m >= 1 && m - 1 < NF && rank[m - 1] >= 0) v += c_st.hann_sym[128 + i] * dsil[128LL * (rank[m - 1] + 1) + i];
+        dr10[p] = v;
+    }
+    __syncthreads();
+    // (1') polyphase resampler: out[5q + j] = sum_k kern[j][k] wave[8q + k - 10]
+    float* dp = w.dpred + (long long)item * L;
+    for (long long idx = tid; idx < len; idx += blockDim.x) {
+        float acc = 0.f;
+        for (long long q = (idx + 10) / 8; q >= 0; --q) {
+            const long long k = idx + 10 - 8 * q;
+            if (k >= 28) break;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const long long n = 5 * q + j;
+                if (n < L10) acc = fmaf(c_st.resamp[j][k], dr10[n], acc);
+            }
+        }
+        dp[idx] = acc;
+    }
 }
 
 bool g_tables_ready[64] = {};
@@ -309,7 +452,7 @@ int se_cal_si_snr(const float* separated, const float* source, const int32_t* le
     cudaStream_t st = (cudaStream_t)stream;
     float* per = nullptr;
     SE_CUDA_OK(cudaMallocAsync(&per, sizeof(float) * B, st));
-    si_snr_kernel<<<B, kThreads, 0, st>>>(separated, source, length_dev, L, 1e-8f, per);
+    si_snr_kernel<<<B, kThreads, 0, st>>>(separated, source, length_dev, L, 1e-8f, per, nullptr, 0.f);
     mean_kernel<<<1, 1, 0, st>>>(per, B, 1.0f, out);
     SE_CUDA_OK(cudaGetLastError());
     SE_CUDA_OK(cudaFreeAsync(per, st));
@@ -341,6 +484,111 @@ int se_stoi_loss(const float* y_true, const float* y_pred, const int32_t* lens_d
     mean_kernel<<<1, 1, 0, st>>>(D, B, -1.0f, out);  // reduction="mean": -D.mean()
     SE_CUDA_OK(cudaGetLastError());
     SE_CUDA_OK(cudaFreeAsync(base, st));
+    return 0;
+}
+
+int se_loss_terms_grad(const float* source, const float* pred, const int32_t* lens_dev, int B, int64_t L, float* out2,
+                       float* d_stoi, float* d_sisnr, void* stream) {
+    SE_REQUIRE(source && pred && lens_dev && out2 && d_stoi && d_sisnr, "se_loss_terms_grad: null buffer");
+    SE_REQUIRE(B > 0 && L > 0, "se_loss_terms_grad: empty batch");
+    if (upload_tables()) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    SE_CUDA_OK(cudaMemsetAsync(d_stoi, 0, sizeof(float) * (size_t)B * L, st));
+    SE_CUDA_OK(cudaMemsetAsync(d_sisnr, 0, sizeof(float) * (size_t)B * L, st));
+    StoiWork w{};
+    w.L10max = (5 * L + 7) / 8 + 8;
+    w.NFmax = (int)(w.L10max / 128) + 2;
+    w.Lsmax = 128LL * (w.NFmax + 2);
+    w.NSmax = (int)(w.Lsmax / 128) + 2;
+    w.NBmax = 257;
+    float* base = nullptr;
+    const size_t n_r10 = (size_t)B * 2 * w.L10max, n_sil = (size_t)B * 2 * w.Lsmax, n_en = (size_t)B * w.NFmax,
+                 n_oct = (size_t)B * 2 * 15 * w.NSmax, n_spec = (size_t)B * w.NSmax * w.NBmax * 2,
+                 n_doct = (size_t)B * 15 * w.NSmax, n_dsil = (size_t)B * w.Lsmax, n_dr10 = (size_t)B * w.L10max;
+    SE_CUDA_OK(cudaMallocAsync(&base,
+                               sizeof(float) * (n_r10 + n_sil + n_en + n_oct + n_spec + n_doct + n_dsil + n_dr10 + 2 * B) +
+                                   sizeof(int) * 2 * n_en,
+                               st));
+    w.r10 = base;
+    w.sil = w.r10 + n_r10;
+    w.energy = w.sil + n_sil;
+    w.oct = w.energy + n_en;
+    w.spec = w.oct + n_oct;
+    w.doct = w.spec + n_spec;
+    w.dsil = w.doct + n_doct;
+    w.dr10 = w.dsil + n_dsil;
+    float* D = w.dr10 + n_dr10;
+    float* per = D + B;
+    w.sel = reinterpret_cast<int*>(per + B);
+    w.rank = w.sel + n_en;
+    w.dpred = d_stoi;
+    w.gscale = -1.0f / B;
+    stoi_kernel<<<B, kThreads, 0, st>>>(source, pred, lens_dev, L, w, D);
+    mean_kernel<<<1, 1, 0, st>>>(D, B, -1.0f, out2);
+    si_snr_kernel<<<B, kThreads, 0, st>>>(pred, source, lens_dev, L, 1e-8f, per, d_sisnr, 1.0f / B);
+    mean_kernel<<<1, 1, 0, st>>>(per, B, 1.0f, out2 + 1);
+    SE_CUDA_OK(cudaGetLastError());
+    SE_CUDA_OK(cudaFreeAsync(base, st));
+    return 0;
+}
+
+static __global__ void axpby_kernel(const float* a, const float* x, const float* b, const float* y, float* out, long long n) {
+    const float fa = *a, fb = *b;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = fa * x[i] + fb * y[i];
+}
+static __global__ void __launch_bounds__(512) sqnorm_kernel(const float* g, long long n, double* acc) {
+    __shared__ double red[16];
+    double s = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        s += (double)g[i] * g[i];
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+// torch.nn.utils.clip_grad_norm_ (coef = max_norm / (norm + 1e-6), clamped to 1) + torch.optim.Adam (no weight decay)
+static __global__ void clip_adam_kernel(float* theta, float* grad, float* m, float* v, long long n, float lr, float b1, float b2,
+                                 float eps, float bc1, float bc2, float max_norm, float gscale, const double* sq,
+                                 float* norm_out) {
+    const float norm = (float)sqrt(*sq) * gscale;
+    float coef = gscale;
+    if (max_norm > 0.f) coef *= fminf(1.f, max_norm / (norm + 1e-6f));
+    if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float g = grad[i] * coef;
+        grad[i] = g;
+        const float mi = b1 * m[i] + (1.f - b1) * g;
+        const float vi = b2 * v[i] + (1.f - b2) * g * g;
+        m[i] = mi;
+        v[i] = vi;
+        theta[i] -= lr / bc1 * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+    }
+}
+
+int se_axpby_dev(const float* a, const float* x, const float* b, const float* y, float* out, int64_t n, void* stream) {
+    SE_REQUIRE(a && x && b && y && out, "se_axpby_dev: null buffer");
+    if (n <= 0) return 0;
+    long long g = (n + 255) / 256;
+    axpby_kernel<<<(int)(g > 1184 ? 1184 : g), 256, 0, (cudaStream_t)stream>>>(a, x, b, y, out, n);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int se_clip_adam_step(float* theta, float* grad, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                      float eps, int step, float max_norm, float grad_scale, float* norm_out, void* stream) {
+    SE_REQUIRE(theta && grad && m && v, "se_clip_adam_step: null buffer");
+    SE_REQUIRE(n > 0 && step >= 1, "se_clip_adam_step: bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sq = nullptr;
+    SE_CUDA_OK(cudaMallocAsync(&sq, sizeof(double), st));
+    SE_CUDA_OK(cudaMemsetAsync(sq, 0, sizeof(double), st));
+    long long g = (n + 511) / 512;
+    sqnorm_kernel<<<(int)(g > 592 ? 592 : g), 512, 0, st>>>(grad, n, sq);
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    g = (n + 255) / 256;
+    clip_adam_kernel<<<(int)(g > 1184 ? 1184 : g), 256, 0, st>>>(theta, grad, m, v, n, lr, beta1, beta2, eps, bc1, bc2, max_norm,
+                                                                 grad_scale, sq, norm_out);
+    SE_CUDA_OK(cudaGetLastError());
+    SE_CUDA_OK(cudaFreeAsync(sq, st));
     return 0;
 }
 

@@ -187,6 +187,9 @@ struct StftParams {
     float* noisy;  // mic-0 spectrum [B][T][F][2]
     // optional full spectrum in the reference layout [R][M][F][T][2] (se_stft_trans); feat/noisy may be null
     float* spec_ref;
+    // training layout: stream s = n*nb + i reads utterance i at in_offset + n*hop_chunk (0: every stream is its own row)
+    int nb;
+    long long hop_chunk;
 };
 int launch_stft_features(const StftParams& p, cudaStream_t st);
 // features from a spectrum in the reference layout [B][M][F][T][2] (for TemporalCRN.forward, CRN_ELU.py:369-373)
@@ -214,5 +217,84 @@ int init_fft_tables();  // uploads twiddles / window / envelope to constant memo
 int launch_set_io(IoDesc* dst, const IoDesc& v, cudaStream_t st);
 int launch_segmentation(const float* x, int B, int C, long long L, int K, int gap, int N, float* out, cudaStream_t st);
 int launch_over_add(const float* chunks, int C, int N, int K, int gap, float* out, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------------------------------
+// training step (train.py:195-204): backward kernels (train_kernels.cu).  All fp32 on CUDA cores; gradients of the
+// packed weights are accumulated in a twin of the weight arena and scattered back to the reference layout.
+// ---------------------------------------------------------------------------------------------------------------
+struct StridedRows {  // row m = (b*Tn + t)*Fo + f of a [B][Tn][Fo] grid lives at base + b*sB + t*sT + f*sF
+    long long sB, sT, sF;
+};
+// dW[n][k] += sum_m G(m,n) * A(m,k), dbias[n] += sum_m G(m,n)   (A gathered exactly like the forward GEMM `p`)
+// G(m,n) = G[b*g.sB + t*g.sT + f*g.sF + n], n < N (odd_tail as in the forward).  dW has the packed layout [Npad][K].
+int launch_wgrad(const GemmParams& p, const float* G, StridedRows g, float* dW, float* dbias, cudaStream_t st);
+// dA(m,k) = sum_n G(m,n) * W[n][k], scatter-added at dA + (same offsets as the forward gather); dA is a twin of the
+// forward operand buffer (zero-initialised by the caller; contributions of overlapping taps accumulate)
+int launch_dgrad(const GemmParams& p, const float* G, StridedRows g, float* dA, cudaStream_t st);
+
+struct GlnBwdParams {
+    int B, T, F, C;       // y is compact [B][T][F][C]; statistics count = `count` real elements
+    int student, per_feature, elu;  // elu: y = elu(z) and the result is d loss / d z
+    const float* y;
+    const double* stats;
+    double count;
+    const float* w;       // affine weight [C] (or [F*C] per feature)
+    const float* g;       // d loss / d normalised output, element (b,t,f,c) at g[b*gB + t*gT + f*gF + c]
+    long long gB, gT, gF;
+    float* dw;            // accumulated (atomics), same indexing as w
+    float* db;
+    double* red;          // [B][2] scratch: sum g*w, sum g*w*(y-mean)
+    float* dy;            // element (b,t,f,c) at dy[((b*T+t)*F+f)*oC + c*ostep + ooff]
+    int oC, ostep, ooff;
+};
+int launch_gln_bwd(const GlnBwdParams& p, cudaStream_t st);
+
+struct BlendBwdParams {  // gated skip blend of CRN_ELU.py:297-306, backward
+    int B, T, Fs, Fy, C, student;
+    const float* g;  // d loss / d block output [B][T][Fs][C] strided
+    long long gB, gT, gF;
+    const float *y, *rm, *rr;  // saved: raw deconv+elu [B][T][Fy][C], raw mask conv, elu(residual conv) [B][T][Fs][C]
+    const double *stats, *stats_r;
+    double count, count_r;
+    const float *w, *b, *wr, *br;
+    float* g_o;   // [B][T][Fy][C]  d loss / d GLN(y)
+    float* g_r;   // [B][T][Fs][C]  d loss / d GLN_r(rm)
+    float* G2;    // [B*T*Fs][2C]: column 2c+1 = d loss / d (pre-ELU residual conv); column 2c left for the GLN_r backward
+};
+int launch_blend_bwd(const BlendBwdParams& p, cudaStream_t st);
+// uv [rows][2C] (u_c, v_c interleaved, bias included), dy [rows][C] -> uv := (dy*sig(v), dy*u*sig(v)*(1-sig(v)))
+int launch_gate_bwd(float* uv, const float* dy, long long rows, int C, cudaStream_t st);
+// de [n] *= (e > 0 ? 1 : e + 1)
+int launch_elu_bwd(float* de, const float* e, long long n, cudaStream_t st);
+// dst(b,t,f,c) += src(b,t,f,c) over [B][T][F][C] with independent strides (residual path of the pre-convolutions)
+int launch_add_strided(float* dst, StridedRows d, const float* src, StridedRows s, int B, int T, int F, int C,
+                       cudaStream_t st);
+// GRU cell backward for one step (PyTorch gate order r,z,n): dh = dH + dhrec; writes dgi, dgh (3H each) and dhrec := dh*z
+int launch_gru_bwd_pw(const float* gi, long long giB, const float* gh, long long ghB, const float* hprev, long long hB,
+                      const float* dH, long long dHB, float* dhrec, float* dgi, float* dgh, long long dgB, int B, int H,
+                      cudaStream_t st);
+// generic row copy between two strided slabs: dst[b*dB + i] = src[b*sB + i] (or 0 when src == nullptr), i < count
+int launch_copy_rows(float* dst, long long dB, const float* src, long long sB, int count, int nb, cudaStream_t st);
+
+// chunk-major training layout: stream s = n*b + i is chunk n of utterance i
+// pred[i][j] = (chunk_{q/P-1}[..] + chunk_{q/P}[..]) / 2 at q = j + P + front (utility.py:393-403), j < L
+int launch_over_add_cm(const float* chunks, int nb, int N, int K, int front, long long L, float* pred, cudaStream_t st);
+// adjoint + envelope: dchunk[s][n] = 0.5 * dpred[i][n0*P + n - P - front] / env[n]  (zero outside [0,L))
+int launch_over_add_cm_bwd(const float* dpred, int nb, int N, int K, int front, long long L, float* dchunks,
+                           cudaStream_t st);
+struct MaskBwdParams {
+    int B, student;
+    const float* dspec;   // STFT of dchunk/env, reference layout [B][1][F][T][2]
+    const float* y;       // raw last deconv output [B][T][F][2]
+    const double* stats;
+    double count;
+    const float *w, *b;
+    const float* noisy;   // [B][T][F][2]
+    float* g;             // out: d loss / d GLN(y) [B][T][F][2]
+};
+int launch_mask_bwd(const MaskBwdParams& p, cudaStream_t st);
+// arena <-> flat parameter vector (map[pos] = 1 + flat index, 0 = padding)
+int launch_arena_gather(float* arena, const int* map, const float* theta, long long n, cudaStream_t st);
+int launch_arena_scatter_add(const float* garena, const int* map, float* grad, long long n, cudaStream_t st);
 
 }  // namespace se

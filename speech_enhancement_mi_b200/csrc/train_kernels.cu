@@ -1,0 +1,498 @@
+// Backward kernels of the CRN_ELU training micro-step (train.py:195-198: realtime_process -> compute_loss ->
+// backward).  The reference gets these from PyTorch autograd; here every adjoint is written out:
+//   * dense contractions (causal / transposed convolutions, 1x1 pairs, GRU projections, Linear): weight gradient
+//     dW = G^T . im2col(A) and data gradient dA = col2im(G . W), both driven by the SAME GemmParams (gather table,
+//     strides, packed weights) as the forward GEMM, so no second description of a layer exists;
+//   * GlobalLayerNorm (CRN_ELU.py:37-56), gate (:240), ELU, gated skip blend (:297-306), GRU cell (:173).
+// The carried conv buffers and the GRU state are detached in the reference (CRN_ELU.py:185,243): the gradient of a
+// chunk never leaves the chunk, so the backward runs batched over all chunks of all utterances at once.
+// fp32 on CUDA cores: the training configuration of the reference is one utterance piece per step (config.yaml:92),
+// i.e. a few dozen chunk-streams -- these kernels are sized for that, not for the 1024-stream inference path.
+#include "se_internal.h"
+
+namespace se {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ long long row_off(int m, int rows_per_stream, int Fo, long long sB, long long sT,
+                                             long long sF, int* f_out = nullptr) {
+    const int b = m / rows_per_stream;
+    const int r = m - b * rows_per_stream;
+    const int t = r / Fo;
+    const int f = r - t * Fo;
+    if (f_out) *f_out = f;
+    return b * sB + t * sT + f * sF;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// weight gradient: 64 (n) x 64 (k) tile per CTA, reduction over a slice of the rows, atomics into the arena twin
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WG_BM = 16;
+__global__ void __launch_bounds__(kThreads) wgrad_kernel(GemmParams p, const float* __restrict__ G, StridedRows g,
+                                                         float* __restrict__ dW, float* __restrict__ dbias,
+                                                         int rows_per_cta) {
+    __shared__ __align__(16) float Gs[WG_BM][64 + 4];
+    __shared__ __align__(16) float As[WG_BM][64 + 4];
+    const int tid = threadIdx.x;
+    const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int m_begin = blockIdx.z * rows_per_cta;
+    const int m_end = min(p.M, m_begin + rows_per_cta);
+    const int tx = tid & 15, ty = tid >> 4;
+    const int rps = p.Tn * p.Fo;
+    const float* A = reinterpret_cast<const float*>(p.A);
+    float acc[4][4] = {};
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int m0 = m_begin; m0 < m_end; m0 += WG_BM) {
+        {  // G tile: 16 rows x 64 columns, 4 elements per thread (one row, 4 consecutive columns)
+            const int r = tid >> 4, c4 = (tid & 15) * 4;
+            const int m = m0 + r;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (m < m_end) {
+                int f;
+                const long long off = row_off(m, rps, p.Fo, g.sB, g.sT, g.sF, &f);
+                const int nlim = (p.odd_tail && f == p.Fo - 1) ? p.N / 2 : p.N;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n0 + c4 + j < nlim) v[j] = G[off + n0 + c4 + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Gs[r][c4 + j] = v[j];
+        }
+        {  // A tile: 16 rows x 64 k, one gathered float4 per thread
+            const int r = tid >> 4, ku = tid & 15;
+            const int m = m0 + r, k = k0 + 4 * ku;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < m_end && k < p.K)
+                v = *reinterpret_cast<const float4*>(A + row_off(m, rps, p.Fo, p.sB, p.sT, p.sF) + __ldg(p.koff + (k >> 2)));
+            *reinterpret_cast<float4*>(&As[r][4 * ku]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < WG_BM; ++r) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[r][tx * 4]);
+            const float4 gg = *reinterpret_cast<const float4*>(&Gs[r][ty * 4]);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const float gv[4] = {gg.x, gg.y, gg.z, gg.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                bsum[i] += gv[i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], av[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int n = n0 + ty * 4 + i;
+        if (n >= p.N) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = k0 + tx * 4 + j;
+            if (k < p.K && acc[i][j] != 0.f) atomicAdd(dW + (long long)n * p.K + k, acc[i][j]);
+        }
+        if (dbias != nullptr && blockIdx.x == 0 && tx == 0 && bsum[i] != 0.f) atomicAdd(dbias + n, bsum[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// data gradient: 64 (rows) x 64 (k) tile per CTA, reduction over the N columns, scatter-add through the gather table
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) dgrad_kernel(GemmParams p, const float* __restrict__ G, StridedRows g,
+                                                         float* __restrict__ dA) {
+    __shared__ __align__(16) float Gs[16][64 + 4];  // [n][m]
+    __shared__ __align__(16) float Ws[16][64 + 4];  // [n][k]
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int rps = p.Tn * p.Fo;
+    const float* W = reinterpret_cast<const float*>(p.W);
+    // this thread loads G for row (tid >> 2), columns 4*(tid & 3) .. +3 of every 16-column step
+    const int lr = tid >> 2, lc = (tid & 3) * 4;
+    long long goff = -1;
+    int nlim_l = 0;
+    if (m0 + lr < p.M) {
+        int f;
+        goff = row_off(m0 + lr, rps, p.Fo, g.sB, g.sT, g.sF, &f);
+        nlim_l = (p.odd_tail && f == p.Fo - 1) ? p.N / 2 : p.N;
+    }
+    float acc[4][4] = {};
+    for (int n0 = 0; n0 < p.N; n0 += 16) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + lc + j;
+            Gs[lc + j][lr] = (goff >= 0 && n < nlim_l) ? G[goff + n] : 0.f;
+        }
+        {
+            const int n = n0 + (tid >> 4), k = k0 + 4 * (tid & 15);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < p.N && k < p.K) v = *reinterpret_cast<const float4*>(W + (long long)n * p.K + k);
+            *reinterpret_cast<float4*>(&Ws[tid >> 4][4 * (tid & 15)]) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int n = 0; n < 16; ++n) {
+            const float4 gg = *reinterpret_cast<const float4*>(&Gs[n][ty * 4]);
+            const float4 w = *reinterpret_cast<const float4*>(&Ws[n][tx * 4]);
+            const float gv[4] = {gg.x, gg.y, gg.z, gg.w};
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(gv[i], wv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    const int k = k0 + tx * 4;
+    if (k >= p.K) return;
+    const int ko = __ldg(p.koff + (k >> 2));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= p.M) continue;
+        float* dst = dA + row_off(m, rps, p.Fo, p.sB, p.sT, p.sF) + ko;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (acc[i][j] != 0.f) atomicAdd(dst + j, acc[i][j]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GlobalLayerNorm backward.  out = (y - mu) / D * w + b,  D = sqrt(var + eps) + eps (teacher) | sqrt(var) + eps (student)
+//   g = dout * w;  dy = (g - mean(g)) / D - (y - mu) * sum(g (y - mu)) / (N D^2 s),  s = dD/dvar^-1 / 2 = sqrt(var [+ eps])
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void gln_consts(const double* stats, int b, double count, int student, float& mean,
+                                           float& inv, float& s) {
+    const double mu = stats[2 * b] / count;
+    double var = stats[2 * b + 1] / count - mu * mu;
+    if (var < 0.0) var = 0.0;
+    const float varf = (float)var;
+    s = student ? sqrtf(varf) : sqrtf(varf + 1e-8f);
+    inv = 1.0f / (s + 1e-8f);
+    mean = (float)mu;
+}
+
+__global__ void __launch_bounds__(kThreads) gln_bwd_reduce_kernel(GlnBwdParams p) {
+    __shared__ float sdw[kThreads], sdb[kThreads];
+    __shared__ double red[2][kThreads / 32];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int Ce = p.per_feature ? p.F * p.C : p.C;  // period of the affine index
+    const int npos = p.per_feature ? p.T : p.T * p.F;
+    const int lanes = Ce < kThreads ? Ce : kThreads;
+    const int groups = kThreads / lanes;
+    const int lane = tid % lanes, group = tid / lanes;
+    float mean, inv, s;
+    gln_consts(p.stats, b, p.count, p.student, mean, inv, s);
+    if (tid < lanes) {
+        sdw[tid] = 0.f;
+        sdb[tid] = 0.f;
+    }
+    __syncthreads();
+    double sg = 0.0, sgy = 0.0;
+    if (group < groups) {
+        for (int k = lane; k < Ce; k += lanes) {
+            const float w = p.w[k];
+            const int fk = p.per_feature ? k / p.C : 0, ck = p.per_feature ? k - fk * p.C : k;
+            float dwk = 0.f, dbk = 0.f;
+            for (int pos = group; pos < npos; pos += groups) {
+                int t, f;
+                if (p.per_feature) {
+                    t = pos;
+                    f = fk;
+                } else {
+                    t = pos / p.F;
+                    f = pos - t * p.F;
+                }
+                const float go = p.g[b * p.gB + t * p.gT + f * p.gF + ck];
+                const float yc = p.y[((long long)b * npos + pos) * Ce + k] - mean;
+                dwk = fmaf(go, yc * inv, dwk);
+                dbk += go;
+                const float gw = go * w;
+                sg += gw;
+                sgy += (double)gw * yc;
+            }
+            if (Ce <= kThreads) {
+                atomicAdd(&sdw[lane], dwk);
+                atomicAdd(&sdb[lane], dbk);
+            } else {
+                atomicAdd(p.dw + k, dwk);
+                atomicAdd(p.db + k, dbk);
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        sg += __shfl_xor_sync(0xffffffffu, sg, off);
+        sgy += __shfl_xor_sync(0xffffffffu, sgy, off);
+    }
+    if ((tid & 31) == 0) {
+        red[0][tid >> 5] = sg;
+        red[1][tid >> 5] = sgy;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0, c = 0;
+        for (int w = 0; w < kThreads / 32; ++w) {
+            a += red[0][w];
+            c += red[1][w];
+        }
+        p.red[2 * b] = a;
+        p.red[2 * b + 1] = c;
+    }
+    if (Ce <= kThreads && tid < lanes) {
+        atomicAdd(p.dw + tid, sdw[tid]);
+        atomicAdd(p.db + tid, sdb[tid]);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) gln_bwd_apply_kernel(GlnBwdParams p) {
+    const int b = blockIdx.y;
+    const int Ce = p.per_feature ? p.F * p.C : p.C;
+    const int n = p.T * p.F * p.C;
+    float mean, inv, s;
+    gln_consts(p.stats, b, p.count, p.student, mean, inv, s);
+    const float mg = (float)(p.red[2 * b] / p.count);
+    const float coef = (s > 0.f) ? (float)(p.red[2 * b + 1] / p.count) * inv * inv / s : 0.f;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        const int c = e % p.C;
+        const int pf = e / p.C;  // t*F + f
+        const int t = pf / p.F, f = pf - t * p.F;
+        const int k = p.per_feature ? f * p.C + c : c;
+        (void)Ce;
+        const float y = p.y[(long long)b * n + e];
+        const float gw = p.g[b * p.gB + t * p.gT + f * p.gF + c] * p.w[k];
+        float d = (gw - mg) * inv - (y - mean) * coef;
+        if (p.elu) d *= (y > 0.f ? 1.f : y + 1.f);
+        p.dy[((long long)b * p.T * p.F + pf) * p.oC + c * p.ostep + p.ooff] = d;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gated skip blend backward (CRN_ELU.py:297-306): out = m * rr + (1 - m) * o,  m = sigmoid(GLN_r(rm)), o = GLN(y)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) blend_bwd_kernel(BlendBwdParams p) {
+    const int Fm = p.Fs > p.Fy ? p.Fs : p.Fy;
+    const long long per = (long long)p.T * Fm * p.C;
+    const long long total = per * p.B;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per);
+        long long r = i - b * per;
+        const int c = (int)(r % p.C);
+        r /= p.C;
+        const int f = (int)(r % Fm), t = (int)(r / Fm);
+        float mean, inv, s, mr, ir, sr;
+        gln_consts(p.stats, b, p.count, p.student, mean, inv, s);
+        gln_consts(p.stats_r, b, p.count_r, p.student, mr, ir, sr);
+        float go = 0.f, m = 0.f;
+        if (f < p.Fs) {
+            go = p.g[b * p.gB + t * p.gT + f * p.gF + c];
+            const long long ri = (((long long)b * p.T + t) * p.Fs + f) * p.C + c;
+            m = sigmoidf_((p.rm[ri] - mr) * ir * p.wr[c] + p.br[c]);
+            const float rr = p.rr[ri];
+            float o = 0.f;
+            if (f < p.Fy) o = (p.y[(((long long)b * p.T + t) * p.Fy + f) * p.C + c] - mean) * inv * p.w[c] + p.b[c];
+            p.g_r[ri] = go * (rr - o) * m * (1.f - m);
+            p.G2[ri * 2 + 1] = go * m * (rr > 0.f ? 1.f : rr + 1.f);
+        }
+        if (f < p.Fy) p.g_o[(((long long)b * p.T + t) * p.Fy + f) * p.C + c] = go * (1.f - m);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) gate_bwd_kernel(float* __restrict__ uv, const float* __restrict__ dy,
+                                                            long long n) {  // n = rows * C
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float u = uv[2 * i], v = uv[2 * i + 1], d = dy[i];
+        const float sg = sigmoidf_(v);
+        uv[2 * i] = d * sg;
+        uv[2 * i + 1] = d * u * sg * (1.f - sg);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) elu_bwd_kernel(float* __restrict__ de, const float* __restrict__ e,
+                                                           long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = e[i];
+        de[i] *= (v > 0.f ? 1.f : v + 1.f);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) add_strided_kernel(float* dst, StridedRows d, const float* src,
+                                                               StridedRows s, int B, int T, int F, int C) {
+    const long long total = (long long)B * T * F * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long r = i / C;
+        const int f = (int)(r % F);
+        r /= F;
+        const int t = (int)(r % T), b = (int)(r / T);
+        dst[b * d.sB + t * d.sT + f * d.sF + c] += src[b * s.sB + t * s.sT + f * s.sF + c];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) gru_bwd_pw_kernel(const float* __restrict__ gi, long long giB,
+                                                              const float* __restrict__ gh, long long ghB,
+                                                              const float* __restrict__ hprev, long long hB,
+                                                              const float* __restrict__ dH, long long dHB,
+                                                              float* __restrict__ dhrec, float* __restrict__ dgi,
+                                                              float* __restrict__ dgh, long long dgB, int B, int H) {
+    const long long total = (long long)B * H;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % H), b = (int)(i / H);
+        const float* a = gi + b * giB;
+        const float* h = gh + b * ghB;
+        const float r = sigmoidf_(a[j] + h[j]);
+        const float z = sigmoidf_(a[H + j] + h[H + j]);
+        const float hn = h[2 * H + j];
+        const float n = tanhf(a[2 * H + j] + r * hn);
+        const float hp = hprev[b * hB + j];
+        const float dh = dH[b * dHB + j] + dhrec[(long long)b * H + j];
+        const float dan = dh * (1.f - z) * (1.f - n * n);
+        const float daz = dh * (hp - n) * z * (1.f - z);
+        const float dar = dan * hn * r * (1.f - r);
+        float* o = dgi + b * dgB;
+        float* q = dgh + b * dgB;
+        o[j] = dar;
+        o[H + j] = daz;
+        o[2 * H + j] = dan;
+        q[j] = dar;
+        q[H + j] = daz;
+        q[2 * H + j] = dan * r;
+        dhrec[(long long)b * H + j] = dh * z;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) copy_rows_kernel(float* dst, long long dB, const float* src, long long sB,
+                                                             int count) {
+    const int b = blockIdx.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        dst[b * dB + i] = src ? src[b * sB + i] : 0.f;
+}
+
+__global__ void __launch_bounds__(kThreads) arena_gather_kernel(float* arena, const int* map, const float* theta,
+                                                                long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int s = map[i];
+        arena[i] = s > 0 ? theta[s - 1] : 0.f;
+    }
+}
+__global__ void __launch_bounds__(kThreads) arena_scatter_add_kernel(const float* garena, const int* map, float* grad,
+                                                                     long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int s = map[i];
+        const float v = garena[i];
+        if (s > 0 && v != 0.f) atomicAdd(grad + (s - 1), v);
+    }
+}
+
+inline int grid_for(long long n) {
+    long long g = (n + kThreads - 1) / kThreads;
+    const long long cap = 148LL * 8;
+    return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int launch_wgrad(const GemmParams& p, const float* G, StridedRows g, float* dW, float* dbias, cudaStream_t st) {
+    if (p.M <= 0) return 0;
+    SE_REQUIRE(!p.a_half, "wgrad: fp32 operands only");
+    const int kt = (p.K + 63) / 64, nt = (p.N + 63) / 64;
+    int splits = (148 * 4 + kt * nt - 1) / (kt * nt);
+    const int max_splits = (p.M + 4 * WG_BM - 1) / (4 * WG_BM);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    int rows = (p.M + splits - 1) / splits;
+    rows = (rows + WG_BM - 1) / WG_BM * WG_BM;
+    splits = (p.M + rows - 1) / rows;
+    wgrad_kernel<<<dim3(kt, nt, splits), kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_dgrad(const GemmParams& p, const float* G, StridedRows g, float* dA, cudaStream_t st) {
+    if (p.M <= 0) return 0;
+    SE_REQUIRE(!p.a_half, "dgrad: fp32 operands only");
+    dgrad_kernel<<<dim3((p.M + 63) / 64, (p.K + 63) / 64), kThreads, 0, st>>>(p, G, g, dA);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_gln_bwd(const GlnBwdParams& p, cudaStream_t st) {
+    if (p.B <= 0) return 0;
+    const int Ce = p.per_feature ? p.F * p.C : p.C;
+    (void)Ce;
+    gln_bwd_reduce_kernel<<<p.B, kThreads, 0, st>>>(p);
+    const int n = p.T * p.F * p.C;
+    int gx = (n + kThreads * 4 - 1) / (kThreads * 4);
+    gln_bwd_apply_kernel<<<dim3(gx < 1 ? 1 : gx, p.B), kThreads, 0, st>>>(p);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_blend_bwd(const BlendBwdParams& p, cudaStream_t st) {
+    if (p.B <= 0) return 0;
+    const int Fm = p.Fs > p.Fy ? p.Fs : p.Fy;
+    blend_bwd_kernel<<<grid_for((long long)p.B * p.T * Fm * p.C), kThreads, 0, st>>>(p);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_gate_bwd(float* uv, const float* dy, long long rows, int C, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    gate_bwd_kernel<<<grid_for(rows * C), kThreads, 0, st>>>(uv, dy, rows * C);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_elu_bwd(float* de, const float* e, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    elu_bwd_kernel<<<grid_for(n), kThreads, 0, st>>>(de, e, n);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_add_strided(float* dst, StridedRows d, const float* src, StridedRows s, int B, int T, int F, int C,
+                       cudaStream_t st) {
+    if (B <= 0) return 0;
+    add_strided_kernel<<<grid_for((long long)B * T * F * C), kThreads, 0, st>>>(dst, d, src, s, B, T, F, C);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_gru_bwd_pw(const float* gi, long long giB, const float* gh, long long ghB, const float* hprev, long long hB,
+                      const float* dH, long long dHB, float* dhrec, float* dgi, float* dgh, long long dgB, int B, int H,
+                      cudaStream_t st) {
+    if (B <= 0) return 0;
+    gru_bwd_pw_kernel<<<grid_for((long long)B * H), kThreads, 0, st>>>(gi, giB, gh, ghB, hprev, hB, dH, dHB, dhrec, dgi,
+                                                                      dgh, dgB, B, H);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_copy_rows(float* dst, long long dB, const float* src, long long sB, int count, int nb, cudaStream_t st) {
+    if (nb <= 0 || count <= 0) return 0;
+    SE_REQUIRE(nb <= 65535, "copy_rows: at most 65535 rows per launch");
+    int gx = (count + kThreads - 1) / kThreads;
+    if (gx > 64) gx = 64;
+    copy_rows_kernel<<<dim3(gx, nb), kThreads, 0, st>>>(dst, dB, src, sB, count);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_arena_gather(float* arena, const int* map, const float* theta, long long n, cudaStream_t st) {
+    arena_gather_kernel<<<grid_for(n), kThreads, 0, st>>>(arena, map, theta, n);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int launch_arena_scatter_add(const float* garena, const int* map, float* grad, long long n, cudaStream_t st) {
+    arena_scatter_add_kernel<<<grid_for(n), kThreads, 0, st>>>(garena, map, grad, n);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace se

@@ -1,0 +1,128 @@
+"""GPU parity of the training micro-step (train.py:195-204) through the drop-in API: realtime_process under autograd
+(se_crn_train_forward / se_crn_train_backward), compute_loss with its native backward (se_loss_terms_grad), and the
+native clip + Adam step (se_clip_adam_step), against fixtures produced by the UNMODIFIED reference
+(tests/golden/train_grads.npz, oracle/make_golden.py train) and against the oracle's autograd.
+
+Stated tolerances (fp32 arithmetic, sums re-associated by tiling / atomics): pred 2e-4 of the peak, loss terms 2e-3,
+d loss / d pred 1e-2 of its peak, every parameter gradient 2e-2 of that tensor's peak (tf32 mode: 0.1 and cosine
+similarity >= 0.99 over all parameters)."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from common import GOLDEN, SMALL, TEACHER, make_model, rel_err
+from oracle import crn_oracle, synth
+from test_loss_oracle_golden import CASES, pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _step(model, mix, src, lens, flag):
+    model.zero_grad()
+    pred = model.realtime_process(torch.from_numpy(mix).cuda(), flag)
+    pred.retain_grad()
+    with contextlib.redirect_stdout(io.StringIO()):
+        loss, mae, sisnr = model.compute_loss(torch.from_numpy(src).cuda(), pred, torch.tensor(lens))
+    loss.backward()
+    grads = {k: p.grad.detach().cpu().numpy() for k, p in model.named_parameters() if p.grad is not None}
+    return (pred.detach().cpu().numpy(), pred.grad.cpu().numpy(),
+            np.array([float(loss), float(mae), float(sisnr)]), grads)
+
+
+def _report(grads, g, prefix, tol):
+    bad = []
+    for k in [k[len(prefix):] for k in g.files if k.startswith(prefix)]:
+        e = rel_err(grads[k], g[prefix + k])
+        if not e < tol:
+            bad.append((k, e))
+    assert not bad, "parameter gradients off: " + ", ".join(f"{k}: {e:.3g}" for k, e in bad)
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_loss_gradient_matches_oracle_autograd(tag):
+    from speech_enhancement_mi_b200.CRN_ELU import _LossTermsFn
+    g = np.load(os.path.join(GOLDEN, "losses.npz"))
+    source, pred = pair(tag)
+    lens = torch.from_numpy(g[f"{tag}_lens"])
+    p_ref = pred.clone().requires_grad_(True)
+    loss_ref, mae_ref, sis_ref = crn_oracle.compute_loss(source, p_ref, lens)
+    loss_ref.backward()
+    p = pred.clone().cuda().requires_grad_(True)
+    mae, sis = _LossTermsFn.apply(source.cuda(), p, lens)
+    loss = 0.7 * mae + 0.3 * (-sis)
+    loss.backward()
+    assert abs(float(mae) - float(mae_ref)) < 2e-4 and abs(float(-sis) - float(sis_ref)) < 2e-3
+    assert rel_err(p.grad.cpu().numpy(), p_ref.grad.numpy()) < 1e-2
+
+
+def test_small_train_step_matches_reference():
+    g = np.load(os.path.join(GOLDEN, "train_grads.npz"))
+    model = make_model("crn_small", precision="fp32").cuda().train()
+    mix, src = synth.make_mixture(2, 8000)
+    pred, dpred, losses, grads = _step(model, mix, src, [8000, 6500], False)
+    assert rel_err(pred, g["small_pred"]) < 2e-4
+    assert np.allclose(losses, g["small_loss"], atol=2e-3)
+    assert rel_err(dpred, g["small_dpred"]) < 1e-2
+    _report(grads, g, "small_grad/", 2e-2)
+    # flag=True: the next piece continues with the carried conv buffers / GRU state (CRN_ELU.py:474-481)
+    mix2, src2 = synth.make_mixture(2, 4800, first_stream=100)
+    pred, dpred, losses, grads = _step(model, mix2, src2, [4800, 4800], True)
+    assert rel_err(pred, g["small_cont_pred"]) < 2e-4
+    assert np.allclose(losses, g["small_cont_loss"], atol=2e-3)
+    _report(grads, g, "small_cont_grad/", 2e-2)
+
+
+def test_teacher_train_step_matches_reference():
+    g = np.load(os.path.join(GOLDEN, "train_grads.npz"))
+    model = make_model("crn_teacher", precision="fp32").cuda().train()
+    mix, src = synth.make_mixture(1, 6400)
+    pred, dpred, losses, grads = _step(model, mix, src, [6400], False)
+    assert rel_err(pred, g["teacher_pred"]) < 2e-4
+    assert np.allclose(losses, g["teacher_loss"], atol=2e-3)
+    assert rel_err(dpred, g["teacher_dpred"]) < 1e-2
+    bad = []
+    for k in [k[len("teacher_gnorm/"):] for k in g.files if k.startswith("teacher_gnorm/")]:
+        gn = float(g["teacher_gnorm/" + k])
+        if abs(float(np.linalg.norm(grads[k].astype(np.float64))) - gn) > 2e-2 * gn + 1e-9:
+            bad.append((k, "norm"))
+        head = g["teacher_ghead/" + k]
+        if np.abs(grads[k].reshape(-1)[:64] - head).max() > 2e-2 * (np.abs(grads[k]).max() + 1e-30):
+            bad.append((k, "head"))
+    assert not bad, bad
+
+
+def test_tf32_training_gradients_close():
+    g = np.load(os.path.join(GOLDEN, "train_grads.npz"))
+    model = make_model("crn_small", precision="tf32").cuda().train()
+    mix, src = synth.make_mixture(2, 8000)
+    pred, dpred, losses, grads = _step(model, mix, src, [8000, 6500], False)
+    assert rel_err(pred, g["small_pred"]) < 2e-2
+    a = np.concatenate([grads[k[len("small_grad/"):]].reshape(-1) for k in g.files if k.startswith("small_grad/")])
+    b = np.concatenate([g[k].reshape(-1) for k in g.files if k.startswith("small_grad/")])
+    assert float(a @ b / (np.linalg.norm(a) * np.linalg.norm(b))) > 0.99
+
+
+def test_native_clip_adam_matches_torch():
+    """se_clip_adam_step against clip_grad_norm_(5) + torch.optim.Adam(3e-4) (train.py:200-204; config.yaml:10,99-100)."""
+    import ctypes as C
+    from speech_enhancement_mi_b200._native import check, lib
+    torch.manual_seed(0)
+    n = 100003
+    theta0, grads = torch.randn(n), [torch.randn(n) * s for s in (0.001, 3.0, 0.05)]
+    p = theta0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p], lr=3e-4, betas=(0.9, 0.999))
+    theta, m, v = theta0.clone().cuda(), torch.zeros(n).cuda(), torch.zeros(n).cuda()
+    norm = torch.zeros(1).cuda()
+    for step, gr in enumerate(grads, 1):
+        p.grad = gr.clone()
+        ref_norm = torch.nn.utils.clip_grad_norm_([p], 5.0)
+        opt.step()
+        gd = gr.clone().cuda()
+        check(lib().se_clip_adam_step(theta.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, 3e-4, 0.9, 0.999, 1e-8,
+                                      step, 5.0, 1.0, norm.data_ptr(), None), "se_clip_adam_step")
+        assert abs(float(norm) - float(ref_norm)) < 1e-4 * float(ref_norm)
+        assert (theta.cpu() - p.detach()).abs().max() < 1e-6
