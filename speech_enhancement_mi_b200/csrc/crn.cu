@@ -50,7 +50,7 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
     long long per_stream() const { return sB; }
 };
 
-enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV };
+enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ };
 enum Stage { ST_STFT = 0, ST_PRECONV, ST_ENCODER, ST_GRU, ST_DECODER, ST_MASK, ST_ROLL, ST_COUNT };
 const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"};
 
@@ -853,7 +853,7 @@ int build_ctx(se_ctx* c) {
         if (dev_alloc(c, &c->gh_all, (size_t)T * 3 * H * maxB)) return 1;
         if (dev_alloc(c, &c->dgi, (size_t)T * 3 * H * maxB)) return 1;
         if (dev_alloc(c, &c->dgh, (size_t)T * 3 * H * maxB)) return 1;
-        if (dev_alloc(c, &c->dhrec, (size_t)H * maxB)) return 1;
+        if (dev_alloc(c, &c->dhrec, (size_t)2 * H * maxB)) return 1;
         if (dev_alloc(c, &c->dxg, (size_t)T * c->feat * maxB)) return 1;
         c->twins.push_back({c->dxg, (size_t)T * c->feat * maxB * sizeof(float)});
         for (int l = 0; l < 2; ++l) {
@@ -1051,7 +1051,24 @@ int build_ctx(se_ctx* c) {
             b.meta("gru.l" + s + ".step" + std::to_string(t), 2.0 * 3 * H * H, 4.0 * (3 * H + 2 * H));
             b.push_gemm(ST_GRU, gp, 1, pw, k_off);
         }
-        for (int t = 0; t < T && !fused; ++t) {
+        const bool seq = c->train && gru_seq_supported(H);
+        if (seq) {  // training: the whole recurrence of the layer is one persistent kernel (gru_seq.cu)
+            GemmParams gp{};  // describes W_hh for the backward's batched recompute / weight gradient
+            gp.A = c->hseq[l];
+            gp.sB = (long long)(T + 1) * H;
+            gp.Tn = 1;
+            gp.Fo = 1;
+            fill_gemm_common(c, gp, pw, 3 * H, k_off);
+            gp.epi = EPI_BIAS;
+            gp.out = c->gh;
+            gp.oB = 3 * H;
+            b.meta("gru.l" + s + ".recurrence", 2.0 * T * 3 * H * H, 4.0 * T * (3 * H + 2 * H));
+            b.push_gemm(ST_GRU, gp, 1, pw, k_off);
+            c->ops.back().kind = OP_GRU_SEQ;
+            c->ops.back().gru_layer = l;
+            c->gru_rec.op_hh[l] = (int)c->ops.size() - 1;
+        }
+        for (int t = 0; t < T && !fused && !seq; ++t) {
             GemmParams gp{};
             gp.A = c->hseq[l] + (long long)t * H;
             gp.sB = (long long)(T + 1) * H;
@@ -1191,7 +1208,7 @@ int build_ctx(se_ctx* c) {
     for (size_t i = 0; i < c->ops.size(); ++i) {
         Op& op = c->ops[i];
         const OpFix& f = b.fix[i];
-        if (op.kind == OP_GEMM) {
+        if (op.kind == OP_GEMM || op.kind == OP_GRU_SEQ) {
             op.g.W = (c->half && op.g.a_half) ? static_cast<const void*>(reinterpret_cast<const unsigned short*>(c->warena_h) + f.w_off)
                                               : static_cast<const void*>(c->warena + f.w_off);
             op.g.bias = c->warena + f.b_off;
@@ -1255,7 +1272,20 @@ int build_ctx(se_ctx* c) {
     return 0;
 }
 
+int run_gemm_impl(const se_ctx* c, const GemmParams& g, int stage, const std::string& label, cudaStream_t st);
+// SE_B200_SYNC=1 (debug): synchronise after every GEMM launch and report the op that faulted
 int run_gemm(const se_ctx* c, const GemmParams& g, int stage, const std::string& label, cudaStream_t st) {
+    static const bool sync = getenv("SE_B200_SYNC") != nullptr;
+    if (run_gemm_impl(c, g, stage, label, st)) return 1;
+    if (sync) {
+        const cudaError_t e = cudaStreamSynchronize(st);
+        SE_REQUIRE(e == cudaSuccess, "GEMM '" + label + "' (M=" + std::to_string(g.M) + " N=" + std::to_string(g.N) +
+                                         " K=" + std::to_string(g.K) + " epi=" + std::to_string(g.epi) +
+                                         ") failed: " + cudaGetErrorString(e));
+    }
+    return 0;
+}
+int run_gemm_impl(const se_ctx* c, const GemmParams& g, int stage, const std::string& label, cudaStream_t st) {
     if (g.epi == EPI_GRU || g.epi == EPI_ELU_GATE) return launch_gemm_tf32(g, st);
     if (c->tf32 && (c->half || ((c->tc_mask >> stage) & 1u)) && gemm_tf32_supported(g)) return launch_gemm_tf32(g, st);
     SE_REQUIRE(!c->half, "internal: fp16 operands need the tensor-core GEMM (" + label + ")");
@@ -1278,11 +1308,7 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
                 g.b0 = s0;
                 return run_gemm(c, g, op.stage, op.label, st);
             }
-            if (g.epi == EPI_GRU || g.epi == EPI_ELU_GATE) return launch_gemm_tf32(g, st);
-            if (c->tf32 && (c->half || ((c->tc_mask >> op.stage) & 1u)) && gemm_tf32_supported(g))
-                return launch_gemm_tf32(g, st);
-            SE_REQUIRE(!c->half, "internal: fp16 operands need the tensor-core GEMM (" + op.label + ")");
-            return launch_gemm_fp32(g, st);
+            return run_gemm(c, g, op.stage, op.label, st);
         }
         case OP_NORM: {
             NormApplyParams n = op.n;
@@ -1295,6 +1321,8 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
             pc.B = B;
             return launch_preconv(pc, st);
         }
+        case OP_GRU_SEQ:
+            SE_REQUIRE(false, "internal: the persistent GRU op only runs inside the training forward");
         case OP_GRU_PW:
             return launch_gru_pointwise(op.gi + (long long)s0 * op.giB, op.giB, op.gh + (long long)s0 * 3 * op.H,
                                         op.hprev + (long long)s0 * op.hB, op.hB, op.hout + (long long)s0 * op.hB, B, op.H,
@@ -1465,6 +1493,23 @@ int train_forward(se_ctx* c, const float* mixture, int nb, long long L, int flag
                     if (launch_op(c, c->ops[k], nb, st, n * nb)) return 1;
             }
             i = j;
+            continue;
+        }
+        if (op.kind == OP_GRU_SEQ) {
+            GruSeqParams gp{};
+            gp.Whh = reinterpret_cast<const float*>(op.g.W);
+            gp.Kp = op.g.K;
+            gp.bhh = op.g.bias;
+            gp.gi = c->gi_l[op.gru_layer];
+            gp.giB = (long long)T * 3 * c->H;
+            gp.hseq = c->hseq[op.gru_layer];
+            gp.hB = (long long)(T + 1) * c->H;
+            gp.H = c->H;
+            gp.T = T;
+            gp.nb = nb;
+            gp.N = N;
+            if (launch_gru_seq_fwd(gp, st)) return 1;
+            ++i;
             continue;
         }
         if (op.state_entry >= 0 && N > 1 && shift_state(op.state_entry)) return 1;
@@ -1654,6 +1699,24 @@ int train_backward(se_ctx* c, const float* dpred, float* grad_flat, cudaStream_t
             gh.oT = 3 * H;
             gh.vec4 = 1;
             if (run_gemm(c, gh, ST_GRU, "gru.bwd.hh", st)) return 1;
+            if (gru_seq_supported(H)) {
+                GruSeqBwdParams bp{};
+                bp.Whh = reinterpret_cast<const float*>(hop.g.W);
+                bp.Kp = hop.g.K;
+                bp.gi = c->gi_l[l];
+                bp.gh = c->gh_all;
+                bp.gB = (long long)T * 3 * H;
+                bp.hseq = c->hseq[l];
+                bp.dH = c->dH[l];
+                bp.hB = (long long)(T + 1) * H;
+                bp.dgi = c->dgi;
+                bp.dgh = c->dgh;
+                bp.dhrec = c->dhrec;
+                bp.H = H;
+                bp.T = T;
+                bp.B = Bp;
+                if (launch_gru_seq_bwd(bp, st)) return 1;
+            }
             SE_CUDA_OK(cudaMemsetAsync(c->dhrec, 0, (size_t)Bp * H * sizeof(float), st));
             GemmParams rec = hop.g;  // dhrec[b][:] += dgh_t . W_hh
             rec.A = c->dhrec;
@@ -1662,7 +1725,7 @@ int train_backward(se_ctx* c, const float* dpred, float* grad_flat, cudaStream_t
             rec.sF = 0;
             rec.Tn = 1;
             rec.M = Bp;
-            for (int t = T - 1; t >= 0; --t) {
+            for (int t = T - 1; t >= 0 && !gru_seq_supported(H); --t) {
                 if (launch_gru_bwd_pw(c->gi_l[l] + (long long)t * 3 * H, (long long)T * 3 * H,
                                       c->gh_all + (long long)t * 3 * H, (long long)T * 3 * H,
                                       c->hseq[l] + (long long)t * H, (long long)(T + 1) * H,

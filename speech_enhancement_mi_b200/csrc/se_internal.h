@@ -273,6 +273,32 @@ int launch_add_strided(float* dst, StridedRows d, const float* src, StridedRows 
 int launch_gru_bwd_pw(const float* gi, long long giB, const float* gh, long long ghB, const float* hprev, long long hB,
                       const float* dH, long long dHB, float* dhrec, float* dgi, float* dgh, long long dgB, int B, int H,
                       cudaStream_t st);
+// persistent small-batch GRU recurrence (gru_seq.cu): one cooperative launch per layer for all chunks and steps
+struct GruSeqParams {
+    const float* Whh;  // packed [3H][Kp], rows r | z | n (PyTorch order), b_hh separately
+    int Kp;
+    const float* bhh;
+    const float* gi;   // input projections incl. b_ih: gi[s*giB + t*3H + n]
+    long long giB;
+    float* hseq;       // hseq[s*hB + t*H + j], t in [0, T]: slot 0 = state entering the chunk
+    long long hB;
+    int H, T, nb, N;   // streams s = n*nb + i (chunk n of utterance i); chunk n starts from the last state of chunk n-1
+};
+struct GruSeqBwdParams {
+    const float* Whh;
+    int Kp;
+    const float *gi, *gh;  // [B][T][3H] input / recurrent projections (biases included)
+    long long gB;
+    const float* hseq;     // [B][T+1][H]
+    const float* dH;       // [B][T+1][H] d loss / d h_t from the layer above (slot t+1 for step t)
+    long long hB;
+    float *dgi, *dgh;      // out [B][T][3H]
+    float* dhrec;          // scratch [2][B][H]
+    int H, T, B;
+};
+bool gru_seq_supported(int H);
+int launch_gru_seq_fwd(const GruSeqParams& p, cudaStream_t st);
+int launch_gru_seq_bwd(const GruSeqBwdParams& p, cudaStream_t st);
 // generic row copy between two strided slabs: dst[b*dB + i] = src[b*sB + i] (or 0 when src == nullptr), i < count
 int launch_copy_rows(float* dst, long long dB, const float* src, long long sB, int count, int nb, cudaStream_t st);
 
