@@ -56,6 +56,7 @@ class NativeTrainer:
         self.device = int(device if device is not None else model._pick_device(None))
         self.micro = 0
         self.step_count = 0
+        self.phase_events = None  # set to [] to collect (name, start, end) CUDA events of the micro-step phases
         if max_chunk_streams:
             model._max_streams = max(model._max_streams, int(max_chunk_streams))
         with torch.cuda.device(self.device):
@@ -83,6 +84,15 @@ class NativeTrainer:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def _mark(self, name=None, start=None):
+        if self.phase_events is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        if name is not None:
+            self.phase_events.append((name, start, e))
+        return e
+
     def _rebind(self):
         check(lib().se_crn_bind_weights_flat(self.ctx, self.theta.data_ptr(), self._stream()), "se_crn_bind_weights_flat")
         self.model._tbound_versions = tuple((t.data_ptr(), t._version) for t in self.model._train_params())
@@ -99,14 +109,18 @@ class NativeTrainer:
             st = self._stream()
             dev = self.theta.device
             pred = torch.empty((B, L), dtype=torch.float32, device=dev)
+            mark = self._mark
+            t0 = mark()
             check(lib().se_crn_train_forward(self.ctx, mixture.data_ptr(), B, L, int(bool(flag)), pred.data_ptr(), st),
                   "se_crn_train_forward")
+            t1 = mark("forward", t0)
             out2 = torch.empty(2, dtype=torch.float32, device=dev)
             d_stoi = torch.empty((B, L), dtype=torch.float32, device=dev)
             d_sisnr = torch.empty((B, L), dtype=torch.float32, device=dev)
             lens = torch.as_tensor(length).to(device=dev, dtype=torch.int32)
             check(lib().se_loss_terms_grad(source.data_ptr(), pred.data_ptr(), lens.data_ptr(), B, L, out2.data_ptr(),
                                            d_stoi.data_ptr(), d_sisnr.data_ptr(), st), "se_loss_terms_grad")
+            t2 = mark("loss+grad", t1)
             if check_nan and bool(torch.isnan(out2).any()):  # CRN_ELU.py:531-534: NaN loss => zero-filled, no gradient
                 self.micro += 1
                 return torch.zeros_like(out2)
@@ -116,6 +130,7 @@ class NativeTrainer:
                   "se_crn_train_backward")
             check(lib().se_axpby_dev(self.one.data_ptr(), self.grad.data_ptr(), self.one.data_ptr(), self.gtmp.data_ptr(),
                                      self.grad.data_ptr(), self.grad.numel(), st), "se_axpby_dev")
+            mark("backward", t2)
         self.micro += 1
         self.last_pred = pred
         return out2

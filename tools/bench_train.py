@@ -74,6 +74,15 @@ for it in range(args.warmup + args.steps):
 e1 = torch.cuda.Event(enable_timing=True)
 e1.record()
 barrier()
+tr.phase_events = []  # one more (untimed) step with per-phase events
+for _ in range(2):
+    tr.micro_step(mix, src, lens, False, check_nan=False)
+tr.optimizer_step()
+torch.cuda.synchronize()
+phases = {}
+for name, a, b in tr.phase_events:
+    phases[name] = phases.get(name, 0.0) + a.elapsed_time(b)
+tr.phase_events = None
 ms = e0.elapsed_time(e1) / args.steps
 t = torch.tensor([ms], device="cuda")
 if world > 1:
@@ -84,7 +93,7 @@ if rank == 0:
         "metric": "CRN_ELU training: optimizer steps/s (2 micro-steps of forward+loss+backward, all-reduce, clip, Adam)",
         "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world, "ms_per_step": ms,
         "trained_audio_s_per_s": world * 2 * B * args.seconds / (ms * 1e-3),
-        "ms_micro_steps": t_micro / args.steps, "ms_allreduce_clip_adam_rebind": t_opt / args.steps,
+        "ms_micro_steps": t_micro / args.steps, "ms_phases_per_step": phases, "ms_allreduce_clip_adam_rebind": t_opt / args.steps,
         "config": {"model": args.model, "batch_per_rank": B, "piece_seconds": args.seconds, "precision": args.precision,
                    "gradient_accumulation": 2, "params": int(tr.theta.numel())},
         "loss_first": losses[0], "loss_last": losses[-1], "scaling": "weak", "data": "synthetic"}))
