@@ -56,6 +56,7 @@ class NativeTrainer:
         self.device = int(device if device is not None else model._pick_device(None))
         self.micro = 0
         self.step_count = 0
+        self._graphs = {}
         self.phase_events = None  # set to [] to collect (name, start, end) CUDA events of the micro-step phases
         if max_chunk_streams:
             model._max_streams = max(model._max_streams, int(max_chunk_streams))
@@ -97,40 +98,93 @@ class NativeTrainer:
         check(lib().se_crn_bind_weights_flat(self.ctx, self.theta.data_ptr(), self._stream()), "se_crn_bind_weights_flat")
         self.model._tbound_versions = tuple((t.data_ptr(), t._version) for t in self.model._train_params())
 
-    def micro_step(self, mixture, source, length, flag=False, check_nan=True):
-        """One forward + backward; gradients accumulate.  Returns a device tensor [stoi_loss, sisnr_db]."""
+    def _launch_micro(self, mixture, source, lens, B, L, flag, pred, out2, d_stoi, d_sisnr):
+        """The native calls of one micro-step, all on the current stream (capturable into a CUDA graph)."""
+        st = self._stream()
+        mark = self._mark
+        t0 = mark()
+        check(lib().se_crn_train_forward(self.ctx, mixture.data_ptr(), B, L, int(bool(flag)), pred.data_ptr(), st),
+              "se_crn_train_forward")
+        t1 = mark("forward", t0)
+        check(lib().se_loss_terms_grad(source.data_ptr(), pred.data_ptr(), lens.data_ptr(), B, L, out2.data_ptr(),
+                                       d_stoi.data_ptr(), d_sisnr.data_ptr(), st), "se_loss_terms_grad")
+        t2 = mark("loss+grad", t1)
+        check(lib().se_axpby_dev(self.w_stoi.data_ptr(), d_stoi.data_ptr(), self.w_sisnr.data_ptr(), d_sisnr.data_ptr(),
+                                 d_stoi.data_ptr(), d_stoi.numel(), st), "se_axpby_dev")
+        check(lib().se_crn_train_backward(self.ctx, d_stoi.data_ptr(), self.gtmp.data_ptr(), st), "se_crn_train_backward")
+        check(lib().se_axpby_dev(self.one.data_ptr(), self.grad.data_ptr(), self.one.data_ptr(), self.gtmp.data_ptr(),
+                                 self.grad.data_ptr(), self.grad.numel(), st), "se_axpby_dev")
+        mark("backward", t2)
+
+    def micro_step(self, mixture, source, length, flag=False, check_nan=True, graph=False):
+        """One forward + backward; gradients accumulate.  Returns a device tensor [stoi_loss, sisnr_db].
+
+        ``graph=True`` replays the micro-step as ONE CUDA graph (captured on first use per (B, L, flag); inputs are
+        staged into fixed device buffers).  A NaN loss is then not filtered (check_nan needs the eager path)."""
         B, _, L = mixture.shape
         with torch.cuda.device(self.device):
             _, n_chunks = _native.chunk_grid(L + (0 if flag else self.model.segment_length // 2), self.model.segment_length)
-            ctx = self.model._ensure_train_ctx(B * n_chunks, self.device, keep_state=bool(flag))
-            if ctx is not self.ctx and ctx.value != self.ctx.value:  # context re-created with a larger capacity
+            if B * n_chunks > self.model._tctx_capacity:
+                ctx = self.model._ensure_train_ctx(B * n_chunks, self.device, keep_state=bool(flag))
                 self.ctx = ctx
+                self._graphs.clear()
                 self._rebind()
-            st = self._stream()
             dev = self.theta.device
+            lens = torch.as_tensor(length)
+            if lens.device != dev or lens.dtype != torch.int32:
+                lens = lens.to(device=dev, dtype=torch.int32)
+            if graph:
+                key = (B, L, bool(flag))
+                g = self._graphs.get(key)
+                if g is None:
+                    bufs = dict(mix=torch.empty_like(mixture), src=torch.empty_like(source), lens=torch.empty_like(lens),
+                                pred=torch.empty((B, L), dtype=torch.float32, device=dev),
+                                out2=torch.empty(2, dtype=torch.float32, device=dev),
+                                d_stoi=torch.empty((B, L), dtype=torch.float32, device=dev),
+                                d_sisnr=torch.empty((B, L), dtype=torch.float32, device=dev))
+                    for k, v in (("mix", mixture), ("src", source), ("lens", lens)):
+                        bufs[k].copy_(v)
+                    if not flag:  # eager warm-up (one-time lazy setup inside the library); flag=False resets the state
+                        saved = self.grad.clone()
+                        self._launch_micro(bufs["mix"], bufs["src"], bufs["lens"], B, L, flag, bufs["pred"], bufs["out2"],
+                                           bufs["d_stoi"], bufs["d_sisnr"])
+                        self.grad.copy_(saved)
+                    torch.cuda.synchronize()
+                    cg = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(cg):
+                        self._launch_micro(bufs["mix"], bufs["src"], bufs["lens"], B, L, flag, bufs["pred"], bufs["out2"],
+                                           bufs["d_stoi"], bufs["d_sisnr"])
+                    g = self._graphs[key] = (cg, bufs)
+                cg, bufs = g
+                bufs["mix"].copy_(mixture, non_blocking=True)
+                bufs["src"].copy_(source, non_blocking=True)
+                bufs["lens"].copy_(lens, non_blocking=True)
+                cg.replay()
+                self.micro += 1
+                self.last_pred = bufs["pred"]
+                return bufs["out2"]
             pred = torch.empty((B, L), dtype=torch.float32, device=dev)
-            mark = self._mark
-            t0 = mark()
-            check(lib().se_crn_train_forward(self.ctx, mixture.data_ptr(), B, L, int(bool(flag)), pred.data_ptr(), st),
-                  "se_crn_train_forward")
-            t1 = mark("forward", t0)
             out2 = torch.empty(2, dtype=torch.float32, device=dev)
             d_stoi = torch.empty((B, L), dtype=torch.float32, device=dev)
             d_sisnr = torch.empty((B, L), dtype=torch.float32, device=dev)
-            lens = torch.as_tensor(length).to(device=dev, dtype=torch.int32)
-            check(lib().se_loss_terms_grad(source.data_ptr(), pred.data_ptr(), lens.data_ptr(), B, L, out2.data_ptr(),
-                                           d_stoi.data_ptr(), d_sisnr.data_ptr(), st), "se_loss_terms_grad")
-            t2 = mark("loss+grad", t1)
-            if check_nan and bool(torch.isnan(out2).any()):  # CRN_ELU.py:531-534: NaN loss => zero-filled, no gradient
+            if check_nan:  # CRN_ELU.py:531-534: a NaN loss is zero-filled and contributes no gradient
+                st = self._stream()
+                check(lib().se_crn_train_forward(self.ctx, mixture.data_ptr(), B, L, int(bool(flag)), pred.data_ptr(), st),
+                      "se_crn_train_forward")
+                check(lib().se_loss_terms_grad(source.data_ptr(), pred.data_ptr(), lens.data_ptr(), B, L, out2.data_ptr(),
+                                               d_stoi.data_ptr(), d_sisnr.data_ptr(), st), "se_loss_terms_grad")
                 self.micro += 1
-                return torch.zeros_like(out2)
-            check(lib().se_axpby_dev(self.w_stoi.data_ptr(), d_stoi.data_ptr(), self.w_sisnr.data_ptr(), d_sisnr.data_ptr(),
-                                     d_stoi.data_ptr(), d_stoi.numel(), st), "se_axpby_dev")
-            check(lib().se_crn_train_backward(self.ctx, d_stoi.data_ptr(), self.gtmp.data_ptr(), st),
-                  "se_crn_train_backward")
-            check(lib().se_axpby_dev(self.one.data_ptr(), self.grad.data_ptr(), self.one.data_ptr(), self.gtmp.data_ptr(),
-                                     self.grad.data_ptr(), self.grad.numel(), st), "se_axpby_dev")
-            mark("backward", t2)
+                self.last_pred = pred
+                if bool(torch.isnan(out2).any()):
+                    return torch.zeros_like(out2)
+                check(lib().se_axpby_dev(self.w_stoi.data_ptr(), d_stoi.data_ptr(), self.w_sisnr.data_ptr(),
+                                         d_sisnr.data_ptr(), d_stoi.data_ptr(), d_stoi.numel(), st), "se_axpby_dev")
+                check(lib().se_crn_train_backward(self.ctx, d_stoi.data_ptr(), self.gtmp.data_ptr(), st),
+                      "se_crn_train_backward")
+                check(lib().se_axpby_dev(self.one.data_ptr(), self.grad.data_ptr(), self.one.data_ptr(),
+                                         self.gtmp.data_ptr(), self.grad.data_ptr(), self.grad.numel(), st), "se_axpby_dev")
+                return out2
+            self._launch_micro(mixture, source, lens, B, L, flag, pred, out2, d_stoi, d_sisnr)
         self.micro += 1
         self.last_pred = pred
         return out2

@@ -29,6 +29,7 @@ ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--warmup", type=int, default=3)
 ap.add_argument("--precision", default="tf32")
 ap.add_argument("--model", default="teacher")
+ap.add_argument("--graph", action="store_true", help="replay each micro-step as one CUDA graph")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -43,7 +44,7 @@ B, L = args.batch, int(args.seconds * 16000)
 tr = NativeTrainer(model, device=local, gradient_accumulation=2)
 mix, src = synth.make_mixture(B, L, first_stream=rank * B)
 mix, src = torch.from_numpy(mix).cuda(), torch.from_numpy(src).cuda()
-lens = torch.full((B,), L, dtype=torch.int32)
+lens = torch.full((B,), L, dtype=torch.int32, device="cuda")
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
 t_micro = t_opt = 0.0
 losses = []
@@ -62,7 +63,7 @@ for it in range(args.warmup + args.steps):
         e0.record()
     ev[0].record()
     for _ in range(2):
-        out = tr.micro_step(mix, src, lens, False, check_nan=False)
+        out = tr.micro_step(mix, src, lens, False, check_nan=False, graph=args.graph)
     ev[1].record()
     tr.optimizer_step()
     ev[2].record()
@@ -95,7 +96,7 @@ if rank == 0:
         "trained_audio_s_per_s": world * 2 * B * args.seconds / (ms * 1e-3),
         "ms_micro_steps": t_micro / args.steps, "ms_phases_per_step": phases, "ms_allreduce_clip_adam_rebind": t_opt / args.steps,
         "config": {"model": args.model, "batch_per_rank": B, "piece_seconds": args.seconds, "precision": args.precision,
-                   "gradient_accumulation": 2, "params": int(tr.theta.numel())},
+                   "gradient_accumulation": 2, "cuda_graph": bool(args.graph), "params": int(tr.theta.numel())},
         "loss_first": losses[0], "loss_last": losses[-1], "scaling": "weak", "data": "synthetic"}))
 if world > 1:
     dist.destroy_process_group()
