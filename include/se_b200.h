@@ -124,6 +124,9 @@ typedef struct se_fsn_config {
     int32_t sb_num_neighbors; /* 15                                    */
     int32_t fb_num_neighbors; /* 0                                     */
     int32_t max_streams;      /* capacity of the per-stream LSTM state */
+    int32_t precision;        /* SE_PRECISION_TF32, or SE_PRECISION_FP16: sub-band LSTM operands (98.7 % of the
+                                 FLOPs) stored as fp16 -- the reference itself runs this model under fp16 autocast
+                                 on CUDA (fullsubnet.py:943) */
 } se_fsn_config;
 typedef struct se_fsn se_fsn;
 

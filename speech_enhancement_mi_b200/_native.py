@@ -40,7 +40,7 @@ class SeCrnConfig(C.Structure):
 
 class SeFsnConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ("num_freqs", "num_mics", "fb_hidden", "sb_hidden", "num_layers",
-                                         "sb_num_neighbors", "fb_num_neighbors", "max_streams")]
+                                         "sb_num_neighbors", "fb_num_neighbors", "max_streams", "precision")]
 
 
 _P = C.c_void_p

@@ -11,6 +11,7 @@
 //   [ x: T x Kin_pad | h(layer 0): (T+1) x H | h(layer 1): (T+1) x H ]      slot 0 of an h history = carried state
 // The reflect-padded neighbour gather is expanded once per chunk into the x part of the sub-band records (540 KB per
 // stream and chunk, against 15.4 GFLOP of LSTM work per stream and chunk).
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <string.h>
 
@@ -65,6 +66,13 @@ struct se_fsn {
     int* cstep = nullptr;        // [B][2]
     float* warena = nullptr;
     size_t warena_floats = 0;
+    // SE_PRECISION_FP16: the sub-band records (x_t and the h histories, 98.7 % of the FLOPs read them) and the sub-band
+    // weights are stored as fp16 (tcgen05 kind::f16, fp32 accumulate; cell state c and all statistics stay fp32)
+    bool half = false;
+    int sesz = 4;   // element size of the sub-band records
+    int Ksp = 0;    // sub-band input size padded to whole k-blocks (32 floats / 64 halves)
+    void* warena_h = nullptr;
+    std::vector<int> g_half;  // per gemm: operands are fp16
     int* karena = nullptr;
     std::vector<int> khost;
     std::vector<std::function<void(const HostParams&, float*)>> packers;
@@ -201,7 +209,7 @@ __global__ void __launch_bounds__(256) fsn_scale_fb_kernel(float* rec, long long
 // grid (T, B), one thread per (f, k)
 __global__ void __launch_bounds__(256) fsn_unfold_kernel(const float* pline, int Pp, const float* fbout, int Fp, int F,
                                                          int W, const float* cstate, float* sbrec, long long recS,
-                                                         int Ks) {
+                                                         int Ks, int Ksp, int half) {
     const int t = blockIdx.x, b = blockIdx.y;
     const float inv = cstate[4 * b + 3];
     const float* P = pline + ((long long)b * T + t) * Pp;
@@ -211,16 +219,19 @@ __global__ void __launch_bounds__(256) fsn_unfold_kernel(const float* pline, int
         float v = 0.f;
         if (k < W) v = P[f + k];
         else if (k == W) v = fo[f];
-        sbrec[((long long)b * F + f) * recS + (long long)t * Ks + k] = v * inv;
+        const long long o = ((long long)b * F + f) * recS + (long long)t * Ksp + k;
+        if (half) reinterpret_cast<__half*>(sbrec)[o] = __float2half_rn(v * inv);
+        else sbrec[o] = v * inv;
     }
 }
 
 // carried state: h history slot T -> slot 0 for both layers.  grid (rows, ceil(H/256))
-__global__ void fsn_roll_kernel(float* rec, long long recB, long long h0, long long h1, int H) {
+template <typename E>
+__global__ void fsn_roll_kernel(E* rec, long long recB, long long h0, long long h1, int H) {
     const long long r = blockIdx.x;
     const int j = blockIdx.y * blockDim.x + threadIdx.x;
     if (j >= H) return;
-    float* base = rec + r * recB;
+    E* base = rec + r * recB;
     base[h0 + j] = base[h0 + (long long)T * H + j];
     base[h1 + j] = base[h1 + (long long)T * H + j];
 }
@@ -307,7 +318,10 @@ void register_params(se_fsn* c) {
 
 // one LSTM layer: T step GEMMs.  rec/recB: record buffer; xoff(t), hoff(t): offsets of x_t / h_{t-1} inside a record
 void build_lstm(se_fsn* c, const std::string& prefix, int layer, int Kin, int Kin_pad, int H, float* rec,
-                long long recB, std::function<long long(int)> xoff, long long hhist, float* cbuf, int rows_per_stream) {
+                long long recB, std::function<long long(int)> xoff, long long hhist, float* cbuf, int rows_per_stream,
+                bool half = false) {
+    const int U = half ? 8 : 4;    // elements per 16-byte gather unit
+    const int esz = half ? 2 : 4;
     const int K = Kin_pad + H;
     const int N = 4 * H;
     const size_t w_off = c->reserve_w((size_t)N * K), b_off = c->reserve_w(N);
@@ -327,10 +341,12 @@ void build_lstm(se_fsn* c, const std::string& prefix, int layer, int Kin, int Ki
         }
     });
     for (int t = 0; t < T; ++t) {
-        std::vector<int> koff(K / 4);
-        for (int u = 0; u < Kin_pad / 4; ++u) koff[u] = (int)(xoff(t) + 4 * u);
-        for (int u = 0; u < H / 4; ++u) koff[Kin_pad / 4 + u] = (int)(hhist + (long long)t * H + 4 * u);
+        std::vector<int> koff(K / U);
+        for (int u = 0; u < Kin_pad / U; ++u) koff[u] = (int)(xoff(t) + U * u);
+        for (int u = 0; u < H / U; ++u) koff[Kin_pad / U + u] = (int)(hhist + (long long)t * H + U * u);
         GemmParams g{};
+        g.a_half = half ? 1 : 0;
+        g.out_half = half ? 1 : 0;
         g.A = rec;
         g.sB = recB;
         g.Tn = 1;
@@ -339,7 +355,7 @@ void build_lstm(se_fsn* c, const std::string& prefix, int layer, int Kin, int Ki
         g.N = N;
         g.Npad = N;
         g.epi = EPI_LSTM;
-        g.out = rec + hhist + (long long)(t + 1) * H;  // h_t
+        g.out = reinterpret_cast<float*>(reinterpret_cast<char*>(rec) + (hhist + (long long)(t + 1) * H) * esz);  // h_t
         g.oB = recB;
         g.hprev = cbuf;  // c_{t-1}, updated in place
         g.hB = H;
@@ -351,11 +367,14 @@ void build_lstm(se_fsn* c, const std::string& prefix, int layer, int Kin, int Ki
         c->g_b.push_back(b_off);
         c->g_k.push_back(c->reserve_k(koff));
         c->g_rows.push_back(rows_per_stream);
+        c->g_half.push_back(half ? 1 : 0);
     }
 }
 
 void build_fc(se_fsn* c, const std::string& prefix, int H, int N, float* rec, long long recB, long long h1hist, int epi,
-              float* out, long long oB, long long oT, int vec4, double* stats, int rows_per_stream_T) {
+              float* out, long long oB, long long oT, int vec4, double* stats, int rows_per_stream_T, bool half = false) {
+    const int U = half ? 8 : 4;
+    const int esz = half ? 2 : 4;
     const int Npad = round_up(N, gemm_tf32_tile_n(N));
     const size_t w_off = c->reserve_w((size_t)Npad * H), b_off = c->reserve_w(Npad);
     c->packers.push_back([=](const HostParams& hp, float* arena) {
@@ -366,10 +385,11 @@ void build_fc(se_fsn* c, const std::string& prefix, int H, int N, float* rec, lo
             arena[b_off + n] = b[n];
         }
     });
-    std::vector<int> koff(H / 4);
-    for (int u = 0; u < H / 4; ++u) koff[u] = 4 * u;
+    std::vector<int> koff(H / U);
+    for (int u = 0; u < H / U; ++u) koff[u] = U * u;
     GemmParams g{};
-    g.A = rec + h1hist + H;  // h_1 .. h_T of the top layer
+    g.a_half = half ? 1 : 0;
+    g.A = reinterpret_cast<char*>(rec) + (h1hist + H) * esz;  // h_1 .. h_T of the top layer
     g.sB = recB;
     g.sT = H;
     g.Tn = T;
@@ -388,6 +408,7 @@ void build_fc(se_fsn* c, const std::string& prefix, int H, int N, float* rec, lo
     c->g_b.push_back(b_off);
     c->g_k.push_back(c->reserve_k(koff));
     c->g_rows.push_back(rows_per_stream_T);
+    c->g_half.push_back(half ? 1 : 0);
 }
 
 int build(se_fsn* c) {
@@ -409,19 +430,24 @@ int build(se_fsn* c) {
     c->NB = 2 * g.sb_num_neighbors + 1;
     c->Ks = c->NB + 1;
     c->Kf = round_up(c->F * c->M, 32) ;  // whole k-blocks, so that [x | h] stays k-block aligned
-    const int Ksp = round_up(c->Ks, 32);
-    SE_REQUIRE(Ksp == c->Ks, "FullSubNet: sub-band input size must be a multiple of 32 (31 neighbours + 1)");
+    SE_REQUIRE(g.precision == SE_PRECISION_TF32 || g.precision == SE_PRECISION_FP16,
+               "FullSubNet: precision must be SE_PRECISION_TF32 or SE_PRECISION_FP16");
+    c->half = g.precision == SE_PRECISION_FP16;
+    c->sesz = c->half ? 2 : 4;
+    SE_REQUIRE(round_up(c->Ks, 32) == c->Ks, "FullSubNet: sub-band input size must be a multiple of 32 (31 neighbours + 1)");
+    c->Ksp = round_up(c->Ks, c->half ? 64 : 32);
+    SE_REQUIRE(!c->half || g.sb_hidden % 64 == 0, "FullSubNet fp16: sb_hidden must be a multiple of 64");
     register_params(c);
     const int B = c->maxB, F = c->F, Hf = c->Hf, Hs = c->Hs;
     c->f_h0 = (long long)T * c->Kf;
     c->f_h1 = c->f_h0 + (long long)(T + 1) * Hf;
     c->recF = c->f_h1 + (long long)(T + 1) * Hf;
-    c->s_h0 = (long long)T * c->Ks;
+    c->s_h0 = (long long)T * c->Ksp;
     c->s_h1 = c->s_h0 + (long long)(T + 1) * Hs;
     c->recS = c->s_h1 + (long long)(T + 1) * Hs;
     const int Fp = round_up(F, 4), Pp = round_up(F + 2 * g.sb_num_neighbors, 4);
     if (dev_alloc(c, &c->fbrec, (size_t)c->recF * B)) return 1;
-    if (dev_alloc(c, &c->sbrec, (size_t)c->recS * B * F)) return 1;
+    if (dev_alloc(c, reinterpret_cast<char**>(&c->sbrec), (size_t)c->recS * B * F * c->sesz)) return 1;
     if (dev_alloc(c, &c->fbc, (size_t)2 * B * Hf)) return 1;
     if (dev_alloc(c, &c->sbc, (size_t)2 * B * F * Hs)) return 1;
     if (dev_alloc(c, &c->fbout, (size_t)B * T * Fp)) return 1;
@@ -441,16 +467,20 @@ int build(se_fsn* c) {
     build_lstm(c, "fb_model", 1, Hf, Hf, Hf, c->fbrec, recF, [=](int t) { return fh0 + (long long)(t + 1) * Hf; }, fh1,
                c->fbc + (size_t)B * Hf, 1);
     build_fc(c, "fb_model", Hf, F, c->fbrec, recF, fh1, EPI_RELU_STATS, c->fbout, (long long)T * Fp, Fp, 1, nullptr, T);
-    build_lstm(c, "sb_model", 0, Ks, Ks, Hs, c->sbrec, recS, [=](int t) { return (long long)t * Ks; }, sh0, c->sbc, F);
+    const int Ksp = c->Ksp;
+    build_lstm(c, "sb_model", 0, Ks, Ksp, Hs, c->sbrec, recS, [=](int t) { return (long long)t * Ksp; }, sh0, c->sbc, F,
+               c->half);
     build_lstm(c, "sb_model", 1, Hs, Hs, Hs, c->sbrec, recS, [=](int t) { return sh0 + (long long)(t + 1) * Hs; }, sh1,
-               c->sbc + (size_t)B * F * Hs, F);
-    build_fc(c, "sb_model", Hs, 2, c->sbrec, recS, sh1, EPI_BIAS, c->crm, 2LL * T, 2, 0, nullptr, F * T);
+               c->sbc + (size_t)B * F * Hs, F, c->half);
+    build_fc(c, "sb_model", Hs, 2, c->sbrec, recS, sh1, EPI_BIAS, c->crm, 2LL * T, 2, 0, nullptr, F * T, c->half);
 
     if (dev_alloc(c, &c->warena, c->warena_floats)) return 1;
+    if (c->half && dev_alloc(c, reinterpret_cast<char**>(&c->warena_h), c->warena_floats * 2)) return 1;
     if (dev_alloc(c, &c->karena, c->khost.size())) return 1;
     SE_CUDA_OK(cudaMemcpy(c->karena, c->khost.data(), c->khost.size() * sizeof(int), cudaMemcpyHostToDevice));
     for (size_t i = 0; i < c->gemms.size(); ++i) {
-        c->gemms[i].W = c->warena + c->g_w[i];
+        c->gemms[i].W = c->g_half[i] ? static_cast<const void*>(reinterpret_cast<const __half*>(c->warena_h) + c->g_w[i])
+                                     : static_cast<const void*>(c->warena + c->g_w[i]);
         c->gemms[i].bias = c->warena + c->g_b[i];
         c->gemms[i].koff = c->karena + c->g_k[i];
     }
@@ -485,14 +515,18 @@ int enqueue(se_fsn* c, int B, cudaStream_t st) {
     }
     fsn_cumnorm_kernel<<<(B + 127) / 128, 128, 0, st>>>(c->sums, c->cstate, c->cstep, 1, (double)F * c->Ks * T, B);
     fsn_unfold_kernel<<<dim3(T, B), 256, 0, st>>>(c->pline, Pp, c->fbout, Fp, F, c->NB, c->cstate, c->sbrec, c->recS,
-                                                  c->Ks);
+                                                  c->Ks, c->Ksp, c->half ? 1 : 0);
     for (int i = 0; i < 2 * T; ++i)
         if (run_gemm(c, gi++, B, st)) return 1;
     if (run_gemm(c, gi++, B, st)) return 1;
     const long long total = (long long)B * 2 * F * T;
     fsn_out_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(c->crm, c->out_cell, F, total);
-    fsn_roll_kernel<<<dim3(B, (Hf + 255) / 256), 256, 0, st>>>(c->fbrec, c->recF, c->f_h0, c->f_h1, Hf);
-    fsn_roll_kernel<<<dim3(B * F, (Hs + 255) / 256), 256, 0, st>>>(c->sbrec, c->recS, c->s_h0, c->s_h1, Hs);
+    fsn_roll_kernel<float><<<dim3(B, (Hf + 255) / 256), 256, 0, st>>>(c->fbrec, c->recF, c->f_h0, c->f_h1, Hf);
+    if (c->half)
+        fsn_roll_kernel<__half><<<dim3(B * F, (Hs + 255) / 256), 256, 0, st>>>(reinterpret_cast<__half*>(c->sbrec), c->recS,
+                                                                             c->s_h0, c->s_h1, Hs);
+    else
+        fsn_roll_kernel<float><<<dim3(B * F, (Hs + 255) / 256), 256, 0, st>>>(c->sbrec, c->recS, c->s_h0, c->s_h1, Hs);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -563,6 +597,11 @@ int se_fsn_bind_weights(se_fsn* c, const float* const* ptrs, int n, void* stream
     for (auto& f : c->packers) f(hp, arena.data());
     SE_CUDA_OK(cudaDeviceSynchronize());
     SE_CUDA_OK(cudaMemcpy(c->warena, arena.data(), arena.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (c->half) {  // fp16 copy of the arena (same indexing): the sub-band GEMMs read their weights from it
+        std::vector<__half> ah(arena.size());
+        for (size_t i = 0; i < arena.size(); ++i) ah[i] = __float2half_rn(arena[i]);
+        SE_CUDA_OK(cudaMemcpy(c->warena_h, ah.data(), ah.size() * sizeof(__half), cudaMemcpyHostToDevice));
+    }
     c->weights_bound = true;
     return 0;
 }
@@ -575,7 +614,8 @@ int se_fsn_reset_state(se_fsn* c, int first, int count, void* stream) {
     const size_t F = c->F;
     // zero LSTM states (fullsubnet.py:826-830) and reset both CumLayerNorms (:831-832)
     SE_CUDA_OK(cudaMemsetAsync(c->fbrec + c->recF * first, 0, (size_t)c->recF * count * sizeof(float), st));
-    SE_CUDA_OK(cudaMemsetAsync(c->sbrec + c->recS * first * F, 0, (size_t)c->recS * count * F * sizeof(float), st));
+    SE_CUDA_OK(cudaMemsetAsync(reinterpret_cast<char*>(c->sbrec) + (size_t)c->recS * first * F * c->sesz, 0,
+                               (size_t)c->recS * count * F * c->sesz, st));
     for (int l = 0; l < 2; ++l) {
         SE_CUDA_OK(cudaMemsetAsync(c->fbc + ((size_t)l * c->maxB + first) * c->Hf, 0,
                                    (size_t)count * c->Hf * sizeof(float), st));

@@ -579,7 +579,9 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
                             const float cn = fg * pc[i] + ig * gg;
                             const long long bb = p.b0 + mm;
                             p.out2[bb * p.o2B + ju] = cn;
-                            p.out[bb * p.oB + ju] = og * fast_tanh(cn);
+                            const float hv = og * fast_tanh(cn);
+                            if (p.out_half) reinterpret_cast<__half*>(p.out)[bb * p.oB + ju] = __float2half_rn(hv);
+                            else p.out[bb * p.oB + ju] = hv;
                         }
                     }
                     __syncwarp();

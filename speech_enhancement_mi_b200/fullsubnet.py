@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import utility
+from . import _native
 from ._native import SeFsnConfig, check, lib
 
 EPS = 1e-8
@@ -70,8 +71,14 @@ class FullSubNet(BaseModel):
                  fb_output_activate_function, sb_output_activate_function, fb_model_hidden_size, sb_model_hidden_size,
                  num_mics, norm_type="offline_laplace_norm", num_groups_in_drop_band=2, num_layers=2, weight_init=True,
                  sample_rate=16000, segment_length=400, win_length=20, hop_length=10, n_fft=320, max_streams=None,
-                 device=None):
+                 device=None, precision=None):
         super().__init__()
+        # extra (not in the reference): "tf32" = tcgen05 on fp32 storage; "fp16" = sub-band LSTM operands stored as
+        # fp16 with fp32 accumulation / cell state -- the reference runs this model under fp16 autocast on CUDA
+        # (fullsubnet.py:943)
+        self.precision = precision or os.environ.get("SE_B200_FSN_PRECISION", "tf32")
+        if self.precision not in ("tf32", "fp16"):
+            raise ValueError("precision must be 'tf32' or 'fp16'")
         assert sequence_model in ("GRU", "LSTM"), f"{self.__class__.__name__} only support GRU and LSTM."
         if sequence_model != "LSTM" or fb_output_activate_function != "ReLU" or sb_output_activate_function:
             raise NotImplementedError("the B200 path builds the configuration of config.yaml:153-172 "
@@ -129,7 +136,8 @@ class FullSubNet(BaseModel):
             self._destroy()
         if self._ctx is None:
             cfg = SeFsnConfig(self.num_freqs, self.num_mics, self.fb_model_hidden_size, self.sb_model_hidden_size,
-                              self.num_layers, self.sb_num_neighbors, self.fb_num_neighbors, need)
+                              self.num_layers, self.sb_num_neighbors, self.fb_num_neighbors, need,
+                              _native.SE_PRECISION_FP16 if self.precision == "fp16" else _native.SE_PRECISION_TF32)
             ctx = C.c_void_p()
             check(lib().se_fsn_create(C.byref(ctx), dev, C.byref(cfg)), "se_fsn_create")
             self._ctx, self._ctx_device, self._ctx_capacity, self._fresh = ctx, dev, need, True

@@ -62,6 +62,24 @@ def test_forward_chunk_matches_reference(tag, cfg, seed):
     assert rel_err(f2, g["fwd_chunk1_again"]) < TOL_REL
 
 
+def test_fp16_subband_operands_match_reference():
+    """SE_PRECISION_FP16: sub-band LSTM operands stored as fp16 (the reference's own CUDA path runs under fp16 autocast,
+    fullsubnet.py:943); same stated tolerance as the tf32 mode, on the full-size configuration."""
+    g = load("fsn_full")
+    m = make(FSN_FULL, 5, precision="fp16")
+    x1 = torch.from_numpy(g["x_chunk1"]).cuda()
+    m.reset_state(x1.shape[0])
+    f1 = m.forward(x1).cpu().numpy()
+    f2 = m.forward(x1).cpu().numpy()
+    assert rel_err(f1, g["fwd_chunk1"]) < TOL_REL
+    assert rel_err(f2, g["fwd_chunk1_again"]) < TOL_REL
+    seed, B, L = [int(v) for v in g["meta"]]
+    mix, src = synth.make_mixture(B, L)
+    pred = m.realtime_process(torch.from_numpy(mix).cuda(), None, flag=False, train=False)[0].cpu().numpy()
+    assert np.abs(pred - g["out"]).max() < TOL_REL * max(1.0, np.abs(g["out"]).max())
+    assert si_sdr_db(pred, g["out"]) > TOL_DB
+
+
 def test_realtime_process_matches_reference():
     g = load("fsn_small")
     m = make(FSN_SMALL, 11)

@@ -22,13 +22,14 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--streams", type=int, default=64)
 ap.add_argument("--seconds", type=float, default=3.0)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--precision", default="fp16", choices=["tf32", "fp16"])
 args = ap.parse_args()
 cfg = dict(num_freqs=201, num_mics=3, fb_hidden=512, sb_hidden=384, sb_num_neighbors=15, fb_num_neighbors=0, num_layers=2)
 m = fullsubnet.FullSubNet(num_freqs=201, look_ahead=0, sequence_model="LSTM", fb_num_neighbors=0, sb_num_neighbors=15,
                           fb_output_activate_function="ReLU", sb_output_activate_function=False,
                           fb_model_hidden_size=512, sb_model_hidden_size=384, num_mics=3, num_layers=2, weight_init=False,
                           sample_rate=16000, segment_length=3200, win_length=25, hop_length=10, n_fft=400,
-                          max_streams=args.streams)
+                          max_streams=args.streams, precision=args.precision)
 m.load_state_dict({k: torch.from_numpy(v) for k, v in synth.make_fsn_weights(seed=5, **cfg).items()})
 B, L = args.streams, int(args.seconds * 16000)
 base, _ = synth.make_mixture(min(B, 16), L)
@@ -47,4 +48,4 @@ flops = 15547.6e6 * B * n_chunks
 print(json.dumps({"metric": "enhanced audio-sec/sec (FullSubNet, chunked train=False path)", "value": B * args.seconds / (ms * 1e-3),
                   "unit": "audio-s/s", "streams": B, "utterance_s": args.seconds, "chunks": n_chunks,
                   "ms_per_utterance_batch": ms, "ms_per_chunk_step": ms / n_chunks,
-                  "achieved_tflops": flops / (ms * 1e-3) / 1e12, "dtype": "tf32", "data": "synthetic"}))
+                  "achieved_tflops": flops / (ms * 1e-3) / 1e12, "dtype": args.precision, "data": "synthetic"}))
