@@ -8,10 +8,15 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <cooperative_groups.h>
+
+#include <string>
 #include <vector>
 
 #include "../../include/se_b200.h"
 #include "se_internal.h"
+
+namespace cg = cooperative_groups;
 
 namespace se {
 namespace {
@@ -129,19 +134,35 @@ struct StoiWork {
     float gscale;   // -1 / B
 };
 
+// One cooperative grid of (G, B) CTAs: the G CTAs of an item share its heavy loops (resampler, spectrogram DFTs and
+// their adjoints) and separate the stages with grid barriers; the light serial stages (frame energies, silent-frame
+// selection) are recomputed by every CTA in shared memory.  Items that the reference scores 0.99 (too short) stay in
+// the grid (they must reach every barrier) but do no work.
 __global__ void __launch_bounds__(kThreads) stoi_kernel(const float* y_true, const float* y_pred, const int* lens,
-                                                        long long L, StoiWork w, float* D) {
+                                                        long long L, StoiWork w, float* D, double* dacc) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smraw[];
+    float* s_energy = reinterpret_cast<float*>(smraw);       // [NFmax]
+    int* s_sel = reinterpret_cast<int*>(s_energy + w.NFmax);  // [NFmax]
+    int* s_rank = s_sel + w.NFmax;                            // [NFmax]
+    float* s_v = reinterpret_cast<float*>(s_rank + w.NFmax);  // [256] windowed frame / its gradient
+    float* s_pw = s_v + 256;                                  // [2*257] power per bin, then (2 dP re, 2 dP im)
     __shared__ double red[kThreads / 32];
     __shared__ float redf[kThreads / 32];
     __shared__ float2 tw[512];
     __shared__ int s_ns;
-    const int item = blockIdx.x, tid = threadIdx.x;
+    const int item = blockIdx.y, tid = threadIdx.x, G = gridDim.x, g = blockIdx.x;
+    const long long it0 = (long long)g * blockDim.x + tid, stride = (long long)G * blockDim.x;
     const long long len = min((long long)lens[item], L);
     const float* src[2] = {y_true + (long long)item * L, y_pred + (long long)item * L};
     float* r10[2] = {w.r10 + ((long long)item * 2) * w.L10max, w.r10 + ((long long)item * 2 + 1) * w.L10max};
     float* sil[2] = {w.sil + ((long long)item * 2) * w.Lsmax, w.sil + ((long long)item * 2 + 1) * w.Lsmax};
-    float* energy = w.energy + (long long)item * w.NFmax;
-    int* sel = w.sel + (long long)item * w.NFmax;
+    float* oct[2] = {w.oct + ((long long)item * 2) * 15 * w.NSmax, w.oct + ((long long)item * 2 + 1) * 15 * w.NSmax};
+    const bool want_grad = w.dpred != nullptr;
+    float* doct = want_grad ? w.doct + (long long)item * 15 * w.NSmax : nullptr;
+    float* dsil = want_grad ? w.dsil + (long long)item * w.Lsmax : nullptr;
+    float* dr10 = want_grad ? w.dr10 + (long long)item * w.L10max : nullptr;
+    float* spec = want_grad ? w.spec + (long long)item * w.NSmax * w.NBmax * 2 : nullptr;
     for (int i = tid; i < 512; i += blockDim.x) {
         float sn, cs;
         sincospif(-(float)i / 256.f, &sn, &cs);  // exp(-2 pi i k / 512)
@@ -150,7 +171,7 @@ __global__ void __launch_bounds__(kThreads) stoi_kernel(const float* y_true, con
     // (1) resample: out[5q + j] = sum_k kern[j][k] * wave[8q + k - 10], target length ceil(5 len / 8)
     const long long L10 = (5 * len + 7) / 8;
     for (int sgl = 0; sgl < 2; ++sgl)
-        for (long long n = tid; n < L10; n += blockDim.x) {
+        for (long long n = it0; n < L10; n += stride) {
             const long long q = n / 5;
             const int j = (int)(n - 5 * q);
             float acc = 0.f;
@@ -161,85 +182,103 @@ __global__ void __launch_bounds__(kThreads) stoi_kernel(const float* y_true, con
             }
             r10[sgl][n] = acc;
         }
-    __syncthreads();
+    if (want_grad) {
+        for (long long i = it0; i < 15LL * w.NSmax; i += stride) doct[i] = 0.f;
+        for (long long i = it0; i < w.Lsmax; i += stride) dsil[i] = 0.f;
+    }
+    grid.sync();
     // (2) removeSilentFrames: frames of 256 at hop 128 of the TRUE signal, energy, mask, compaction (order kept)
     const int n1 = (int)(L10 / 256), n2 = L10 >= 128 ? (int)((L10 - 128) / 256) : 0;
     const int NF = n1 + n2;
-    if (NF == 0) {  // torch.max of an empty tensor raises -> the reference falls back to the raw signal, <= 512 samples
-        if (tid == 0) D[item] = 0.99f;
-        return;
-    }
-    float emax = -INFINITY;
-    for (int m = tid; m < NF; m += blockDim.x) {
-        float acc = 0.f;
-        for (int i = 0; i < 256; ++i) {
-            const float v = c_st.hann_sym[i] * r10[0][128 * m + i];
-            acc = fmaf(v, v, acc);
+    bool alive = NF > 0;  // torch.max of an empty tensor raises -> the reference falls back to the raw signal, <= 512 samples
+    int ns = 0;
+    long long Ls = 0;
+    if (alive) {
+        float emax = -INFINITY;
+        for (int m = tid; m < NF; m += blockDim.x) {
+            float acc = 0.f;
+            for (int i = 0; i < 256; ++i) {
+                const float v = c_st.hann_sym[i] * __ldcg(&r10[0][128 * m + i]);
+                acc = fmaf(v, v, acc);
+            }
+            const float e = 20.f * log10f(sqrtf(acc) / 16.0f + (float)kEps64);
+            s_energy[m] = e;
+            s_rank[m] = -1;
+            emax = fmaxf(emax, e);
         }
-        const float e = 20.f * log10f(sqrtf(acc) / 16.0f + (float)kEps64);
-        energy[m] = e;
-        emax = fmaxf(emax, e);
-    }
-    emax = block_max(emax, redf);
-    if (tid == 0) {
-        int ns = 0;
-        for (int m = 0; m < NF; ++m)
-            if (energy[m] - emax + 40.f > 0.f) sel[ns++] = m;
-        s_ns = ns;
-    }
-    __syncthreads();
-    const int ns = s_ns;
-    const long long Ls = 128LL * (ns + 1);
-    if (Ls <= 512) {
-        if (tid == 0) D[item] = 0.99f;
-        return;
-    }
-    for (int sgl = 0; sgl < 2; ++sgl)
-        for (long long n = tid; n < Ls; n += blockDim.x) {
-            const int k = (int)(n / 128), i = (int)(n % 128);
-            float v = 0.f;
-            if (k < ns) v += c_st.hann_sym[i] * r10[sgl][128 * sel[k] + i];                 // first half of frame k
-            if (k >= 1) v += c_st.hann_sym[128 + i] * r10[sgl][128 * sel[k - 1] + 128 + i];  // second half of frame k-1
-            sil[sgl][n] = v;
+        emax = block_max(emax, redf);
+        if (tid == 0) {
+            int k = 0;
+            for (int m = 0; m < NF; ++m)
+                if (s_energy[m] - emax + 40.f > 0.f) {
+                    s_rank[m] = k;
+                    s_sel[k++] = m;
+                }
+            s_ns = k;
         }
-    __syncthreads();
-    // (3) power spectrogram (n_fft 512, hann(256) centred, hop 128, center=True reflect) -> one-third octave bands
-    const int NS = 1 + (int)(Ls / 128);
-    float* oct[2] = {w.oct + ((long long)item * 2) * 15 * w.NSmax, w.oct + ((long long)item * 2 + 1) * 15 * w.NSmax};
-    const int klo = c_st.band_lo[0], khi = c_st.band_hi[14];
-    for (int sgl = 0; sgl < 2; ++sgl) {
-        for (int i = tid; i < 15 * NS; i += blockDim.x) oct[sgl][(i / NS) * w.NSmax + i % NS] = 0.f;
         __syncthreads();
-        const int nb = khi - klo;
-        for (int o = tid; o < NS * nb; o += blockDim.x) {
-            const int r = o / nb, k = klo + o % nb;
-            float re = 0.f, im = 0.f;
-            for (int n = 0; n < 256; ++n) {  // the window is zero outside [128, 384) of the 512-sample frame
-                long long pos = 128LL * r + 128 + n - 256;  // index into the un-padded signal
+        ns = s_ns;
+        Ls = 128LL * (ns + 1);
+        alive = Ls > 512;
+    }
+    if (alive) {
+        for (int sgl = 0; sgl < 2; ++sgl)
+            for (long long n = it0; n < Ls; n += stride) {
+                const int k = (int)(n / 128), i = (int)(n % 128);
+                float v = 0.f;
+                if (k < ns) v += c_st.hann_sym[i] * __ldcg(&r10[sgl][128 * s_sel[k] + i]);                 // first half of frame k
+                if (k >= 1) v += c_st.hann_sym[128 + i] * __ldcg(&r10[sgl][128 * s_sel[k - 1] + 128 + i]);  // second half of frame k-1
+                sil[sgl][n] = v;
+            }
+    }
+    grid.sync();
+    // (3) power spectrogram (n_fft 512, hann(256) centred, hop 128, center=True reflect) -> one-third octave bands;
+    //     one CTA per frame, two threads per bin (each sums half of the 256 window samples)
+    const int NS = alive ? 1 + (int)(Ls / 128) : 0;
+    const int klo = c_st.band_lo[0], khi = c_st.band_hi[14];
+    const int nb = khi - klo;
+    for (int sgl = 0; sgl < 2 && alive; ++sgl) {
+        for (int r = g; r < NS; r += G) {
+            if (tid < 256) {
+                long long pos = 128LL * r + 128 + tid - 256;  // index into the un-padded signal
                 if (pos < 0) pos = -pos;
                 if (pos >= Ls) pos = 2 * (Ls - 1) - pos;
-                const float v = sil[sgl][pos] * c_st.hann_per[n];
-                const float2 t = tw[(k * (n + 128)) & 511];
-                re = fmaf(v, t.x, re);
-                im = fmaf(v, t.y, im);
+                s_v[tid] = __ldcg(&sil[sgl][pos]) * c_st.hann_per[tid];
             }
-            const float pw = re * re + im * im;
-            if (sgl == 1 && w.spec != nullptr) {
-                float* sp = w.spec + (((long long)item * w.NSmax + r) * w.NBmax + (k - klo)) * 2;
-                sp[0] = re;
-                sp[1] = im;
+            __syncthreads();
+            {
+                const int kk = tid >> 1, h = tid & 1;
+                float re = 0.f, im = 0.f;
+                if (kk < nb) {
+                    const int k = klo + kk;
+                    for (int n = 128 * h; n < 128 * h + 128; ++n) {  // the window is zero outside [128, 384) of the frame
+                        const float2 t = tw[(k * (n + 128)) & 511];
+                        re = fmaf(s_v[n], t.x, re);
+                        im = fmaf(s_v[n], t.y, im);
+                    }
+                }
+                re += __shfl_xor_sync(0xffffffffu, re, 1);
+                im += __shfl_xor_sync(0xffffffffu, im, 1);
+                if (kk < nb && h == 0) {
+                    s_pw[kk] = re * re + im * im;
+                    if (sgl == 1 && want_grad) {
+                        float* sp = spec + ((long long)r * w.NBmax + kk) * 2;
+                        sp[0] = re;
+                        sp[1] = im;
+                    }
+                }
             }
-            for (int j = 0; j < 15; ++j)
-                if (k >= c_st.band_lo[j] && k < c_st.band_hi[j]) atomicAdd(&oct[sgl][j * w.NSmax + r], pw);
+            __syncthreads();
+            if (tid < 15) {
+                float acc = 0.f;
+                for (int k = c_st.band_lo[tid]; k < c_st.band_hi[tid]; ++k) acc += s_pw[k - klo];
+                oct[sgl][tid * w.NSmax + r] = sqrtf(acc + 1e-14f);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        for (int i = tid; i < 15 * NS; i += blockDim.x) {
-            float* p = &oct[sgl][(i / NS) * w.NSmax + i % NS];
-            *p = sqrtf(*p + 1e-14f);
-        }
-        __syncthreads();
     }
-    // (4) 30-frame segments: clip, normalise, correlate
+    grid.sync();
+    // (4) 30-frame segments: clip, normalise, correlate (and, for the backward, d oct_pred)
     const int Nseg = 30;
     int M = NS - (Nseg - 1);
     int seglen = Nseg;
@@ -249,129 +288,110 @@ __global__ void __launch_bounds__(kThreads) stoi_kernel(const float* y_true, con
     }
     const float c = 5.62341325f;
     double dsum = 0;
-    for (int row = tid; row < 15 * M; row += blockDim.x) {
-        const int m = row / 15, j = row % 15;
-        const float* X = oct[0] + j * w.NSmax + m;
-        const float* Y = oct[1] + j * w.NSmax + m;
-        float nx = 0.f, ny = 0.f, mx = 0.f;
-        for (int i = 0; i < seglen; ++i) {
-            nx = fmaf(X[i], X[i], nx);
-            ny = fmaf(Y[i], Y[i], ny);
-            mx += X[i];
-        }
-        const float alpha = sqrtf(nx) / (sqrtf(ny) + (float)kEps64);
-        mx /= seglen;
-        float my = 0.f;
-        for (int i = 0; i < seglen; ++i) my += fminf(Y[i] * alpha, X[i] + X[i] * c);
-        my /= seglen;
-        float sxx = 0.f, syy = 0.f, sxy = 0.f;
-        for (int i = 0; i < seglen; ++i) {
-            const float xc = X[i] - mx, yc = fminf(Y[i] * alpha, X[i] + X[i] * c) - my;
-            sxx = fmaf(xc, xc, sxx);
-            syy = fmaf(yc, yc, syy);
-            sxy = fmaf(xc, yc, sxy);
-        }
-        dsum += sxy / ((sqrtf(sxx) + (float)kEps64) * (sqrtf(syy) + (float)kEps64));
-    }
-    const double tot = block_sum(dsum, red);
-    if (tid == 0) D[item] = (float)(tot / (15.0 * M));
-    if (w.dpred == nullptr) return;
-
-    // ================= backward: d (-mean_B D) / d pred, stage by stage in reverse =====================================
-    float* doct = w.doct + (long long)item * 15 * w.NSmax;
-    float* dsil = w.dsil + (long long)item * w.Lsmax;
-    float* dr10 = w.dr10 + (long long)item * w.L10max;
-    int* rank = w.rank + (long long)item * w.NFmax;
-    float* spec = w.spec + (long long)item * w.NSmax * w.NBmax * 2;
-    for (int i = tid; i < 15 * w.NSmax; i += blockDim.x) doct[i] = 0.f;
-    for (long long i = tid; i < Ls; i += blockDim.x) dsil[i] = 0.f;
-    for (int m = tid; m < NF; m += blockDim.x) rank[m] = -1;
-    __syncthreads();
-    for (int k = tid; k < ns; k += blockDim.x) rank[sel[k]] = k;
-    // (4') correlation rows -> d oct_pred
     const float wrow = w.gscale / (15.0f * M);
-    for (int row = tid; row < 15 * M; row += blockDim.x) {
-        const int m = row / 15, j = row % 15;
+    for (long long row = it0; row < 15LL * M && alive; row += stride) {
+        const int m = (int)(row / 15), j = (int)(row % 15);
         const float* X = oct[0] + j * w.NSmax + m;
         const float* Y = oct[1] + j * w.NSmax + m;
         float nx = 0.f, ny = 0.f, mx = 0.f;
         for (int i = 0; i < seglen; ++i) {
-            nx = fmaf(X[i], X[i], nx);
-            ny = fmaf(Y[i], Y[i], ny);
-            mx += X[i];
+            const float x = __ldcg(X + i), y = __ldcg(Y + i);
+            nx = fmaf(x, x, nx);
+            ny = fmaf(y, y, ny);
+            mx += x;
         }
         const float sny = sqrtf(ny), snx = sqrtf(nx);
         const float alpha = snx / (sny + (float)kEps64);
         mx /= seglen;
         float my = 0.f;
-        for (int i = 0; i < seglen; ++i) my += fminf(Y[i] * alpha, X[i] + X[i] * c);
+        for (int i = 0; i < seglen; ++i) {
+            const float x = __ldcg(X + i);
+            my += fminf(__ldcg(Y + i) * alpha, x + x * c);
+        }
         my /= seglen;
         float sxx = 0.f, syy = 0.f, sxy = 0.f;
         for (int i = 0; i < seglen; ++i) {
-            const float xc = X[i] - mx, yc = fminf(Y[i] * alpha, X[i] + X[i] * c) - my;
+            const float x = __ldcg(X + i);
+            const float xc = x - mx, yc = fminf(__ldcg(Y + i) * alpha, x + x * c) - my;
             sxx = fmaf(xc, xc, sxx);
             syy = fmaf(yc, yc, syy);
             sxy = fmaf(xc, yc, sxy);
         }
         const float ssy = sqrtf(syy);
         const float dx = sqrtf(sxx) + (float)kEps64, dy = ssy + (float)kEps64;
-        const float c1 = 1.f / (dx * dy), c2 = ssy > 0.f ? sxy / (dx * dy * dy * ssy) : 0.f;
-        // d value / d y_i = c1 xc_i - c2 yc_i (its mean over i vanishes because xc and yc are centred)
-        float dalpha = 0.f;
-        for (int i = 0; i < seglen; ++i) {
-            const float ay = Y[i] * alpha, lim = X[i] + X[i] * c;
-            if (ay < lim) dalpha += (c1 * (X[i] - mx) - c2 * (ay - my)) * Y[i];
-        }
-        const float da = sny > 0.f ? -dalpha * snx / ((sny + (float)kEps64) * (sny + (float)kEps64) * sny) : 0.f;
-        for (int i = 0; i < seglen; ++i) {
-            const float ay = Y[i] * alpha, lim = X[i] + X[i] * c;
-            float g = da * Y[i];
-            if (ay < lim) g += alpha * (c1 * (X[i] - mx) - c2 * (ay - my));
-            atomicAdd(&doct[j * w.NSmax + m + i], wrow * g);
+        dsum += sxy / (dx * dy);
+        if (want_grad) {
+            const float c1 = 1.f / (dx * dy), c2 = ssy > 0.f ? sxy / (dx * dy * dy * ssy) : 0.f;
+            // d value / d y_i = c1 xc_i - c2 yc_i (its mean over i vanishes because xc and yc are centred)
+            float dalpha = 0.f;
+            for (int i = 0; i < seglen; ++i) {
+                const float x = __ldcg(X + i), y = __ldcg(Y + i);
+                const float ay = y * alpha, lim = x + x * c;
+                if (ay < lim) dalpha += (c1 * (x - mx) - c2 * (ay - my)) * y;
+            }
+            const float da = sny > 0.f ? -dalpha * snx / ((sny + (float)kEps64) * (sny + (float)kEps64) * sny) : 0.f;
+            for (int i = 0; i < seglen; ++i) {
+                const float x = __ldcg(X + i), y = __ldcg(Y + i);
+                const float ay = y * alpha, lim = x + x * c;
+                float gq = da * y;
+                if (ay < lim) gq += alpha * (c1 * (x - mx) - c2 * (ay - my));
+                atomicAdd(&doct[j * w.NSmax + m + i], wrow * gq);
+            }
         }
     }
-    __syncthreads();
+    const double tot = block_sum(dsum, red);
+    if (tid == 0 && alive) atomicAdd(dacc + item, tot);
+    grid.sync();
+    if (g == 0 && tid == 0) D[item] = alive ? (float)(__ldcg(dacc + item) / (15.0 * M)) : 0.99f;
+    if (!want_grad) return;
+
+    // ================= backward: d (-mean_B D) / d pred, stage by stage in reverse =====================================
     // (3') band energies -> power spectrum -> frames of the silent-frame-removed signal
-    {
-        const int nb = khi - klo;
-        for (int o = tid; o < NS * nb; o += blockDim.x) {
-            const int r = o / nb, k = klo + o % nb;
+    for (int r = g; r < NS && alive; r += G) {
+        if (tid < nb) {
+            const int k = klo + tid;
             float dP = 0.f;
             for (int j = 0; j < 15; ++j)
-                if (k >= c_st.band_lo[j] && k < c_st.band_hi[j]) dP += doct[j * w.NSmax + r] / (2.f * oct[1][j * w.NSmax + r]);
-            float* sp = spec + ((long long)r * w.NBmax + (k - klo)) * 2;
-            sp[0] *= 2.f * dP;
-            sp[1] *= 2.f * dP;
+                if (k >= c_st.band_lo[j] && k < c_st.band_hi[j])
+                    dP += __ldcg(&doct[j * w.NSmax + r]) / (2.f * __ldcg(&oct[1][j * w.NSmax + r]));
+            const float* sp = spec + ((long long)r * w.NBmax + tid) * 2;
+            s_pw[2 * tid] = 2.f * dP * sp[0];
+            s_pw[2 * tid + 1] = 2.f * dP * sp[1];
         }
         __syncthreads();
-        for (int o = tid; o < NS * 256; o += blockDim.x) {
-            const int r = o >> 8, n = o & 255;
+        {
+            const int n = tid >> 1, h = tid & 1;  // two threads per window sample, each sums half of the bins
+            const int k0 = h ? nb / 2 : 0, k1 = h ? nb : nb / 2;
             float dv = 0.f;
-            const float* sp = spec + (long long)r * w.NBmax * 2;
-            for (int kk = 0; kk < nb; ++kk) {
+            for (int kk = k0; kk < k1; ++kk) {
                 const float2 t = tw[((klo + kk) * (n + 128)) & 511];
-                dv = fmaf(sp[2 * kk], t.x, dv);
-                dv = fmaf(sp[2 * kk + 1], t.y, dv);
+                dv = fmaf(s_pw[2 * kk], t.x, dv);
+                dv = fmaf(s_pw[2 * kk + 1], t.y, dv);
             }
-            long long pos = 128LL * r + 128 + n - 256;
-            if (pos < 0) pos = -pos;
-            if (pos >= Ls) pos = 2 * (Ls - 1) - pos;
-            atomicAdd(&dsil[pos], dv * c_st.hann_per[n]);
+            dv += __shfl_xor_sync(0xffffffffu, dv, 1);
+            if (h == 0) {
+                long long pos = 128LL * r + 128 + n - 256;
+                if (pos < 0) pos = -pos;
+                if (pos >= Ls) pos = 2 * (Ls - 1) - pos;
+                atomicAdd(&dsil[pos], dv * c_st.hann_per[n]);
+            }
         }
         __syncthreads();
     }
+    grid.sync();
     // (2') overlap-add of the kept frames -> resampled signal
-    for (long long p = tid; p < L10; p += blockDim.x) {
+    for (long long p = it0; p < L10 && alive; p += stride) {
         const int m = (int)(p / 128), i = (int)(p % 128);
         float v = 0.f;
-        if (m < NF && rank[m] >= 0) v += c_st.hann_sym[i] * dsil[128LL * rank[m] + i];
-        if (m >= 1 && m - 1 < NF && rank[m - 1] >= 0) v += c_st.hann_sym[128 + i] * dsil[128LL * (rank[m - 1] + 1) + i];
+        if (m < NF && s_rank[m] >= 0) v += c_st.hann_sym[i] * __ldcg(&dsil[128LL * s_rank[m] + i]);
+        if (m >= 1 && m - 1 < NF && s_rank[m - 1] >= 0)
+            v += c_st.hann_sym[128 + i] * __ldcg(&dsil[128LL * (s_rank[m - 1] + 1) + i]);
         dr10[p] = v;
     }
-    __syncthreads();
+    grid.sync();
     // (1') polyphase resampler: out[5q + j] = sum_k kern[j][k] wave[8q + k - 10]
     float* dp = w.dpred + (long long)item * L;
-    for (long long idx = tid; idx < len; idx += blockDim.x) {
+    for (long long idx = it0; idx < len && alive; idx += stride) {
         float acc = 0.f;
         for (long long q = (idx + 10) / 8; q >= 0; --q) {
             const long long k = idx + 10 - 8 * q;
@@ -379,11 +399,36 @@ __global__ void __launch_bounds__(kThreads) stoi_kernel(const float* y_true, con
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
                 const long long n = 5 * q + j;
-                if (n < L10) acc = fmaf(c_st.resamp[j][k], dr10[n], acc);
+                if (n < L10) acc = fmaf(c_st.resamp[j][k], __ldcg(&dr10[n]), acc);
             }
         }
         dp[idx] = acc;
     }
+}
+
+// cooperative launch: G CTAs per item, all co-resident
+int launch_stoi(const float* y_true, const float* y_pred, const int* lens, int B, long long L, const StoiWork& w, float* D,
+                double* dacc, cudaStream_t st) {
+    const size_t smem = (size_t)w.NFmax * (sizeof(float) + 2 * sizeof(int)) + (256 + 2 * 257) * sizeof(float);
+    int dev = 0, sms = 0, per_sm = 0;
+    SE_CUDA_OK(cudaGetDevice(&dev));
+    SE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    SE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, stoi_kernel, kThreads, smem));
+    SE_REQUIRE(per_sm >= 1, "stoi: kernel does not fit on an SM");
+    int G = sms * per_sm / B;
+    if (G > 96) G = 96;
+    SE_REQUIRE(G >= 1, "stoi: batch larger than one co-resident grid (" + std::to_string(sms * per_sm) + " items)");
+    SE_CUDA_OK(cudaMemsetAsync(dacc, 0, sizeof(double) * B, st));
+    const float* a0 = y_true;
+    const float* a1 = y_pred;
+    const int* a2 = lens;
+    long long a3 = L;
+    StoiWork a4 = w;
+    float* a5 = D;
+    double* a6 = dacc;
+    void* args[] = {&a0, &a1, &a2, &a3, &a4, &a5, &a6};
+    SE_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(stoi_kernel), dim3(G, B), dim3(kThreads), args, smem, st));
+    return 0;
 }
 
 bool g_tables_ready[64] = {};
@@ -480,7 +525,10 @@ int se_stoi_loss(const float* y_true, const float* y_pred, const int32_t* lens_d
     w.oct = w.energy + n_en;
     float* D = w.oct + n_oct;
     w.sel = reinterpret_cast<int*>(D + B);
-    stoi_kernel<<<B, kThreads, 0, st>>>(y_true, y_pred, lens_dev, L, w, D);
+    double* dacc = nullptr;
+    SE_CUDA_OK(cudaMallocAsync(&dacc, sizeof(double) * B, st));
+    if (launch_stoi(y_true, y_pred, lens_dev, B, L, w, D, dacc, st)) return 1;
+    SE_CUDA_OK(cudaFreeAsync(dacc, st));
     mean_kernel<<<1, 1, 0, st>>>(D, B, -1.0f, out);  // reduction="mean": -D.mean()
     SE_CUDA_OK(cudaGetLastError());
     SE_CUDA_OK(cudaFreeAsync(base, st));
@@ -523,7 +571,10 @@ int se_loss_terms_grad(const float* source, const float* pred, const int32_t* le
     w.rank = w.sel + n_en;
     w.dpred = d_stoi;
     w.gscale = -1.0f / B;
-    stoi_kernel<<<B, kThreads, 0, st>>>(source, pred, lens_dev, L, w, D);
+    double* dacc = nullptr;
+    SE_CUDA_OK(cudaMallocAsync(&dacc, sizeof(double) * B, st));
+    if (launch_stoi(source, pred, lens_dev, B, L, w, D, dacc, st)) return 1;
+    SE_CUDA_OK(cudaFreeAsync(dacc, st));
     mean_kernel<<<1, 1, 0, st>>>(D, B, -1.0f, out2);
     si_snr_kernel<<<B, kThreads, 0, st>>>(pred, source, lens_dev, L, 1e-8f, per, d_sisnr, 1.0f / B);
     mean_kernel<<<1, 1, 0, st>>>(per, B, 1.0f, out2 + 1);

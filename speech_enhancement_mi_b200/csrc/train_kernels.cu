@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kThreads) gln_bwd_reduce_kernel(GlnBwdParams p
             const float w = p.w[k];
             const int fk = p.per_feature ? k / p.C : 0, ck = p.per_feature ? k - fk * p.C : k;
             float dwk = 0.f, dbk = 0.f;
-            for (int pos = group; pos < npos; pos += groups) {
+            for (int pos = group + groups * blockIdx.y; pos < npos; pos += groups * gridDim.y) {
                 int t, f;
                 if (p.per_feature) {
                     t = pos;
@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(kThreads) gln_bwd_reduce_kernel(GlnBwdParams p
             a += red[0][w];
             c += red[1][w];
         }
-        p.red[2 * b] = a;
-        p.red[2 * b + 1] = c;
+        atomicAdd(p.red + 2 * b, a);  // zeroed by the launcher; gridDim.y CTAs share a stream
+        atomicAdd(p.red + 2 * b + 1, c);
     }
     if (Ce <= kThreads && tid < lanes) {
         atomicAdd(p.dw + tid, sdw[tid]);
@@ -425,8 +425,14 @@ int launch_dgrad(const GemmParams& p, const float* G, StridedRows g, float* dA, 
 int launch_gln_bwd(const GlnBwdParams& p, cudaStream_t st) {
     if (p.B <= 0) return 0;
     const int Ce = p.per_feature ? p.F * p.C : p.C;
-    (void)Ce;
-    gln_bwd_reduce_kernel<<<p.B, kThreads, 0, st>>>(p);
+    SE_CUDA_OK(cudaMemsetAsync(p.red, 0, (size_t)2 * p.B * sizeof(double), st));
+    const int npos = p.per_feature ? p.T : p.T * p.F;
+    const int lanes = Ce < kThreads ? Ce : kThreads;
+    int split = npos / (4 * (kThreads / lanes));  // at least 4 positions per thread group
+    if (split > 32) split = 32;
+    if (split * p.B > 148 * 8) split = 148 * 8 / p.B;
+    if (split < 1) split = 1;
+    gln_bwd_reduce_kernel<<<dim3(p.B, split), kThreads, 0, st>>>(p);
     const int n = p.T * p.F * p.C;
     int gx = (n + kThreads * 4 - 1) / (kThreads * 4);
     gln_bwd_apply_kernel<<<dim3(gx < 1 ? 1 : gx, p.B), kThreads, 0, st>>>(p);
