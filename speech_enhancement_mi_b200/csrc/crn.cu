@@ -1306,8 +1306,11 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
                 if (g.gi) g.gi += (long long)s0 * g.giB;
                 if (g.hprev) g.hprev += (long long)s0 * g.hB;
                 g.b0 = s0;
-                return run_gemm(c, g, op.stage, op.label, st);
+                // per-chunk recurrent GEMMs have a handful of rows: CUDA-core kernel (the tensor-core kernel's scalar
+                // store path needs 16-byte aligned rows, which a 1-row slice of the shared gh buffer does not guarantee)
+                return launch_gemm_fp32(g, st);
             }
+            if (op.chunk_serial) return launch_gemm_fp32(g, st);
             return run_gemm(c, g, op.stage, op.label, st);
         }
         case OP_NORM: {
