@@ -133,6 +133,24 @@ def test_true_streaming_steps_equal_realtime_process(precision):
     assert np.abs(y - ref).max() < 2e-5
 
 
+def test_pipelined_host_steps_equal_device_steps():
+    """process_chunk_host (pinned host buffers, copies on side streams, double-buffered staging) returns exactly what
+    process_chunk returns for the same chunks, also when many steps are in flight."""
+    model = make_model("crn_small", "fp32")
+    B, N = 4, 9
+    mix, _ = synth.make_mixture(B, 1600 * (N + 1))
+    chunks = [torch.from_numpy(mix[:, :, 1600 * n:1600 * n + 3200].copy()) for n in range(N)]
+    model.reset()
+    want = [model.process_chunk(c.cuda()).cpu().numpy() for c in chunks]
+    model.reset()
+    pinned = [c.pin_memory() for c in chunks]
+    outs = [torch.empty((B, 1600), dtype=torch.float32).pin_memory() for _ in range(N)]
+    events = [model.process_chunk_host(pinned[n], outs[n]) for n in range(N)]  # no synchronisation in between
+    for n in range(N):
+        events[n].synchronize()
+        assert np.array_equal(outs[n].numpy(), want[n]), n
+
+
 def test_graph_and_eager_agree_and_reset_restores():
     from speech_enhancement_mi_b200._native import check, lib
     model = make_model("crn_small")
