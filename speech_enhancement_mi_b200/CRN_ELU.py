@@ -418,11 +418,17 @@ class TemporalCRN(nn.Module):
             self._tbound_versions = versions
         return self._tctx
 
+    @staticmethod
+    def _train_capacity(B, n_chunks):
+        """Chunk-streams to allocate: at least the 44 chunks of the longest piece the reference's data pipeline emits
+        (config.yaml:11 max_length 60000), so that flag=True pieces of any such length find the carried state."""
+        return B * max(n_chunks, 44)
+
     def _train_forward(self, mixture, flag):
         B, _, L = mixture.shape
         dev = self._pick_device(mixture)
         _, n_chunks = _native.chunk_grid(L + (0 if flag else self.segment_length // 2), self.segment_length)
-        ctx = self._ensure_train_ctx(B * n_chunks, dev, keep_state=bool(flag))
+        ctx = self._ensure_train_ctx(self._train_capacity(B, n_chunks), dev, keep_state=bool(flag))
         with torch.cuda.device(dev):
             xd = self._to_device(mixture, dev)
             pred = torch.empty((B, L), dtype=torch.float32, device=xd.device)
@@ -452,7 +458,7 @@ class TemporalCRN(nn.Module):
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             dev = self._pick_device(mixture)
             _, n_chunks = _native.chunk_grid(L + (0 if flag else self.segment_length // 2), self.segment_length)
-            self._ensure_train_ctx(B * n_chunks, dev, keep_state=bool(flag))
+            self._ensure_train_ctx(self._train_capacity(B, n_chunks), dev, keep_state=bool(flag))
             return _RealtimeTrainFn.apply(self, mixture, bool(flag), *self._train_params())
         dev = self._pick_device(mixture)
         ctx = self._ensure_ctx(B, dev, keep_state=bool(flag))

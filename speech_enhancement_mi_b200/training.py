@@ -65,6 +65,7 @@ class NativeTrainer:
             model._ensure_train_ctx(1, self.device, keep_state=False)
             self.ctx = model._tctx
             params = model._train_params()
+            self.param_names = [lib().se_crn_param_name(self.ctx, i).decode() for i in range(len(params))]
             n = lib().se_crn_num_theta(self.ctx)
             dev = torch.device("cuda", self.device)
             self.theta = torch.cat([p.detach().to(device=dev, dtype=torch.float32).reshape(-1) for p in params])
@@ -80,6 +81,12 @@ class NativeTrainer:
             self.w_stoi = torch.full((1,), 0.7 / self.accum, dtype=torch.float32, device=dev)    # CRN_ELU.py:529
             self.w_sisnr = torch.full((1,), -0.3 / self.accum, dtype=torch.float32, device=dev)  # sisnr enters negated
             self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._rebind()
+
+    def reload_parameters(self):
+        """After model.load_state_dict (resume, train.py:110): copy_ wrote through the views into the flat vector; re-lay
+        the weights out."""
+        with torch.cuda.device(self.device):
             self._rebind()
 
     def _stream(self):
