@@ -95,6 +95,27 @@ def test_teacher_train_step_matches_reference():
     assert not bad, bad
 
 
+def test_student_train_step_matches_oracle_autograd():
+    """Distilled student (distillation_crn.py:51,340 numerics): realtime_process returns (pred, features) as in the
+    reference; gradients of the compute_loss part against the oracle's autograd with student=True."""
+    from common import STUDENT
+    w = synth.make_crn_weights(seed=3, **STUDENT)
+    o = crn_oracle.CRNOracle({k: torch.from_numpy(v) for k, v in w.items()}, segment_length=3200, student=True, **STUDENT)
+    mix, src = synth.make_mixture(1, 4800)
+    _, dpred_ref, losses_ref, grads_ref = crn_oracle.train_step_grads(o, mix, src, [4800], False)
+    model = make_model("crn_student", precision="fp32").cuda().train()
+    pred, feats = model.realtime_process(torch.from_numpy(mix).cuda(), False)
+    pred.retain_grad()
+    with contextlib.redirect_stdout(io.StringIO()):
+        loss, mae, sisnr = model.compute_loss(torch.from_numpy(src).cuda(), pred, torch.tensor([4800]))
+    loss.backward()
+    assert abs(float(loss) - losses_ref[0]) < 2e-3
+    assert rel_err(pred.grad.cpu().numpy(), dpred_ref.numpy()) < 1e-2
+    bad = [(k, rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy())) for k, p in model.named_parameters()
+           if k in grads_ref and not rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy()) < 2e-2]
+    assert not bad, bad
+
+
 def test_tf32_training_gradients_close():
     g = np.load(os.path.join(GOLDEN, "train_grads.npz"))
     model = make_model("crn_small", precision="tf32").cuda().train()
