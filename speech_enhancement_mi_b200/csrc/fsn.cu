@@ -69,6 +69,7 @@ struct se_fsn {
     // SE_PRECISION_FP16: the sub-band records (x_t and the h histories, 98.7 % of the FLOPs read them) and the sub-band
     // weights are stored as fp16 (tcgen05 kind::f16, fp32 accumulate; cell state c and all statistics stay fp32)
     bool half = false;
+    bool wide_tiles = true;  // 256-column LSTM tiles where the hidden size allows (SE_B200_FSN_WIDE=0: 128-column tiles)
     int sesz = 4;   // element size of the sub-band records
     int Ksp = 0;    // sub-band input size padded to whole k-blocks (32 floats / 64 halves)
     void* warena_h = nullptr;
@@ -322,6 +323,7 @@ void build_lstm(se_fsn* c, const std::string& prefix, int layer, int Kin, int Ki
                 bool half = false) {
     const int U = half ? 8 : 4;    // elements per 16-byte gather unit
     const int esz = half ? 2 : 4;
+    const int U_tile = (H % 64 == 0 && c->wide_tiles) ? 64 : 32;  // hidden units per output tile
     const int K = Kin_pad + H;
     const int N = 4 * H;
     const size_t w_off = c->reserve_w((size_t)N * K), b_off = c->reserve_w(N);
@@ -332,8 +334,8 @@ void build_lstm(se_fsn* c, const std::string& prefix, int layer, int Kin, int Ki
         const std::vector<float>& bi = hp.at(prefix + ".sequence_model.bias_ih_l" + s);
         const std::vector<float>& bh = hp.at(prefix + ".sequence_model.bias_hh_l" + s);
         for (int n = 0; n < N; ++n) {
-            // tile y holds [i | f | g | o] of hidden units 32y .. 32y+31 (gemm_tc.cu EPI_LSTM; nn.LSTM gate order i,f,g,o)
-            const int src = ((n % 128) / 32) * H + (n / 128) * 32 + n % 32;
+            // tile y holds [i | f | g | o] of hidden units U*y .. U*y+U-1 (gemm_tc.cu EPI_LSTM; nn.LSTM gate order i,f,g,o)
+            const int src = ((n % (4 * U_tile)) / U_tile) * H + (n / (4 * U_tile)) * U_tile + n % U_tile;
             float* row = arena + w_off + (size_t)n * K;
             for (int k = 0; k < Kin; ++k) row[k] = wi[(size_t)src * Kin + k];
             for (int k = 0; k < H; ++k) row[Kin_pad + k] = wh[(size_t)src * H + k];
@@ -355,6 +357,7 @@ void build_lstm(se_fsn* c, const std::string& prefix, int layer, int Kin, int Ki
         g.N = N;
         g.Npad = N;
         g.epi = EPI_LSTM;
+        g.lstm_units = U_tile;
         g.out = reinterpret_cast<float*>(reinterpret_cast<char*>(rec) + (hhist + (long long)(t + 1) * H) * esz);  // h_t
         g.oB = recB;
         g.hprev = cbuf;  // c_{t-1}, updated in place
@@ -433,6 +436,7 @@ int build(se_fsn* c) {
     SE_REQUIRE(g.precision == SE_PRECISION_TF32 || g.precision == SE_PRECISION_FP16,
                "FullSubNet: precision must be SE_PRECISION_TF32 or SE_PRECISION_FP16");
     c->half = g.precision == SE_PRECISION_FP16;
+    if (const char* e = getenv("SE_B200_FSN_WIDE")) c->wide_tiles = atoi(e) != 0;
     c->sesz = c->half ? 2 : 4;
     SE_REQUIRE(round_up(c->Ks, 32) == c->Ks, "FullSubNet: sub-band input size must be a multiple of 32 (31 neighbours + 1)");
     c->Ksp = round_up(c->Ks, c->half ? 64 : 32);

@@ -534,7 +534,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
                     }
                 }
                 __syncwarp();
-            } else if (BN == 128 && p.epi == EPI_LSTM) {
+            } else if ((BN == 128 || BN == 256) && p.epi == EPI_LSTM) {
                 // tile columns: [i | f | g | o] of hidden units j0 .. j0+32 (nn.LSTM gate order); 8 units per pass.
                 // c_prev = hprev (row stride hB), h' -> out (oB), c' -> out2 (o2B); Tn = Fo = 1: row = sequence
                 constexpr int U = BN / 4;
@@ -743,7 +743,7 @@ int launch_tc(const GemmParams& p, cudaStream_t st) {
 template <typename AT>
 int launch_elem(const GemmParams& p, cudaStream_t st) {
     if (p.epi == EPI_GRU) return launch_tc<96, AT>(p, st);
-    if (p.epi == EPI_LSTM) return launch_tc<128, AT>(p, st);
+    if (p.epi == EPI_LSTM) return p.lstm_units == 64 ? launch_tc<256, AT>(p, st) : launch_tc<128, AT>(p, st);
     switch (gemm_tf32_tile_n(p.N)) {
         case 16: return launch_tc<16, AT>(p, st);
         case 32: return launch_tc<32, AT>(p, st);
@@ -759,7 +759,9 @@ bool gemm_tf32_supported(const GemmParams& p) {
     const int bke = p.a_half ? 64 : 32, ue = p.a_half ? 8 : 4;  // elements per k-block / per 16-byte gather unit
     if (p.K % bke != 0 || p.K < bke || p.K / ue > 512) return false;  // whole k-blocks (host pads with zero weights)
     if (p.epi == EPI_GRU) return p.H % 32 == 0 && p.Tn == 1 && p.Fo == 1 && p.N == 3 * p.H;
-    if (p.epi == EPI_LSTM) return p.H % 32 == 0 && p.Tn == 1 && p.Fo == 1 && p.N == 4 * p.H && p.Npad == p.N;
+    if (p.epi == EPI_LSTM)
+        return p.H % (p.lstm_units == 64 ? 64 : 32) == 0 && (p.lstm_units == 0 || p.lstm_units == 32 || p.lstm_units == 64) &&
+               p.Tn == 1 && p.Fo == 1 && p.N == 4 * p.H && p.Npad == p.N;
     if (p.Npad % gemm_tf32_tile_n(p.N) != 0) return false;
     if (p.epi == EPI_ELU_GATE) return p.Npad == 16 && p.C2 >= 1 && p.C2 <= 16 && p.W2 && p.bias2;
     if (p.epi == EPI_SKIP && (p.o2B != p.oB || p.o2T != p.oT || p.o2F != p.oF)) return false;
