@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--model", default="teacher", choices=["teacher", "student"])
     ap.add_argument("--cpu-streams", type=int, default=16, help="streams in the CPU baseline sample")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of the cpu_baseline leg")
+    ap.add_argument("--latency-steps", type=int, default=1000, help="steps of the p99 chunk-latency pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
@@ -280,6 +281,17 @@ def main():
     total_ms = events[0].elapsed_time(events[K])
     lat = sorted(events[k].elapsed_time(events[k + 1]) for k in range(K))
     clocks = sampler.stop()
+    # p99 chunk latency (BASELINE.json metric; SURVEY.md section 8(d): >= 1000 steps after warm-up): a separate pass so
+    # that the percentile does not rest on the K timed steps alone.  Real-time deadline: 100 ms per chunk step.
+    NLAT = max(K, args.latency_steps)
+    if NLAT > K:
+        lev = [torch.cuda.Event(enable_timing=True) for _ in range(NLAT + 1)]
+        lev[0].record()
+        for k in range(NLAT):
+            model.process_chunk(chunk_view(W + K + k), out)
+            lev[k + 1].record()
+        torch.cuda.synchronize()
+        lat = sorted(lev[k].elapsed_time(lev[k + 1]) for k in range(NLAT))
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -398,7 +410,8 @@ def main():
                        "streams_per_gpu": B, "precision": args.precision,
                        "l2": f"inputs larger than L2: {RING}-hop input ring of {sig.numel() * 4 / 1e6:.0f} MB and a "
                              f"per-step working set of several GB, both > 126 MB L2"},
-            "p99_chunk_latency_ms": lat[min(K - 1, int(0.99 * K))], "p50_chunk_latency_ms": lat[K // 2],
+            "p99_chunk_latency_ms": lat[min(len(lat) - 1, int(0.99 * len(lat)))],
+            "p50_chunk_latency_ms": lat[len(lat) // 2], "latency_steps": len(lat),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches * K, "roofline": roofline, "stages": stages, "kernels": kernels,
             "cpu_baseline": cpu,
         }
