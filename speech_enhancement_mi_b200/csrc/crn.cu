@@ -50,7 +50,7 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
     long long per_stream() const { return sB; }
 };
 
-enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ };
+enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ, OP_DECONV_LAST, OP_SKIP_SMALL };
 enum Stage { ST_STFT = 0, ST_PRECONV, ST_ENCODER, ST_GRU, ST_DECODER, ST_MASK, ST_ROLL, ST_COUNT };
 const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"};
 
@@ -64,6 +64,9 @@ struct Op {
     int rows_per_stream = 0;
     NormApplyParams n;
     PreconvParams pc;
+    DeconvLastParams dl;
+    SkipSmallParams sk;
+    int small_c = 0;  // channel count of the two small-layer kernels
     // GRU pointwise
     const float* gi = nullptr;
     long long giB = 0;
@@ -178,6 +181,7 @@ struct se_ctx {
     float* E(float* base, long long elems) const {  // element offset into an operand buffer
         return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + elems * esz);
     }
+    bool small_layers = true;  // SE_B200_SMALL_LAYERS=0: keep the two small-channel layers on the GEMM path (A/B switch)
     unsigned tc_mask = 0xffffffffu;  // SE_B200_TC_MASK: bit per Stage that may use the tensor-core GEMM (debug)
     std::map<int, cudaGraphExec_t> graphs;  // keyed by B
     cudaStream_t own_stream = nullptr;
@@ -661,6 +665,22 @@ struct Builder {
                  4.0 * Cin * T * Fin + 4.0 * T * Fy * Cout_real);
             push_gemm(ST_DECODER, g, T * Fo, pw, k_off);
             rec.op_deconv = (int)c->ops.size() - 1;
+            if (c->half && !c->train && !skip && Cout_real == 2 && KT == 3 && deconv_last_supported(Cin) &&
+                c->small_layers) {
+                Op& op = c->ops.back();  // same packed weights and report entry, served by the direct kernel
+                op.kind = OP_DECONV_LAST;
+                op.small_c = Cin;
+                op.dl = DeconvLastParams{};
+                op.dl.in = reinterpret_cast<const __half*>(in.base);
+                op.dl.sB = in.sB;
+                op.dl.sT = in.sT;
+                op.dl.sF = in.sF;
+                op.dl.Fin = Fin;
+                op.dl.d = d;
+                op.dl.Kp = pw.K;
+                op.dl.y = y;
+                op.dl.stats = g.stats;
+            }
         }
         if (!skip) {
             if (c->train) c->deconv_recs.push_back(rec);
@@ -713,6 +733,21 @@ struct Builder {
             meta(name + ".skip1x1", 4.0 * rows * Cout_real * Cout_real, 12.0 * rows * Cout_real);
             push_gemm(ST_DECODER, g, rows, pw, k_off);
             rec.op_skip = (int)c->ops.size() - 1;
+            if (c->half && !c->train && skip->C == Cout_real && skip_small_supported(Cout_real) && c->small_layers) {
+                Op& op = c->ops.back();
+                op.kind = OP_SKIP_SMALL;
+                op.small_c = Cout_real;
+                op.sk = SkipSmallParams{};
+                op.sk.in = reinterpret_cast<const __half*>(skip->interior());
+                op.sk.sB = skip->sB;
+                op.sk.sT = skip->sT;
+                op.sk.sF = skip->sF;
+                op.sk.Fs = Fs;
+                op.sk.Kp = pw.K;
+                op.sk.rm = reinterpret_cast<__half*>(tmp_rm);
+                op.sk.rr = reinterpret_cast<__half*>(tmp_rr);
+                op.sk.stats = g.stats;
+            }
         }
         {
             NormApplyParams n{};
@@ -772,6 +807,7 @@ int build_ctx(se_ctx* c) {
     c->ue = 16 / c->esz;
     c->kblock = 128 / c->esz;
     if (const char* e = getenv("SE_B200_TC_MASK")) c->tc_mask = (unsigned)strtoul(e, nullptr, 0);
+    if (const char* e = getenv("SE_B200_SMALL_LAYERS")) c->small_layers = atoi(e) != 0;
     for (int i = 0; i < c->L; ++i) {
         SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
         SE_REQUIRE(!c->half || g.num_channels[i] % 8 == 0, "fp16 mode: num_channels must be multiples of 8");
@@ -1208,7 +1244,13 @@ int build_ctx(se_ctx* c) {
     for (size_t i = 0; i < c->ops.size(); ++i) {
         Op& op = c->ops[i];
         const OpFix& f = b.fix[i];
-        if (op.kind == OP_GEMM || op.kind == OP_GRU_SEQ) {
+        if (op.kind == OP_DECONV_LAST) {
+            op.dl.w = c->warena + f.w_off;
+            op.dl.bias = c->warena + f.b_off;
+        } else if (op.kind == OP_SKIP_SMALL) {
+            op.sk.w = c->warena + f.w_off;
+            op.sk.bias = c->warena + f.b_off;
+        } else if (op.kind == OP_GEMM || op.kind == OP_GRU_SEQ) {
             op.g.W = (c->half && op.g.a_half) ? static_cast<const void*>(reinterpret_cast<const unsigned short*>(c->warena_h) + f.w_off)
                                               : static_cast<const void*>(c->warena + f.w_off);
             op.g.bias = c->warena + f.b_off;
@@ -1323,6 +1365,16 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
             pc.b0 = 0;
             pc.B = B;
             return launch_preconv(pc, st);
+        }
+        case OP_DECONV_LAST: {
+            DeconvLastParams dl = op.dl;
+            dl.B = B;
+            return launch_deconv_last(dl, op.small_c, st);
+        }
+        case OP_SKIP_SMALL: {
+            SkipSmallParams sk = op.sk;
+            sk.B = B;
+            return launch_skip_small(sk, op.small_c, st);
         }
         case OP_GRU_SEQ:
             SE_REQUIRE(false, "internal: the persistent GRU op only runs inside the training forward");

@@ -1,5 +1,6 @@
 // Internal declarations shared by the .cu translation units of libse_b200.so (not part of the C-ABI).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -276,6 +277,34 @@ int launch_add_strided(float* dst, StridedRows d, const float* src, StridedRows 
 int launch_gru_bwd_pw(const float* gi, long long giB, const float* gh, long long ghB, const float* hprev, long long hB,
                       const float* dH, long long dHB, float* dhrec, float* dgi, float* dgh, long long dgB, int B, int H,
                       cudaStream_t st);
+// small-channel layers on CUDA cores (small_layers.cu; fp16 operand mode)
+struct DeconvLastParams {
+    const __half* in;      // last decoder input buffer (padded row 0, frame 0), element strides below
+    long long sB, sT, sF;
+    int Fin, d;            // input bins, time dilation
+    const float* w;        // fp32 packed [4][Kp]: row n = parity * 2 + co, column (kt * 3 + j) * Cin + ci
+    int Kp;
+    const float* bias;
+    float* y;              // [B][T][2 Fin - 1][2] fp32 (raw elu output; normalised inside the mask kernel)
+    double* stats;
+    int B;
+};
+struct SkipSmallParams {
+    const __half* in;      // skip tensor = interior of an encoder input buffer
+    long long sB, sT, sF;
+    int Fs;
+    const float* w;        // fp32 packed [2C][Kp], rows interleaved (mask_c, residual_c)
+    int Kp;
+    const float* bias;
+    __half *rm, *rr;       // [B][T][Fs][C]
+    double* stats;
+    int B;
+};
+bool deconv_last_supported(int Cin);
+bool skip_small_supported(int C);
+int launch_deconv_last(const DeconvLastParams& p, int Cin, cudaStream_t st);
+int launch_skip_small(const SkipSmallParams& p, int C, cudaStream_t st);
+
 // persistent small-batch GRU recurrence (gru_seq.cu): one cooperative launch per layer for all chunks and steps
 struct GruSeqParams {
     const float* Whh;  // packed [3H][Kp], rows r | z | n (PyTorch order), b_hh separately
