@@ -29,7 +29,11 @@ template <int KPL>
 __global__ void __launch_bounds__(kWarps * 32) gru_seq_fwd_kernel(GruSeqParams p) {
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31;
-    const int j = blockIdx.x * kWarps + (threadIdx.x >> 5);  // hidden unit of this warp
+    // gridDim.x = unit blocks x stream groups: group sg serves streams i = sg, sg + SG, ... of every chunk, so that larger
+    // batches are spread over more warps instead of lengthening the latency-bound pass of one warp
+    const int ublocks = (p.H + kWarps - 1) / kWarps;
+    const int SG = gridDim.x / ublocks, sg = blockIdx.x / ublocks;
+    const int j = (blockIdx.x % ublocks) * kWarps + (threadIdx.x >> 5);  // hidden unit of this warp
     const int H = p.H, T = p.T;
     const bool active = j < H;
     float wr[KPL], wz[KPL], wn[KPL];
@@ -49,7 +53,7 @@ __global__ void __launch_bounds__(kWarps * 32) gru_seq_fwd_kernel(GruSeqParams p
     for (int n = 0; n < p.N; ++n) {
         for (int t = 0; t < T; ++t) {
             if (active) {
-                for (int i = 0; i < p.nb; ++i) {
+                for (int i = sg; i < p.nb; i += SG) {
                     const long long s = (long long)n * p.nb + i;
                     const float* hp = (t == 0 && n > 0) ? p.hseq + (s - p.nb) * p.hB + (long long)T * H
                                                         : p.hseq + s * p.hB + (long long)t * H;
@@ -91,7 +95,9 @@ template <int KPL>
 __global__ void __launch_bounds__(kWarps * 32) gru_seq_bwd_kernel(GruSeqBwdParams p) {
     cg::grid_group grid = cg::this_grid();
     const int lane = threadIdx.x & 31;
-    const int k = blockIdx.x * kWarps + (threadIdx.x >> 5);  // hidden unit (input side of W_hh) of this warp
+    const int ublocks = (p.H + kWarps - 1) / kWarps;
+    const int SG = gridDim.x / ublocks, sg = blockIdx.x / ublocks;  // stream groups, as in the forward kernel
+    const int k = (blockIdx.x % ublocks) * kWarps + (threadIdx.x >> 5);  // hidden unit (input side of W_hh) of this warp
     const int H = p.H, T = p.T;
     const bool active = k < H;
     float wc[3 * KPL];  // column k of W_hh: rows n = lane + 32 q, q < 3H/32
@@ -136,7 +142,7 @@ __global__ void __launch_bounds__(kWarps * 32) gru_seq_bwd_kernel(GruSeqBwdParam
         grid.sync();
         // phase B: nxt[s][k] += sum_n dgh[s][t][n] * W_hh[n][k]
         if (active) {
-            for (int s = 0; s < p.B; ++s) {
+            for (int s = sg; s < p.B; s += SG) {
                 const float* q = p.dgh + (long long)s * p.gB + (long long)t * 3 * H;
                 float acc = 0.f;
 #pragma unroll
@@ -153,13 +159,16 @@ __global__ void __launch_bounds__(kWarps * 32) gru_seq_bwd_kernel(GruSeqBwdParam
 }
 
 template <typename P, typename K>
-int launch_coop(K kernel, const P& p, int H, cudaStream_t st, const char* what) {
-    const int grid = (H + kWarps - 1) / kWarps;
+int launch_coop(K kernel, const P& p, int H, int want_groups, cudaStream_t st, const char* what) {
+    const int ublocks = (H + kWarps - 1) / kWarps;
     int dev = 0, sms = 0, per_sm = 0;
     SE_CUDA_OK(cudaGetDevice(&dev));
     SE_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     SE_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarps * 32, 0));
-    SE_REQUIRE(grid <= sms * per_sm, std::string(what) + ": hidden size too large for one co-resident grid");
+    SE_REQUIRE(ublocks <= sms * per_sm, std::string(what) + ": hidden size too large for one co-resident grid");
+    int groups = want_groups < 1 ? 1 : want_groups;
+    if (groups > sms * per_sm / ublocks) groups = sms * per_sm / ublocks;  // every CTA must be resident (grid barriers)
+    const int grid = ublocks * groups;
     P copy = p;
     void* args[] = {&copy};
     SE_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kernel), dim3(grid), dim3(kWarps * 32), args, 0, st));
@@ -170,11 +179,11 @@ int launch_coop(K kernel, const P& p, int H, cudaStream_t st, const char* what) 
 
 #define SE_GRU_DISPATCH(KERNEL, P)                                                        \
     switch (p.H / 32) {                                                                   \
-        case 1: return launch_coop(KERNEL<1>, p, p.H, st, #KERNEL);                       \
-        case 2: return launch_coop(KERNEL<2>, p, p.H, st, #KERNEL);                       \
-        case 4: return launch_coop(KERNEL<4>, p, p.H, st, #KERNEL);                       \
-        case 8: return launch_coop(KERNEL<8>, p, p.H, st, #KERNEL);                       \
-        case 16: return launch_coop(KERNEL<16>, p, p.H, st, #KERNEL);                     \
+        case 1: return launch_coop(KERNEL<1>, p, p.H, groups, st, #KERNEL);               \
+        case 2: return launch_coop(KERNEL<2>, p, p.H, groups, st, #KERNEL);               \
+        case 4: return launch_coop(KERNEL<4>, p, p.H, groups, st, #KERNEL);               \
+        case 8: return launch_coop(KERNEL<8>, p, p.H, groups, st, #KERNEL);               \
+        case 16: return launch_coop(KERNEL<16>, p, p.H, groups, st, #KERNEL);             \
     }
 
 bool gru_seq_supported(int H) { return H == 32 || H == 64 || H == 128 || H == 256 || H == 512; }
@@ -182,6 +191,7 @@ bool gru_seq_supported(int H) { return H == 32 || H == 64 || H == 128 || H == 25
 int launch_gru_seq_fwd(const GruSeqParams& p, cudaStream_t st) {
     SE_REQUIRE(gru_seq_supported(p.H), "gru_seq: hidden size must be 32, 64, 128, 256 or 512");
     if (p.nb <= 0 || p.N <= 0) return 0;
+    const int groups = p.nb < 4 ? p.nb : 4;
     SE_GRU_DISPATCH(gru_seq_fwd_kernel, GruSeqParams)
     return 2;
 }
@@ -189,6 +199,7 @@ int launch_gru_seq_fwd(const GruSeqParams& p, cudaStream_t st) {
 int launch_gru_seq_bwd(const GruSeqBwdParams& p, cudaStream_t st) {
     SE_REQUIRE(gru_seq_supported(p.H), "gru_seq: hidden size must be 32, 64, 128, 256 or 512");
     if (p.B <= 0) return 0;
+    const int groups = p.B < 8 ? p.B : 8;
     SE_GRU_DISPATCH(gru_seq_bwd_kernel, GruSeqBwdParams)
     return 2;
 }
