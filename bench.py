@@ -56,18 +56,50 @@ def parse():
 # clocks
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """Samples SM clock / throttle reasons of one GPU with nvidia-smi while the timed region runs."""
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs: NVML in-process, back to back with a 5 ms pause (an
+    `nvidia-smi -lms` child needs about a second to come up on an 8-GPU box and then misses short timed regions); falls
+    back to the nvidia-smi loop when the NVML binding is unavailable."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASON_BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index):
+    def __init__(self, index, uuid=None):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.uuid = uuid
+        self.samples = []  # [sm_mhz, sm_max_mhz, hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap]
         self.proc = None
+        self.stamps = []         # wall-clock time of every NVML sample
+        self.window = [None, None]  # [start, end] of the timed region: only samples inside it are reported
+        self._halt = threading.Event()
+
+    def _run_nvml(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid) if self.uuid else pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+        while not self._halt.is_set():
+            sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+            try:
+                bits = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+            except Exception:
+                bits = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.stamps.append(time.time())
+            self.samples.append([str(sm), str(mx)] + [("Active" if bits & self.REASON_BITS[n] else "Not Active") for n in
+                                                      ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                       "sw_power_cap")])
+            self._halt.wait(0.005)
 
     def run(self):
+        try:
+            self._run_nvml()
+            return
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -78,12 +110,18 @@ class ClockSampler(threading.Thread):
             pass
 
     def stop(self):
+        self._halt.set()
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        samples = self.samples
+        if self.window[0] is not None and len(self.stamps) == len(self.samples):
+            lo, hi = self.window[0], self.window[1] if self.window[1] is not None else float("inf")
+            inside = [x for x, ts in zip(self.samples, self.stamps) if lo <= ts <= hi]
+            samples = inside or samples
+        for s in samples:
             try:
                 sm.append(int(float(s[0])))
                 mx = max(mx, int(float(s[1])))
@@ -268,16 +306,22 @@ def main():
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
     sampler.start()
-    time.sleep(0.3)
+    time.sleep(0.05)
     events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
     barrier()
+    sampler.window[0] = time.time()
     events[0].record()
     for k in range(K):
         model.process_chunk(chunk_view(W + k), out)
         events[k + 1].record()
     barrier()
+    sampler.window[1] = time.time()
     total_ms = events[0].elapsed_time(events[K])
     lat = sorted(events[k].elapsed_time(events[k + 1]) for k in range(K))
     clocks = sampler.stop()
