@@ -204,6 +204,10 @@ class TemporalCRN(nn.Module):
         self._bound_versions = None
         self._fresh = True  # no chunk processed since the last reset
         # training context (chunk-major batch; created on the first realtime_process under autograd)
+        # offline inference of a few long signals goes through the chunk-major batched forward (see realtime_process)
+        self.chunk_batch = os.environ.get("SE_B200_CHUNK_BATCH", "1") != "0"
+        self.chunk_batch_max_streams = 8
+        self._state_owner = "stream"
         self._tctx = None
         self._tctx_device = None
         self._tctx_capacity = 0
@@ -461,6 +465,20 @@ class TemporalCRN(nn.Module):
             self._ensure_train_ctx(self._train_capacity(B, n_chunks), dev, keep_state=bool(flag))
             return _RealtimeTrainFn.apply(self, mixture, bool(flag), *self._train_params())
         dev = self._pick_device(mixture)
+        # Few streams, many chunks (a file, predict.py:92): the carried state of a chunk is just the tail of the previous
+        # chunk's layer inputs (CRN_ELU.py:243), so every layer can run ONCE over all chunks of all streams and only the
+        # GRU recurrence stays serial -- the chunk-major forward of the training context, without a backward.
+        _, n_chunks = _native.chunk_grid(L + (0 if flag else self.segment_length // 2), self.segment_length)
+        batched = self._state_owner == "chunk-batch" if flag else (
+            self.chunk_batch and self.precision != "fp16" and B <= self.chunk_batch_max_streams
+            and 4 <= n_chunks <= 1024)  # fp16 operand mode exists only on the streaming path
+        if batched:
+            with torch.no_grad():
+                pred = self._train_forward(mixture, flag)
+            self._state_owner = "chunk-batch"
+            self._fresh = False
+            return pred if mixture.is_cuda else pred.cpu()
+        self._state_owner = "stream"
         ctx = self._ensure_ctx(B, dev, keep_state=bool(flag))
         with torch.cuda.device(dev):
             if mixture.is_cuda:
