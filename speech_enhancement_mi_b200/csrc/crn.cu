@@ -50,7 +50,7 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
     long long per_stream() const { return sB; }
 };
 
-enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ, OP_DECONV_LAST, OP_SKIP_SMALL };
+enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ, OP_DECONV_LAST, OP_SKIP_SMALL, OP_GRU_TC };
 enum Stage { ST_STFT = 0, ST_PRECONV, ST_ENCODER, ST_GRU, ST_DECODER, ST_MASK, ST_ROLL, ST_COUNT };
 const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"};
 
@@ -66,6 +66,7 @@ struct Op {
     PreconvParams pc;
     DeconvLastParams dl;
     SkipSmallParams sk;
+    GruTcParams gt;
     int small_c = 0;  // channel count of the two small-layer kernels
     // GRU pointwise
     const float* gi = nullptr;
@@ -181,6 +182,8 @@ struct se_ctx {
     float* E(float* base, long long elems) const {  // element offset into an operand buffer
         return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + elems * esz);
     }
+    bool gru_persist = true;   // SE_B200_GRU_PERSIST=0: one GEMM launch per recurrent step instead of the persistent kernel
+    int* gru_counters = nullptr;
     bool small_layers = true;  // SE_B200_SMALL_LAYERS=0: keep the two small-channel layers on the GEMM path (A/B switch)
     unsigned tc_mask = 0xffffffffu;  // SE_B200_TC_MASK: bit per Stage that may use the tensor-core GEMM (debug)
     std::map<int, cudaGraphExec_t> graphs;  // keyed by B
@@ -808,6 +811,7 @@ int build_ctx(se_ctx* c) {
     c->kblock = 128 / c->esz;
     if (const char* e = getenv("SE_B200_TC_MASK")) c->tc_mask = (unsigned)strtoul(e, nullptr, 0);
     if (const char* e = getenv("SE_B200_SMALL_LAYERS")) c->small_layers = atoi(e) != 0;
+    if (const char* e = getenv("SE_B200_GRU_PERSIST")) c->gru_persist = atoi(e) != 0;
     for (int i = 0; i < c->L; ++i) {
         SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
         SE_REQUIRE(!c->half || g.num_channels[i] % 8 == 0, "fp16 mode: num_channels must be multiples of 8");
@@ -915,6 +919,7 @@ int build_ctx(se_ctx* c) {
     c->n_stats = 3 + c->L + 1 + 2 * c->L;
     if (dev_alloc(c, &c->stats, (size_t)c->n_stats * 2 * maxB)) return 1;
     if (dev_alloc(c, &c->io_dev, 1)) return 1;
+    if (dev_alloc(c, &c->gru_counters, (size_t)2 * ((maxB + 127) / 128))) return 1;
 
     // ---- program ----------------------------------------------------------------------------------------------
     Builder b{c, {}};
@@ -1060,7 +1065,27 @@ int build_ctx(se_ctx* c) {
                 arena[pw.b_off + n] = bh[src];
             }
         });
-        for (int t = 0; t < T && fused; ++t) {
+        const bool persist = fused && c->half && c->gru_persist && gru_tc_persist_supported(H);
+        if (persist) {  // the whole recurrence of the layer: one persistent tensor-core kernel (gru_tc_persist.cu)
+            GemmParams gp{};
+            fill_gemm_common(c, gp, pw, 3 * H, k_off);
+            gp.epi = EPI_GRU;
+            b.meta("gru.l" + s + ".recurrence", 2.0 * T * 3 * H * H, 4.0 * T * (3 * H + 2 * H));
+            b.push_gemm(ST_GRU, gp, 1, pw, k_off);
+            Op& op = c->ops.back();
+            op.kind = OP_GRU_TC;
+            op.gru_layer = l;
+            op.gt = GruTcParams{};
+            op.gt.Kp = pw.K;
+            op.gt.gi = c->gi_l[l];
+            op.gt.giB = (long long)T * 3 * H;
+            op.gt.hseq = reinterpret_cast<__half*>(c->hseq[l]);
+            op.gt.hB = (long long)(T + 1) * H;
+            op.gt.h32 = c->h32[l];
+            op.gt.H = H;
+            op.gt.T = T;
+        }
+        for (int t = 0; t < T && fused && !persist; ++t) {
             GemmParams gp{};
             gp.A = c->E(c->hseq[l], (long long)t * H);
             gp.sB = (long long)(T + 1) * H;
@@ -1244,7 +1269,11 @@ int build_ctx(se_ctx* c) {
     for (size_t i = 0; i < c->ops.size(); ++i) {
         Op& op = c->ops[i];
         const OpFix& f = b.fix[i];
-        if (op.kind == OP_DECONV_LAST) {
+        if (op.kind == OP_GRU_TC) {
+            op.gt.Whh = reinterpret_cast<const __half*>(c->warena_h) + f.w_off;
+            op.gt.bhh = c->warena + f.b_off;
+            op.gt.counters = c->gru_counters + (size_t)op.gru_layer * ((c->maxB + 127) / 128);
+        } else if (op.kind == OP_DECONV_LAST) {
             op.dl.w = c->warena + f.w_off;
             op.dl.bias = c->warena + f.b_off;
         } else if (op.kind == OP_SKIP_SMALL) {
@@ -1365,6 +1394,11 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
             pc.b0 = 0;
             pc.B = B;
             return launch_preconv(pc, st);
+        }
+        case OP_GRU_TC: {
+            GruTcParams gt = op.gt;
+            gt.B = B;
+            return launch_gru_tc_persist(gt, st);
         }
         case OP_DECONV_LAST: {
             DeconvLastParams dl = op.dl;

@@ -305,6 +305,22 @@ bool skip_small_supported(int C);
 int launch_deconv_last(const DeconvLastParams& p, int Cin, cudaStream_t st);
 int launch_skip_small(const SkipSmallParams& p, int C, cudaStream_t st);
 
+// persistent tensor-core GRU recurrence of the streaming path (gru_tc_persist.cu; fp16 operand mode)
+struct GruTcParams {
+    const __half* Whh;   // packed as for EPI_GRU: row n = gate (n % 96) / 32 of unit 32 (n / 96) + n % 32; pitch Kp halves
+    int Kp;
+    const float* bhh;    // same row order
+    const float* gi;     // input projections incl. b_ih, PyTorch gate order: gi[b*giB + t*3H + {0,H,2H} + j]
+    long long giB;
+    __half* hseq;        // [B][T+1][H] fp16: slot t = operand of step t, slot t+1 = its result
+    long long hB;
+    float* h32;          // [B][H] fp32 master state, updated in place
+    int* counters;       // [ceil(B/128)] release/acquire counters of the m-tile groups (zeroed by the launcher)
+    int H, T, B;
+};
+bool gru_tc_persist_supported(int H);
+int launch_gru_tc_persist(const GruTcParams& p, cudaStream_t st);
+
 // persistent small-batch GRU recurrence (gru_seq.cu): one cooperative launch per layer for all chunks and steps
 struct GruSeqParams {
     const float* Whh;  // packed [3H][Kp], rows r | z | n (PyTorch order), b_hh separately
