@@ -231,19 +231,23 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_persist_kernel(GruTcParams
         const long long b = ok ? m : 0;
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
         float* h32 = p.h32 + b * p.H + j0;
+        // fp32 master state of this row's 32 units: lives in registers for the whole chunk
+        float4 ph[8];
+#pragma unroll
+        for (int v4 = 0; v4 < 8; ++v4)
+            ph[v4] = ok ? *(reinterpret_cast<const float4*>(h32) + v4) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int t = 0; t < p.T; ++t) {
             const float* gi = p.gi + b * p.giB + (long long)t * 3 * p.H + j0;
             __half* hout = p.hseq + b * p.hB + (long long)(t + 1) * p.H + j0;
             // the cell's other inputs do not depend on the MMAs: fetch all of them (4 x 128 bytes of this row) while the
             // operand loads and the MMA chain of this step run
-            float4 pr[8], pz[8], pn[8], ph[8];
+            float4 pr[8], pz[8], pn[8];
 #pragma unroll
             for (int v4 = 0; v4 < 8; ++v4) {
                 const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                 pr[v4] = ok ? __ldg(reinterpret_cast<const float4*>(gi) + v4) : z4;
                 pz[v4] = ok ? __ldg(reinterpret_cast<const float4*>(gi + p.H) + v4) : z4;
                 pn[v4] = ok ? __ldg(reinterpret_cast<const float4*>(gi + 2 * p.H) + v4) : z4;
-                ph[v4] = ok ? *(reinterpret_cast<const float4*>(h32) + v4) : z4;
             }
             mbar_wait(tfull_bar, (uint32_t)(t & 1));
             tc_fence_after();
@@ -271,9 +275,9 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_persist_kernel(GruTcParams
                     const float ng = fast_tanh(gn[i] + rg * (__uint_as_float(v[16 + i]) + s_bias[64 + u0 + i]));
                     hn[i] = (1.0f - zg) * ng + zg * hp[i];
                 }
+                ph[2 * c8] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                ph[2 * c8 + 1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
                 if (ok) {
-                    reinterpret_cast<float4*>(h32 + u0)[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    reinterpret_cast<float4*>(h32 + u0)[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
                     const __half2 h0 = __floats2half2_rn(hn[0], hn[1]), h1 = __floats2half2_rn(hn[2], hn[3]),
                                   h2 = __floats2half2_rn(hn[4], hn[5]), h3 = __floats2half2_rn(hn[6], hn[7]);
                     uint4 pk;
@@ -286,9 +290,15 @@ __global__ void __launch_bounds__(kThreads, 1) gru_tc_persist_kernel(GruTcParams
             }
             tc_fence_before();
             mbar_arrive(tempty_bar);  // accumulator drained: the MMAs of step t+1 may overwrite it
-            __threadfence();          // h_t of this thread's row is visible device-wide before the counter moves
+            // publish h_t: the named barrier orders the 128 rows' stores before the single release at gpu scope
+            // (cumulative), which the producers of the whole m-tile group acquire
             asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (warp == 5 && lane == 0) atomicAdd(p.counters + mt, 1);
+            if (warp == 5 && lane == 0)
+                asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p.counters + mt) : "memory");
+        }
+        if (ok) {
+#pragma unroll
+            for (int v4 = 0; v4 < 8; ++v4) reinterpret_cast<float4*>(h32)[v4] = ph[v4];
         }
     }
     tc_fence_before();
