@@ -160,10 +160,15 @@ constexpr int kW2Floats = 32 * 16 + 32;  // fused small gate: W2 [2*C2][16] + bi
 template <int BN>
 struct Cfg {
     static constexpr int NACC = BN > 128 ? 2 : 4;  // TMEM accumulators = epilogue groups
-    static constexpr int STAGES = BN > 128 ? 3 : (BN > 32 ? 4 : 6);
+    static constexpr int STAGES = BN > 128 ? 3 : (BN > 32 ? 4 : (BN == 16 ? 4 : 6));  // BN 16: room for the gate tiles
     static constexpr int WARPS = kFirstEpiWarp + 4 * NACC;
     static constexpr int THREADS = WARPS * 32;
-    static constexpr int TMEM_COLS_RAW = NACC * BN;
+    // back-to-back gate (BN == 16, fp16 operands): a second accumulator of 32 columns per group, the ELU tile as an
+    // fp16 A operand (128 rows x 128 B) per group and the 32 x 16 gate weights as a B operand (4 KB)
+    static constexpr int GATE_COLS = BN == 16 ? 32 : 0;
+    static constexpr int ETILE_BYTES = BN == 16 ? NACC * BM * BKB : 0;
+    static constexpr int W2T_BYTES = BN == 16 ? 32 * BKB : 0;
+    static constexpr int TMEM_COLS_RAW = NACC * (BN + GATE_COLS);
     static constexpr uint32_t TMEM_COLS =
         TMEM_COLS_RAW <= 32 ? 32
                             : (TMEM_COLS_RAW <= 64 ? 64 : (TMEM_COLS_RAW <= 128 ? 128 : (TMEM_COLS_RAW <= 256 ? 256 : 512)));
@@ -171,9 +176,11 @@ struct Cfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int KOFF_MAX = 512;  // K <= 2048
-    static constexpr int OFF_KOFF = TILE_BYTES;
+    static constexpr int OFF_ETILE = TILE_BYTES;               // 1024-aligned (SWIZZLE_128B atoms)
+    static constexpr int OFF_W2T = OFF_ETILE + ETILE_BYTES;    // 1024-aligned
+    static constexpr int OFF_KOFF = OFF_W2T + W2T_BYTES;
     static constexpr int OFF_BAR = OFF_KOFF + KOFF_MAX * 4;
-    static constexpr int NBAR = 2 * STAGES + 2 * NACC;
+    static constexpr int NBAR = 2 * STAGES + 2 * NACC + (BN == 16 ? NACC : 0);
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int OFF_W2 = (OFF_TMEM + 8 + 15) / 16 * 16;  // float [kW2Floats]
     static constexpr int OFF_BIAS = OFF_W2 + kW2Floats * 4;       // float [4*NACC warps][BN]: warp-private bias row
@@ -309,9 +316,23 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
     const AT* const Abase = reinterpret_cast<const AT*>(p.A);
     const AT* const Wbase = reinterpret_cast<const AT*>(p.W);
     const bool out_half = p.out_half != 0;
+    // back-to-back gate on the tensor core: fp16 operands only (the ELU tile is rounded to fp16 exactly as the unfused
+    // path rounds tmp_e); tf32 mode keeps the register version
+    const bool b2b = BN == 16 && p.epi == EPI_ELU_GATE && sizeof(AT) == 2;
     if (BN == 16 && p.epi == EPI_ELU_GATE) {
         for (int i = tid; i < 2 * p.C2 * 16; i += S::THREADS) s_w2[i] = __ldg(p.W2 + i);
         for (int i = tid; i < 2 * p.C2; i += S::THREADS) s_w2[32 * 16 + i] = __ldg(p.bias2 + i);
+        if (b2b) {  // W2 rows n = 2c (trans) / 2c+1 (gated), K = 16 inputs: chunk j (8 halves) of row n, rows >= 2 C2 zero
+            for (int u = tid; u < 32 * 2; u += S::THREADS) {
+                const int n = u >> 1, j = u & 1;
+                __align__(16) __half h[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(n < 2 * p.C2 ? __ldg(p.W2 + n * 16 + 8 * j + i) : 0.f);
+                *reinterpret_cast<uint4*>(tiles_ptr + S::OFF_W2T + (n >> 3) * 1024 + (n & 7) * 128 + ((j ^ (n & 7)) << 4)) =
+                    *reinterpret_cast<const uint4*>(h);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -321,6 +342,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
         for (int g = 0; g < NACC; ++g) {
             mbar_init(tfull_bar(g), 1);
             mbar_init(tempty_bar(g), BN == 96 ? 128 * NACC : 128);  // GRU tiles are read by every group
+            if (BN == 16) mbar_init(bar0 + 8u * (2 * STAGES + 2 * NACC + g), 1);  // gate MMA of group g finished
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -587,7 +609,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
                     __syncwarp();
                 }
             } else if (BN == 16 && p.epi == EPI_ELU_GATE) {
-                // conv + ELU, then the gated 1x1 pair of CRN_ELU.py:240 in registers (C2 <= 16 channels), + statistics
+                // conv + ELU, then the gated 1x1 pair of CRN_ELU.py:240 (C2 <= 16 channels), + statistics
                 uint32_t vr[16];
                 float e[16], y[16];
                 wait_acc();
@@ -597,8 +619,53 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
                 mbar_arrive(tempty_bar(acc));
 #pragma unroll
                 for (int i = 0; i < 16; ++i) e[i] = fast_elu(__uint_as_float(vr[i]) + sbias[i]);
-                if (p.C2 <= 8) small_gate<8>(s_w2, e, p.C2, y);
-                else small_gate<16>(s_w2, e, p.C2, y);
+                if (b2b) {
+                    // second GEMM on the tensor core: this row of the ELU tile as fp16 into the group's A-operand tile
+                    // (logical 16-byte chunks 0 and 1 of row r), one M128 x N32 x K16 MMA, gate on its 32 columns
+                    const int r = q * 32 + lane;
+                    unsigned char* et = tiles_ptr + S::OFF_ETILE + g * (BM * BKB) + (r >> 3) * 1024 + (r & 7) * 128;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const __half2 h0 = __floats2half2_rn(e[8 * j], e[8 * j + 1]), h1 = __floats2half2_rn(e[8 * j + 2], e[8 * j + 3]),
+                                      h2 = __floats2half2_rn(e[8 * j + 4], e[8 * j + 5]), h3 = __floats2half2_rn(e[8 * j + 6], e[8 * j + 7]);
+                        uint4 pk;
+                        pk.x = *reinterpret_cast<const uint32_t*>(&h0);
+                        pk.y = *reinterpret_cast<const uint32_t*>(&h1);
+                        pk.z = *reinterpret_cast<const uint32_t*>(&h2);
+                        pk.w = *reinterpret_cast<const uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(et + ((j ^ (r & 7)) << 4)) = pk;
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> MMA (async proxy)
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                    const uint32_t gate_bar = bar0 + 8u * (2 * STAGES + 2 * NACC + g);
+                    const uint32_t tgate = tmem_base + (uint32_t)(NACC * BN + g * 32);
+                    if ((ew & 3) == 0 && lane == 0) {
+                        tc_fence_after();
+                        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                        tc_mma<__half>(tgate, make_desc(tiles + S::OFF_ETILE + (uint32_t)g * (BM * BKB)),
+                                       make_desc(tiles + S::OFF_W2T), idesc2, 0u);
+                        tc_commit(gate_bar);
+                    }
+                    if ((ew & 3) == 0) mbar_wait<32>(gate_bar, (it / NACC) & 1);
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                    tc_fence_after();
+                    uint32_t gv[32];
+                    const uint32_t tg = tgate + ((uint32_t)(q * 32) << 16);
+                    tmem_ld16_nowait(tg, gv);
+                    tmem_ld16_nowait(tg + 16, gv + 16);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    const float* b2 = s_w2 + 32 * 16;
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        y[c] = c < p.C2 ? (__uint_as_float(gv[2 * c]) + b2[2 * c]) *
+                                              fast_sigmoid(__uint_as_float(gv[2 * c + 1]) + b2[2 * c + 1])
+                                        : 0.f;
+                } else if (p.C2 <= 8) {
+                    small_gate<8>(s_w2, e, p.C2, y);
+                } else {
+                    small_gate<16>(s_w2, e, p.C2, y);
+                }
                 if (row_ok) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
