@@ -184,6 +184,7 @@ struct se_ctx {
     }
     bool gru_persist = true;   // SE_B200_GRU_PERSIST=0: one GEMM launch per recurrent step instead of the persistent kernel
     int* gru_counters = nullptr;
+    bool b2b_gate = true;      // SE_B200_B2B=0: 32- / 64-channel gates as separate GEMMs
     bool small_layers = true;  // SE_B200_SMALL_LAYERS=0: keep the two small-channel layers on the GEMM path (A/B switch)
     unsigned tc_mask = 0xffffffffu;  // SE_B200_TC_MASK: bit per Stage that may use the tensor-core GEMM (debug)
     std::map<int, cudaGraphExec_t> graphs;  // keyed by B
@@ -435,7 +436,11 @@ struct Builder {
         const int Cp_in = in.C;
         const int Cp_out = round_up(Cout_real, 4);
         const int rows = T * Fo;
-        const bool fuse_gate = tc_stage(stage) && Cp_out <= 16 && !c->train;
+        // gate fused into the conv GEMM: in registers for <= 16 channels, as a back-to-back tensor-core GEMM (fp16 operands)
+        // for 32 / 64 channels (SE_B200_B2B=0 keeps those two levels on separate kernels)
+        const bool fuse_gate = tc_stage(stage) && !c->train &&
+                               (Cp_out <= 16 || (c->half && c->b2b_gate && (Cout_real == 32 || Cout_real == 64)));
+        const int w2_pitch = gemm_tf32_tile_n(Cout_real);
         double* stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
         float* const tmp_e = tmp_buf(c->tmp_e, (size_t)rows * Cp_out);
         float* const tmp_y = tmp_buf(c->tmp_y, (size_t)rows * Cp_out);
@@ -474,7 +479,7 @@ struct Builder {
             });
             size_t w2_off = NONE, b2_off = NONE;
             if (fuse_gate) {
-                w2_off = c->reserve_w((size_t)2 * Cout_real * 16);
+                w2_off = c->reserve_w((size_t)2 * Cout_real * w2_pitch);
                 b2_off = c->reserve_w((size_t)2 * Cout_real);
                 c->packers.push_back([=](const HostParams& hp, float* arena) {
                     const std::vector<float>& wt = hp.at(name + ".conv_trans.weight");
@@ -483,8 +488,8 @@ struct Builder {
                     const std::vector<float>& bg = hp.at(name + ".conv_gated.bias");
                     for (int co = 0; co < Cout_real; ++co) {
                         for (int ci = 0; ci < Cout_real; ++ci) {
-                            arena[w2_off + (size_t)(2 * co) * 16 + ci] = wt[co * Cout_real + ci];
-                            arena[w2_off + (size_t)(2 * co + 1) * 16 + ci] = wg[co * Cout_real + ci];
+                            arena[w2_off + (size_t)(2 * co) * w2_pitch + ci] = wt[co * Cout_real + ci];
+                            arena[w2_off + (size_t)(2 * co + 1) * w2_pitch + ci] = wg[co * Cout_real + ci];
                         }
                         arena[b2_off + 2 * co] = bt[co];
                         arena[b2_off + 2 * co + 1] = bg[co];
@@ -812,6 +817,7 @@ int build_ctx(se_ctx* c) {
     if (const char* e = getenv("SE_B200_TC_MASK")) c->tc_mask = (unsigned)strtoul(e, nullptr, 0);
     if (const char* e = getenv("SE_B200_SMALL_LAYERS")) c->small_layers = atoi(e) != 0;
     if (const char* e = getenv("SE_B200_GRU_PERSIST")) c->gru_persist = atoi(e) != 0;
+    if (const char* e = getenv("SE_B200_B2B")) c->b2b_gate = atoi(e) != 0;
     for (int i = 0; i < c->L; ++i) {
         SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
         SE_REQUIRE(!c->half || g.num_channels[i] % 8 == 0, "fp16 mode: num_channels must be multiples of 8");

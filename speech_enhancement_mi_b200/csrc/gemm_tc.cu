@@ -157,17 +157,19 @@ __device__ __forceinline__ void stats_commit(double* stats, int stride, int b, f
 
 constexpr int kW2Floats = 32 * 16 + 32;  // fused small gate: W2 [2*C2][16] + bias2 [2*C2], C2 <= 16
 
-template <int BN>
+// B2B: the kernel instance carries the back-to-back gate GEMM (EPI_ELU_GATE): always for BN = 16 (first encoder conv),
+// for BN = 32 / 64 only in the dedicated instances (fp16 operands) so that the plain GEMMs keep their deeper pipelines
+template <int BN, bool B2B = (BN == 16)>
 struct Cfg {
-    static constexpr int NACC = BN > 128 ? 2 : 4;  // TMEM accumulators = epilogue groups
-    static constexpr int STAGES = BN > 128 ? 3 : (BN > 32 ? 4 : (BN == 16 ? 4 : 6));  // BN 16: room for the gate tiles
+    static constexpr int NACC = (BN > 128 || (B2B && BN > 16)) ? 2 : 4;  // TMEM accumulators = epilogue groups
+    static constexpr int STAGES = BN > 128 ? 3 : (BN > 32 ? 4 : (B2B ? 4 : 6));  // B2B: room for the gate tiles
     static constexpr int WARPS = kFirstEpiWarp + 4 * NACC;
     static constexpr int THREADS = WARPS * 32;
     // back-to-back gate (BN == 16, fp16 operands): a second accumulator of 32 columns per group, the ELU tile as an
     // fp16 A operand (128 rows x 128 B) per group and the 32 x 16 gate weights as a B operand (4 KB)
-    static constexpr int GATE_COLS = BN == 16 ? 32 : 0;
-    static constexpr int ETILE_BYTES = BN == 16 ? NACC * BM * BKB : 0;
-    static constexpr int W2T_BYTES = BN == 16 ? 32 * BKB : 0;
+    static constexpr int GATE_COLS = B2B ? 2 * BN : 0;
+    static constexpr int ETILE_BYTES = B2B ? NACC * BM * BKB : 0;
+    static constexpr int W2T_BYTES = B2B ? 2 * BN * BKB : 0;
     static constexpr int TMEM_COLS_RAW = NACC * (BN + GATE_COLS);
     static constexpr uint32_t TMEM_COLS =
         TMEM_COLS_RAW <= 32 ? 32
@@ -180,7 +182,7 @@ struct Cfg {
     static constexpr int OFF_W2T = OFF_ETILE + ETILE_BYTES;    // 1024-aligned
     static constexpr int OFF_KOFF = OFF_W2T + W2T_BYTES;
     static constexpr int OFF_BAR = OFF_KOFF + KOFF_MAX * 4;
-    static constexpr int NBAR = 2 * STAGES + 2 * NACC + (BN == 16 ? NACC : 0);
+    static constexpr int NBAR = 2 * STAGES + 2 * NACC + (B2B ? NACC : 0);
     static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
     static constexpr int OFF_W2 = (OFF_TMEM + 8 + 15) / 16 * 16;  // float [kW2Floats]
     static constexpr int OFF_BIAS = OFF_W2 + kW2Floats * 4;       // float [4*NACC warps][BN]: warp-private bias row
@@ -282,11 +284,11 @@ __device__ __forceinline__ void small_gate(const float* s_w2, const float* e, in
     }
 }
 
-template <int BN, typename AT>
-__global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const GemmParams p) {
+template <int BN, typename AT, bool B2B = (BN == 16)>
+__global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1) gemm_tc_kernel(const GemmParams p) {
     constexpr int BKE = BKB / (int)sizeof(AT);  // elements per k-block
     constexpr int UE = 16 / (int)sizeof(AT);    // elements per 16-byte gather unit
-    using S = Cfg<BN>;
+    using S = Cfg<BN, B2B>;
     constexpr int STAGES = S::STAGES;
     constexpr int NACC = S::NACC;
     extern __shared__ unsigned char smem_raw[];
@@ -318,16 +320,20 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
     const bool out_half = p.out_half != 0;
     // back-to-back gate on the tensor core: fp16 operands only (the ELU tile is rounded to fp16 exactly as the unfused
     // path rounds tmp_e); tf32 mode keeps the register version
-    const bool b2b = BN == 16 && p.epi == EPI_ELU_GATE && sizeof(AT) == 2;
-    if (BN == 16 && p.epi == EPI_ELU_GATE) {
-        for (int i = tid; i < 2 * p.C2 * 16; i += S::THREADS) s_w2[i] = __ldg(p.W2 + i);
-        for (int i = tid; i < 2 * p.C2; i += S::THREADS) s_w2[32 * 16 + i] = __ldg(p.bias2 + i);
-        if (b2b) {  // W2 rows n = 2c (trans) / 2c+1 (gated), K = 16 inputs: chunk j (8 halves) of row n, rows >= 2 C2 zero
-            for (int u = tid; u < 32 * 2; u += S::THREADS) {
-                const int n = u >> 1, j = u & 1;
+    const bool b2b = B2B && p.epi == EPI_ELU_GATE && sizeof(AT) == 2;
+    // gate bias: behind the fp32 weights of the register version (BN = 16), else at the start of the same region
+    float* const s_b2 = BN == 16 ? s_w2 + 32 * 16 : s_w2;
+    if (B2B && p.epi == EPI_ELU_GATE) {
+        if (BN == 16)
+            for (int i = tid; i < 2 * p.C2 * 16; i += S::THREADS) s_w2[i] = __ldg(p.W2 + i);
+        for (int i = tid; i < 2 * p.C2; i += S::THREADS) s_b2[i] = __ldg(p.bias2 + i);
+        if (b2b) {  // W2 [2 C2][BN] fp32, rows n = 2c (trans) / 2c+1 (gated): chunk j (8 halves) of row n, rows >= 2 C2 zero
+            constexpr int CPR = BN / 8;  // 16-byte chunks per row
+            for (int u = tid; u < 2 * BN * CPR; u += S::THREADS) {
+                const int n = u / CPR, j = u % CPR;
                 __align__(16) __half h[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(n < 2 * p.C2 ? __ldg(p.W2 + n * 16 + 8 * j + i) : 0.f);
+                for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(n < 2 * p.C2 ? __ldg(p.W2 + n * BN + 8 * j + i) : 0.f);
                 *reinterpret_cast<uint4*>(tiles_ptr + S::OFF_W2T + (n >> 3) * 1024 + (n & 7) * 128 + ((j ^ (n & 7)) << 4)) =
                     *reinterpret_cast<const uint4*>(h);
             }
@@ -342,7 +348,7 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
         for (int g = 0; g < NACC; ++g) {
             mbar_init(tfull_bar(g), 1);
             mbar_init(tempty_bar(g), BN == 96 ? 128 * NACC : 128);  // GRU tiles are read by every group
-            if (BN == 16) mbar_init(bar0 + 8u * (2 * STAGES + 2 * NACC + g), 1);  // gate MMA of group g finished
+            if (B2B) mbar_init(bar0 + 8u * (2 * STAGES + 2 * NACC + g), 1);  // gate MMA of group g finished
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -608,22 +614,25 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
                     }
                     __syncwarp();
                 }
-            } else if (BN == 16 && p.epi == EPI_ELU_GATE) {
-                // conv + ELU, then the gated 1x1 pair of CRN_ELU.py:240 (C2 <= 16 channels), + statistics
-                uint32_t vr[16];
-                float e[16], y[16];
+            } else if (B2B && p.epi == EPI_ELU_GATE && (BN > 16 || b2b)) {
+                // conv + ELU, then the gated 1x1 pair of CRN_ELU.py:240 as a SECOND GEMM on the tensor core: this row of
+                // the ELU tile goes as fp16 into the group's A-operand tile (logical 16-byte chunks 0 .. BN/8-1 of row r),
+                // BN/16 MMAs M128 x N(2 BN) x K16 against the resident gate weights, gate on the 2 BN result columns
+                const int r = q * 32 + lane;
+                unsigned char* et = tiles_ptr + S::OFF_ETILE + g * (BM * BKB) + (r >> 3) * 1024 + (r & 7) * 128;
                 wait_acc();
-                tmem_ld16_nowait(tlane, vr);
-                tmem_ld_wait();
-                tc_fence_before();
-                mbar_arrive(tempty_bar(acc));
 #pragma unroll
-                for (int i = 0; i < 16; ++i) e[i] = fast_elu(__uint_as_float(vr[i]) + sbias[i]);
-                if (b2b) {
-                    // second GEMM on the tensor core: this row of the ELU tile as fp16 into the group's A-operand tile
-                    // (logical 16-byte chunks 0 and 1 of row r), one M128 x N32 x K16 MMA, gate on its 32 columns
-                    const int r = q * 32 + lane;
-                    unsigned char* et = tiles_ptr + S::OFF_ETILE + g * (BM * BKB) + (r >> 3) * 1024 + (r & 7) * 128;
+                for (int c0 = 0; c0 < BN; c0 += 16) {
+                    uint32_t vr[16];
+                    tmem_ld16_nowait(tlane + c0, vr);
+                    tmem_ld_wait();
+                    if (c0 + 16 >= BN) {  // conv accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        mbar_arrive(tempty_bar(acc));
+                    }
+                    float e[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) e[i] = fast_elu(__uint_as_float(vr[i]) + sbias[c0 + i]);
 #pragma unroll
                     for (int j = 0; j < 2; ++j) {
                         const __half2 h0 = __floats2half2_rn(e[8 * j], e[8 * j + 1]), h1 = __floats2half2_rn(e[8 * j + 2], e[8 * j + 3]),
@@ -633,39 +642,70 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
                         pk.y = *reinterpret_cast<const uint32_t*>(&h1);
                         pk.z = *reinterpret_cast<const uint32_t*>(&h2);
                         pk.w = *reinterpret_cast<const uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(et + ((j ^ (r & 7)) << 4)) = pk;
+                        *reinterpret_cast<uint4*>(et + (((c0 / 8 + j) ^ (r & 7)) << 4)) = pk;
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> MMA (async proxy)
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-                    const uint32_t gate_bar = bar0 + 8u * (2 * STAGES + 2 * NACC + g);
-                    const uint32_t tgate = tmem_base + (uint32_t)(NACC * BN + g * 32);
-                    if ((ew & 3) == 0 && lane == 0) {
-                        tc_fence_after();
-                        constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-                        tc_mma<__half>(tgate, make_desc(tiles + S::OFF_ETILE + (uint32_t)g * (BM * BKB)),
-                                       make_desc(tiles + S::OFF_W2T), idesc2, 0u);
-                        tc_commit(gate_bar);
-                    }
-                    if ((ew & 3) == 0) mbar_wait<32>(gate_bar, (it / NACC) & 1);
-                    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> MMA (async proxy)
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                const uint32_t gate_bar = bar0 + 8u * (2 * STAGES + 2 * NACC + g);
+                const uint32_t tgate = tmem_base + (uint32_t)(NACC * BN + g * 2 * BN);
+                if ((ew & 3) == 0 && lane == 0) {
                     tc_fence_after();
+                    constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                    const uint64_t ad = make_desc(tiles + S::OFF_ETILE + (uint32_t)g * (BM * BKB));
+                    const uint64_t bd = make_desc(tiles + S::OFF_W2T);
+#pragma unroll
+                    for (int kk = 0; kk < BN / 16; ++kk)
+                        tc_mma<__half>(tgate, ad + (uint64_t)(2 * kk), bd + (uint64_t)(2 * kk), idesc2, kk ? 1u : 0u);
+                    tc_commit(gate_bar);
+                }
+                if ((ew & 3) == 0) mbar_wait<32>(gate_bar, (it / NACC) & 1);
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                tc_fence_after();
+                const uint32_t tg = tgate + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+                for (int c0 = 0; c0 < 2 * BN; c0 += 32) {  // 32 gate columns = 16 output channels per pass
                     uint32_t gv[32];
-                    const uint32_t tg = tgate + ((uint32_t)(q * 32) << 16);
-                    tmem_ld16_nowait(tg, gv);
-                    tmem_ld16_nowait(tg + 16, gv + 16);
+                    tmem_ld16_nowait(tg + c0, gv);
+                    tmem_ld16_nowait(tg + c0 + 16, gv + 16);
                     tmem_ld_wait();
-                    tc_fence_before();
-                    const float* b2 = s_w2 + 32 * 16;
+                    const int ch0 = c0 / 2;
+                    float y[16];
 #pragma unroll
                     for (int c = 0; c < 16; ++c)
-                        y[c] = c < p.C2 ? (__uint_as_float(gv[2 * c]) + b2[2 * c]) *
-                                              fast_sigmoid(__uint_as_float(gv[2 * c + 1]) + b2[2 * c + 1])
-                                        : 0.f;
-                } else if (p.C2 <= 8) {
-                    small_gate<8>(s_w2, e, p.C2, y);
-                } else {
-                    small_gate<16>(s_w2, e, p.C2, y);
+                        y[c] = ch0 + c < p.C2 ? (__uint_as_float(gv[2 * c]) + s_b2[c0 + 2 * c]) *
+                                                    fast_sigmoid(__uint_as_float(gv[2 * c + 1]) + s_b2[c0 + 2 * c + 1])
+                                              : 0.f;
+                    if (row_ok) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            s_acc += y[i];
+                            ss_acc += y[i] * y[i];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        *reinterpret_cast<float4*>(srow + i) = make_float4(y[i], y[i + 1], y[i + 2], y[i + 3]);
+                    __syncwarp();
+                    float* outp = out_half ? reinterpret_cast<float*>(reinterpret_cast<__half*>(p.out) + ch0) : p.out + ch0;
+                    store_chunk<16>(stg, 0, outp, ooff, min(16, p.C2 - ch0), vec4, lane, out_half);
+                    __syncwarp();
                 }
+                tc_fence_before();
+                stats_commit(p.stats, p.stats_stride ? p.stats_stride : 2, b, s_acc, ss_acc);
+            } else if (BN == 16 && p.epi == EPI_ELU_GATE) {
+                // tf32 mode: conv + ELU, then the gated 1x1 pair in registers (C2 <= 16 channels), + statistics
+                uint32_t vr[16];
+                float e[16], y[16];
+                wait_acc();
+                tmem_ld16_nowait(tlane, vr);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(tempty_bar(acc));
+#pragma unroll
+                for (int i = 0; i < 16; ++i) e[i] = fast_elu(__uint_as_float(vr[i]) + sbias[i]);
+                if (p.C2 <= 8) small_gate<8>(s_w2, e, p.C2, y);
+                else small_gate<16>(s_w2, e, p.C2, y);
                 if (row_ok) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -787,12 +827,12 @@ __global__ void __launch_bounds__(Cfg<BN>::THREADS, 1) gemm_tc_kernel(const Gemm
 
 int g_num_sms = 0;
 
-template <int BN, typename AT>
+template <int BN, typename AT, bool B2B = (BN == 16)>
 int launch_tc(const GemmParams& p, cudaStream_t st) {
-    using S = Cfg<BN>;
+    using S = Cfg<BN, B2B>;
     static bool configured = false;
     if (!configured) {
-        SE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
+        SE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AT, B2B>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
         configured = true;
     }
     if (g_num_sms == 0) {
@@ -802,7 +842,7 @@ int launch_tc(const GemmParams& p, cudaStream_t st) {
     }
     const int ntiles = ((p.M + BM - 1) / BM) * ((p.epi == EPI_GRU ? p.N : p.Npad) / BN);
     const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;  // persistent: one CTA per SM
-    gemm_tc_kernel<BN, AT><<<grid, S::THREADS, S::BYTES, st>>>(p);
+    gemm_tc_kernel<BN, AT, B2B><<<grid, S::THREADS, S::BYTES, st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -811,6 +851,8 @@ template <typename AT>
 int launch_elem(const GemmParams& p, cudaStream_t st) {
     if (p.epi == EPI_GRU) return launch_tc<96, AT>(p, st);
     if (p.epi == EPI_LSTM) return p.lstm_units == 64 ? launch_tc<256, AT>(p, st) : launch_tc<128, AT>(p, st);
+    if (p.epi == EPI_ELU_GATE && sizeof(AT) == 2 && p.Npad == 32) return launch_tc<32, AT, true>(p, st);
+    if (p.epi == EPI_ELU_GATE && sizeof(AT) == 2 && p.Npad == 64) return launch_tc<64, AT, true>(p, st);
     switch (gemm_tf32_tile_n(p.N)) {
         case 16: return launch_tc<16, AT>(p, st);
         case 32: return launch_tc<32, AT>(p, st);
@@ -830,7 +872,9 @@ bool gemm_tf32_supported(const GemmParams& p) {
         return p.H % (p.lstm_units == 64 ? 64 : 32) == 0 && (p.lstm_units == 0 || p.lstm_units == 32 || p.lstm_units == 64) &&
                p.Tn == 1 && p.Fo == 1 && p.N == 4 * p.H && p.Npad == p.N;
     if (p.Npad % gemm_tf32_tile_n(p.N) != 0) return false;
-    if (p.epi == EPI_ELU_GATE) return p.Npad == 16 && p.C2 >= 1 && p.C2 <= 16 && p.W2 && p.bias2;
+    if (p.epi == EPI_ELU_GATE)  // register version: N <= 16; back-to-back tensor-core version (fp16 operands): N <= 64
+        return (p.Npad == 16 || (p.a_half && (p.Npad == 32 || p.Npad == 64))) && p.C2 >= 1 && p.C2 <= p.Npad && p.W2 &&
+               p.bias2;
     if (p.epi == EPI_SKIP && (p.o2B != p.oB || p.o2T != p.oT || p.o2F != p.oF)) return false;
     if (p.vec4 && ((p.oF % 4) || (p.oT % 4) || (p.oB % 4))) return false;
     return p.N >= 1;
