@@ -50,7 +50,7 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
     long long per_stream() const { return sB; }
 };
 
-enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ, OP_DECONV_LAST, OP_SKIP_SMALL, OP_GRU_TC };
+enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ, OP_DECONV_LAST, OP_SKIP_SMALL, OP_GRU_TC, OP_PRECONV_TC };
 enum Stage { ST_STFT = 0, ST_PRECONV, ST_ENCODER, ST_GRU, ST_DECODER, ST_MASK, ST_ROLL, ST_COUNT };
 const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"};
 
@@ -67,6 +67,7 @@ struct Op {
     DeconvLastParams dl;
     SkipSmallParams sk;
     GruTcParams gt;
+    PreconvTcParams pt;
     int small_c = 0;  // channel count of the two small-layer kernels
     // GRU pointwise
     const float* gi = nullptr;
@@ -184,6 +185,11 @@ struct se_ctx {
     }
     bool gru_persist = true;   // SE_B200_GRU_PERSIST=0: one GEMM launch per recurrent step instead of the persistent kernel
     int* gru_counters = nullptr;
+    // SE_B200_PRECONV_TC=1 (fp16 mode): pre-convolutions on the tensor cores (preconv_tc.cu: implicit conv through
+    // shifted no-swizzle UMMA descriptors).  Correct, but 0.43 ms per layer against 0.23 ms for the CUDA-core kernel --
+    // an M128 x N16 x K16 MMA costs ~100 cycles whatever its size -- so it stays opt-in.
+    bool preconv_tc = false;
+    __half* pre_h[3] = {nullptr, nullptr, nullptr};  // tensor-core pre-convolution inputs [maxB][25][272][8] halves
     bool b2b_gate = true;      // SE_B200_B2B=0: 32- / 64-channel gates as separate GEMMs
     bool small_layers = true;  // SE_B200_SMALL_LAYERS=0: keep the two small-channel layers on the GEMM path (A/B switch)
     unsigned tc_mask = 0xffffffffu;  // SE_B200_TC_MASK: bit per Stage that may use the tensor-core GEMM (debug)
@@ -818,6 +824,8 @@ int build_ctx(se_ctx* c) {
     if (const char* e = getenv("SE_B200_SMALL_LAYERS")) c->small_layers = atoi(e) != 0;
     if (const char* e = getenv("SE_B200_GRU_PERSIST")) c->gru_persist = atoi(e) != 0;
     if (const char* e = getenv("SE_B200_B2B")) c->b2b_gate = atoi(e) != 0;
+    if (const char* e = getenv("SE_B200_PRECONV_TC")) c->preconv_tc = atoi(e) != 0;
+    c->preconv_tc = c->preconv_tc && c->half && !c->train;
     for (int i = 0; i < c->L; ++i) {
         SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
         SE_REQUIRE(!c->half || g.num_channels[i] % 8 == 0, "fp16 mode: num_channels must be multiples of 8");
@@ -838,7 +846,11 @@ int build_ctx(se_ctx* c) {
     const int C0p = 8;
     const int H = c->H;
     // ---- activations ------------------------------------------------------------------------------------------
-    c->pre_in.resize(c->train ? 0 : 3);
+    const long long pre_h_sB = (long long)PRECONV_TP * PRECONV_TC_POS * 8;  // halves per stream
+    if (c->preconv_tc)
+        for (int i = 0; i < 3; ++i)
+            if (dev_alloc(c, &c->pre_h[i], (size_t)pre_h_sB * maxB)) return 1;
+    c->pre_in.resize((c->train || c->preconv_tc) ? 0 : 3);
     for (int i = 0; i < (int)c->pre_in.size(); ++i) {
         PreBuf& pb = c->pre_in[i];
         pb.d = 1 << i;
@@ -937,7 +949,56 @@ int build_ctx(se_ctx* c) {
                      nx.interior(), nx.sB, nx.sT, nx.sF, true, slot++, i, nx.dinterior());
         c->conv_recs.back().need_dgrad = i > 0;
     }
-    for (int i = 0; i < 3 && !c->train; ++i) {  // pre-convolutions: one fused kernel per layer (preconv.cu), exact fp32 in both modes
+    for (int i = 0; i < 3 && c->preconv_tc; ++i) {  // fp16 mode: pre-convolutions on the tensor cores (preconv_tc.cu)
+        const std::string name = "preconvlist." + std::to_string(i);
+        const size_t w_off = c->reserve_w(PRECONV_W_FLOATS);
+        c->packers.push_back([=](const HostParams& hp, float* arena) {
+            const std::vector<float>& w = hp.at(name + ".conv.weight");  // [Co][Ci][KF][KT]
+            float* a = arena + w_off;
+            for (int kt = 0; kt < 5; ++kt)
+                for (int ci = 0; ci < 5; ++ci)
+                    for (int kf = 0; kf < 5; ++kf)
+                        for (int co = 0; co < 5; ++co)
+                            a[(kt * 5 + ci) * 28 + kf * 5 + co] = w[((co * 5 + ci) * 5 + kf) * 5 + kt];
+            for (int co = 0; co < 5; ++co) {
+                a[PRECONV_W_BIAS + co] = hp.at(name + ".conv.bias")[co];
+                for (int k = 0; k < 5; ++k) {
+                    a[PRECONV_W_WT + co * 5 + k] = hp.at(name + ".conv_trans.weight")[co * 5 + k];
+                    a[PRECONV_W_WG + co * 5 + k] = hp.at(name + ".conv_gated.weight")[co * 5 + k];
+                }
+                a[PRECONV_W_BT + co] = hp.at(name + ".conv_trans.bias")[co];
+                a[PRECONV_W_BG + co] = hp.at(name + ".conv_gated.bias")[co];
+                a[PRECONV_W_NW + co] = hp.at(name + ".norm.weight")[co];
+                a[PRECONV_W_NB + co] = hp.at(name + ".norm.bias")[co];
+            }
+        });
+        Op op{};
+        op.kind = OP_PRECONV_TC;
+        op.stage = ST_PRECONV;
+        op.pt.in = c->pre_h[i];
+        op.pt.in_sB = pre_h_sB;
+        op.pt.d = 1 << i;
+        op.pt.student = c->student;
+        if (i < 2) {
+            op.pt.out = c->pre_h[i + 1] + (4LL * PRECONV_TC_POS + 2 * (2 << i)) * 8;  // frame 4, bin 0 of the next layer
+            op.pt.oB = pre_h_sB;
+            op.pt.oT = (long long)PRECONV_TC_POS * 8;
+            op.pt.oF = 8;
+        } else {
+            const Act& nx = c->enc_in[0];
+            op.pt.out = reinterpret_cast<__half*>(nx.interior());
+            op.pt.oB = nx.sB;
+            op.pt.oT = nx.sT;
+            op.pt.oF = nx.sF;
+        }
+        op.label = name + ".fused";
+        op.alg_flops = 2.0 * T * NBIN * 5 * (125 + 10);
+        op.alg_bytes = 2.0 * 8 * NBIN * (PRECONV_TP + T);
+        c->ops.push_back(op);
+        b.fix.push_back({NONE, NONE, -1, w_off, NONE, NONE, NONE});
+        slot++;
+    }
+    for (int i = 0; i < 3 && !c->train && !c->preconv_tc; ++i) {  // pre-convolutions: one fused kernel per layer (preconv.cu), exact fp32
         const PreBuf& in = c->pre_in[i];
         const std::string name = "preconvlist." + std::to_string(i);
         const size_t w_off = c->reserve_w(PRECONV_W_FLOATS);
@@ -1294,6 +1355,8 @@ int build_ctx(se_ctx* c) {
                 op.g.W2 = c->warena + f.w2_off;
                 op.g.bias2 = c->warena + f.b2_off;
             }
+        } else if (op.kind == OP_PRECONV_TC) {
+            op.pt.w = c->warena + f.nw_off;
         } else if (op.kind == OP_PRECONV) {
             op.pc.w = c->warena + f.nw_off;
         } else if (op.kind == OP_NORM) {
@@ -1318,6 +1381,11 @@ int build_ctx(se_ctx* c) {
     };
     if (c->train)
         for (const Act& a : c->pre_act) add_state(a.base, a.sB, (long long)T * a.sT, (int)(a.padT0 * a.sT));
+    for (int i = 0; i < 3 && c->preconv_tc; ++i) {  // rolled by the kernel itself; a reset clears the whole slab
+        RollEntry e{reinterpret_cast<float*>(c->pre_h[i]), pre_h_sB / 2, 0, 0, (int)(pre_h_sB / 2)};
+        c->zero_tab.e[c->zero_tab.n++] = e;
+        c->state_floats += 5 * 4 * NBIN;
+    }
     for (const PreBuf& pb : c->pre_in) {  // rolled by the preconv kernel itself; a reset clears the whole slab
         RollEntry e{pb.base, pb.sB, 0, 0, (int)pb.sB};
         c->zero_tab.e[c->zero_tab.n++] = e;
@@ -1401,6 +1469,12 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
             pc.B = B;
             return launch_preconv(pc, st);
         }
+        case OP_PRECONV_TC: {
+            PreconvTcParams pt = op.pt;
+            pt.b0 = 0;
+            pt.B = B;
+            return launch_preconv_tc(pt, st);
+        }
         case OP_GRU_TC: {
             GruTcParams gt = op.gt;
             gt.B = B;
@@ -1444,12 +1518,19 @@ int enqueue_stream_step(se_ctx* c, int B, cudaStream_t st, int stage_filter = -1
         sp.B = B;
         sp.M = 3;
         sp.student = c->student;
-        const PreBuf& a = c->pre_in[0];
-        sp.feat = a.interior();
-        sp.fB = a.sB;
-        sp.fC = a.sC;
-        sp.fT = a.Fpp;
-        sp.fF = 1;
+        if (c->preconv_tc) {
+            sp.feat_h8 = c->pre_h[0] + (4LL * PRECONV_TC_POS + 2) * 8;  // frame 4, bin 0 (dilation 1: position 2)
+            sp.fB = (long long)PRECONV_TP * PRECONV_TC_POS * 8;
+            sp.fT = (long long)PRECONV_TC_POS * 8;
+            sp.fF = 8;
+        } else {
+            const PreBuf& a = c->pre_in[0];
+            sp.feat = a.interior();
+            sp.fB = a.sB;
+            sp.fC = a.sC;
+            sp.fT = a.Fpp;
+            sp.fF = 1;
+        }
         sp.noisy = c->noisy;
         if (launch_stft_features(sp, st)) return 1;
     }
@@ -2099,8 +2180,15 @@ int se_crn_forward_chunk(se_ctx* c, const float* spec_in, float* spec_out, int B
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     SE_CUDA_OK(cudaMemsetAsync(c->stats, 0, (size_t)c->n_stats * 2 * c->maxB * sizeof(double), st));
-    const PreBuf& a = c->pre_in[0];
-    if (launch_features_from_spec(spec_in, B, 3, c->student, a.interior(), a.sB, a.sC, a.Fpp, 1, c->noisy, st)) return 1;
+    if (c->preconv_tc) {
+        if (launch_features_from_spec(spec_in, B, 3, c->student, nullptr, (long long)PRECONV_TP * PRECONV_TC_POS * 8, 0,
+                                      (long long)PRECONV_TC_POS * 8, 8, c->noisy, st,
+                                      c->pre_h[0] + (4LL * PRECONV_TC_POS + 2) * 8))
+            return 1;
+    } else {
+        const PreBuf& a = c->pre_in[0];
+        if (launch_features_from_spec(spec_in, B, 3, c->student, a.interior(), a.sB, a.sC, a.Fpp, 1, c->noisy, st)) return 1;
+    }
     if (enqueue_net(c, B, st, -1)) return 1;
     MaskIstftParams mp{};
     mp.B = B;
@@ -2165,7 +2253,21 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
         return (i >= 0 && i < limit) ? i : -1;
     };
     int i;
-    if ((i = idx_of("pre_in", 3)) >= 0 && c->train) {
+    if ((i = idx_of("pre_in", 3)) >= 0 && c->preconv_tc) {  // channels-last fp16 units -> [T][F][5] on the host
+        dims[0] = T;
+        dims[1] = NBIN;
+        dims[2] = 5;
+        SE_REQUIRE((int64_t)T * NBIN * 5 <= max_floats, "se_debug_read: destination too small");
+        const size_t n = (size_t)PRECONV_TP * PRECONV_TC_POS * 8;
+        std::vector<__half> slab(n);
+        SE_CUDA_OK(cudaMemcpy(slab.data(), c->pre_h[i] + (size_t)b * n, n * sizeof(__half), cudaMemcpyDeviceToHost));
+        for (int tt = 0; tt < T; ++tt)
+            for (int ff = 0; ff < NBIN; ++ff)
+                for (int cc = 0; cc < 5; ++cc)
+                    host_dst[((size_t)tt * NBIN + ff) * 5 + cc] =
+                        __half2float(slab[((size_t)(tt + 4) * PRECONV_TC_POS + ff + 2 * (1 << i)) * 8 + cc]);
+        return 0;
+    } else if ((i = idx_of("pre_in", 3)) >= 0 && c->train) {
         from_act(c->pre_act[i]);
     } else if ((i = idx_of("pre_in", 3)) >= 0) {  // planar -> [T][F][5] on the host
         const PreBuf& pb = c->pre_in[i];

@@ -8,6 +8,7 @@
 //             of torch.fft.irfft inside torch.istft).
 // Reference call sites: CRN_ELU.py:417-424 (stft_trans), :369-373 (features), :401-405 + utility.py:439-442 (mask),
 // CRN_ELU.py:426-432 (istft_trans), utility.py:393-403 (over_add).
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include <vector>
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
             *dst = v;
         }
     }
-    if (p.feat != nullptr) {
+    if (p.feat != nullptr || p.feat_h8 != nullptr) {
         for (int o = tid; o < GROUP * NBIN; o += blockDim.x) {
             const int k = o % NBIN;
             const int fr = o / NBIN;
@@ -161,12 +162,23 @@ __global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
                 ph[m] = p.student ? atanf(v.y / (v.x + 1e-8f) + 1e-8f)  // distillation_crn.py:340
                                   : atan2f(v.y, v.x);                   // CRN_ELU.py:370
             }
-            float* f = p.feat + b * p.fB + t * p.fT + k * p.fF;
-            f[0] = mag[0];
-            f[p.fC] = mag[1];
-            f[2 * p.fC] = mag[2];
-            f[3 * p.fC] = ph[0] - ph[1];
-            f[4 * p.fC] = ph[0] - ph[2];
+            if (p.feat_h8 != nullptr) {
+                const __half2 h0 = __floats2half2_rn(mag[0], mag[1]), h1 = __floats2half2_rn(mag[2], ph[0] - ph[1]),
+                              h2 = __floats2half2_rn(ph[0] - ph[2], 0.f);
+                uint4 u;
+                u.x = *reinterpret_cast<const unsigned*>(&h0);
+                u.y = *reinterpret_cast<const unsigned*>(&h1);
+                u.z = *reinterpret_cast<const unsigned*>(&h2);
+                u.w = 0u;
+                *reinterpret_cast<uint4*>(p.feat_h8 + b * p.fB + t * p.fT + k * p.fF) = u;
+            } else {
+                float* f = p.feat + b * p.fB + t * p.fT + k * p.fF;
+                f[0] = mag[0];
+                f[p.fC] = mag[1];
+                f[2 * p.fC] = mag[2];
+                f[3 * p.fC] = ph[0] - ph[1];
+                f[4 * p.fC] = ph[0] - ph[2];
+            }
             reinterpret_cast<float2*>(p.noisy)[((long long)b * T + t) * NBIN + k] = s.spec[0][fr][k];
         }
     }
@@ -176,7 +188,7 @@ __global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
 __global__ void __launch_bounds__(256) features_from_spec_kernel(const float* __restrict__ spec, int B, int M,
                                                                  int student, float* __restrict__ feat, long long fB,
                                                                  long long fC, long long fT, long long fF,
-                                                                 float* __restrict__ noisy) {
+                                                                 float* __restrict__ noisy, __half* feat_h8) {
     const long long total = (long long)B * T * NBIN;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -192,12 +204,23 @@ __global__ void __launch_bounds__(256) features_from_spec_kernel(const float* __
             mag[m] = sqrtf(v.x * v.x + v.y * v.y + 1e-10f);
             ph[m] = student ? atanf(v.y / (v.x + 1e-8f) + 1e-8f) : atan2f(v.y, v.x);
         }
-        float* f = feat + b * fB + t * fT + k * fF;
-        f[0] = mag[0];
-        f[fC] = mag[1];
-        f[2 * fC] = mag[2];
-        f[3 * fC] = ph[0] - ph[1];
-        f[4 * fC] = ph[0] - ph[2];
+        if (feat_h8 != nullptr) {
+            const __half2 h0 = __floats2half2_rn(mag[0], mag[1]), h1 = __floats2half2_rn(mag[2], ph[0] - ph[1]),
+                          h2 = __floats2half2_rn(ph[0] - ph[2], 0.f);
+            uint4 u;
+            u.x = *reinterpret_cast<const unsigned*>(&h0);
+            u.y = *reinterpret_cast<const unsigned*>(&h1);
+            u.z = *reinterpret_cast<const unsigned*>(&h2);
+            u.w = 0u;
+            *reinterpret_cast<uint4*>(feat_h8 + b * fB + t * fT + k * fF) = u;
+        } else {
+            float* f = feat + b * fB + t * fT + k * fF;
+            f[0] = mag[0];
+            f[fC] = mag[1];
+            f[2 * fC] = mag[2];
+            f[3 * fC] = ph[0] - ph[1];
+            f[4 * fC] = ph[0] - ph[2];
+        }
         reinterpret_cast<float2*>(noisy)[((long long)b * T + t) * NBIN + k] = v0;
     }
 }
@@ -469,7 +492,8 @@ int init_fft_tables() {
 
 int launch_stft_features(const StftParams& p, cudaStream_t st) {
     SE_REQUIRE(p.M >= 1 && p.M <= 3, "stft: at most 3 microphones per launch");
-    SE_REQUIRE(p.feat == nullptr || p.M == 3, "stft features need exactly 3 microphones (CRN_ELU.py:369-373)");
+    SE_REQUIRE((p.feat == nullptr && p.feat_h8 == nullptr) || p.M == 3,
+               "stft features need exactly 3 microphones (CRN_ELU.py:369-373)");
     if (p.B == 0) return 0;
     stft_features_kernel<<<dim3(p.B, T / GROUP), 224, sizeof(StftSmem), st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
@@ -477,13 +501,13 @@ int launch_stft_features(const StftParams& p, cudaStream_t st) {
 }
 
 int launch_features_from_spec(const float* spec, int B, int M, int student, float* feat, long long fB, long long fC,
-                              long long fT, long long fF, float* noisy, cudaStream_t st) {
+                              long long fT, long long fF, float* noisy, cudaStream_t st, __half* feat_h8) {
     SE_REQUIRE(M == 3, "features need exactly 3 microphones (CRN_ELU.py:369-373)");
     if (B == 0) return 0;
     const long long total = (long long)B * T * NBIN;
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    features_from_spec_kernel<<<grid, 256, 0, st>>>(spec, B, M, student, feat, fB, fC, fT, fF, noisy);
+    features_from_spec_kernel<<<grid, 256, 0, st>>>(spec, B, M, student, feat, fB, fC, fT, fF, noisy, feat_h8);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }

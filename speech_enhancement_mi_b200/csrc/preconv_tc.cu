@@ -1,0 +1,309 @@
+// Pre-convolution block (CRN_ELU.py:337-339,375-376) on the tensor cores, fp16 operand mode: 5x5 frequency-dilated
+// causal conv (5 -> 5 channels) + ELU + gated 1x1 + GlobalLayerNorm + residual + causal state roll, one persistent CTA
+// per stream at a time.
+//
+// No im2col is ever materialised.  The whole zero-bordered input of the chunk sits in shared memory channels-last,
+// X[25 frames][272 positions][8 halves] (one 16-byte unit per (frame, bin); bin f at position f + 2d), and a conv tap is
+// just a SHIFT of that buffer: for the 128 consecutive output bins of a tile, tap (kt, kf) reads the 128 consecutive
+// units starting at X[t + kt][f0 + kf d].  In the canonical K-major no-swizzle UMMA layout -- ((8, n), 2):((16 B, SBO),
+// LBO) -- eight consecutive units are one core matrix, SBO = 128 B walks the 8-row groups and LBO, the distance between
+// the two 16-byte K chunks of one MMA, is free: one tcgen05.mma (M128 x N16 x K16) consumes TWO taps, the first chunk at
+// the descriptor's start address, the second LBO bytes further.  13 MMAs per tile of 128 bins instead of 80,000 FMAs.
+//
+// GlobalLayerNorm needs the statistics of the whole stream before anything can be written, and 4221 x 5 pre-norm values
+// do not fit beside the input: the conv is simply issued twice (pass 1: statistics, pass 2: normalise + residual +
+// store) -- the tensor work is free, the epilogue (ELU, 5x5 gate) costs ~120 instructions per output position and pass.
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "se_internal.h"
+
+namespace se {
+namespace {
+
+constexpr int T = kFramesPerChunk;  // 21
+constexpr int NB = 201;
+constexpr int TP = T + 4;           // 25 frames: 4 carried + 21 new
+constexpr int FPOS = PRECONV_TC_POS;  // 272 positions per frame row
+constexpr int ROW_BYTES = FPOS * 16;
+constexpr int X_BYTES = TP * ROW_BYTES;  // 108,800
+constexpr int NPAIR = 13;                // 25 taps, two per MMA
+constexpr int W_BYTES = NPAIR * 512;     // B tiles: [pair][k chunk (256 B)][n group (128 B)][8 rows x 16 B]
+constexpr int NTILE = 2 * T;             // 2 tiles of 128 bins per frame
+constexpr int kThreads = 10 * 32;        // warp 0: MMA issuer; warps 2..9: two epilogue groups; all: loads
+constexpr int kEpiWarp0 = 2;
+constexpr int NACC = 16;                 // TMEM accumulators of 16 columns: the MMA warp runs up to 16 tiles ahead of the
+                                         // epilogue, hiding the commit -> wait -> tcgen05.ld -> arrive round trip per tile
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint64_t t0 = 0;
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_try_wait(bar, parity)) return;
+        if ((spins & 1023u) == 0) {  // protocol bug: fail loudly (after ~2 s) instead of hanging the GPU
+            const uint64_t t = global_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// K-major, no swizzle (cute::UMMA::LayoutType::SWIZZLE_NONE = 0): start >> 4 | LBO >> 4 @16 | SBO >> 4 @32 | version 1 @46
+__device__ __forceinline__ uint64_t make_desc_ns(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_elu(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+
+__global__ void __launch_bounds__(kThreads, 1) preconv_tc_kernel(PreconvTcParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sx = smem;                         // X
+    unsigned char* swt = smem + X_BYTES;              // B tiles
+    float* sp = reinterpret_cast<float*>(swt + W_BYTES);  // packed fp32 parameters (bias, gate, norm)
+    uint64_t* s_bar = reinterpret_cast<uint64_t*>(sp + PRECONV_W_FLOATS);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NACC);
+    double* s_red = reinterpret_cast<double*>(s_tmem + 2);  // [2][8 warps]
+    float* s_co = reinterpret_cast<float*>(s_red + 16);     // mean, inv
+    const uint32_t x_smem = smem_u32(sx), w_smem = smem_u32(swt), bar0 = smem_u32(s_bar);
+    auto tfull = [&](uint32_t a) { return bar0 + 8u * a; };
+    auto tempty = [&](uint32_t a) { return bar0 + 8u * (NACC + a); };
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int d = p.d;
+
+    // ---- one-time set-up: parameters, B tiles (fp16, canonical no-swizzle K-major), barriers, TMEM ----------------------
+    for (int i = tid; i < PRECONV_W_FLOATS; i += kThreads) sp[i] = __ldg(p.w + i);
+    __syncthreads();
+    // B[pair][kc][n][k]: chunk kc <-> tap 2 pair + kc = (kt, kf); row n = output channel co (< 5), k = input channel ci (< 5)
+    for (int u = tid; u < NPAIR * 2 * 16; u += kThreads) {
+        const int n = u & 15, kc = (u >> 4) & 1, pair = u >> 5;
+        const int tap = 2 * pair + kc;
+        __align__(16) __half h[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            float v = 0.f;
+            if (tap < 25 && n < 5 && k < 5) v = sp[((tap / 5) * 5 + k) * 28 + (tap % 5) * 5 + n];  // packed [(kt*5+ci)*28 + kf*5 + co]
+            h[k] = __float2half_rn(v);
+        }
+        *reinterpret_cast<uint4*>(swt + pair * 512 + kc * 256 + (n >> 3) * 128 + (n & 7) * 16) = *reinterpret_cast<const uint4*>(h);
+    }
+    if (tid == 0) {
+        for (int a = 0; a < NACC; ++a) {
+            mbar_init(tfull(a), 1);
+            mbar_init(tempty(a), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)(NACC * 16))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+
+    uint32_t tile_it = 0;  // tiles issued / consumed so far by this CTA (accumulator = tile_it & 1), same count in every role
+    for (int stream = blockIdx.x; stream < p.B; stream += gridDim.x) {
+        const int b = p.b0 + stream;
+        __half* gx = p.in + (long long)b * p.in_sB;
+        // ---- the chunk's input: 25 frames x 272 units, contiguous --------------------------------------------------------
+        for (int i = tid; i < X_BYTES / 16; i += kThreads)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(x_smem + 16u * i), "l"(reinterpret_cast<const uint4*>(gx) + i)
+                         : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        // causal state: the last 4 frames of this chunk's input become frames 0..3 of the next chunk (CRN_ELU.py:246)
+        for (int i = tid; i < 4 * FPOS; i += kThreads)
+            reinterpret_cast<uint4*>(gx)[i] = reinterpret_cast<const uint4*>(sx + T * ROW_BYTES)[i];
+
+        for (int pass = 0; pass < 2; ++pass) {
+            if (warp == 0) {
+                // ============================ MMA issuer ============================
+                if (lane == 0) {
+                    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                    for (int tile = 0; tile < NTILE; ++tile) {
+                        const uint32_t it = tile_it + tile, acc = it % NACC;
+                        mbar_wait(tempty(acc), ((it / NACC) & 1) ^ 1);
+                        tc_fence_after();
+                        const int t = tile >> 1, f0 = (tile & 1) * 128;
+#pragma unroll
+                        for (int pair = 0; pair < NPAIR; ++pair) {
+                            const int ta = 2 * pair, tb = 2 * pair + 1 < 25 ? 2 * pair + 1 : 2 * pair;
+                            const uint32_t offa = (uint32_t)(((t + ta / 5) * FPOS + f0 + (ta % 5) * d) * 16);
+                            const uint32_t offb = (uint32_t)(((t + tb / 5) * FPOS + f0 + (tb % 5) * d) * 16);
+                            const uint32_t lbo = offb > offa ? offb - offa : 16u;  // last pair: second chunk has zero weights
+                            tc_mma_f16(tmem_base + acc * 16, make_desc_ns(x_smem + offa, lbo, 128u),
+                                       make_desc_ns(w_smem + pair * 512, 256u, 128u), idesc, pair ? 1u : 0u);
+                        }
+                        tc_commit(tfull(acc));
+                    }
+                }
+                __syncwarp();
+            } else if (warp >= kEpiWarp0) {
+                // ============================ epilogue groups: thread = output bin ============================
+                const int ew = warp - kEpiWarp0, g = ew >> 2, q = warp & 3;
+                float psum = 0.f, psq = 0.f;
+                const float mean = s_co[0], inv = s_co[1];  // valid in pass 1 (written after pass 0)
+                for (int tile = g; tile < NTILE; tile += 2) {
+                    const uint32_t it = tile_it + tile, acc = it % NACC;
+                    const int t = tile >> 1, f = (tile & 1) * 128 + q * 32 + lane;
+                    mbar_wait(tfull(acc), (it / NACC) & 1);
+                    tc_fence_after();
+                    uint32_t v[8];
+                    tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 16, v);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    mbar_arrive(tempty(acc));
+                    if (f < NB) {
+                        float e[5], y[5];
+#pragma unroll
+                        for (int c = 0; c < 5; ++c) e[c] = fast_elu(__uint_as_float(v[c]) + sp[PRECONV_W_BIAS + c]);
+#pragma unroll
+                        for (int co = 0; co < 5; ++co) {
+                            float a = sp[PRECONV_W_BT + co], gt = sp[PRECONV_W_BG + co];
+#pragma unroll
+                            for (int k = 0; k < 5; ++k) {
+                                a = fmaf(sp[PRECONV_W_WT + co * 5 + k], e[k], a);
+                                gt = fmaf(sp[PRECONV_W_WG + co * 5 + k], e[k], gt);
+                            }
+                            y[co] = a * fast_sigmoid(gt);
+                        }
+                        if (pass == 0) {
+#pragma unroll
+                            for (int c = 0; c < 5; ++c) {
+                                psum += y[c];
+                                psq += y[c] * y[c];
+                            }
+                        } else {
+                            // normalise, add the block input (CRN_ELU.py:376) and write the next layer's input unit
+                            const __half* xin = reinterpret_cast<const __half*>(sx + ((t + 4) * FPOS + f + 2 * d) * 16);
+                            float o[5];
+#pragma unroll
+                            for (int c = 0; c < 5; ++c)
+                                o[c] = (y[c] - mean) * inv * sp[PRECONV_W_NW + c] + sp[PRECONV_W_NB + c] + __half2float(xin[c]);
+                            const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]),
+                                          h2 = __floats2half2_rn(o[4], 0.f);
+                            uint4 u;
+                            u.x = *reinterpret_cast<const unsigned*>(&h0);
+                            u.y = *reinterpret_cast<const unsigned*>(&h1);
+                            u.z = *reinterpret_cast<const unsigned*>(&h2);
+                            u.w = 0u;
+                            *reinterpret_cast<uint4*>(p.out + (long long)b * p.oB + (long long)t * p.oT + (long long)f * p.oF) = u;
+                        }
+                    }
+                }
+                if (pass == 0) {  // GlobalLayerNorm statistics of this stream (CRN_ELU.py:40-41), reduced in double
+                    double ds = psum, dq = psq;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) {
+                        ds += __shfl_xor_sync(0xffffffffu, ds, off);
+                        dq += __shfl_xor_sync(0xffffffffu, dq, off);
+                    }
+                    if (lane == 0) {
+                        s_red[ew] = ds;
+                        s_red[8 + ew] = dq;
+                    }
+                }
+            }
+            tile_it += NTILE;
+            __syncthreads();
+            if (pass == 0) {
+                if (tid == 0) {
+                    double ds = 0.0, dq = 0.0;
+                    for (int w = 0; w < 8; ++w) {
+                        ds += s_red[w];
+                        dq += s_red[8 + w];
+                    }
+                    const double count = 5.0 * NB * T;
+                    const double mu = ds / count;
+                    double var = dq / count - mu * mu;
+                    if (var < 0.0) var = 0.0;
+                    const float varf = (float)var;
+                    const float den = p.student ? (sqrtf(varf) + 1e-8f) : (sqrtf(varf + 1e-8f) + 1e-8f);
+                    s_co[0] = (float)mu;
+                    s_co[1] = 1.0f / den;
+                }
+                __syncthreads();
+            }
+        }
+        // every thread is done with X (pass-1 residual reads included) before the next stream overwrites it
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NACC * 16)) : "memory");
+    }
+}
+
+constexpr size_t kSmemBytes = X_BYTES + W_BYTES + PRECONV_W_FLOATS * 4 + 2 * NACC * 8 + 8 + 16 * 8 + 16;
+
+}  // namespace
+
+int launch_preconv_tc(const PreconvTcParams& p, cudaStream_t st) {
+    if (p.B <= 0) return 0;
+    SE_REQUIRE(p.d == 1 || p.d == 2 || p.d == 4, "preconv_tc: frequency dilation must be 1, 2 or 4 (CRN_ELU.py:336)");
+    static bool configured = false;
+    if (!configured) {
+        SE_CUDA_OK(cudaFuncSetAttribute(preconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
+        configured = true;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        SE_CUDA_OK(cudaGetDevice(&dev));
+        SE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    preconv_tc_kernel<<<p.B < num_sms ? p.B : num_sms, kThreads, kSmemBytes, st>>>(p);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace se

@@ -152,6 +152,22 @@ struct PreconvParams {
 };
 int launch_preconv(const PreconvParams& p, cudaStream_t st);
 
+// the same block on the tensor cores (preconv_tc.cu; fp16 operand mode).  Activations of this chain are channels-last
+// fp16 per stream: [25 frames: 4 carried + 21 new][PRECONV_TC_POS positions][8 halves], bin f of a layer with
+// dilation d at position f + 2d, everything else zero (the conv's frequency padding and the tile overrun).
+constexpr int PRECONV_TC_POS = 272;
+struct PreconvTcParams {
+    __half* in;          // this layer's input buffer (frames 0..3 are rewritten with the carried state)
+    long long in_sB;     // halves per stream
+    int d;               // frequency dilation 1 / 2 / 4
+    const float* w;      // packed fp32 weights (same block as PreconvParams::w)
+    __half* out;         // out(b, t, f) = 16-byte unit at out + b*oB + t*oT + f*oF (halves): interior of the next input
+    long long oB, oT, oF;
+    int student;
+    int b0, B;
+};
+int launch_preconv_tc(const PreconvTcParams& p, cudaStream_t st);
+
 // GRU cell pointwise update for the fp32 path (PyTorch nn.GRU gate order r,z,n; CRN_ELU.py:127-133)
 int launch_gru_pointwise(const float* gi, long long giB, const float* gh, const float* hprev, long long hB,
                          float* hout, int B, int H, cudaStream_t st);
@@ -186,6 +202,9 @@ struct StftParams {
     const IoDesc* io;  // chunk source
     int B, M;          // streams, microphones (3)
     int student;       // phase formula of distillation_crn.py:340
+    // feat_h8 != nullptr: one 16-byte unit (5 features as fp16 + 3 zeros) per (frame, bin) at feat_h8 + b*fB + t*fT + f*fF
+    // (halves) instead of the fp32 planes below (tensor-core pre-convolutions)
+    __half* feat_h8;
     float* feat;       // preconv-0 input buffer interior: feat[b*fB + c*fC + t*fT + f*fF], c < 5
     long long fB, fC, fT, fF;
     float* noisy;  // mic-0 spectrum [B][T][F][2]
@@ -198,7 +217,7 @@ struct StftParams {
 int launch_stft_features(const StftParams& p, cudaStream_t st);
 // features from a spectrum in the reference layout [B][M][F][T][2] (for TemporalCRN.forward, CRN_ELU.py:369-373)
 int launch_features_from_spec(const float* spec, int B, int M, int student, float* feat, long long fB, long long fC,
-                              long long fT, long long fF, float* noisy, cudaStream_t st);
+                              long long fT, long long fF, float* noisy, cudaStream_t st, __half* feat_h8 = nullptr);
 
 struct MaskIstftParams {
     const IoDesc* io;     // out pointer for the fused streaming path (may be null when out_chunk is set)

@@ -181,3 +181,22 @@ def test_weights_rebind_after_update():
     model.cuda()
     y3 = model.realtime_process(x).cpu().numpy()
     assert np.abs(y2 - y3).max() < 2e-5
+
+
+def test_tensor_core_preconv_matches_reference(monkeypatch):
+    """SE_B200_PRECONV_TC=1: the pre-convolutions as implicit convolutions on the tensor cores (shifted no-swizzle UMMA
+    descriptors over the channels-last input resident in shared memory; opt-in because it is slower than the CUDA-core
+    kernel).  Same stated fp16 tolerance against the reference fixture, teacher and small configuration."""
+    monkeypatch.setenv("SE_B200_PRECONV_TC", "1")
+    for tag in ("crn_small", "crn_teacher"):
+        g = load_golden(tag)
+        tol = TOL["fp16"]
+        model = make_model(tag, "fp16")
+        B, L = int(g["meta"][1]), int(g["meta"][2])
+        mix, _ = synth.make_mixture(B, L)
+        y = model.realtime_process(torch.from_numpy(mix).cuda()).cpu().numpy()
+        assert np.abs(y - g["out"]).max() < tol["wave_max_abs"] * max(1.0, np.abs(g["out"]).max())
+        assert si_sdr_db(y, g["out"]) > tol["si_sdr_vs_ref_db"]
+        mix2, _ = synth.make_mixture(B, L // 2, first_stream=100)
+        y2 = model.realtime_process(torch.from_numpy(mix2).cuda(), True).cpu().numpy()  # carried state across calls
+        assert np.abs(y2 - g["out_cont"]).max() < tol["wave_max_abs"] * max(1.0, np.abs(g["out_cont"]).max())
