@@ -3,16 +3,18 @@
 // per stream at a time.
 //
 // No im2col is ever materialised.  The whole zero-bordered input of the chunk sits in shared memory channels-last,
-// X[25 frames][272 positions][8 halves] (one 16-byte unit per (frame, bin); bin f at position f + 2d), and a conv tap is
-// just a SHIFT of that buffer: for the 128 consecutive output bins of a tile, tap (kt, kf) reads the 128 consecutive
-// units starting at X[t + kt][f0 + kf d].  In the canonical K-major no-swizzle UMMA layout -- ((8, n), 2):((16 B, SBO),
-// LBO) -- eight consecutive units are one core matrix, SBO = 128 B walks the 8-row groups and LBO, the distance between
-// the two 16-byte K chunks of one MMA, is free: one tcgen05.mma (M128 x N16 x K16) consumes TWO taps, the first chunk at
-// the descriptor's start address, the second LBO bytes further.  13 MMAs per tile of 128 bins instead of 80,000 FMAs.
-//
-// GlobalLayerNorm needs the statistics of the whole stream before anything can be written, and 4221 x 5 pre-norm values
-// do not fit beside the input: the conv is simply issued twice (pass 1: statistics, pass 2: normalise + residual +
-// store) -- the tensor work is free, the epilogue (ELU, 5x5 gate) costs ~120 instructions per output position and pass.
+// X[25 frames][272 positions][8 halves] (one 16-byte unit per (frame, bin); bin f at position f + 2d), and the
+// convolution is split as   out[t][f][co] = sum_kf Z_t[f + kf d][kf][co],   Z_t[pos][kf][co] = sum_{kt,ci} w[co][ci][kf][kt] X[t+kt][pos][ci]:
+//   * Z_t is a plain GEMM over the UNSHIFTED positions (M = 256 positions, K = 5 frames x 8 channels, N = 5 taps x 8
+//     channels = 48 with padding).  In the canonical K-major no-swizzle UMMA layout -- ((8, n), 2):((16 B, SBO), LBO) --
+//     eight consecutive units of a frame row are one core matrix, SBO = 128 B walks the 8-row groups and LBO, the distance
+//     between the two 16-byte K chunks of one MMA, is the ROW PITCH: one tcgen05.mma (M128 x N48 x K16) consumes two
+//     frames.  3 MMAs per 128 positions, 126 per stream and layer (a first version with the taps in K needed 1092 MMAs
+//     of N = 16 and was MMA-issue bound: ~100 cycles per instruction whatever its size).
+//   * the frequency taps become a shift-and-add in the epilogue: Z_t goes TMEM -> registers -> shared memory, and the
+//     thread of bin f adds the five rows f, f + d, ..., f + 4d.
+// GlobalLayerNorm needs the statistics of the whole stream before anything can be written: the 4221 x 5 gated values wait
+// in shared memory as fp16 planes; a second sweep normalises, adds the block input and stores the next layer's units.
 #include <cuda_fp16.h>
 #include <stdint.h>
 
@@ -27,13 +29,18 @@ constexpr int TP = T + 4;           // 25 frames: 4 carried + 21 new
 constexpr int FPOS = PRECONV_TC_POS;  // 272 positions per frame row
 constexpr int ROW_BYTES = FPOS * 16;
 constexpr int X_BYTES = TP * ROW_BYTES;  // 108,800
-constexpr int NPAIR = 13;                // 25 taps, two per MMA
-constexpr int W_BYTES = NPAIR * 512;     // B tiles: [pair][k chunk (256 B)][n group (128 B)][8 rows x 16 B]
-constexpr int NTILE = 2 * T;             // 2 tiles of 128 bins per frame
-constexpr int kThreads = 10 * 32;        // warp 0: MMA issuer; warps 2..9: two epilogue groups; all: loads
+constexpr int ZCOLS = 40;                // Z row: [kf][8 channels], 5 taps
+constexpr int ZPITCH = 44;               // floats per Z row: 11 x 16 B, so that 8 consecutive rows hit 8 different bank groups
+constexpr int Z_BYTES = 256 * ZPITCH * 4; // 45,056
+constexpr int YPITCH = 208;              // bins per (channel, frame) row of the fp16 planes
+constexpr int Y_BYTES = 5 * T * YPITCH * 2;  // 43,680
+constexpr int NPAIR = 3;                 // frame pairs (0,1) (2,3) (4,-)
+constexpr int WPAIR_BYTES = 2 * 6 * 128; // B tile of a pair: [k chunk (768 B)][n group of 8 rows (128 B)][8 rows x 16 B]
+constexpr int W_BYTES = NPAIR * WPAIR_BYTES;
+constexpr int NTILE = 2 * T;             // 2 tiles of 128 positions per frame
+constexpr int kThreads = 10 * 32;        // warp 0: MMA issuer; warps 2..9: epilogue; all: loads and the final sweep
 constexpr int kEpiWarp0 = 2;
-constexpr int NACC = 16;                 // TMEM accumulators of 16 columns: the MMA warp runs up to 16 tiles ahead of the
-                                         // epilogue, hiding the commit -> wait -> tcgen05.ld -> arrive round trip per tile
+constexpr int NACC = 8;                  // TMEM accumulators (64-column slots, 48 used): the MMA warp runs 4 frames ahead
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -98,11 +105,20 @@ __device__ __forceinline__ uint64_t make_desc_ns(uint32_t smem_addr, uint32_t lb
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_elu(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
 
+__device__ __forceinline__ void tmem_ld8_nowait8(uint32_t taddr, float* r) {
+    uint32_t v[8];
+    tmem_ld8_nowait(taddr, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(v[i]);
+}
+
 __global__ void __launch_bounds__(kThreads, 1) preconv_tc_kernel(PreconvTcParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* sx = smem;                         // X
-    unsigned char* swt = smem + X_BYTES;              // B tiles
-    float* sp = reinterpret_cast<float*>(swt + W_BYTES);  // packed fp32 parameters (bias, gate, norm)
+    unsigned char* sx = smem;                                       // X
+    float* sz = reinterpret_cast<float*>(smem + X_BYTES);           // Z of the current frame [256][40]
+    __half* sy = reinterpret_cast<__half*>(smem + X_BYTES + Z_BYTES);  // gated values [5][21][208]
+    unsigned char* swt = smem + X_BYTES + Z_BYTES + Y_BYTES;        // B tiles
+    float* sp = reinterpret_cast<float*>(swt + W_BYTES);            // packed fp32 parameters (bias, gate, norm)
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(sp + PRECONV_W_FLOATS);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * NACC);
     double* s_red = reinterpret_cast<double*>(s_tmem + 2);  // [2][8 warps]
@@ -116,18 +132,19 @@ __global__ void __launch_bounds__(kThreads, 1) preconv_tc_kernel(PreconvTcParams
     // ---- one-time set-up: parameters, B tiles (fp16, canonical no-swizzle K-major), barriers, TMEM ----------------------
     for (int i = tid; i < PRECONV_W_FLOATS; i += kThreads) sp[i] = __ldg(p.w + i);
     __syncthreads();
-    // B[pair][kc][n][k]: chunk kc <-> tap 2 pair + kc = (kt, kf); row n = output channel co (< 5), k = input channel ci (< 5)
-    for (int u = tid; u < NPAIR * 2 * 16; u += kThreads) {
-        const int n = u & 15, kc = (u >> 4) & 1, pair = u >> 5;
-        const int tap = 2 * pair + kc;
+    // B[pair][kc][n][k]: chunk kc <-> frame tap kt = 2 pair + kc; row n = kf * 8 + co; k = input channel ci
+    for (int u = tid; u < NPAIR * 2 * 48; u += kThreads) {
+        const int n = u % 48, kc = (u / 48) & 1, pair = u / 96;
+        const int kt = 2 * pair + kc, kf = n >> 3, co = n & 7;
         __align__(16) __half h[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
             float v = 0.f;
-            if (tap < 25 && n < 5 && k < 5) v = sp[((tap / 5) * 5 + k) * 28 + (tap % 5) * 5 + n];  // packed [(kt*5+ci)*28 + kf*5 + co]
+            if (kt < 5 && kf < 5 && co < 5 && k < 5) v = sp[(kt * 5 + k) * 28 + kf * 5 + co];  // packed [(kt*5+ci)*28 + kf*5 + co]
             h[k] = __float2half_rn(v);
         }
-        *reinterpret_cast<uint4*>(swt + pair * 512 + kc * 256 + (n >> 3) * 128 + (n & 7) * 16) = *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(swt + pair * WPAIR_BYTES + kc * 768 + (n >> 3) * 128 + (n & 7) * 16) =
+            *reinterpret_cast<const uint4*>(h);
     }
     if (tid == 0) {
         for (int a = 0; a < NACC; ++a) {
@@ -137,7 +154,7 @@ __global__ void __launch_bounds__(kThreads, 1) preconv_tc_kernel(PreconvTcParams
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)(NACC * 16))
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(512u)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -147,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) preconv_tc_kernel(PreconvTcParams
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
 
-    uint32_t tile_it = 0;  // tiles issued / consumed so far by this CTA (accumulator = tile_it & 1), same count in every role
+    uint32_t tile_it = 0;  // tiles issued / consumed so far by this CTA, same count in every role
     for (int stream = blockIdx.x; stream < p.B; stream += gridDim.x) {
         const int b = p.b0 + stream;
         __half* gx = p.in + (long long)b * p.in_sB;
@@ -163,127 +180,154 @@ __global__ void __launch_bounds__(kThreads, 1) preconv_tc_kernel(PreconvTcParams
         for (int i = tid; i < 4 * FPOS; i += kThreads)
             reinterpret_cast<uint4*>(gx)[i] = reinterpret_cast<const uint4*>(sx + T * ROW_BYTES)[i];
 
-        for (int pass = 0; pass < 2; ++pass) {
-            if (warp == 0) {
-                // ============================ MMA issuer ============================
-                if (lane == 0) {
-                    constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-                    for (int tile = 0; tile < NTILE; ++tile) {
-                        const uint32_t it = tile_it + tile, acc = it % NACC;
-                        mbar_wait(tempty(acc), ((it / NACC) & 1) ^ 1);
-                        tc_fence_after();
-                        const int t = tile >> 1, f0 = (tile & 1) * 128;
-#pragma unroll
-                        for (int pair = 0; pair < NPAIR; ++pair) {
-                            const int ta = 2 * pair, tb = 2 * pair + 1 < 25 ? 2 * pair + 1 : 2 * pair;
-                            const uint32_t offa = (uint32_t)(((t + ta / 5) * FPOS + f0 + (ta % 5) * d) * 16);
-                            const uint32_t offb = (uint32_t)(((t + tb / 5) * FPOS + f0 + (tb % 5) * d) * 16);
-                            const uint32_t lbo = offb > offa ? offb - offa : 16u;  // last pair: second chunk has zero weights
-                            tc_mma_f16(tmem_base + acc * 16, make_desc_ns(x_smem + offa, lbo, 128u),
-                                       make_desc_ns(w_smem + pair * 512, 256u, 128u), idesc, pair ? 1u : 0u);
-                        }
-                        tc_commit(tfull(acc));
-                    }
-                }
-                __syncwarp();
-            } else if (warp >= kEpiWarp0) {
-                // ============================ epilogue groups: thread = output bin ============================
-                const int ew = warp - kEpiWarp0, g = ew >> 2, q = warp & 3;
-                float psum = 0.f, psq = 0.f;
-                const float mean = s_co[0], inv = s_co[1];  // valid in pass 1 (written after pass 0)
-                for (int tile = g; tile < NTILE; tile += 2) {
+        if (warp == 0) {
+            // ============================ MMA issuer: Z of every frame, two tiles of 128 positions ============================
+            if (lane == 0) {
+                constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(48 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                for (int tile = 0; tile < NTILE; ++tile) {
                     const uint32_t it = tile_it + tile, acc = it % NACC;
-                    const int t = tile >> 1, f = (tile & 1) * 128 + q * 32 + lane;
-                    mbar_wait(tfull(acc), (it / NACC) & 1);
+                    mbar_wait(tempty(acc), ((it / NACC) & 1) ^ 1);
                     tc_fence_after();
-                    uint32_t v[8];
-                    tmem_ld8_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + acc * 16, v);
-                    tmem_ld_wait();
-                    tc_fence_before();
-                    mbar_arrive(tempty(acc));
-                    if (f < NB) {
-                        float e[5], y[5];
+                    const int t = tile >> 1, pos0 = (tile & 1) * 128;
 #pragma unroll
-                        for (int c = 0; c < 5; ++c) e[c] = fast_elu(__uint_as_float(v[c]) + sp[PRECONV_W_BIAS + c]);
-#pragma unroll
-                        for (int co = 0; co < 5; ++co) {
-                            float a = sp[PRECONV_W_BT + co], gt = sp[PRECONV_W_BG + co];
-#pragma unroll
-                            for (int k = 0; k < 5; ++k) {
-                                a = fmaf(sp[PRECONV_W_WT + co * 5 + k], e[k], a);
-                                gt = fmaf(sp[PRECONV_W_WG + co * 5 + k], e[k], gt);
-                            }
-                            y[co] = a * fast_sigmoid(gt);
-                        }
-                        if (pass == 0) {
-#pragma unroll
-                            for (int c = 0; c < 5; ++c) {
-                                psum += y[c];
-                                psq += y[c] * y[c];
-                            }
-                        } else {
-                            // normalise, add the block input (CRN_ELU.py:376) and write the next layer's input unit
-                            const __half* xin = reinterpret_cast<const __half*>(sx + ((t + 4) * FPOS + f + 2 * d) * 16);
-                            float o[5];
-#pragma unroll
-                            for (int c = 0; c < 5; ++c)
-                                o[c] = (y[c] - mean) * inv * sp[PRECONV_W_NW + c] + sp[PRECONV_W_NB + c] + __half2float(xin[c]);
-                            const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]),
-                                          h2 = __floats2half2_rn(o[4], 0.f);
-                            uint4 u;
-                            u.x = *reinterpret_cast<const unsigned*>(&h0);
-                            u.y = *reinterpret_cast<const unsigned*>(&h1);
-                            u.z = *reinterpret_cast<const unsigned*>(&h2);
-                            u.w = 0u;
-                            *reinterpret_cast<uint4*>(p.out + (long long)b * p.oB + (long long)t * p.oT + (long long)f * p.oF) = u;
-                        }
+                    for (int pair = 0; pair < NPAIR; ++pair) {
+                        const uint32_t offa = (uint32_t)(((t + 2 * pair) * FPOS + pos0) * 16);
+                        const uint32_t lbo = pair < 2 ? (uint32_t)ROW_BYTES : 16u;  // (4,-): the second chunk has zero weights
+                        tc_mma_f16(tmem_base + acc * 64, make_desc_ns(x_smem + offa, lbo, 128u),
+                                   make_desc_ns(w_smem + pair * WPAIR_BYTES, 768u, 128u), idesc, pair ? 1u : 0u);
                     }
-                }
-                if (pass == 0) {  // GlobalLayerNorm statistics of this stream (CRN_ELU.py:40-41), reduced in double
-                    double ds = psum, dq = psq;
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) {
-                        ds += __shfl_xor_sync(0xffffffffu, ds, off);
-                        dq += __shfl_xor_sync(0xffffffffu, dq, off);
-                    }
-                    if (lane == 0) {
-                        s_red[ew] = ds;
-                        s_red[8 + ew] = dq;
-                    }
+                    tc_commit(tfull(acc));
                 }
             }
-            tile_it += NTILE;
-            __syncthreads();
-            if (pass == 0) {
-                if (tid == 0) {
-                    double ds = 0.0, dq = 0.0;
-                    for (int w = 0; w < 8; ++w) {
-                        ds += s_red[w];
-                        dq += s_red[8 + w];
+            __syncwarp();
+        } else if (warp >= kEpiWarp0) {
+            // ============================ epilogue: 256 threads ============================
+            const int ew = warp - kEpiWarp0, g = ew >> 2, q = warp & 3;
+            const int pos = 128 * g + 32 * q + lane;  // Z row this thread moves out of TMEM
+            const int f = ew * 32 + lane;             // output bin this thread finishes
+            float psum = 0.f, psq = 0.f;
+            // the 65 scalars of the cell (conv bias, the two 5x5 gate matrices and their biases) live in registers: read
+            // from shared memory they were 70 dependent loads per output and half of the kernel's time
+            float cb[5], wt[25], wg[25], bt[5], bg[5];
+#pragma unroll
+            for (int i = 0; i < 5; ++i) {
+                cb[i] = sp[PRECONV_W_BIAS + i];
+                bt[i] = sp[PRECONV_W_BT + i];
+                bg[i] = sp[PRECONV_W_BG + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 25; ++i) {
+                wt[i] = sp[PRECONV_W_WT + i];
+                wg[i] = sp[PRECONV_W_WG + i];
+            }
+            for (int t = 0; t < T; ++t) {
+                const uint32_t it = tile_it + 2 * t + g, acc = it % NACC;
+                mbar_wait(tfull(acc), (it / NACC) & 1);
+                tc_fence_after();
+                float z[ZCOLS];
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 64;
+#pragma unroll
+                for (int kf = 0; kf < 5; ++kf) tmem_ld8_nowait8(ta + 8 * kf, z + 8 * kf);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(tempty(acc));
+                float4* zr = reinterpret_cast<float4*>(sz + pos * ZPITCH);
+#pragma unroll
+                for (int i = 0; i < ZCOLS / 4; ++i) zr[i] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // Z of frame t complete
+                if (f < NB) {
+                    float e[5];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) e[c] = cb[c];
+#pragma unroll
+                    for (int kf = 0; kf < 5; ++kf) {  // out[f] = sum_kf Z[f + kf d][kf]
+                        const float* zs = sz + (f + kf * d) * ZPITCH + 8 * kf;
+                        const float4 a = *reinterpret_cast<const float4*>(zs);
+                        e[0] += a.x;
+                        e[1] += a.y;
+                        e[2] += a.z;
+                        e[3] += a.w;
+                        e[4] += zs[4];
                     }
-                    const double count = 5.0 * NB * T;
-                    const double mu = ds / count;
-                    double var = dq / count - mu * mu;
-                    if (var < 0.0) var = 0.0;
-                    const float varf = (float)var;
-                    const float den = p.student ? (sqrtf(varf) + 1e-8f) : (sqrtf(varf + 1e-8f) + 1e-8f);
-                    s_co[0] = (float)mu;
-                    s_co[1] = 1.0f / den;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) e[c] = fast_elu(e[c]);
+#pragma unroll
+                    for (int co = 0; co < 5; ++co) {
+                        float a = bt[co], gt = bg[co];
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) {
+                            a = fmaf(wt[co * 5 + k], e[k], a);
+                            gt = fmaf(wg[co * 5 + k], e[k], gt);
+                        }
+                        const float y = a * fast_sigmoid(gt);
+                        psum += y;
+                        psq += y * y;
+                        sy[(co * T + t) * YPITCH + f] = __float2half_rn(y);
+                    }
                 }
-                __syncthreads();
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read Z before the next frame overwrites it
+            }
+            // GlobalLayerNorm statistics of this stream (CRN_ELU.py:40-41), reduced in double
+            double ds = psum, dq = psq;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                ds += __shfl_xor_sync(0xffffffffu, ds, off);
+                dq += __shfl_xor_sync(0xffffffffu, dq, off);
+            }
+            if (lane == 0) {
+                s_red[ew] = ds;
+                s_red[8 + ew] = dq;
             }
         }
-        // every thread is done with X (pass-1 residual reads included) before the next stream overwrites it
+        tile_it += NTILE;
+        __syncthreads();
+        if (tid == 0) {
+            double ds = 0.0, dq = 0.0;
+            for (int w = 0; w < 8; ++w) {
+                ds += s_red[w];
+                dq += s_red[8 + w];
+            }
+            const double count = 5.0 * NB * T;
+            const double mu = ds / count;
+            double var = dq / count - mu * mu;
+            if (var < 0.0) var = 0.0;
+            const float varf = (float)var;
+            const float den = p.student ? (sqrtf(varf) + 1e-8f) : (sqrtf(varf + 1e-8f) + 1e-8f);
+            s_co[0] = (float)mu;
+            s_co[1] = 1.0f / den;
+        }
+        __syncthreads();
+        // ---- normalise, add the block input (CRN_ELU.py:376) and write the next layer's input units ---------------------------
+        {
+            const float mean = s_co[0], inv = s_co[1];
+            for (int i = tid; i < T * NB; i += kThreads) {
+                const int t = i / NB, f = i - t * NB;
+                const __half* xin = reinterpret_cast<const __half*>(sx + ((t + 4) * FPOS + f + 2 * d) * 16);
+                float o[5];
+#pragma unroll
+                for (int c = 0; c < 5; ++c)
+                    o[c] = (__half2float(sy[(c * T + t) * YPITCH + f]) - mean) * inv * sp[PRECONV_W_NW + c] + sp[PRECONV_W_NB + c] +
+                           __half2float(xin[c]);
+                const __half2 h0 = __floats2half2_rn(o[0], o[1]), h1 = __floats2half2_rn(o[2], o[3]), h2 = __floats2half2_rn(o[4], 0.f);
+                uint4 u;
+                u.x = *reinterpret_cast<const unsigned*>(&h0);
+                u.y = *reinterpret_cast<const unsigned*>(&h1);
+                u.z = *reinterpret_cast<const unsigned*>(&h2);
+                u.w = 0u;
+                *reinterpret_cast<uint4*>(p.out + (long long)b * p.oB + (long long)t * p.oT + (long long)f * p.oF) = u;
+            }
+        }
+        __syncthreads();  // everyone is done with X and the planes before the next stream overwrites them
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(NACC * 16)) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
-constexpr size_t kSmemBytes = X_BYTES + W_BYTES + PRECONV_W_FLOATS * 4 + 2 * NACC * 8 + 8 + 16 * 8 + 16;
+constexpr size_t kSmemBytes = X_BYTES + Z_BYTES + Y_BYTES + W_BYTES + PRECONV_W_FLOATS * 4 + 2 * NACC * 8 + 8 + 16 * 8 + 16;
 
 }  // namespace
 

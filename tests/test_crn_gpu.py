@@ -183,11 +183,12 @@ def test_weights_rebind_after_update():
     assert np.abs(y2 - y3).max() < 2e-5
 
 
-def test_tensor_core_preconv_matches_reference(monkeypatch):
-    """SE_B200_PRECONV_TC=1: the pre-convolutions as implicit convolutions on the tensor cores (shifted no-swizzle UMMA
-    descriptors over the channels-last input resident in shared memory; opt-in because it is slower than the CUDA-core
-    kernel).  Same stated fp16 tolerance against the reference fixture, teacher and small configuration."""
-    monkeypatch.setenv("SE_B200_PRECONV_TC", "1")
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_fp16_preconv_variants_match_reference(monkeypatch, tc):
+    """fp16 mode runs the pre-convolutions on the tensor cores (preconv_tc.cu: implicit convolution through no-swizzle
+    UMMA descriptors over the channels-last input resident in shared memory); SE_B200_PRECONV_TC=0 keeps the fp32
+    CUDA-core kernel.  Both against the reference fixture at the stated fp16 tolerance, incl. the carried state."""
+    monkeypatch.setenv("SE_B200_PRECONV_TC", tc)
     for tag in ("crn_small", "crn_teacher"):
         g = load_golden(tag)
         tol = TOL["fp16"]
