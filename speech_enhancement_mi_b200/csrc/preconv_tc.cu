@@ -30,8 +30,9 @@ constexpr int FPOS = PRECONV_TC_POS;  // 272 positions per frame row
 constexpr int ROW_BYTES = FPOS * 16;
 constexpr int X_BYTES = TP * ROW_BYTES;  // 108,800
 constexpr int ZCOLS = 40;                // Z row: [kf][8 channels], 5 taps
-constexpr int ZPITCH = 44;               // floats per Z row: 11 x 16 B, so that 8 consecutive rows hit 8 different bank groups
-constexpr int Z_BYTES = 256 * ZPITCH * 4; // 45,056
+constexpr int ZPITCH = 56;               // halves per Z row: 7 x 16 B, so that 8 consecutive rows hit 8 different bank groups
+constexpr int ZBUF = 256 * ZPITCH;       // halves per buffer
+constexpr int Z_BYTES = 2 * ZBUF * 2;    // 57,344: fp16, double-buffered over the frame parity (one barrier per frame)
 constexpr int YPITCH = 208;              // bins per (channel, frame) row of the fp16 planes
 constexpr int Y_BYTES = 5 * T * YPITCH * 2;  // 43,680
 constexpr int NPAIR = 3;                 // frame pairs (0,1) (2,3) (4,-)
@@ -115,7 +116,7 @@ __device__ __forceinline__ void tmem_ld8_nowait8(uint32_t taddr, float* r) {
 __global__ void __launch_bounds__(kThreads, 1) preconv_tc_kernel(PreconvTcParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* sx = smem;                                       // X
-    float* sz = reinterpret_cast<float*>(smem + X_BYTES);           // Z of the current frame [256][40]
+    __half* sz = reinterpret_cast<__half*>(smem + X_BYTES);         // Z of two frames [2][256][56] fp16
     __half* sy = reinterpret_cast<__half*>(smem + X_BYTES + Z_BYTES);  // gated values [5][21][208]
     unsigned char* swt = smem + X_BYTES + Z_BYTES + Y_BYTES;        // B tiles
     float* sp = reinterpret_cast<float*>(swt + W_BYTES);            // packed fp32 parameters (bias, gate, norm)
@@ -231,23 +232,36 @@ __global__ void __launch_bounds__(kThreads, 1) preconv_tc_kernel(PreconvTcParams
                 tmem_ld_wait();
                 tc_fence_before();
                 mbar_arrive(tempty(acc));
-                float4* zr = reinterpret_cast<float4*>(sz + pos * ZPITCH);
+                uint4* zr = reinterpret_cast<uint4*>(sz + (t & 1) * ZBUF + pos * ZPITCH);
 #pragma unroll
-                for (int i = 0; i < ZCOLS / 4; ++i) zr[i] = make_float4(z[4 * i], z[4 * i + 1], z[4 * i + 2], z[4 * i + 3]);
-                asm volatile("bar.sync 1, 256;" ::: "memory");  // Z of frame t complete
+                for (int kf = 0; kf < 5; ++kf) {
+                    const __half2 h0 = __floats2half2_rn(z[8 * kf], z[8 * kf + 1]), h1 = __floats2half2_rn(z[8 * kf + 2], z[8 * kf + 3]),
+                                  h2 = __floats2half2_rn(z[8 * kf + 4], 0.f);
+                    uint4 u;
+                    u.x = *reinterpret_cast<const unsigned*>(&h0);
+                    u.y = *reinterpret_cast<const unsigned*>(&h1);
+                    u.z = *reinterpret_cast<const unsigned*>(&h2);
+                    u.w = 0u;
+                    zr[kf] = u;
+                }
+                // Z of frame t complete.  One barrier per frame is enough: frame t+2 overwrites this buffer only after the
+                // barrier of frame t+1, which every thread reaches after it has finished reading frame t
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (f < NB) {
                     float e[5];
 #pragma unroll
                     for (int c = 0; c < 5; ++c) e[c] = cb[c];
 #pragma unroll
                     for (int kf = 0; kf < 5; ++kf) {  // out[f] = sum_kf Z[f + kf d][kf]
-                        const float* zs = sz + (f + kf * d) * ZPITCH + 8 * kf;
-                        const float4 a = *reinterpret_cast<const float4*>(zs);
+                        const uint4 u = *reinterpret_cast<const uint4*>(sz + (t & 1) * ZBUF + (f + kf * d) * ZPITCH + 8 * kf);
+                        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+                        const float2 c2 = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                        const float2 c4 = __half22float2(*reinterpret_cast<const __half2*>(&u.z));
                         e[0] += a.x;
                         e[1] += a.y;
-                        e[2] += a.z;
-                        e[3] += a.w;
-                        e[4] += zs[4];
+                        e[2] += c2.x;
+                        e[3] += c2.y;
+                        e[4] += c4.x;
                     }
 #pragma unroll
                     for (int c = 0; c < 5; ++c) e[c] = fast_elu(e[c]);
@@ -265,7 +279,6 @@ __global__ void __launch_bounds__(kThreads, 1) preconv_tc_kernel(PreconvTcParams
                         sy[(co * T + t) * YPITCH + f] = __float2half_rn(y);
                     }
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read Z before the next frame overwrites it
             }
             // GlobalLayerNorm statistics of this stream (CRN_ELU.py:40-41), reduced in double
             double ds = psum, dq = psq;
