@@ -53,7 +53,7 @@ struct StftSmem {
     float2 spec[3][GROUP][NBIN + 1];
 };
 
-__global__ void __launch_bounds__(256) stft_features_kernel(StftParams p) {
+__global__ void __launch_bounds__(448, 2) stft_features_kernel(StftParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -495,7 +495,7 @@ int launch_stft_features(const StftParams& p, cudaStream_t st) {
     SE_REQUIRE((p.feat == nullptr && p.feat_h8 == nullptr) || p.M == 3,
                "stft features need exactly 3 microphones (CRN_ELU.py:369-373)");
     if (p.B == 0) return 0;
-    stft_features_kernel<<<dim3(p.B, T / GROUP), 224, sizeof(StftSmem), st>>>(p);
+    stft_features_kernel<<<dim3(p.B, T / GROUP), 448, sizeof(StftSmem), st>>>(p);  // 420 (mic, frame, n2) units per stage: one round, 28 warps per SM
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
