@@ -2377,6 +2377,11 @@ int se_crn_kernel_info(const se_ctx* c, int index, char* name, int name_cap, dou
         fl = op.alg_flops;
         by = op.alg_bytes;
         stg = op.stage;
+        // the op table counts 4 bytes per element; in fp16 operand mode the tensors of the encoder / decoder / Linear+GLN
+        // ops really are 2 bytes wide (the GRU projections keep their fp32 gi stream, the last deconv its fp32 output)
+        if (c->half && op.kind != OP_PRECONV_TC && op.kind != OP_PRECONV && op.kind != OP_GRU_TC &&
+            op.label.find("input_proj") == std::string::npos && op.label.find("step") == std::string::npos)
+            by *= op.kind == OP_DECONV_LAST ? 0.75 : 0.5;
     } else if (index == n + 1) {
         label = "mask+istft+ola";
         by = 4.0 * (2 * 2 * NBIN * T + PHOP + 2 * PHOP);
