@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 #include <math.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "se_internal.h"
@@ -303,54 +304,76 @@ __global__ void __launch_bounds__(256) mask_istft_kernel(MaskIstftParams p) {
         __syncthreads();
         if (p.spec_ref != nullptr && p.out_chunk == nullptr && p.carry == nullptr) continue;  // forward(): no iSTFT
 
+        // exp(-2 pi i j / 20) = (kC20[j], kS20[j]); both stages are fully unrolled so that every twiddle is an immediate
+        constexpr float kC20[20] = {1.0f, 0.951056516f, 0.809016994f, 0.587785252f, 0.309016994f, 0.0f, -0.309016994f, -0.587785252f, -0.809016994f, -0.951056516f, -1.0f, -0.951056516f, -0.809016994f, -0.587785252f, -0.309016994f, 0.0f, 0.309016994f, 0.587785252f, 0.809016994f, 0.951056516f};
+        constexpr float kS20[20] = {0.0f, -0.309016994f, -0.587785252f, -0.809016994f, -0.951056516f, -1.0f, -0.951056516f, -0.809016994f, -0.587785252f, -0.309016994f, 0.0f, 0.309016994f, 0.587785252f, 0.809016994f, 0.951056516f, 1.0f, 0.951056516f, 0.809016994f, 0.587785252f, 0.309016994f};
         // ---- stage A: z[k1][n2] = sum_k2 Xfull[k1 + 20 k2] * conj(W20)^(n2 k2), then * conj(W400)^(n2 k1) -------
-        for (int o = tid; o < GROUP * 11 * 20; o += blockDim.x) {
-            const int n2 = o % 20;
-            const int k1 = (o / 20) % 11;
-            const int fr = o / 220;
-            float re = 0.f, im = 0.f;
-            int idx = 0;
-#pragma unroll 5
+        // register-blocked like the forward transform: a thread loads the 20 inputs of one (frame, k1) once and produces
+        // 10 of the 20 outputs with immediate twiddles (40 loads feed 800 FMAs; the loop version spent 40 shared-memory
+        // loads per 80 FMAs)
+        for (int o = tid; o < GROUP * 11 * 2; o += blockDim.x) {
+            const int half = o & 1;
+            const int k1 = (o >> 1) % 11;
+            const int fr = o / 22;
+            float2 v[20];
+#pragma unroll
             for (int k2 = 0; k2 < 20; ++k2) {
                 const int k = k1 + 20 * k2;
-                float2 v;
                 if (k <= 200) {
-                    v = s.spec[fr][k];
+                    v[k2] = s.spec[fr][k];
                 } else {
-                    v = s.spec[fr][NFFT - k];
-                    v.y = -v.y;
+                    v[k2] = s.spec[fr][NFFT - k];
+                    v[k2].y = -v[k2].y;
                 }
-                const float2 w = s.w20[idx];  // conj applied below
-                re = fmaf(v.x, w.x, re);
-                re = fmaf(v.y, w.y, re);
-                im = fmaf(v.y, w.x, im);
-                im = fmaf(-v.x, w.y, im);
-                idx += n2;
-                if (idx >= 20) idx -= 20;
             }
-            s.z[fr][k1][n2] = cmul_conj(make_float2(re, im), s.w400[n2 * k1]);
+            auto emit = [&](auto n2c) {
+                constexpr int n2 = decltype(n2c)::value;
+                float re = 0.f, im = 0.f;
+#pragma unroll
+                for (int k2 = 0; k2 < 20; ++k2) {  // v * conj(w), w = (kC20, kS20)[(n2 k2) % 20]
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const float wc = kC20[(n2 * k2) % 20], ws = kS20[(n2 * k2) % 20];
+                    re = fmaf(v[k2].x, wc, re);
+                    re = fmaf(v[k2].y, ws, re);
+                    im = fmaf(v[k2].y, wc, im);
+                    im = fmaf(-v[k2].x, ws, im);
+                }
+                s.z[fr][k1][n2] = cmul_conj(make_float2(re, im), s.w400[n2 * k1]);
+            };
+            if (half == 0) {
+                emit(std::integral_constant<int, 0>{}); emit(std::integral_constant<int, 1>{}); emit(std::integral_constant<int, 2>{});
+                emit(std::integral_constant<int, 3>{}); emit(std::integral_constant<int, 4>{}); emit(std::integral_constant<int, 5>{});
+                emit(std::integral_constant<int, 6>{}); emit(std::integral_constant<int, 7>{}); emit(std::integral_constant<int, 8>{});
+                emit(std::integral_constant<int, 9>{});
+            } else {
+                emit(std::integral_constant<int, 10>{}); emit(std::integral_constant<int, 11>{}); emit(std::integral_constant<int, 12>{});
+                emit(std::integral_constant<int, 13>{}); emit(std::integral_constant<int, 14>{}); emit(std::integral_constant<int, 15>{});
+                emit(std::integral_constant<int, 16>{}); emit(std::integral_constant<int, 17>{}); emit(std::integral_constant<int, 18>{});
+                emit(std::integral_constant<int, 19>{});
+            }
         }
         __syncthreads();
         // ---- stage C: x[20 n1 + n2] = (z0 + (-1)^n1 z10 + 2 sum_{k1=1..9} Re(z[k1] conj(W20)^(n1 k1))) / 400 ----
-        for (int o = tid; o < GROUP * NFFT; o += blockDim.x) {
-            const int n = o % NFFT;
-            const int fr = o / NFFT;
-            const int n1 = n / 20, n2 = n % 20;
-            float acc = 0.f;
-            int idx = n1;
+        // one thread per (frame, n2): 11 inputs in registers, all 20 outputs n1 with immediate twiddles
+        for (int o = tid; o < GROUP * 20; o += blockDim.x) {
+            const int n2 = o % 20;
+            const int fr = o / 20;
+            float2 zv[11];
 #pragma unroll
-            for (int k1 = 1; k1 <= 9; ++k1) {
-                const float2 v = s.z[fr][k1][n2];
-                const float2 w = s.w20[idx];
-                acc = fmaf(v.x, w.x, acc);
-                acc = fmaf(v.y, w.y, acc);  // Re(v * conj(w))
-                idx += n1;
-                if (idx >= 20) idx -= 20;
+            for (int k1 = 0; k1 <= 10; ++k1) zv[k1] = s.z[fr][k1][n2];
+#pragma unroll
+            for (int n1 = 0; n1 < 20; ++n1) {
+                float acc = 0.f;
+#pragma unroll
+                for (int k1 = 1; k1 <= 9; ++k1) {  // Re(z * conj(w)), w = (kC20, kS20)[(n1 k1) % 20]
+                    acc = fmaf(zv[k1].x, kC20[(n1 * k1) % 20], acc);
+                    acc = fmaf(zv[k1].y, kS20[(n1 * k1) % 20], acc);
+                }
+                const float x = (zv[0].x + ((n1 & 1) ? -zv[10].x : zv[10].x) + 2.f * acc) * (1.0f / NFFT);
+                const int n = 20 * n1 + n2;
+                s.frames[fr][n] = x * s.win[n];
             }
-            const float z0 = s.z[fr][0][n2].x;
-            const float z10 = s.z[fr][10][n2].x;
-            const float x = (z0 + ((n1 & 1) ? -z10 : z10) + 2.f * acc) * (1.0f / NFFT);
-            s.frames[fr][n] = x * s.win[n];
         }
         __syncthreads();
         // ---- overlap-add of this group's frames (deterministic order: ascending frame) ---------------------------
