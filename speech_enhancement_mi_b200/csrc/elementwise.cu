@@ -116,61 +116,112 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* v) {
         v[2 * i + 1] = f.y;
     }
 }
-__global__ void __launch_bounds__(256) norm_apply_h8_kernel(NormApplyParams p) {
+__device__ __forceinline__ void load8(const float* __restrict__ q, float* v) {
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(q)), hi = __ldg(reinterpret_cast<const float4*>(q) + 1);
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+}
+// A thread keeps ONE (bin, 8-channel) unit for all frames of the block: the affine terms are loaded once and folded with
+// the stream's statistics into one FMA per value (x * a + d, a = w / den, d = b - mean * a), the index arithmetic is
+// done once per unit instead of once per access, and the frame loop is unrolled so that up to 3 x kNormFrames 16-byte
+// loads are in flight per thread.  The outputs are rounded to fp16, which hides the re-association and the fast
+// reciprocal / exponential of the mask sigmoid (the exact-order fp32 path is norm_apply_kernel above).
+template <int MODE>
+__global__ void __launch_bounds__(256, MODE == 2 ? 2 : 4) norm_apply_h8_kernel(NormApplyParams p) {
     const int t0 = blockIdx.x * kNormFrames;
     const int b = p.b0 + blockIdx.y;
     __shared__ float s_co[4];
     if (threadIdx.x == 0) {
         gln_coeffs(p.stats, b, p.count, p.student, s_co[0], s_co[1]);
-        if (p.mode == 2) gln_coeffs(p.stats_r, b, p.count_r, p.student, s_co[2], s_co[3]);
+        if (MODE == 2) gln_coeffs(p.stats_r, b, p.count_r, p.student, s_co[2], s_co[3]);
     }
     __syncthreads();
-    const float mean = s_co[0], inv = s_co[1], mr = s_co[2], ir = s_co[3];
+    const float mean = s_co[0], inv = s_co[1];
     const int C8 = p.C >> 3;
     const int n8 = p.F * C8;
-    const int total = n8 * min(kNormFrames, p.T - t0);
+    const int nt = min(kNormFrames, p.T - t0);
     const __half* yh = reinterpret_cast<const __half*>(p.y);
     const __half* rmh = reinterpret_cast<const __half*>(p.rm);
     const __half* rrh = reinterpret_cast<const __half*>(p.rr);
     __half* oh = reinterpret_cast<__half*>(p.out);
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int tl = i / n8;
-        const int j = i - tl * n8;
-        const int t = t0 + tl;
+    for (int j = threadIdx.x; j < n8; j += blockDim.x) {
         const int f = j / C8;
         const int c = (j - f * C8) * 8;
-        float o[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o[k] = 0.f;
-        uint4 uy = make_uint4(0, 0, 0, 0), um = uy, ur = uy;
-        if (f < p.Fy) uy = *reinterpret_cast<const uint4*>(yh + (((long long)b * p.T + t) * p.Fy + f) * p.C + c);
-        if (p.mode == 2) {
-            const long long ri = (((long long)b * p.T + t) * p.F + f) * p.C + c;
-            um = *reinterpret_cast<const uint4*>(rmh + ri);
-            ur = *reinterpret_cast<const uint4*>(rrh + ri);
-        }
-        if (f < p.Fy) {
-            float y[8];
-            unpack8(uy, y);
+        const bool has_y = f < p.Fy;
+        float a[8], d[8], ar[8], dr[8];
+        {
             const int wi = p.per_feature ? (f * p.C + c) : c;
-#pragma unroll
-            for (int k = 0; k < 8; ++k) o[k] = (y[k] - mean) * inv * p.w[wi + k] + p.b[wi + k];
-        }
-        if (p.mode == 2) {
-            float rm[8], rr[8];
-            unpack8(um, rm);
-            unpack8(ur, rr);
+            load8(p.w + wi, a);
+            load8(p.b + wi, d);
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const float m = sigmoidf_((rm[k] - mr) * ir * p.wr[c + k] + p.br[c + k]);
-                o[k] = m * rr[k] + (1.0f - m) * o[k];
+                a[k] *= inv;
+                d[k] = fmaf(-mean, a[k], d[k]);
             }
         }
-        uint4 uo;
-        __half2* ho = reinterpret_cast<__half2*>(&uo);
+        if (MODE == 2) {
+            const float mr = s_co[2], ir = s_co[3];
+            load8(p.wr + c, ar);
+            load8(p.br + c, dr);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) ho[k] = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
-        *reinterpret_cast<uint4*>(oh + b * p.oB + t * p.oT + f * p.oF + c) = uo;
+            for (int k = 0; k < 8; ++k) {
+                ar[k] *= -ir;  // the sigmoid needs -(x * ar + dr)
+                dr[k] = fmaf(-mr, ar[k], -dr[k]);
+            }
+        }
+        const __half* yp = yh + (((long long)b * p.T + t0) * p.Fy + f) * p.C + c;
+        const long long ystep = (long long)p.Fy * p.C;
+        const long long ri = (((long long)b * p.T + t0) * p.F + f) * p.C + c;
+        const long long rstep = (long long)p.F * p.C;
+        __half* op = oh + b * p.oB + t0 * p.oT + f * p.oF + c;
+        // frames in batches of FB: all loads of a batch are issued before its first use
+        constexpr int FB = MODE == 2 ? 4 : kNormFrames;
+#pragma unroll
+        for (int tb = 0; tb < kNormFrames; tb += FB) {
+            uint4 uy[FB], um[FB], ur[FB];
+#pragma unroll
+            for (int q = 0; q < FB; ++q) {
+                const int tl = tb + q;
+                uy[q] = make_uint4(0, 0, 0, 0);
+                if (tl < kNormFrames && tl < nt) {
+                    if (has_y) uy[q] = *reinterpret_cast<const uint4*>(yp + tl * ystep);
+                    if (MODE == 2) {
+                        um[q] = *reinterpret_cast<const uint4*>(rmh + ri + tl * rstep);
+                        ur[q] = *reinterpret_cast<const uint4*>(rrh + ri + tl * rstep);
+                    }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < FB; ++q) {
+                const int tl = tb + q;
+                if (tl < kNormFrames && tl < nt) {
+                    float o[8];
+                    if (has_y) {
+                        unpack8(uy[q], o);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[k] = fmaf(o[k], a[k], d[k]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) o[k] = 0.f;
+                    }
+                    if (MODE == 2) {
+                        float rm[8], rr[8];
+                        unpack8(um[q], rm);
+                        unpack8(ur[q], rr);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const float m = __fdividef(1.0f, 1.0f + __expf(fmaf(rm[k], ar[k], dr[k])));
+                            o[k] = fmaf(m, rr[k] - o[k], o[k]);
+                        }
+                    }
+                    uint4 uo;
+                    __half2* ho = reinterpret_cast<__half2*>(&uo);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ho[k] = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
+                    *reinterpret_cast<uint4*>(op + tl * p.oT) = uo;
+                }
+            }
+        }
     }
 }
 
@@ -258,7 +309,8 @@ int launch_norm_apply(const NormApplyParams& p, cudaStream_t st) {
     SE_REQUIRE(p.B <= 65535, "norm_apply: at most 65535 streams per launch");
     const dim3 grid((p.T + kNormFrames - 1) / kNormFrames, p.B);
     if (p.in_half && p.out_half && p.mode != 1 && p.C % 8 == 0 && p.oF % 8 == 0 && p.oT % 8 == 0 && p.oB % 8 == 0) {
-        norm_apply_h8_kernel<<<grid, 256, 0, st>>>(p);
+        if (p.mode == 2) norm_apply_h8_kernel<2><<<grid, 256, 0, st>>>(p);
+        else norm_apply_h8_kernel<0><<<grid, 256, 0, st>>>(p);
     } else {
         const int n4 = p.F * (p.C / 4);
         const int threads = n4 >= 256 ? 256 : (n4 >= 128 ? 128 : 64);

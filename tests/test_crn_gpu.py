@@ -201,3 +201,37 @@ def test_fp16_preconv_variants_match_reference(monkeypatch, tc):
         mix2, _ = synth.make_mixture(B, L // 2, first_stream=100)
         y2 = model.realtime_process(torch.from_numpy(mix2).cuda(), True).cpu().numpy()  # carried state across calls
         assert np.abs(y2 - g["out_cont"]).max() < tol["wave_max_abs"] * max(1.0, np.abs(g["out_cont"]).max())
+
+
+@pytest.mark.parametrize("precision", ["fp16", "fp32"])
+def test_full_size_1024_streams_replicas_match_oracle_checked_streams(precision):
+    """BASELINE configs[1] size (teacher, 1024 concurrent streams, the bench's precision): 8 distinct streams are checked
+    against the oracle over 4 chunk steps; the 1024-stream batch holds 128 shuffled replicas of each, and every replica
+    must reproduce its original -- all m-tiles, stream groups and persistent-kernel CTAs of the full-size launch compute
+    the same function as the small launch the oracle can afford to check."""
+    oracle, _ = make_oracle("crn_teacher")
+    model = make_model("crn_teacher", precision)
+    D, B, N = 8, 1024, 4
+    mix, _ = synth.make_mixture(D, 1600 * (N + 1))
+    chunks = [torch.from_numpy(mix[:, :, 1600 * n:1600 * n + 3200].copy()) for n in range(N)]
+    with torch.no_grad():
+        oracle.reset()
+        state = None
+        want = []
+        for c in chunks:
+            y, state = oracle.stream_step(c, state)
+            want.append(y.numpy())
+    want = np.concatenate(want, axis=-1)
+    model.reset()
+    small = np.concatenate([model.process_chunk(c.cuda()).cpu().numpy() for c in chunks], axis=-1)
+    tol = TOL[precision]
+    peak = max(1.0, float(np.abs(want).max()))
+    assert np.abs(small - want).max() < tol["wave_max_abs"] * peak
+    assert si_sdr_db(small[:, 1600:], want[:, 1600:]) > tol["si_sdr_vs_ref_db"]
+    perm = torch.from_numpy(np.random.default_rng(5).permutation(B) % D)
+    model.reset()
+    big = np.concatenate([model.process_chunk(c[perm].cuda()).cpu().numpy() for c in chunks], axis=-1)
+    # replicas differ from the small launch only through the order of the GLN statistics atomics (fp64) and tile borders
+    rep_tol = 2e-5 if precision == "fp32" else 2e-3
+    assert np.abs(big - small[perm.numpy()]).max() < rep_tol * peak
+    assert np.abs(big - want[perm.numpy()]).max() < tol["wave_max_abs"] * peak
