@@ -128,31 +128,61 @@ __device__ __forceinline__ void load8(const float* __restrict__ q, float* v) {
 // reciprocal / exponential of the mask sigmoid (the exact-order fp32 path is norm_apply_kernel above).
 template <int MODE>
 __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 4) norm_apply_h8_kernel(NormApplyParams p) {
+    constexpr int FB = MODE == 2 ? 4 : kNormFrames;  // frames per batch: all loads of a batch are issued before its first use
     const int t0 = blockIdx.x * kNormFrames;
     const int b = p.b0 + blockIdx.y;
     __shared__ float s_co[4];
-    if (threadIdx.x == 0) {
-        gln_coeffs(p.stats, b, p.count, p.student, s_co[0], s_co[1]);
-        if (MODE == 2) gln_coeffs(p.stats_r, b, p.count_r, p.student, s_co[2], s_co[3]);
-    }
-    __syncthreads();
-    const float mean = s_co[0], inv = s_co[1];
     const int C8 = p.C >> 3;
     const int n8 = p.F * C8;
     const int nt = min(kNormFrames, p.T - t0);
-    const __half* yh = reinterpret_cast<const __half*>(p.y);
-    const __half* rmh = reinterpret_cast<const __half*>(p.rm);
-    const __half* rrh = reinterpret_cast<const __half*>(p.rr);
-    __half* oh = reinterpret_cast<__half*>(p.out);
-    for (int j = threadIdx.x; j < n8; j += blockDim.x) {
+    const __half* yh = reinterpret_cast<const __half*>(p.y) + ((long long)b * p.T + t0) * p.Fy * p.C;
+    const __half* rmh = reinterpret_cast<const __half*>(p.rm) + ((long long)b * p.T + t0) * p.F * p.C;
+    const __half* rrh = reinterpret_cast<const __half*>(p.rr) + ((long long)b * p.T + t0) * p.F * p.C;
+    __half* oh = reinterpret_cast<__half*>(p.out) + b * p.oB + t0 * p.oT;
+    const int ystep = p.Fy * p.C, rstep = p.F * p.C;
+    bool first = true;
+    for (int j = threadIdx.x; first || j < n8; j += blockDim.x) {
+        const bool live = j < n8;  // only the first pass can be dead (every thread has to reach the barrier below)
         const int f = j / C8;
         const int c = (j - f * C8) * 8;
-        const bool has_y = f < p.Fy;
+        const bool has_y = live && f < p.Fy;
+        const int yo = f * p.C + c, ro = yo;  // offsets inside a frame (y rows hold Fy bins, the skip rows F bins)
         float a[8], d[8], ar[8], dr[8];
-        {
+        uint4 uy[FB], um[FB], ur[FB];
+        auto issue = [&](int tb) {
+#pragma unroll
+            for (int q = 0; q < FB; ++q) {
+                const int tl = tb + q;
+                uy[q] = make_uint4(0, 0, 0, 0);
+                if (tl < kNormFrames && tl < nt && live) {
+                    if (has_y) uy[q] = *reinterpret_cast<const uint4*>(yh + tl * ystep + yo);
+                    if (MODE == 2) {
+                        um[q] = *reinterpret_cast<const uint4*>(rmh + tl * rstep + ro);
+                        ur[q] = *reinterpret_cast<const uint4*>(rrh + tl * rstep + ro);
+                    }
+                }
+            }
+        };
+        // everything this unit reads is requested before the stream's statistics are needed
+        issue(0);
+        if (live) {
             const int wi = p.per_feature ? (f * p.C + c) : c;
             load8(p.w + wi, a);
             load8(p.b + wi, d);
+            if (MODE == 2) {
+                load8(p.wr + c, ar);
+                load8(p.br + c, dr);
+            }
+        }
+        if (first) {
+            if (threadIdx.x == 0) gln_coeffs(p.stats, b, p.count, p.student, s_co[0], s_co[1]);
+            if (MODE == 2 && threadIdx.x == 32) gln_coeffs(p.stats_r, b, p.count_r, p.student, s_co[2], s_co[3]);
+            __syncthreads();
+            first = false;
+        }
+        if (!live) break;
+        {
+            const float mean = s_co[0], inv = s_co[1];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 a[k] *= inv;
@@ -160,37 +190,17 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 4) norm_apply_h8_kernel(N
             }
         }
         if (MODE == 2) {
-            const float mr = s_co[2], ir = s_co[3];
-            load8(p.wr + c, ar);
-            load8(p.br + c, dr);
+            // the mask is 1 / (1 + 2^(-(x * ar + dr) * log2 e)): fold the sign and log2 e into the affine terms
+            const float mr = s_co[2], ir = s_co[3] * -1.4426950408889634f;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                ar[k] *= -ir;  // the sigmoid needs -(x * ar + dr)
-                dr[k] = fmaf(-mr, ar[k], -dr[k]);
+                ar[k] *= ir;
+                dr[k] = fmaf(-mr, ar[k], -1.4426950408889634f * dr[k]);
             }
         }
-        const __half* yp = yh + (((long long)b * p.T + t0) * p.Fy + f) * p.C + c;
-        const long long ystep = (long long)p.Fy * p.C;
-        const long long ri = (((long long)b * p.T + t0) * p.F + f) * p.C + c;
-        const long long rstep = (long long)p.F * p.C;
-        __half* op = oh + b * p.oB + t0 * p.oT + f * p.oF + c;
-        // frames in batches of FB: all loads of a batch are issued before its first use
-        constexpr int FB = MODE == 2 ? 4 : kNormFrames;
 #pragma unroll
         for (int tb = 0; tb < kNormFrames; tb += FB) {
-            uint4 uy[FB], um[FB], ur[FB];
-#pragma unroll
-            for (int q = 0; q < FB; ++q) {
-                const int tl = tb + q;
-                uy[q] = make_uint4(0, 0, 0, 0);
-                if (tl < kNormFrames && tl < nt) {
-                    if (has_y) uy[q] = *reinterpret_cast<const uint4*>(yp + tl * ystep);
-                    if (MODE == 2) {
-                        um[q] = *reinterpret_cast<const uint4*>(rmh + ri + tl * rstep);
-                        ur[q] = *reinterpret_cast<const uint4*>(rrh + ri + tl * rstep);
-                    }
-                }
-            }
+            if (tb > 0) issue(tb);
 #pragma unroll
             for (int q = 0; q < FB; ++q) {
                 const int tl = tb + q;
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 4) norm_apply_h8_kernel(N
                         unpack8(ur[q], rr);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            const float m = __fdividef(1.0f, 1.0f + __expf(fmaf(rm[k], ar[k], dr[k])));
+                            const float m = __fdividef(1.0f, 1.0f + exp2f(fmaf(rm[k], ar[k], dr[k])));
                             o[k] = fmaf(m, rr[k] - o[k], o[k]);
                         }
                     }
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 2 : 4) norm_apply_h8_kernel(N
                     __half2* ho = reinterpret_cast<__half2*>(&uo);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) ho[k] = __floats2half2_rn(o[2 * k], o[2 * k + 1]);
-                    *reinterpret_cast<uint4*>(op + tl * p.oT) = uo;
+                    *reinterpret_cast<uint4*>(oh + tl * p.oT + f * p.oF + c) = uo;
                 }
             }
         }
