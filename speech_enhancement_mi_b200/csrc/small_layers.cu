@@ -1,11 +1,15 @@
-// Direct CUDA-core kernels for the two layer shapes that the 128-row tensor-core tiles serve badly (fp16 operand mode):
+// Dedicated kernels for the two layer shapes that the 128-row tcgen05 tiles serve badly (fp16 operand mode):
 //   * the last transposed convolution (CRN_ELU.py:352-358, 16 -> 2 channels): the GEMM has N = 4 useful columns of a
 //     16-wide tile and gathers 9 taps x 16 channels per row -- 0.6 % of the tensor peak, 194 us per step;
 //   * the 1x1 mask / residual pair on a 16- (or 8-) channel skip tensor (CRN_ELU.py:305-306): K = 16 is padded to a
 //     64-element k-block, so 3/4 of the operand traffic and of the MMA work is zeros -- 151 us per step.
-// Both are a few hundred FMAs per output position on data that is read once: one thread per position, weights
-// broadcast from shared memory, per-stream GlobalLayerNorm statistics reduced per block.
+// Both read their data once.  Default: warp-level mma.sync kernels whose A fragments come straight from global memory
+// (second half of this file; 0.074 / 0.064 ms).  SE_B200_SMALL_MMA=0 selects the first generation kept for A/B runs:
+// one thread per position on the CUDA cores, weights broadcast from shared memory (0.112 / 0.110 ms, bound by the
+// shared-memory operand fetches).  Per-stream GlobalLayerNorm statistics are reduced per block in both.
 #include <cuda_fp16.h>
+
+#include <cstdlib>
 
 #include "se_internal.h"
 
@@ -177,6 +181,232 @@ __global__ void __launch_bounds__(256) skip_small_kernel(SkipSmallParams p) {
     block_stats(s, ss, p.stats, b);
 }
 
+// ---- warp-level tensor-core versions (mma.sync m16n8k16, fp16 operands, fp32 accumulate) ------------------------------
+// The CUDA-core kernels above are bound by the shared-memory operand fetches (one LDS per 1-3 FMAs: 110 us each, three
+// times their FMA and HBM bounds).  Both layers are tiny GEMMs over positions whose A rows are 16 consecutive fp16
+// channels in memory, so a warp loads the m16k16 A fragment of 16 consecutive positions straight from global memory
+// (4-byte loads, every 32-byte sector used whole), keeps the B fragments (weights, rounded to fp16 like every other
+// GEMM operand of this mode) in registers for its lifetime, and never touches shared memory.
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// D = A B + (c0, c1, c0, c1): the bias pair of the lane's two columns is the C operand, no accumulator initialisation
+__device__ __forceinline__ void mma16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1, float c0, float c1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+        : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+    const __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t ld_u32(const __half* q) { return __ldg(reinterpret_cast<const unsigned int*>(q)); }
+__device__ __forceinline__ uint2 ld_u64(const __half* q) { return __ldg(reinterpret_cast<const uint2*>(q)); }
+// The order of the 16 k slots of a step is free as long as A and B agree: with 16 channels per row, lane t supplies
+// channels 4t .. 4t+3 (slots 2t, 2t+1 <- channels 4t, 4t+1; slots 2t+8, 2t+9 <- channels 4t+2, 4t+3), one 8-byte load
+// per row; with 8 channels the upper slots are zero and lane t supplies channels 2t, 2t+1.
+
+// grid (2, B): the warps of a stream's blocks stride over its groups of 16 positions.  Fragment roles (g = lane / 4,
+// t = lane % 4): A rows g, g + 8 = positions, B column g = output channel of the n-tile, C columns 2t, 2t + 1.
+// n-tiles [0, C/8) are the mask channels, [C/8, C/4) the residual channels.
+template <int C>
+__global__ void __launch_bounds__(256) skip_small_mma_kernel(SkipSmallParams p) {
+    constexpr int NT = C / 4, HT = NT / 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    uint32_t bf[NT][2];
+    float bs[NT][2];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        const int kind = j / HT, ch0 = 8 * (j % HT);
+        const float* wr = p.w + (long long)(2 * (ch0 + g) + kind) * p.Kp;
+        if (C == 16) {
+            bf[j][0] = pack_h2(__ldg(wr + 4 * t), __ldg(wr + 4 * t + 1));
+            bf[j][1] = pack_h2(__ldg(wr + 4 * t + 2), __ldg(wr + 4 * t + 3));
+        } else {
+            bf[j][0] = pack_h2(__ldg(wr + 2 * t), __ldg(wr + 2 * t + 1));
+            bf[j][1] = 0u;
+        }
+        bs[j][0] = __ldg(p.bias + 2 * (ch0 + 2 * t) + kind);
+        bs[j][1] = __ldg(p.bias + 2 * (ch0 + 2 * t + 1) + kind);
+    }
+    const int b = blockIdx.y;
+    const int total = T * p.Fs;
+    const int ngroups = (total + 15) >> 4;
+    const int stride = gridDim.x * 8;
+    // everything below a stream's base pointers is 32-bit element arithmetic (a stream's buffers are far below 2^31)
+    const __half* in = p.in + (long long)b * p.sB + (C == 16 ? 4 : 2) * t;
+    const int sT = (int)p.sT, sF = (int)p.sF, Fs = p.Fs;
+    const bool odd = t & 1;  // even lanes store row g (their own pair + the neighbour's), odd lanes row g + 8
+    __half* rm = p.rm + (long long)b * total * C + 2 * (t & 2) + (odd ? 8 * C : 0);
+    __half* rr = p.rr + (long long)b * total * C + 2 * (t & 2) + (odd ? 8 * C : 0);
+    float s = 0.f, ss = 0.f;
+    // two groups per pass (both groups' loads are in flight together); the weights are fetched once per warp
+    for (int g0 = blockIdx.x * 8 + warp; g0 < ngroups; g0 += 2 * stride) {
+        int row0[2];
+        uint32_t a[2][4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int rb = (g0 + q * stride) * 16;  // warp-uniform: one division per group
+            const int tb = rb / Fs, fb = rb - tb * Fs;
+            row0[q] = rb + g;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                int tt = tb, f = fb + g + 8 * h;
+                if (f >= Fs) {  // Fs >= 16 (checked by the launcher): at most one wrap
+                    f -= Fs;
+                    ++tt;
+                }
+                if (tt >= T) {  // beyond the last position: computed on valid memory, never stored
+                    tt = T - 1;
+                    f = Fs - 1;
+                }
+                const __half* src = in + (tt * sT + f * sF);
+                if (C == 16) {
+                    const uint2 u = ld_u64(src);
+                    a[q][h] = u.x;
+                    a[q][2 + h] = u.y;
+                } else {
+                    a[q][h] = ld_u32(src);
+                    a[q][2 + h] = 0u;
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const bool v0 = row0[q] < total, v1 = row0[q] + 8 < total;
+            const bool ov = odd ? v1 : v0;
+            const int o = row0[q] * C;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                float c[4];
+                mma16816(c, a[q][0], a[q][1], a[q][2], a[q][3], bf[j][0], bf[j][1], bs[j][0], bs[j][1]);
+                const bool mask = j < HT;
+                if (mask) {
+                    if (v0) {
+                        s += c[0] + c[1];
+                        ss = fmaf(c[0], c[0], fmaf(c[1], c[1], ss));
+                    }
+                    if (v1) {
+                        s += c[2] + c[3];
+                        ss = fmaf(c[2], c[2], fmaf(c[3], c[3], ss));
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) c[k] = elu_fast(c[k]);
+                }
+                const uint32_t p0 = pack_h2(c[0], c[1]), p1 = pack_h2(c[2], c[3]);
+                const uint32_t got = __shfl_xor_sync(0xffffffffu, odd ? p0 : p1, 1);
+                const uint2 v = odd ? make_uint2(got, p1) : make_uint2(p0, got);
+                if (ov) *reinterpret_cast<uint2*>((mask ? rm : rr) + (o + 8 * (j % HT))) = v;
+            }
+        }
+    }
+    block_stats(s, ss, p.stats, b);
+}
+
+// grid (1, B): the warps of a stream's block stride over its (16 input bins f' = the rows of the fragment, frame) tasks.
+// K = 9 taps x CIN (one k-step per tap), N = 4 (n = parity * 2 + co) of an 8-wide tile: lanes t = 0 / 1 hold the even /
+// odd output bin of rows g, g + 8.
+template <int CIN>
+__global__ void __launch_bounds__(256) deconv_last_mma_kernel(DeconvLastParams p) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+    uint32_t bf[9][2];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        bf[tap][0] = bf[tap][1] = 0u;
+        if (g < 4) {
+            const float* wr = p.w + (long long)g * p.Kp + tap * CIN;
+            if (CIN == 16) {
+                bf[tap][0] = pack_h2(__ldg(wr + 4 * t), __ldg(wr + 4 * t + 1));
+                bf[tap][1] = pack_h2(__ldg(wr + 4 * t + 2), __ldg(wr + 4 * t + 3));
+            } else {
+                bf[tap][0] = pack_h2(__ldg(wr + 2 * t), __ldg(wr + 2 * t + 1));
+            }
+        }
+    }
+    const float b0 = t < 2 ? __ldg(p.bias + 2 * t) : 0.f, b1 = t < 2 ? __ldg(p.bias + 2 * t + 1) : 0.f;
+    const int b = blockIdx.y;
+    const int Fy = 2 * p.Fin - 1;
+    const int ntasks = ((p.Fin + 15) >> 4) * T;  // task = (group of 16 bins, frame), frame fastest: the warps of a
+    float s = 0.f, ss = 0.f;                      // block work on neighbouring frames of one group (shared input rows)
+    // everything below the stream's base pointer is 32-bit element arithmetic (a stream's buffer is far below 2^31)
+    const __half* in = p.in + (long long)b * p.sB + (CIN == 16 ? 4 : 2) * t;
+    const int sT = (int)p.sT, sF = (int)p.sF;
+    const int step = gridDim.x * 8;
+    auto fetch = [&](uint32_t (&a)[9][4], int task) {
+        if (task >= ntasks) return;
+        const int grp = task / T, tt = task - grp * T;
+        int ro[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int f = grp * 16 + g + 8 * h;
+            const int fl = f < p.Fin ? f : p.Fin - 1;  // clamped: computed on valid memory, never stored
+            ro[h] = fl * sF + tt * sT;
+        }
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int off = (2 - kt) * p.d * sT + (2 - j) * sF;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (CIN == 16) {
+                        const uint2 u = ld_u64(in + (ro[h] + off));
+                        a[kt * 3 + j][h] = u.x;
+                        a[kt * 3 + j][2 + h] = u.y;
+                    } else {
+                        a[kt * 3 + j][h] = ld_u32(in + (ro[h] + off));
+                        a[kt * 3 + j][2 + h] = 0u;
+                    }
+                }
+            }
+        }
+    };
+    auto compute = [&](const uint32_t (&a)[9][4], int task) {
+        const int grp = task / T, tt = task - grp * T;
+        // two accumulation chains (even / odd taps) halve the dependent-mma latency
+        float c[4] = {b0, b1, b0, b1}, c2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            if (tap & 1) mma16816(c2, a[tap][0], a[tap][1], a[tap][2], a[tap][3], bf[tap][0], bf[tap][1]);
+            else mma16816(c, a[tap][0], a[tap][1], a[tap][2], a[tap][3], bf[tap][0], bf[tap][1]);
+        }
+        if (t < 2) {  // t = parity of the output bin
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int f = grp * 16 + g + 8 * h;
+                if (f < p.Fin && (t == 0 || f < p.Fin - 1)) {
+                    const float e0 = elu_fast(c[2 * h] + c2[2 * h]), e1 = elu_fast(c[2 * h + 1] + c2[2 * h + 1]);
+                    reinterpret_cast<float2*>(p.y)[((long long)b * T + tt) * Fy + 2 * f + t] = make_float2(e0, e1);
+                    s += e0 + e1;
+                    ss += e0 * e0 + e1 * e1;
+                }
+            }
+        }
+    };
+    // software pipeline over the warp's tasks: the fragments of the next task are requested before the current one is
+    // multiplied (two register sets, ping-pong), so the DRAM latency of a task hides behind its predecessor
+    uint32_t fa[9][4], fb[9][4];
+    int task = blockIdx.x * 8 + warp;
+    fetch(fa, task);
+    while (task < ntasks) {
+        fetch(fb, task + step);
+        compute(fa, task);
+        task += step;
+        if (task >= ntasks) break;
+        fetch(fa, task + step);
+        compute(fb, task);
+        task += step;
+    }
+    block_stats(s, ss, p.stats, b);
+}
+
 }  // namespace
 
 bool deconv_last_supported(int Cin) { return Cin == 8 || Cin == 16; }
@@ -185,9 +415,12 @@ bool skip_small_supported(int C) { return C == 8 || C == 16; }
 int launch_deconv_last(const DeconvLastParams& p, int Cin, cudaStream_t st) {
     if (p.B <= 0) return 0;
     SE_REQUIRE(p.B <= 65535, "deconv_last: at most 65535 streams per launch");
-    const dim3 grid((p.Fin + 31) / 32, p.B);
-    if (Cin == 16) deconv_last_kernel<16><<<grid, 256, 0, st>>>(p);
-    else if (Cin == 8) deconv_last_kernel<8><<<grid, 256, 0, st>>>(p);
+    static const bool cuda_cores = getenv("SE_B200_SMALL_MMA") && atoi(getenv("SE_B200_SMALL_MMA")) == 0;  // A/B switch
+    const dim3 grid(cuda_cores ? (p.Fin + 31) / 32 : 1, p.B);  // one block per stream: fewer, longer blocks measured fastest
+    if (cuda_cores && Cin == 16) deconv_last_kernel<16><<<grid, 256, 0, st>>>(p);
+    else if (cuda_cores && Cin == 8) deconv_last_kernel<8><<<grid, 256, 0, st>>>(p);
+    else if (Cin == 16) deconv_last_mma_kernel<16><<<grid, 256, 0, st>>>(p);
+    else if (Cin == 8) deconv_last_mma_kernel<8><<<grid, 256, 0, st>>>(p);
     else SE_REQUIRE(false, "deconv_last: input channels must be 8 or 16");
     SE_CUDA_OK(cudaGetLastError());
     return 0;
@@ -196,9 +429,13 @@ int launch_deconv_last(const DeconvLastParams& p, int Cin, cudaStream_t st) {
 int launch_skip_small(const SkipSmallParams& p, int C, cudaStream_t st) {
     if (p.B <= 0) return 0;
     SE_REQUIRE(p.B <= 65535, "skip_small: at most 65535 streams per launch");
-    const dim3 grid((T * p.Fs + 255) / 256, p.B);
-    if (C == 16) skip_small_kernel<16><<<grid, 256, 0, st>>>(p);
-    else if (C == 8) skip_small_kernel<8><<<grid, 256, 0, st>>>(p);
+    SE_REQUIRE(p.Fs >= 16, "skip_small: at least 16 bins");
+    static const bool cuda_cores = getenv("SE_B200_SMALL_MMA") && atoi(getenv("SE_B200_SMALL_MMA")) == 0;  // A/B switch
+    const dim3 grid(cuda_cores ? (T * p.Fs + 255) / 256 : 2, p.B);
+    if (cuda_cores && C == 16) skip_small_kernel<16><<<grid, 256, 0, st>>>(p);
+    else if (cuda_cores && C == 8) skip_small_kernel<8><<<grid, 256, 0, st>>>(p);
+    else if (C == 16) skip_small_mma_kernel<16><<<grid, 256, 0, st>>>(p);
+    else if (C == 8) skip_small_mma_kernel<8><<<grid, 256, 0, st>>>(p);
     else SE_REQUIRE(false, "skip_small: channels must be 8 or 16");
     SE_CUDA_OK(cudaGetLastError());
     return 0;
