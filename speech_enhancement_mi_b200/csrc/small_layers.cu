@@ -212,46 +212,59 @@ __device__ __forceinline__ uint2 ld_u64(const __half* q) { return __ldg(reinterp
 // channels 4t .. 4t+3 (slots 2t, 2t+1 <- channels 4t, 4t+1; slots 2t+8, 2t+9 <- channels 4t+2, 4t+3), one 8-byte load
 // per row; with 8 channels the upper slots are zero and lane t supplies channels 2t, 2t+1.
 
-// grid (2, B): the warps of a stream's blocks stride over its groups of 16 positions.  Fragment roles (g = lane / 4,
+// grid (gx, B): the warps of a stream's blocks stride over its groups of 16 positions.  Fragment roles (g = lane / 4,
 // t = lane % 4): A rows g, g + 8 = positions, B column g = output channel of the n-tile, C columns 2t, 2t + 1.
-// n-tiles [0, C/8) are the mask channels, [C/8, C/4) the residual channels.
-template <int C>
+// n-tiles [0, C/8) are the mask channels, [C/8, C/4) the residual channels.  Lane t supplies the CPL = C/4 consecutive
+// channels CPL t .. CPL t + CPL - 1 of its rows (one 8 / 16 / 2 x 16 byte load per row); k-step s consumes elements
+// 4s .. 4s+3 of that chunk.  NSPLIT > 1 splits the n-tiles over neighbouring warps that read the same rows; measured for
+// C = 64 (NSPLIT = 2, 64 registers of B fragments): 0.148 ms against 0.094 ms of the tcgen05 GEMM, whose 128-wide tile is
+// full at that width -- so 64 channels stay on the GEMM path and the dispatch below stops at 32 (0.099 -> 0.078 ms).
+template <int C, int NSPLIT, int GQ>
 __global__ void __launch_bounds__(256) skip_small_mma_kernel(SkipSmallParams p) {
-    constexpr int NT = C / 4, HT = NT / 2;
+    constexpr int NT = C / 4, HT = NT / 2;          // n-tiles, n-tiles per kind
+    constexpr int KS = C >= 16 ? C / 16 : 1;        // k-steps
+    constexpr int CPL = C >= 16 ? C / 4 : 2;        // channels per lane and row
+    constexpr int NTW = NT / NSPLIT;                // n-tiles of this warp
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-    uint32_t bf[NT][2];
-    float bs[NT][2];
+    const int ns = warp % NSPLIT, wg = warp / NSPLIT;  // n-split index, group-worker index
+    uint32_t bf[NTW][KS][2];
+    float bs[NTW][2];
 #pragma unroll
-    for (int j = 0; j < NT; ++j) {
+    for (int jj = 0; jj < NTW; ++jj) {
+        const int j = ns * NTW + jj;
         const int kind = j / HT, ch0 = 8 * (j % HT);
-        const float* wr = p.w + (long long)(2 * (ch0 + g) + kind) * p.Kp;
-        if (C == 16) {
-            bf[j][0] = pack_h2(__ldg(wr + 4 * t), __ldg(wr + 4 * t + 1));
-            bf[j][1] = pack_h2(__ldg(wr + 4 * t + 2), __ldg(wr + 4 * t + 3));
-        } else {
-            bf[j][0] = pack_h2(__ldg(wr + 2 * t), __ldg(wr + 2 * t + 1));
-            bf[j][1] = 0u;
+        const float* wr = p.w + (long long)(2 * (ch0 + g) + kind) * p.Kp + CPL * t;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+            if (C >= 16) {  // 16-byte aligned: Kp and the arena offsets are multiples of 4 floats
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(wr) + ks);
+                bf[jj][ks][0] = pack_h2(w4.x, w4.y);
+                bf[jj][ks][1] = pack_h2(w4.z, w4.w);
+            } else {
+                bf[jj][ks][0] = pack_h2(__ldg(wr), __ldg(wr + 1));
+                bf[jj][ks][1] = 0u;
+            }
         }
-        bs[j][0] = __ldg(p.bias + 2 * (ch0 + 2 * t) + kind);
-        bs[j][1] = __ldg(p.bias + 2 * (ch0 + 2 * t + 1) + kind);
+        bs[jj][0] = __ldg(p.bias + 2 * (ch0 + 2 * t) + kind);
+        bs[jj][1] = __ldg(p.bias + 2 * (ch0 + 2 * t + 1) + kind);
     }
     const int b = blockIdx.y;
     const int total = T * p.Fs;
     const int ngroups = (total + 15) >> 4;
-    const int stride = gridDim.x * 8;
+    const int stride = gridDim.x * (8 / NSPLIT);
     // everything below a stream's base pointers is 32-bit element arithmetic (a stream's buffers are far below 2^31)
-    const __half* in = p.in + (long long)b * p.sB + (C == 16 ? 4 : 2) * t;
+    const __half* in = p.in + (long long)b * p.sB + CPL * t;
     const int sT = (int)p.sT, sF = (int)p.sF, Fs = p.Fs;
     const bool odd = t & 1;  // even lanes store row g (their own pair + the neighbour's), odd lanes row g + 8
     __half* rm = p.rm + (long long)b * total * C + 2 * (t & 2) + (odd ? 8 * C : 0);
     __half* rr = p.rr + (long long)b * total * C + 2 * (t & 2) + (odd ? 8 * C : 0);
     float s = 0.f, ss = 0.f;
-    // two groups per pass (both groups' loads are in flight together); the weights are fetched once per warp
-    for (int g0 = blockIdx.x * 8 + warp; g0 < ngroups; g0 += 2 * stride) {
-        int row0[2];
-        uint32_t a[2][4];
+    // GQ groups per pass (their loads are in flight together); the weights are fetched once per warp
+    for (int g0 = blockIdx.x * (8 / NSPLIT) + wg; g0 < ngroups; g0 += GQ * stride) {
+        int row0[GQ];
+        uint32_t a[GQ][KS][4];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < GQ; ++q) {
             const int rb = (g0 + q * stride) * 16;  // warp-uniform: one division per group
             const int tb = rb / Fs, fb = rb - tb * Fs;
             row0[q] = rb + g;
@@ -267,26 +280,39 @@ __global__ void __launch_bounds__(256) skip_small_mma_kernel(SkipSmallParams p) 
                     f = Fs - 1;
                 }
                 const __half* src = in + (tt * sT + f * sF);
-                if (C == 16) {
+                if (C >= 32) {
+#pragma unroll
+                    for (int u = 0; u < CPL / 8; ++u) {
+                        const uint4 v = __ldg(reinterpret_cast<const uint4*>(src) + u);
+                        a[q][2 * u][h] = v.x;
+                        a[q][2 * u][2 + h] = v.y;
+                        a[q][2 * u + 1][h] = v.z;
+                        a[q][2 * u + 1][2 + h] = v.w;
+                    }
+                } else if (C == 16) {
                     const uint2 u = ld_u64(src);
-                    a[q][h] = u.x;
-                    a[q][2 + h] = u.y;
+                    a[q][0][h] = u.x;
+                    a[q][0][2 + h] = u.y;
                 } else {
-                    a[q][h] = ld_u32(src);
-                    a[q][2 + h] = 0u;
+                    a[q][0][h] = ld_u32(src);
+                    a[q][0][2 + h] = 0u;
                 }
             }
         }
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
+        for (int q = 0; q < GQ; ++q) {
             const bool v0 = row0[q] < total, v1 = row0[q] + 8 < total;
             const bool ov = odd ? v1 : v0;
             const int o = row0[q] * C;
 #pragma unroll
-            for (int j = 0; j < NT; ++j) {
+            for (int jj = 0; jj < NTW; ++jj) {
+                const int j = ns * NTW + jj;
                 float c[4];
-                mma16816(c, a[q][0], a[q][1], a[q][2], a[q][3], bf[j][0], bf[j][1], bs[j][0], bs[j][1]);
-                const bool mask = j < HT;
+                mma16816(c, a[q][0][0], a[q][0][1], a[q][0][2], a[q][0][3], bf[jj][0][0], bf[jj][0][1], bs[jj][0], bs[jj][1]);
+#pragma unroll
+                for (int ks = 1; ks < KS; ++ks)
+                    mma16816(c, a[q][ks][0], a[q][ks][1], a[q][ks][2], a[q][ks][3], bf[jj][ks][0], bf[jj][ks][1]);
+                const bool mask = j < HT;  // warp-uniform
                 if (mask) {
                     if (v0) {
                         s += c[0] + c[1];
@@ -410,7 +436,7 @@ __global__ void __launch_bounds__(256) deconv_last_mma_kernel(DeconvLastParams p
 }  // namespace
 
 bool deconv_last_supported(int Cin) { return Cin == 8 || Cin == 16; }
-bool skip_small_supported(int C) { return C == 8 || C == 16; }
+bool skip_small_supported(int C) { return C == 8 || C == 16 || C == 32; }
 
 int launch_deconv_last(const DeconvLastParams& p, int Cin, cudaStream_t st) {
     if (p.B <= 0) return 0;
@@ -431,12 +457,14 @@ int launch_skip_small(const SkipSmallParams& p, int C, cudaStream_t st) {
     SE_REQUIRE(p.B <= 65535, "skip_small: at most 65535 streams per launch");
     SE_REQUIRE(p.Fs >= 16, "skip_small: at least 16 bins");
     static const bool cuda_cores = getenv("SE_B200_SMALL_MMA") && atoi(getenv("SE_B200_SMALL_MMA")) == 0;  // A/B switch
-    const dim3 grid(cuda_cores ? (T * p.Fs + 255) / 256 : 2, p.B);
-    if (cuda_cores && C == 16) skip_small_kernel<16><<<grid, 256, 0, st>>>(p);
-    else if (cuda_cores && C == 8) skip_small_kernel<8><<<grid, 256, 0, st>>>(p);
-    else if (C == 16) skip_small_mma_kernel<16><<<grid, 256, 0, st>>>(p);
-    else if (C == 8) skip_small_mma_kernel<8><<<grid, 256, 0, st>>>(p);
-    else SE_REQUIRE(false, "skip_small: channels must be 8 or 16");
+    const bool cc = cuda_cores && C <= 16;
+    const dim3 grid(cc ? (T * p.Fs + 255) / 256 : (C <= 16 ? 2 : 1), p.B);
+    if (cc && C == 16) skip_small_kernel<16><<<grid, 256, 0, st>>>(p);
+    else if (cc && C == 8) skip_small_kernel<8><<<grid, 256, 0, st>>>(p);
+    else if (C == 32) skip_small_mma_kernel<32, 1, 1><<<grid, 256, 0, st>>>(p);
+    else if (C == 16) skip_small_mma_kernel<16, 1, 2><<<grid, 256, 0, st>>>(p);
+    else if (C == 8) skip_small_mma_kernel<8, 1, 2><<<grid, 256, 0, st>>>(p);
+    else SE_REQUIRE(false, "skip_small: channels must be 8, 16 or 32");
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
