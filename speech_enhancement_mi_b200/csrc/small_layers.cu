@@ -441,7 +441,7 @@ bool skip_small_supported(int C) { return C == 8 || C == 16 || C == 32; }
 int launch_deconv_last(const DeconvLastParams& p, int Cin, cudaStream_t st) {
     if (p.B <= 0) return 0;
     SE_REQUIRE(p.B <= 65535, "deconv_last: at most 65535 streams per launch");
-    static const bool cuda_cores = getenv("SE_B200_SMALL_MMA") && atoi(getenv("SE_B200_SMALL_MMA")) == 0;  // A/B switch
+    const bool cuda_cores = getenv("SE_B200_SMALL_MMA") && atoi(getenv("SE_B200_SMALL_MMA")) == 0;  // A/B switch
     const dim3 grid(cuda_cores ? (p.Fin + 31) / 32 : 1, p.B);  // one block per stream: fewer, longer blocks measured fastest
     if (cuda_cores && Cin == 16) deconv_last_kernel<16><<<grid, 256, 0, st>>>(p);
     else if (cuda_cores && Cin == 8) deconv_last_kernel<8><<<grid, 256, 0, st>>>(p);
@@ -456,7 +456,7 @@ int launch_skip_small(const SkipSmallParams& p, int C, cudaStream_t st) {
     if (p.B <= 0) return 0;
     SE_REQUIRE(p.B <= 65535, "skip_small: at most 65535 streams per launch");
     SE_REQUIRE(p.Fs >= 16, "skip_small: at least 16 bins");
-    static const bool cuda_cores = getenv("SE_B200_SMALL_MMA") && atoi(getenv("SE_B200_SMALL_MMA")) == 0;  // A/B switch
+    const bool cuda_cores = getenv("SE_B200_SMALL_MMA") && atoi(getenv("SE_B200_SMALL_MMA")) == 0;  // A/B switch
     const bool cc = cuda_cores && C <= 16;
     const dim3 grid(cc ? (T * p.Fs + 255) / 256 : (C <= 16 ? 2 : 1), p.B);
     if (cc && C == 16) skip_small_kernel<16><<<grid, 256, 0, st>>>(p);

@@ -203,6 +203,27 @@ def test_fp16_preconv_variants_match_reference(monkeypatch, tc):
         assert np.abs(y2 - g["out_cont"]).max() < tol["wave_max_abs"] * max(1.0, np.abs(g["out_cont"]).max())
 
 
+@pytest.mark.parametrize("variant", ["mma", "cuda_cores", "gemm"])
+def test_fp16_small_layer_variants_match_reference(monkeypatch, variant):
+    """The last transposed convolution and the 8/16/32-channel skip 1x1 pairs run on warp-level mma.sync kernels in fp16
+    mode (small_layers.cu); SE_B200_SMALL_MMA=0 keeps the CUDA-core generation, SE_B200_SMALL_LAYERS=0 the tcgen05 GEMM
+    path.  All three against the reference fixtures (small / teacher / student shapes) at the stated fp16 tolerance."""
+    if variant == "cuda_cores":
+        monkeypatch.setenv("SE_B200_SMALL_MMA", "0")
+    elif variant == "gemm":
+        monkeypatch.setenv("SE_B200_SMALL_LAYERS", "0")
+    for tag in CONFIGS:
+        g = load_golden(tag)
+        tol = TOL["fp16"]
+        model = make_model(tag, "fp16")
+        B, L = int(g["meta"][1]), int(g["meta"][2])
+        mix, _ = synth.make_mixture(B, L)
+        y = model.realtime_process(torch.from_numpy(mix).cuda())
+        y = (y[0] if isinstance(y, tuple) else y).cpu().numpy()
+        assert np.abs(y - g["out"]).max() < tol["wave_max_abs"] * max(1.0, np.abs(g["out"]).max()), tag
+        assert si_sdr_db(y, g["out"]) > tol["si_sdr_vs_ref_db"], tag
+
+
 @pytest.mark.parametrize("precision", ["fp16", "fp32"])
 def test_full_size_1024_streams_replicas_match_oracle_checked_streams(precision):
     """BASELINE configs[1] size (teacher, 1024 concurrent streams, the bench's precision): 8 distinct streams are checked
