@@ -30,9 +30,11 @@ constexpr int GROUP = 7;            // frames handled per pass
 constexpr int ROW = 21;             // padded row length (float2) of the 20x20 intermediate
 
 __constant__ float2 c_w20[20];    // exp(-2 pi i j / 20)
-__constant__ float2 c_w400[400];  // exp(-2 pi i j / 400)
-__constant__ float c_window[NFFT];
-__constant__ float c_env[K];  // sum_t w^2 at output positions (istft window envelope, trimmed)
+// tables indexed per thread live in global memory: a warp reading 32 different words of a __constant__ array is served
+// one word at a time (the constant cache broadcasts, it does not gather)
+__device__ float2 c_w400[400];  // exp(-2 pi i j / 400)
+__device__ float c_window[NFFT];
+__device__ float c_env[K];  // sum_t w^2 at output positions (istft window envelope, trimmed)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
