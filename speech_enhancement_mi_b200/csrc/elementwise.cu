@@ -254,15 +254,28 @@ __global__ void __launch_bounds__(256) gru_pointwise_kernel(const float* __restr
     }
 }
 
+// grid (slices, B): a block moves one slice of kRollSlice floats of one entry of one stream; the launcher lays the
+// entries' slices end to end (no empty blocks), four 16-byte loads per thread are in flight before the first store
+constexpr int kRollSlice = 4096;
 __global__ void __launch_bounds__(256) roll_kernel(RollTable tab, int first, int zero) {
-    const RollEntry e = tab.e[blockIdx.y];
-    const int b = first + blockIdx.z;
+    int ei = 0;
+    while (ei + 1 < tab.n && (int)blockIdx.x >= tab.first_block[ei + 1]) ++ei;
+    const RollEntry e = tab.e[ei];
+    const int b = first + blockIdx.y;
     float* base = e.base + b * e.sB;
     const int n4 = e.count >> 2;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!zero) v = *reinterpret_cast<const float4*>(base + e.src_off + 4 * i);
-        *reinterpret_cast<float4*>(base + e.dst_off + 4 * i) = v;
+    const int i0 = ((int)blockIdx.x - tab.first_block[ei]) * (kRollSlice / 4) + threadIdx.x;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int i = i0 + 256 * k;
+        if (!zero && i < n4) v[k] = *reinterpret_cast<const float4*>(base + e.src_off + 4 * i);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int i = i0 + 256 * k;
+        if (i < n4) *reinterpret_cast<float4*>(base + e.dst_off + 4 * i) = v[k];
     }
 }
 
@@ -338,16 +351,20 @@ int launch_gru_pointwise(const float* gi, long long giB, const float* gh, const 
     return 0;
 }
 
-static int roll_or_zero(const RollTable& tab, int first, int B, int zero, cudaStream_t st) {
-    if (B == 0 || tab.n == 0) return 0;
-    int maxc = 0;
-    for (int i = 0; i < tab.n; ++i) maxc = tab.e[i].count > maxc ? tab.e[i].count : maxc;
-    int gx = (maxc / 4 + 255) / 256;
-    gx = gx < 1 ? 1 : (gx > 32 ? 32 : gx);
-    // gridDim.z is limited to 65535 streams per launch
+static int roll_or_zero(const RollTable& tab_in, int first, int B, int zero, cudaStream_t st) {
+    if (B == 0 || tab_in.n == 0) return 0;
+    RollTable tab = tab_in;
+    int blocks = 0;
+    for (int i = 0; i < tab.n; ++i) {
+        tab.first_block[i] = blocks;
+        blocks += (tab.e[i].count + kRollSlice - 1) / kRollSlice;
+    }
+    tab.first_block[tab.n] = blocks;
+    if (blocks == 0) return 0;
+    // gridDim.y is limited to 65535 streams per launch
     for (int off = 0; off < B; off += 65535) {
         const int nb = (B - off) < 65535 ? (B - off) : 65535;
-        roll_kernel<<<dim3(gx, tab.n, nb), 256, 0, st>>>(tab, first + off, zero);
+        roll_kernel<<<dim3(blocks, nb), 256, 0, st>>>(tab, first + off, zero);
         SE_CUDA_OK(cudaGetLastError());
     }
     return 0;

@@ -182,6 +182,7 @@ struct RollEntry {
 struct RollTable {
     RollEntry e[24];
     int n;
+    int first_block[25];  // filled by the launcher: blocks [first_block[i], first_block[i+1]) serve entry i
 };
 int launch_roll(const RollTable& tab, int first, int B, cudaStream_t st);
 int launch_zero(const RollTable& tab, int first, int B, cudaStream_t st);  // zero [dst_off, dst_off+count)
