@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(448, 2) stft_features_kernel(StftParams p) {
     constexpr float kC20[20] = {1.0f, 0.951056516f, 0.809016994f, 0.587785252f, 0.309016994f, 0.0f, -0.309016994f, -0.587785252f, -0.809016994f, -0.951056516f, -1.0f, -0.951056516f, -0.809016994f, -0.587785252f, -0.309016994f, 0.0f, 0.309016994f, 0.587785252f, 0.809016994f, 0.951056516f};
     constexpr float kS20[20] = {0.0f, -0.309016994f, -0.587785252f, -0.809016994f, -0.951056516f, -1.0f, -0.951056516f, -0.809016994f, -0.587785252f, -0.309016994f, 0.0f, 0.309016994f, 0.587785252f, 0.809016994f, 0.951056516f, 1.0f, 0.951056516f, 0.809016994f, 0.587785252f, 0.309016994f};
     // ---- stage 1: per (mic, frame, n2) the 20-point DFT over n1 of the windowed real samples, k1 = 0..10 (the rest by
-    //      Hermitian symmetry), then the twiddle W400^(n2 k1).  20 loads feed 440 FMAs held in registers.
+    //      Hermitian symmetry), then the twiddle W400^(n2 k1).  20 loads feed 200 FMAs held in registers.
     for (int u = tid; u < M * GROUP * 20; u += blockDim.x) {
         const int n2 = u % 20;
         const int fr = (u / 20) % GROUP;
@@ -96,13 +96,20 @@ __global__ void __launch_bounds__(448, 2) stft_features_kernel(StftParams p) {
         float v[20];
 #pragma unroll
         for (int n1 = 0; n1 < 20; ++n1) v[n1] = x[20 * n1 + n2] * s.win[20 * n1 + n2];
+        // W^((20-n) k) = conj(W^(n k)): inputs n and 20-n share a twiddle, so the sums run over their sum / difference
+        float sp[10], dm[10];
+#pragma unroll
+        for (int n1 = 1; n1 <= 9; ++n1) {
+            sp[n1] = v[n1] + v[20 - n1];
+            dm[n1] = v[n1] - v[20 - n1];
+        }
 #pragma unroll
         for (int k1 = 0; k1 <= 10; ++k1) {
-            float re = 0.f, im = 0.f;
+            float re = (k1 & 1) ? v[0] - v[10] : v[0] + v[10], im = 0.f;
 #pragma unroll
-            for (int n1 = 0; n1 < 20; ++n1) {
-                re = fmaf(v[n1], kC20[(n1 * k1) % 20], re);
-                im = fmaf(v[n1], kS20[(n1 * k1) % 20], im);
+            for (int n1 = 1; n1 <= 9; ++n1) {
+                re = fmaf(sp[n1], kC20[(n1 * k1) % 20], re);
+                im = fmaf(dm[n1], kS20[(n1 * k1) % 20], im);
             }
             s.y[m][fr][k1][n2] = make_float2(re, im);
         }
@@ -121,18 +128,26 @@ __global__ void __launch_bounds__(448, 2) stft_features_kernel(StftParams p) {
             const float2 v = s.y[m][fr][kr][n2];
             yr[n2] = cmul(make_float2(v.x, sg * v.y), s.w400[n2 * k1]);  // twiddle W400^(n2 k1)
         }
+        float2 sp2[10], dm2[10];
+#pragma unroll
+        for (int n2 = 1; n2 <= 9; ++n2) {
+            sp2[n2] = make_float2(yr[n2].x + yr[20 - n2].x, yr[n2].y + yr[20 - n2].y);
+            dm2[n2] = make_float2(yr[n2].x - yr[20 - n2].x, yr[n2].y - yr[20 - n2].y);
+        }
 #pragma unroll
         for (int k2 = 0; k2 <= 10; ++k2) {
             const int k = k1 + 20 * k2;
             if (k < NBIN) {
-                float re = 0.f, im = 0.f;
+                // y[n] W + y[20-n] conj(W) = (sp.x c - dm.y s, dm.x s + sp.y c), sp / dm = sum / difference of the pair
+                float re = (k2 & 1) ? yr[0].x - yr[10].x : yr[0].x + yr[10].x;
+                float im = (k2 & 1) ? yr[0].y - yr[10].y : yr[0].y + yr[10].y;
 #pragma unroll
-                for (int n2 = 0; n2 < 20; ++n2) {
+                for (int n2 = 1; n2 <= 9; ++n2) {
                     const float wc = kC20[(n2 * k2) % 20], ws = kS20[(n2 * k2) % 20];
-                    re = fmaf(yr[n2].x, wc, re);
-                    re = fmaf(-yr[n2].y, ws, re);
-                    im = fmaf(yr[n2].x, ws, im);
-                    im = fmaf(yr[n2].y, wc, im);
+                    re = fmaf(sp2[n2].x, wc, re);
+                    re = fmaf(-dm2[n2].y, ws, re);
+                    im = fmaf(dm2[n2].x, ws, im);
+                    im = fmaf(sp2[n2].y, wc, im);
                 }
                 // DC and Nyquist bins of a real signal are exactly real (pocketfft r2c returns +0 there)
                 if (k == 0 || k == NBIN - 1) im = 0.f;
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(256, 3) mask_istft_kernel(MaskIstftParams p) {
         constexpr float kS20[20] = {0.0f, -0.309016994f, -0.587785252f, -0.809016994f, -0.951056516f, -1.0f, -0.951056516f, -0.809016994f, -0.587785252f, -0.309016994f, 0.0f, 0.309016994f, 0.587785252f, 0.809016994f, 0.951056516f, 1.0f, 0.951056516f, 0.809016994f, 0.587785252f, 0.309016994f};
         // ---- stage A: z[k1][n2] = sum_k2 Xfull[k1 + 20 k2] * conj(W20)^(n2 k2), then * conj(W400)^(n2 k1) -------
         // register-blocked like the forward transform: a thread loads the 20 inputs of one (frame, k1) once and produces
-        // 10 of the 20 outputs with immediate twiddles (40 loads feed 800 FMAs; the loop version spent 40 shared-memory
+        // 10 of the 20 outputs with immediate twiddles (40 loads feed 360 FMAs; the loop version spent 40 shared-memory
         // loads per 80 FMAs)
         for (int o = tid; o < GROUP * 11 * 2; o += blockDim.x) {
             const int half = o & 1;
@@ -330,18 +345,24 @@ __global__ void __launch_bounds__(256, 3) mask_istft_kernel(MaskIstftParams p) {
                     v[k2].y = -v[k2].y;
                 }
             }
+            // v[k] conj(w) + v[20-k] w = (sp.x c + dm.y s, sp.y c - dm.x s), sp / dm = sum / difference of the pair
+            float2 sp[10], dm[10];
+#pragma unroll
+            for (int k2 = 1; k2 <= 9; ++k2) {
+                sp[k2] = make_float2(v[k2].x + v[20 - k2].x, v[k2].y + v[20 - k2].y);
+                dm[k2] = make_float2(v[k2].x - v[20 - k2].x, v[k2].y - v[20 - k2].y);
+            }
             auto emit = [&](auto n2c) {
                 constexpr int n2 = decltype(n2c)::value;
-                float re = 0.f, im = 0.f;
+                float re = (n2 & 1) ? v[0].x - v[10].x : v[0].x + v[10].x;
+                float im = (n2 & 1) ? v[0].y - v[10].y : v[0].y + v[10].y;
 #pragma unroll
-                for (int k2 = 0; k2 < 20; ++k2) {  // v * conj(w), w = (kC20, kS20)[(n2 k2) % 20]
-                    constexpr int dummy = 0;
-                    (void)dummy;
+                for (int k2 = 1; k2 <= 9; ++k2) {  // w = (kC20, kS20)[(n2 k2) % 20]
                     const float wc = kC20[(n2 * k2) % 20], ws = kS20[(n2 * k2) % 20];
-                    re = fmaf(v[k2].x, wc, re);
-                    re = fmaf(v[k2].y, ws, re);
-                    im = fmaf(v[k2].y, wc, im);
-                    im = fmaf(-v[k2].x, ws, im);
+                    re = fmaf(sp[k2].x, wc, re);
+                    re = fmaf(dm[k2].y, ws, re);
+                    im = fmaf(sp[k2].y, wc, im);
+                    im = fmaf(-dm[k2].x, ws, im);
                 }
                 s.z[fr][k1][n2] = cmul_conj(make_float2(re, im), s.w400[n2 * k1]);
             };

@@ -239,20 +239,35 @@ def test_full_size_1024_streams_replicas_match_oracle_checked_streams(precision)
         oracle.reset()
         state = None
         want = []
+        on_cut = torch.zeros(D, dtype=torch.bool)
         for c in chunks:
+            # The reference's phase feature is an UNWRAPPED atan2 (CRN_ELU.py:370-371): a bin on the negative real axis
+            # whose imaginary part is rounding noise (here 1.8e-7 vs -8.5e-8 next to a spectrum peak of 48) gets +pi or
+            # -pi depending on the last bit of the FFT, and the feature jumps by 2 pi.  Both results are valid roundings
+            # of the same signal, but such a stream cannot be compared at the fp32 tolerance: streams whose two spectra
+            # (both within 2e-7 of the peak of each other, asserted) land on different sides of the cut are left out of
+            # the tight check and held to the fp16 tolerance instead.
+            xo = oracle.stft_trans(c)
+            xc = model.stft_trans(c.cuda()).cpu()
+            assert (xo - xc).abs().max() < 1e-6 * xo.abs().max()
+            jump = (torch.atan2(xo[..., 1], xo[..., 0]) - torch.atan2(xc[..., 1], xc[..., 0])).abs() > 3.0
+            on_cut |= jump.flatten(1).any(1)
             y, state = oracle.stream_step(c, state)
             want.append(y.numpy())
     want = np.concatenate(want, axis=-1)
+    keep = (~on_cut).numpy()
+    assert keep.sum() >= D // 2
     model.reset()
     small = np.concatenate([model.process_chunk(c.cuda()).cpu().numpy() for c in chunks], axis=-1)
     tol = TOL[precision]
     peak = max(1.0, float(np.abs(want).max()))
-    assert np.abs(small - want).max() < tol["wave_max_abs"] * peak
-    assert si_sdr_db(small[:, 1600:], want[:, 1600:]) > tol["si_sdr_vs_ref_db"]
+    assert np.abs(small - want)[keep].max() < tol["wave_max_abs"] * peak
+    assert np.abs(small - want).max() < TOL["fp16"]["wave_max_abs"] * peak  # streams on the cut: still the same signal
+    assert si_sdr_db(small[keep][:, 1600:], want[keep][:, 1600:]) > tol["si_sdr_vs_ref_db"]
     perm = torch.from_numpy(np.random.default_rng(5).permutation(B) % D)
     model.reset()
     big = np.concatenate([model.process_chunk(c[perm].cuda()).cpu().numpy() for c in chunks], axis=-1)
     # replicas differ from the small launch only through the order of the GLN statistics atomics (fp64) and tile borders
     rep_tol = 2e-5 if precision == "fp32" else 2e-3
     assert np.abs(big - small[perm.numpy()]).max() < rep_tol * peak
-    assert np.abs(big - want[perm.numpy()]).max() < tol["wave_max_abs"] * peak
+    assert np.abs(big - want[perm.numpy()])[keep[perm.numpy()]].max() < tol["wave_max_abs"] * peak
