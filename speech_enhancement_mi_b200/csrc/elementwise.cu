@@ -127,8 +127,8 @@ __device__ __forceinline__ void load8(const float* __restrict__ q, float* v) {
 // loads are in flight per thread.  The outputs are rounded to fp16, which hides the re-association and the fast
 // reciprocal / exponential of the mask sigmoid (the exact-order fp32 path is norm_apply_kernel above).
 template <int MODE>
-__global__ void __launch_bounds__(256, MODE == 2 ? 2 : 4) norm_apply_h8_kernel(NormApplyParams p) {
-    constexpr int FB = MODE == 2 ? 4 : kNormFrames;  // frames per batch: all loads of a batch are issued before its first use
+__global__ void __launch_bounds__(256, MODE == 2 ? 3 : 4) norm_apply_h8_kernel(NormApplyParams p) {
+    constexpr int FB = MODE == 2 ? 2 : kNormFrames;  // frames per batch: all loads of a batch are issued before its first use
     const int t0 = blockIdx.x * kNormFrames;
     const int b = p.b0 + blockIdx.y;
     __shared__ float s_co[4];
