@@ -393,7 +393,7 @@ def main():
             traffic = json.load(f).get("dram_bytes_per_launch", {})
     except Exception:
         pass
-    stages, kernels, roofline = {}, [], None
+    stages, kernels, roofline, step_aggregate = {}, [], None, None
     if rank == 0:
         import re
         L = lib()
@@ -431,6 +431,14 @@ def main():
             st["ms"] += g["ms_total"]
         for st in stages.values():
             st["share"] = st["ms"] / tot
+        # whole-step context for the per-kernel rooflines: algorithmic flops / bytes of ALL kernels over the timed step
+        step_flops = sum(g["flops"] * g["launches"] for g in groups.values())
+        step_bytes = sum(g["bytes"] * g["launches"] for g in groups.values())
+        step_aggregate = {"algorithmic_tflop_per_s": step_flops / (ms_per_step * 1e-3) / 1e12,
+                          "frac_of_tensor_peak_sustained": step_flops / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
+                          "algorithmic_gb_per_s": step_bytes / (ms_per_step * 1e-3) / 1e9,
+                          "frac_of_hbm_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                          "sum_of_kernel_ms": tot}
         top = max(kernels, key=lambda k: k["share"])
         roofline = {"kernel": top["name"], "launches_per_step": top["launches"], "ms_per_launch": top["ms"],
                     "share_of_step": top["share"], "bound": top["bound"], "achieved": top["achieved"],
@@ -456,7 +464,7 @@ def main():
                              f"per-step working set of several GB, both > 126 MB L2"},
             "p99_chunk_latency_ms": lat[min(len(lat) - 1, int(0.99 * len(lat)))],
             "p50_chunk_latency_ms": lat[len(lat) // 2], "latency_steps": len(lat),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * K, "roofline": roofline, "stages": stages, "kernels": kernels,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * K, "roofline": roofline, "step_aggregate": step_aggregate, "stages": stages, "kernels": kernels,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)
