@@ -387,17 +387,22 @@ __global__ void __launch_bounds__(256, 3) mask_istft_kernel(MaskIstftParams p) {
             float2 zv[11];
 #pragma unroll
             for (int k1 = 0; k1 <= 10; ++k1) zv[k1] = s.z[fr][k1][n2];
+            // outputs n1 and 20 - n1 share the cosine sum and differ in the sign of the sine sum
 #pragma unroll
-            for (int n1 = 0; n1 < 20; ++n1) {
-                float acc = 0.f;
+            for (int n1 = 0; n1 <= 10; ++n1) {
+                float ac = 0.f, as = 0.f;
 #pragma unroll
                 for (int k1 = 1; k1 <= 9; ++k1) {  // Re(z * conj(w)), w = (kC20, kS20)[(n1 k1) % 20]
-                    acc = fmaf(zv[k1].x, kC20[(n1 * k1) % 20], acc);
-                    acc = fmaf(zv[k1].y, kS20[(n1 * k1) % 20], acc);
+                    ac = fmaf(zv[k1].x, kC20[(n1 * k1) % 20], ac);
+                    as = fmaf(zv[k1].y, kS20[(n1 * k1) % 20], as);
                 }
-                const float x = (zv[0].x + ((n1 & 1) ? -zv[10].x : zv[10].x) + 2.f * acc) * (1.0f / NFFT);
+                const float base = zv[0].x + ((n1 & 1) ? -zv[10].x : zv[10].x);
                 const int n = 20 * n1 + n2;
-                s.frames[fr][n] = x * s.win[n];
+                s.frames[fr][n] = (base + 2.f * (ac + as)) * (1.0f / NFFT) * s.win[n];
+                if (n1 >= 1 && n1 <= 9) {
+                    const int m = 20 * (20 - n1) + n2;
+                    s.frames[fr][m] = (base + 2.f * (ac - as)) * (1.0f / NFFT) * s.win[m];
+                }
             }
         }
         __syncthreads();
