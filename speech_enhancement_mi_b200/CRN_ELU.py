@@ -94,10 +94,16 @@ class _RealtimeTrainFn(torch.autograd.Function):
     def forward(ctx, model, mixture, flag, *params):
         ctx.model = model
         ctx.shapes = [p.shape for p in params]
-        return model._train_forward(mixture, flag)
+        pred = model._train_forward(mixture, flag)
+        ctx.fwd_gen = model._fwd_gen  # the training context keeps the activations of its LAST forward only
+        return pred
 
     @staticmethod
     def backward(ctx, dpred):
+        if ctx.fwd_gen != ctx.model._fwd_gen:
+            raise RuntimeError("backward() of a realtime_process result whose activations are gone: another forward ran "
+                               "on the model's training context in between (call backward before the next "
+                               "realtime_process, as train.py:195-198 does)")
         flat, offsets = ctx.model._train_backward(dpred)
         grads = [flat[o:o + s.numel()].view(s) for o, s in zip(offsets, ctx.shapes)]
         return (None, None, None, *grads)
@@ -199,6 +205,8 @@ class TemporalCRN(nn.Module):
         self._max_streams = int(max_streams) if max_streams else 0
         self._device_index = device
         self._ctx = None
+        self._tctx_gen = 0  # bumped whenever the native training context is (re-)created
+        self._fwd_gen = 0   # bumped by every forward on the training context
         self._ctx_device = None
         self._ctx_capacity = 0
         self._bound_versions = None
@@ -409,6 +417,7 @@ class TemporalCRN(nn.Module):
             cfg = self._config(need, training=True)
             check(lib().se_ctx_create(C.byref(ctx), device, C.byref(cfg)), "se_ctx_create(training)")
             self._tctx, self._tctx_device, self._tctx_capacity = ctx, device, need
+            self._tctx_gen += 1  # a new native object (the old handle, possibly the same address, is dead)
             n = lib().se_crn_num_params(ctx)
             self._t_offsets = [lib().se_crn_param_offset(ctx, i) for i in range(n)]
         tensors = self._train_params()
@@ -438,6 +447,7 @@ class TemporalCRN(nn.Module):
             pred = torch.empty((B, L), dtype=torch.float32, device=xd.device)
             check(lib().se_crn_train_forward(ctx, xd.data_ptr(), B, L, int(bool(flag)), pred.data_ptr(),
                                              self._stream_ptr(dev)), "se_crn_train_forward")
+        self._fwd_gen += 1
         return pred
 
     def _train_backward(self, dpred):

@@ -16,6 +16,7 @@
 
 #include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,37 @@ namespace se {
 
 static thread_local std::string g_err;
 void set_error(const std::string& msg) { g_err = msg; }
+
+// ---- per-device launch configuration (se_internal.h) ----------------------------------------------------------------
+namespace {
+std::mutex g_cfg_mutex;
+std::map<std::pair<int, const void*>, int> g_dyn_smem;  // (device, kernel) -> largest size opted in so far
+std::map<int, int> g_sm_count;
+}  // namespace
+int ensure_dyn_smem(const void* func, int bytes) {
+    int dev = 0;
+    SE_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    int& have = g_dyn_smem[{dev, func}];
+    if (have < bytes) {
+        SE_CUDA_OK(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        have = bytes;
+    }
+    return 0;
+}
+int num_sms_current_device(int* out) {
+    int dev = 0;
+    SE_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    auto it = g_sm_count.find(dev);
+    if (it == g_sm_count.end()) {
+        int n = 0;
+        SE_CUDA_OK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        it = g_sm_count.emplace(dev, n).first;
+    }
+    *out = it->second;
+    return 0;
+}
 
 namespace {
 
@@ -50,7 +82,8 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
     long long per_stream() const { return sB; }
 };
 
-enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ, OP_DECONV_LAST, OP_SKIP_SMALL, OP_GRU_TC, OP_PRECONV_TC };
+enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ, OP_DECONV_LAST, OP_SKIP_SMALL, OP_GRU_TC, OP_PRECONV_TC,
+              OP_PRECONV3, OP_ENC_MMA };
 enum Stage { ST_STFT = 0, ST_PRECONV, ST_ENCODER, ST_GRU, ST_DECODER, ST_MASK, ST_ROLL, ST_COUNT };
 const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"};
 
@@ -68,6 +101,9 @@ struct Op {
     SkipSmallParams sk;
     GruTcParams gt;
     PreconvTcParams pt;
+    Preconv3Params p3;
+    EncMmaParams em;
+    int em_cin = 0, em_cout = 0;
     int small_c = 0;  // channel count of the two small-layer kernels
     // GRU pointwise
     const float* gi = nullptr;
@@ -190,6 +226,13 @@ struct se_ctx {
     // against 0.231 ms for the fp32 CUDA-core kernel.  SE_B200_PRECONV_TC=0 keeps the CUDA-core kernel.
     bool preconv_tc = true;
     __half* pre_h[3] = {nullptr, nullptr, nullptr};  // tensor-core pre-convolution inputs [maxB][25][272][8] halves
+    // fp16 mode: the three pre-convolutions as ONE launch and the small-channel encoder blocks as one launch each, warp-level
+    // mma.sync with the stream resident in shared memory (front_mma.cu).  SE_B200_FRONT_MMA=0 / SE_B200_ENC_MMA=0 keep the
+    // round-1 kernels (preconv_tc.cu per layer; back-to-back tcgen05 GEMM + separate GlobalLayerNorm pass).
+    bool front_mma = true, enc_mma = true;
+    __half* feat_h = nullptr;     // features of the chunk [maxB][21][224][8] halves (borders stay zero)
+    __half* pre_state = nullptr;  // carried frames of the three pre-convolutions [maxB][3][4][224][8] halves
+    size_t pre3_w_off[3] = {0, 0, 0};
     bool b2b_gate = true;      // SE_B200_B2B=0: 32- / 64-channel gates as separate GEMMs
     bool small_layers = true;  // SE_B200_SMALL_LAYERS=0: keep the two small-channel layers on the GEMM path (A/B switch)
     unsigned tc_mask = 0xffffffffu;  // SE_B200_TC_MASK: bit per Stage that may use the tensor-core GEMM (debug)
@@ -444,8 +487,12 @@ struct Builder {
         const int rows = T * Fo;
         // gate fused into the conv GEMM: in registers for <= 16 channels, as a back-to-back tensor-core GEMM (fp16 operands)
         // for 32 / 64 channels (SE_B200_B2B=0 keeps those two levels on separate kernels)
-        const bool fuse_gate = tc_stage(stage) && !c->train &&
-                               (Cp_out <= 16 || (c->half && c->b2b_gate && (Cout_real == 32 || Cout_real == 64)));
+        // small-channel encoder levels (fp16 mode): conv + ELU + gate + GlobalLayerNorm as ONE launch (front_mma.cu)
+        const bool use_mma = c->enc_mma && stage == ST_ENCODER && !residual && KF == 5 && KT == 3 && strideF == 2 &&
+                             dilF == 1 && Cp_out == Cout_real && in.padF0 == 2 && in.padT0 == 2 * dilT &&
+                             enc_mma_supported(Cp_in, Cout_real, in.Tp, in.Fp, Fo);
+        const bool fuse_gate = use_mma || (tc_stage(stage) && !c->train &&
+                               (Cp_out <= 16 || (c->half && c->b2b_gate && (Cout_real == 32 || Cout_real == 64))));
         const int w2_pitch = gemm_tf32_tile_n(Cout_real);
         double* stats = c->stats + (size_t)stats_slot * 2 * c->maxB;
         float* const tmp_e = tmp_buf(c->tmp_e, (size_t)rows * Cp_out);
@@ -527,6 +574,37 @@ struct Builder {
                     meta(name + ".conv+elu+gate", conv_fl + 4.0 * rows * Cout_real * Cout_real, in_b + 4.0 * rows * Cout_real);
                 else
                     meta(name + ".conv+elu", conv_fl, in_b + 4.0 * rows * Cout_real);
+            }
+            if (use_mma) {
+                const size_t nw_off = pack_affine(name + ".norm.weight", Cout_real, Cp_out);
+                const size_t nb_off = pack_affine(name + ".norm.bias", Cout_real, Cp_out);
+                Op op{};
+                op.kind = OP_ENC_MMA;
+                op.stage = stage;
+                op.em = EncMmaParams{};
+                op.em.in = reinterpret_cast<const __half*>(in.base);
+                op.em.in_sB = in.sB;
+                op.em.Tp = in.Tp;
+                op.em.Fp = in.Fp;
+                op.em.dt = dilT;
+                op.em.Fo = Fo;
+                op.em.Kp = pw.K;
+                op.em.w2_pitch = w2_pitch;
+                op.em.out = reinterpret_cast<__half*>(dst);
+                op.em.oB = dB;
+                op.em.oT = dT;
+                op.em.oF = dF;
+                op.em.student = c->student;
+                op.em_cin = Cp_in;
+                op.em_cout = Cout_real;
+                op.label = name + ".conv+elu+gate+gln";
+                op.alg_flops = 2.0 * rows * Cout_real * (KT * KF * Cin_real) + 4.0 * rows * Cout_real * Cout_real;
+                op.alg_bytes = 4.0 * Cin_real * in.Tp * in.F + 4.0 * rows * Cout_real;
+                m_label.clear();
+                m_flops = m_bytes = 0;
+                c->ops.push_back(op);
+                fix.push_back({pw.w_off, pw.b_off, -1, nw_off, nb_off, NONE, NONE, w2_off, b2_off});
+                return;
             }
             push_gemm(stage, g, rows, pw, k_off, w2_off, b2_off);
             rec.op_conv = (int)c->ops.size() - 1;
@@ -826,6 +904,10 @@ int build_ctx(se_ctx* c) {
     if (const char* e = getenv("SE_B200_B2B")) c->b2b_gate = atoi(e) != 0;
     if (const char* e = getenv("SE_B200_PRECONV_TC")) c->preconv_tc = atoi(e) != 0;
     c->preconv_tc = c->preconv_tc && c->half && !c->train;
+    if (const char* e = getenv("SE_B200_FRONT_MMA")) c->front_mma = atoi(e) != 0;
+    if (const char* e = getenv("SE_B200_ENC_MMA")) c->enc_mma = atoi(e) != 0;
+    c->front_mma = c->front_mma && c->preconv_tc;  // replaces the per-layer tensor-core kernels
+    c->enc_mma = c->enc_mma && c->half && !c->train;
     for (int i = 0; i < c->L; ++i) {
         SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
         SE_REQUIRE(!c->half || g.num_channels[i] % 8 == 0, "fp16 mode: num_channels must be multiples of 8");
@@ -847,9 +929,14 @@ int build_ctx(se_ctx* c) {
     const int H = c->H;
     // ---- activations ------------------------------------------------------------------------------------------
     const long long pre_h_sB = (long long)PRECONV_TP * PRECONV_TC_POS * 8;  // halves per stream
-    if (c->preconv_tc)
+    const long long feat_sB = (long long)T * PRECONV3_POS * 8, pre_state_sB = 3LL * 4 * PRECONV3_POS * 8;  // halves
+    if (c->front_mma) {
+        if (dev_alloc(c, &c->feat_h, (size_t)feat_sB * maxB)) return 1;
+        if (dev_alloc(c, &c->pre_state, (size_t)pre_state_sB * maxB)) return 1;
+    } else if (c->preconv_tc) {
         for (int i = 0; i < 3; ++i)
             if (dev_alloc(c, &c->pre_h[i], (size_t)pre_h_sB * maxB)) return 1;
+    }
     c->pre_in.resize((c->train || c->preconv_tc) ? 0 : 3);
     for (int i = 0; i < (int)c->pre_in.size(); ++i) {
         PreBuf& pb = c->pre_in[i];
@@ -949,7 +1036,55 @@ int build_ctx(se_ctx* c) {
                      nx.interior(), nx.sB, nx.sT, nx.sF, true, slot++, i, nx.dinterior());
         c->conv_recs.back().need_dgrad = i > 0;
     }
-    for (int i = 0; i < 3 && c->preconv_tc; ++i) {  // fp16 mode: pre-convolutions on the tensor cores (preconv_tc.cu)
+    auto pack_preconv_block = [&](const std::string& name) -> size_t {  // PRECONV_W_* layout (se_internal.h)
+        const size_t w_off = c->reserve_w(PRECONV_W_FLOATS);
+        c->packers.push_back([=](const HostParams& hp, float* arena) {
+            const std::vector<float>& w = hp.at(name + ".conv.weight");  // [Co][Ci][KF][KT]
+            float* a = arena + w_off;
+            for (int kt = 0; kt < 5; ++kt)
+                for (int ci = 0; ci < 5; ++ci)
+                    for (int kf = 0; kf < 5; ++kf)
+                        for (int co = 0; co < 5; ++co)
+                            a[(kt * 5 + ci) * 28 + kf * 5 + co] = w[((co * 5 + ci) * 5 + kf) * 5 + kt];
+            for (int co = 0; co < 5; ++co) {
+                a[PRECONV_W_BIAS + co] = hp.at(name + ".conv.bias")[co];
+                for (int k = 0; k < 5; ++k) {
+                    a[PRECONV_W_WT + co * 5 + k] = hp.at(name + ".conv_trans.weight")[co * 5 + k];
+                    a[PRECONV_W_WG + co * 5 + k] = hp.at(name + ".conv_gated.weight")[co * 5 + k];
+                }
+                a[PRECONV_W_BT + co] = hp.at(name + ".conv_trans.bias")[co];
+                a[PRECONV_W_BG + co] = hp.at(name + ".conv_gated.bias")[co];
+                a[PRECONV_W_NW + co] = hp.at(name + ".norm.weight")[co];
+                a[PRECONV_W_NB + co] = hp.at(name + ".norm.bias")[co];
+            }
+        });
+        return w_off;
+    };
+    if (c->front_mma) {  // fp16 mode: the three pre-convolution blocks in one launch (front_mma.cu)
+        for (int i = 0; i < 3; ++i) c->pre3_w_off[i] = pack_preconv_block("preconvlist." + std::to_string(i));
+        const Act& nx = c->enc_in[0];
+        Op op{};
+        op.kind = OP_PRECONV3;
+        op.stage = ST_PRECONV;
+        op.p3 = Preconv3Params{};
+        op.p3.feat = c->feat_h;
+        op.p3.feat_sB = feat_sB;
+        op.p3.state = c->pre_state;
+        op.p3.state_sB = pre_state_sB;
+        op.p3.out = reinterpret_cast<__half*>(nx.interior());
+        op.p3.oB = nx.sB;
+        op.p3.oT = nx.sT;
+        op.p3.oF = nx.sF;
+        op.p3.student = c->student;
+        op.label = "preconvlist.0-2.fused";
+        op.alg_flops = 3 * 2.0 * T * NBIN * 5 * (125 + 10);
+        // features in, block output out, 4 carried frames per layer read and written (fp32 sizes, as for every other op)
+        op.alg_bytes = 4.0 * 5 * NBIN * (T + T + 3 * 2 * 4);
+        c->ops.push_back(op);
+        b.fix.push_back({NONE, NONE, -1, NONE, NONE, NONE, NONE});
+        slot += 3;
+    }
+    for (int i = 0; i < 3 && c->preconv_tc && !c->front_mma; ++i) {  // fp16 mode: pre-convolutions on the tensor cores (preconv_tc.cu)
         const std::string name = "preconvlist." + std::to_string(i);
         const size_t w_off = c->reserve_w(PRECONV_W_FLOATS);
         c->packers.push_back([=](const HostParams& hp, float* arena) {
@@ -1355,6 +1490,15 @@ int build_ctx(se_ctx* c) {
                 op.g.W2 = c->warena + f.w2_off;
                 op.g.bias2 = c->warena + f.b2_off;
             }
+        } else if (op.kind == OP_PRECONV3) {
+            for (int l = 0; l < 3; ++l) op.p3.w[l] = c->warena + c->pre3_w_off[l];
+        } else if (op.kind == OP_ENC_MMA) {
+            op.em.w = c->warena + f.w_off;
+            op.em.bias = c->warena + f.b_off;
+            op.em.w2 = c->warena + f.w2_off;
+            op.em.bias2 = c->warena + f.b2_off;
+            op.em.nw = c->warena + f.nw_off;
+            op.em.nb = c->warena + f.nb_off;
         } else if (op.kind == OP_PRECONV_TC) {
             op.pt.w = c->warena + f.nw_off;
         } else if (op.kind == OP_PRECONV) {
@@ -1381,7 +1525,12 @@ int build_ctx(se_ctx* c) {
     };
     if (c->train)
         for (const Act& a : c->pre_act) add_state(a.base, a.sB, (long long)T * a.sT, (int)(a.padT0 * a.sT));
-    for (int i = 0; i < 3 && c->preconv_tc; ++i) {  // rolled by the kernel itself; a reset clears the whole slab
+    if (c->front_mma) {  // rolled by the kernel itself; the borders of the feature buffer are never written
+        RollEntry e{reinterpret_cast<float*>(c->pre_state), pre_state_sB / 2, 0, 0, (int)(pre_state_sB / 2)};
+        c->zero_tab.e[c->zero_tab.n++] = e;
+        c->state_floats += 3 * 5 * 4 * NBIN;
+    }
+    for (int i = 0; i < 3 && c->preconv_tc && !c->front_mma; ++i) {  // rolled by the kernel itself; a reset clears the whole slab
         RollEntry e{reinterpret_cast<float*>(c->pre_h[i]), pre_h_sB / 2, 0, 0, (int)(pre_h_sB / 2)};
         c->zero_tab.e[c->zero_tab.n++] = e;
         c->state_floats += 5 * 4 * NBIN;
@@ -1475,6 +1624,18 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
             pt.B = B;
             return launch_preconv_tc(pt, st);
         }
+        case OP_PRECONV3: {
+            Preconv3Params p3 = op.p3;
+            p3.b0 = 0;
+            p3.B = B;
+            return launch_preconv3(p3, st);
+        }
+        case OP_ENC_MMA: {
+            EncMmaParams em = op.em;
+            em.b0 = 0;
+            em.B = B;
+            return launch_enc_mma(em, op.em_cin, op.em_cout, st);
+        }
         case OP_GRU_TC: {
             GruTcParams gt = op.gt;
             gt.B = B;
@@ -1518,7 +1679,12 @@ int enqueue_stream_step(se_ctx* c, int B, cudaStream_t st, int stage_filter = -1
         sp.B = B;
         sp.M = 3;
         sp.student = c->student;
-        if (c->preconv_tc) {
+        if (c->front_mma) {
+            sp.feat_h8 = c->feat_h + PRECONV3_BORDER * 8;  // frame 0, bin 0
+            sp.fB = (long long)T * PRECONV3_POS * 8;
+            sp.fT = (long long)PRECONV3_POS * 8;
+            sp.fF = 8;
+        } else if (c->preconv_tc) {
             sp.feat_h8 = c->pre_h[0] + (4LL * PRECONV_TC_POS + 2) * 8;  // frame 4, bin 0 (dilation 1: position 2)
             sp.fB = (long long)PRECONV_TP * PRECONV_TC_POS * 8;
             sp.fT = (long long)PRECONV_TC_POS * 8;
@@ -2180,7 +2346,11 @@ int se_crn_forward_chunk(se_ctx* c, const float* spec_in, float* spec_out, int B
     if (B == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     SE_CUDA_OK(cudaMemsetAsync(c->stats, 0, (size_t)c->n_stats * 2 * c->maxB * sizeof(double), st));
-    if (c->preconv_tc) {
+    if (c->front_mma) {
+        if (launch_features_from_spec(spec_in, B, 3, c->student, nullptr, (long long)T * PRECONV3_POS * 8, 0,
+                                      (long long)PRECONV3_POS * 8, 8, c->noisy, st, c->feat_h + PRECONV3_BORDER * 8))
+            return 1;
+    } else if (c->preconv_tc) {
         if (launch_features_from_spec(spec_in, B, 3, c->student, nullptr, (long long)PRECONV_TP * PRECONV_TC_POS * 8, 0,
                                       (long long)PRECONV_TC_POS * 8, 8, c->noisy, st,
                                       c->pre_h[0] + (4LL * PRECONV_TC_POS + 2) * 8))
@@ -2253,7 +2423,22 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
         return (i >= 0 && i < limit) ? i : -1;
     };
     int i;
-    if ((i = idx_of("pre_in", 3)) >= 0 && c->preconv_tc) {  // channels-last fp16 units -> [T][F][5] on the host
+    if ((i = idx_of("pre_in", 3)) >= 0 && c->front_mma) {  // only the features reach HBM: layers 1, 2 live in shared memory
+        SE_REQUIRE(i == 0, "se_debug_read: pre_in1 / pre_in2 are not materialised by the fused pre-convolution kernel");
+        dims[0] = T;
+        dims[1] = NBIN;
+        dims[2] = 5;
+        SE_REQUIRE((int64_t)T * NBIN * 5 <= max_floats, "se_debug_read: destination too small");
+        const size_t n = (size_t)T * PRECONV3_POS * 8;
+        std::vector<__half> slab(n);
+        SE_CUDA_OK(cudaMemcpy(slab.data(), c->feat_h + (size_t)b * n, n * sizeof(__half), cudaMemcpyDeviceToHost));
+        for (int tt = 0; tt < T; ++tt)
+            for (int ff = 0; ff < NBIN; ++ff)
+                for (int cc = 0; cc < 5; ++cc)
+                    host_dst[((size_t)tt * NBIN + ff) * 5 + cc] =
+                        __half2float(slab[((size_t)tt * PRECONV3_POS + ff + PRECONV3_BORDER) * 8 + cc]);
+        return 0;
+    } else if ((i = idx_of("pre_in", 3)) >= 0 && c->preconv_tc) {  // channels-last fp16 units -> [T][F][5] on the host
         dims[0] = T;
         dims[1] = NBIN;
         dims[2] = 5;

@@ -1,0 +1,575 @@
+// Front end of the CRN chunk step for the small-channel layers (fp16 operand mode), one stream per CTA at a time with
+// the stream's activations resident in shared memory:
+//
+//   preconv3_mma_kernel   the three pre-convolution blocks of CRN_ELU.py:337-339,375-376 (5x5 frequency-dilated causal
+//                         conv 5 -> 5 + ELU + gated 1x1 pair + GlobalLayerNorm + residual) in ONE launch.  The feature
+//                         tensor is read from HBM once, the three layers update it in place in shared memory, only the
+//                         4 carried frames per layer (CRN_ELU.py:243-246) and the final output touch HBM.
+//   enc_mma_kernel        one gated causal conv block of the encoder (CRN_ELU.py:230-247, k(5,3), stride (2,1), time
+//                         dilation 2^i) for the levels with <= 16 input and <= 32 output channels: conv + ELU + gated 1x1
+//                         pair + GlobalLayerNorm in one launch (was: back-to-back tcgen05 GEMM + separate norm pass).
+//
+// Why not tcgen05 here: with 8 / 16 / 32 output channels a 128-row UMMA tile is A-bandwidth bound (the tensor core
+// re-reads 4 KB of A for 16 columns of output) and every frequency / time tap needs its own shifted descriptor; the
+// per-tile cost of the issue / commit / TMEM round trip dominated (0.14 - 0.19 ms per layer, 9-16 % of the HBM floor).
+// Warp-level mma.sync.m16n8k16 reads each A fragment with one ldmatrix.x4 straight from the resident input (any tap is
+// just an address offset), keeps the accumulators in registers where the ELU / gate / statistics epilogue runs, feeds
+// the gate GEMM from the accumulator registers (the C fragment of two n-tiles IS the A fragment of a k-step), and needs
+// no barriers inside a layer.  GlobalLayerNorm statistics are reduced inside the CTA (no atomics, no second launch).
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "se_internal.h"
+
+namespace se {
+namespace {
+
+constexpr int T = kFramesPerChunk;  // 21
+constexpr int NB = 201;
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float x, float y) {
+    const __half2 h = __floats2half2_rn(x, y);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_elu(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float* o) {
+    uint4 u;
+    u.x = pack_h2(o[0], o[1]);
+    u.y = pack_h2(o[2], o[3]);
+    u.z = pack_h2(o[4], o[5]);
+    u.w = pack_h2(o[6], o[7]);
+    return u;
+}
+
+// GlobalLayerNorm coefficients of one stream from the per-thread partial sums (CRN_ELU.py:40-51 /
+// distillation_crn.py:51): every thread calls this; returns after a __syncthreads with s_co = {mean, 1/den}
+__device__ __forceinline__ void block_gln(float psum, float psq, double count, int student, double* s_red, float* s_co) {
+    double ds = psum, dq = psq;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, off);
+        dq += __shfl_xor_sync(0xffffffffu, dq, off);
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) {
+        s_red[warp] = ds;
+        s_red[kWarps + warp] = dq;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, q = 0.0;
+        for (int w = 0; w < kWarps; ++w) {
+            a += s_red[w];
+            q += s_red[kWarps + w];
+        }
+        const double mu = a / count;
+        double var = q / count - mu * mu;
+        if (var < 0.0) var = 0.0;
+        const float varf = (float)var;
+        const float den = student ? (sqrtf(varf) + 1e-8f) : (sqrtf(varf + 1e-8f) + 1e-8f);
+        s_co[0] = (float)mu;
+        s_co[1] = 1.0f / den;
+    }
+    __syncthreads();
+}
+
+// =====================================================================================================================
+// three pre-convolution blocks, fused
+// =====================================================================================================================
+// X[25 frames: 4 carried + 21 new][224 positions][8 halves]: bin f at position 8 + f, zero elsewhere (the conv's
+// frequency padding 2 d <= 8 and the overrun of the last 16-row tile).  Output row (t, f), tap (kt, kf) reads unit
+// (t + kt) * 224 + 8 + f + (kf - 2) d: sixteen consecutive rows are sixteen consecutive 16-byte units = one conflict-free
+// ldmatrix phase per 8 rows.  K = 25 taps x 8 channel slots = 13 k-steps of two taps; N = 8 (5 real output channels).
+constexpr int P3_POS = 224;
+constexpr int P3_BORDER = 8;
+constexpr int P3_ROW_BYTES = P3_POS * 16;
+constexpr int P3_X_BYTES = (T + 4) * P3_ROW_BYTES;       // 89,600
+constexpr int P3_YPITCH = 208;                           // 13 tiles of 16 bins per frame
+constexpr int P3_Y_BYTES = T * P3_YPITCH * 16;           // 69,888: gated values (pre-norm) as fp16 units
+constexpr int P3_KS = 13;
+constexpr int P3_WF_LAYER = (P3_KS + 2) * 32;            // uint2 per layer: 13 conv k-steps + 2 gate n-tiles
+constexpr int P3_WF_BYTES = 3 * P3_WF_LAYER * 8;         // 11,520
+constexpr int P3_NPAR = 32;                              // floats per layer: cb[8] bt[8] bg[8] | nw[5] nb[5] (pad)
+constexpr int P3_PAR_BYTES = 3 * P3_NPAR * 4;
+constexpr int P3_OFF_Y = P3_X_BYTES;
+constexpr int P3_OFF_WF = P3_OFF_Y + P3_Y_BYTES;
+constexpr int P3_OFF_PAR = P3_OFF_WF + P3_WF_BYTES;
+constexpr int P3_OFF_RED = P3_OFF_PAR + P3_PAR_BYTES;    // double [2][16]
+constexpr int P3_OFF_CO = P3_OFF_RED + 2 * kWarps * 8;   // float [2]
+constexpr int P3_SMEM = P3_OFF_CO + 16;
+constexpr int P3_MT = T * 13;                            // 273 tiles of 16 rows
+static_assert(P3_SMEM <= 227 * 1024, "shared memory budget");
+
+__global__ void __launch_bounds__(kThreads, 1) preconv3_mma_kernel(Preconv3Params p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sx = smem;
+    unsigned char* sy = smem + P3_OFF_Y;
+    uint2* swf = reinterpret_cast<uint2*>(smem + P3_OFF_WF);
+    float* spar = reinterpret_cast<float*>(smem + P3_OFF_PAR);
+    double* s_red = reinterpret_cast<double*>(smem + P3_OFF_RED);
+    float* s_co = reinterpret_cast<float*>(smem + P3_OFF_CO);
+    const uint32_t x_smem = smem_u32(sx);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+
+    // ---- one-time set-up: B fragments (fp16) and the small fp32 parameters of the three layers ---------------------
+    // packed parameter block of a layer (se_internal.h PRECONV_W_*): conv [(kt*5+ci)*28 + kf*5 + co], ...
+    for (int i = tid; i < 3 * P3_WF_LAYER; i += kThreads) {
+        const int l = i / P3_WF_LAYER, r = i - l * P3_WF_LAYER, s = r >> 5, ln = r & 31;
+        const int gg = ln >> 2, t4 = ln & 3;
+        const float* w = p.w[l];
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (s < P3_KS) {  // conv k-step s: taps 2s (k 0..7) and 2s+1 (k 8..15), B column = output channel gg
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int tap = 2 * s + h;
+                const int kt = tap / 5, kf = tap - 5 * kt;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int ci = 2 * t4 + e;
+                    if (tap < 25 && ci < 5 && gg < 5) v[2 * h + e] = __ldg(w + (kt * 5 + ci) * 28 + kf * 5 + gg);
+                }
+            }
+        } else {  // gate n-tile (0: conv_trans, 1: conv_gated): k = ELU channel 2 t4 + e, column = output channel gg
+            const int base = s == P3_KS ? PRECONV_W_WT : PRECONV_W_WG;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int k = 2 * t4 + e;
+                if (k < 5 && gg < 5) v[e] = __ldg(w + base + gg * 5 + k);
+            }
+        }
+        swf[i] = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
+    }
+    for (int i = tid; i < 3 * P3_NPAR; i += kThreads) {
+        const int l = i / P3_NPAR, r = i - l * P3_NPAR;
+        const float* w = p.w[l];
+        float v = 0.f;
+        if (r < 8) v = r < 5 ? __ldg(w + PRECONV_W_BIAS + r) : 0.f;
+        else if (r < 16) v = r - 8 < 5 ? __ldg(w + PRECONV_W_BT + r - 8) : 0.f;
+        else if (r < 24) v = r - 16 < 5 ? __ldg(w + PRECONV_W_BG + r - 16) : 0.f;
+        spar[i] = v;
+    }
+    __syncthreads();
+
+    // per-lane ldmatrix role: matrices 0/1 = rows 0-7 / 8-15 of the k-step's first tap, 2/3 = of its second tap
+    const int mi = lane >> 3;
+    const int rowoff = (lane & 7) + 8 * (mi & 1);
+    const int tapsel = mi >> 1;
+
+    for (int stream = blockIdx.x; stream < p.B; stream += gridDim.x) {
+        const int b = p.b0 + stream;
+        __half* gstate = p.state + (long long)b * p.state_sB;
+        {  // frames 0..3 <- carried state of layer 0, frames 4..24 <- this chunk's features
+            const uint4* s0 = reinterpret_cast<const uint4*>(gstate);
+            const uint4* s1 = reinterpret_cast<const uint4*>(p.feat + (long long)b * p.feat_sB);
+            for (int i = tid; i < 4 * P3_POS; i += kThreads) cp_async16(x_smem + 16u * i, s0 + i);
+            for (int i = tid; i < T * P3_POS; i += kThreads) cp_async16(x_smem + 4 * P3_ROW_BYTES + 16u * i, s1 + i);
+            cp_async_commit();
+            cp_async_wait_all();
+            __syncthreads();
+        }
+#pragma unroll 1
+        for (int l = 0; l < 3; ++l) {
+            const int d = 1 << l;
+            // causal state of this layer for the next chunk: the last 4 frames of its input (CRN_ELU.py:246)
+            {
+                uint4* dst = reinterpret_cast<uint4*>(gstate + (long long)l * 4 * P3_POS * 8);
+                const uint4* src = reinterpret_cast<const uint4*>(sx + T * P3_ROW_BYTES);
+                for (int i = tid; i < 4 * P3_POS; i += kThreads) dst[i] = src[i];
+            }
+            const uint2* wf = swf + l * P3_WF_LAYER;
+            const float* par = spar + l * P3_NPAR;
+            const float cb0 = par[2 * tg], cb1 = par[2 * tg + 1];
+            const float bt0 = par[8 + 2 * tg], bt1 = par[8 + 2 * tg + 1];
+            const float bg0 = par[16 + 2 * tg], bg1 = par[16 + 2 * tg + 1];
+            const uint2 wgt = wf[P3_KS * 32 + lane], wgg = wf[(P3_KS + 1) * 32 + lane];
+            float psum = 0.f, psq = 0.f;
+            // ---- pass 1: conv + ELU + gate -> Y, statistics.  Two 16-row tiles per iteration (independent mma chains) ----
+            for (int mt0 = 2 * warp; mt0 < P3_MT; mt0 += 2 * kWarps) {
+                float acc[2][4];
+                uint32_t abase[2];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int mt = min(mt0 + q, P3_MT - 1);  // odd tail: the second tile repeats the last one (not stored)
+                    const int t = mt / 13, ft = mt - 13 * t;
+                    abase[q] = x_smem + (uint32_t)((t * P3_POS + P3_BORDER + 16 * ft + rowoff) * 16);
+                    acc[q][0] = acc[q][2] = cb0;
+                    acc[q][1] = acc[q][3] = cb1;
+                }
+#pragma unroll
+                for (int s = 0; s < P3_KS; ++s) {
+                    const int tapA = 2 * s, tapB = 2 * s + 1 < 25 ? 2 * s + 1 : 24;  // tap 25: zero weights, valid address
+                    const int offA = (tapA / 5) * P3_POS + (tapA % 5 - 2) * d;
+                    const int offB = (tapB / 5) * P3_POS + (tapB % 5 - 2) * d;
+                    const int off = (tapsel ? offB : offA) * 16;
+                    const uint2 w = wf[s * 32 + lane];
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        uint32_t a[4];
+                        ldsm_x4(abase[q] + off, a);
+                        mma16816(acc[q], a, w.x, w.y);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int mt = mt0 + q;
+                    if (mt >= P3_MT) break;
+                    const int t = mt / 13, ft = mt - 13 * t;
+                    // ELU, then the gated 1x1 pair on the tensor core: the C fragment is the A fragment (k = channel)
+                    uint32_t a2[4];
+                    a2[0] = pack_h2(fast_elu(acc[q][0]), fast_elu(acc[q][1]));
+                    a2[1] = pack_h2(fast_elu(acc[q][2]), fast_elu(acc[q][3]));
+                    a2[2] = a2[3] = 0u;
+                    float gt[4] = {bt0, bt1, bt0, bt1}, gg4[4] = {bg0, bg1, bg0, bg1};
+                    mma16816(gt, a2, wgt.x, wgt.y);
+                    mma16816(gg4, a2, wgg.x, wgg.y);
+                    float y[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) y[i] = gt[i] * fast_sigmoid(gg4[i]);
+                    const int f0 = 16 * ft + g, f1 = f0 + 8;
+                    // columns >= 5 are exactly 0 (zero weights and biases): no channel mask needed in the statistics
+                    if (f0 < NB) {
+                        psum += y[0] + y[1];
+                        psq = fmaf(y[0], y[0], fmaf(y[1], y[1], psq));
+                    }
+                    if (f1 < NB) {
+                        psum += y[2] + y[3];
+                        psq = fmaf(y[2], y[2], fmaf(y[3], y[3], psq));
+                    }
+                    if (tg < 3) {
+                        unsigned char* yr = sy + (size_t)(t * P3_YPITCH) * 16 + 4 * tg;
+                        *reinterpret_cast<uint32_t*>(yr + f0 * 16) = pack_h2(y[0], y[1]);
+                        *reinterpret_cast<uint32_t*>(yr + f1 * 16) = pack_h2(y[2], y[3]);
+                    }
+                }
+            }
+            __syncthreads();  // frames 0..3 of X are dead from here on
+            if (l < 2) {      // carried state of the next layer -> frames 0..3 (overlaps the statistics and pass 2)
+                const uint4* s0 = reinterpret_cast<const uint4*>(gstate + (long long)(l + 1) * 4 * P3_POS * 8);
+                for (int i = tid; i < 4 * P3_POS; i += kThreads) cp_async16(x_smem + 16u * i, s0 + i);
+                cp_async_commit();
+            }
+            block_gln(psum, psq, 5.0 * NB * T, p.student, s_red, s_co);
+            // ---- pass 2: normalise + residual (CRN_ELU.py:376), in place (next layer's input) or to the output ----------
+            {
+                const float mean = s_co[0], inv = s_co[1];
+                const float* w = p.w[l];
+                float na[5], nd[5];
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                    na[c] = __ldg(w + PRECONV_W_NW + c);
+                    nd[c] = __ldg(w + PRECONV_W_NB + c);
+                }
+                for (int i = tid; i < T * NB; i += kThreads) {
+                    const int t = i / NB, f = i - t * NB;
+                    uint4* xu = reinterpret_cast<uint4*>(sx + ((t + 4) * P3_POS + P3_BORDER + f) * 16);
+                    float yv[8], xv[8];
+                    unpack8(*reinterpret_cast<const uint4*>(sy + (t * P3_YPITCH + f) * 16), yv);
+                    unpack8(*xu, xv);
+                    float o[5];
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) o[c] = (yv[c] - mean) * inv * na[c] + nd[c] + xv[c];
+                    uint4 u;
+                    u.x = pack_h2(o[0], o[1]);
+                    u.y = pack_h2(o[2], o[3]);
+                    u.z = pack_h2(o[4], 0.f);
+                    u.w = 0u;
+                    if (l < 2) *xu = u;
+                    else
+                        *reinterpret_cast<uint4*>(p.out + (long long)b * p.oB + (long long)t * p.oT + (long long)f * p.oF) = u;
+                }
+            }
+            cp_async_wait_all();
+            __syncthreads();
+        }
+    }
+}
+
+// =====================================================================================================================
+// encoder block with few channels: conv k(5,3) stride (2,1) dilation (1,dt) + ELU + gated 1x1 pair + GlobalLayerNorm
+// =====================================================================================================================
+// The stream's zero-bordered input [Tp][Fp][CIN] is de-interleaved on the way into shared memory into planes
+// X[parity of the padded bin][channel octet][Tp][Jp] of 16-byte units (Jp = ceil(Fp / 2)), so that the stride-2 rows of
+// a tap are consecutive units: output row m = t Jp + f' (f' < Fo valid, the 2 extra rows per frame are computed and
+// dropped) and tap (kt, kf) read unit m + kt dt Jp + (kf >> 1) of plane (kf & 1, octet).
+template <int CIN, int COUT>
+struct EncCfg {
+    static constexpr int NH = CIN / 8;
+    static constexpr int KS = (15 * CIN + 15) / 16;  // conv k-steps (CIN = 8: two taps per step, the 16th tap is zero)
+    static constexpr int NT = COUT / 8;
+    static constexpr int KS2 = (COUT + 15) / 16;
+    static constexpr int NT2 = 2 * NT;
+    static constexpr int SLACK = 64;  // units behind every plane (tile overrun of the last frame)
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads, 1) enc_mma_kernel(EncMmaParams p) {
+    using S = EncCfg<CIN, COUT>;
+    constexpr int NH = S::NH, KS = S::KS, NT = S::NT, KS2 = S::KS2, NT2 = S::NT2;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int Jp = (p.Fp + 1) >> 1;
+    const int plane = p.Tp * Jp + S::SLACK;  // units per plane
+    unsigned char* sx = smem;
+    unsigned char* sy = smem + p.off_y;
+    uint2* swf = reinterpret_cast<uint2*>(smem + p.off_wf);
+    uint2* swf2 = swf + KS * NT * 32;
+    float* spar = reinterpret_cast<float*>(swf2 + KS2 * NT2 * 32);  // cb[COUT] | b2t[COUT] | b2g[COUT]
+    double* s_red = reinterpret_cast<double*>(spar + 3 * COUT);
+    float* s_co = reinterpret_cast<float*>(s_red + 2 * kWarps);
+    const uint32_t x_smem = smem_u32(sx);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+
+    // ---- one-time set-up -----------------------------------------------------------------------------------------
+    for (int i = tid; i < 2 * NH * plane; i += kThreads) reinterpret_cast<uint4*>(sx)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < KS * NT * 32; i += kThreads) {  // conv B fragments: column n = output channel, k = (tap, ci)
+        const int ln = i & 31, nt = (i >> 5) % NT, ks = (i >> 5) / NT;
+        const int n = nt * 8 + (ln >> 2), k0 = ks * 16 + 2 * (ln & 3);
+        const float* wr = p.w + (long long)n * p.Kp;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + (e & 1) + 8 * (e >> 1);
+            v[e] = k < 15 * CIN ? __ldg(wr + k) : 0.f;
+        }
+        swf[i] = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
+    }
+    for (int i = tid; i < KS2 * NT2 * 32; i += kThreads) {  // gate B fragments: n-tiles [0,NT) trans, [NT,2NT) gated
+        const int ln = i & 31, nt2 = (i >> 5) % NT2, ks2 = (i >> 5) / NT2;
+        const int kind = nt2 / NT, ch = (nt2 % NT) * 8 + (ln >> 2), k0 = ks2 * 16 + 2 * (ln & 3);
+        const float* wr = p.w2 + (long long)(2 * ch + kind) * p.w2_pitch;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k = k0 + (e & 1) + 8 * (e >> 1);
+            v[e] = k < COUT ? __ldg(wr + k) : 0.f;
+        }
+        swf2[i] = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
+    }
+    for (int i = tid; i < COUT; i += kThreads) {
+        spar[i] = __ldg(p.bias + i);
+        spar[COUT + i] = __ldg(p.bias2 + 2 * i);
+        spar[2 * COUT + i] = __ldg(p.bias2 + 2 * i + 1);
+    }
+
+    auto issue_load = [&](int b) {  // global [Tp][Fp][NH] units -> planes
+        const uint4* src = reinterpret_cast<const uint4*>(p.in + (long long)b * p.in_sB);
+        const int total = p.Tp * p.Fp * NH;
+        for (int u = tid; u < total; u += kThreads) {
+            const int h = NH == 1 ? 0 : (u & (NH - 1));
+            const int pl = NH == 1 ? u : u / NH;
+            const int tt = pl / p.Fp, pos = pl - tt * p.Fp;
+            const int unit = ((pos & 1) * NH + h) * plane + tt * Jp + (pos >> 1);
+            cp_async16(x_smem + 16u * unit, src + u);
+        }
+        cp_async_commit();
+    };
+
+    // per-lane ldmatrix role.  CIN = 8: matrices 0/1 = rows 0-7 / 8-15 of the step's first tap, 2/3 = of its second tap;
+    // CIN = 16: matrices 0/1 = channel octet 0, 2/3 = octet 1 of the step's single tap
+    const int mi = lane >> 3;
+    const int rowoff = (lane & 7) + 8 * (mi & 1);
+    const int sel = mi >> 1;
+    const int dtJ = p.dt * Jp;
+    const int Mtot = T * Jp;
+    const int MT = (Mtot + 15) >> 4;
+    const int Fo = p.Fo;
+    const double count = (double)COUT * Fo * T;
+    constexpr int UPR = COUT / 8;  // 16-byte units per output row
+
+    __syncthreads();
+    if (blockIdx.x < p.B) issue_load(p.b0 + blockIdx.x);
+    for (int stream = blockIdx.x; stream < p.B; stream += gridDim.x) {
+        const int b = p.b0 + stream;
+        cp_async_wait_all();
+        __syncthreads();
+        float psum = 0.f, psq = 0.f;
+        // ---- pass 1: conv + ELU + gate -> Y (fp16, [T][Fo][COUT]) + statistics; two 16-row tiles per iteration --------
+        for (int mt0 = 2 * warp; mt0 < MT; mt0 += 2 * kWarps) {
+            float acc[2][NT][4];
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    acc[q][nt][0] = acc[q][nt][2] = spar[8 * nt + 2 * tg];
+                    acc[q][nt][1] = acc[q][nt][3] = spar[8 * nt + 2 * tg + 1];
+                }
+            const uint32_t abase = x_smem + (uint32_t)((mt0 * 16 + rowoff) * 16);
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+                int unit;
+                if (CIN == 8) {
+                    const int tapA = 2 * ks, tapB = 2 * ks + 1 < 15 ? 2 * ks + 1 : 14;  // tap 15: zero weights
+                    const int uA = (tapA / 5) * dtJ + ((tapA % 5) >> 1) + ((tapA % 5) & 1) * plane;
+                    const int uB = (tapB / 5) * dtJ + ((tapB % 5) >> 1) + ((tapB % 5) & 1) * plane;
+                    unit = sel ? uB : uA;
+                } else {
+                    const int kt = ks / 5, kf = ks % 5;
+                    unit = kt * dtJ + (kf >> 1) + ((kf & 1) * NH + sel) * plane;
+                }
+                uint32_t a[2][4];
+                ldsm_x4(abase + (uint32_t)(unit * 16), a[0]);
+                ldsm_x4(abase + (uint32_t)((unit + 16) * 16), a[1]);
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) {
+                    const uint2 w = swf[(ks * NT + nt) * 32 + lane];
+                    mma16816(acc[0][nt], a[0], w.x, w.y);
+                    mma16816(acc[1][nt], a[1], w.x, w.y);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (mt0 + q >= MT) break;
+                uint32_t a2[KS2][4];
+#pragma unroll
+                for (int s = 0; s < KS2; ++s) {
+                    a2[s][0] = pack_h2(fast_elu(acc[q][2 * s][0]), fast_elu(acc[q][2 * s][1]));
+                    a2[s][1] = pack_h2(fast_elu(acc[q][2 * s][2]), fast_elu(acc[q][2 * s][3]));
+                    if (2 * s + 1 < NT) {
+                        a2[s][2] = pack_h2(fast_elu(acc[q][2 * s + 1][0]), fast_elu(acc[q][2 * s + 1][1]));
+                        a2[s][3] = pack_h2(fast_elu(acc[q][2 * s + 1][2]), fast_elu(acc[q][2 * s + 1][3]));
+                    } else {
+                        a2[s][2] = a2[s][3] = 0u;
+                    }
+                }
+                const int r0 = (mt0 + q) * 16 + g, r1 = r0 + 8;
+                const int t0 = r0 / Jp, f0 = r0 - t0 * Jp, t1 = r1 / Jp, f1 = r1 - t1 * Jp;
+                const bool v0 = t0 < T && f0 < Fo, v1 = t1 < T && f1 < Fo;
+                __half* y0 = reinterpret_cast<__half*>(sy) + (size_t)(t0 * Fo + f0) * COUT + 2 * tg;
+                __half* y1 = reinterpret_cast<__half*>(sy) + (size_t)(t1 * Fo + f1) * COUT + 2 * tg;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {  // trans tile j and gated tile NT + j land in the same lanes and slots
+                    float gt[4], gg4[4];
+                    gt[0] = gt[2] = spar[COUT + 8 * j + 2 * tg];
+                    gt[1] = gt[3] = spar[COUT + 8 * j + 2 * tg + 1];
+                    gg4[0] = gg4[2] = spar[2 * COUT + 8 * j + 2 * tg];
+                    gg4[1] = gg4[3] = spar[2 * COUT + 8 * j + 2 * tg + 1];
+#pragma unroll
+                    for (int s = 0; s < KS2; ++s) {
+                        const uint2 wt = swf2[(s * NT2 + j) * 32 + lane], wg = swf2[(s * NT2 + NT + j) * 32 + lane];
+                        mma16816(gt, a2[s], wt.x, wt.y);
+                        mma16816(gg4, a2[s], wg.x, wg.y);
+                    }
+                    float y[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) y[i] = gt[i] * fast_sigmoid(gg4[i]);
+                    if (v0) {
+                        psum += y[0] + y[1];
+                        psq = fmaf(y[0], y[0], fmaf(y[1], y[1], psq));
+                        *reinterpret_cast<uint32_t*>(y0 + 8 * j) = pack_h2(y[0], y[1]);
+                    }
+                    if (v1) {
+                        psum += y[2] + y[3];
+                        psq = fmaf(y[2], y[2], fmaf(y[3], y[3], psq));
+                        *reinterpret_cast<uint32_t*>(y1 + 8 * j) = pack_h2(y[2], y[3]);
+                    }
+                }
+            }
+        }
+        __syncthreads();  // X is dead: fetch the next stream's input while this one is normalised and written out
+        if (stream + (int)gridDim.x < p.B) issue_load(b + gridDim.x);
+        block_gln(psum, psq, count, p.student, s_red, s_co);
+        // ---- pass 2: GlobalLayerNorm -> the next block's input interior --------------------------------------------
+        {
+            const float mean = s_co[0], inv = s_co[1];
+            const int c8 = tid % UPR;  // kThreads % UPR == 0: a thread always serves the same channel octet
+            float na[8], nd[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                na[k] = __ldg(p.nw + 8 * c8 + k) * inv;
+                nd[k] = fmaf(-mean, na[k], __ldg(p.nb + 8 * c8 + k));
+            }
+            __half* ob = p.out + (long long)b * p.oB + 8 * c8;
+            const int total = T * Fo * UPR;
+            for (int u = tid; u < total; u += kThreads) {
+                const int row = u / UPR;
+                const int t = row / Fo, f = row - t * Fo;
+                float v[8];
+                unpack8(reinterpret_cast<const uint4*>(sy)[u], v);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = fmaf(v[k], na[k], nd[k]);
+                *reinterpret_cast<uint4*>(ob + (long long)t * p.oT + (long long)f * p.oF) = pack8(v);
+            }
+        }
+    }
+    cp_async_wait_all();
+}
+
+template <int CIN, int COUT>
+int launch_enc(EncMmaParams p, cudaStream_t st) {
+    using S = EncCfg<CIN, COUT>;
+    const int Jp = (p.Fp + 1) / 2;
+    const int plane = p.Tp * Jp + S::SLACK;
+    size_t off = (size_t)2 * S::NH * plane * 16;
+    p.off_y = (int)off;
+    off += (size_t)T * p.Fo * COUT * 2;
+    off = (off + 15) / 16 * 16;
+    p.off_wf = (int)off;
+    off += (size_t)(S::KS * S::NT + S::KS2 * S::NT2) * 32 * 8 + 3 * COUT * 4 + 2 * kWarps * 8 + 16;
+    SE_REQUIRE(off <= 227 * 1024, "enc_mma: the stream does not fit in shared memory");
+    SE_DYN_SMEM((enc_mma_kernel<CIN, COUT>), off);
+    int num_sms = 0;
+    if (num_sms_current_device(&num_sms)) return 1;
+    enc_mma_kernel<CIN, COUT><<<p.B < num_sms ? p.B : num_sms, kThreads, off, st>>>(p);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+bool enc_mma_supported(int Cin, int Cout, int Tp, int Fp, int Fo) {
+    if (!((Cin == 8 || Cin == 16) && (Cout == 8 || Cout == 16 || Cout == 32))) return false;
+    const int Jp = (Fp + 1) / 2;
+    const size_t bytes = (size_t)2 * (Cin / 8) * (Tp * Jp + 64) * 16 + (size_t)T * Fo * Cout * 2 + 40 * 1024;
+    return bytes <= 227 * 1024 && Fo <= Jp;
+}
+
+int launch_enc_mma(const EncMmaParams& p, int Cin, int Cout, cudaStream_t st) {
+    if (p.B <= 0) return 0;
+    SE_REQUIRE(enc_mma_supported(Cin, Cout, p.Tp, p.Fp, p.Fo), "enc_mma: unsupported shape");
+    if (Cin == 8 && Cout == 8) return launch_enc<8, 8>(p, st);
+    if (Cin == 8 && Cout == 16) return launch_enc<8, 16>(p, st);
+    if (Cin == 8 && Cout == 32) return launch_enc<8, 32>(p, st);
+    if (Cin == 16 && Cout == 8) return launch_enc<16, 8>(p, st);
+    if (Cin == 16 && Cout == 16) return launch_enc<16, 16>(p, st);
+    return launch_enc<16, 32>(p, st);
+}
+
+int launch_preconv3(const Preconv3Params& p, cudaStream_t st) {
+    if (p.B <= 0) return 0;
+    SE_DYN_SMEM(preconv3_mma_kernel, P3_SMEM);
+    int num_sms = 0;
+    if (num_sms_current_device(&num_sms)) return 1;
+    preconv3_mma_kernel<<<p.B < num_sms ? p.B : num_sms, kThreads, P3_SMEM, st>>>(p);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace se

@@ -825,21 +825,12 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1) gemm_tc_kernel(const
     }
 }
 
-int g_num_sms = 0;
-
 template <int BN, typename AT, bool B2B = (BN == 16)>
 int launch_tc(const GemmParams& p, cudaStream_t st) {
     using S = Cfg<BN, B2B>;
-    static bool configured = false;
-    if (!configured) {
-        SE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, AT, B2B>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::BYTES));
-        configured = true;
-    }
-    if (g_num_sms == 0) {
-        int dev = 0;
-        SE_CUDA_OK(cudaGetDevice(&dev));
-        SE_CUDA_OK(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    SE_DYN_SMEM((gemm_tc_kernel<BN, AT, B2B>), S::BYTES);
+    int g_num_sms = 0;
+    if (num_sms_current_device(&g_num_sms)) return 1;
     const int ntiles = ((p.M + BM - 1) / BM) * ((p.epi == EPI_GRU ? p.N : p.Npad) / BN);
     const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;  // persistent: one CTA per SM
     gemm_tc_kernel<BN, AT, B2B><<<grid, S::THREADS, S::BYTES, st>>>(p);

@@ -319,15 +319,29 @@ int launch_gru_tc_persist(const GruTcParams& p, cudaStream_t st) {
     SE_REQUIRE(gru_tc_persist_supported(p.H), "gru_tc_persist: hidden size must be a multiple of 64 that fits shared memory");
     if (p.B <= 0) return 0;
     const size_t smem = gru_tc_smem_bytes(p.H);
-    static size_t configured = 0;
-    if (configured < smem) {
-        SE_CUDA_OK(cudaFuncSetAttribute(gru_tc_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    SE_DYN_SMEM(gru_tc_persist_kernel, smem);
+    // The CTAs of an m-tile group wait for one another (release / acquire counter in L2), so every group of a launch must
+    // be resident at once: one CTA per SM (shared memory), hence at most floor(SMs / (H / 32)) m-tiles per launch.  More
+    // streams run as successive launches ("waves") over slices of the batch instead of relying on the dispatch order.
+    int num_sms = 0;
+    if (num_sms_current_device(&num_sms)) return 1;
+    const int ntn = p.H / 32;
+    const int tiles_per_wave = num_sms / ntn;
+    SE_REQUIRE(tiles_per_wave >= 1, "gru_tc_persist: more n-tiles than SMs");
+    const int mtiles = (p.B + BM - 1) / BM;
+    SE_CUDA_OK(cudaMemsetAsync(p.counters, 0, sizeof(int) * mtiles, st));
+    for (int m0 = 0; m0 < mtiles; m0 += tiles_per_wave) {
+        GruTcParams w = p;
+        const int b0 = m0 * BM;
+        const int nt = mtiles - m0 < tiles_per_wave ? mtiles - m0 : tiles_per_wave;
+        w.B = (p.B - b0) < nt * BM ? (p.B - b0) : nt * BM;
+        w.gi = p.gi + (long long)b0 * p.giB;
+        w.hseq = p.hseq + (long long)b0 * p.hB;
+        w.h32 = p.h32 + (long long)b0 * p.H;
+        w.counters = p.counters + m0;
+        gru_tc_persist_kernel<<<nt * ntn, kThreads, smem, st>>>(w);
+        SE_CUDA_OK(cudaGetLastError());
     }
-    const int grid = ((p.B + BM - 1) / BM) * (p.H / 32);
-    SE_CUDA_OK(cudaMemsetAsync(p.counters, 0, sizeof(int) * ((p.B + BM - 1) / BM), st));
-    gru_tc_persist_kernel<<<grid, kThreads, smem, st>>>(p);
-    SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

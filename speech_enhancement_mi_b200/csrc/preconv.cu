@@ -224,17 +224,9 @@ int launch_d(const PreconvParams& p, cudaStream_t st) {
     constexpr size_t bytes = (size_t)(2 * CH * TP * PRECONV_FPP(D) + PRECONV_W_FLOATS) * sizeof(float) +
                              2 * (kThreads / 32) * sizeof(double);
     static_assert(bytes <= 227 * 1024, "two input buffers must fit in shared memory");
-    static bool configured = false;
-    if (!configured) {
-        SE_CUDA_OK(cudaFuncSetAttribute(preconv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = true;
-    }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        SE_CUDA_OK(cudaGetDevice(&dev));
-        SE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    SE_DYN_SMEM(preconv_kernel<D>, bytes);
+    int num_sms = 0;
+    if (num_sms_current_device(&num_sms)) return 1;
     preconv_kernel<D><<<p.B < num_sms ? p.B : num_sms, kThreads, bytes, st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;

@@ -347,17 +347,9 @@ constexpr size_t kSmemBytes = X_BYTES + Z_BYTES + Y_BYTES + W_BYTES + PRECONV_W_
 int launch_preconv_tc(const PreconvTcParams& p, cudaStream_t st) {
     if (p.B <= 0) return 0;
     SE_REQUIRE(p.d == 1 || p.d == 2 || p.d == 4, "preconv_tc: frequency dilation must be 1, 2 or 4 (CRN_ELU.py:336)");
-    static bool configured = false;
-    if (!configured) {
-        SE_CUDA_OK(cudaFuncSetAttribute(preconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes));
-        configured = true;
-    }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        SE_CUDA_OK(cudaGetDevice(&dev));
-        SE_CUDA_OK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
+    SE_DYN_SMEM(preconv_tc_kernel, kSmemBytes);
+    int num_sms = 0;
+    if (num_sms_current_device(&num_sms)) return 1;
     preconv_tc_kernel<<<p.B < num_sms ? p.B : num_sms, kThreads, kSmemBytes, st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;

@@ -31,6 +31,16 @@ void set_error(const std::string& msg);
         }                                           \
     } while (0)
 
+// Per-device launch configuration (the C-ABI takes a device index, so one process may drive several GPUs):
+// ensure_dyn_smem opts `func` into `bytes` of dynamic shared memory on the CURRENT device, once per (device, kernel,
+// size); num_sms_current_device caches the SM count per device.  Both are thread-safe (crn.cu).
+int ensure_dyn_smem(const void* func, int bytes);
+int num_sms_current_device(int* out);
+#define SE_DYN_SMEM(kernel, bytes)                                                     \
+    do {                                                                               \
+        if (se::ensure_dyn_smem(reinterpret_cast<const void*>(kernel), (int)(bytes))) return 1; \
+    } while (0)
+
 // ---------------------------------------------------------------------------------------------------------------
 // gathered GEMM:  C[m][n] = sum_k A(m,k) * W[n][k],  m = (b*Tn + t)*Fo + f
 //   A(m,k) = A[b*sB + t*sT + f*sF + koff[k/4] + k%4]          (implicit im2col over channels-last activations)
@@ -167,6 +177,43 @@ struct PreconvTcParams {
     int b0, B;
 };
 int launch_preconv_tc(const PreconvTcParams& p, cudaStream_t st);
+
+// the three pre-convolution blocks in one launch and the small-channel encoder blocks (front_mma.cu; fp16 operand mode,
+// warp-level mma.sync with the stream's activations resident in shared memory)
+struct Preconv3Params {
+    const __half* feat;   // this chunk's features [B][21 frames][224 positions][8 halves], bin f at position 8 + f
+    long long feat_sB;    // halves per stream
+    __half* state;        // carried frames [B][3 layers][4 frames][224][8 halves] (read, then replaced)
+    long long state_sB;
+    const float* w[3];    // packed fp32 parameter blocks (PRECONV_W_* offsets above)
+    __half* out;          // out(b, t, f) = 16-byte unit at out + b*oB + t*oT + f*oF (halves)
+    long long oB, oT, oF;
+    int student;
+    int b0, B;
+};
+int launch_preconv3(const Preconv3Params& p, cudaStream_t st);
+constexpr int PRECONV3_POS = 224, PRECONV3_BORDER = 8;
+
+struct EncMmaParams {
+    const __half* in;     // zero-bordered input [B][Tp][Fp][Cin] (frame 0 = first carried frame, bin 0 = first pad bin)
+    long long in_sB;
+    int Tp, Fp, dt;       // Tp = 2 dt + 21 frames, Fp = F_in + 4 bins, time dilation dt
+    int Fo;               // output bins
+    const float* w;       // conv weights fp32 [>= Cout][Kp], column (kt * 5 + kf) * Cin + ci
+    int Kp;
+    const float* bias;
+    const float* w2;      // gate weights fp32 [2 Cout][w2_pitch], rows interleaved (conv_trans c, conv_gated c)
+    int w2_pitch;
+    const float* bias2;   // [2 Cout], interleaved like the rows
+    const float *nw, *nb; // GlobalLayerNorm affine [Cout]
+    __half* out;          // out(b, t, f, :) at out + b*oB + t*oT + f*oF (halves), Cout contiguous
+    long long oB, oT, oF;
+    int student;
+    int b0, B;
+    int off_y, off_wf;    // shared-memory offsets (filled by the launcher)
+};
+bool enc_mma_supported(int Cin, int Cout, int Tp, int Fp, int Fo);
+int launch_enc_mma(const EncMmaParams& p, int Cin, int Cout, cudaStream_t st);
 
 // GRU cell pointwise update for the fp32 path (PyTorch nn.GRU gate order r,z,n; CRN_ELU.py:127-133)
 int launch_gru_pointwise(const float* gi, long long giB, const float* gh, const float* hprev, long long hB,

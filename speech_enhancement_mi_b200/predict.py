@@ -24,7 +24,12 @@ def predict(args):
     stage_dir = os.path.join(config["config"]["checkpoint_dir"], "denoise", args.user_defined_name)
     model = getattr(CRN_ELU, args.name)(**config[args.name])
     path = os.path.join(stage_dir, args.name + ".pth")
-    if os.path.exists(path):
+    if not os.path.exists(path):
+        if not getattr(args, "allow_random_init", False):
+            raise FileNotFoundError(f"{path}: no checkpoint to evaluate (train first, or pass --allow_random_init to "
+                                    "measure the real-time factor on random weights)")
+        print(f"WARNING: {path} is missing; evaluating RANDOM-INIT weights (quality numbers are meaningless)")
+    else:
         model.load_state_dict(torch.load(path), strict=False)  # predict.py:47
     model.eval()
     data = SyntheticPartyDataset(size=args.items, max_length=config["config"]["max_length"])
@@ -53,4 +58,5 @@ if __name__ == "__main__":
     ap.add_argument("config_path")
     ap.add_argument("--user_defined_name", default="model")
     ap.add_argument("--items", type=int, default=8)
+    ap.add_argument("--allow_random_init", action="store_true")
     predict(ap.parse_args())

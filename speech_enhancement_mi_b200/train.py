@@ -79,8 +79,10 @@ class Processor:
         self.dataset = SyntheticPartyDataset(size=args.items, max_length=self.config["config"]["max_length"],
                                              num_mic=self.config["config"]["num_mic"])
         if args.engine == "native":
-            # capacity for the longest piece (pieces with flag=True must find the context of their predecessor)
-            max_chunks = 2 * (int(self.config["config"]["max_length"]) // self.model.segment_length + 3)
+            # capacity for the longest piece (pieces with flag=True must find the context of their predecessor), never
+            # below what the model's own evaluation path asks for (dev pass of every epoch)
+            max_chunks = max(2 * (int(self.config["config"]["max_length"]) // self.model.segment_length + 3),
+                             self.model._train_capacity(1, 0))
             self.trainer = NativeTrainer(self.model, lr=self.lr, max_grad_norm=self.config["config"]["max_grad_norm"],
                                          gradient_accumulation=self.accum, device=self.local_rank,
                                          max_chunk_streams=max_chunks)
@@ -170,6 +172,14 @@ class Processor:
         for epoch in range(self.epoch + 1, num_epoch):
             train_loss = self.run_epoch("train", self.args.steps)
             dev_loss = self.run_epoch("dev", max(1, self.args.steps // 4))
+            # data parallel: every rank evaluated its own shard.  The plateau scheduler and the "best model" decision must
+            # see ONE number on every rank, or the ranks halve the learning rate in different epochs and the replicas drift
+            # apart (parameters are never re-broadcast after the first step).
+            if torch.distributed.is_available() and torch.distributed.is_initialized() \
+                    and torch.distributed.get_world_size() > 1:
+                t = torch.tensor([dev_loss], dtype=torch.float64, device=f"cuda:{self.local_rank}")
+                torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.SUM)
+                dev_loss = float(t[0]) / torch.distributed.get_world_size()
             improved = dev_loss < self.last_loss
             if improved:
                 self.last_loss = dev_loss

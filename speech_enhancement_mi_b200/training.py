@@ -62,8 +62,10 @@ class NativeTrainer:
             model._max_streams = max(model._max_streams, int(max_chunk_streams))
         with torch.cuda.device(self.device):
             model.to(f"cuda:{self.device}")
-            model._ensure_train_ctx(1, self.device, keep_state=False)
-            self.ctx = model._tctx
+            # sized like the model's own evaluation path sizes it (44 chunk-streams per utterance), so that the dev pass of
+            # an epoch (model.realtime_process -> chunk-batched forward) never has to re-create the context
+            model._ensure_train_ctx(model._train_capacity(1, 0), self.device, keep_state=False)
+            self._ctx_gen = model._tctx_gen
             params = model._train_params()
             self.param_names = [lib().se_crn_param_name(self.ctx, i).decode() for i in range(len(params))]
             n = lib().se_crn_num_theta(self.ctx)
@@ -82,6 +84,20 @@ class NativeTrainer:
             self.w_sisnr = torch.full((1,), -0.3 / self.accum, dtype=torch.float32, device=dev)  # sisnr enters negated
             self.norm = torch.zeros(1, dtype=torch.float32, device=dev)
             self._rebind()
+
+    @property
+    def ctx(self):
+        """The model's CURRENT native training context.  The handle is never cached: the model re-creates the context
+        when a call needs more chunk-streams (the old handle is then freed); CUDA graphs captured on the old context and
+        its weight binding die with it."""
+        if self.model._tctx is None:
+            self.model._ensure_train_ctx(self.model._train_capacity(1, 0), self.device, keep_state=False)
+        if self.model._tctx_gen != self._ctx_gen:
+            self._ctx_gen = self.model._tctx_gen
+            self._graphs.clear()
+            with torch.cuda.device(self.device):
+                self._rebind()
+        return self.model._tctx
 
     def reload_parameters(self):
         """After model.load_state_dict (resume, train.py:110): copy_ wrote through the views into the flat vector; re-lay
@@ -102,7 +118,8 @@ class NativeTrainer:
         return e
 
     def _rebind(self):
-        check(lib().se_crn_bind_weights_flat(self.ctx, self.theta.data_ptr(), self._stream()), "se_crn_bind_weights_flat")
+        check(lib().se_crn_bind_weights_flat(self.model._tctx, self.theta.data_ptr(), self._stream()),
+              "se_crn_bind_weights_flat")
         self.model._tbound_versions = tuple((t.data_ptr(), t._version) for t in self.model._train_params())
 
     def _launch_micro(self, mixture, source, lens, B, L, flag, pred, out2, d_stoi, d_sisnr):
@@ -112,6 +129,7 @@ class NativeTrainer:
         t0 = mark()
         check(lib().se_crn_train_forward(self.ctx, mixture.data_ptr(), B, L, int(bool(flag)), pred.data_ptr(), st),
               "se_crn_train_forward")
+        self.model._fwd_gen += 1
         t1 = mark("forward", t0)
         check(lib().se_loss_terms_grad(source.data_ptr(), pred.data_ptr(), lens.data_ptr(), B, L, out2.data_ptr(),
                                        d_stoi.data_ptr(), d_sisnr.data_ptr(), st), "se_loss_terms_grad")
@@ -131,11 +149,9 @@ class NativeTrainer:
         B, _, L = mixture.shape
         with torch.cuda.device(self.device):
             _, n_chunks = _native.chunk_grid(L + (0 if flag else self.model.segment_length // 2), self.model.segment_length)
-            if B * n_chunks > self.model._tctx_capacity:
-                ctx = self.model._ensure_train_ctx(B * n_chunks, self.device, keep_state=bool(flag))
-                self.ctx = ctx
-                self._graphs.clear()
-                self._rebind()
+            if self.model._tctx is None or B * n_chunks > self.model._tctx_capacity:
+                self.model._ensure_train_ctx(self.model._train_capacity(B, n_chunks), self.device, keep_state=bool(flag))
+            _ = self.ctx  # notices a re-created context (here or by the model's evaluation path): graphs dropped, weights re-bound
             dev = self.theta.device
             lens = torch.as_tensor(length)
             if lens.device != dev or lens.dtype != torch.int32:
@@ -178,6 +194,7 @@ class NativeTrainer:
                 st = self._stream()
                 check(lib().se_crn_train_forward(self.ctx, mixture.data_ptr(), B, L, int(bool(flag)), pred.data_ptr(), st),
                       "se_crn_train_forward")
+                self.model._fwd_gen += 1
                 check(lib().se_loss_terms_grad(source.data_ptr(), pred.data_ptr(), lens.data_ptr(), B, L, out2.data_ptr(),
                                                d_stoi.data_ptr(), d_sisnr.data_ptr(), st), "se_loss_terms_grad")
                 self.micro += 1
@@ -199,6 +216,7 @@ class NativeTrainer:
     def optimizer_step(self):
         """All-reduce (data parallel), clip_grad_norm_(max_grad_norm), Adam, re-layout of the weights, zero_grad."""
         with torch.cuda.device(self.device):
+            _ = self.ctx  # re-bind first if the evaluation path re-created the context since the last micro-step
             scale = allreduce_mean_(self.grad, self.group)
             self.step_count += 1
             check(lib().se_clip_adam_step(self.theta.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
