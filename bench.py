@@ -9,8 +9,14 @@ state carried in HBM.  Workload = BASELINE.json configs[1]: teacher CRN_ELU, 102
 Streams are independent, so N GPUs run N x 1024 streams with no data-path collective ("weak" scaling); NCCL is used
 only to take the max of the device time over ranks.
 
-`--impl reference` times the reference algorithm's CPU restatement (oracle/, torch CPU ops = the kernels the reference
-runs in predict.py:48) on the host cores, on a bounded sample of the same workload.
+`--impl reference` times the UNMODIFIED reference (`oracle/_ref/reference.zip`, packed from /root/reference by
+`oracle/build_ref.py`; `CRN_ELU.TemporalCRN.realtime_process` on torch CPU ops, as predict.py:48,92 runs it) on the
+host cores, on a bounded sample of the same workload; without the archive it falls back to the oracle restatement.
+
+Besides the headline (fp16 operand mode) the line carries, measured in the same run: `modes` (the same workload in tf32
+and exact fp32 mode), `latency` (p50 / p99 chunk latency at 1 and 16 streams), and `configs` -- the other BASELINE.json
+configurations: the distilled student at 2048 streams per GPU (configs[2]), FullSubNet on 3 s utterances (configs[3]) and
+the training step with its NCCL gradient all-reduce (configs[4]).  `--no-extras` skips them.
 """
 from __future__ import annotations
 
@@ -45,6 +51,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU time budget of the cpu_baseline leg")
     ap.add_argument("--latency-steps", type=int, default=1000, help="steps of the p99 chunk-latency pass")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip modes / latency / configs (headline only)")
+    ap.add_argument("--student-streams", type=int, default=2048, help="configs[2]: 16384 streams over 8 GPUs")
+    ap.add_argument("--fsn-streams", type=int, default=256, help="configs[3]: FullSubNet utterances per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-step", action="store_true",
                     help="warm up, then run ONE chunk step inside cudaProfilerStart/Stop (for ncu --profile-from-start off) "
@@ -162,73 +171,96 @@ def build_model(args, max_streams):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU baseline (oracle port) -- the only place bench.py touches oracle/
+# CPU legs: the UNMODIFIED reference from oracle/_ref (kind "reference"), else the oracle restatement (kind "port").
+# The only places bench.py touches oracle/ -- as the thing timed BESIDE the product, never inside it.
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_baseline(args, n_streams, budget_s, min_steps=3):
+def _reference_model(args):
+    """(model, kind): the reference's own TemporalCRN with the synthetic weights, or None when the archive is absent."""
     import torch
-    from oracle.crn_oracle import CRNOracle  # checker / baseline only
+    from oracle import ref_loader
     from speech_enhancement_mi_b200 import synth, workload
+    if not ref_loader.available():
+        return None
     cfg = workload.TEACHER if args.model == "teacher" else workload.STUDENT
+    if args.model == "teacher":
+        (mod,) = ref_loader.load(("CRN_ELU",))
+        model = mod.TemporalCRN(segment_length=3200, dropout=0.0, **cfg)
+    else:
+        (mod,) = ref_loader.load(("distillation_crn",))
+        model = mod.TemporalCRN(segment_length=3200, dropout=0.0, **cfg)
+    w = synth.make_crn_weights(seed=0, **cfg)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in synth.with_alias_keys(w).items()}, strict=True)
+    return model.eval()
+
+
+def _cpu_run(args, n_streams, steps, warmup, budget_s=None):
+    """Times the CPU implementation on `n_streams` of the workload's streams.  A step = every stream advanced by one second
+    of audio through the reference's public call `realtime_process` (10 chunk hops + its own padding chunks); the port
+    advances chunk by chunk.  Returns (audio-s/s, ms per step, steps done, kind, cores, description)."""
+    import torch
+    from speech_enhancement_mi_b200 import workload
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    w = synth.make_crn_weights(seed=0, **cfg)
-    oracle = CRNOracle({k: torch.from_numpy(v) for k, v in w.items()}, segment_length=3200,
-                       student=args.model == "student", **cfg)
-    sig = torch.from_numpy(synthetic_signal(n_streams, (RING + 1) * 1600))
-    carry = None
+    ref = _reference_model(args)
+    L = 16000
+    sig = torch.from_numpy(synthetic_signal(n_streams, L))
     times = []
     with torch.no_grad():
-        oracle.stream_step(sig[:, :, :3200], None)  # warm-up (thread pool, allocator)
-        oracle.reset()
+        if ref is not None:
+            def step():
+                y = ref.realtime_process(sig)
+                return y[0] if isinstance(y, tuple) else y
+            audio_per_step = n_streams * L / 16000.0
+            kind = "reference"
+            what = (f"unmodified reference {'CRN_ELU' if args.model == 'teacher' else 'distillation_crn'}.TemporalCRN."
+                    f"realtime_process (oracle/_ref/reference.zip) on [{n_streams}, 3, {L}] per step")
+        else:
+            from oracle.crn_oracle import CRNOracle
+            from speech_enhancement_mi_b200 import synth
+            cfg = workload.TEACHER if args.model == "teacher" else workload.STUDENT
+            w = synth.make_crn_weights(seed=0, **cfg)
+            oracle = CRNOracle({k: torch.from_numpy(v) for k, v in w.items()}, segment_length=3200,
+                               student=args.model == "student", **cfg)
+            state = {"carry": None, "i": 0}
+
+            def step():
+                off = (state["i"] % 8) * 1600
+                state["i"] += 1
+                out, state["carry"] = oracle.stream_step(sig[:, :, off:off + 3200], state["carry"])
+                return out
+            audio_per_step = n_streams * workload.AUDIO_SEC_PER_STEP
+            kind = "port"
+            what = f"oracle/crn_oracle.py stream_step (restating CRN_ELU.py:367-509) on {n_streams} streams per step"
+        for _ in range(max(warmup, 1)):
+            step()
         t_start = time.perf_counter()
-        n = 0
         while True:
-            off = (n % RING) * 1600
             t0 = time.perf_counter()
-            _, carry = oracle.stream_step(sig[:, :, off:off + 3200], carry)
+            step()
             times.append(time.perf_counter() - t0)
-            n += 1
-            if n >= min_steps and time.perf_counter() - t_start > budget_s:
+            if budget_s is None and len(times) >= steps:
+                break
+            if budget_s is not None and len(times) >= 2 and time.perf_counter() - t_start > budget_s:
                 break
     mean = sum(times) / len(times)
-    return {"value": n_streams * workload.AUDIO_SEC_PER_STEP / mean, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_streams} of the workload's streams x {len(times)} chunk steps, teacher fp32, torch CPU ops "
-                      f"with {cores} threads (oracle/crn_oracle.py stream_step)",
-            "ms_per_step": mean * 1e3}
+    return audio_per_step / mean, mean * 1e3, len(times), kind, cores, what
+
+
+def cpu_baseline(args, n_streams, budget_s):
+    value, ms, n, kind, cores, what = _cpu_run(args, n_streams, steps=0, warmup=1, budget_s=budget_s)
+    return {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n_streams} of the workload's streams, {n} steps, fp32 torch CPU ops with {cores} threads: {what}",
+            "ms_per_step": ms}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from speech_enhancement_mi_b200 import workload
     n = args.cpu_streams
-    # warm-up + exactly K timed steps of the bounded sample
-    import torch
-    from oracle.crn_oracle import CRNOracle
-    from speech_enhancement_mi_b200 import synth
-    cfg = workload.TEACHER if args.model == "teacher" else workload.STUDENT
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    w = synth.make_crn_weights(seed=0, **cfg)
-    oracle = CRNOracle({k: torch.from_numpy(v) for k, v in w.items()}, segment_length=3200,
-                       student=args.model == "student", **cfg)
-    sig = torch.from_numpy(synthetic_signal(n, (RING + 1) * 1600))
-    carry = None
-    steps = min(args.steps, 40)
-    with torch.no_grad():
-        for i in range(max(args.warmup, 1)):
-            off = (i % RING) * 1600
-            _, carry = oracle.stream_step(sig[:, :, off:off + 3200], carry)
-        t0 = time.perf_counter()
-        for i in range(steps):
-            off = (i % RING) * 1600
-            _, carry = oracle.stream_step(sig[:, :, off:off + 3200], carry)
-        dt = time.perf_counter() - t0
-    ms = dt / steps * 1e3
-    value = n * workload.AUDIO_SEC_PER_STEP / (dt / steps)
-    sample = (f"{n} of the {args.streams} streams per step, {steps} steps, torch CPU ops with {cores} threads "
-              f"(oracle/crn_oracle.py, restating CRN_ELU.py:367-509)")
+    steps = min(args.steps, 20)
+    value, ms, steps, kind, cores, what = _cpu_run(args, n, steps=steps, warmup=max(args.warmup, 1))
+    sample = f"{n} of the {args.streams} streams per step, {steps} steps, fp32 torch CPU ops with {cores} threads: {what}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": max(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -236,7 +268,7 @@ def run_reference(args):
         "config": {"workload": f"CRN_ELU {args.model} batched streaming inference, {args.streams} concurrent synthetic "
                                f"streams per GPU, 3200-sample chunks at hop 1600 (BASELINE.json configs[1])",
                    "streams_per_gpu": args.streams, "precision": "fp32", "sample": sample},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -387,13 +419,22 @@ def main():
         peaks["src"] = "measured"
     except Exception:
         pass
-    traffic = {}
+    # DRAM bytes per launch come from an ncu capture of one chunk step (tools/ncu_step_summary.py); they are reported only
+    # when that capture was taken on the library this run loads (source hash recorded with the capture)
+    traffic, traffic_note = {}, "no ncu capture for this build"
     try:
+        from speech_enhancement_mi_b200 import build as native_build
         with open(os.path.join(REPO, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch", {})
+            tj = json.load(f)
+        if tj.get("source_hash") == native_build.source_hash():
+            traffic = tj.get("dram_bytes_per_launch", {})
+            traffic_note = f"ncu dram__bytes_read+write per launch, capture {tj.get('capture', '?')} of this build"
+        else:
+            traffic_note = "profiles/ncu_traffic.json was captured on another build of the library: not reported"
     except Exception:
         pass
     stages, kernels, roofline, step_aggregate = {}, [], None, None
+    launches_per_chunk = lib().se_crn_launches_per_chunk(model._ctx)
     if rank == 0:
         import re
         L = lib()
@@ -439,20 +480,64 @@ def main():
                           "algorithmic_gb_per_s": step_bytes / (ms_per_step * 1e-3) / 1e9,
                           "frac_of_hbm_peak": step_bytes / (ms_per_step * 1e-3) / 1e9 / peaks["hbm_gbs"],
                           "sum_of_kernel_ms": tot}
-        top = max(kernels, key=lambda k: k["share"])
-        roofline = {"kernel": top["name"], "launches_per_step": top["launches"], "ms_per_launch": top["ms"],
+        # `roofline` = the WORST kernel of the step (lowest fraction of its bound among the kernels that hold >= 2 % of the
+        # step), with the whole-step aggregate beside it; the per-kernel list is in `kernels`.
+        cand = [k for k in kernels if k["share"] >= 0.02] or kernels
+        top = min(cand, key=lambda k: k["frac"])
+        roofline = {"kernel": top["name"], "selection": "worst fraction among kernels with >= 2 % of the step",
+                    "launches_per_step": top["launches"], "ms_per_launch": top["ms"],
                     "share_of_step": top["share"], "bound": top["bound"], "achieved": top["achieved"],
                     "peak": top["peak"], "unit": top["unit"], "frac": top["frac"], "traffic": top["traffic"],
-                    "peak_source": f"{peaks['src']} ({'bf16/fp16 dense burst; tf32 math runs at half that rate' if top['bound'] == 'tensor' else 'copy bandwidth'})"}
+                    "traffic_source": traffic_note,
+                    "peak_source": f"{peaks['src']} ({'bf16/fp16 dense burst; tf32 math runs at half that rate' if top['bound'] == 'tensor' else 'copy bandwidth'})",
+                    "step": step_aggregate,
+                    "kernels_at_or_above_half_of_bound": sum(1 for k in kernels if k["frac"] >= 0.5),
+                    "kernels_total": len(kernels)}
         if "frac_of_tf32_rate" in top:
             roofline["frac_of_tf32_rate"] = top["frac_of_tf32_rate"]
 
+    # ---- the rest of the contract, measured in the same run (every rank takes part: the parts hold barriers) -------
+    modes, latency, configs = None, None, None
+    if not args.no_extras:
+        from tools import bench_parts
+        del model
+        torch.cuda.empty_cache()
+        short = max(3, min(K, 10))
+        modes = {"fp16": {"ms_per_step": ms_per_step, "value": value, "unit": UNIT}}
+        for prec in ("tf32", "fp32"):
+            r = bench_parts.crn_stream(args.model, B, prec, steps=short if prec == "tf32" else max(3, short // 2), dev=dev)
+            modes[prec] = {"ms_per_step": r["ms_per_step"], "value": r["value"], "unit": UNIT, "steps": r["steps"],
+                           "algorithmic_tflop_per_s": r["algorithmic_tflop_per_s"]}
+        modes["note"] = ("same workload and streams; fp32 = exact CUDA-core arithmetic (parity anchor), tf32 = tcgen05 kind::tf32 "
+                         "on fp32 storage, fp16 = fp16 operand storage with fp32 accumulation / statistics / state (headline)")
+        latency = {}
+        for nb in (1, 16):
+            r = bench_parts.crn_stream(args.model, nb, args.precision, steps=20, latency_steps=300, dev=dev)
+            latency[f"streams_{nb}"] = {k: r[k] for k in ("ms_per_step", "p50_chunk_latency_ms", "p99_chunk_latency_ms",
+                                                          "latency_steps", "value")}
+        latency["note"] = "device time of one chunk step (CUDA events), real-time deadline 100 ms per step"
+        configs = {}
+        r = bench_parts.crn_stream("student", args.student_streams, args.precision, steps=short, dev=dev)
+        r["roofline"] = {"bound": "tensor", "achieved": r["algorithmic_tflop_per_s"], "peak": peaks["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": r["algorithmic_tflop_per_s"] / peaks["bf16_tflops"],
+                         "note": "whole-step algorithmic FLOPs (250.9 MFLOP per stream-chunk) over the step time"}
+        r["workload"] = (f"distilled student CRN, {args.student_streams} concurrent streams per GPU "
+                         "(BASELINE.json configs[2]: 16384 streams over 8 GPUs)")
+        configs["student_streams"] = r
+        r = bench_parts.fsn_utterances(args.fsn_streams, seconds=3.0, reps=1, precision="fp16", peak_tflops=peaks["bf16_tflops"],
+                                       dev=dev)
+        r["workload"] = f"FullSubNet, {args.fsn_streams} synthetic 3 s utterances per GPU, train=False chunk loop (BASELINE.json configs[3])"
+        configs["fsn_3s"] = r
+        r = bench_parts.train_step(batch=1, seconds=2.0, steps=5, warmup=2, precision="tf32", graph=True, dev=dev)
+        r["workload"] = ("CRN_ELU compute_loss training step, one 2 s piece per rank, grad-accum 2, gradient all-reduce over the "
+                         "ranks of this run (BASELINE.json configs[4])")
+        configs["train_step"] = r
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(args, args.cpu_streams, args.cpu_seconds)
 
     if rank == 0:
-        launches = lib().se_crn_launches_per_chunk(model._ctx) + 1  # + the io-descriptor kernel
+        launches = launches_per_chunk + 1  # + the io-descriptor kernel
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -464,7 +549,8 @@ def main():
                              f"per-step working set of several GB, both > 126 MB L2"},
             "p99_chunk_latency_ms": lat[min(len(lat) - 1, int(0.99 * len(lat)))],
             "p50_chunk_latency_ms": lat[len(lat) // 2], "latency_steps": len(lat),
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * K, "roofline": roofline, "step_aggregate": step_aggregate, "stages": stages, "kernels": kernels,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches * K, "roofline": roofline, "step_aggregate": step_aggregate,
+            "modes": modes, "latency": latency, "configs": configs, "stages": stages, "kernels": kernels,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), file=_REAL_STDOUT, flush=True)

@@ -19,6 +19,8 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "se_internal.h"
 
 namespace se {
@@ -35,8 +37,10 @@ __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                  : "r"(addr));
 }
+// not volatile: a pure register function, so that the compiler may move the dependent HMMA behind the NEXT ldmatrix (two
+// volatile statements keep their order, which serialised every ldmatrix -> mma pair on the ~30-cycle shared-memory latency)
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -45,8 +49,24 @@ __device__ __forceinline__ uint32_t pack_h2(float x, float y) {
     const __half2 h = __floats2half2_rn(x, y);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_elu(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+// MUFU forms with flush-to-zero: without .ftz the compiler wraps every ex2 / rcp in a denormal range check (FSETP + two
+// predicated FMULs), which tripled the instruction count of the epilogues (ncu: FMUL 14 %, FSETP 6 % of the kernel)
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2e = 1.4426950408889634f;
+// gate: the caller passes z = -log2(e) * (pre-activation); the factor is folded into the gate weights and bias
+__device__ __forceinline__ float sigmoid_from_neg_log2(float z) { return rcp_ftz(1.0f + ex2_ftz(z)); }
+__device__ __forceinline__ float fast_elu(float x) { return x > 0.f ? x : ex2_ftz(x * kLog2e) - 1.0f; }
+// exact quotient r / d for r < 65536 with magic = ceil(2^32 / d)
+__device__ __forceinline__ int div_magic(int r, uint32_t magic) { return (int)__umulhi((uint32_t)r, magic); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
@@ -72,6 +92,7 @@ __device__ __forceinline__ uint4 pack8(const float* o) {
 
 // GlobalLayerNorm coefficients of one stream from the per-thread partial sums (CRN_ELU.py:40-51 /
 // distillation_crn.py:51): every thread calls this; returns after a __syncthreads with s_co = {mean, 1/den}
+template <int NWARPS = kWarps>
 __device__ __forceinline__ void block_gln(float psum, float psq, double count, int student, double* s_red, float* s_co) {
     double ds = psum, dq = psq;
 #pragma unroll
@@ -82,14 +103,14 @@ __device__ __forceinline__ void block_gln(float psum, float psq, double count, i
     const int warp = threadIdx.x >> 5;
     if ((threadIdx.x & 31) == 0) {
         s_red[warp] = ds;
-        s_red[kWarps + warp] = dq;
+        s_red[NWARPS + warp] = dq;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         double a = 0.0, q = 0.0;
-        for (int w = 0; w < kWarps; ++w) {
+        for (int w = 0; w < NWARPS; ++w) {
             a += s_red[w];
-            q += s_red[kWarps + w];
+            q += s_red[NWARPS + w];
         }
         const double mu = a / count;
         double var = q / count - mu * mu;
@@ -108,28 +129,42 @@ __device__ __forceinline__ void block_gln(float psum, float psq, double count, i
 // X[25 frames: 4 carried + 21 new][224 positions][8 halves]: bin f at position 8 + f, zero elsewhere (the conv's
 // frequency padding 2 d <= 8 and the overrun of the last 16-row tile).  Output row (t, f), tap (kt, kf) reads unit
 // (t + kt) * 224 + 8 + f + (kf - 2) d: sixteen consecutive rows are sixteen consecutive 16-byte units = one conflict-free
-// ldmatrix phase per 8 rows.  K = 25 taps x 8 channel slots = 13 k-steps of two taps; N = 8 (5 real output channels).
+// ldmatrix phase per 8 rows.  N = 8 (5 real output channels); a fragment = two frequency taps of one input frame x 8
+// channel slots (k = 16).  One warp owns a column of 16 bins and walks the 25 input frames: the three fragments of input
+// frame u serve the five output frames u - kt, whose accumulators roll through five register slots.
 constexpr int P3_POS = 224;
 constexpr int P3_BORDER = 8;
 constexpr int P3_ROW_BYTES = P3_POS * 16;
 constexpr int P3_X_BYTES = (T + 4) * P3_ROW_BYTES;       // 89,600
 constexpr int P3_YPITCH = 208;                           // 13 tiles of 16 bins per frame
 constexpr int P3_Y_BYTES = T * P3_YPITCH * 16;           // 69,888: gated values (pre-norm) as fp16 units
-constexpr int P3_KS = 13;
-constexpr int P3_WF_LAYER = (P3_KS + 2) * 32;            // uint2 per layer: 13 conv k-steps + 2 gate n-tiles
+constexpr int P3_THREADS = 512;
+constexpr int P3_WARPS = P3_THREADS / 32;
+// conv B fragments per layer: 10 x (kt, j) with j = frequency-tap pair (0,1) / (2,3) of one input frame, then 3 for tap 4,
+// which pairs the SAME tap of two consecutive input frames: (kt 0, kt 1), (kt 2, kt 3), (kt 4, zero)
+constexpr int P3_NFR = 13;
+constexpr int P3_WF_LAYER = (P3_NFR + 2) * 32;           // uint2 per layer: 13 conv fragments + 2 gate n-tiles
 constexpr int P3_WF_BYTES = 3 * P3_WF_LAYER * 8;         // 11,520
-constexpr int P3_NPAR = 32;                              // floats per layer: cb[8] bt[8] bg[8] | nw[5] nb[5] (pad)
+constexpr int P3_NPAR = 32;                              // floats per layer: cb[8] bt[8] bg[8] nw[8]
 constexpr int P3_PAR_BYTES = 3 * P3_NPAR * 4;
 constexpr int P3_OFF_Y = P3_X_BYTES;
 constexpr int P3_OFF_WF = P3_OFF_Y + P3_Y_BYTES;
 constexpr int P3_OFF_PAR = P3_OFF_WF + P3_WF_BYTES;
 constexpr int P3_OFF_RED = P3_OFF_PAR + P3_PAR_BYTES;    // double [2][16]
-constexpr int P3_OFF_CO = P3_OFF_RED + 2 * kWarps * 8;   // float [2]
+constexpr int P3_OFF_CO = P3_OFF_RED + 2 * 16 * 8;       // float [2]
 constexpr int P3_SMEM = P3_OFF_CO + 16;
-constexpr int P3_MT = T * 13;                            // 273 tiles of 16 rows
 static_assert(P3_SMEM <= 227 * 1024, "shared memory budget");
 
-__global__ void __launch_bounds__(kThreads, 1) preconv3_mma_kernel(Preconv3Params p) {
+// ldmatrix as a PURE function of (address, epoch): not volatile, so that the compiler may hoist the loads of the next
+// input frame above the epilogue of the current one.  `epoch` is produced by a volatile statement behind the barrier
+// that published the data, which pins the load below that barrier (and makes loads of different layers distinct).
+__device__ __forceinline__ void ldsm_x4_dep(uint32_t addr, uint32_t epoch, uint32_t (&r)[4]) {
+    asm("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+        : "r"(addr), "r"(epoch));
+}
+
+__global__ void __launch_bounds__(P3_THREADS, 1) preconv3_mma_kernel(Preconv3Params p) {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* sx = smem;
     unsigned char* sy = smem + P3_OFF_Y;
@@ -142,47 +177,61 @@ __global__ void __launch_bounds__(kThreads, 1) preconv3_mma_kernel(Preconv3Param
 
     // ---- one-time set-up: B fragments (fp16) and the small fp32 parameters of the three layers ---------------------
     // packed parameter block of a layer (se_internal.h PRECONV_W_*): conv [(kt*5+ci)*28 + kf*5 + co], ...
-    for (int i = tid; i < 3 * P3_WF_LAYER; i += kThreads) {
+    // The conv_gated weights and bias carry the factor -log2(e) of the sigmoid (1 / (1 + 2^z)).
+    for (int i = tid; i < 3 * P3_WF_LAYER; i += P3_THREADS) {
         const int l = i / P3_WF_LAYER, r = i - l * P3_WF_LAYER, s = r >> 5, ln = r & 31;
         const int gg = ln >> 2, t4 = ln & 3;
-        const float* w = p.w[l];
+        const float* w = l == 0 ? p.w[0] : (l == 1 ? p.w[1] : p.w[2]);
         float v[4] = {0.f, 0.f, 0.f, 0.f};
-        if (s < P3_KS) {  // conv k-step s: taps 2s (k 0..7) and 2s+1 (k 8..15), B column = output channel gg
+        if (s < P3_NFR) {  // k 0..7 <- tap (ktA, kfA), k 8..15 <- tap (ktB, kfB); column = output channel gg
+            int ktA, kfA, ktB, kfB;
+            if (s < 10) {
+                ktA = ktB = s >> 1;
+                kfA = 2 * (s & 1);
+                kfB = kfA + 1;
+            } else {
+                ktA = 2 * (s - 10);
+                ktB = ktA + 1;  // 5: no such tap, zero
+                kfA = kfB = 4;
+            }
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int tap = 2 * s + h;
-                const int kt = tap / 5, kf = tap - 5 * kt;
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int ci = 2 * t4 + e;
-                    if (tap < 25 && ci < 5 && gg < 5) v[2 * h + e] = __ldg(w + (kt * 5 + ci) * 28 + kf * 5 + gg);
+            for (int e = 0; e < 2; ++e) {
+                const int ci = 2 * t4 + e;
+                if (ci < 5 && gg < 5) {
+                    v[e] = __ldg(w + (ktA * 5 + ci) * 28 + kfA * 5 + gg);
+                    if (ktB < 5) v[2 + e] = __ldg(w + (ktB * 5 + ci) * 28 + kfB * 5 + gg);
                 }
             }
         } else {  // gate n-tile (0: conv_trans, 1: conv_gated): k = ELU channel 2 t4 + e, column = output channel gg
-            const int base = s == P3_KS ? PRECONV_W_WT : PRECONV_W_WG;
+            const bool gated = s != P3_NFR;
+            const int base = gated ? PRECONV_W_WG : PRECONV_W_WT;
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int k = 2 * t4 + e;
-                if (k < 5 && gg < 5) v[e] = __ldg(w + base + gg * 5 + k);
+                if (k < 5 && gg < 5) v[e] = __ldg(w + base + gg * 5 + k) * (gated ? -kLog2e : 1.f);
             }
         }
         swf[i] = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
     }
-    for (int i = tid; i < 3 * P3_NPAR; i += kThreads) {
-        const int l = i / P3_NPAR, r = i - l * P3_NPAR;
-        const float* w = p.w[l];
+    for (int i = tid; i < 3 * P3_NPAR; i += P3_THREADS) {
+        const int l = i / P3_NPAR, r = i - l * P3_NPAR, c = r & 7;
+        const float* w = l == 0 ? p.w[0] : (l == 1 ? p.w[1] : p.w[2]);
         float v = 0.f;
-        if (r < 8) v = r < 5 ? __ldg(w + PRECONV_W_BIAS + r) : 0.f;
-        else if (r < 16) v = r - 8 < 5 ? __ldg(w + PRECONV_W_BT + r - 8) : 0.f;
-        else if (r < 24) v = r - 16 < 5 ? __ldg(w + PRECONV_W_BG + r - 16) : 0.f;
+        if (c < 5) {
+            if (r < 8) v = __ldg(w + PRECONV_W_BIAS + c);
+            else if (r < 16) v = __ldg(w + PRECONV_W_BT + c);
+            else if (r < 24) v = -kLog2e * __ldg(w + PRECONV_W_BG + c);
+            else v = __ldg(w + PRECONV_W_NW + c);
+        }
         spar[i] = v;
     }
     __syncthreads();
 
-    // per-lane ldmatrix role: matrices 0/1 = rows 0-7 / 8-15 of the k-step's first tap, 2/3 = of its second tap
+    // per-lane ldmatrix role: matrices 0/1 = rows 0-7 / 8-15 of the fragment's first tap, 2/3 = of its second tap
     const int mi = lane >> 3;
     const int rowoff = (lane & 7) + 8 * (mi & 1);
     const int tapsel = mi >> 1;
+    uint32_t epoch_base = 0;
 
     for (int stream = blockIdx.x; stream < p.B; stream += gridDim.x) {
         const int b = p.b0 + stream;
@@ -190,8 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1) preconv3_mma_kernel(Preconv3Param
         {  // frames 0..3 <- carried state of layer 0, frames 4..24 <- this chunk's features
             const uint4* s0 = reinterpret_cast<const uint4*>(gstate);
             const uint4* s1 = reinterpret_cast<const uint4*>(p.feat + (long long)b * p.feat_sB);
-            for (int i = tid; i < 4 * P3_POS; i += kThreads) cp_async16(x_smem + 16u * i, s0 + i);
-            for (int i = tid; i < T * P3_POS; i += kThreads) cp_async16(x_smem + 4 * P3_ROW_BYTES + 16u * i, s1 + i);
+            for (int i = tid; i < 4 * P3_POS; i += P3_THREADS) cp_async16(x_smem + 16u * i, s0 + i);
+            for (int i = tid; i < T * P3_POS; i += P3_THREADS) cp_async16(x_smem + 4 * P3_ROW_BYTES + 16u * i, s1 + i);
             cp_async_commit();
             cp_async_wait_all();
             __syncthreads();
@@ -199,96 +248,116 @@ __global__ void __launch_bounds__(kThreads, 1) preconv3_mma_kernel(Preconv3Param
 #pragma unroll 1
         for (int l = 0; l < 3; ++l) {
             const int d = 1 << l;
+            uint32_t epoch;  // see ldsm_x4_dep
+            asm volatile("mov.u32 %0, %1;" : "=r"(epoch) : "r"(++epoch_base));
             // causal state of this layer for the next chunk: the last 4 frames of its input (CRN_ELU.py:246)
             {
                 uint4* dst = reinterpret_cast<uint4*>(gstate + (long long)l * 4 * P3_POS * 8);
                 const uint4* src = reinterpret_cast<const uint4*>(sx + T * P3_ROW_BYTES);
-                for (int i = tid; i < 4 * P3_POS; i += kThreads) dst[i] = src[i];
+                for (int i = tid; i < 4 * P3_POS; i += P3_THREADS) dst[i] = src[i];
             }
             const uint2* wf = swf + l * P3_WF_LAYER;
             const float* par = spar + l * P3_NPAR;
             const float cb0 = par[2 * tg], cb1 = par[2 * tg + 1];
             const float bt0 = par[8 + 2 * tg], bt1 = par[8 + 2 * tg + 1];
             const float bg0 = par[16 + 2 * tg], bg1 = par[16 + 2 * tg + 1];
-            const uint2 wgt = wf[P3_KS * 32 + lane], wgg = wf[(P3_KS + 1) * 32 + lane];
+            const uint2 wgt = wf[P3_NFR * 32 + lane], wgg = wf[(P3_NFR + 1) * 32 + lane];
+            uint2 wr[P3_NFR];  // the layer's conv weights stay in registers
+#pragma unroll
+            for (int i = 0; i < P3_NFR; ++i) wr[i] = wf[i * 32 + lane];
+            // byte offset of this lane's tap inside an input frame row, for the three fragments of a frame:
+            // j = 0, 1: taps kf = 2 j + tapsel; j = 2: tap 4 of this frame (tapsel 0) / of the next frame (tapsel 1)
+            const int o0 = (tapsel - 2) * d * 16, o1 = tapsel * d * 16, o2 = 2 * d * 16 + tapsel * P3_ROW_BYTES;
             float psum = 0.f, psq = 0.f;
-            // ---- pass 1: conv + ELU + gate -> Y, statistics.  Two 16-row tiles per iteration (independent mma chains) ----
-            for (int mt0 = 2 * warp; mt0 < P3_MT; mt0 += 2 * kWarps) {
-                float acc[2][4];
-                uint32_t abase[2];
+            // ---- pass 1.  One warp owns a column of 16 bins (warps 13..15 only help with the copies and pass 2) and
+            // streams over the 25 input frames: the fragments of input frame u feed the output frames u - kt (kt = 0..4),
+            // whose accumulators roll through five register slots; output frame u - 4 is complete after frame u: ELU, gate,
+            // statistics, gated values -> Y.  3 ldmatrix and 15 mma per 16-row tile (13 + 15 with one fragment per tap
+            // pair and no reuse).  The first and last five frames are peeled so that the steady state has no conditions:
+            // the compiler interleaves the epilogue of frame u with the mma of frame u + 1 in one basic block.
+            if (warp < 13) {
+                const int ft = warp;
+                // rows 16 ft + g are always real bins (<= 199); rows + 8 run past bin 200 only in the last column
+                const float m1 = (ft < 12 || g == 0) ? 1.f : 0.f;
+                const uint32_t a_col = x_smem + (uint32_t)((P3_BORDER + 16 * ft + rowoff) * 16);
+                unsigned char* y_col = sy + (size_t)((16 * ft + g) * 16 + 4 * tg);
+                float acc[5][4];
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int mt = min(mt0 + q, P3_MT - 1);  // odd tail: the second tile repeats the last one (not stored)
-                    const int t = mt / 13, ft = mt - 13 * t;
-                    abase[q] = x_smem + (uint32_t)((t * P3_POS + P3_BORDER + 16 * ft + rowoff) * 16);
-                    acc[q][0] = acc[q][2] = cb0;
-                    acc[q][1] = acc[q][3] = cb1;
+                for (int i = 0; i < 5; ++i) {
+                    acc[i][0] = acc[i][2] = cb0;
+                    acc[i][1] = acc[i][3] = cb1;
                 }
+                // KIND 0: frames 0..4 (outputs u - kt < 0 do not exist), 1: steady state, 2: frames 20..24 (outputs > 20
+                // do not exist; the last frame has no successor for the second half of f2)
+                auto frames5 = [&](auto kind, int ub) {
+                    constexpr int KIND = decltype(kind)::value;
 #pragma unroll
-                for (int s = 0; s < P3_KS; ++s) {
-                    const int tapA = 2 * s, tapB = 2 * s + 1 < 25 ? 2 * s + 1 : 24;  // tap 25: zero weights, valid address
-                    const int offA = (tapA / 5) * P3_POS + (tapA % 5 - 2) * d;
-                    const int offB = (tapB / 5) * P3_POS + (tapB % 5 - 2) * d;
-                    const int off = (tapsel ? offB : offA) * 16;
-                    const uint2 w = wf[s * 32 + lane];
+                    for (int ui = 0; ui < 5; ++ui) {
+                        const int u = ub + ui;
+                        uint32_t f0[4], f1[4], f2[4];
+                        const uint32_t arow = a_col + (uint32_t)(u * P3_ROW_BYTES);
+                        ldsm_x4_dep(arow + o0, epoch, f0);
+                        ldsm_x4_dep(arow + o1, epoch, f1);
+                        ldsm_x4_dep(arow + ((KIND == 2 && ui == 4) ? 2 * d * 16 : o2), epoch, f2);
 #pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        uint32_t a[4];
-                        ldsm_x4(abase[q] + off, a);
-                        mma16816(acc[q], a, w.x, w.y);
+                        for (int kt = 0; kt < 5; ++kt) {
+                            const bool live = KIND == 1 || (KIND == 0 && ui - kt >= 0) || (KIND == 2 && ui - kt <= 0);
+                            if (live) {
+                                float(&c)[4] = acc[(ui - kt + 5) % 5];
+                                mma16816(c, f0, wr[2 * kt].x, wr[2 * kt].y);
+                                mma16816(c, f1, wr[2 * kt + 1].x, wr[2 * kt + 1].y);
+                                if ((kt & 1) == 0) mma16816(c, f2, wr[10 + kt / 2].x, wr[10 + kt / 2].y);
+                            }
+                        }
+                        if (KIND != 0 || ui == 4) {
+                            const int t = u - 4;
+                            float(&c)[4] = acc[(ui + 1) % 5];
+                            // ELU, then the gated 1x1 pair on the tensor core: the C fragment is the A fragment
+                            uint32_t a2[4];
+                            a2[0] = pack_h2(fast_elu(c[0]), fast_elu(c[1]));
+                            a2[1] = pack_h2(fast_elu(c[2]), fast_elu(c[3]));
+                            a2[2] = a2[3] = 0u;
+                            float gt[4] = {bt0, bt1, bt0, bt1}, gg4[4] = {bg0, bg1, bg0, bg1};
+                            mma16816(gt, a2, wgt.x, wgt.y);
+                            mma16816(gg4, a2, wgg.x, wgg.y);
+                            // columns >= 5 are exactly 0 (zero weights and biases): every lane stores, no channel mask
+                            const float y0 = gt[0] * sigmoid_from_neg_log2(gg4[0]);
+                            const float y1 = gt[1] * sigmoid_from_neg_log2(gg4[1]);
+                            const float y2 = m1 * gt[2] * sigmoid_from_neg_log2(gg4[2]);
+                            const float y3 = m1 * gt[3] * sigmoid_from_neg_log2(gg4[3]);
+                            psum += (y0 + y1) + (y2 + y3);
+                            psq = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, psq))));
+                            unsigned char* yr = y_col + (size_t)t * (P3_YPITCH * 16);
+                            *reinterpret_cast<uint32_t*>(yr) = pack_h2(y0, y1);
+                            *reinterpret_cast<uint32_t*>(yr + 8 * 16) = pack_h2(y2, y3);
+                            c[0] = c[2] = cb0;
+                            c[1] = c[3] = cb1;
+                        }
                     }
-                }
-#pragma unroll
-                for (int q = 0; q < 2; ++q) {
-                    const int mt = mt0 + q;
-                    if (mt >= P3_MT) break;
-                    const int t = mt / 13, ft = mt - 13 * t;
-                    // ELU, then the gated 1x1 pair on the tensor core: the C fragment is the A fragment (k = channel)
-                    uint32_t a2[4];
-                    a2[0] = pack_h2(fast_elu(acc[q][0]), fast_elu(acc[q][1]));
-                    a2[1] = pack_h2(fast_elu(acc[q][2]), fast_elu(acc[q][3]));
-                    a2[2] = a2[3] = 0u;
-                    float gt[4] = {bt0, bt1, bt0, bt1}, gg4[4] = {bg0, bg1, bg0, bg1};
-                    mma16816(gt, a2, wgt.x, wgt.y);
-                    mma16816(gg4, a2, wgg.x, wgg.y);
-                    float y[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) y[i] = gt[i] * fast_sigmoid(gg4[i]);
-                    const int f0 = 16 * ft + g, f1 = f0 + 8;
-                    // columns >= 5 are exactly 0 (zero weights and biases): no channel mask needed in the statistics
-                    if (f0 < NB) {
-                        psum += y[0] + y[1];
-                        psq = fmaf(y[0], y[0], fmaf(y[1], y[1], psq));
-                    }
-                    if (f1 < NB) {
-                        psum += y[2] + y[3];
-                        psq = fmaf(y[2], y[2], fmaf(y[3], y[3], psq));
-                    }
-                    if (tg < 3) {
-                        unsigned char* yr = sy + (size_t)(t * P3_YPITCH) * 16 + 4 * tg;
-                        *reinterpret_cast<uint32_t*>(yr + f0 * 16) = pack_h2(y[0], y[1]);
-                        *reinterpret_cast<uint32_t*>(yr + f1 * 16) = pack_h2(y[2], y[3]);
-                    }
-                }
+                };
+                frames5(std::integral_constant<int, 0>{}, 0);
+#pragma unroll 1
+                for (int ub = 5; ub < 20; ub += 5) frames5(std::integral_constant<int, 1>{}, ub);
+                frames5(std::integral_constant<int, 2>{}, 20);
             }
             __syncthreads();  // frames 0..3 of X are dead from here on
             if (l < 2) {      // carried state of the next layer -> frames 0..3 (overlaps the statistics and pass 2)
                 const uint4* s0 = reinterpret_cast<const uint4*>(gstate + (long long)(l + 1) * 4 * P3_POS * 8);
-                for (int i = tid; i < 4 * P3_POS; i += kThreads) cp_async16(x_smem + 16u * i, s0 + i);
+                for (int i = tid; i < 4 * P3_POS; i += P3_THREADS) cp_async16(x_smem + 16u * i, s0 + i);
                 cp_async_commit();
             }
-            block_gln(psum, psq, 5.0 * NB * T, p.student, s_red, s_co);
+            block_gln<P3_WARPS>(psum, psq, 5.0 * NB * T, p.student, s_red, s_co);
             // ---- pass 2: normalise + residual (CRN_ELU.py:376), in place (next layer's input) or to the output ----------
             {
                 const float mean = s_co[0], inv = s_co[1];
-                const float* w = p.w[l];
-                float na[5], nd[5];
+                float na[5], nd[5];  // y * na + nd = (y - mean) * inv * w + b
 #pragma unroll
                 for (int c = 0; c < 5; ++c) {
-                    na[c] = __ldg(w + PRECONV_W_NW + c);
-                    nd[c] = __ldg(w + PRECONV_W_NB + c);
+                    na[c] = par[24 + c] * inv;
+                    nd[c] = fmaf(-mean, na[c], __ldg((l == 0 ? p.w[0] : (l == 1 ? p.w[1] : p.w[2])) + PRECONV_W_NB + c));
                 }
-                for (int i = tid; i < T * NB; i += kThreads) {
+                __half* ob = p.out + (long long)b * p.oB;
+                for (int i = tid; i < T * NB; i += P3_THREADS) {
                     const int t = i / NB, f = i - t * NB;
                     uint4* xu = reinterpret_cast<uint4*>(sx + ((t + 4) * P3_POS + P3_BORDER + f) * 16);
                     float yv[8], xv[8];
@@ -296,15 +365,14 @@ __global__ void __launch_bounds__(kThreads, 1) preconv3_mma_kernel(Preconv3Param
                     unpack8(*xu, xv);
                     float o[5];
 #pragma unroll
-                    for (int c = 0; c < 5; ++c) o[c] = (yv[c] - mean) * inv * na[c] + nd[c] + xv[c];
+                    for (int c = 0; c < 5; ++c) o[c] = fmaf(yv[c], na[c], nd[c]) + xv[c];
                     uint4 u;
                     u.x = pack_h2(o[0], o[1]);
                     u.y = pack_h2(o[2], o[3]);
                     u.z = pack_h2(o[4], 0.f);
                     u.w = 0u;
                     if (l < 2) *xu = u;
-                    else
-                        *reinterpret_cast<uint4*>(p.out + (long long)b * p.oB + (long long)t * p.oT + (long long)f * p.oF) = u;
+                    else *reinterpret_cast<uint4*>(ob + (long long)t * p.oT + (long long)f * p.oF) = u;
                 }
             }
             cp_async_wait_all();
@@ -330,6 +398,88 @@ struct EncCfg {
     static constexpr int SLACK = 64;  // units behind every plane (tile overrun of the last frame)
 };
 
+// NQ consecutive 16-row tiles starting at mt0 (all < MT): conv, ELU, gate, statistics, gated values -> Y
+template <int CIN, int COUT, int NQ>
+__device__ __forceinline__ void enc_tiles(int mt0, const EncMmaParams& p, uint32_t x_smem, int rowoff, int sel, int dtJ,
+                                          int plane, int Jp, const uint2* swf, const uint2* swf2, const float* spar,
+                                          unsigned char* sy, int lane, float& psum, float& psq) {
+    using S = EncCfg<CIN, COUT>;
+    constexpr int NH = S::NH, KS = S::KS, NT = S::NT, KS2 = S::KS2, NT2 = S::NT2;
+    const int g = lane >> 2, tg = lane & 3;
+    float acc[NQ][NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const float2 cb = *reinterpret_cast<const float2*>(spar + 8 * nt + 2 * tg);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            acc[q][nt][0] = acc[q][nt][2] = cb.x;
+            acc[q][nt][1] = acc[q][nt][3] = cb.y;
+        }
+    }
+    const uint32_t abase = x_smem + (uint32_t)((mt0 * 16 + rowoff) * 16);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+        int unit;
+        if (CIN == 8) {
+            const int tapA = 2 * ks, tapB = 2 * ks + 1 < 15 ? 2 * ks + 1 : 14;  // tap 15: zero weights, valid address
+            const int uA = (tapA / 5) * dtJ + ((tapA % 5) >> 1) + ((tapA % 5) & 1) * plane;
+            const int uB = (tapB / 5) * dtJ + ((tapB % 5) >> 1) + ((tapB % 5) & 1) * plane;
+            unit = sel ? uB : uA;
+        } else {
+            const int kt = ks / 5, kf = ks % 5;
+            unit = kt * dtJ + (kf >> 1) + ((kf & 1) * NH + sel) * plane;
+        }
+        uint32_t a[NQ][4];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) ldsm_x4(abase + (uint32_t)((unit + 16 * q) * 16), a[q]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const uint2 w = swf[(ks * NT + nt) * 32 + lane];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) mma16816(acc[q][nt], a[q], w.x, w.y);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        uint32_t a2[KS2][4];
+#pragma unroll
+        for (int s = 0; s < KS2; ++s) {
+            a2[s][0] = pack_h2(fast_elu(acc[q][2 * s][0]), fast_elu(acc[q][2 * s][1]));
+            a2[s][1] = pack_h2(fast_elu(acc[q][2 * s][2]), fast_elu(acc[q][2 * s][3]));
+            if (2 * s + 1 < NT) {
+                a2[s][2] = pack_h2(fast_elu(acc[q][2 * s + 1][0]), fast_elu(acc[q][2 * s + 1][1]));
+                a2[s][3] = pack_h2(fast_elu(acc[q][2 * s + 1][2]), fast_elu(acc[q][2 * s + 1][3]));
+            } else {
+                a2[s][2] = a2[s][3] = 0u;
+            }
+        }
+        const int r0 = (mt0 + q) * 16 + g, r1 = r0 + 8;
+        const int t0 = div_magic(r0, p.magic_Jp), f0 = r0 - t0 * Jp, t1 = div_magic(r1, p.magic_Jp), f1 = r1 - t1 * Jp;
+        const bool v0 = t0 < T && f0 < p.Fo, v1 = t1 < T && f1 < p.Fo;
+        const float m0 = v0 ? 1.f : 0.f, m1 = v1 ? 1.f : 0.f;
+        __half* y0 = reinterpret_cast<__half*>(sy) + (size_t)(t0 * p.Fo + f0) * COUT + 2 * tg;
+        __half* y1 = reinterpret_cast<__half*>(sy) + (size_t)(t1 * p.Fo + f1) * COUT + 2 * tg;
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {  // trans tile j and gated tile NT + j land in the same lanes and slots
+            const float2 bt = *reinterpret_cast<const float2*>(spar + COUT + 8 * j + 2 * tg);
+            const float2 bg = *reinterpret_cast<const float2*>(spar + 2 * COUT + 8 * j + 2 * tg);
+            float gt[4] = {bt.x, bt.y, bt.x, bt.y}, gg4[4] = {bg.x, bg.y, bg.x, bg.y};
+#pragma unroll
+            for (int s = 0; s < KS2; ++s) {
+                const uint2 wt = swf2[(s * NT2 + j) * 32 + lane], wg = swf2[(s * NT2 + NT + j) * 32 + lane];
+                mma16816(gt, a2[s], wt.x, wt.y);
+                mma16816(gg4, a2[s], wg.x, wg.y);
+            }
+            const float ya = m0 * gt[0] * sigmoid_from_neg_log2(gg4[0]), yb = m0 * gt[1] * sigmoid_from_neg_log2(gg4[1]);
+            const float yc = m1 * gt[2] * sigmoid_from_neg_log2(gg4[2]), yd = m1 * gt[3] * sigmoid_from_neg_log2(gg4[3]);
+            psum += (ya + yb) + (yc + yd);
+            psq = fmaf(ya, ya, fmaf(yb, yb, fmaf(yc, yc, fmaf(yd, yd, psq))));
+            if (v0) *reinterpret_cast<uint32_t*>(y0 + 8 * j) = pack_h2(ya, yb);
+            if (v1) *reinterpret_cast<uint32_t*>(y1 + 8 * j) = pack_h2(yc, yd);
+        }
+    }
+}
+
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kThreads, 1) enc_mma_kernel(EncMmaParams p) {
     using S = EncCfg<CIN, COUT>;
@@ -341,11 +491,11 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mma_kernel(EncMmaParams p) {
     unsigned char* sy = smem + p.off_y;
     uint2* swf = reinterpret_cast<uint2*>(smem + p.off_wf);
     uint2* swf2 = swf + KS * NT * 32;
-    float* spar = reinterpret_cast<float*>(swf2 + KS2 * NT2 * 32);  // cb[COUT] | b2t[COUT] | b2g[COUT]
+    float* spar = reinterpret_cast<float*>(swf2 + KS2 * NT2 * 32);  // cb[COUT] | b2t[COUT] | -log2(e) b2g[COUT]
     double* s_red = reinterpret_cast<double*>(spar + 3 * COUT);
     float* s_co = reinterpret_cast<float*>(s_red + 2 * kWarps);
     const uint32_t x_smem = smem_u32(sx);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tg = lane & 3;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     // ---- one-time set-up -----------------------------------------------------------------------------------------
     for (int i = tid; i < 2 * NH * plane; i += kThreads) reinterpret_cast<uint4*>(sx)[i] = make_uint4(0, 0, 0, 0);
@@ -361,22 +511,24 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mma_kernel(EncMmaParams p) {
         }
         swf[i] = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
     }
-    for (int i = tid; i < KS2 * NT2 * 32; i += kThreads) {  // gate B fragments: n-tiles [0,NT) trans, [NT,2NT) gated
+    // gate B fragments: n-tiles [0,NT) conv_trans, [NT,2NT) conv_gated scaled by -log2(e) (sigmoid = 1 / (1 + 2^z))
+    for (int i = tid; i < KS2 * NT2 * 32; i += kThreads) {
         const int ln = i & 31, nt2 = (i >> 5) % NT2, ks2 = (i >> 5) / NT2;
         const int kind = nt2 / NT, ch = (nt2 % NT) * 8 + (ln >> 2), k0 = ks2 * 16 + 2 * (ln & 3);
         const float* wr = p.w2 + (long long)(2 * ch + kind) * p.w2_pitch;
+        const float sc = kind ? -kLog2e : 1.f;
         float v[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int k = k0 + (e & 1) + 8 * (e >> 1);
-            v[e] = k < COUT ? __ldg(wr + k) : 0.f;
+            v[e] = k < COUT ? sc * __ldg(wr + k) : 0.f;
         }
         swf2[i] = make_uint2(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]));
     }
     for (int i = tid; i < COUT; i += kThreads) {
         spar[i] = __ldg(p.bias + i);
         spar[COUT + i] = __ldg(p.bias2 + 2 * i);
-        spar[2 * COUT + i] = __ldg(p.bias2 + 2 * i + 1);
+        spar[2 * COUT + i] = -kLog2e * __ldg(p.bias2 + 2 * i + 1);
     }
 
     auto issue_load = [&](int b) {  // global [Tp][Fp][NH] units -> planes
@@ -385,7 +537,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mma_kernel(EncMmaParams p) {
         for (int u = tid; u < total; u += kThreads) {
             const int h = NH == 1 ? 0 : (u & (NH - 1));
             const int pl = NH == 1 ? u : u / NH;
-            const int tt = pl / p.Fp, pos = pl - tt * p.Fp;
+            const int tt = div_magic(pl, p.magic_Fp), pos = pl - tt * p.Fp;
             const int unit = ((pos & 1) * NH + h) * plane + tt * Jp + (pos >> 1);
             cp_async16(x_smem + 16u * unit, src + u);
         }
@@ -398,8 +550,8 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mma_kernel(EncMmaParams p) {
     const int rowoff = (lane & 7) + 8 * (mi & 1);
     const int sel = mi >> 1;
     const int dtJ = p.dt * Jp;
-    const int Mtot = T * Jp;
-    const int MT = (Mtot + 15) >> 4;
+    const int MT = (T * Jp + 15) >> 4;
+    const int mt_lo = (warp * MT) / kWarps, mt_hi = ((warp + 1) * MT) / kWarps;  // the warp's contiguous tile range
     const int Fo = p.Fo;
     const double count = (double)COUT * Fo * T;
     constexpr int UPR = COUT / 8;  // 16-byte units per output row
@@ -411,88 +563,12 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mma_kernel(EncMmaParams p) {
         cp_async_wait_all();
         __syncthreads();
         float psum = 0.f, psq = 0.f;
-        // ---- pass 1: conv + ELU + gate -> Y (fp16, [T][Fo][COUT]) + statistics; two 16-row tiles per iteration --------
-        for (int mt0 = 2 * warp; mt0 < MT; mt0 += 2 * kWarps) {
-            float acc[2][NT][4];
-#pragma unroll
-            for (int q = 0; q < 2; ++q)
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    acc[q][nt][0] = acc[q][nt][2] = spar[8 * nt + 2 * tg];
-                    acc[q][nt][1] = acc[q][nt][3] = spar[8 * nt + 2 * tg + 1];
-                }
-            const uint32_t abase = x_smem + (uint32_t)((mt0 * 16 + rowoff) * 16);
-#pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-                int unit;
-                if (CIN == 8) {
-                    const int tapA = 2 * ks, tapB = 2 * ks + 1 < 15 ? 2 * ks + 1 : 14;  // tap 15: zero weights
-                    const int uA = (tapA / 5) * dtJ + ((tapA % 5) >> 1) + ((tapA % 5) & 1) * plane;
-                    const int uB = (tapB / 5) * dtJ + ((tapB % 5) >> 1) + ((tapB % 5) & 1) * plane;
-                    unit = sel ? uB : uA;
-                } else {
-                    const int kt = ks / 5, kf = ks % 5;
-                    unit = kt * dtJ + (kf >> 1) + ((kf & 1) * NH + sel) * plane;
-                }
-                uint32_t a[2][4];
-                ldsm_x4(abase + (uint32_t)(unit * 16), a[0]);
-                ldsm_x4(abase + (uint32_t)((unit + 16) * 16), a[1]);
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) {
-                    const uint2 w = swf[(ks * NT + nt) * 32 + lane];
-                    mma16816(acc[0][nt], a[0], w.x, w.y);
-                    mma16816(acc[1][nt], a[1], w.x, w.y);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                if (mt0 + q >= MT) break;
-                uint32_t a2[KS2][4];
-#pragma unroll
-                for (int s = 0; s < KS2; ++s) {
-                    a2[s][0] = pack_h2(fast_elu(acc[q][2 * s][0]), fast_elu(acc[q][2 * s][1]));
-                    a2[s][1] = pack_h2(fast_elu(acc[q][2 * s][2]), fast_elu(acc[q][2 * s][3]));
-                    if (2 * s + 1 < NT) {
-                        a2[s][2] = pack_h2(fast_elu(acc[q][2 * s + 1][0]), fast_elu(acc[q][2 * s + 1][1]));
-                        a2[s][3] = pack_h2(fast_elu(acc[q][2 * s + 1][2]), fast_elu(acc[q][2 * s + 1][3]));
-                    } else {
-                        a2[s][2] = a2[s][3] = 0u;
-                    }
-                }
-                const int r0 = (mt0 + q) * 16 + g, r1 = r0 + 8;
-                const int t0 = r0 / Jp, f0 = r0 - t0 * Jp, t1 = r1 / Jp, f1 = r1 - t1 * Jp;
-                const bool v0 = t0 < T && f0 < Fo, v1 = t1 < T && f1 < Fo;
-                __half* y0 = reinterpret_cast<__half*>(sy) + (size_t)(t0 * Fo + f0) * COUT + 2 * tg;
-                __half* y1 = reinterpret_cast<__half*>(sy) + (size_t)(t1 * Fo + f1) * COUT + 2 * tg;
-#pragma unroll
-                for (int j = 0; j < NT; ++j) {  // trans tile j and gated tile NT + j land in the same lanes and slots
-                    float gt[4], gg4[4];
-                    gt[0] = gt[2] = spar[COUT + 8 * j + 2 * tg];
-                    gt[1] = gt[3] = spar[COUT + 8 * j + 2 * tg + 1];
-                    gg4[0] = gg4[2] = spar[2 * COUT + 8 * j + 2 * tg];
-                    gg4[1] = gg4[3] = spar[2 * COUT + 8 * j + 2 * tg + 1];
-#pragma unroll
-                    for (int s = 0; s < KS2; ++s) {
-                        const uint2 wt = swf2[(s * NT2 + j) * 32 + lane], wg = swf2[(s * NT2 + NT + j) * 32 + lane];
-                        mma16816(gt, a2[s], wt.x, wt.y);
-                        mma16816(gg4, a2[s], wg.x, wg.y);
-                    }
-                    float y[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) y[i] = gt[i] * fast_sigmoid(gg4[i]);
-                    if (v0) {
-                        psum += y[0] + y[1];
-                        psq = fmaf(y[0], y[0], fmaf(y[1], y[1], psq));
-                        *reinterpret_cast<uint32_t*>(y0 + 8 * j) = pack_h2(y[0], y[1]);
-                    }
-                    if (v1) {
-                        psum += y[2] + y[3];
-                        psq = fmaf(y[2], y[2], fmaf(y[3], y[3], psq));
-                        *reinterpret_cast<uint32_t*>(y1 + 8 * j) = pack_h2(y[2], y[3]);
-                    }
-                }
-            }
-        }
+        // ---- pass 1: conv + ELU + gate -> Y (fp16, [T][Fo][COUT]) + statistics; two 16-row tiles in flight ------------
+        int mt = mt_lo;
+        for (; mt + 2 <= mt_hi; mt += 2)
+            enc_tiles<CIN, COUT, 2>(mt, p, x_smem, rowoff, sel, dtJ, plane, Jp, swf, swf2, spar, sy, lane, psum, psq);
+        if (mt < mt_hi)
+            enc_tiles<CIN, COUT, 1>(mt, p, x_smem, rowoff, sel, dtJ, plane, Jp, swf, swf2, spar, sy, lane, psum, psq);
         __syncthreads();  // X is dead: fetch the next stream's input while this one is normalised and written out
         if (stream + (int)gridDim.x < p.B) issue_load(b + gridDim.x);
         block_gln(psum, psq, count, p.student, s_red, s_co);
@@ -510,7 +586,7 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mma_kernel(EncMmaParams p) {
             const int total = T * Fo * UPR;
             for (int u = tid; u < total; u += kThreads) {
                 const int row = u / UPR;
-                const int t = row / Fo, f = row - t * Fo;
+                const int t = div_magic(row, p.magic_Fo), f = row - t * Fo;
                 float v[8];
                 unpack8(reinterpret_cast<const uint4*>(sy)[u], v);
 #pragma unroll
@@ -534,6 +610,11 @@ int launch_enc(EncMmaParams p, cudaStream_t st) {
     p.off_wf = (int)off;
     off += (size_t)(S::KS * S::NT + S::KS2 * S::NT2) * 32 * 8 + 3 * COUT * 4 + 2 * kWarps * 8 + 16;
     SE_REQUIRE(off <= 227 * 1024, "enc_mma: the stream does not fit in shared memory");
+    auto magic = [](int d) { return (uint32_t)(((1ull << 32) + d - 1) / d); };  // exact for dividends < 65536
+    SE_REQUIRE(p.Tp * p.Fp < 65536 && T * Jp + 64 < 65536, "enc_mma: index range of the magic division");
+    p.magic_Jp = magic(Jp);
+    p.magic_Fo = magic(p.Fo);
+    p.magic_Fp = magic(p.Fp);
     SE_DYN_SMEM((enc_mma_kernel<CIN, COUT>), off);
     int num_sms = 0;
     if (num_sms_current_device(&num_sms)) return 1;
@@ -567,7 +648,7 @@ int launch_preconv3(const Preconv3Params& p, cudaStream_t st) {
     SE_DYN_SMEM(preconv3_mma_kernel, P3_SMEM);
     int num_sms = 0;
     if (num_sms_current_device(&num_sms)) return 1;
-    preconv3_mma_kernel<<<p.B < num_sms ? p.B : num_sms, kThreads, P3_SMEM, st>>>(p);
+    preconv3_mma_kernel<<<p.B < num_sms ? p.B : num_sms, P3_THREADS, P3_SMEM, st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }

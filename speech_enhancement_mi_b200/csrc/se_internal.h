@@ -211,6 +211,7 @@ struct EncMmaParams {
     int student;
     int b0, B;
     int off_y, off_wf;    // shared-memory offsets (filled by the launcher)
+    uint32_t magic_Jp, magic_Fo, magic_Fp;  // ceil(2^32 / d) of the three run-time divisors (filled by the launcher)
 };
 bool enc_mma_supported(int Cin, int Cout, int Tp, int Fp, int Fo);
 int launch_enc_mma(const EncMmaParams& p, int Cin, int Cout, cudaStream_t st);

@@ -65,5 +65,9 @@ for t in sorted(table, key=lambda t: -t["duration_us"])[:12]:
     print(f"  {t['label']:34s} {t['duration_us']:8.1f} us  {100 * t['duration_us'] / tot:5.1f}%  dram "
           f"{(t['dram_read_bytes'] or 0) / 1e6:7.1f}+{(t['dram_write_bytes'] or 0) / 1e6:6.1f} MB  tensor {t['tensor_pipe_pct']}")
 tj = os.path.join(os.path.dirname(os.path.abspath(out)), "ncu_traffic.json")
-json.dump({"source": os.path.basename(out) + ".csv", "streams": meta["streams"], "precision": meta["precision"],
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from speech_enhancement_mi_b200 import build as native_build  # noqa: E402
+# the capture is only valid for the library it was taken on: bench.py reports `traffic` when this hash matches its own
+json.dump({"source": os.path.basename(out) + ".csv", "capture": os.path.basename(out), "source_hash": native_build.source_hash(),
+           "streams": meta["streams"], "precision": meta["precision"],
            "dram_bytes_per_launch": {k: traffic[k] / count[k] for k in traffic}}, open(tj, "w"), indent=1)
