@@ -213,6 +213,11 @@ int se_crn_time_kernel(se_ctx* ctx, int index, int B, int iters, float* ms);
  * dims = {T, F, C}.  Names: "pre_in<i>", "enc_in<i>", "dec_in<j>", "xg", "fcraw", "hseq<l>", "ylast", "noisy".
  * Synchronises the device.  Used by tests/ to localise a parity failure to one layer (CRN_ELU.py:375-399). */
 int se_debug_read(se_ctx* ctx, const char* name, int b, float* host_dst, int64_t max_floats, int* dims);
+/* Run ONLY the fused mask stage of the chunk step (last GlobalLayerNorm made an identity, decompress_cIRM of
+ * utility.py:439-442, complex multiply with the mic-0 spectrum of CRN_ELU.py:401-405) on caller data, all DEVICE memory:
+ * mask [B, T, F, 2] (the values that enter decompress_cIRM), noisy [B, T, F, 2] -> spec_out [B, F, T, 2] (the layout
+ * forward() returns).  Lets tests drive the clamp |m| >= 9.9, which random-init weights never reach.  Synchronises. */
+int se_debug_mask_spectrum(se_ctx* ctx, const float* mask, const float* noisy, float* spec_out, int B);
 
 #ifdef __cplusplus
 }

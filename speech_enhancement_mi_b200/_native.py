@@ -97,6 +97,7 @@ SIGNATURES = {
     "se_clip_adam_step": (_I, [_P, _P, _P, _P, _L, C.c_float, C.c_float, C.c_float, C.c_float, _I, C.c_float,
                                C.c_float, _P, _P]),
     "se_debug_read": (_I, [_P, C.c_char_p, _I, _P, _L, C.POINTER(C.c_int)]),
+    "se_debug_mask_spectrum": (_I, [_P, _P, _P, _P, _I]),
 }
 
 _lib = None

@@ -105,6 +105,13 @@ struct Op {
     EncMmaParams em;
     int em_cin = 0, em_cout = 0;
     int small_c = 0;  // channel count of the two small-layer kernels
+    // TMA operand delivery (gemm_tc.cu): geometry of the tensor the A operand is gathered from, [B][Tp][Fp][C] at `tma_base`
+    // with the row grid starting at (frame t_org, bin f_org) and advancing fstep bins per output bin.  C = 0: not described.
+    const void* tma_base = nullptr;
+    int tma_C = 0, tma_Fp = 0, tma_Tp = 0, tma_fstep = 1, tma_t_org = 0, tma_f_org = 0;
+    long long tma_sT = 0, tma_sB = 0;
+    bool tma_ok = false;
+    GemmTma tma{};
     // GRU pointwise
     const float* gi = nullptr;
     long long giB = 0;
@@ -230,6 +237,7 @@ struct se_ctx {
     // mma.sync with the stream resident in shared memory (front_mma.cu).  SE_B200_FRONT_MMA=0 / SE_B200_ENC_MMA=0 keep the
     // round-1 kernels (preconv_tc.cu per layer; back-to-back tcgen05 GEMM + separate GlobalLayerNorm pass).
     bool front_mma = true, enc_mma = true;
+    bool use_tma = true;  // SE_B200_TMA=0: every tcgen05 GEMM keeps the cp.async gather producers
     __half* feat_h = nullptr;     // features of the chunk [maxB][21][224][8] halves (borders stay zero)
     __half* pre_state = nullptr;  // carried frames of the three pre-convolutions [maxB][3][4][224][8] halves
     size_t pre3_w_off[3] = {0, 0, 0};
@@ -431,6 +439,20 @@ struct Builder {
         fix.push_back({pw.w_off, pw.b_off, k_off, NONE, NONE, NONE, NONE, w2_off, b2_off});
     }
     bool tc_stage(int stage) const { return c->tf32 && ((c->tc_mask >> stage) & 1u); }
+    // describes, for the op pushed last, the tensor its A operand is gathered from (see Op::tma_*)
+    void tma_src(const void* base, int C, int Fp, int Tp, long long sT, long long sB, int fstep = 1, int t_org = 0,
+                 int f_org = 0) {
+        Op& op = c->ops.back();
+        op.tma_base = base;
+        op.tma_C = C;
+        op.tma_Fp = Fp;
+        op.tma_Tp = Tp;
+        op.tma_sT = sT;
+        op.tma_sB = sB;
+        op.tma_fstep = fstep;
+        op.tma_t_org = t_org;
+        op.tma_f_org = f_org;
+    }
     // inference: the per-layer temporaries share four buffers; training: every layer keeps its own (saved for backward)
     float* tmp_buf(float* shared, size_t floats_per_stream) {
         if (!c->train) return shared;
@@ -609,6 +631,7 @@ struct Builder {
             push_gemm(stage, g, rows, pw, k_off, w2_off, b2_off);
             rec.op_conv = (int)c->ops.size() - 1;
             c->ops.back().state_entry = state_entry;
+            tma_src(in.base, in.C, in.Fp, in.Tp, in.sT, in.sB, strideF);
         }
         // (2) gated 1x1 pair + statistics -> tmp_y [B][T][Fo][Cp_out]
         if (!fuse_gate) {
@@ -648,6 +671,7 @@ struct Builder {
             meta(name + ".gate1x1", 4.0 * rows * Cout_real * Cout_real, 8.0 * rows * Cout_real);
             push_gemm(stage, g, rows, pw, k_off);
             rec.op_gate = (int)c->ops.size() - 1;
+            tma_src(tmp_e, Cp_out, Fo, T, (long long)Fo * Cp_out, (long long)rows * Cp_out);
         }
         // (3) GlobalLayerNorm (+ residual) -> destination
         {
@@ -757,6 +781,7 @@ struct Builder {
                  4.0 * Cin * T * Fin + 4.0 * T * Fy * Cout_real);
             push_gemm(ST_DECODER, g, T * Fo, pw, k_off);
             rec.op_deconv = (int)c->ops.size() - 1;
+            tma_src(in.base, in.C, in.Fp, in.Tp, in.sT, in.sB);
             if (c->half && !c->train && !skip && Cout_real == 2 && KT == 3 && deconv_last_supported(Cin) &&
                 c->small_layers) {
                 Op& op = c->ops.back();  // same packed weights and report entry, served by the direct kernel
@@ -825,6 +850,7 @@ struct Builder {
             meta(name + ".skip1x1", 4.0 * rows * Cout_real * Cout_real, 12.0 * rows * Cout_real);
             push_gemm(ST_DECODER, g, rows, pw, k_off);
             rec.op_skip = (int)c->ops.size() - 1;
+            tma_src(skip->base, skip->C, skip->Fp, skip->Tp, skip->sT, skip->sB, 1, skip->padT0, skip->padF0);
             if (c->half && !c->train && skip->C == Cout_real && skip_small_supported(Cout_real) && c->small_layers) {
                 Op& op = c->ops.back();
                 op.kind = OP_SKIP_SMALL;
@@ -904,6 +930,8 @@ int build_ctx(se_ctx* c) {
     if (const char* e = getenv("SE_B200_B2B")) c->b2b_gate = atoi(e) != 0;
     if (const char* e = getenv("SE_B200_PRECONV_TC")) c->preconv_tc = atoi(e) != 0;
     c->preconv_tc = c->preconv_tc && c->half && !c->train;
+    if (const char* e = getenv("SE_B200_TMA")) c->use_tma = atoi(e) != 0;
+    c->use_tma = c->use_tma && c->half && !c->train;
     if (const char* e = getenv("SE_B200_FRONT_MMA")) c->front_mma = atoi(e) != 0;
     if (const char* e = getenv("SE_B200_ENC_MMA")) c->enc_mma = atoi(e) != 0;
     c->front_mma = c->front_mma && c->preconv_tc;  // replaces the per-layer tensor-core kernels
@@ -1253,6 +1281,8 @@ int build_ctx(se_ctx* c) {
             b.meta("gru.l" + s + ".input_proj", 2.0 * T * 3 * H * Kin, 4.0 * T * (Kin + 3 * H));
             b.push_gemm(ST_GRU, gp, T, pw, k_off);
             c->gru_rec.op_in[l] = (int)c->ops.size() - 1;
+            if (l == 0) b.tma_src(c->xg, feat, 1, T, feat, (long long)T * feat);
+            else b.tma_src(c->hseq[0], H, 1, T + 1, H, (long long)(T + 1) * H, 1, 1, 0);
         }
         const int k_off = b.koff_dense(H);
         PackedW pw = reserve_packed(c, 3 * H, H);
@@ -1388,6 +1418,7 @@ int build_ctx(se_ctx* c) {
         b.meta("gru.fc+elu", 2.0 * T * feat * H, 4.0 * T * (H + feat));
         b.push_gemm(ST_GRU, gp, T, pw, k_off);
         c->gru_rec.op_fc = (int)c->ops.size() - 1;
+        b.tma_src(c->hseq[1], H, 1, T + 1, H, (long long)(T + 1) * H, 1, 1, 0);
 
         const Act& nx = c->dec_in[0];
         NormApplyParams n{};
@@ -1489,6 +1520,37 @@ int build_ctx(se_ctx* c) {
             if (f.w2_off != NONE) {
                 op.g.W2 = c->warena + f.w2_off;
                 op.g.bias2 = c->warena + f.b2_off;
+            }
+            // TMA delivery where every k-block of the gather is 64 contiguous channels of one (frame, bin) tap
+            if (op.kind == OP_GEMM && c->use_tma && op.tma_C > 0 && op.tma_C % 64 == 0 && op.g.a_half) {
+                GemmParams probe = op.g;
+                probe.M = op.rows_per_stream;
+                const int nkb = op.g.K / 64;
+                std::vector<int> kc(4 * nkb, 0);
+                bool ok = gemm_tma_supported(probe) && op.g.Fo * op.g.Tn == op.rows_per_stream;
+                for (int kb = 0; kb < nkb && ok; ++kb) {
+                    const int e = c->khost[f.k_off + 8 * kb];
+                    for (int j = 1; j < 8; ++j) ok = ok && c->khost[f.k_off + 8 * kb + j] == e + 8 * j;
+                    kc[4 * kb + 2] = (int)(e / op.tma_sT);
+                    const int rem = (int)(e % op.tma_sT);
+                    kc[4 * kb + 1] = rem / op.tma_C;
+                    kc[4 * kb] = rem % op.tma_C;
+                    ok = ok && kc[4 * kb] % 64 == 0;
+                }
+                // weights beyond the real K are zero, but their k-blocks must still address valid channels: the padding
+                // units of the koff table point at offset 0 (frame 0, bin 0, channel 0), which the loop above maps there
+                if (ok) {
+                    int* kdev = nullptr;
+                    if (dev_alloc(c, &kdev, kc.size())) return 1;
+                    SE_CUDA_OK(cudaMemcpy(kdev, kc.data(), kc.size() * sizeof(int), cudaMemcpyHostToDevice));
+                    if (make_gemm_tma(&op.tma, op.tma_base, op.tma_C, op.tma_Fp, op.tma_Tp, op.tma_sT, op.tma_sB, c->maxB,
+                                      op.g.Fo, op.tma_fstep, op.g.Tn, op.g.W, op.g.K, op.g.Npad, gemm_tf32_tile_n(op.g.N)))
+                        return 1;
+                    op.tma.t_org = op.tma_t_org;
+                    op.tma.f_org = op.tma_f_org;
+                    op.tma.kcoord = reinterpret_cast<const int4*>(kdev);
+                    op.tma_ok = true;
+                }
             }
         } else if (op.kind == OP_PRECONV3) {
             for (int l = 0; l < 3; ++l) op.p3.w[l] = c->warena + c->pre3_w_off[l];
@@ -1605,6 +1667,7 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
                 return launch_gemm_fp32(g, st);
             }
             if (op.chunk_serial) return launch_gemm_fp32(g, st);
+            if (op.tma_ok) return launch_gemm_tma(g, op.tma, st);
             return run_gemm(c, g, op.stage, op.label, st);
         }
         case OP_NORM: {
@@ -2505,6 +2568,44 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
     return 0;
 }
 
+
+int se_debug_mask_spectrum(se_ctx* c, const float* mask, const float* noisy, float* spec_out, int B) {
+    SE_REQUIRE(c != nullptr && mask != nullptr && noisy != nullptr && spec_out != nullptr && B > 0,
+               "se_debug_mask_spectrum: bad arguments");
+    SE_CUDA_OK(cudaSetDevice(c->device));
+    // identity GlobalLayerNorm in front of the mask: sum = 0, sum of squares = count  ->  mean 0, variance 1 (the
+    // denominator sqrt(1 + 1e-8) + 1e-8 differs from 1 by 1.5e-8); affine weight 1, bias 0
+    const double count = 2.0 * NBIN * T;
+    std::vector<double> st(2 * (size_t)B);
+    for (int b = 0; b < B; ++b) {
+        st[2 * b] = 0.0;
+        st[2 * b + 1] = count;
+    }
+    const float wb[4] = {1.f, 1.f, 0.f, 0.f};
+    double* d_st = nullptr;
+    float* d_wb = nullptr;
+    SE_CUDA_OK(cudaMalloc(&d_st, st.size() * sizeof(double)));
+    SE_CUDA_OK(cudaMalloc(&d_wb, sizeof(wb)));
+    SE_CUDA_OK(cudaMemcpy(d_st, st.data(), st.size() * sizeof(double), cudaMemcpyHostToDevice));
+    SE_CUDA_OK(cudaMemcpy(d_wb, wb, sizeof(wb), cudaMemcpyHostToDevice));
+    MaskIstftParams mp{};
+    mp.B = B;
+    mp.student = c->student;
+    mp.y = mask;
+    mp.stats = d_st;
+    mp.count = count;
+    mp.w = d_wb;
+    mp.b = d_wb + 2;
+    mp.noisy = noisy;
+    mp.spec_ref = spec_out;
+    const int rc = launch_mask_istft(mp, nullptr);
+    const cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(d_st);
+    cudaFree(d_wb);
+    if (rc) return rc;
+    SE_CUDA_OK(e);
+    return 0;
+}
 
 // ---- training ---------------------------------------------------------------------------------------------------
 int64_t se_crn_num_theta(const se_ctx* c) { return c ? c->n_theta : -1; }

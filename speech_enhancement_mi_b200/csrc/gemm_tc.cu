@@ -18,6 +18,7 @@
 //                      epilogue function, parks the chunk in a warp-private staging buffer and the warp writes it out
 //                      with coalesced 16-byte stores.
 // Every mbarrier wait is bounded (trap after ~2 s) so that a protocol bug cannot hang the GPU.
+#include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
 
@@ -78,6 +79,23 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32
 }
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA tile loads (cp.async.bulk.tensor, SASS: UTMALDG): box of the tensor map at the given coordinates -> shared memory,
+// completion counted in bytes on the mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -284,8 +302,9 @@ __device__ __forceinline__ void small_gate(const float* s_w2, const float* e, in
     }
 }
 
-template <int BN, typename AT, bool B2B = (BN == 16)>
-__global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1) gemm_tc_kernel(const GemmParams p) {
+template <int BN, typename AT, bool B2B = (BN == 16), bool TMA = false>
+__global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
+    gemm_tc_kernel(const GemmParams p, const __grid_constant__ GemmTma tm) {
     constexpr int BKE = BKB / (int)sizeof(AT);  // elements per k-block
     constexpr int UE = 16 / (int)sizeof(AT);    // elements per 16-byte gather unit
     using S = Cfg<BN, B2B>;
@@ -311,10 +330,16 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1) gemm_tc_kernel(const
     const int lane = tid & 31;
     const int nkb = p.K / BKE;  // K and Npad are padded by the host (zero weights): no bounds checks on either operand
     const int ntn = (p.epi == EPI_GRU ? p.N : p.Npad) / BN;
-    const int ntiles = ((p.M + BM - 1) / BM) * ntn;
     const int rowsPerStream = p.Tn * p.Fo;
+    const int nstreams = p.M / rowsPerStream;
+    // TMA: a tile is a rectangle of tm.bb streams x tm.bt frames x Fo bins (tm.rows of the 128 rows are real)
+    const int ntiles = (TMA ? ((nstreams + tm.bb - 1) / tm.bb) * tm.tgroups * tm.fsegs : (p.M + BM - 1) / BM) * ntn;
 
-    for (int i = tid; i < p.K / UE; i += S::THREADS) s_koff[i] = __ldg(p.koff + i);
+    if (TMA) {  // per k-block box origin (channel, bin, frame, -)
+        for (int i = tid; i < 4 * nkb; i += S::THREADS) s_koff[i] = __ldg(reinterpret_cast<const int*>(tm.kcoord) + i);
+    } else {
+        for (int i = tid; i < p.K / UE; i += S::THREADS) s_koff[i] = __ldg(p.koff + i);
+    }
     const AT* const Abase = reinterpret_cast<const AT*>(p.A);
     const AT* const Wbase = reinterpret_cast<const AT*>(p.W);
     const bool out_half = p.out_half != 0;
@@ -342,7 +367,7 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1) gemm_tc_kernel(const
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), kProducerThreads);
+            mbar_init(full_bar(s), TMA ? 1 : kProducerThreads);
             mbar_init(empty_bar(s), 1);
         }
         for (int g = 0; g < NACC; ++g) {
@@ -363,7 +388,32 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1) gemm_tc_kernel(const
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
 
-    if (warp < 4) {
+    if (TMA && warp < 4) {
+        // ============================ producer (TMA): one elected thread ============================
+        if (tid == 0) {
+            uint32_t ps = 0, pphase = 0;
+            const uint32_t tx = (uint32_t)tm.a_bytes + (uint32_t)S::B_STAGE_BYTES;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int tile_m = tile / ntn, n0 = (tile % ntn) * BN;
+                const int fsg = tile_m % tm.fsegs, tq = tile_m / tm.fsegs;
+                const int bgrp = tq / tm.tgroups, tgrp = tq - bgrp * tm.tgroups;
+                const int cb = p.b0 + bgrp * tm.bb, ct = tm.t_org + tgrp * tm.bt;
+                const int cf = tm.f_org + fsg * tm.Fs * tm.fstep;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait<32>(empty_bar(ps), pphase ^ 1u);
+                    const uint32_t stage = tiles + (uint32_t)ps * S::STAGE_BYTES;
+                    mbar_arrive_expect_tx(full_bar(ps), tx);
+                    tma_load_4d(stage, &tm.a, full_bar(ps), s_koff[4 * kb], cf + s_koff[4 * kb + 1],
+                                ct + s_koff[4 * kb + 2], cb);
+                    tma_load_2d(stage + A_STAGE_BYTES, &tm.w, full_bar(ps), kb * BKE, n0);
+                    if (++ps == STAGES) {
+                        ps = 0;
+                        pphase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp < 4) {
         // ============================ producers ============================
         // thread (g = tid/8, j = tid%8) serves chunk j of rows g, g+16, g+32, ... of both operand tiles
         const int j = tid & 7;
@@ -489,7 +539,20 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1) gemm_tc_kernel(const
             int b = -1;
             long long ooff = -1;
             int nlim = p.N;  // columns this row owns (merged-parity transposed conv: half of them on the last bin)
-            if (m < p.M) {
+            if (TMA) {  // rectangular tile: row r = (stream bi, frame ti, bin f) of tile (bgrp, tgrp)
+                const int tile_m = tile / ntn;
+                const int fsg = tile_m % tm.fsegs, tq = tile_m / tm.fsegs;
+                const int bgrp = tq / tm.tgroups, tgrp = tq - bgrp * tm.tgroups;
+                const int r = q * 32 + lane, rpf = tm.bt * tm.Fs;
+                const int bi = r / rpf, rr = r - bi * rpf;
+                const int ti = rr / tm.Fs, f = fsg * tm.Fs + (rr - ti * tm.Fs);
+                const int bl = bgrp * tm.bb + bi, t = tgrp * tm.bt + ti;
+                if (r < tm.rows && bl < nstreams && t < p.Tn) {
+                    b = p.b0 + bl;
+                    ooff = b * p.oB + t * p.oT + f * p.oF;
+                    if (p.odd_tail && f == p.Fo - 1) nlim = p.N >> 1;
+                }
+            } else if (m < p.M) {
                 const int bl = m / rowsPerStream;
                 const int rr = m - bl * rowsPerStream;
                 const int t = rr / p.Fo;
@@ -828,12 +891,27 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1) gemm_tc_kernel(const
 template <int BN, typename AT, bool B2B = (BN == 16)>
 int launch_tc(const GemmParams& p, cudaStream_t st) {
     using S = Cfg<BN, B2B>;
-    SE_DYN_SMEM((gemm_tc_kernel<BN, AT, B2B>), S::BYTES);
+    SE_DYN_SMEM((gemm_tc_kernel<BN, AT, B2B, false>), S::BYTES);
     int g_num_sms = 0;
     if (num_sms_current_device(&g_num_sms)) return 1;
     const int ntiles = ((p.M + BM - 1) / BM) * ((p.epi == EPI_GRU ? p.N : p.Npad) / BN);
     const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;  // persistent: one CTA per SM
-    gemm_tc_kernel<BN, AT, B2B><<<grid, S::THREADS, S::BYTES, st>>>(p);
+    static const GemmTma no_tma{};
+    gemm_tc_kernel<BN, AT, B2B, false><<<grid, S::THREADS, S::BYTES, st>>>(p, no_tma);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+template <int BN>
+int launch_tc_tma(const GemmParams& p, const GemmTma& tm, cudaStream_t st) {
+    using S = Cfg<BN, false>;
+    SE_DYN_SMEM((gemm_tc_kernel<BN, __half, false, true>), S::BYTES);
+    int g_num_sms = 0;
+    if (num_sms_current_device(&g_num_sms)) return 1;
+    const int nstreams = p.M / (p.Tn * p.Fo);
+    const int ntiles = ((nstreams + tm.bb - 1) / tm.bb) * tm.tgroups * tm.fsegs * (p.Npad / BN);
+    const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
+    gemm_tc_kernel<BN, __half, false, true><<<grid, S::THREADS, S::BYTES, st>>>(p, tm);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
@@ -869,6 +947,98 @@ bool gemm_tf32_supported(const GemmParams& p) {
     if (p.epi == EPI_SKIP && (p.o2B != p.oB || p.o2T != p.oT || p.o2F != p.oF)) return false;
     if (p.vec4 && ((p.oF % 4) || (p.oT % 4) || (p.oB % 4))) return false;
     return p.N >= 1;
+}
+
+bool gemm_tma_supported(const GemmParams& p) {
+    if (!p.a_half || !gemm_tf32_supported(p)) return false;
+    if (p.epi == EPI_GRU || p.epi == EPI_LSTM || p.epi == EPI_ELU_GATE) return false;  // their own tile walks
+    return gemm_tf32_tile_n(p.N) >= 32 && p.Tn * p.Fo > 0 && p.Fo <= BM;
+}
+
+int launch_gemm_tma(const GemmParams& p, const GemmTma& tm, cudaStream_t st) {
+    SE_REQUIRE(gemm_tma_supported(p), "gemm_tc: shape not supported by the TMA path");
+    if (p.M <= 0) return 0;
+    switch (gemm_tf32_tile_n(p.N)) {
+        case 32: return launch_tc_tma<32>(p, tm, st);
+        case 64: return launch_tc_tma<64>(p, tm, st);
+        case 128: return launch_tc_tma<128>(p, tm, st);
+        default: return launch_tc_tma<256>(p, tm, st);
+    }
+}
+
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {  // the driver entry point is fetched at run time: the library does not link libcuda
+    static EncodeTiledFn fn = [] {
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(f);
+    }();
+    return fn;
+}
+}  // namespace
+
+int make_gemm_tma(GemmTma* out, const void* a_base, int C, int Fp, int Tp, long long sT, long long sB, int nB, int Fo,
+                  int fstep, int Tn, const void* w_base, int K, int Npad, int BN) {
+    static_assert(sizeof(TmaDesc) == sizeof(CUtensorMap), "TmaDesc must hold a CUtensorMap");
+    EncodeTiledFn enc = encode_tiled_fn();
+    SE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    SE_REQUIRE(C % 64 == 0 && BN <= 256 && K % 64 == 0 && Fo >= 1 && Tn >= 1, "make_gemm_tma: shape");
+    // Tile shape: Fs bins (a divisor of Fo) x bt frames (a divisor of Tn: no ragged frame groups) x bb streams, as many
+    // of the 128 rows as possible; among (nearly) equal fills the one with the longest contiguous run (bins, then frames)
+    int Fs = 0, bt = 0, bb = 0, best = 0;
+    for (int fs = Fo; fs >= 1; --fs) {
+        if (Fo % fs != 0 || fs > BM) continue;
+        for (int t = Tn; t >= 1; --t) {
+            if (Tn % t != 0 || fs * t > BM) continue;
+            int b = BM / (fs * t);
+            if (b > 16) b = 16;
+            const int rows = fs * t * b;
+            if (rows > best + best / 20) {  // a candidate later in this order must fill > 5 % more rows to win
+                best = rows;
+                Fs = fs;
+                bt = t;
+                bb = b;
+            }
+        }
+    }
+    SE_REQUIRE(best > 0, "make_gemm_tma: no tile shape");
+    {  // activations [nB][Tp][Fp][C] fp16: box = 64 channels x Fo bins (every fstep-th) x bt frames x bb streams
+        const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Fp, (cuuint64_t)Tp, (cuuint64_t)nB};
+        const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)sT * 2, (cuuint64_t)sB * 2};
+        const cuuint32_t box[4] = {64, (cuuint32_t)((Fs - 1) * fstep + 1), (cuuint32_t)bt, (cuuint32_t)bb};
+        const cuuint32_t estr[4] = {1, (cuuint32_t)fstep, 1, 1};
+        const CUresult r = enc(reinterpret_cast<CUtensorMap*>(&out->a), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                               const_cast<void*>(a_base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (activations) failed with " + std::to_string((int)r));
+    }
+    {  // weights [Npad][K] fp16, K-major: box = 64 x BN
+        const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Npad};
+        const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+        const cuuint32_t box[2] = {64, (cuuint32_t)BN};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(reinterpret_cast<CUtensorMap*>(&out->w), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                               const_cast<void*>(w_base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (weights) failed with " + std::to_string((int)r));
+    }
+    out->bt = bt;
+    out->bb = bb;
+    out->Fs = Fs;
+    out->fsegs = Fo / Fs;
+    out->fstep = fstep;
+    out->tgroups = Tn / bt;
+    out->rows = bb * bt * Fs;
+    out->a_bytes = out->rows * BKB;
+    return 0;
 }
 
 int gemm_tf32_tile_n(int N) {

@@ -101,6 +101,33 @@ struct GemmParams {
     int lstm_units;
 };
 
+// TMA operand delivery for the tcgen05 GEMM (gemm_tc.cu; fp16 operands whose k-blocks are 64 contiguous channels).
+// One elected thread issues two cp.async.bulk.tensor loads per k-block -- the activation tile and the weight tile, both
+// landing in the canonical K-major SWIZZLE_128B layout the UMMA descriptors read -- instead of 128 threads gathering
+// 16-byte units with cp.async.  Tiles are RECTANGLES of the activation tensor [B][T][F][C]: `bb` streams x `bt` frames x
+// `Fs` bins of one of the `fsegs` equal segments of the Fo output bins (rows ordered stream, frame, bin; at most 128),
+// so that one 4-D box (C: 64, F: Fs taken every `fstep`-th bin, T: bt, B: bb) is the whole A tile of a k-block; the
+// per-k-block (channel, bin, frame) origin is a coordinate.
+struct alignas(64) TmaDesc {
+    unsigned long long opaque[16];  // CUtensorMap
+};
+struct GemmTma {
+    TmaDesc a, w;
+    int bt, bb;         // frames / streams per tile
+    int Fs, fsegs;      // bins per tile and tiles per bin axis (Fs * fsegs = Fo)
+    int fstep;          // input bins per output bin
+    int rows;           // bb * bt * Fs rows of the 128-row tile are real
+    int tgroups;        // ceil(Tn / bt) tiles per stream group
+    int a_bytes;        // bytes one activation box delivers (rows * 128)
+    int t_org, f_org;   // tensor coordinates of (frame 0, bin 0) of the row grid
+    const int4* kcoord; // per k-block: (channel, bin, frame) offsets of the box origin
+};
+// builds the two tensor maps; A is the tensor [nB][Tp][Fp][C] (fp16) at `a_base` with element strides (sB, sT, C)
+int make_gemm_tma(GemmTma* out, const void* a_base, int C, int Fp, int Tp, long long sT, long long sB, int nB, int Fo,
+                  int fstep, int Tn, const void* w_base, int K, int Npad, int BN);
+int launch_gemm_tma(const GemmParams& p, const GemmTma& tm, cudaStream_t st);
+bool gemm_tma_supported(const GemmParams& p);
+
 int launch_gemm_fp32(const GemmParams& p, cudaStream_t st);
 int launch_gemm_tf32(const GemmParams& p, cudaStream_t st);  // tcgen05 path (gemm_tc.cu)
 bool gemm_tf32_supported(const GemmParams& p);

@@ -20,12 +20,17 @@ SMALL = dict(num_channels=[8, 8, 16, 16], num_freqs=201, hidden=32, num_layers=2
 CONFIGS = {"crn_small": (SMALL, 7, False), "crn_teacher": (TEACHER, 0, False), "crn_student": (STUDENT, 3, True)}
 
 # Stated floating-point tolerances of the CUDA path against the reference (north_star: "max-abs error on the waveform
-# plus an SI-SDR delta").  fp32 mode re-associates sums (tiled GEMM, four-step FFT) but keeps fp32 everywhere.
+# plus an SI-SDR delta"), set at roughly 4-5x the error MEASURED on the three fixtures (B200, round 2; worst case in
+# brackets) so that a regression of that size fails:
+#   fp32  re-associates sums (tiled GEMM, four-step FFT) but keeps fp32 everywhere  [wave 3e-6 x peak, spectrum 2.2e-6, 114 dB]
+#   tf32  tcgen05 kind::tf32 on fp32 storage (10-bit mantissa operands)              [wave 3.0e-3 x peak, spectrum 2.0e-3, 55.9 dB]
+#   fp16  fp16 operand storage (11-bit significand), fp32 accumulate / statistics / state
+#                                                                                    [wave 5.0e-3 x peak (student), spectrum 2.9e-3, 53.0 dB]
+# wave_max_abs is relative to max(1, peak of the reference waveform); spec_rel to the peak of the reference spectrum.
 TOL = {
-    "fp32": dict(wave_max_abs=2e-4, spec_rel=2e-4, si_sdr_vs_ref_db=70.0),
-    "tf32": dict(wave_max_abs=2e-2, spec_rel=2e-2, si_sdr_vs_ref_db=40.0),
-    # fp16 operand storage (11-bit significand like tf32, round-to-nearest), fp32 accumulate / statistics / state
-    "fp16": dict(wave_max_abs=2e-2, spec_rel=2e-2, si_sdr_vs_ref_db=40.0),
+    "fp32": dict(wave_max_abs=2e-5, spec_rel=2e-5, si_sdr_vs_ref_db=100.0),
+    "tf32": dict(wave_max_abs=1.2e-2, spec_rel=1e-2, si_sdr_vs_ref_db=48.0),
+    "fp16": dict(wave_max_abs=1.2e-2, spec_rel=1.2e-2, si_sdr_vs_ref_db=48.0),
 }
 
 

@@ -81,8 +81,8 @@ def test_forward_chunk_matches_reference(tag, precision):
 def test_realtime_process_matches_reference(tag, precision, chunk_batch):
     """chunk_batch=False: the serial chunk loop (se_crn_realtime_process); True: every layer once over all chunks, only
     the GRU serial (chunk-major forward; offline files with few streams).  fp32: CUDA-core exact mode.  tf32: tcgen05 tensor cores (operands truncated to TF32, fp32 accumulate in TMEM);
-    stated tolerance: max-abs <= 2e-2 x peak and >= 40 dB SI-SDR against the reference waveform (BASELINE.md section 3:
-    the reference under bf16 autocast sits at 3.2e-2 / 42 dB)."""
+    stated tolerances: tests/common.py TOL (for context, BASELINE.md section 3: the reference under its own bf16 autocast
+    sits at 3.2e-2 x peak / 42 dB)."""
     g = load_golden(tag)
     tol = TOL[precision]
     if chunk_batch and precision == "fp16":
@@ -256,7 +256,10 @@ def test_full_size_1024_streams_replicas_match_oracle_checked_streams(precision)
             want.append(y.numpy())
     want = np.concatenate(want, axis=-1)
     keep = (~on_cut).numpy()
-    assert keep.sum() >= D // 2
+    # at most ONE of the 8 streams may sit on the branch cut (observed: one, stream-dependent on the FFT's last bit); more
+    # would mean the transform itself has drifted, not the cut
+    print(f"streams on the atan2 branch cut (held to the fp16 tolerance): {np.flatnonzero(on_cut.numpy()).tolist()}")
+    assert int(on_cut.sum()) <= 1
     model.reset()
     small = np.concatenate([model.process_chunk(c.cuda()).cpu().numpy() for c in chunks], axis=-1)
     tol = TOL[precision]
@@ -271,3 +274,98 @@ def test_full_size_1024_streams_replicas_match_oracle_checked_streams(precision)
     rep_tol = 2e-5 if precision == "fp32" else 2e-3
     assert np.abs(big - small[perm.numpy()]).max() < rep_tol * peak
     assert np.abs(big - want[perm.numpy()])[keep[perm.numpy()]].max() < tol["wave_max_abs"] * peak
+
+
+@pytest.mark.parametrize("switch", ["SE_B200_FRONT_MMA", "SE_B200_ENC_MMA", "SE_B200_TMA"])
+def test_fp16_round2_kernel_switches_match_reference(monkeypatch, switch):
+    """Round-2 kernels against the kernels they replace: the fused pre-convolutions / small-channel encoder blocks
+    (front_mma.cu, warp-level mma.sync on SMEM-resident streams) and the TMA operand delivery of the tcgen05 GEMM.  The
+    default path is covered by every other test; here each switch is turned OFF and the older path must still meet the
+    fixtures (all three configurations, incl. the carried state of a flag=True continuation)."""
+    monkeypatch.setenv(switch, "0")
+    for tag in CONFIGS:
+        g = load_golden(tag)
+        tol = TOL["fp16"]
+        model = make_model(tag, "fp16")
+        B, L = int(g["meta"][1]), int(g["meta"][2])
+        mix, _ = synth.make_mixture(B, L)
+        y = model.realtime_process(torch.from_numpy(mix).cuda())
+        y = (y[0] if isinstance(y, tuple) else y).cpu().numpy()
+        assert np.abs(y - g["out"]).max() < tol["wave_max_abs"] * max(1.0, np.abs(g["out"]).max()), tag
+        assert si_sdr_db(y, g["out"]) > tol["si_sdr_vs_ref_db"], tag
+        if "out_cont" in g:
+            mix2, _ = synth.make_mixture(B, L // 2, first_stream=100)
+            y2 = model.realtime_process(torch.from_numpy(mix2).cuda(), True).cpu().numpy()
+            assert np.abs(y2 - g["out_cont"]).max() < tol["wave_max_abs"] * max(1.0, np.abs(g["out_cont"]).max()), tag
+
+
+def test_full_size_2048_student_streams_replicas_match_oracle_checked_streams():
+    """BASELINE configs[2] per-GPU size (distilled student, 16384 streams over 8 GPUs = 2048 per GPU, fp16 operands): 8
+    distinct streams are checked against the oracle over 3 chunk steps, the 2048-stream batch holds 256 shuffled replicas
+    of each and every replica must reproduce its original (all waves of the persistent GRU kernel, all stream-CTAs of the
+    front-end kernels, all tiles of the TMA GEMMs)."""
+    oracle, _ = make_oracle("crn_student")
+    model = make_model("crn_student", "fp16")
+    D, B, N = 8, 2048, 3
+    mix, _ = synth.make_mixture(D, 1600 * (N + 1))
+    chunks = [torch.from_numpy(mix[:, :, 1600 * n:1600 * n + 3200].copy()) for n in range(N)]
+    with torch.no_grad():
+        oracle.reset()
+        state, want = None, []
+        for c in chunks:
+            y, state = oracle.stream_step(c, state)
+            want.append(y.numpy())
+    want = np.concatenate(want, axis=-1)
+    tol = TOL["fp16"]
+    peak = max(1.0, float(np.abs(want).max()))
+    model.reset()
+    small = np.concatenate([model.process_chunk(c.cuda()).cpu().numpy() for c in chunks], axis=-1)
+    assert np.abs(small - want).max() < tol["wave_max_abs"] * peak
+    perm = torch.from_numpy(np.random.default_rng(11).permutation(B) % D)
+    model.reset()
+    big = np.concatenate([model.process_chunk(c[perm].cuda()).cpu().numpy() for c in chunks], axis=-1)
+    assert np.abs(big - small[perm.numpy()]).max() < 2e-3 * peak
+    assert np.abs(big - want[perm.numpy()]).max() < tol["wave_max_abs"] * peak
+
+
+def test_cirm_clamp_edge_through_the_fused_mask_kernel_and_fsn_apply_mask():
+    """decompress_cIRM (utility.py:439-442) at and beyond the clamp |m| >= 9.9 -- values random-init weights never produce
+    -- through BOTH product kernels that contain it: the fused mask stage of the CRN chunk step (se_debug_mask_spectrum:
+    the mask kernel with an identity GlobalLayerNorm in front) and FullSubNet's se_fsn_apply_mask.  With a mic-0 spectrum
+    of 1 + 0j the enhanced spectrum IS the decompressed mask; reference: utility.decompress_cIRM on linspace(-12, 12)
+    from framing.npz (generated by the unmodified reference)."""
+    import ctypes as C
+    from speech_enhancement_mi_b200._native import check, lib
+    g = load_golden("framing")
+    m_in, want = g["cirm_in"], g["cirm_out"]  # 4001 values in [-12, 12]
+    assert np.abs(m_in).max() >= 11.9 and (np.abs(m_in) >= 9.9).sum() > 500
+    F, T = 201, 21
+    n = F * T * 2
+    reps = (n + m_in.size - 1) // m_in.size
+    flat = np.tile(m_in, reps)[:n].astype(np.float32)
+    flat_want = np.tile(want, reps)[:n].astype(np.float32)
+    lim = 10.0 * np.log((10 + 9.9) / (10 - 9.9))
+    assert abs(np.abs(flat_want).max() - lim) < 1e-3  # the fixture saturates at 10 ln(199)
+    # ---- CRN fused mask kernel: mask [B, T, F, 2] -> spec [B, F, T, 2]
+    model = make_model("crn_small", "fp32")
+    model.forward(torch.zeros(1, 3, F, T, 2).cuda())  # creates the context
+    mask = torch.from_numpy(flat.reshape(1, T, F, 2)).cuda()
+    noisy = torch.zeros(1, T, F, 2, device="cuda")
+    noisy[..., 0] = 1.0
+    out = torch.empty(1, F, T, 2, device="cuda")
+    check(lib().se_debug_mask_spectrum(model._ctx, mask.data_ptr(), noisy.data_ptr(), out.data_ptr(), 1),
+          "se_debug_mask_spectrum")
+    got = out.cpu().numpy().transpose(0, 2, 1, 3).reshape(-1)  # back to [T, F, 2] order
+    assert np.isfinite(got).all()
+    # identity norm: (m - 0) / (sqrt(1 + 1e-8) + 1e-8) moves m by 1.5e-8 relative; d/dm of the decompression is <= 100
+    assert np.abs(got - flat_want).max() <= 2e-4 * lim
+    assert np.abs(np.abs(got).max() - lim) < 1e-3
+    # ---- FullSubNet: crm [R, 2, F, T], x [R, 2, F, T] -> [R, F, T, 2]
+    crm = torch.from_numpy(flat.reshape(1, 2, F, T)).cuda()
+    x = torch.zeros(1, 2, F, T, device="cuda")
+    x[:, 0] = 1.0
+    out2 = torch.empty(1, F, T, 2, device="cuda")
+    check(lib().se_fsn_apply_mask(crm.data_ptr(), x.data_ptr(), out2.data_ptr(), 1, F, T, None), "se_fsn_apply_mask")
+    got2 = out2.cpu().numpy().transpose(0, 3, 1, 2).reshape(-1)  # [2, F, T] order of crm
+    assert np.isfinite(got2).all()
+    assert np.abs(got2 - flat_want).max() <= 1e-4 * lim
