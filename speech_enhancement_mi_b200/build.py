@@ -35,7 +35,8 @@ def sources():
 
 
 def headers():
-    return sorted(glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(HERE, "..", "include", "*.h")))
+    return sorted(glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                  glob.glob(os.path.join(HERE, "..", "include", "*.h")))
 
 
 def _sha(paths, extra=""):

@@ -83,7 +83,7 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
 };
 
 enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ, OP_DECONV_LAST, OP_SKIP_SMALL, OP_GRU_TC, OP_PRECONV_TC,
-              OP_PRECONV3, OP_ENC_MMA };
+              OP_PRECONV3, OP_ENC_MMA, OP_DEC_MMA };
 enum Stage { ST_STFT = 0, ST_PRECONV, ST_ENCODER, ST_GRU, ST_DECODER, ST_MASK, ST_ROLL, ST_COUNT };
 const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"};
 
@@ -103,7 +103,8 @@ struct Op {
     PreconvTcParams pt;
     Preconv3Params p3;
     EncMmaParams em;
-    int em_cin = 0, em_cout = 0;
+    DecMmaParams dm;
+    int em_cin = 0, em_cout = 0;  // channel counts of the mma.sync block kernels (encoder / decoder)
     int small_c = 0;  // channel count of the two small-layer kernels
     // TMA operand delivery (gemm_tc.cu): geometry of the tensor the A operand is gathered from, [B][Tp][Fp][C] at `tma_base`
     // with the row grid starting at (frame t_org, bin f_org) and advancing fstep bins per output bin.  C = 0: not described.
@@ -237,6 +238,7 @@ struct se_ctx {
     // mma.sync with the stream resident in shared memory (front_mma.cu).  SE_B200_FRONT_MMA=0 / SE_B200_ENC_MMA=0 keep the
     // round-1 kernels (preconv_tc.cu per layer; back-to-back tcgen05 GEMM + separate GlobalLayerNorm pass).
     bool front_mma = true, enc_mma = true;
+    bool dec_mma = true;  // SE_B200_DEC_MMA=0: small-channel decoder blocks as deconv GEMM + skip-pair kernel + blend kernel
     bool use_tma = true;  // SE_B200_TMA=0: every tcgen05 GEMM keeps the cp.async gather producers
     __half* feat_h = nullptr;     // features of the chunk [maxB][21][224][8] halves (borders stay zero)
     __half* pre_state = nullptr;  // carried frames of the three pre-convolutions [maxB][3][4][224][8] halves
@@ -894,6 +896,53 @@ struct Builder {
             push_norm(ST_DECODER, n, w_off, b_off, wr_off, br_off);
             rec.op_norm = (int)c->ops.size() - 1;
         }
+        // small-channel levels (fp16 mode): the three ops above become ONE launch (back_mma.cu); their packed weights and
+        // report entries are reused
+        if (c->dec_mma && skip->C == Cout_real && Cop == Cout_real &&
+            dec_mma_supported(Cin, Cout_real, in.Tp, in.Fp, Fin, Fs)) {
+            const Op o_norm = c->ops.back();
+            const OpFix f_norm = fix.back();
+            c->ops.pop_back();
+            fix.pop_back();
+            const Op o_skip = c->ops.back();
+            const OpFix f_skip = fix.back();
+            c->ops.pop_back();
+            fix.pop_back();
+            const Op o_dec = c->ops.back();
+            const OpFix f_dec = fix.back();
+            c->ops.pop_back();
+            fix.pop_back();
+            Op op{};
+            op.kind = OP_DEC_MMA;
+            op.stage = ST_DECODER;
+            op.dm = DecMmaParams{};
+            op.dm.in = reinterpret_cast<const __half*>(in.base);
+            op.dm.in_sB = in.sB;
+            op.dm.Tp = in.Tp;
+            op.dm.Fp = in.Fp;
+            op.dm.d = d;
+            op.dm.Fin = Fin;
+            op.dm.Kp = o_dec.g.K;
+            op.dm.skip = reinterpret_cast<const __half*>(skip->interior());
+            op.dm.sk_sB = skip->sB;
+            op.dm.sk_sT = skip->sT;
+            op.dm.sk_sF = skip->sF;
+            op.dm.Fs = Fs;
+            op.dm.K2p = o_skip.g.K;
+            op.dm.out = reinterpret_cast<__half*>(dst);
+            op.dm.oB = dB;
+            op.dm.oT = dT;
+            op.dm.oF = dF;
+            op.dm.student = c->student;
+            op.em_cin = Cin;
+            op.em_cout = Cout_real;
+            op.label = name + ".deconv+skip+blend";
+            op.alg_flops = o_dec.alg_flops + o_skip.alg_flops;
+            op.alg_bytes = 4.0 * Cin * T * Fin + 4.0 * 2 * T * Fs * Cout_real;  // input and skip tensor in, block output out
+            c->ops.push_back(op);
+            fix.push_back({f_dec.w_off, f_dec.b_off, -1, f_norm.nw_off, f_norm.nb_off, f_norm.nwr_off, f_norm.nbr_off,
+                           f_skip.w_off, f_skip.b_off});
+        }
         if (c->train) c->deconv_recs.push_back(rec);
     }
 };
@@ -936,6 +985,8 @@ int build_ctx(se_ctx* c) {
     if (const char* e = getenv("SE_B200_ENC_MMA")) c->enc_mma = atoi(e) != 0;
     c->front_mma = c->front_mma && c->preconv_tc;  // replaces the per-layer tensor-core kernels
     c->enc_mma = c->enc_mma && c->half && !c->train;
+    if (const char* e = getenv("SE_B200_DEC_MMA")) c->dec_mma = atoi(e) != 0;
+    c->dec_mma = c->dec_mma && c->half && !c->train;
     for (int i = 0; i < c->L; ++i) {
         SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
         SE_REQUIRE(!c->half || g.num_channels[i] % 8 == 0, "fp16 mode: num_channels must be multiples of 8");
@@ -1554,6 +1605,15 @@ int build_ctx(se_ctx* c) {
             }
         } else if (op.kind == OP_PRECONV3) {
             for (int l = 0; l < 3; ++l) op.p3.w[l] = c->warena + c->pre3_w_off[l];
+        } else if (op.kind == OP_DEC_MMA) {
+            op.dm.w = c->warena + f.w_off;
+            op.dm.bias = c->warena + f.b_off;
+            op.dm.w2 = c->warena + f.w2_off;
+            op.dm.bias2 = c->warena + f.b2_off;
+            op.dm.nw = c->warena + f.nw_off;
+            op.dm.nb = c->warena + f.nb_off;
+            op.dm.nwr = c->warena + f.nwr_off;
+            op.dm.nbr = c->warena + f.nbr_off;
         } else if (op.kind == OP_ENC_MMA) {
             op.em.w = c->warena + f.w_off;
             op.em.bias = c->warena + f.b_off;
@@ -1698,6 +1758,12 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
             em.b0 = 0;
             em.B = B;
             return launch_enc_mma(em, op.em_cin, op.em_cout, st);
+        }
+        case OP_DEC_MMA: {
+            DecMmaParams dm = op.dm;
+            dm.b0 = 0;
+            dm.B = B;
+            return launch_dec_mma(dm, op.em_cin, op.em_cout, st);
         }
         case OP_GRU_TC: {
             GruTcParams gt = op.gt;

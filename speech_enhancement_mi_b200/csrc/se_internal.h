@@ -243,6 +243,33 @@ struct EncMmaParams {
 bool enc_mma_supported(int Cin, int Cout, int Tp, int Fp, int Fo);
 int launch_enc_mma(const EncMmaParams& p, int Cin, int Cout, cudaStream_t st);
 
+// one transposed-conv decoder block with few channels in one launch (back_mma.cu; fp16 operand mode): ConvTranspose2d
+// (both output parities) + ELU + GlobalLayerNorm + the gated skip (1x1 mask / residual pair on the skip tensor,
+// GlobalLayerNorm of the mask, sigmoid blend) of CRN_ELU.py:290-307
+struct DecMmaParams {
+    const __half* in;      // deconv input [B][Tp = 21 + 2 d][Fp = Fin + 2][Cin]: one zero bin each side, 2 d zero frames behind
+    long long in_sB;
+    int Tp, Fp, d, Fin;
+    const float* w;        // deconv weights fp32 [2 Cout][Kp]: row parity * Cout + co, column (kt * 3 + j) * Cin + ci
+    int Kp;
+    const float* bias;     // [2 Cout]
+    const __half* skip;    // skip tensor (b, t, f, :) at skip + b*sk_sB + t*sk_sT + f*sk_sF, Cout channels
+    long long sk_sB, sk_sT, sk_sF;
+    int Fs;                // bins of the skip tensor = bins of the block output (>= 2 Fin - 1)
+    const float* w2;       // skip pair fp32 [2 Cout][K2p], rows interleaved (residualmask c, residual c)
+    int K2p;
+    const float* bias2;
+    const float *nw, *nb, *nwr, *nbr;  // norm / residualnorm affine [Cout]
+    __half* out;           // out(b, t, f, :) at out + b*oB + t*oT + f*oF
+    long long oB, oT, oF;
+    int student;
+    int b0, B;
+    int off_y, off_wf;                      // shared-memory offsets (filled by the launcher)
+    uint32_t magic_Fp, magic_Fs, magic_in;  // ceil(2^32 / d) of the run-time divisors (filled by the launcher)
+};
+bool dec_mma_supported(int Cin, int Cout, int Tp, int Fp, int Fin, int Fs);
+int launch_dec_mma(const DecMmaParams& p, int Cin, int Cout, cudaStream_t st);
+
 // GRU cell pointwise update for the fp32 path (PyTorch nn.GRU gate order r,z,n; CRN_ELU.py:127-133)
 int launch_gru_pointwise(const float* gi, long long giB, const float* gh, const float* hprev, long long hB,
                          float* hout, int B, int H, cudaStream_t st);
