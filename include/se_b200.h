@@ -144,6 +144,18 @@ int se_fsn_reset_state(se_fsn* ctx, int first, int count, void* stream);
  *   x [B, 2M, F, T] (M real planes then M imaginary planes, fullsubnet.py:835-844) -> compressed cIRM [B, 2, F, T];
  *   advances the LSTM states fh / sh and the CumLayerNorm running means of streams [0, B). */
 int se_fsn_forward_chunk(se_fsn* ctx, const float* x, float* out, int B, void* stream);
+/* replaces: the layout half of FullSubNet.stft_trans / preprocessing (fullsubnet.py:835-844, 880-886): spectrum
+ * [R, M, F, T, 2] (se_stft_trans) -> x [R, 2M, F, T] (M real planes, then M imaginary planes) and / or the mic-0 pair
+ * x0 [R, 2, F, T]; either output may be NULL */
+int se_fsn_planes(const float* spec, int R, int M, int F, int T, float* x, float* x0, void* stream);
+/* replaces: FullSubNet.realtime_process (fullsubnet.py:903-961), everything on the device in one call: front pad (flag = 0),
+ * segmentation, per-chunk STFT, the chunk loop (train = 0, :932-945; one CUDA-graph replay per chunk) or all chunks as ONE
+ * forward (train = 1, :921-927: both CumLayerNorms see the whole utterance), decompress_cIRM, complex mask, iSTFT and
+ * both overlap-adds.  mixture [B, M, L], source [B, M, L] or NULL -> pred [B, L]; optional outputs (NULL to skip):
+ * crm [N, B, 2, F, T] (compressed mask), s [N, B, 2, F, T] (mic-0 spectrum of `source`), x0 [N, B, 2, F, T] (mic-0
+ * spectrum of the mixture), N = chunks of se_chunk_grid(L + (flag ? 0 : 1600)).  flag = 1 continues the carried state. */
+int se_fsn_realtime_process(se_fsn* ctx, const float* mixture, const float* source, int B, int64_t L, int flag, int train,
+                            float* pred, float* crm, float* s, float* x0, void* stream);
 /* replaces: decompress_cIRM + complex multiply with mic 0 (fullsubnet.py:949-953):
  *   crm [R, 2, F, T], x [R, 2, F, T] (mic-0 real / imaginary) -> enhanced spectrum [R, F, T, 2] */
 int se_fsn_apply_mask(const float* crm, const float* x, float* out, int R, int F, int T, void* stream);

@@ -216,9 +216,39 @@ def run_fsn(cfg, seed, B, L, tag, continuation=False):
     print(tag, {k: v.shape for k, v in res.items()}, "peak", float(np.abs(res["out"]).max()), "params", n)
 
 
+def run_fsn_whole(cfg, seed, B, L, tag):
+    """Reference FullSubNet.realtime_process(train=True) (fullsubnet.py:921-927: all chunks concatenated into ONE forward,
+    both CumLayerNorms see the whole utterance) plus a flag=True continuation piece, with the 4-tuple outputs."""
+    weights = synth.make_fsn_weights(seed=seed, **cfg)
+    model = fullsubnet.FullSubNet(
+        num_freqs=cfg["num_freqs"], look_ahead=0, sequence_model="LSTM", fb_num_neighbors=cfg["fb_num_neighbors"],
+        sb_num_neighbors=cfg["sb_num_neighbors"], fb_output_activate_function="ReLU", sb_output_activate_function=False,
+        fb_model_hidden_size=cfg["fb_hidden"], sb_model_hidden_size=cfg["sb_hidden"], num_mics=cfg["num_mics"],
+        norm_type="offline_laplace_norm", num_groups_in_drop_band=2, num_layers=cfg["num_layers"], weight_init=False,
+        sample_rate=16000, segment_length=3200, win_length=25, hop_length=10, n_fft=400)
+    missing, unexpected = model.load_state_dict({k: torch.from_numpy(v) for k, v in weights.items()}, strict=True)
+    assert not missing and not unexpected
+    model.eval()
+    mix, src = synth.make_mixture(B, L)
+    s3 = torch.from_numpy(np.repeat(src[:, None, :], 3, axis=1).copy())
+    res = {}
+    with torch.no_grad():
+        pred, crm, sf, xf = model.realtime_process(torch.from_numpy(mix), s3, flag=False, train=True)
+        res["out"], res["crm"], res["sf"], res["xf"] = pred.numpy(), crm.numpy(), sf.numpy(), xf.numpy()
+        mix2, src2 = synth.make_mixture(B, L // 2, first_stream=100)
+        s32 = torch.from_numpy(np.repeat(src2[:, None, :], 3, axis=1).copy())
+        res["out_cont"] = model.realtime_process(torch.from_numpy(mix2), s32, flag=True, train=True)[0].numpy()
+    res["meta"] = np.array([seed, B, L])
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **res)
+    print(tag, {k: v.shape for k, v in res.items()}, "peak", float(np.abs(res["out"]).max()))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if "fsn_whole" in sys.argv[1:]:
+        run_fsn_whole(FSN_SMALL, 11, 2, 4000, "fsn_small_whole")
+        sys.exit(0)
     if "loss" in sys.argv[1:]:
         losses()
         sys.exit(0)

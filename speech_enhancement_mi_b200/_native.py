@@ -81,6 +81,8 @@ SIGNATURES = {
     "se_fsn_reset_state": (_I, [_P, _I, _I, _P]),
     "se_fsn_forward_chunk": (_I, [_P, _P, _P, _I, _P]),
     "se_fsn_apply_mask": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "se_fsn_planes": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "se_fsn_realtime_process": (_I, [_P, _P, _P, _I, _L, _I, _I, _P, _P, _P, _P, _P]),
     "se_unfold": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "se_cal_si_snr": (_I, [_P, _P, _P, _I, _L, _P, _P]),
     "se_stoi_loss": (_I, [_P, _P, _P, _I, _L, _P, _P]),

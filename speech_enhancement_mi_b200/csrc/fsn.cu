@@ -84,6 +84,11 @@ struct se_fsn {
     bool weights_bound = false;
     std::map<int, cudaGraphExec_t> graphs;
     cudaStream_t own_stream = nullptr;
+    // scratch of se_fsn_realtime_process (grown on demand; sized by chunks x streams)
+    float *rt_spec = nullptr, *rt_xin = nullptr, *rt_x0 = nullptr, *rt_crm = nullptr, *rt_s = nullptr, *rt_enh = nullptr,
+          *rt_chunks = nullptr, *rt_pline = nullptr, *rt_fbout = nullptr;
+    size_t rt_rows = 0, rt_rows_train = 0;
+    IoDesc* rt_io = nullptr;
     const float* cur_x = nullptr;  // indirection cell for graph replay
     const float** x_cell = nullptr;
     float** out_cell = nullptr;
@@ -482,6 +487,7 @@ int build(se_fsn* c) {
     if (c->half && dev_alloc(c, reinterpret_cast<char**>(&c->warena_h), c->warena_floats * 2)) return 1;
     if (dev_alloc(c, &c->karena, c->khost.size())) return 1;
     SE_CUDA_OK(cudaMemcpy(c->karena, c->khost.data(), c->khost.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (init_fft_tables()) return 1;  // se_fsn_realtime_process frames and transforms on this device
     for (size_t i = 0; i < c->gemms.size(); ++i) {
         c->gemms[i].W = c->g_half[i] ? static_cast<const void*>(reinterpret_cast<const __half*>(c->warena_h) + c->g_w[i])
                                      : static_cast<const void*>(c->warena + c->g_w[i]);
@@ -497,13 +503,24 @@ int run_gemm(se_fsn* c, int i, int B, cudaStream_t st) {
     return launch_gemm_tf32(g, st);
 }
 
-int enqueue(se_fsn* c, int B, cudaStream_t st) {
-    const int F = c->F, M = c->M, Hf = c->Hf, Hs = c->Hs;
-    const int Fp = round_up(F, 4), Pp = round_up(F + 2 * c->cfg.sb_num_neighbors, 4);
-    SE_CUDA_OK(cudaMemsetAsync(c->sums, 0, (size_t)4 * c->maxB * sizeof(double), st));
-    fsn_mag_kernel<<<dim3(M, B), 256, (size_t)F * T * sizeof(float), st>>>(c->x_cell, M, F, c->fbrec, c->recF, c->Kf,
-                                                                           c->sums);
-    fsn_cumnorm_kernel<<<(B + 127) / 128, 128, 0, st>>>(c->sums, c->cstate, c->cstep, 0, (double)M * F * T, B);
+// The chunk step in four phases.  whole = 0: the streaming chunk step (fullsubnet.py:932-945), both CumLayerNorms advance
+// once per chunk.  whole = 1 (train=True, :921-927: all chunks as ONE forward): the caller runs phase 0 over all chunks
+// first (sum of |X| over the whole utterance), one full-band norm update, phase 1 over all chunks (full-band model, sums
+// of the sub-band input), one sub-band norm update, phase 2 over all chunks.
+int phase_mag(se_fsn* c, int B, cudaStream_t st) {  // |X| -> full-band record, sum of |X|
+    fsn_mag_kernel<<<dim3(c->M, B), 256, (size_t)c->F * T * sizeof(float), st>>>(c->x_cell, c->M, c->F, c->fbrec, c->recF,
+                                                                               c->Kf, c->sums);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int phase_norm(se_fsn* c, int which, double count, int B, cudaStream_t st) {
+    fsn_cumnorm_kernel<<<(B + 127) / 128, 128, 0, st>>>(c->sums, c->cstate, c->cstep, which, count, B);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int phase_fullband(se_fsn* c, int B, cudaStream_t st) {  // scale, reflect-padded line, full-band LSTM + Linear + ReLU
+    const int F = c->F, M = c->M;
+    const int Pp = round_up(F + 2 * c->cfg.sb_num_neighbors, 4);
     fsn_scale_fb_kernel<<<dim3(T, B), 256, 0, st>>>(c->fbrec, c->recF, c->Kf, M * F, F, c->cfg.sb_num_neighbors,
                                                     c->cstate, c->pline, Pp, c->sums);
     int gi = 0;
@@ -514,18 +531,23 @@ int enqueue(se_fsn* c, int B, cudaStream_t st) {
         g.M = B * c->g_rows[gi];
         g.stats = c->sums + 2;
         g.stats_stride = 4;  // sums holds 4 doubles per stream
-        ++gi;
         if (launch_gemm_tf32(g, st)) return 1;
     }
-    fsn_cumnorm_kernel<<<(B + 127) / 128, 128, 0, st>>>(c->sums, c->cstate, c->cstep, 1, (double)F * c->Ks * T, B);
+    fsn_roll_kernel<float><<<dim3(B, (c->Hf + 255) / 256), 256, 0, st>>>(c->fbrec, c->recF, c->f_h0, c->f_h1, c->Hf);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+int phase_subband(se_fsn* c, int B, cudaStream_t st) {  // unfold, sub-band LSTM + Linear, compressed cIRM out
+    const int F = c->F, Hs = c->Hs;
+    const int Fp = round_up(F, 4), Pp = round_up(F + 2 * c->cfg.sb_num_neighbors, 4);
     fsn_unfold_kernel<<<dim3(T, B), 256, 0, st>>>(c->pline, Pp, c->fbout, Fp, F, c->NB, c->cstate, c->sbrec, c->recS,
                                                   c->Ks, c->Ksp, c->half ? 1 : 0);
+    int gi = 2 * T + 1;
     for (int i = 0; i < 2 * T; ++i)
         if (run_gemm(c, gi++, B, st)) return 1;
     if (run_gemm(c, gi++, B, st)) return 1;
     const long long total = (long long)B * 2 * F * T;
     fsn_out_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(c->crm, c->out_cell, F, total);
-    fsn_roll_kernel<float><<<dim3(B, (Hf + 255) / 256), 256, 0, st>>>(c->fbrec, c->recF, c->f_h0, c->f_h1, Hf);
     if (c->half)
         fsn_roll_kernel<__half><<<dim3(B * F, (Hs + 255) / 256), 256, 0, st>>>(reinterpret_cast<__half*>(c->sbrec), c->recS,
                                                                              c->s_h0, c->s_h1, Hs);
@@ -533,6 +555,69 @@ int enqueue(se_fsn* c, int B, cudaStream_t st) {
         fsn_roll_kernel<float><<<dim3(B * F, (Hs + 255) / 256), 256, 0, st>>>(c->sbrec, c->recS, c->s_h0, c->s_h1, Hs);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
+}
+
+int enqueue(se_fsn* c, int B, cudaStream_t st) {
+    SE_CUDA_OK(cudaMemsetAsync(c->sums, 0, (size_t)4 * c->maxB * sizeof(double), st));
+    if (phase_mag(c, B, st)) return 1;
+    if (phase_norm(c, 0, (double)c->M * c->F * T, B, st)) return 1;
+    if (phase_fullband(c, B, st)) return 1;
+    if (phase_norm(c, 1, (double)c->F * c->Ks * T, B, st)) return 1;
+    return phase_subband(c, B, st);
+}
+
+// spectrum [R][M][F][T][2] (se_stft layout) -> x [R][2M][F][T] (M real planes, then M imaginary planes; fullsubnet.py:
+// 835-844) and, optionally, the mic-0 pair x0 [R][2][F][T] (:950)
+__global__ void fsn_planes_kernel(const float* spec, int M, int F, float* x, float* x0, long long total) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long ft = i % ((long long)F * T);
+        const long long rm = i / ((long long)F * T);
+        const int m = (int)(rm % M);
+        const long long r = rm / M;
+        const float2 v = reinterpret_cast<const float2*>(spec)[i];
+        if (x) {
+            x[((r * 2 * M + m) * F) * T + ft] = v.x;
+            x[((r * 2 * M + M + m) * F) * T + ft] = v.y;
+        }
+        if (x0 && m == 0) {
+            x0[(r * 2 * F) * T + ft] = v.x;
+            x0[((r * 2 + 1) * F) * T + ft] = v.y;
+        }
+    }
+}
+
+int run_chunk_graph(se_fsn* c, int B, cudaStream_t st) {
+    auto it = c->graphs.find(B);
+    if (it == c->graphs.end()) {
+        if (!c->own_stream) SE_CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        SE_CUDA_OK(cudaStreamBeginCapture(c->own_stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = enqueue(c, B, c->own_stream);
+        cudaError_t e = cudaStreamEndCapture(c->own_stream, &graph);
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return 1;
+        }
+        SE_CUDA_OK(e);
+        cudaGraphExec_t exec = nullptr;
+        SE_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
+        SE_CUDA_OK(cudaGraphDestroy(graph));
+        it = c->graphs.emplace(B, exec).first;
+    }
+    SE_CUDA_OK(cudaGraphLaunch(it->second, st));
+    return 0;
+}
+
+template <typename Tp>
+int regrow(se_fsn* c, Tp** buf, size_t count) {  // scratch: freed and re-allocated larger (registered for destroy)
+    if (*buf) {
+        for (void*& q : c->allocs)
+            if (q == *buf) q = nullptr;
+        SE_CUDA_OK(cudaFree(*buf));
+        *buf = nullptr;
+    }
+    return dev_alloc(c, buf, count);
 }
 
 }  // namespace
@@ -639,24 +724,119 @@ int se_fsn_forward_chunk(se_fsn* c, const float* x, float* out, int B, void* str
     SE_CUDA_OK(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     fsn_set_cells<<<1, 1, 0, st>>>(c->x_cell, x, c->out_cell, out);
-    auto it = c->graphs.find(B);
-    if (it == c->graphs.end()) {
-        if (!c->own_stream) SE_CUDA_OK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-        cudaGraph_t graph = nullptr;
-        SE_CUDA_OK(cudaStreamBeginCapture(c->own_stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = enqueue(c, B, c->own_stream);
-        cudaError_t e = cudaStreamEndCapture(c->own_stream, &graph);
-        if (rc) {
-            if (graph) cudaGraphDestroy(graph);
-            return 1;
-        }
-        SE_CUDA_OK(e);
-        cudaGraphExec_t exec = nullptr;
-        SE_CUDA_OK(cudaGraphInstantiate(&exec, graph, 0));
-        SE_CUDA_OK(cudaGraphDestroy(graph));
-        it = c->graphs.emplace(B, exec).first;
+    return run_chunk_graph(c, B, st);
+}
+
+int se_fsn_realtime_process(se_fsn* c, const float* mixture, const float* source, int B, int64_t L, int flag, int train,
+                            float* pred, float* crm_out, float* s_out, float* x0_out, void* stream) {
+    SE_REQUIRE(c != nullptr && c->weights_bound, "se_fsn_realtime_process: context without weights");
+    SE_REQUIRE(mixture != nullptr && pred != nullptr && L > 0, "se_fsn_realtime_process: null buffer");
+    SE_REQUIRE(B >= 1 && B <= c->maxB, "se_fsn_realtime_process: B exceeds max_streams");
+    SE_REQUIRE(c->M <= 3, "se_fsn_realtime_process: the framing kernel serves at most 3 microphones");
+    SE_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = c->F, M = c->M, K = 3200, P = K / 2;
+    const int front = flag ? 0 : P;  // fullsubnet.py:905-908
+    int gap = 0, N = 0;
+    if (se_chunk_grid(L + front, K, &gap, &N)) return 1;
+    const size_t R = (size_t)N * B;
+    const size_t per = (size_t)F * T;
+    const int Fp = round_up(F, 4), Pp = round_up(F + 2 * c->cfg.sb_num_neighbors, 4);
+    if (R > c->rt_rows) {
+        if (regrow(c, &c->rt_spec, (size_t)B * M * per * 2)) return 1;
+        if (regrow(c, &c->rt_xin, (size_t)B * 2 * M * per)) return 1;
+        if (regrow(c, &c->rt_x0, R * 2 * per)) return 1;
+        if (regrow(c, &c->rt_crm, R * 2 * per)) return 1;
+        if (regrow(c, &c->rt_s, R * 2 * per)) return 1;
+        if (regrow(c, &c->rt_enh, R * 2 * per)) return 1;
+        if (regrow(c, &c->rt_chunks, R * K)) return 1;
+        if (!c->rt_io && dev_alloc(c, &c->rt_io, 1)) return 1;
+        c->rt_rows = R;
+        c->rt_rows_train = 0;
     }
-    SE_CUDA_OK(cudaGraphLaunch(it->second, st));
+    if (train && R > c->rt_rows_train) {  // train=True keeps every chunk's network input and full-band results
+        if (regrow(c, &c->rt_xin, R * 2 * M * per)) return 1;
+        if (regrow(c, &c->rt_pline, R * T * Pp)) return 1;
+        if (regrow(c, &c->rt_fbout, R * T * Fp)) return 1;
+        c->rt_rows_train = R;
+    }
+    if (!flag && se_fsn_reset_state(c, 0, B, stream)) return 1;  // :913-915
+    float* crm_all = crm_out ? crm_out : c->rt_crm;
+    float* x0_all = x0_out ? x0_out : c->rt_x0;
+    // STFT of chunk n of every stream straight from the signal: the zero padding of utility.padding (P samples in front,
+    // gap + P behind) and the front pad of :905-908 are the out-of-range reads of the framing kernel
+    auto stft_chunk = [&](const float* sig, int n, float* xin, float* x0) -> int {
+        IoDesc io{sig, (long long)M * L, L, -(long long)P - front + (long long)n * P, L, nullptr, 0, 0};
+        if (launch_set_io(c->rt_io, io, st)) return 1;
+        StftParams sp{};
+        sp.io = c->rt_io;
+        sp.B = B;
+        sp.M = M;
+        sp.spec_ref = c->rt_spec;
+        if (launch_stft_features(sp, st)) return 1;
+        const long long total = (long long)B * M * per;
+        fsn_planes_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(c->rt_spec, M, F, xin, x0, total);
+        SE_CUDA_OK(cudaGetLastError());
+        return 0;
+    };
+    if (!train) {
+        for (int n = 0; n < N; ++n) {  // strictly serial: LSTM states and running norms are carried (:932-945)
+            if (stft_chunk(mixture, n, c->rt_xin, x0_all + (size_t)n * B * 2 * per)) return 1;
+            fsn_set_cells<<<1, 1, 0, st>>>(c->x_cell, c->rt_xin, c->out_cell, crm_all + (size_t)n * B * 2 * per);
+            if (run_chunk_graph(c, B, st)) return 1;
+        }
+    } else {
+        const size_t xin_chunk = (size_t)B * 2 * M * per;
+        SE_CUDA_OK(cudaMemsetAsync(c->sums, 0, (size_t)4 * c->maxB * sizeof(double), st));
+        for (int n = 0; n < N; ++n) {
+            if (stft_chunk(mixture, n, c->rt_xin + n * xin_chunk, x0_all + (size_t)n * B * 2 * per)) return 1;
+            fsn_set_cells<<<1, 1, 0, st>>>(c->x_cell, c->rt_xin + n * xin_chunk, c->out_cell, crm_all);
+            if (phase_mag(c, B, st)) return 1;
+        }
+        if (phase_norm(c, 0, (double)M * F * T * N, B, st)) return 1;  // ONE CumLayerNorm step over all N*T frames
+        SE_CUDA_OK(cudaMemsetAsync(c->sums, 0, (size_t)4 * c->maxB * sizeof(double), st));
+        for (int n = 0; n < N; ++n) {
+            fsn_set_cells<<<1, 1, 0, st>>>(c->x_cell, c->rt_xin + n * xin_chunk, c->out_cell, crm_all);
+            if (phase_mag(c, B, st)) return 1;  // re-creates the record of this chunk (its sum slot is not used again)
+            if (phase_fullband(c, B, st)) return 1;
+            SE_CUDA_OK(cudaMemcpyAsync(c->rt_pline + (size_t)n * B * T * Pp, c->pline, (size_t)B * T * Pp * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, st));
+            SE_CUDA_OK(cudaMemcpyAsync(c->rt_fbout + (size_t)n * B * T * Fp, c->fbout, (size_t)B * T * Fp * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, st));
+        }
+        if (phase_norm(c, 1, (double)F * c->Ks * T * N, B, st)) return 1;
+        for (int n = 0; n < N; ++n) {
+            SE_CUDA_OK(cudaMemcpyAsync(c->pline, c->rt_pline + (size_t)n * B * T * Pp, (size_t)B * T * Pp * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, st));
+            SE_CUDA_OK(cudaMemcpyAsync(c->fbout, c->rt_fbout + (size_t)n * B * T * Fp, (size_t)B * T * Fp * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, st));
+            fsn_set_cells<<<1, 1, 0, st>>>(c->x_cell, c->rt_xin + n * xin_chunk, c->out_cell,
+                                           crm_all + (size_t)n * B * 2 * per);
+            if (phase_subband(c, B, st)) return 1;
+        }
+    }
+    if (source != nullptr && s_out != nullptr)  // spectrum of the clean source, mic 0 (:880-886), returned to the caller
+        for (int n = 0; n < N; ++n)
+            if (stft_chunk(source, n, nullptr, s_out + (size_t)n * B * 2 * per)) return 1;
+    // decompress_cIRM + complex mask (:949-953), per-chunk iSTFT and the 50 % chunk overlap-add (:955-957)
+    if (se_fsn_apply_mask(crm_all, x0_all, c->rt_enh, (int)R, F, T, stream)) return 1;
+    MaskIstftParams mp{};
+    mp.B = (int)R;
+    mp.spec_in = c->rt_enh;
+    mp.out_chunk = c->rt_chunks;
+    if (launch_mask_istft(mp, st)) return 1;
+    return launch_over_add_cm(c->rt_chunks, B, N, K, front, L, pred, st);
+}
+
+int se_fsn_planes(const float* spec, int R, int M, int F, int Tn, float* x, float* x0, void* stream) {
+    SE_REQUIRE(spec != nullptr && (x != nullptr || x0 != nullptr), "se_fsn_planes: null buffer");
+    SE_REQUIRE(R >= 0 && M >= 1 && F >= 1 && Tn == T, "se_fsn_planes: bad shape (T must be 21)");
+    const long long total = (long long)R * M * F * T;
+    if (total == 0) return 0;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 32) grid = 148 * 32;
+    fsn_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(spec, M, F, x, x0, total);
+    SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

@@ -185,15 +185,23 @@ class FullSubNet(BaseModel):
         self._fresh = False
         return out.to(noisy_complex.device)
 
+    def _spectrum(self, x, dev):
+        R, M, K = x.shape
+        xd = _f32(x, dev)
+        spec = torch.empty((R, M, self.num_freqs, 1 + K // self.hop_samples, 2), dtype=torch.float32, device=xd.device)
+        check(lib().se_stft_trans(None, xd.data_ptr(), R, spec.data_ptr(), _stream(dev)), "se_stft_trans")
+        return spec
+
     def stft_trans(self, x):
         """[R, M, K] -> [R, 2M, F, T] (fullsubnet.py:835-844)."""
         R, M, K = x.shape
         dev = self._pick_device(x)
         with torch.cuda.device(dev):
-            xd = _f32(x, dev)
-            s = torch.empty((R, M, self.num_freqs, 1 + K // self.hop_samples, 2), dtype=torch.float32, device=xd.device)
-            check(lib().se_stft_trans(None, xd.data_ptr(), R, s.data_ptr(), _stream(dev)), "se_stft_trans")
-            s = torch.cat([s[..., 0], s[..., 1]], dim=1).contiguous()  # layout only
+            spec = self._spectrum(x, dev)
+            T = spec.shape[3]
+            s = torch.empty((R, 2 * M, self.num_freqs, T), dtype=torch.float32, device=spec.device)
+            check(lib().se_fsn_planes(spec.data_ptr(), R, M, self.num_freqs, T, s.data_ptr(), None, _stream(dev)),
+                  "se_fsn_planes")
         return s.to(x.device)
 
     def istft_trans(self, x):
@@ -221,9 +229,13 @@ class FullSubNet(BaseModel):
         if source is None:
             return x, None, gap
         seg_s, gap = self.segmentation(source)
-        s = self.stft_trans(seg_s)
-        s = s.reshape([B, -1] + list(s.shape[1:])).transpose(0, 1)
-        s = torch.stack([s[:, :, 0], s[:, :, self.num_mics]], dim=2)
+        dev = self._pick_device(seg_s)
+        with torch.cuda.device(dev):
+            spec = self._spectrum(seg_s, dev)
+            R, M, Fq, T = spec.shape[:4]
+            s = torch.empty((R, 2, Fq, T), dtype=torch.float32, device=spec.device)  # mic-0 real / imaginary (:886)
+            check(lib().se_fsn_planes(spec.data_ptr(), R, M, Fq, T, None, s.data_ptr(), _stream(dev)), "se_fsn_planes")
+        s = s.to(source.device).reshape([B, -1] + list(s.shape[1:])).transpose(0, 1)
         return x, s, gap
 
     def postprocessing(self, sp, gap):
@@ -233,45 +245,41 @@ class FullSubNet(BaseModel):
         return self.overadd(y.reshape(N, B, -1).permute(1, 0, 2), gap)
 
     def realtime_process(self, mixture, source=None, flag=False, train=True):
-        """fullsubnet.py:903-961, chunk loop (``train=False``).  Returns ``pred`` when ``source`` is None, else the
-        reference's 4-tuple (pred [B, L], pred_crm [N, B, 2, F, T], s [N, B, 2, F, T], x [N, B, 2, F, T])."""
-        if train:
-            raise NotImplementedError("train=True (all chunks concatenated into one forward, fullsubnet.py:921-927) is not "
-                                      "built; the reference's trainers and predictors call train=False")
-        B, Cm, _ = mixture.shape
+        """fullsubnet.py:903-961 in ONE native call (se_fsn_realtime_process): front pad, segmentation, per-chunk STFT, the
+        chunk loop (``train=False``: what the reference's trainers and predictors call, :932-945) or all chunks as one
+        forward (``train=True``, the signature's default, :921-927), mask, iSTFT, overlap-add.  Returns ``pred`` when
+        ``source`` is None, else the reference's 4-tuple (pred [B, L], pred_crm [N, B, 2, F, T], s [N, B, 2, F, T],
+        x [N, B, 2, F, T]).  No PyTorch arithmetic: tensors are only allocated here."""
+        B, Cm, L = mixture.shape
+        if Cm != self.num_mics:
+            raise ValueError(f"mixture must be [B, {self.num_mics}, L]")
         dev = self._pick_device(mixture)
         P = self.segment_length // 2
-        if not flag:
-            pad = torch.zeros((B, Cm, P), dtype=mixture.dtype, device=mixture.device)
-            mixture = torch.cat([pad, mixture], dim=-1)
-            if source is not None:
-                source = torch.cat([pad, source], dim=-1)
         ctx = self._ensure_ctx(B, dev, keep_state=bool(flag))
+        _, N = _native.chunk_grid(L + (0 if flag else P), self.segment_length)
+        T = 1 + self.segment_length // self.hop_samples
         with torch.cuda.device(dev):
-            x, s, gap = self.preprocessing(_f32(mixture, dev), None if source is None else _f32(source, dev))
-            N = x.shape[0]
+            xd = _f32(mixture, dev)
+            sd = None if source is None else _f32(source, dev)
+            pred = torch.empty((B, L), dtype=torch.float32, device=xd.device)
+            if source is None:
+                crm = s = x0 = None
+            else:
+                shape = (N, B, 2, self.num_freqs, T)
+                crm, s, x0 = (torch.empty(shape, dtype=torch.float32, device=xd.device) for _ in range(3))
             if not flag:
-                self.reset_state(B)
                 self.exist_prob = 0.0
-            x = x.contiguous()
-            T = x.shape[-1]
-            pred_crm = torch.empty((N, B, 2, self.num_freqs, T), dtype=torch.float32, device=x.device)
-            st = _stream(dev)
-            for idx in range(N):  # strictly serial: LSTM state and running norms are carried (fullsubnet.py:932-945)
-                check(lib().se_fsn_forward_chunk(ctx, x[idx].data_ptr(), pred_crm[idx].data_ptr(), B, st),
-                      "se_fsn_forward_chunk")
+            check(lib().se_fsn_realtime_process(ctx, xd.data_ptr(), None if sd is None else sd.data_ptr(), B, L,
+                                                int(bool(flag)), int(bool(train)), pred.data_ptr(),
+                                                None if crm is None else crm.data_ptr(),
+                                                None if s is None else s.data_ptr(),
+                                                None if x0 is None else x0.data_ptr(), _stream(dev)),
+                  "se_fsn_realtime_process")
             self._fresh = False
-            x0 = torch.stack([x[:, :, 0], x[:, :, self.num_mics]], dim=2).contiguous()  # mic-0 real / imaginary
-            enh = torch.empty((N * B, self.num_freqs, T, 2), dtype=torch.float32, device=x.device)
-            check(lib().se_fsn_apply_mask(pred_crm.data_ptr(), x0.data_ptr(), enh.data_ptr(), N * B, self.num_freqs, T,
-                                          st), "se_fsn_apply_mask")
-            pred = self.postprocessing(enh.reshape(N, B, self.num_freqs, T, 2), gap)
-            if not flag:
-                pred = pred[..., P:]
         pred = pred.to(mixture.device)
         if source is None:
             return pred
-        return pred, pred_crm.to(mixture.device), s.to(mixture.device), x0.to(mixture.device)
+        return pred, crm.to(mixture.device), s.to(mixture.device), x0.to(mixture.device)
 
     def compute_loss(self, source, pred_source, xf, sf, cIRM, length):
         """fullsubnet.py:964-987 (forward only): loss = 0.7 * stoi_loss + 0.3 * (-SI-SNR); NaN => zero-filled."""

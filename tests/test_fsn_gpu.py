@@ -112,3 +112,40 @@ def test_streams_independent_and_oracle_agrees():
     assert np.abs(y - want.numpy()).max() < TOL_REL * max(1.0, float(want.abs().max()))
     yb = m.realtime_process(x[2:3].cuda(), None, flag=False, train=False).cpu().numpy()
     assert np.abs(yb[0] - y[2]).max() < 1e-4
+
+
+def test_realtime_process_whole_utterance_train_true_matches_reference():
+    """train=True (the signature's default, fullsubnet.py:921-927): all chunks concatenated into ONE forward, so both
+    CumLayerNorms take a single step over the whole utterance instead of one per chunk.  Fixture: the unmodified reference
+    with train=True, incl. the 4-tuple outputs and a flag=True continuation piece (second norm step, carried LSTM state)."""
+    g = load("fsn_small_whole")
+    m = make(FSN_SMALL, 11)
+    B, L = int(g["meta"][1]), int(g["meta"][2])
+    mix, src = synth.make_mixture(B, L)
+    s3 = torch.from_numpy(np.repeat(src[:, None, :], 3, axis=1).copy())
+    pred, crm, sf, xf = m.realtime_process(torch.from_numpy(mix).cuda(), s3.cuda(), flag=False, train=True)
+    pred = pred.cpu().numpy()
+    assert rel_err(crm.cpu().numpy(), g["crm"]) < TOL_REL
+    assert rel_err(sf.cpu().numpy(), g["sf"]) < 1e-5 and rel_err(xf.cpu().numpy(), g["xf"]) < 1e-5
+    assert np.abs(pred - g["out"]).max() < TOL_REL * max(1.0, np.abs(g["out"]).max())
+    assert si_sdr_db(pred, g["out"]) > TOL_DB
+    mix2, _ = synth.make_mixture(B, L // 2, first_stream=100)
+    p2 = m.realtime_process(torch.from_numpy(mix2).cuda(), None, flag=True, train=True).cpu().numpy()
+    assert np.abs(p2 - g["out_cont"]).max() < TOL_REL * max(1.0, np.abs(g["out_cont"]).max())
+    # the chunk loop is a different function of the same weights (per-chunk running norms): it must NOT reproduce this
+    p_loop = m.realtime_process(torch.from_numpy(mix).cuda(), None, flag=False, train=False).cpu().numpy()
+    assert np.abs(p_loop - g["out"]).max() > 10 * np.abs(pred - g["out"]).max()
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+def test_full_config_realtime_process_matches_reference(precision):
+    """config.yaml:153-172 sizes (full-band 512, sub-band 384 hidden units) through the whole realtime_process in both
+    precisions of the LSTM operands."""
+    g = load("fsn_full")
+    m = make(FSN_FULL, 5, precision=precision)
+    seed, B, L = [int(v) for v in g["meta"]]
+    mix, _ = synth.make_mixture(B, L)
+    pred = m.realtime_process(torch.from_numpy(mix).cuda(), None, flag=False, train=False).cpu().numpy()
+    assert pred.shape == g["out"].shape
+    assert np.abs(pred - g["out"]).max() < TOL_REL * max(1.0, np.abs(g["out"]).max())
+    assert si_sdr_db(pred, g["out"]) > TOL_DB
