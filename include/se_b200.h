@@ -229,6 +229,10 @@ int se_debug_read(se_ctx* ctx, const char* name, int b, float* host_dst, int64_t
  * utility.py:439-442, complex multiply with the mic-0 spectrum of CRN_ELU.py:401-405) on caller data, all DEVICE memory:
  * mask [B, T, F, 2] (the values that enter decompress_cIRM), noisy [B, T, F, 2] -> spec_out [B, F, T, 2] (the layout
  * forward() returns).  Lets tests drive the clamp |m| >= 9.9, which random-init weights never reach.  Synchronises. */
+/* Diagnostic: cycle accounting of the warp roles of the TMA tcgen05 GEMM (contexts created with SE_B200_GEMM_PROFILE=1):
+ * out8 = {MMA thread waiting for operands, for a drained accumulator, MMA loop total, producer waiting for a free stage,
+ * producer total, epilogue waiting for an accumulator, epilogue total, tiles}, summed over CTAs since the last reset. */
+int se_debug_gemm_counters(uint64_t* out8, int reset);
 int se_debug_mask_spectrum(se_ctx* ctx, const float* mask, const float* noisy, float* spec_out, int B);
 
 #ifdef __cplusplus

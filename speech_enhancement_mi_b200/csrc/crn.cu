@@ -2635,6 +2635,11 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
 }
 
 
+int se_debug_gemm_counters(uint64_t* out8, int reset) {
+    static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "counter width");
+    return gemm_profile_read(reinterpret_cast<unsigned long long*>(out8), reset);
+}
+
 int se_debug_mask_spectrum(se_ctx* c, const float* mask, const float* noisy, float* spec_out, int B) {
     SE_REQUIRE(c != nullptr && mask != nullptr && noisy != nullptr && spec_out != nullptr && B > 0,
                "se_debug_mask_spectrum: bad arguments");

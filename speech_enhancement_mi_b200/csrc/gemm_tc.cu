@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "se_internal.h"
 
@@ -97,8 +98,61 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* map, uint3
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
         : "memory");
 }
+// ---- CTA pair (cta_group::2): two CTAs of a cluster run ONE M256 MMA; the leader (cluster rank 0) issues it ---------
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank) {  // same offset in CTA `rank`
+    uint32_t a;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local_addr), "r"(rank));
+    return a;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// tile load whose completion is counted on an mbarrier that may live in the PEER CTA of the pair (the leader's)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const void* map, uint32_t bar_cluster, int c0, int c1, int c2,
+                                                 int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {  // arrive on `bar` of the CTAs in `mask`
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// One lane of the (converged) warp.  The single-thread roles run their loops WARP-UNIFORMLY and only predicate the issue
+// on this: inside an `if (lane == 0)` region ptxas treats every operand as divergent and wraps each tcgen05.mma / TMA
+// in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop (about 100 cycles per MMA -- more than a 128 x 64 MMA takes to execute).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -173,14 +227,31 @@ __device__ __forceinline__ void stats_commit(double* stats, int stride, int b, f
     }
 }
 
+// Cycle accounting of the warp roles (diagnostic; SE_B200_GEMM_PROFILE=1 at context creation turns it on through
+// GemmTma::profile): [0] MMA thread waiting for operands (full), [1] for a drained accumulator (tempty), [2] total MMA-thread
+// loop, [3] producer waiting for a free stage (empty), [4] producer total, [5] epilogue lead warps waiting for an
+// accumulator (tfull), [6] epilogue lead warps total, [7] tiles.  Summed over CTAs; read with se_debug_gemm_counters.
+__device__ unsigned long long g_gemm_prof[8];
+#ifndef SE_GEMM_PROFILE
+#define SE_GEMM_PROFILE 0  // build with -DSE_GEMM_PROFILE=1 (tools/gemm_roles.py does) to compile the accounting in
+#endif
+#ifndef SE_GEMM_TMA_FENCE
+#define SE_GEMM_TMA_FENCE 0
+#endif
+constexpr bool kProf = SE_GEMM_PROFILE != 0;
+
 constexpr int kW2Floats = 32 * 16 + 32;  // fused small gate: W2 [2*C2][16] + bias2 [2*C2], C2 <= 16
 
 // B2B: the kernel instance carries the back-to-back gate GEMM (EPI_ELU_GATE): always for BN = 16 (first encoder conv),
 // for BN = 32 / 64 only in the dedicated instances (fp16 operands) so that the plain GEMMs keep their deeper pipelines
-template <int BN, bool B2B = (BN == 16)>
+// TMA: 0 = cp.async gather producers, 1 = TMA tile loads, 2 = TMA + CTA pair (cta_group::2: the two CTAs of a cluster run
+// one M256 x BN MMA; each holds its own 128 rows of A and HALF of the weight tile, which halves the shared-memory reads of
+// the tensor core and the fill traffic per SM -- these GEMMs run at the shared-memory bandwidth of their operand tiles)
+template <int BN, bool B2B = (BN == 16), int TMA = 0>
 struct Cfg {
     static constexpr int NACC = (BN > 128 || (B2B && BN > 16)) ? 2 : 4;  // TMEM accumulators = epilogue groups
-    static constexpr int STAGES = BN > 128 ? 3 : (BN > 32 ? 4 : (B2B ? 4 : 6));  // B2B: room for the gate tiles
+    static constexpr int STAGES = TMA == 2 ? (BN > 128 ? 4 : (BN > 64 ? 5 : 6))
+                                           : (BN > 128 ? 3 : (BN > 32 ? 4 : (B2B ? 4 : 6)));  // B2B: room for the gate tiles
     static constexpr int WARPS = kFirstEpiWarp + 4 * NACC;
     static constexpr int THREADS = WARPS * 32;
     // back-to-back gate (BN == 16, fp16 operands): a second accumulator of 32 columns per group, the ELU tile as an
@@ -192,7 +263,7 @@ struct Cfg {
     static constexpr uint32_t TMEM_COLS =
         TMEM_COLS_RAW <= 32 ? 32
                             : (TMEM_COLS_RAW <= 64 ? 64 : (TMEM_COLS_RAW <= 128 ? 128 : (TMEM_COLS_RAW <= 256 ? 256 : 512)));
-    static constexpr int B_STAGE_BYTES = BN * BKB;
+    static constexpr int B_STAGE_BYTES = (TMA == 2 ? BN / 2 : BN) * BKB;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int TILE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int KOFF_MAX = 512;  // K <= 2048
@@ -302,14 +373,16 @@ __device__ __forceinline__ void small_gate(const float* s_w2, const float* e, in
     }
 }
 
-template <int BN, typename AT, bool B2B = (BN == 16), bool TMA = false>
-__global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
+template <int BN, typename AT, bool B2B = (BN == 16), int TMA = 0>
+__global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
     gemm_tc_kernel(const GemmParams p, const __grid_constant__ GemmTma tm) {
     constexpr int BKE = BKB / (int)sizeof(AT);  // elements per k-block
     constexpr int UE = 16 / (int)sizeof(AT);    // elements per 16-byte gather unit
-    using S = Cfg<BN, B2B>;
+    using S = Cfg<BN, B2B, TMA>;
     constexpr int STAGES = S::STAGES;
     constexpr int NACC = S::NACC;
+    constexpr bool PAIR = TMA == 2;
+    constexpr int CS = PAIR ? 2 : 1;  // CTAs per tile row group
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t tiles = (raw + 1023u) & ~1023u;  // SWIZZLE_128B atoms need 1024-byte alignment
@@ -327,13 +400,20 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);  // provably warp-uniform: role dispatch of the issuing warps
     const int lane = tid & 31;
     const int nkb = p.K / BKE;  // K and Npad are padded by the host (zero weights): no bounds checks on either operand
     const int ntn = (p.epi == EPI_GRU ? p.N : p.Npad) / BN;
     const int rowsPerStream = p.Tn * p.Fo;
     const int nstreams = p.M / rowsPerStream;
     // TMA: a tile is a rectangle of tm.bb streams x tm.bt frames x Fo bins (tm.rows of the 128 rows are real)
-    const int ntiles = (TMA ? ((nstreams + tm.bb - 1) / tm.bb) * tm.tgroups * tm.fsegs : (p.M + BM - 1) / BM) * ntn;
+    const int ntiles_m = TMA ? ((nstreams + tm.bb - 1) / tm.bb) * tm.tgroups * tm.fsegs : (p.M + BM - 1) / BM;
+    // CTA pair: the cluster walks "super-tiles" = two consecutive m-tiles x one n-tile; rank r owns m-tile 2 j + r (its
+    // rows of A, its TMEM lanes, its epilogue).  An m-tile past the end is a dummy (out-of-range boxes are zero-filled,
+    // every row masked): both CTAs of a pair run the same number of stages.
+    const uint32_t crank = PAIR ? (uint32_t)(blockIdx.x & 1) : 0u;
+    const int tfirst = (int)blockIdx.x / CS, tstep = (int)gridDim.x / CS;
+    const int ntiles = ((ntiles_m + CS - 1) / CS) * ntn;
 
     if (TMA) {  // per k-block box origin (channel, bin, frame, -)
         for (int i = tid; i < 4 * nkb; i += S::THREADS) s_koff[i] = __ldg(reinterpret_cast<const int*>(tm.kcoord) + i);
@@ -367,53 +447,83 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
     }
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), TMA ? 1 : kProducerThreads);
+            mbar_init(full_bar(s), TMA ? 1 : kProducerThreads);  // pair: only the leader's is used (bytes of both CTAs)
             mbar_init(empty_bar(s), 1);
         }
         for (int g = 0; g < NACC; ++g) {
             mbar_init(tfull_bar(g), 1);
-            mbar_init(tempty_bar(g), BN == 96 ? 128 * NACC : 128);  // GRU tiles are read by every group
+            // GRU tiles are read by every group; pair: the leader's barrier collects the epilogue threads of both CTAs
+            mbar_init(tempty_bar(g), BN == 96 ? 128 * NACC : (PAIR ? 256 : 128));
             if (B2B) mbar_init(bar0 + 8u * (2 * STAGES + 2 * NACC + g), 1);  // gate MMA of group g finished
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 4) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
-                     "r"(S::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                         "r"(S::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                         "r"(S::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // the peer's barriers and TMEM exist before anything is signalled at them
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
 
-    if (TMA && warp < 4) {
-        // ============================ producer (TMA): one elected thread ============================
-        if (tid == 0) {
+    if (TMA && warp_u < 4) {
+        // ============================ producer (TMA): warp 0, one elected lane issues ============================
+        if (warp_u == 0) {
             uint32_t ps = 0, pphase = 0;
-            const uint32_t tx = (uint32_t)tm.a_bytes + (uint32_t)S::B_STAGE_BYTES;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int tile_m = tile / ntn, n0 = (tile % ntn) * BN;
+            // bytes that complete a stage: this CTA's two boxes; pair: the boxes of both CTAs land on the LEADER's barrier
+            const uint32_t tx = (uint32_t)CS * ((uint32_t)tm.a_bytes + (uint32_t)S::B_STAGE_BYTES);
+            constexpr int wrows = PAIR ? BN / 2 : BN;  // weight rows this CTA holds
+            const bool prof = kProf && tm.profile != 0;
+            long long w_empty = 0;
+            const long long t_begin = kProf ? clock64() : 0;
+            for (int tile = tfirst; tile < ntiles; tile += tstep) {
+                const int tile_m = (tile / ntn) * CS + (int)crank, n0 = (tile % ntn) * BN;
                 const int fsg = tile_m % tm.fsegs, tq = tile_m / tm.fsegs;
                 const int bgrp = tq / tm.tgroups, tgrp = tq - bgrp * tm.tgroups;
                 const int cb = p.b0 + bgrp * tm.bb, ct = tm.t_org + tgrp * tm.bt;
                 const int cf = tm.f_org + fsg * tm.Fs * tm.fstep;
                 for (int kb = 0; kb < nkb; ++kb) {
+                    const long long t0 = prof ? clock64() : 0;
                     mbar_wait<32>(empty_bar(ps), pphase ^ 1u);
+                    if (prof) w_empty += clock64() - t0;
                     const uint32_t stage = tiles + (uint32_t)ps * S::STAGE_BYTES;
-                    mbar_arrive_expect_tx(full_bar(ps), tx);
-                    tma_load_4d(stage, &tm.a, full_bar(ps), s_koff[4 * kb], cf + s_koff[4 * kb + 1],
-                                ct + s_koff[4 * kb + 2], cb);
-                    tma_load_2d(stage + A_STAGE_BYTES, &tm.w, full_bar(ps), kb * BKE, n0);
+                    const int k0 = s_koff[4 * kb], k1 = s_koff[4 * kb + 1], k2 = s_koff[4 * kb + 2];
+                    if (elect_one()) {
+                        if (PAIR) {
+                            const uint32_t lead_full = mapa_rank(full_bar(ps), 0);
+                            if (crank == 0) mbar_arrive_expect_tx(full_bar(ps), tx);
+                            tma_load_4d_pair(stage, &tm.a, lead_full, k0, cf + k1, ct + k2, cb);
+                            tma_load_2d_pair(stage + A_STAGE_BYTES, &tm.w, lead_full, kb * BKE, n0 + (int)crank * wrows);
+                        } else {
+                            mbar_arrive_expect_tx(full_bar(ps), tx);
+                            tma_load_4d(stage, &tm.a, full_bar(ps), k0, cf + k1, ct + k2, cb);
+                            tma_load_2d(stage + A_STAGE_BYTES, &tm.w, full_bar(ps), kb * BKE, n0);
+                        }
+                    }
+                    __syncwarp();
                     if (++ps == STAGES) {
                         ps = 0;
                         pphase ^= 1u;
                     }
                 }
             }
+            if (prof && lane == 0) {
+                atomicAdd(&g_gemm_prof[3], (unsigned long long)w_empty);
+                atomicAdd(&g_gemm_prof[4], (unsigned long long)(clock64() - t_begin));
+            }
         }
-    } else if (warp < 4) {
+    } else if (warp_u < 4) {
         // ============================ producers ============================
         // thread (g = tid/8, j = tid%8) serves chunk j of rows g, g+16, g+32, ... of both operand tiles
         const int j = tid & 7;
@@ -422,7 +532,7 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
         constexpr int B_ITERS = BN / 16;
         uint32_t ps = 0, pphase = 0;  // stage ring position / phase (the ring runs on across tiles)
         const int q16 = 16 / p.Fo, r16 = 16 % p.Fo;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int tile = tfirst; tile < ntiles; tile += tstep) {
             const int m0 = (tile / ntn) * BM;
             const int n0 = (tile % ntn) * BN;
             const AT* arow[BM / 16];
@@ -480,39 +590,66 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
                 }
             }
         }
-    } else if (warp == 4) {
+    } else if (warp_u == 4) {
         // ============================ MMA issuer ============================
+        const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         // instruction descriptor: D=f32 (1<<4), A/B format @7/@10 (tf32 = 2, f16 = 0), K-major both, N>>3 @17, M>>4 @24
         constexpr uint32_t fmt = sizeof(AT) == 4 ? 2u : 0u;
         constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)(BM >> 4) << 24);
-        if (lane == 0) {
+        constexpr uint32_t idesc_pair = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+        if (!PAIR || crank == 0) {  // pair: only the leader issues (for both CTAs); the warp loops, one lane issues
             uint32_t ms = 0, mphase = 0, it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const bool prof = kProf && TMA && tm.profile != 0;
+            long long w_full = 0, w_tempty = 0;
+            const long long t_begin = kProf ? clock64() : 0;
+            for (int tile = tfirst; tile < ntiles; tile += tstep, ++it) {
                 const int g = it % NACC;
+                const long long t0 = prof ? clock64() : 0;
                 mbar_wait<0>(tempty_bar(g), ((it / NACC) & 1) ^ 1);  // the epilogue has drained this accumulator
+                if (prof) w_tempty += clock64() - t0;
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(g * BN);
+                const uint32_t tacc = tmem_base_u + (uint32_t)(g * BN);
                 uint32_t acc = 0;
                 for (int kb = 0; kb < nkb; ++kb) {
+                    const long long t1 = prof ? clock64() : 0;
                     mbar_wait<0>(full_bar(ms), mphase);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic) -> async proxy
+                    if (prof) w_full += clock64() - t1;
+                    // cp.async wrote the stage through the generic proxy; TMA stages are already async-proxy writes, and
+                    // the fence would make this thread wait for its own MMAs in flight (one k-block at a time)
+                    if (!TMA || SE_GEMM_TMA_FENCE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     tc_fence_after();
                     const uint64_t adesc = make_desc(tiles + ms * (uint32_t)S::STAGE_BYTES);
                     const uint64_t bdesc = adesc + (uint64_t)(A_STAGE_BYTES >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk) {
-                        // one MMA consumes 32 bytes of K (8 tf32 / 16 fp16): +2 in the (addr >> 4) field of the atom
-                        tc_mma<AT>(tacc, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, acc);
-                        acc = 1;
+                        for (int kk = 0; kk < 4; ++kk) {
+                            // one MMA consumes 32 bytes of K (8 tf32 / 16 fp16): +2 in the (addr >> 4) field of the atom
+                            const uint32_t a1 = kk ? 1u : acc;
+                            if (PAIR) tc_mma_f16_pair(tacc, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc_pair, a1);
+                            else tc_mma<AT>(tacc, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, a1);
+                        }
+                        if (PAIR) tc_commit_pair(empty_bar(ms), 3);  // the stage is free in BOTH CTAs
+                        else tc_commit(empty_bar(ms));
                     }
-                    tc_commit(empty_bar(ms));
+                    __syncwarp();
+                    acc = 1;
                     if (++ms == STAGES) {
                         ms = 0;
                         mphase ^= 1u;
                     }
                 }
-                tc_commit(tfull_bar(g));
+                if (elect_one()) {
+                    if (PAIR) tc_commit_pair(tfull_bar(g), 3);  // each CTA's epilogue reads its own 128 TMEM lanes
+                    else tc_commit(tfull_bar(g));
+                }
+                __syncwarp();
+            }
+            if (prof && lane == 0) {
+                atomicAdd(&g_gemm_prof[0], (unsigned long long)w_full);
+                atomicAdd(&g_gemm_prof[1], (unsigned long long)w_tempty);
+                atomicAdd(&g_gemm_prof[2], (unsigned long long)(clock64() - t_begin));
+                atomicAdd(&g_gemm_prof[7], (unsigned long long)it);
             }
         }
         __syncwarp();
@@ -530,7 +667,9 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
         const bool gru = BN == 96 && p.epi == EPI_GRU;
         uint32_t it = gru ? 0 : g;
         const uint32_t it_step = gru ? 1 : NACC;
-        for (int tile = blockIdx.x + it * gridDim.x; tile < ntiles; tile += it_step * gridDim.x, it += it_step) {
+        const uint32_t lead_tempty0 = PAIR ? mapa_rank(tempty_bar(0), 0) : 0u;  // pair: the leader's "accumulator drained"
+        const long long t_epi_begin = kProf ? clock64() : 0;
+        for (int tile = tfirst + it * tstep; tile < ntiles; tile += it_step * tstep, it += it_step) {
             const int acc = gru ? (int)(it % NACC) : g;
             const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             const int m0 = (tile / ntn) * BM;
@@ -540,7 +679,7 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
             long long ooff = -1;
             int nlim = p.N;  // columns this row owns (merged-parity transposed conv: half of them on the last bin)
             if (TMA) {  // rectangular tile: row r = (stream bi, frame ti, bin f) of tile (bgrp, tgrp)
-                const int tile_m = tile / ntn;
+                const int tile_m = (tile / ntn) * CS + (int)crank;
                 const int fsg = tile_m % tm.fsegs, tq = tile_m / tm.fsegs;
                 const int bgrp = tq / tm.tgroups, tgrp = tq - bgrp * tm.tgroups;
                 const int r = q * 32 + lane, rpf = tm.bt * tm.Fs;
@@ -569,7 +708,12 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
             float s_acc = 0.f, ss_acc = 0.f;
             auto wait_acc = [&]() {
                 // one warp per group polls the mbarrier, the other three block on a hardware named barrier
-                if ((ew & 3) == 0) mbar_wait<64>(tfull_bar(acc), (it / NACC) & 1);
+                if ((ew & 3) == 0) {
+                    const bool prof = kProf && TMA && tm.profile != 0 && lane == 0;
+                    const long long t0 = prof ? clock64() : 0;
+                    mbar_wait<64>(tfull_bar(acc), (it / NACC) & 1);
+                    if (prof) atomicAdd(&g_gemm_prof[5], (unsigned long long)(clock64() - t0));
+                }
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
                 tc_fence_after();
             };
@@ -712,7 +856,7 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
                 const uint32_t gate_bar = bar0 + 8u * (2 * STAGES + 2 * NACC + g);
                 const uint32_t tgate = tmem_base + (uint32_t)(NACC * BN + g * 2 * BN);
-                if ((ew & 3) == 0 && lane == 0) {
+                if ((ew & 3) == 0 && elect_one()) {
                     tc_fence_after();
                     constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
                     const uint64_t ad = make_desc(tiles + S::OFF_ETILE + (uint32_t)g * (BM * BKB));
@@ -798,7 +942,8 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
                     tmem_ld_wait();
                     if (c0 + CH >= BN) {  // accumulator fully read: hand it back to the MMA warp
                         tc_fence_before();
-                        mbar_arrive(tempty_bar(acc));
+                        if (PAIR) mbar_arrive_cluster(lead_tempty0 + 8u * (uint32_t)acc);  // the leader issues the next MMAs
+                        else mbar_arrive(tempty_bar(acc));
                     }
                     const int n = n0 + c0;
                     if (n >= p.N) continue;  // (CTA-uniform) nothing but padding in this pass
@@ -878,41 +1023,71 @@ __global__ void __launch_bounds__(Cfg<BN, B2B>::THREADS, 1)
                 if (want_stats) stats_commit(p.stats, p.stats_stride ? p.stats_stride : 2, b, s_acc, ss_acc);
             }
         }
+        if (kProf && TMA && tm.profile != 0 && (ew & 3) == 0 && lane == 0)
+            atomicAdd(&g_gemm_prof[6], (unsigned long long)(clock64() - t_epi_begin));
         tc_fence_before();
     }
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while the pair's MMAs / barriers may still touch it
     if (warp == 4) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(S::TMEM_COLS)
-                     : "memory");
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(S::TMEM_COLS)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(S::TMEM_COLS)
+                         : "memory");
     }
 }
 
 template <int BN, typename AT, bool B2B = (BN == 16)>
 int launch_tc(const GemmParams& p, cudaStream_t st) {
     using S = Cfg<BN, B2B>;
-    SE_DYN_SMEM((gemm_tc_kernel<BN, AT, B2B, false>), S::BYTES);
+    SE_DYN_SMEM((gemm_tc_kernel<BN, AT, B2B, 0>), S::BYTES);
     int g_num_sms = 0;
     if (num_sms_current_device(&g_num_sms)) return 1;
     const int ntiles = ((p.M + BM - 1) / BM) * ((p.epi == EPI_GRU ? p.N : p.Npad) / BN);
     const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;  // persistent: one CTA per SM
     static const GemmTma no_tma{};
-    gemm_tc_kernel<BN, AT, B2B, false><<<grid, S::THREADS, S::BYTES, st>>>(p, no_tma);
+    gemm_tc_kernel<BN, AT, B2B, 0><<<grid, S::THREADS, S::BYTES, st>>>(p, no_tma);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
 template <int BN>
 int launch_tc_tma(const GemmParams& p, const GemmTma& tm, cudaStream_t st) {
-    using S = Cfg<BN, false>;
-    SE_DYN_SMEM((gemm_tc_kernel<BN, __half, false, true>), S::BYTES);
     int g_num_sms = 0;
     if (num_sms_current_device(&g_num_sms)) return 1;
     const int nstreams = p.M / (p.Tn * p.Fo);
-    const int ntiles = ((nstreams + tm.bb - 1) / tm.bb) * tm.tgroups * tm.fsegs * (p.Npad / BN);
-    const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
-    gemm_tc_kernel<BN, __half, false, true><<<grid, S::THREADS, S::BYTES, st>>>(p, tm);
-    SE_CUDA_OK(cudaGetLastError());
+    const int ntiles_m = ((nstreams + tm.bb - 1) / tm.bb) * tm.tgroups * tm.fsegs;
+    if (!tm.pair) {
+        using S = Cfg<BN, false, 1>;
+        SE_DYN_SMEM((gemm_tc_kernel<BN, __half, false, 1>), S::BYTES);
+        const int ntiles = ntiles_m * (p.Npad / BN);
+        const int grid = ntiles < g_num_sms ? ntiles : g_num_sms;
+        gemm_tc_kernel<BN, __half, false, 1><<<grid, S::THREADS, S::BYTES, st>>>(p, tm);
+        SE_CUDA_OK(cudaGetLastError());
+        return 0;
+    }
+    // CTA pairs: clusters of two CTAs (same TPC), one cluster per super-tile at a time
+    using S = Cfg<BN, false, 2>;
+    SE_DYN_SMEM((gemm_tc_kernel<BN, __half, false, 2>), S::BYTES);
+    const int nsuper = ((ntiles_m + 1) / 2) * (p.Npad / BN);
+    int nclusters = g_num_sms / 2;
+    if (nsuper < nclusters) nclusters = nsuper;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * nclusters);
+    cfg.blockDim = dim3(S::THREADS);
+    cfg.dynamicSmemBytes = S::BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, __half, false, 2>, p, tm));
     return 0;
 }
 
@@ -1019,10 +1194,22 @@ int make_gemm_tma(GemmTma* out, const void* a_base, int C, int Fp, int Tp, long 
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (activations) failed with " + std::to_string((int)r));
     }
-    {  // weights [Npad][K] fp16, K-major: box = 64 x BN
+    // CTA pair mode (cta_group::2; SE_B200_TMA_PAIR=0 keeps one CTA per tile): each CTA of the pair holds half the weight
+    // tile, so a 256-row M tile fetches the weights once.  With the tensor pipe fed at its own pace (tools/gemm_roles.py:
+    // the MMA warp otherwise waits for operand stages ~45 % of the time) the operand stream from L2 is what bounds the
+    // long-K GEMMs, and the pair cuts it by a quarter (BN 128) to a third (BN 256).  Measured at 1024 streams, pair vs
+    // single: 768-column GRU projections 110 -> 94 us and 51 -> 48 us, 3x3 convolutions (K >= 576) 89 -> 85, 97 -> 93,
+    // 91 -> 86 us; the short-K GEMMs (1x1 gates / skips, fc: K <= 256) are epilogue-bound and lose 4 us to the cluster
+    // launch, so they stay single.  SE_B200_TMA_PAIR=2 forces the pair everywhere.
+    int pair = BN == 256 || K >= 576;
+    if (const char* e = getenv("SE_B200_TMA_PAIR")) pair = atoi(e) == 2 ? 1 : (atoi(e) != 0 && pair);
+    if (BN / 2 < 16) pair = 0;
+    out->pair = pair;
+    out->profile = getenv("SE_B200_GEMM_PROFILE") ? atoi(getenv("SE_B200_GEMM_PROFILE")) : 0;
+    {  // weights [Npad][K] fp16, K-major: box = 64 x BN (pair: x BN / 2, the slice of one CTA)
         const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)Npad};
         const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-        const cuuint32_t box[2] = {64, (cuuint32_t)BN};
+        const cuuint32_t box[2] = {64, (cuuint32_t)(pair ? BN / 2 : BN)};
         const cuuint32_t estr[2] = {1, 1};
         const CUresult r = enc(reinterpret_cast<CUtensorMap*>(&out->w), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                                const_cast<void*>(w_base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1038,6 +1225,16 @@ int make_gemm_tma(GemmTma* out, const void* a_base, int C, int Fp, int Tp, long 
     out->tgroups = Tn / bt;
     out->rows = bb * bt * Fs;
     out->a_bytes = out->rows * BKB;
+    return 0;
+}
+
+int gemm_profile_read(unsigned long long* out8, int reset) {
+    SE_CUDA_OK(cudaDeviceSynchronize());
+    if (out8) SE_CUDA_OK(cudaMemcpyFromSymbol(out8, g_gemm_prof, 8 * sizeof(unsigned long long)));
+    if (reset) {
+        const unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        SE_CUDA_OK(cudaMemcpyToSymbol(g_gemm_prof, z, sizeof(z)));
+    }
     return 0;
 }
 

@@ -116,6 +116,8 @@ struct GemmTma {
     int bt, bb;         // frames / streams per tile
     int Fs, fsegs;      // bins per tile and tiles per bin axis (Fs * fsegs = Fo)
     int fstep;          // input bins per output bin
+    int profile;        // 1: the warp roles account their wait cycles in g_gemm_prof (diagnostic)
+    int pair;           // 1: CTA-pair kernel (cta_group::2, M256 MMAs over two SMs); the weight box is half a tile
     int rows;           // bb * bt * Fs rows of the 128-row tile are real
     int tgroups;        // ceil(Tn / bt) tiles per stream group
     int a_bytes;        // bytes one activation box delivers (rows * 128)
@@ -127,6 +129,7 @@ int make_gemm_tma(GemmTma* out, const void* a_base, int C, int Fp, int Tp, long 
                   int fstep, int Tn, const void* w_base, int K, int Npad, int BN);
 int launch_gemm_tma(const GemmParams& p, const GemmTma& tm, cudaStream_t st);
 bool gemm_tma_supported(const GemmParams& p);
+int gemm_profile_read(unsigned long long* out8, int reset);  // diagnostic cycle counters of the TMA GEMM roles
 
 int launch_gemm_fp32(const GemmParams& p, cudaStream_t st);
 int launch_gemm_tf32(const GemmParams& p, cudaStream_t st);  // tcgen05 path (gemm_tc.cu)
