@@ -233,6 +233,10 @@ int se_debug_read(se_ctx* ctx, const char* name, int b, float* host_dst, int64_t
  * out8 = {MMA thread waiting for operands, for a drained accumulator, MMA loop total, producer waiting for a free stage,
  * producer total, epilogue waiting for an accumulator, epilogue total, tiles}, summed over CTAs since the last reset. */
 int se_debug_gemm_counters(uint64_t* out8, int reset);
+/* Same for the wavefront GRU (builds with -DSE_GRU_PROFILE=1): out16 = [layer][{producer waiting for the published state,
+ * producer waiting for a free stage, MMA warp waiting for operands, MMA warp total, epilogue waiting for the accumulator,
+ * epilogue total, MMA warp waiting for the drained accumulator, steps}]. */
+int se_debug_gru_counters(uint64_t* out16, int reset);
 int se_debug_mask_spectrum(se_ctx* ctx, const float* mask, const float* noisy, float* spec_out, int B);
 
 #ifdef __cplusplus

@@ -101,6 +101,7 @@ SIGNATURES = {
     "se_debug_read": (_I, [_P, C.c_char_p, _I, _P, _L, C.POINTER(C.c_int)]),
     "se_debug_mask_spectrum": (_I, [_P, _P, _P, _P, _I]),
     "se_debug_gemm_counters": (_I, [C.POINTER(C.c_uint64), _I]),
+    "se_debug_gru_counters": (_I, [C.POINTER(C.c_uint64), _I]),
 }
 
 _lib = None

@@ -83,7 +83,7 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
 };
 
 enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ, OP_DECONV_LAST, OP_SKIP_SMALL, OP_GRU_TC, OP_PRECONV_TC,
-              OP_PRECONV3, OP_ENC_MMA, OP_DEC_MMA };
+              OP_PRECONV3, OP_ENC_MMA, OP_DEC_MMA, OP_GRU_WAVE };
 enum Stage { ST_STFT = 0, ST_PRECONV, ST_ENCODER, ST_GRU, ST_DECODER, ST_MASK, ST_ROLL, ST_COUNT };
 const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"};
 
@@ -100,6 +100,7 @@ struct Op {
     DeconvLastParams dl;
     SkipSmallParams sk;
     GruTcParams gt;
+    GruWaveParams gw;
     PreconvTcParams pt;
     Preconv3Params p3;
     EncMmaParams em;
@@ -227,6 +228,9 @@ struct se_ctx {
     float* E(float* base, long long elems) const {  // element offset into an operand buffer
         return reinterpret_cast<float*>(reinterpret_cast<char*>(base) + elems * esz);
     }
+    int gru_wave = 1;          // SE_B200_GRU_WAVE=0: one persistent kernel per layer (+ the layer-1 projection GEMM) instead
+                               // of the two-layer wavefront kernel (gru_wave.cu); 2: also where H is too large for the
+                               // wavefront, use the one-layer form of gru_wave.cu instead of gru_tc_persist.cu
     bool gru_persist = true;   // SE_B200_GRU_PERSIST=0: one GEMM launch per recurrent step instead of the persistent kernel
     int* gru_counters = nullptr;
     // fp16 mode: pre-convolutions on the tensor cores (preconv_tc.cu: implicit conv through no-swizzle UMMA descriptors
@@ -976,6 +980,7 @@ int build_ctx(se_ctx* c) {
     if (const char* e = getenv("SE_B200_TC_MASK")) c->tc_mask = (unsigned)strtoul(e, nullptr, 0);
     if (const char* e = getenv("SE_B200_SMALL_LAYERS")) c->small_layers = atoi(e) != 0;
     if (const char* e = getenv("SE_B200_GRU_PERSIST")) c->gru_persist = atoi(e) != 0;
+    if (const char* e = getenv("SE_B200_GRU_WAVE")) c->gru_wave = atoi(e);
     if (const char* e = getenv("SE_B200_B2B")) c->b2b_gate = atoi(e) != 0;
     if (const char* e = getenv("SE_B200_PRECONV_TC")) c->preconv_tc = atoi(e) != 0;
     c->preconv_tc = c->preconv_tc && c->half && !c->train;
@@ -1294,10 +1299,26 @@ int build_ctx(se_ctx* c) {
     const int Fg = c->Fg, Cg = c->Cg, feat = c->feat;
     auto perm = [=](int ours) { return (ours % Cg) * Fg + ours / Cg; };
     const int gru_slot = slot++;
+    // fp16 inference: both recurrences and the layer-1 projection as ONE wavefront launch (gru_wave.cu)
+    const bool wave = !c->train && c->half && c->gru_persist && c->gru_wave && gru_tc_persist_supported(H) &&
+                      gru_wave_supported(H, 2);
+    PackedW wave_pw[3];  // W_hh0, W_ih1 (gate-tile order), W_hh1
     for (int l = 0; l < 2; ++l) {
         const int Kin = l == 0 ? feat : H;
         const std::string s = std::to_string(l);
-        {  // input projection for all T frames at once
+        if (wave && l == 1) {  // W_ih1 in the gate-tile order of the fused cell; no batched projection
+            PackedW pw = reserve_packed(c, 3 * H, H);
+            wave_pw[1] = pw;
+            c->packers.push_back([=](const HostParams& hp, float* arena) {
+                const std::vector<float>& w = hp.at("gru.sequence_model.weight_ih_l1");
+                const std::vector<float>& bi = hp.at("gru.sequence_model.bias_ih_l1");
+                for (int n = 0; n < 3 * H; ++n) {
+                    const int src = ((n % 96) / 32) * H + (n / 96) * 32 + n % 32;
+                    for (int k = 0; k < H; ++k) arena[pw.w_off + (size_t)n * pw.K + k] = w[(size_t)src * H + k];
+                    arena[pw.b_off + n] = bi[src];
+                }
+            });
+        } else {  // input projection for all T frames at once
             const int k_off = b.koff_dense(Kin);
             PackedW pw = reserve_packed(c, 3 * H, Kin);
             c->packers.push_back([=](const HostParams& hp, float* arena) {
@@ -1349,6 +1370,34 @@ int build_ctx(se_ctx* c) {
             }
         });
         const bool persist = fused && c->half && c->gru_persist && gru_tc_persist_supported(H);
+        if (wave) {
+            wave_pw[2 * l] = pw;
+            if (l == 1) {
+                Op op{};
+                op.kind = OP_GRU_WAVE;
+                op.stage = ST_GRU;
+                op.rows_per_stream = 1;
+                op.label = "gru.l0+l1.recurrence(wavefront)";
+                op.alg_flops = 2.0 * T * 3 * H * H * 3;          // W_hh0, W_ih1, W_hh1
+                op.alg_bytes = 22.0 * T * H;  // gi0 (fp32) read; h0 history written, read by both layers; h1 written + read (fp16)
+                op.gw = GruWaveParams{};
+                op.gw.Kp = pw.K;
+                op.gw.gi0 = c->gi_l[0];
+                op.gw.giB = (long long)T * 3 * H;
+                op.gw.hseq0 = reinterpret_cast<__half*>(c->hseq[0]);
+                op.gw.hseq1 = reinterpret_cast<__half*>(c->hseq[1]);
+                op.gw.hB = (long long)(T + 1) * H;
+                op.gw.h32_0 = c->h32[0];
+                op.gw.h32_1 = c->h32[1];
+                op.gw.H = H;
+                op.gw.T = T;
+                op.gw.layers = 2;
+                c->ops.push_back(op);
+                b.fix.push_back({wave_pw[0].w_off, wave_pw[0].b_off, -1, wave_pw[1].w_off, wave_pw[1].b_off,
+                                 wave_pw[2].w_off, wave_pw[2].b_off});
+            }
+            continue;
+        }
         if (persist) {  // the whole recurrence of the layer: one persistent tensor-core kernel (gru_tc_persist.cu)
             GemmParams gp{};
             fill_gemm_common(c, gp, pw, 3 * H, k_off);
@@ -1356,6 +1405,22 @@ int build_ctx(se_ctx* c) {
             b.meta("gru.l" + s + ".recurrence", 2.0 * T * 3 * H * H, 4.0 * T * (3 * H + 2 * H));
             b.push_gemm(ST_GRU, gp, 1, pw, k_off);
             Op& op = c->ops.back();
+            if (c->gru_wave == 2 && gru_wave_supported(H, 1)) {  // H too large for the wavefront: its one-layer form (measured
+                                                               // 151 us vs 146 us per layer at H = 512: opt-in)
+                op.kind = OP_GRU_WAVE;
+                op.gru_layer = l;
+                op.gw = GruWaveParams{};
+                op.gw.Kp = pw.K;
+                op.gw.gi0 = c->gi_l[l];
+                op.gw.giB = (long long)T * 3 * H;
+                op.gw.hseq0 = reinterpret_cast<__half*>(c->hseq[l]);
+                op.gw.hB = (long long)(T + 1) * H;
+                op.gw.h32_0 = c->h32[l];
+                op.gw.H = H;
+                op.gw.T = T;
+                op.gw.layers = 1;
+                continue;
+            }
             op.kind = OP_GRU_TC;
             op.gru_layer = l;
             op.gt = GruTcParams{};
@@ -1553,7 +1618,22 @@ int build_ctx(se_ctx* c) {
     for (size_t i = 0; i < c->ops.size(); ++i) {
         Op& op = c->ops[i];
         const OpFix& f = b.fix[i];
-        if (op.kind == OP_GRU_TC) {
+        if (op.kind == OP_GRU_WAVE) {
+            const __half* wh = reinterpret_cast<const __half*>(c->warena_h);
+            op.gw.Whh0 = wh + f.w_off;
+            op.gw.bhh0 = c->warena + f.b_off;
+            op.gw.cstride = (c->maxB + 127) / 128;
+            op.gw.counters = c->gru_counters;
+            if (op.gw.layers == 2) {
+                op.gw.Wih1 = wh + f.nw_off;
+                op.gw.bih1 = c->warena + f.nb_off;
+                op.gw.Whh1 = wh + f.nwr_off;
+                op.gw.bhh1 = c->warena + f.nbr_off;
+            } else {
+                op.gw.counters += (size_t)op.gru_layer * op.gw.cstride;
+            }
+            if (make_gru_wave_maps(&op.gw, c->maxB)) return 1;
+        } else if (op.kind == OP_GRU_TC) {
             op.gt.Whh = reinterpret_cast<const __half*>(c->warena_h) + f.w_off;
             op.gt.bhh = c->warena + f.b_off;
             op.gt.counters = c->gru_counters + (size_t)op.gru_layer * ((c->maxB + 127) / 128);
@@ -1764,6 +1844,12 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
             dm.b0 = 0;
             dm.B = B;
             return launch_dec_mma(dm, op.em_cin, op.em_cout, st);
+        }
+        case OP_GRU_WAVE: {
+            GruWaveParams gw = op.gw;
+            gw.B = B;
+            gw.b0 = 0;
+            return launch_gru_wave(gw, st);
         }
         case OP_GRU_TC: {
             GruTcParams gt = op.gt;
@@ -2635,6 +2721,10 @@ int se_debug_read(se_ctx* c, const char* name, int b, float* host_dst, int64_t m
 }
 
 
+int se_debug_gru_counters(uint64_t* out16, int reset) {
+    return gru_profile_read(reinterpret_cast<unsigned long long*>(out16), reset);
+}
+
 int se_debug_gemm_counters(uint64_t* out8, int reset) {
     static_assert(sizeof(uint64_t) == sizeof(unsigned long long), "counter width");
     return gemm_profile_read(reinterpret_cast<unsigned long long*>(out8), reset);
@@ -2736,7 +2826,7 @@ int se_crn_kernel_info(const se_ctx* c, int index, char* name, int name_cap, dou
         stg = op.stage;
         // the op table counts 4 bytes per element; in fp16 operand mode the tensors of the encoder / decoder / Linear+GLN
         // ops really are 2 bytes wide (the GRU projections keep their fp32 gi stream, the last deconv its fp32 output)
-        if (c->half && op.kind != OP_PRECONV_TC && op.kind != OP_PRECONV && op.kind != OP_GRU_TC &&
+        if (c->half && op.kind != OP_PRECONV_TC && op.kind != OP_PRECONV && op.kind != OP_GRU_TC && op.kind != OP_GRU_WAVE &&
             op.label.find("input_proj") == std::string::npos && op.label.find("step") == std::string::npos)
             by *= op.kind == OP_DECONV_LAST ? 0.75 : 0.5;
     } else if (index == n + 1) {

@@ -1228,6 +1228,22 @@ int make_gemm_tma(GemmTma* out, const void* a_base, int C, int Fp, int Tp, long 
     return 0;
 }
 
+int make_tma_3d_f16(TmaDesc* out, const void* base, int d0, int d1, int d2, long long s1, long long s2, int b0, int b1,
+                    int b2) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    SE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+    SE_REQUIRE(b0 * 2 == 128, "make_tma_3d_f16: the box must span one 128-byte swizzle row");
+    const cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)d2};
+    const cuuint64_t strides[2] = {(cuuint64_t)s1 * 2, (cuuint64_t)s2 * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, (cuuint32_t)b2};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base),
+                           dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SE_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (3-D) failed with " + std::to_string((int)r));
+    return 0;
+}
+
 int gemm_profile_read(unsigned long long* out8, int reset) {
     SE_CUDA_OK(cudaDeviceSynchronize());
     if (out8) SE_CUDA_OK(cudaMemcpyFromSymbol(out8, g_gemm_prof, 8 * sizeof(unsigned long long)));

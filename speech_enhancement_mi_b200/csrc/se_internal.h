@@ -446,6 +446,32 @@ struct GruTcParams {
 bool gru_tc_persist_supported(int H);
 int launch_gru_tc_persist(const GruTcParams& p, cudaStream_t st);
 
+// two-layer wavefront recurrence (gru_wave.cu): both layers in one launch, layer 1 one step behind layer 0 and fed by
+// h0_t directly (no batched input projection of layer 1)
+struct GruWaveParams {
+    TmaDesc h0map, h1map;  // [maxB][T+1][H] fp16 state histories, box 64 x 1 x 128 (make_gru_wave_maps)
+    const __half *Whh0, *Wih1, *Whh1;  // packed as for EPI_GRU (see GruTcParams), pitch Kp halves
+    int Kp;
+    const float *bhh0, *bih1, *bhh1;   // same row order
+    const float* gi0;      // layer-0 input projections incl. b_ih, PyTorch gate order
+    long long giB;
+    __half *hseq0, *hseq1; // slot t = operand of step t, slot t+1 = its result
+    long long hB;
+    float *h32_0, *h32_1;  // [B][H] fp32 master states, updated in place
+    int* counters;         // [2][cstride] release/acquire counters per (layer, m-tile) (zeroed by the launcher)
+    int cstride;
+    int H, T, B;
+    int layers;            // 2: wavefront over both layers; 1: one layer (the *0 fields) -- H too large for two slices
+    int b0, mtiles;        // set by the launcher: first stream / m-tiles of this launch
+};
+bool gru_wave_supported(int H, int layers);
+int make_gru_wave_maps(GruWaveParams* p, int maxB);
+int launch_gru_wave(const GruWaveParams& p, cudaStream_t st);
+int gru_profile_read(unsigned long long* out16, int reset);  // diagnostic cycle counters of the roles (-DSE_GRU_PROFILE=1)
+// 3-D tiled tensor map over fp16 data: dims (d0 fastest), strides of d1 / d2 in elements, box, SWIZZLE_128B
+int make_tma_3d_f16(TmaDesc* out, const void* base, int d0, int d1, int d2, long long s1, long long s2, int b0, int b1,
+                    int b2);
+
 // persistent small-batch GRU recurrence (gru_seq.cu): one cooperative launch per layer for all chunks and steps
 struct GruSeqParams {
     const float* Whh;  // packed [3H][Kp], rows r | z | n (PyTorch order), b_hh separately
