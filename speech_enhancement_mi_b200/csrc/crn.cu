@@ -1675,7 +1675,7 @@ int build_ctx(se_ctx* c) {
                     if (dev_alloc(c, &kdev, kc.size())) return 1;
                     SE_CUDA_OK(cudaMemcpy(kdev, kc.data(), kc.size() * sizeof(int), cudaMemcpyHostToDevice));
                     if (make_gemm_tma(&op.tma, op.tma_base, op.tma_C, op.tma_Fp, op.tma_Tp, op.tma_sT, op.tma_sB, c->maxB,
-                                      op.g.Fo, op.tma_fstep, op.g.Tn, op.g.W, op.g.K, op.g.Npad, gemm_tf32_tile_n(op.g.N)))
+                                      op.g.Fo, op.tma_fstep, op.g.Tn, op.g.W, op.g.K, op.g.Npad, gemm_tma_tile_n(op.g)))
                         return 1;
                     op.tma.t_org = op.tma_t_org;
                     op.tma.f_org = op.tma_f_org;

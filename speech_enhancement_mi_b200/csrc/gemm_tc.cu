@@ -104,8 +104,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t local_addr, uint32_t rank
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(a) : "r"(local_addr), "r"(rank));
     return a;
 }
+// RELAXED: the arrive only hands a drained TMEM accumulator back (tcgen05.wait::ld + tcgen05.fence::before_thread_sync
+// order the reads); .release at cluster scope compiles to MEMBAR.ALL.GPU, which made every epilogue thread wait for its
+// own output stores once per tile
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // tile load whose completion is counted on an mbarrier that may live in the PEER CTA of the pair (the leader's)
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* map, uint32_t bar_cluster, int c0, int c1) {
@@ -1130,10 +1133,19 @@ bool gemm_tma_supported(const GemmParams& p) {
     return gemm_tf32_tile_n(p.N) >= 32 && p.Tn * p.Fo > 0 && p.Fo <= BM;
 }
 
+// Output-tile width of the TMA path.  The short-K gated 1x1 pairs are bound by their epilogue (two sigmoid-gated columns per
+// output, statistics, stores): 128-column tiles run on four accumulators = 16 epilogue warps instead of the 8 of a
+// 256-column tile, which is worth more than reading the (short) A rows twice.
+int gemm_tma_tile_n(const GemmParams& p) {
+    const int bn = gemm_tf32_tile_n(p.N);
+    if (bn == 256 && (p.epi == EPI_GATE_STATS || p.epi == EPI_SKIP) && p.K <= 256) return 128;
+    return bn;
+}
+
 int launch_gemm_tma(const GemmParams& p, const GemmTma& tm, cudaStream_t st) {
     SE_REQUIRE(gemm_tma_supported(p), "gemm_tc: shape not supported by the TMA path");
     if (p.M <= 0) return 0;
-    switch (gemm_tf32_tile_n(p.N)) {
+    switch (gemm_tma_tile_n(p)) {
         case 32: return launch_tc_tma<32>(p, tm, st);
         case 64: return launch_tc_tma<64>(p, tm, st);
         case 128: return launch_tc_tma<128>(p, tm, st);

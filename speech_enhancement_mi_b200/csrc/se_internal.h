@@ -135,6 +135,7 @@ int launch_gemm_fp32(const GemmParams& p, cudaStream_t st);
 int launch_gemm_tf32(const GemmParams& p, cudaStream_t st);  // tcgen05 path (gemm_tc.cu)
 bool gemm_tf32_supported(const GemmParams& p);
 int gemm_tf32_tile_n(int N);  // output-tile width (BN) the tcgen05 kernel uses for N logical columns
+int gemm_tma_tile_n(const GemmParams& p);  // ... and the TMA path for this GEMM (may split 256-column tiles)
 
 // ---------------------------------------------------------------------------------------------------------------
 // GlobalLayerNorm application (CRN_ELU.py:37-56), fused with what follows it in the graph
