@@ -83,7 +83,7 @@ struct Act {  // zero-bordered channels-last activation buffer [maxB][Tp][Fp][C]
 };
 
 enum OpKind { OP_GEMM, OP_NORM, OP_GRU_PW, OP_PRECONV, OP_GRU_SEQ, OP_DECONV_LAST, OP_SKIP_SMALL, OP_GRU_TC, OP_PRECONV_TC,
-              OP_PRECONV3, OP_ENC_MMA, OP_DEC_MMA, OP_GRU_WAVE };
+              OP_PRECONV3, OP_ENC_MMA, OP_DEC_MMA, OP_GRU_WAVE, OP_ENC_TC };
 enum Stage { ST_STFT = 0, ST_PRECONV, ST_ENCODER, ST_GRU, ST_DECODER, ST_MASK, ST_ROLL, ST_COUNT };
 const char* kStageNames[ST_COUNT] = {"stft", "preconv", "encoder", "gru", "decoder", "mask_istft", "roll"};
 
@@ -242,6 +242,7 @@ struct se_ctx {
     // mma.sync with the stream resident in shared memory (front_mma.cu).  SE_B200_FRONT_MMA=0 / SE_B200_ENC_MMA=0 keep the
     // round-1 kernels (preconv_tc.cu per layer; back-to-back tcgen05 GEMM + separate GlobalLayerNorm pass).
     bool front_mma = true, enc_mma = true;
+    bool enc_tc = true;  // SE_B200_ENC_TC=0: the 16 -> 32 / 32 -> 64 encoder levels on their round-2a kernels (mma.sync / b2b GEMM)
     bool dec_mma = true;  // SE_B200_DEC_MMA=0: small-channel decoder blocks as deconv GEMM + skip-pair kernel + blend kernel
     bool use_tma = true;  // SE_B200_TMA=0: every tcgen05 GEMM keeps the cp.async gather producers
     __half* feat_h = nullptr;     // features of the chunk [maxB][21][224][8] halves (borders stay zero)
@@ -516,9 +517,11 @@ struct Builder {
         // gate fused into the conv GEMM: in registers for <= 16 channels, as a back-to-back tensor-core GEMM (fp16 operands)
         // for 32 / 64 channels (SE_B200_B2B=0 keeps those two levels on separate kernels)
         // small-channel encoder levels (fp16 mode): conv + ELU + gate + GlobalLayerNorm as ONE launch (front_mma.cu)
-        const bool use_mma = c->enc_mma && stage == ST_ENCODER && !residual && KF == 5 && KT == 3 && strideF == 2 &&
-                             dilF == 1 && Cp_out == Cout_real && in.padF0 == 2 && in.padT0 == 2 * dilT &&
-                             enc_mma_supported(Cp_in, Cout_real, in.Tp, in.Fp, Fo);
+        const bool enc_shape = stage == ST_ENCODER && !residual && KF == 5 && KT == 3 && strideF == 2 && dilF == 1 &&
+                               Cp_out == Cout_real && in.padF0 == 2 && in.padT0 == 2 * dilT && c->half && !c->train;
+        // ... as an implicit GEMM on tcgen05 over the resident input where the channel counts allow it (enc_tc.cu)
+        const bool use_tc = c->enc_tc && enc_shape && enc_tc_supported(Cp_in, Cout_real, in.Tp, in.Fp, Fo);
+        const bool use_mma = use_tc || (c->enc_mma && enc_shape && enc_mma_supported(Cp_in, Cout_real, in.Tp, in.Fp, Fo));
         const bool fuse_gate = use_mma || (tc_stage(stage) && !c->train &&
                                (Cp_out <= 16 || (c->half && c->b2b_gate && (Cout_real == 32 || Cout_real == 64))));
         const int w2_pitch = gemm_tf32_tile_n(Cout_real);
@@ -607,7 +610,7 @@ struct Builder {
                 const size_t nw_off = pack_affine(name + ".norm.weight", Cout_real, Cp_out);
                 const size_t nb_off = pack_affine(name + ".norm.bias", Cout_real, Cp_out);
                 Op op{};
-                op.kind = OP_ENC_MMA;
+                op.kind = use_tc ? OP_ENC_TC : OP_ENC_MMA;
                 op.stage = stage;
                 op.em = EncMmaParams{};
                 op.em.in = reinterpret_cast<const __half*>(in.base);
@@ -988,6 +991,7 @@ int build_ctx(se_ctx* c) {
     c->use_tma = c->use_tma && c->half && !c->train;
     if (const char* e = getenv("SE_B200_FRONT_MMA")) c->front_mma = atoi(e) != 0;
     if (const char* e = getenv("SE_B200_ENC_MMA")) c->enc_mma = atoi(e) != 0;
+    if (const char* e = getenv("SE_B200_ENC_TC")) c->enc_tc = atoi(e) != 0;
     c->front_mma = c->front_mma && c->preconv_tc;  // replaces the per-layer tensor-core kernels
     c->enc_mma = c->enc_mma && c->half && !c->train;
     if (const char* e = getenv("SE_B200_DEC_MMA")) c->dec_mma = atoi(e) != 0;
@@ -1694,7 +1698,7 @@ int build_ctx(se_ctx* c) {
             op.dm.nb = c->warena + f.nb_off;
             op.dm.nwr = c->warena + f.nwr_off;
             op.dm.nbr = c->warena + f.nbr_off;
-        } else if (op.kind == OP_ENC_MMA) {
+        } else if (op.kind == OP_ENC_MMA || op.kind == OP_ENC_TC) {
             op.em.w = c->warena + f.w_off;
             op.em.bias = c->warena + f.b_off;
             op.em.w2 = c->warena + f.w2_off;
@@ -1838,6 +1842,12 @@ int launch_op(const se_ctx* c, const Op& op, int B, cudaStream_t st, int s0 = 0)
             em.b0 = 0;
             em.B = B;
             return launch_enc_mma(em, op.em_cin, op.em_cout, st);
+        }
+        case OP_ENC_TC: {
+            EncMmaParams em = op.em;
+            em.b0 = 0;
+            em.B = B;
+            return launch_enc_tc(em, op.em_cin, op.em_cout, st);
         }
         case OP_DEC_MMA: {
             DecMmaParams dm = op.dm;

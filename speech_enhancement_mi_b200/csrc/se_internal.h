@@ -243,8 +243,12 @@ struct EncMmaParams {
     int b0, B;
     int off_y, off_wf;    // shared-memory offsets (filled by the launcher)
     uint32_t magic_Jp, magic_Fo, magic_Fp;  // ceil(2^32 / d) of the three run-time divisors (filled by the launcher)
+    int plane;            // enc_tc: 16-byte units per (parity, octet) plane (filled by the launcher)
 };
 bool enc_mma_supported(int Cin, int Cout, int Tp, int Fp, int Fo);
+// the same block as an implicit GEMM on tcgen05 over the resident input (enc_tc.cu): 16 -> 32 and 32 -> 64 channels
+bool enc_tc_supported(int Cin, int Cout, int Tp, int Fp, int Fo);
+int launch_enc_tc(const EncMmaParams& p, int Cin, int Cout, cudaStream_t st);
 int launch_enc_mma(const EncMmaParams& p, int Cin, int Cout, cudaStream_t st);
 
 // one transposed-conv decoder block with few channels in one launch (back_mma.cu; fp16 operand mode): ConvTranspose2d
