@@ -609,6 +609,29 @@ struct Builder {
             if (use_mma) {
                 const size_t nw_off = pack_affine(name + ".norm.weight", Cout_real, Cp_out);
                 const size_t nb_off = pack_affine(name + ".norm.bias", Cout_real, Cp_out);
+                size_t w1c_off = NONE, w2c_off = NONE;
+                if (use_tc) {  // the two B operands of enc_tc.cu, element for element in its shared-memory order
+                    const int CI = Cp_in, CO = Cout_real, HP = CI / 16;
+                    const size_t n1 = (size_t)15 * HP * 2 * CO * 8, n2 = (size_t)(CO / 16) * 2 * (2 * CO) * 8;
+                    w1c_off = (c->reserve_w(n1 + 8) + 7) / 8 * 8;  // 16-byte aligned in the fp16 copy of the arena (cp.async)
+                    w2c_off = (c->reserve_w(n2 + 8) + 7) / 8 * 8;
+                    c->packers.push_back([=](const HostParams& hp, float* arena) {
+                        const std::vector<float>& w = hp.at(name + ".conv.weight");  // [Co][Ci][KF][KT]
+                        const std::vector<float>& wt = hp.at(name + ".conv_trans.weight");
+                        const std::vector<float>& wg = hp.at(name + ".conv_gated.weight");
+                        for (size_t i = 0; i < n1; ++i) {
+                            const int cc = (int)(i & 7), n = (int)((i >> 3) % CO), j = (int)(((i >> 3) / CO) & 1);
+                            const int ks = (int)((i >> 3) / (2 * CO)), tap = ks / HP, hp_ = ks % HP;
+                            const int ci = (2 * hp_ + j) * 8 + cc, kt = tap / 5, kf = tap % 5;
+                            arena[w1c_off + i] = ci < Cin_real ? w[((size_t)(n * Cin_real + ci) * KF + kf) * KT + kt] : 0.f;
+                        }
+                        for (size_t i = 0; i < n2; ++i) {
+                            const int cc = (int)(i & 7), r2 = (int)((i >> 3) % (2 * CO)), j = (int)(((i >> 3) / (2 * CO)) & 1);
+                            const int ks2 = (int)((i >> 3) / (4 * CO)), kind = r2 / CO, ch = r2 % CO, k = ks2 * 16 + j * 8 + cc;
+                            arena[w2c_off + i] = kind ? 0.5f * wg[(size_t)ch * CO + k] : wt[(size_t)ch * CO + k];
+                        }
+                    });
+                }
                 Op op{};
                 op.kind = use_tc ? OP_ENC_TC : OP_ENC_MMA;
                 op.stage = stage;
@@ -634,7 +657,7 @@ struct Builder {
                 m_label.clear();
                 m_flops = m_bytes = 0;
                 c->ops.push_back(op);
-                fix.push_back({pw.w_off, pw.b_off, -1, nw_off, nb_off, NONE, NONE, w2_off, b2_off});
+                fix.push_back({pw.w_off, pw.b_off, -1, nw_off, nb_off, w1c_off, w2c_off, w2_off, b2_off});
                 return;
             }
             push_gemm(stage, g, rows, pw, k_off, w2_off, b2_off);
@@ -1699,6 +1722,10 @@ int build_ctx(se_ctx* c) {
             op.dm.nwr = c->warena + f.nwr_off;
             op.dm.nbr = c->warena + f.nbr_off;
         } else if (op.kind == OP_ENC_MMA || op.kind == OP_ENC_TC) {
+            if (op.kind == OP_ENC_TC) {
+                op.em.w1c = reinterpret_cast<const __half*>(c->warena_h) + f.nwr_off;
+                op.em.w2c = reinterpret_cast<const __half*>(c->warena_h) + f.nbr_off;
+            }
             op.em.w = c->warena + f.w_off;
             op.em.bias = c->warena + f.b_off;
             op.em.w2 = c->warena + f.w2_off;

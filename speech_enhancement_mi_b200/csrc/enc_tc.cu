@@ -172,13 +172,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) enc_tc_kernel(EncMmaParams p) {
     double* s_red = reinterpret_cast<double*>(spar + 3 * COUT);
     float* s_co = reinterpret_cast<float*>(s_red + 2 * kTcWarps);
     uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_co + 2);
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 4 * kGroups);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kGroups);
     const uint32_t x_smem = smem_u32(smem), w1_smem = smem_u32(sw1), w2_smem = smem_u32(sw2);
     const uint32_t bar0 = smem_u32(s_bar);
-    auto conv_full = [&](int g) { return bar0 + 8u * g; };
-    auto gate_full = [&](int g) { return bar0 + 8u * (kGroups + g); };
-    auto elu_ready = [&](int g) { return bar0 + 8u * (2 * kGroups + g); };
-    auto acc_free = [&](int g) { return bar0 + 8u * (3 * kGroups + g); };
+    auto acc_full = [&](int g) { return bar0 + 8u * g; };              // the MMAs into accumulator g have completed
+    auto acc_free = [&](int g) { return bar0 + 8u * (kGroups + g); };  // its epilogue group has drained it
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
 #if SE_ENC_PROFILE
@@ -188,20 +186,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) enc_tc_kernel(EncMmaParams p) {
 #endif
 
     // ---- one-time set-up -----------------------------------------------------------------------------------------
-    // conv B operand: MMA ks = (tap, octet pair hp); K chunk j = octet 2 hp + j of the tap; [ks][j][n] x 8 halves
-    for (int i = tid; i < KS * 2 * COUT * 8; i += kTcThreads) {
-        const int c = i & 7, n = (i >> 3) % COUT, j = ((i >> 3) / COUT) & 1, ks = (i >> 3) / (2 * COUT);
-        const int tap = ks / HP, hp = ks % HP;
-        const int k = tap * CIN + (2 * hp + j) * 8 + c;
-        reinterpret_cast<__half*>(sw1)[i] = __float2half_rn(__ldg(p.w + (long long)n * p.Kp + k));
+    // B operands, packed once per weight upload (crn.cu) in exactly this layout:
+    //   conv: MMA ks = (tap, octet pair hp); K chunk j = octet 2 hp + j of the tap; [ks][j][n] x 8 halves
+    //   gate: [ks2][j][n2] x 8 halves, rows [0, COUT) conv_trans, [COUT, 2 COUT) conv_gated scaled by 1/2
+    //         (sigmoid(z) = 1/2 + 1/2 tanh(z / 2))
+    for (int i = tid; i < (S::W1_BYTES + S::W2_BYTES) / 16; i += kTcThreads) {
+        const bool second = i >= S::W1_BYTES / 16;
+        const uint4* src = reinterpret_cast<const uint4*>(second ? p.w2c : p.w1c) + (second ? i - S::W1_BYTES / 16 : i);
+        cp_async16(w1_smem + 16u * (uint32_t)i, src);
     }
-    // gate B operand: rows [0, COUT) conv_trans, [COUT, 2 COUT) conv_gated scaled by 1/2 (sigmoid(z) = 1/2 + 1/2 tanh(z/2))
-    for (int i = tid; i < KS2 * 2 * (2 * COUT) * 8; i += kTcThreads) {
-        const int c = i & 7, n2 = (i >> 3) % (2 * COUT), j = ((i >> 3) / (2 * COUT)) & 1, ks2 = (i >> 3) / (4 * COUT);
-        const int kind = n2 / COUT, ch = n2 % COUT, k = ks2 * 16 + j * 8 + c;
-        const float v = __ldg(p.w2 + (long long)(2 * ch + kind) * p.w2_pitch + k) * (kind ? 0.5f : 1.f);
-        reinterpret_cast<__half*>(sw2)[i] = __float2half_rn(v);
-    }
+    cp_async_commit();
     for (int i = tid; i < COUT; i += kTcThreads) {
         spar[i] = __ldg(p.bias + i);
         spar[COUT + i] = __ldg(p.bias2 + 2 * i);
@@ -212,10 +206,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) enc_tc_kernel(EncMmaParams p) {
     for (int i = tid; i < NPL * plane + kTailUnits; i += kTcThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     if (tid == 0) {
         for (int g = 0; g < kGroups; ++g) {
-            mbar_init(conv_full(g), 1);
-            mbar_init(gate_full(g), 1);
-            mbar_init(elu_ready(g), 128);
-            mbar_init(acc_free(g), 128);
+            mbar_init(acc_full(g), 1);
+            mbar_init(acc_free(g), kMmaWarp * 32);  // every epilogue thread takes its share out of every tile
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -225,7 +217,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) enc_tc_kernel(EncMmaParams p) {
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // weights: generic-proxy stores -> MMA (async proxy)
+    cp_async_wait_all();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // weights: generic-proxy writes -> MMA (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -248,7 +241,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) enc_tc_kernel(EncMmaParams p) {
     const int MT = (T * Jp + BM - 1) / BM;
     const int Fo = p.Fo;
     const double count = (double)COUT * Fo * T;
-    uint32_t uses[kGroups] = {0, 0, 0, 0};  // tiles each accumulator group has been through (phases run on across streams)
 
     for (int stream = blockIdx.x; stream < p.B; stream += gridDim.x) {
         const int b = p.b0 + stream;
@@ -268,145 +260,131 @@ __global__ void __launch_bounds__(kTcThreads, 1) enc_tc_kernel(EncMmaParams p) {
             constexpr uint32_t idesc1 = (1u << 4) | ((uint32_t)(COUT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             constexpr uint32_t idesc2 = (1u << 4) | ((uint32_t)((2 * COUT) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
-            uint32_t uc[kGroups], ug[kGroups];
+            // Phase A: the convolutions of all tiles, streaming through the four accumulators (an accumulator is free again
+            // as soon as its ELU tile has been written); phase B, behind a CTA barrier: the gate MMAs over the ELU tiles.
+            // Keeping the two apart makes each accumulator's round trip MMA -> one epilogue, not conv -> ELU -> gate -> gate
+            // epilogue, so the tensor pipe and the epilogue warps overlap instead of waiting on one another per tile.
+            for (int i = 0; i < MT; ++i) {
+                const int g = i & (kGroups - 1);
+                // use k of an accumulator waits for the drain of use k - 1; every stream goes through an even number of uses
+                mbar_wait(acc_free(g), ((uint32_t)(i >> 2) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t a0 = x_smem + 16u * (uint32_t)(i * BM);
+                const uint32_t tacc = tb + (uint32_t)(g * S::ACC_COLS);
+                if (elect_one()) {
 #pragma unroll
-            for (int g = 0; g < kGroups; ++g) uc[g] = ug[g] = uses[g];
-            // Out-of-order issue: a gate MMA (short, it releases an epilogue group) goes out as soon as its ELU tile is
-            // ready, a conv MMA as soon as its accumulator is free; neither waits behind the other's barrier.
-            int ci = 0, gj = 0;
-            uint64_t t0 = 0;
-            uint32_t spins = 0;
-            while (gj < MT) {
-                bool did = false;
-                if (gj < ci) {
-                    const int g = gj & (kGroups - 1);
-                    if (mbar_test_warp(elu_ready(g), ug[g] & 1u)) {
-                        ++ug[g];
-                        tc_fence_after();
-                        const uint32_t a0 = x_smem + 16u * (uint32_t)(gj * BM);
-                        const uint32_t tacc = tb + (uint32_t)(g * S::ACC_COLS);
-                        if (elect_one()) {
-#pragma unroll
-                            for (int ks2 = 0; ks2 < KS2; ++ks2) {
-                                const uint64_t ad = desc_nosw(a0 + 16u * (uint32_t)(2 * ks2 * plane), 16u * (uint32_t)plane, 128u);
-                                const uint64_t bd = desc_nosw(w2_smem + (uint32_t)(ks2 * 2 * (2 * COUT) * 16), 2 * COUT * 16, 128u);
-                                tc_mma_f16(tacc, ad, bd, idesc2, ks2 ? 1u : 0u);
-                            }
-                            tc_commit(gate_full(g));
-                        }
-                        __syncwarp();
-                        ENC_EV(16 + gj);
-                        ++gj;
-                        did = true;
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const int tap = ks / HP, hp = ks % HP, kt = tap / 5, kf = tap % 5;
+                        const uint32_t unit = (uint32_t)(kt * dtJ + (kf >> 1) + ((kf & 1) * NH + 2 * hp) * plane);
+                        const uint64_t ad = desc_nosw(a0 + 16u * unit, 16u * (uint32_t)plane, 128u);
+                        const uint64_t bd = desc_nosw(w1_smem + (uint32_t)(ks * 2 * COUT * 16), COUT * 16, 128u);
+                        tc_mma_f16(tacc, ad, bd, idesc1, ks ? 1u : 0u);
                     }
+                    tc_commit(acc_full(g));
                 }
-                if (!did && ci < MT) {
-                    const int g = ci & (kGroups - 1);
-                    if (mbar_test_warp(acc_free(g), (uc[g] & 1u) ^ 1u)) {  // the group has drained its accumulator (tile ci - 4)
-                        ++uc[g];
-                        tc_fence_after();
-                        const uint32_t a0 = x_smem + 16u * (uint32_t)(ci * BM);
-                        const uint32_t tacc = tb + (uint32_t)(g * S::ACC_COLS);
-                        if (elect_one()) {
+                __syncwarp();
+                ENC_EV(i);
+            }
+            __syncthreads();  // every ELU tile is written (and fenced towards the async proxy), every conv accumulator drained
+            tc_fence_after();
+            for (int j = 0; j < MT; ++j) {
+                const int g = j & (kGroups - 1);
+                const uint32_t k = (uint32_t)((MT - g + kGroups - 1) / kGroups + (j >> 2));
+                mbar_wait(acc_free(g), (k & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t a0 = x_smem + 16u * (uint32_t)(j * BM);
+                const uint32_t tacc = tb + (uint32_t)(g * S::ACC_COLS);
+                if (elect_one()) {
 #pragma unroll
-                            for (int ks = 0; ks < KS; ++ks) {
-                                const int tap = ks / HP, hp = ks % HP, kt = tap / 5, kf = tap % 5;
-                                const uint32_t unit = (uint32_t)(kt * dtJ + (kf >> 1) + ((kf & 1) * NH + 2 * hp) * plane);
-                                const uint64_t ad = desc_nosw(a0 + 16u * unit, 16u * (uint32_t)plane, 128u);
-                                const uint64_t bd = desc_nosw(w1_smem + (uint32_t)(ks * 2 * COUT * 16), COUT * 16, 128u);
-                                tc_mma_f16(tacc, ad, bd, idesc1, ks ? 1u : 0u);
-                            }
-                            tc_commit(conv_full(g));
-                        }
-                        __syncwarp();
-                        ENC_EV(ci);
-                        ++ci;
-                        did = true;
+                    for (int ks2 = 0; ks2 < KS2; ++ks2) {
+                        const uint64_t ad = desc_nosw(a0 + 16u * (uint32_t)(2 * ks2 * plane), 16u * (uint32_t)plane, 128u);
+                        const uint64_t bd = desc_nosw(w2_smem + (uint32_t)(ks2 * 2 * (2 * COUT) * 16), 2 * COUT * 16, 128u);
+                        tc_mma_f16(tacc, ad, bd, idesc2, ks2 ? 1u : 0u);
                     }
+                    tc_commit(acc_full(g));
                 }
-                if (did) {
-                    spins = 0;
-                } else if ((++spins & 0xfffffu) == 0) {  // protocol bug: fail loudly (after ~2 s) instead of hanging the GPU
-                    const uint64_t t = global_ns();
-                    if (t0 == 0) t0 = t;
-                    else if (t - t0 > 2000000000ull) __trap();
-                }
+                __syncwarp();
+                ENC_EV(16 + j);
             }
         } else if (warp_u < kMmaWarp) {
-            // ============================ epilogue groups: thread = output row ============================
-            const int g = warp >> 2, q = warp & 3;
-            const uint32_t tconv = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * S::ACC_COLS);
-            const uint32_t tgate = tconv;  // the gate accumulator overwrites the (drained) conv accumulator
-            uint32_t use = uses[g];
-            for (int i = g; i < MT; i += kGroups, ++use) {
-                const uint32_t par = use & 1u;
+            // ============================ epilogue: thread = output row x a quarter of the channels ============================
+            // All 16 warps work on every tile: warp (q, cg) owns TMEM lanes 32 q .. 32 q + 31 (rows) and the channel
+            // quarter cg, so the tiles' epilogues are balanced whatever MT is.  Accumulator a = tile & 3.
+            constexpr int CW = COUT / kGroups;  // channels per warp and tile: 16 (two octets) or 8 (one)
+            const int q = warp & 3, cg = warp >> 2;
+            const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
+            // ---- phase A: conv accumulator -> bias, ELU -> fp16 A operand of the gate MMA, in place over the tile's rows ----
+            for (int i = 0; i < MT; ++i) {
+                const int a = i & (kGroups - 1);
+                const int r = i * BM + q * 32 + lane;
+                if (lane == 0) mbar_wait(acc_full(a), (uint32_t)(i >> 2) & 1u);
+                __syncwarp();
+                if (warp == 0) ENC_EV(32 + 8 * i + 1);
+                tc_fence_after();
+                uint32_t v[CW];
+                if (CW == 16) tmem_ld16_nowait(tq + (uint32_t)(a * S::ACC_COLS + cg * CW), v);
+                else tmem_ld8_nowait(tq + (uint32_t)(a * S::ACC_COLS + cg * CW), v);
+                tmem_ld_wait();
+                tc_fence_before();
+                mbar_arrive(acc_free(a));  // this warp's share is out of the accumulator
+                uint32_t h[CW / 2];
+#pragma unroll
+                for (int k = 0; k < CW / 2; ++k)
+                    h[k] = pack_h2(fast_elu(__uint_as_float(v[2 * k]) + spar[cg * CW + 2 * k]),
+                                   fast_elu(__uint_as_float(v[2 * k + 1]) + spar[cg * CW + 2 * k + 1]));
+                // ELU channels of row r = unit r of plane (channel / 8): the row's own input is dead by now
+#pragma unroll
+                for (int o = 0; o < CW / 8; ++o)
+                    *reinterpret_cast<uint4*>(smem + 16 * (size_t)((cg * (CW / 8) + o) * plane + r)) =
+                        make_uint4(h[4 * o], h[4 * o + 1], h[4 * o + 2], h[4 * o + 3]);
+                if (warp == 0) ENC_EV(32 + 8 * i + 2);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> gate MMAs (async proxy)
+            __syncthreads();  // phase boundary (see the MMA issuer)
+            // ---- phase B: gate accumulator -> y = trans * sigmoid(gated), statistics, fp16 in place over the same rows ----
+            for (int i = 0; i < MT; ++i) {
+                const int a = i & (kGroups - 1);
                 const int r = i * BM + q * 32 + lane;
                 const int t = div_magic(r, p.magic_Jp), fo = r - t * Jp;
                 const bool valid = t < T && fo < Fo;
-                // ---- conv accumulator -> bias, ELU -> fp16 A operand of the gate MMA ----
-                if (q == 0) ENC_EV(32 + 8 * i);
-                if (lane == 0) mbar_wait(conv_full(g), par);
+                const uint32_t k = (uint32_t)((MT - a + kGroups - 1) / kGroups + (i >> 2));  // uses of accumulator a so far
+                if (lane == 0) mbar_wait(acc_full(a), k & 1u);
                 __syncwarp();
-                if (q == 0) ENC_EV(32 + 8 * i + 1);
+                if (warp == 0) ENC_EV(32 + 8 * i + 3);
                 tc_fence_after();
-                uint32_t vb[2][16];
-                tmem_ld16_nowait(tconv, vb[0]);
-#pragma unroll
-                for (int c0 = 0; c0 < COUT; c0 += 16) {
-                    uint32_t* v = vb[(c0 >> 4) & 1];
-                    tmem_ld_wait();
-                    if (c0 + 16 < COUT) tmem_ld16_nowait(tconv + c0 + 16, vb[((c0 >> 4) + 1) & 1]);  // in flight under the math
-                    uint32_t h[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        h[k] = pack_h2(fast_elu(__uint_as_float(v[2 * k]) + spar[c0 + 2 * k]),
-                                       fast_elu(__uint_as_float(v[2 * k + 1]) + spar[c0 + 2 * k + 1]));
-                    // ELU channels c0 .. c0+15 of row r = units r of planes c0 / 8 and c0 / 8 + 1 (the row's input is dead)
-                    *reinterpret_cast<uint4*>(smem + 16 * (size_t)((c0 / 8) * plane + r)) = make_uint4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<uint4*>(smem + 16 * (size_t)((c0 / 8 + 1) * plane + r)) = make_uint4(h[4], h[5], h[6], h[7]);
+                uint32_t vt[CW], vg[CW];
+                if (CW == 16) {
+                    tmem_ld16_nowait(tq + (uint32_t)(a * S::ACC_COLS + cg * CW), vt);
+                    tmem_ld16_nowait(tq + (uint32_t)(a * S::ACC_COLS + COUT + cg * CW), vg);
+                } else {
+                    tmem_ld8_nowait(tq + (uint32_t)(a * S::ACC_COLS + cg * CW), vt);
+                    tmem_ld8_nowait(tq + (uint32_t)(a * S::ACC_COLS + COUT + cg * CW), vg);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> MMA (async proxy)
+                tmem_ld_wait();
                 tc_fence_before();
-                mbar_arrive(elu_ready(g));
-                if (q == 0) ENC_EV(32 + 8 * i + 2);
-                // ---- gate accumulator -> y = trans * sigmoid(gated), statistics, fp16 in place over the input rows ----
-                if (lane == 0) mbar_wait(gate_full(g), par);
-                __syncwarp();
-                if (q == 0) ENC_EV(32 + 8 * i + 3);
-                tc_fence_after();
+                mbar_arrive(acc_free(a));
                 const float m = valid ? 1.f : 0.f;
-                uint32_t vtb[2][8], vgb[2][8];
-                tmem_ld8_nowait(tgate, vtb[0]);
-                tmem_ld8_nowait(tgate + COUT, vgb[0]);
+                float y[CW];
 #pragma unroll
-                for (int o = 0; o < COUT / 8; ++o) {
-                    uint32_t *vt = vtb[o & 1], *vg = vgb[o & 1];
-                    tmem_ld_wait();
-                    if (o + 1 < COUT / 8) {  // in flight under the math
-                        tmem_ld8_nowait(tgate + 8 * (o + 1), vtb[(o + 1) & 1]);
-                        tmem_ld8_nowait(tgate + COUT + 8 * (o + 1), vgb[(o + 1) & 1]);
-                    }
-                    float y[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        // trans * sigmoid(gated): the gated weights and bias carry the factor 1/2 of 1/2 + 1/2 tanh(z / 2)
-                        const float th = tanh_approx(__uint_as_float(vg[k]) + spar[2 * COUT + 8 * o + k]);
-                        y[k] = m * (__uint_as_float(vt[k]) + spar[COUT + 8 * o + k]) * fmaf(0.5f, th, 0.5f);
-                        psum += y[k];
-                        psq = fmaf(y[k], y[k], psq);
-                    }
-                    if (valid)
-                        *reinterpret_cast<uint4*>(smem + 16 * (size_t)(o * plane + r)) =
-                            make_uint4(pack_h2(y[0], y[1]), pack_h2(y[2], y[3]), pack_h2(y[4], y[5]), pack_h2(y[6], y[7]));
+                for (int c = 0; c < CW; ++c) {
+                    // trans * sigmoid(gated): the gated weights and bias carry the factor 1/2 of 1/2 + 1/2 tanh(z / 2)
+                    const float th = tanh_approx(__uint_as_float(vg[c]) + spar[2 * COUT + cg * CW + c]);
+                    y[c] = m * (__uint_as_float(vt[c]) + spar[COUT + cg * CW + c]) * fmaf(0.5f, th, 0.5f);
+                    psum += y[c];
+                    psq = fmaf(y[c], y[c], psq);
                 }
-                tc_fence_before();
-                mbar_arrive(acc_free(g));
-                if (q == 0) ENC_EV(32 + 8 * i + 4);
-            }
-        }
-        // every role has been through the same tiles
+                if (valid) {
 #pragma unroll
-        for (int g = 0; g < kGroups; ++g) uses[g] += (uint32_t)((MT - g + kGroups - 1) / kGroups);
+                    for (int o = 0; o < CW / 8; ++o)
+                        *reinterpret_cast<uint4*>(smem + 16 * (size_t)((cg * (CW / 8) + o) * plane + r)) =
+                            make_uint4(pack_h2(y[8 * o], y[8 * o + 1]), pack_h2(y[8 * o + 2], y[8 * o + 3]),
+                                       pack_h2(y[8 * o + 4], y[8 * o + 5]), pack_h2(y[8 * o + 6], y[8 * o + 7]));
+                }
+                if (warp == 0) ENC_EV(32 + 8 * i + 4);
+            }
+        } else {
+            __syncthreads();  // (no such warp today: every warp is an epilogue warp or the issuer) phase boundary
+        }
         __syncthreads();
 #if SE_ENC_PROFILE
         const long long tp2 = clock64();
@@ -446,7 +424,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) enc_tc_kernel(EncMmaParams p) {
                    tp1 - tp0, tp2 - tp1, tp3 - tp2, clock64() - tp3, MT);
             if (stream == 2 * (int)gridDim.x)
                 for (int i = 0; i < MT; ++i)
-                    printf("   tile %d: conv issued %lld gate issued %lld | epi start %lld conv_full %lld elu_ready %lld gate_full %lld done %lld\n",
+                    printf("   tile %d: conv issued %lld gate issued %lld | epi1 start %lld conv done %lld ELU written %lld | gate done %lld y written %lld\n",
                            i, s_ev[i], s_ev[16 + i], s_ev[32 + 8 * i], s_ev[32 + 8 * i + 1], s_ev[32 + 8 * i + 2],
                            s_ev[32 + 8 * i + 3], s_ev[32 + 8 * i + 4]);
         }
@@ -460,6 +438,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) enc_tc_kernel(EncMmaParams p) {
     }
 }
 
+// units per plane, = 1 (mod 8): the octets of one row then sit in different bank groups for pass 2.  (Core matrices that
+// straddle 128-byte lines cost nothing: plane pitches = 0 (mod 8) measured the same MMA rate.)
 int plane_units(int Tp, int Fp) {
     int plane = Tp * ((Fp + 1) / 2);
     while (plane % 8 != 1) ++plane;
@@ -470,7 +450,7 @@ template <int CIN, int COUT>
 size_t enc_tc_bytes(int Tp, int Fp) {
     using S = TcCfg<CIN, COUT>;
     size_t off = ((size_t)S::NPL * plane_units(Tp, Fp) + kTailUnits) * 16;
-    off += S::W1_BYTES + S::W2_BYTES + 3 * COUT * 4 + 2 * kTcWarps * 8 + 8 + 4 * kGroups * 8 + 16;
+    off += S::W1_BYTES + S::W2_BYTES + 3 * COUT * 4 + 2 * kTcWarps * 8 + 8 + 2 * kGroups * 8 + 16;
     return off;
 }
 
@@ -500,9 +480,10 @@ int launch_enc_tc_t(EncMmaParams p, cudaStream_t st) {
 bool enc_tc_supported(int Cin, int Cout, int Tp, int Fp, int Fo) {
     const int Jp = (Fp + 1) / 2;
     if (Fo > Jp || (Tp - T) % 2 != 0) return false;
-    // 16 -> 32 runs too (SE_B200_ENC_TC=2), but measures 125 us against 122 us for the mma.sync kernel: the block is paced
-    // by its per-tile chain conv MMA -> ELU -> gate MMA -> gate epilogue (about 6,000 cycles, 3 tiles deep per accumulator
-    // group), not by the tensor pipe, and the mma.sync version keeps all 16 warps on the transcendentals
+    // 16 -> 32 runs too (SE_B200_ENC_TC=2) but only measures 117 us against 122 us for the mma.sync kernel, so it stays
+    // there by default.  Measured with -DSE_ENC_PROFILE=1: a no-swizzle A operand is read at ~64 B/clk (65 cycles per
+    // K = 16 MMA whatever N <= 64 is, twice the SWIZZLE_128B rate), so the conv phase costs 1,000 (16 ch) / 1,950 (32 ch)
+    // cycles per 128-row tile, and the gate phase is paced by the ~900-cycle accumulator round trip per tile.
     static const int mode = getenv("SE_B200_ENC_TC") ? atoi(getenv("SE_B200_ENC_TC")) : 1;
     if (Cin == 16 && Cout == 32) return mode == 2 && enc_tc_bytes<16, 32>(Tp, Fp) <= 227 * 1024;
     if (Cin == 32 && Cout == 64) return enc_tc_bytes<32, 64>(Tp, Fp) <= 227 * 1024;

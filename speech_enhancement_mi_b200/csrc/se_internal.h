@@ -244,6 +244,7 @@ struct EncMmaParams {
     int off_y, off_wf;    // shared-memory offsets (filled by the launcher)
     uint32_t magic_Jp, magic_Fo, magic_Fp;  // ceil(2^32 / d) of the three run-time divisors (filled by the launcher)
     int plane;            // enc_tc: 16-byte units per (parity, octet) plane (filled by the launcher)
+    const __half *w1c, *w2c;  // enc_tc: conv / gate weights as fp16 UMMA operands in shared-memory order (crn.cu packs them)
 };
 bool enc_mma_supported(int Cin, int Cout, int Tp, int Fp, int Fo);
 // the same block as an implicit GEMM on tcgen05 over the resident input (enc_tc.cu): 16 -> 32 and 32 -> 64 channels
