@@ -276,13 +276,18 @@ def test_full_size_1024_streams_replicas_match_oracle_checked_streams(precision)
     assert np.abs(big - want[perm.numpy()])[keep[perm.numpy()]].max() < tol["wave_max_abs"] * peak
 
 
-@pytest.mark.parametrize("switch", ["SE_B200_FRONT_MMA", "SE_B200_ENC_MMA", "SE_B200_TMA"])
-def test_fp16_round2_kernel_switches_match_reference(monkeypatch, switch):
-    """Round-2 kernels against the kernels they replace: the fused pre-convolutions / small-channel encoder blocks
-    (front_mma.cu, warp-level mma.sync on SMEM-resident streams) and the TMA operand delivery of the tcgen05 GEMM.  The
-    default path is covered by every other test; here each switch is turned OFF and the older path must still meet the
-    fixtures (all three configurations, incl. the carried state of a flag=True continuation)."""
-    monkeypatch.setenv(switch, "0")
+@pytest.mark.parametrize("switch,value", [("SE_B200_FRONT_MMA", "0"), ("SE_B200_ENC_MMA", "0"), ("SE_B200_TMA", "0"),
+                                          ("SE_B200_DEC_MMA", "0"), ("SE_B200_TMA_PAIR", "0"), ("SE_B200_TMA_PAIR", "2"),
+                                          ("SE_B200_GRU_WAVE", "0"), ("SE_B200_GRU_WAVE", "2"), ("SE_B200_ENC_TC", "0"),
+                                          ("SE_B200_ENC_TC", "2")])
+def test_fp16_round2_kernel_switches_match_reference(monkeypatch, switch, value):
+    """Round-2 kernels against the kernels they replace: the fused pre-convolutions / small-channel encoder and decoder
+    blocks (front_mma.cu, back_mma.cu: warp-level mma.sync on SMEM-resident streams), the TMA operand delivery and the
+    CTA-pair mode of the tcgen05 GEMM, the wavefront GRU (gru_wave.cu) and the implicit-GEMM encoder block (enc_tc.cu).
+    The default path is covered by every other test; here each switch is turned OFF (0) or to its opt-in alternative (2:
+    pair mode for every TMA GEMM, the one-layer form of the wavefront kernel, enc_tc for 16 -> 32 channels too) and that
+    path must still meet the fixtures (all three configurations, incl. the carried state of a flag=True continuation)."""
+    monkeypatch.setenv(switch, value)
     for tag in CONFIGS:
         g = load_golden(tag)
         tol = TOL["fp16"]
