@@ -220,7 +220,10 @@ __global__ void __launch_bounds__(256, MODE == 2 ? 3 : 4) norm_apply_h8_kernel(N
                         unpack8(ur[q], rr);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            const float m = __fdividef(1.0f, 1.0f + exp2f(fmaf(rm[k], ar[k], dr[k])));
+                            // one MUFU each (exp2f / __fdividef add range fix-ups around theirs; flushed results are exact)
+                            float e2, m;
+                            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e2) : "f"(fmaf(rm[k], ar[k], dr[k])));
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(m) : "f"(1.0f + e2));
                             o[k] = fmaf(m, rr[k] - o[k], o[k]);
                         }
                     }

@@ -202,9 +202,22 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
 
 // Epilogue math of the tf32 path: MUFU-based exp / reciprocal (relative error ~1e-6, two orders below the TF32 operand
 // rounding of 2^-11 that bounds this path's accuracy; the exact-mode kernels in gemm_fp32.cu keep expm1f / expf / tanhf).
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
-__device__ __forceinline__ float fast_elu(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * x)); }
+// ex2.approx.ftz / rcp.approx.ftz: one MUFU each.  __expf / __fdividef (and exp2f) add a range check and a rescale for
+// denormal results around their MUFU -- about ten instructions per sigmoid instead of four.  Flushed denormals are exact
+// zeros here: sigmoid -> 0 / 1, elu -> -1, tanh -> +-1 at the ends of their ranges.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float fast_elu(float x) { return x > 0.f ? x : ex2_ftz(1.4426950408889634f * x) - 1.0f; }
+__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - 2.0f * rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x)); }
 
 // per-stream (sum, sum of squares) of the rows a warp owns: rows are ordered by stream, so the warp holds a short
 // monotone run of stream indices; one shuffle reduction and one pair of double atomics per distinct stream

@@ -18,7 +18,11 @@ namespace {
 
 constexpr int T = kFramesPerChunk;
 
-__device__ __forceinline__ float elu_fast(float x) { return x > 0.f ? x : __expf(x) - 1.0f; }
+__device__ __forceinline__ float elu_fast(float x) {  // ex2.approx.ftz: one MUFU, no range fix-up (see gemm_tc.cu)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(1.4426950408889634f * x));
+    return x > 0.f ? x : y - 1.0f;
+}
 
 template <int N>
 __device__ __forceinline__ void load_halves(const __half* p, float* v) {  // N = 8 or 16 halves, 16-byte aligned
