@@ -144,6 +144,8 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// n / d by multiply-high with magic = ceil(2^32 / d) (exact for n < 2^32 / d); magic 0 encodes d = 1
+__device__ __forceinline__ int div_mh(int n, uint32_t magic) { return magic ? (int)__umulhi((uint32_t)n, magic) : n; }
 // One lane of the (converged) warp.  The single-thread roles run their loops WARP-UNIFORMLY and only predicate the issue
 // on this: inside an `if (lane == 0)` region ptxas treats every operand as divergent and wraps each tcgen05.mma / TMA
 // in an ELECT + R2UR.BROADCAST + BRA.U.ANY loop (about 100 cycles per MMA -- more than a 128 x 64 MMA takes to execute).
@@ -504,9 +506,11 @@ __global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
             long long w_empty = 0;
             const long long t_begin = kProf ? clock64() : 0;
             for (int tile = tfirst; tile < ntiles; tile += tstep) {
-                const int tile_m = (tile / ntn) * CS + (int)crank, n0 = (tile % ntn) * BN;
-                const int fsg = tile_m % tm.fsegs, tq = tile_m / tm.fsegs;
-                const int bgrp = tq / tm.tgroups, tgrp = tq - bgrp * tm.tgroups;
+                // exact quotients by multiply-high (divisors <= 64, dividends < 2^26): a runtime division is ~50 instructions
+                const int tdiv = div_mh(tile, tm.magic_ntn);
+                const int tile_m = tdiv * CS + (int)crank, n0 = (tile - tdiv * ntn) * BN;
+                const int tq = div_mh(tile_m, tm.magic_fsegs), fsg = tile_m - tq * tm.fsegs;
+                const int bgrp = div_mh(tq, tm.magic_tgroups), tgrp = tq - bgrp * tm.tgroups;
                 const int cb = p.b0 + bgrp * tm.bb, ct = tm.t_org + tgrp * tm.bt;
                 const int cf = tm.f_org + fsg * tm.Fs * tm.fstep;
                 for (int kb = 0; kb < nkb; ++kb) {
@@ -688,16 +692,17 @@ __global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
         for (int tile = tfirst + it * tstep; tile < ntiles; tile += it_step * tstep, it += it_step) {
             const int acc = gru ? (int)(it % NACC) : g;
             const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-            const int m0 = (tile / ntn) * BM;
-            const int n0 = (tile % ntn) * BN;
+            const int tdiv = TMA ? div_mh(tile, tm.magic_ntn) : tile / ntn;
+            const int m0 = tdiv * BM;
+            const int n0 = (tile - tdiv * ntn) * BN;
             const int m = m0 + q * 32 + lane;
             int b = -1;
             long long ooff = -1;
             int nlim = p.N;  // columns this row owns (merged-parity transposed conv: half of them on the last bin)
             if (TMA) {  // rectangular tile: row r = (stream bi, frame ti, bin f) of tile (bgrp, tgrp)
-                const int tile_m = (tile / ntn) * CS + (int)crank;
-                const int fsg = tile_m % tm.fsegs, tq = tile_m / tm.fsegs;
-                const int bgrp = tq / tm.tgroups, tgrp = tq - bgrp * tm.tgroups;
+                const int tile_m = tdiv * CS + (int)crank;
+                const int tq = div_mh(tile_m, tm.magic_fsegs), fsg = tile_m - tq * tm.fsegs;
+                const int bgrp = div_mh(tq, tm.magic_tgroups), tgrp = tq - bgrp * tm.tgroups;
                 const int r = q * 32 + lane, rpf = tm.bt * tm.Fs;
                 const int bi = r / rpf, rr = r - bi * rpf;
                 const int ti = rr / tm.Fs, f = fsg * tm.Fs + (rr - ti * tm.Fs);
@@ -1071,11 +1076,18 @@ int launch_tc(const GemmParams& p, cudaStream_t st) {
 }
 
 template <int BN>
-int launch_tc_tma(const GemmParams& p, const GemmTma& tm, cudaStream_t st) {
+int launch_tc_tma(const GemmParams& p, const GemmTma& tm_in, cudaStream_t st) {
     int g_num_sms = 0;
     if (num_sms_current_device(&g_num_sms)) return 1;
+    GemmTma tm = tm_in;  // + the multiply-high reciprocals of this launch's three tile divisors
     const int nstreams = p.M / (p.Tn * p.Fo);
     const int ntiles_m = ((nstreams + tm.bb - 1) / tm.bb) * tm.tgroups * tm.fsegs;
+    auto magic = [](int d) { return d <= 1 ? 0u : (uint32_t)(((1ull << 32) + (unsigned)d - 1) / (unsigned)d); };
+    tm.magic_ntn = magic(p.Npad / BN);
+    tm.magic_fsegs = magic(tm.fsegs);
+    tm.magic_tgroups = magic(tm.tgroups);
+    SE_REQUIRE((long long)(ntiles_m + 1) * (p.Npad / BN) < (1ll << 26) && p.Npad / BN <= 64 && tm.fsegs <= 64 && tm.tgroups <= 64,
+               "gemm_tc: tile index range of the multiply-high division");
     if (!tm.pair) {
         using S = Cfg<BN, false, 1>;
         SE_DYN_SMEM((gemm_tc_kernel<BN, __half, false, 1>), S::BYTES);

@@ -117,6 +117,7 @@ struct GemmTma {
     int Fs, fsegs;      // bins per tile and tiles per bin axis (Fs * fsegs = Fo)
     int fstep;          // input bins per output bin
     int profile;        // 1: the warp roles account their wait cycles in g_gemm_prof (diagnostic)
+    uint32_t magic_ntn, magic_fsegs, magic_tgroups;  // ceil(2^32 / d) of the tile divisors (filled by the launcher)
     int pair;           // 1: CTA-pair kernel (cta_group::2, M256 MMAs over two SMs); the weight box is half a tile
     int rows;           // bb * bt * Fs rows of the 128-row tile are real
     int tgroups;        // ceil(Tn / bt) tiles per stream group
