@@ -74,6 +74,8 @@ struct se_fsn {
     int Ksp = 0;    // sub-band input size padded to whole k-blocks (32 floats / 64 halves)
     void* warena_h = nullptr;
     std::vector<int> g_half;  // per gemm: operands are fp16
+    std::vector<GemmTma> g_tma;  // per gemm: TMA descriptors (fp16 LSTM steps), valid where g_tma_ok
+    std::vector<int> g_tma_ok;
     int* karena = nullptr;
     std::vector<int> khost;
     std::vector<std::function<void(const HostParams&, float*)>> packers;
@@ -488,11 +490,43 @@ int build(se_fsn* c) {
     if (dev_alloc(c, &c->karena, c->khost.size())) return 1;
     SE_CUDA_OK(cudaMemcpy(c->karena, c->khost.data(), c->khost.size() * sizeof(int), cudaMemcpyHostToDevice));
     if (init_fft_tables()) return 1;  // se_fsn_realtime_process frames and transforms on this device
+    c->g_tma.resize(c->gemms.size());
+    c->g_tma_ok.assign(c->gemms.size(), 0);
+    bool use_tma = true;
+    if (const char* e = getenv("SE_B200_FSN_TMA")) use_tma = atoi(e) != 0;
     for (size_t i = 0; i < c->gemms.size(); ++i) {
         c->gemms[i].W = c->g_half[i] ? static_cast<const void*>(reinterpret_cast<const __half*>(c->warena_h) + c->g_w[i])
                                      : static_cast<const void*>(c->warena + c->g_w[i]);
         c->gemms[i].bias = c->warena + c->g_b[i];
         c->gemms[i].koff = c->karena + c->g_k[i];
+        // fp16 LSTM steps of the sub-band model: TMA operand delivery + CTA pairs (gemm_tc.cu).  A row of the GEMM is one
+        // (stream, bin) sequence record; every 64-wide k-block of [x_t | h_{t-1}] is contiguous inside the record, so the
+        // A tile of a k-block is ONE 2-D box (64 halves at the block's offset x 128 consecutive records).
+        const GemmParams& g = c->gemms[i];
+        if (!(use_tma && c->g_half[i] && g.epi == EPI_LSTM && g.sB % 64 == 0)) continue;
+        GemmParams probe = g;
+        probe.M = c->g_rows[i];
+        if (!gemm_tma_supported(probe)) continue;
+        const int nkb = g.K / 64;
+        std::vector<int> kc(4 * nkb, 0);
+        bool ok = true;
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+            const int e = c->khost[c->g_k[i] + 8 * kb];
+            for (int j = 1; j < 8; ++j) ok = ok && c->khost[c->g_k[i] + 8 * kb + j] == e + 8 * j;
+            ok = ok && e % 8 == 0;
+            kc[4 * kb] = e;
+        }
+        if (!ok) continue;
+        int* kdev = nullptr;
+        if (dev_alloc(c, &kdev, kc.size())) return 1;
+        SE_CUDA_OK(cudaMemcpy(kdev, kc.data(), kc.size() * sizeof(int), cudaMemcpyHostToDevice));
+        const int nrows = c->maxB * c->g_rows[i];
+        if (make_gemm_tma(&c->g_tma[i], g.A, (int)g.sB, 1, 1, g.sB, g.sB, nrows, 1, 1, 1, g.W, g.K, g.Npad, gemm_tma_tile_n(g)))
+            return 1;
+        c->g_tma[i].t_org = 0;
+        c->g_tma[i].f_org = 0;
+        c->g_tma[i].kcoord = reinterpret_cast<const int4*>(kdev);
+        c->g_tma_ok[i] = 1;
     }
     return 0;
 }
@@ -500,6 +534,7 @@ int build(se_fsn* c) {
 int run_gemm(se_fsn* c, int i, int B, cudaStream_t st) {
     GemmParams g = c->gemms[i];
     g.M = B * c->g_rows[i];
+    if (c->g_tma_ok[i]) return launch_gemm_tma(g, c->g_tma[i], st);
     return launch_gemm_tf32(g, st);
 }
 

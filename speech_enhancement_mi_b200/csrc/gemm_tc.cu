@@ -217,9 +217,16 @@ __device__ __forceinline__ float rcp_ftz(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float fast_sigmoid(float x) { return rcp_ftz(1.0f + ex2_ftz(-1.4426950408889634f * x)); }
+// tanh.approx.f32: ONE MUFU (max relative error 2^-11, the precision of the fp16 / tf32 operands these epilogues feed);
+// sigmoid(x) = 1/2 + 1/2 tanh(x / 2).  The LSTM cell is bound by its transcendentals (3 sigmoids + 2 tanh per cell, 16
+// MUFU lanes per SM): 5 MUFU per cell instead of 10 with ex2 + rcp.
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float fast_sigmoid(float x) { return fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
 __device__ __forceinline__ float fast_elu(float x) { return x > 0.f ? x : ex2_ftz(1.4426950408889634f * x) - 1.0f; }
-__device__ __forceinline__ float fast_tanh(float x) { return 1.0f - 2.0f * rcp_ftz(1.0f + ex2_ftz(2.8853900817779268f * x)); }
 
 // per-stream (sum, sum of squares) of the rows a warp owns: rows are ordered by stream, so the warp holds a short
 // monotone run of stream indices; one shuffle reduction and one pair of double atomics per distinct stream
@@ -693,7 +700,7 @@ __global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
             const int acc = gru ? (int)(it % NACC) : g;
             const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             const int tdiv = TMA ? div_mh(tile, tm.magic_ntn) : tile / ntn;
-            const int m0 = tdiv * BM;
+            const int m0 = (TMA ? tdiv * CS + (int)crank : tdiv) * BM;  // (used by the row = sequence epilogues: LSTM)
             const int n0 = (tile - tdiv * ntn) * BN;
             const int m = m0 + q * 32 + lane;
             int b = -1;
@@ -814,7 +821,8 @@ __global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
                     tmem_ld_wait();
                     if (u0 + 8 == U) {
                         tc_fence_before();
-                        mbar_arrive(tempty_bar(acc));
+                        if (PAIR) mbar_arrive_cluster(lead_tempty0 + 8u * (uint32_t)acc);
+                        else mbar_arrive(tempty_bar(acc));
                     }
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
@@ -1154,7 +1162,8 @@ bool gemm_tf32_supported(const GemmParams& p) {
 
 bool gemm_tma_supported(const GemmParams& p) {
     if (!p.a_half || !gemm_tf32_supported(p)) return false;
-    if (p.epi == EPI_GRU || p.epi == EPI_LSTM || p.epi == EPI_ELU_GATE) return false;  // their own tile walks
+    if (p.epi == EPI_GRU || p.epi == EPI_ELU_GATE) return false;  // their own tile walks
+    if (p.epi == EPI_LSTM) return true;  // row = sequence (Tn = Fo = 1): a 128-row tile is 128 consecutive sequences
     return gemm_tf32_tile_n(p.N) >= 32 && p.Tn * p.Fo > 0 && p.Fo <= BM;
 }
 
@@ -1162,6 +1171,7 @@ bool gemm_tma_supported(const GemmParams& p) {
 // output, statistics, stores): 128-column tiles run on four accumulators = 16 epilogue warps instead of the 8 of a
 // 256-column tile, which is worth more than reading the (short) A rows twice.
 int gemm_tma_tile_n(const GemmParams& p) {
+    if (p.epi == EPI_LSTM) return p.lstm_units == 64 ? 256 : 128;  // [i | f | g | o] of 64 / 32 hidden units per tile
     const int bn = gemm_tf32_tile_n(p.N);
     if (bn == 256 && (p.epi == EPI_GATE_STATS || p.epi == EPI_SKIP) && p.K <= 256) return 128;
     return bn;
@@ -1209,7 +1219,7 @@ int make_gemm_tma(GemmTma* out, const void* a_base, int C, int Fp, int Tp, long 
         for (int t = Tn; t >= 1; --t) {
             if (Tn % t != 0 || fs * t > BM) continue;
             int b = BM / (fs * t);
-            if (b > 16) b = 16;
+            if (b > 16 && fs * t > 1) b = 16;  // (row = stream GEMMs take all 128 rows from the stream dimension)
             const int rows = fs * t * b;
             if (rows > best + best / 20) {  // a candidate later in this order must fill > 5 % more rows to win
                 best = rows;
