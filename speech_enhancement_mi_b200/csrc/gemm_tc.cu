@@ -798,21 +798,40 @@ __global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
                 }
                 __syncwarp();
             } else if ((BN == 128 || BN == 256) && p.epi == EPI_LSTM) {
-                // tile columns: [i | f | g | o] of hidden units j0 .. j0+32 (nn.LSTM gate order); 8 units per pass.
-                // c_prev = hprev (row stride hB), h' -> out (oB), c' -> out2 (o2B); Tn = Fo = 1: row = sequence
+                // tile columns: [i | f | g | o] of hidden units j0 .. j0+U (nn.LSTM gate order); 8 units per pass.
+                // c_prev = hprev (row stride hB), h' -> out (oB), c' -> out2 (o2B); Tn = Fo = 1: row = sequence.
+                // Thread = row (its TMEM lane): the four gate pre-activations of 8 units come straight out of TMEM, the cell
+                // state is two 16-byte loads / stores of the thread's own row, h' one 16-byte store (fp16) -- no transposition
+                // through shared memory, no per-cell address arithmetic (the first version spent 170 of its 443 instructions
+                // per pass on that and made the LSTM step GEMMs epilogue-bound: tools/fsn_roles.py).
                 constexpr int U = BN / 4;
-                const int j0 = (tile % ntn) * U;
-                const int ul = lane & 7;
+                const int j0 = n0 / 4;  // = (tile % ntn) * U
+                const bool ok = m < p.M;
+                const long long row = p.b0 + (ok ? m : 0);
+                const float* cin = p.hprev + row * p.hB + j0;
+                float* cout = p.out2 + row * p.o2B + j0;
+                __half* hout_h = reinterpret_cast<__half*>(p.out) + row * p.oB + j0;
+                float* hout_f = p.out + row * p.oB + j0;
+                const bool vec = ((p.hB | p.o2B) & 3) == 0 && (p.out_half ? (p.oB & 7) == 0 : (p.oB & 3) == 0) &&
+                                 ((reinterpret_cast<uintptr_t>(p.hprev) | reinterpret_cast<uintptr_t>(p.out2) |
+                                   reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
+                auto load_c = [&](int u0, float* pc) {  // c_{t-1}: independent of the MMAs, fetched one pass ahead
+                    if (vec) {
+                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 a = ok ? *reinterpret_cast<const float4*>(cin + u0) : z4;
+                        const float4 c = ok ? *reinterpret_cast<const float4*>(cin + u0 + 4) : z4;
+                        pc[0] = a.x, pc[1] = a.y, pc[2] = a.z, pc[3] = a.w, pc[4] = c.x, pc[5] = c.y, pc[6] = c.z, pc[7] = c.w;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) pc[k] = ok ? cin[u0 + k] : 0.f;
+                    }
+                };
+                float pc[8], pcn[8];
+                load_c(0, pc);
                 wait_acc();
 #pragma unroll 1
                 for (int u0 = 0; u0 < U; u0 += 8) {
-                    const int ju = j0 + u0 + ul;
-                    float pc[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int mm = m0 + q * 32 + i * 4 + (lane >> 3);
-                        pc[i] = mm < p.M ? p.hprev[(long long)(p.b0 + mm) * p.hB + ju] : 0.f;
-                    }
+                    if (u0 + 8 < U) load_c(u0 + 8, pcn);
                     uint32_t v[32];
                     tmem_ld8_nowait(tlane + u0, v);
                     tmem_ld8_nowait(tlane + U + u0, v + 8);
@@ -824,31 +843,44 @@ __global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
                         if (PAIR) mbar_arrive_cluster(lead_tempty0 + 8u * (uint32_t)acc);
                         else mbar_arrive(tempty_bar(acc));
                     }
+                    float cn[8], hv[8];
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4)
-                        *reinterpret_cast<uint4*>(srow + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-                    __syncwarp();
-                    const float bi = sbias[u0 + ul], bf = sbias[U + u0 + ul], bg = sbias[2 * U + u0 + ul],
-                                bo = sbias[3 * U + u0 + ul];
+                    for (int k = 0; k < 8; ++k) {
+                        const float ig = fast_sigmoid(__uint_as_float(v[k]) + sbias[u0 + k]);
+                        const float fg = fast_sigmoid(__uint_as_float(v[8 + k]) + sbias[U + u0 + k]);
+                        const float gg = fast_tanh(__uint_as_float(v[16 + k]) + sbias[2 * U + u0 + k]);
+                        const float og = fast_sigmoid(__uint_as_float(v[24 + k]) + sbias[3 * U + u0 + k]);
+                        cn[k] = fmaf(fg, pc[k], ig * gg);
+                        hv[k] = og * fast_tanh(cn[k]);
+                    }
+                    if (ok) {
+                        if (vec) {
+                            *reinterpret_cast<float4*>(cout + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                            *reinterpret_cast<float4*>(cout + u0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                            if (p.out_half) {
+                                const __half2 h0 = __floats2half2_rn(hv[0], hv[1]), h1 = __floats2half2_rn(hv[2], hv[3]),
+                                              h2 = __floats2half2_rn(hv[4], hv[5]), h3 = __floats2half2_rn(hv[6], hv[7]);
+                                uint4 u;
+                                u.x = *reinterpret_cast<const uint32_t*>(&h0);
+                                u.y = *reinterpret_cast<const uint32_t*>(&h1);
+                                u.z = *reinterpret_cast<const uint32_t*>(&h2);
+                                u.w = *reinterpret_cast<const uint32_t*>(&h3);
+                                *reinterpret_cast<uint4*>(hout_h + u0) = u;
+                            } else {
+                                *reinterpret_cast<float4*>(hout_f + u0) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+                                *reinterpret_cast<float4*>(hout_f + u0 + 4) = make_float4(hv[4], hv[5], hv[6], hv[7]);
+                            }
+                        } else {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int r = i * 4 + (lane >> 3);
-                        const int mm = m0 + q * 32 + r;
-                        if (mm < p.M) {
-                            const float* sr = stg + r * SPW;
-                            const float ig = fast_sigmoid(sr[ul] + bi);
-                            const float fg = fast_sigmoid(sr[8 + ul] + bf);
-                            const float gg = fast_tanh(sr[16 + ul] + bg);
-                            const float og = fast_sigmoid(sr[24 + ul] + bo);
-                            const float cn = fg * pc[i] + ig * gg;
-                            const long long bb = p.b0 + mm;
-                            p.out2[bb * p.o2B + ju] = cn;
-                            const float hv = og * fast_tanh(cn);
-                            if (p.out_half) reinterpret_cast<__half*>(p.out)[bb * p.oB + ju] = __float2half_rn(hv);
-                            else p.out[bb * p.oB + ju] = hv;
+                            for (int k = 0; k < 8; ++k) {
+                                cout[u0 + k] = cn[k];
+                                if (p.out_half) hout_h[u0 + k] = __float2half_rn(hv[k]);
+                                else hout_f[u0 + k] = hv[k];
+                            }
                         }
                     }
-                    __syncwarp();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) pc[k] = pcn[k];
                 }
             } else if (B2B && p.epi == EPI_ELU_GATE && (BN > 16 || b2b)) {
                 // conv + ELU, then the gated 1x1 pair of CRN_ELU.py:240 as a SECOND GEMM on the tensor core: this row of
