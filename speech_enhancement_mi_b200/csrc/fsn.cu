@@ -367,10 +367,11 @@ void build_lstm(se_fsn* c, const std::string& prefix, int layer, int Kin, int Ki
         g.lstm_units = U_tile;
         g.out = reinterpret_cast<float*>(reinterpret_cast<char*>(rec) + (hhist + (long long)(t + 1) * H) * esz);  // h_t
         g.oB = recB;
-        g.hprev = cbuf;  // c_{t-1}, updated in place
+        g.hprev = cbuf;  // c_{t-1}, updated in place; unit-major [H][maxB * rows_per_stream] (gemm_tc.cu EPI_LSTM)
         g.hB = H;
         g.out2 = cbuf;
         g.o2B = H;
+        g.c_rows = (long long)c->maxB * rows_per_stream;
         g.H = H;
         c->gemms.push_back(g);
         c->g_w.push_back(w_off);
@@ -741,10 +742,14 @@ int se_fsn_reset_state(se_fsn* c, int first, int count, void* stream) {
     SE_CUDA_OK(cudaMemsetAsync(reinterpret_cast<char*>(c->sbrec) + (size_t)c->recS * first * F * c->sesz, 0,
                                (size_t)c->recS * count * F * c->sesz, st));
     for (int l = 0; l < 2; ++l) {
-        SE_CUDA_OK(cudaMemsetAsync(c->fbc + ((size_t)l * c->maxB + first) * c->Hf, 0,
-                                   (size_t)count * c->Hf * sizeof(float), st));
-        SE_CUDA_OK(cudaMemsetAsync(c->sbc + ((size_t)l * c->maxB + first) * F * c->Hs, 0,
-                                   (size_t)count * F * c->Hs * sizeof(float), st));
+        // cell states are unit-major [layer][H][maxB (* F)]: the streams' columns of every unit row
+        if (count > 0) {
+            SE_CUDA_OK(cudaMemset2DAsync(c->fbc + (size_t)l * c->maxB * c->Hf + first, (size_t)c->maxB * sizeof(float), 0,
+                                         (size_t)count * sizeof(float), (size_t)c->Hf, st));
+            SE_CUDA_OK(cudaMemset2DAsync(c->sbc + (size_t)l * c->maxB * F * c->Hs + (size_t)first * F,
+                                         (size_t)c->maxB * F * sizeof(float), 0, (size_t)count * F * sizeof(float),
+                                         (size_t)c->Hs, st));
+        }
     }
     SE_CUDA_OK(cudaMemsetAsync(c->cstate + 4 * (size_t)first, 0, 4 * (size_t)count * sizeof(float), st));
     SE_CUDA_OK(cudaMemsetAsync(c->cstep + 2 * (size_t)first, 0, 2 * (size_t)count * sizeof(int), st));

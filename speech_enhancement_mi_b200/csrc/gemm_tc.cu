@@ -815,8 +815,16 @@ __global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
                 const bool vec = ((p.hB | p.o2B) & 3) == 0 && (p.out_half ? (p.oB & 7) == 0 : (p.oB & 3) == 0) &&
                                  ((reinterpret_cast<uintptr_t>(p.hprev) | reinterpret_cast<uintptr_t>(p.out2) |
                                    reinterpret_cast<uintptr_t>(p.out)) & 15) == 0;
+                // cell state of the FullSubNet models: UNIT-major [H][c_rows] (c_rows > 0), so that the 32 rows of a warp are
+                // one 128-byte line per unit instead of 32 lines per 16-byte vector (the epilogue is bound by LSU wavefronts)
+                const long long crs = p.c_rows;
+                const float* cin_t = p.hprev + (long long)j0 * crs + row;
+                float* cout_t = p.out2 + (long long)j0 * crs + row;
                 auto load_c = [&](int u0, float* pc) {  // c_{t-1}: independent of the MMAs, fetched one pass ahead
-                    if (vec) {
+                    if (crs) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) pc[k] = ok ? cin_t[(long long)(u0 + k) * crs] : 0.f;
+                    } else if (vec) {
                         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         const float4 a = ok ? *reinterpret_cast<const float4*>(cin + u0) : z4;
                         const float4 c = ok ? *reinterpret_cast<const float4*>(cin + u0 + 4) : z4;
@@ -853,10 +861,16 @@ __global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
                         cn[k] = fmaf(fg, pc[k], ig * gg);
                         hv[k] = og * fast_tanh(cn[k]);
                     }
+                    if (ok && crs) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) cout_t[(long long)(u0 + k) * crs] = cn[k];
+                    }
                     if (ok) {
                         if (vec) {
-                            *reinterpret_cast<float4*>(cout + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                            *reinterpret_cast<float4*>(cout + u0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                            if (!crs) {
+                                *reinterpret_cast<float4*>(cout + u0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                                *reinterpret_cast<float4*>(cout + u0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                            }
                             if (p.out_half) {
                                 const __half2 h0 = __floats2half2_rn(hv[0], hv[1]), h1 = __floats2half2_rn(hv[2], hv[3]),
                                               h2 = __floats2half2_rn(hv[4], hv[5]), h3 = __floats2half2_rn(hv[6], hv[7]);
@@ -873,7 +887,7 @@ __global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
                         } else {
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
-                                cout[u0 + k] = cn[k];
+                                if (!crs) cout[u0 + k] = cn[k];
                                 if (p.out_half) hout_h[u0 + k] = __float2half_rn(hv[k]);
                                 else hout_f[u0 + k] = hv[k];
                             }

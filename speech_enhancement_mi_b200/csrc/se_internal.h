@@ -96,6 +96,7 @@ struct GemmParams {
     int vec4;
     // merged-parity transposed conv: rows with f == Fo-1 own only the first N/2 columns (nothing stored / counted beyond)
     int odd_tail;
+    long long c_rows;  // EPI_LSTM: > 0 = the cell state (hprev / out2) is unit-major [H][c_rows] instead of [rows][H]
     // EPI_LSTM: hidden units per output tile (32 -> 128-column tiles, 64 -> 256-column tiles; 0 = 32).  Wider tiles
     // halve the re-reads of the [x_t | h_{t-1}] operand across the N tiles; the weight rows are packed to match.
     int lstm_units;
