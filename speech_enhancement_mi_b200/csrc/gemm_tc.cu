@@ -837,16 +837,23 @@ __global__ void __launch_bounds__(Cfg<BN, B2B, TMA>::THREADS, 1)
                 float pc[8], pcn[8];
                 load_c(0, pc);
                 wait_acc();
-#pragma unroll 1
-                for (int u0 = 0; u0 < U; u0 += 8) {
-                    if (u0 + 8 < U) load_c(u0 + 8, pcn);
-                    uint32_t v[32];
+                // gate pre-activations of pass u0 + 8 are in flight (TMEM -> registers) while pass u0 is computed
+                uint32_t vb[2][32];
+                auto load_gates = [&](int u0, uint32_t* v) {
                     tmem_ld8_nowait(tlane + u0, v);
                     tmem_ld8_nowait(tlane + U + u0, v + 8);
                     tmem_ld8_nowait(tlane + 2 * U + u0, v + 16);
                     tmem_ld8_nowait(tlane + 3 * U + u0, v + 24);
+                };
+                load_gates(0, vb[0]);
+#pragma unroll 2
+                for (int u0 = 0; u0 < U; u0 += 8) {
+                    uint32_t* v = vb[(u0 >> 3) & 1];
                     tmem_ld_wait();
-                    if (u0 + 8 == U) {
+                    if (u0 + 8 < U) {
+                        load_c(u0 + 8, pcn);
+                        load_gates(u0 + 8, vb[((u0 >> 3) + 1) & 1]);
+                    } else {  // the whole accumulator is in registers: hand it back to the MMA warp
                         tc_fence_before();
                         if (PAIR) mbar_arrive_cluster(lead_tempty0 + 8u * (uint32_t)acc);
                         else mbar_arrive(tempty_bar(acc));
