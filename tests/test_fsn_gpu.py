@@ -149,3 +149,33 @@ def test_full_config_realtime_process_matches_reference(precision):
     assert pred.shape == g["out"].shape
     assert np.abs(pred - g["out"]).max() < TOL_REL * max(1.0, np.abs(g["out"]).max())
     assert si_sdr_db(pred, g["out"]) > TOL_DB
+
+
+@pytest.mark.parametrize("precision", ["tf32", "fp16"])
+def test_partial_state_reset_touches_only_the_given_streams(precision):
+    """se_fsn_reset_state(first, count) (fullsubnet.py:826-832 for a sub-range of the streams): the LSTM cell states are
+    stored unit-major ([H][streams x bins], gemm_tc.cu EPI_LSTM), so a stream range is a strided block of every unit row.
+    Streams 1..2 are reset between two calls, streams 0 and 3 continue: the reset streams must reproduce a run from a
+    fully reset model bit for bit, the others the uninterrupted continuation."""
+    from speech_enhancement_mi_b200._native import check, lib
+    mix1, _ = synth.make_mixture(4, 6400)
+    mix2, _ = synth.make_mixture(4, 6400, first_stream=50)
+    x1, x2 = torch.from_numpy(mix1).cuda(), torch.from_numpy(mix2).cuda()
+
+    cont = make(FSN_SMALL, 11, precision=precision)
+    cont.realtime_process(x1, None, flag=False, train=False)
+    y_cont = cont.realtime_process(x2, None, flag=True, train=False).cpu().numpy()
+
+    fresh = make(FSN_SMALL, 11, precision=precision)
+    fresh.realtime_process(x1, None, flag=False, train=False)  # builds the context; state discarded below
+    fresh.reset_state(4)
+    y_fresh = fresh.realtime_process(x2, None, flag=True, train=False).cpu().numpy()
+
+    part = make(FSN_SMALL, 11, precision=precision)
+    part.realtime_process(x1, None, flag=False, train=False)
+    check(lib().se_fsn_reset_state(part._ctx, 1, 2, None), "se_fsn_reset_state")
+    y = part.realtime_process(x2, None, flag=True, train=False).cpu().numpy()
+
+    assert np.array_equal(y[[0, 3]], y_cont[[0, 3]])
+    assert np.array_equal(y[[1, 2]], y_fresh[[1, 2]])
+    assert np.abs(y_cont[1] - y_fresh[1]).max() > 1e-4  # the carried state matters, or this test would prove nothing
