@@ -161,6 +161,8 @@ def test_partial_state_reset_touches_only_the_given_streams(precision):
     mix1, _ = synth.make_mixture(4, 6400)
     mix2, _ = synth.make_mixture(4, 6400, first_stream=50)
     x1, x2 = torch.from_numpy(mix1).cuda(), torch.from_numpy(mix2).cuda()
+    # fp16 operands need 64-unit tiles (the TMA / CTA-pair path of the LSTM steps): sb_hidden 64 there
+    FSN_SMALL = dict(globals()["FSN_SMALL"], sb_hidden=64) if precision == "fp16" else globals()["FSN_SMALL"]
 
     cont = make(FSN_SMALL, 11, precision=precision)
     cont.realtime_process(x1, None, flag=False, train=False)
