@@ -189,6 +189,18 @@ int se_crn_train_forward(se_ctx* ctx, const float* mixture, int B, int64_t L, in
 /* replaces: the autograd backward from pred to the parameters (train.py:198): dpred [B,L] = d loss / d pred ->
  * grad_flat [num_theta] (overwritten; parameters the graph does not reach, CRN_ELU.py:394-397, get 0) */
 int se_crn_train_backward(se_ctx* ctx, const float* dpred, float* grad_flat, void* stream);
+/* Distillation feature taps (distillation_crn.py:343-377, 454-470): the student / teacher forward also returns five
+ * PRE-activation tensors -- last encoder conv (distillation_crn.py:198,355), GRU Linear (:140,364), and the num_levels-1
+ * gated-skip transposed convs (:253,369-371).  se_crn_train_tap reads tap k of the LAST se_crn_train_forward as
+ * [chunks*B][C][F][T] (chunk-major rows n*B+i, the reference's torch.cat(f, dim=0) order, distillation_crn.py:466);
+ * tap 1 is the Linear output merely re-shaped to (C, F, T) exactly as the reference does.  se_crn_train_backward_taps is
+ * se_crn_train_backward with d loss / d tap_k added at the same points (entries may be NULL), i.e. the autograd backward
+ * of `loss + distillation_loss(ft, fs)` (distillation_crn.py:560-565) from the student's side. */
+int se_crn_train_num_taps(const se_ctx* ctx);
+int se_crn_train_tap_shape(const se_ctx* ctx, int tap, int* C, int* F, int* T);
+int se_crn_train_tap(se_ctx* ctx, int tap, float* out, void* stream);
+int se_crn_train_backward_taps(se_ctx* ctx, const float* dpred, const float* const* dtaps, int n_taps, float* grad_flat,
+                               void* stream);
 /* replaces: compute_loss (CRN_ELU.py:513-535) with its backward: source, pred [B,L], length [B] (int32, device) ->
  * out3 (device) = {stoi_loss, cal_si_snr} = {-mean STOI-like score, mean SI-SNR dB} and their gradients w.r.t. pred
  * (d_stoi, d_sisnr: [B,L] each, device).  The caller forms loss = 0.7 * stoi + 0.3 * (-sisnr). */

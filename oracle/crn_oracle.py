@@ -137,6 +137,9 @@ class CRNOracle:
         self.buf = {}
         self.h = None
 
+    # distillation_crn.py:343-377: when a list, forward() appends the five pre-activation `feature` tensors to it
+    taps = None
+
     # -- a5: TemporalConv2d (CRN_ELU.py:230-247) --------------------------------------------------------------
     def _tconv(self, name, x, stride, dilation, pad_f, pad_t):
         w = self.w
@@ -147,6 +150,7 @@ class CRNOracle:
         inp = torch.cat([state, x], dim=-1)
         o = F.conv2d(inp, w[f"{name}.conv.weight"], w[f"{name}.conv.bias"], stride=stride, padding=(pad_f, 0),
                      dilation=dilation)
+        self._feature = o  # distillation_crn.py:198 `feature = self.net(inp)`
         o = F.elu(o)
         o = F.conv2d(o, w[f"{name}.conv_trans.weight"], w[f"{name}.conv_trans.bias"]) * torch.sigmoid(
             F.conv2d(o, w[f"{name}.conv_gated.weight"], w[f"{name}.conv_gated.bias"]))
@@ -161,6 +165,7 @@ class CRNOracle:
         T = x.shape[-1]
         o = F.conv_transpose2d(x, w[f"{name}.conv.weight"], w[f"{name}.conv.bias"], stride=(2, 1), padding=(2, 0),
                                dilation=(1, dilation_t))[..., -T:]
+        self._feature = o  # distillation_crn.py:253 `feature = out`
         o = F.elu(o)
         o = gln(o, w[f"{name}.norm.weight"], w[f"{name}.norm.bias"], self.student)
         if res is not None:
@@ -200,7 +205,9 @@ class CRNOracle:
             seq = torch.stack(outs, dim=1)
             h_out.append(h)
         self.h = torch.stack(h_out, dim=0).detach()  # CRN_ELU.py:185: detached
-        o = F.elu(seq @ w["gru.fc_output_layer.weight"].t() + w["gru.fc_output_layer.bias"])
+        o = seq @ w["gru.fc_output_layer.weight"].t() + w["gru.fc_output_layer.bias"]
+        self._feature = o  # distillation_crn.py:140 `feature = o`, [B, T, C*F]
+        o = F.elu(o)
         o = gln(o.unsqueeze(1), w["gru.norm.weight"], w["gru.norm.bias"], self.student).squeeze(1)
         return o.permute(0, 2, 1)
 
@@ -235,14 +242,21 @@ class CRNOracle:
             y = self._tconv(f"convlist.{i}", y, (2, 1), (1, d), 2, (self.kernel_size - 1) * d)
             residuals.append(y)
         B, C, Fq, T = y.shape
+        taps = self.taps
+        if taps is not None:
+            taps.append(self._feature)  # of the LAST encoder block only (distillation_crn.py:355)
         if trace is not None:
             trace["xg"] = y
         y = self._gru(y.reshape(B, C * Fq, T)).reshape(B, C, Fq, T)
+        if taps is not None:
+            taps.append(self._feature.reshape(B, C, Fq, T))  # a plain re-shape of [B, T, C*F] (distillation_crn.py:364)
         idx = -2
         for j in range(self.L - 1):
             if trace is not None:
                 trace[f"dec_in{j}"] = y
             y = self._tdeconv(f"deconvlist.{j}", y, 2 ** j, residuals[idx])
+            if taps is not None:
+                taps.append(self._feature)
             idx -= 1
         if trace is not None:
             trace[f"dec_in{self.L - 1}"] = y
@@ -265,7 +279,9 @@ class CRNOracle:
         return istft_chunk(spec.permute(0, 2, 1, 3), self.n_fft, self.hop)
 
     # -- a11: realtime_process (CRN_ELU.py:472-509) -------------------------------------------------------------
-    def realtime_process(self, mixture, flag=False):
+    def realtime_process(self, mixture, flag=False, return_features=False):
+        """return_features: also return the five feature taps, each [N*B, C, F, T] with the chunks concatenated along
+        the batch axis (distillation_crn.py:454-470)."""
         B, C, _ = mixture.shape
         P = self.K // 2
         if not flag:
@@ -274,12 +290,19 @@ class CRNOracle:
         seg, gap = segmentation(mixture, self.K)
         N = seg.shape[0] // B
         spec = self.stft_trans(seg).reshape(B, N, C, self.num_freqs, -1, 2)
-        outs = []
+        outs, feats = [], []
         for n in range(N):
+            self.taps = [] if return_features else None
             e = self.forward(spec[:, n])
+            if return_features:
+                feats.append(self.taps)
+            self.taps = None
             outs.append(self.istft_trans(e))
         y = over_add(torch.stack(outs, dim=1), gap)
-        return y if flag else y[..., P:]
+        y = y if flag else y[..., P:]
+        if return_features:
+            return y, [torch.cat([f[i] for f in feats], dim=0) for i in range(len(feats[0]))]
+        return y
 
     # -- the true-streaming step the CUDA path exposes: chunk in -> hop samples out (SURVEY.md section 3.1 probe) ---
     def stream_step(self, chunk, carry):
@@ -392,6 +415,25 @@ def compute_loss(source, pred, length):
     mae = stoi_loss(source, pred, length)
     sisnr = -cal_si_snr(pred, source, length)
     return 0.7 * mae + 0.3 * sisnr, mae, sisnr
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# f4: distillation loss (distillation_crn.py:548-564).  connectors[i] = (conv weight [Ct, Cs, 1, 1], bn weight [Ct],
+# bn bias [Ct]); BatchNorm2d in training mode = batch statistics over (N, F, T), biased variance, eps 1e-5.
+# ---------------------------------------------------------------------------------------------------------------
+def distillation_loss(ft, fs, connectors):
+    loss = 0.0
+    for t, s, (cw, bw, bb) in zip(ft, fs, connectors):
+        neg = (t < 0.0).float()
+        margin = (t * neg).sum(dim=(0, 2, 3), keepdim=True) / (neg.sum(dim=(0, 2, 3), keepdim=True) + EPS)
+        t = torch.max(t, margin)
+        s = F.conv2d(s, cw)
+        mean = s.mean(dim=(0, 2, 3), keepdim=True)
+        var = s.var(dim=(0, 2, 3), keepdim=True, unbiased=False)
+        s = (s - mean) / torch.sqrt(var + 1e-5) * bw.view(1, -1, 1, 1) + bb.view(1, -1, 1, 1)
+        mask = 1.0 - ((s <= t) & (t <= 0.0)).float()
+        loss = loss + torch.mean((s - t) ** 2 * mask)
+    return loss / len(ft)
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -168,6 +168,79 @@ def train_grads():
           "n grads", sum(1 for k in res if k.startswith("small_grad/")))
 
 
+DISTILL_TEACHER = dict(num_channels=[16, 32, 32, 48], num_freqs=201, hidden=64, num_layers=2, num_inputs=3, kernel_size=3)
+
+
+def tap_sample(x, n=4096):
+    """Every stride-th element of the flattened tensor (at most ~n of them): pins values AND layout of a large tap."""
+    flat = x.detach().reshape(-1)
+    stride = max(1, flat.numel() // n)
+    return flat[::stride].numpy().copy(), stride
+
+
+def distill():
+    """One training step of the UNMODIFIED reference DistillationCRN (distillation_crn.py:504-566): teacher and student
+    realtime_process with their feature taps, compute_loss + distillation_loss, backward.  The teacher is built without
+    `path`, so it is trainable and receives gradients through the margin / target of the distillation loss; the
+    student's same-shaped parameters alias the teacher's (distillation_crn.py:527-529).  Weights are loaded teacher
+    first, student second (the aliased tensors therefore hold the student's values).  Stores the loss scalars, pred,
+    norm + strided samples of every tap and of d loss / d student tap, norm + first 64 entries of every parameter
+    gradient, and the connector parameters (torch.manual_seed(0) initialisation) with their full gradients."""
+    import contextlib
+    import io
+    torch.manual_seed(0)
+    model = distillation_crn.DistillationCRN(segment_length=3200, dropout=0.0, **DISTILL_TEACHER)
+    wt = synth.make_crn_weights(seed=21, **DISTILL_TEACHER)
+    ws = synth.make_crn_weights(seed=22, **STUDENT)
+    model.teacher.load_state_dict({k: torch.from_numpy(v) for k, v in synth.with_alias_keys(wt).items()}, strict=True)
+    model.student.load_state_dict({k: torch.from_numpy(v) for k, v in synth.with_alias_keys(ws).items()}, strict=True)
+    model.train()
+    res = {}
+    for k, v in model.connectors.state_dict().items():
+        res["connector/" + k] = v.detach().numpy().copy()
+
+    # the same computation as DistillationCRN.forward (distillation_crn.py:560-565), unrolled only to keep the taps
+    def step(mix, src, lens, flag, tag):
+        model.zero_grad()
+        noisy, clean, length = torch.from_numpy(mix), torch.from_numpy(src), torch.tensor(lens)
+        _, ft = model.teacher.realtime_process(noisy, flag)
+        pred, fs = model.student.realtime_process(noisy, flag)
+        for f in fs:
+            f.retain_grad()
+        with contextlib.redirect_stdout(io.StringIO()):
+            loss, stoi, sisnr = model.student.compute_loss(clean, pred, length)
+        dl = model.distillation_loss(ft, fs)
+        loss = loss + dl
+        loss.backward()
+        res[tag + "loss"] = np.array([float(loss), float(stoi), float(sisnr), float(dl)])
+        res[tag + "pred"] = pred.detach().numpy()
+        for i in range(len(ft)):
+            for nm, x in (("ft", ft[i]), ("fs", fs[i]), ("dfs", fs[i].grad)):
+                smp, stride = tap_sample(x)
+                res[f"{tag}{nm}{i}_sample"] = smp
+                res[f"{tag}{nm}{i}_norm"] = np.array(float(x.detach().norm()))
+                res[f"{tag}{nm}{i}_shape"] = np.array(list(x.shape) + [stride])
+        for who in ("teacher", "student"):
+            for k, p in getattr(model, who).named_parameters():
+                if p.grad is not None:
+                    res[f"{tag}{who}_gnorm/{k}"] = np.array(float(p.grad.norm()))
+                    res[f"{tag}{who}_ghead/{k}"] = p.grad.flatten()[:64].numpy().copy()
+        for k, p in model.connectors.named_parameters():
+            res[f"{tag}connector_grad/{k}"] = p.grad.numpy().copy()
+
+    mix, src = synth.make_mixture(2, 4000)
+    step(mix, src, [4000, 3300], False, "")
+    mix2, src2 = synth.make_mixture(2, 3200, first_stream=100)
+    step(mix2, src2, [3200, 3200], True, "cont_")
+    # the forward() wrapper itself agrees with the unrolled step (no state is touched: flag=False resets)
+    with contextlib.redirect_stdout(io.StringIO()):
+        l2, s2, n2 = model(torch.from_numpy(mix), torch.from_numpy(src), torch.tensor([4000, 3300]), False)
+    assert abs(float(l2) - float(res["loss"][0])) < 1e-5 * max(1.0, abs(float(l2))), (float(l2), res["loss"])
+    res["meta"] = np.array([21, 22, 2, 4000, 3200])
+    np.savez_compressed(os.path.join(OUT, "distill.npz"), **res)
+    print("distill", res["loss"], res["cont_loss"], "taps", [tuple(res[f"fs{i}_shape"]) for i in range(5)])
+
+
 FSN_SMALL = dict(num_freqs=201, num_mics=3, fb_hidden=64, sb_hidden=32, sb_num_neighbors=15, fb_num_neighbors=0,
                  num_layers=2)
 FSN_FULL = dict(num_freqs=201, num_mics=3, fb_hidden=512, sb_hidden=384, sb_num_neighbors=15, fb_num_neighbors=0,
@@ -255,10 +328,14 @@ if __name__ == "__main__":
     if "train" in sys.argv[1:]:
         train_grads()
         sys.exit(0)
+    if "distill" in sys.argv[1:]:
+        distill()
+        sys.exit(0)
     if "fsn" not in sys.argv[1:]:
         framing()
         losses()
         train_grads()
+        distill()
         run_model(CRN_ELU.TemporalCRN, SMALL, 7, 2, 4000, "crn_small", continuation=True)
         run_model(CRN_ELU.TemporalCRN, TEACHER, 0, 2, 8000, "crn_teacher", continuation=True)
         run_model(distillation_crn.TemporalCRN, STUDENT, 3, 2, 8000, "crn_student")

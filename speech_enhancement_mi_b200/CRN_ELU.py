@@ -448,16 +448,40 @@ class TemporalCRN(nn.Module):
             check(lib().se_crn_train_forward(ctx, xd.data_ptr(), B, L, int(bool(flag)), pred.data_ptr(),
                                              self._stream_ptr(dev)), "se_crn_train_forward")
         self._fwd_gen += 1
+        self._last_chunk_streams = B * n_chunks
         return pred
 
-    def _train_backward(self, dpred):
+    def _train_backward(self, dpred, dtaps=None):
         dev = self._tctx_device
         with torch.cuda.device(dev):
             dp = dpred.detach().to(device=f"cuda:{dev}", dtype=torch.float32).contiguous()
             flat = torch.empty(lib().se_crn_num_theta(self._tctx), dtype=torch.float32, device=dp.device)
-            check(lib().se_crn_train_backward(self._tctx, dp.data_ptr(), flat.data_ptr(), self._stream_ptr(dev)),
-                  "se_crn_train_backward")
+            if dtaps is None:
+                check(lib().se_crn_train_backward(self._tctx, dp.data_ptr(), flat.data_ptr(), self._stream_ptr(dev)),
+                      "se_crn_train_backward")
+            else:  # gradients of the distillation loss injected at the feature taps (distillation_crn.py:560-565)
+                keep = [None if g is None else g.detach().to(device=dp.device, dtype=torch.float32).contiguous()
+                        for g in dtaps]
+                arr = (C.c_void_p * len(keep))(*[None if g is None else g.data_ptr() for g in keep])
+                check(lib().se_crn_train_backward_taps(self._tctx, dp.data_ptr(), arr, len(keep), flat.data_ptr(),
+                                                       self._stream_ptr(dev)), "se_crn_train_backward_taps")
         return flat, self._t_offsets
+
+    def _train_taps(self):
+        """The pre-activation feature taps of the last _train_forward, each [chunks*B, C, F, T]
+        (distillation_crn.py:343-377,466)."""
+        dev = self._tctx_device
+        taps = []
+        with torch.cuda.device(dev):
+            for k in range(lib().se_crn_train_num_taps(self._tctx)):
+                c, f, t = C.c_int(), C.c_int(), C.c_int()
+                check(lib().se_crn_train_tap_shape(self._tctx, k, C.byref(c), C.byref(f), C.byref(t)),
+                      "se_crn_train_tap_shape")
+                out = torch.empty((self._last_chunk_streams, c.value, f.value, t.value), dtype=torch.float32,
+                                  device=f"cuda:{dev}")
+                check(lib().se_crn_train_tap(self._tctx, k, out.data_ptr(), self._stream_ptr(dev)), "se_crn_train_tap")
+                taps.append(out)
+        return taps
 
     def realtime_process(self, mixture, flag=False):
         """[B, M, L] -> [B, L] (CRN_ELU.py:472-509).  One fused native call: padding, chunk grid, per-chunk STFT,

@@ -2135,6 +2135,72 @@ int train_forward(se_ctx* c, const float* mixture, int nb, long long L, int flag
     return 0;
 }
 
+// ---- distillation feature taps (distillation_crn.py:343-377) -------------------------------------------------------
+// The reference returns the PRE-activation outputs of the last encoder conv (TemporalConv2d: `feature = self.net(inp)`,
+// distillation_crn.py:198), of the GRU's Linear (`feature = o`, :140) and of the L-1 gated-skip transposed convs
+// (`feature = out`, :253).  The forward keeps only the activated tensors, so a tap is recomputed on demand by re-running
+// the layer's own GEMM over its saved input with the bias-only epilogue: same operands, same arithmetic, no extra
+// stores in the training step that does not ask for taps.  The same five points accept an injected gradient in
+// train_backward (the distillation loss's d loss / d tap).
+struct Tap {
+    const Op* op = nullptr;
+    int C = 0, Cp = 0, F = 0;
+    bool fc = false;
+};
+int tap_of(const se_ctx* c, int k, Tap& t) {
+    SE_REQUIRE(c->train, "feature taps need a context created with training = 1");
+    SE_REQUIRE(k >= 0 && k <= c->L, "feature tap index out of range (0 .. num_levels)");
+    if (k == 0) {
+        const ConvRec& r = c->conv_recs.back();
+        t.op = &c->ops[r.op_conv];
+        t.C = t.op->g.N;
+        t.Cp = r.Cp_out;
+        t.F = r.Fo;
+    } else if (k == 1) {
+        t.op = &c->ops[c->gru_rec.op_fc];
+        t.C = t.Cp = c->Cg;
+        t.F = c->Fg;
+        t.fc = true;
+    } else {
+        const DeconvRec& r = c->deconv_recs[k - 2];
+        t.op = &c->ops[r.op_deconv];
+        t.C = t.op->g.N / 2;
+        t.Cp = r.Cop;
+        t.F = r.Fy;
+    }
+    return 0;
+}
+Strides4 tap_ours(const Tap& t) {  // channels-last [Bp][T][F][Cp]
+    return Strides4{(long long)T * t.F * t.Cp, (long long)t.F * t.Cp, t.Cp, 1};
+}
+Strides4 tap_theirs(const Tap& t) {
+    // [Bp][C][F][T]; the GRU tap is the Linear's [Bp][T][C*F] memory merely RE-SHAPED to (Bp, C, F, T)
+    // (distillation_crn.py:364 `ft.reshape(B, C, F, T)`), i.e. element (t, c, f) sits at t*C*F + c*F + f
+    if (t.fc) return Strides4{(long long)T * t.C * t.F, (long long)t.C * t.F, 1, t.F};
+    return Strides4{(long long)t.C * t.F * T, 1, T, (long long)t.F * T};
+}
+int train_tap(se_ctx* c, int k, float* out, cudaStream_t st) {
+    SE_REQUIRE(c->t_have_fwd, "se_crn_train_tap: no forward pass to read");
+    Tap t;
+    if (tap_of(c, k, t)) return 1;
+    const int Bp = c->t_N * c->t_nb;
+    GemmParams g = t.op->g;
+    g.M = Bp * t.op->rows_per_stream;
+    g.epi = EPI_BIAS;
+    g.stats = nullptr;
+    g.out = c->sc[1];
+    g.out_half = 0;
+    if (run_gemm(c, g, t.op->stage, "tap." + t.op->label, st)) return 1;
+    return launch_permute4(out, tap_theirs(t), c->sc[1], tap_ours(t), Bp, T, t.F, t.C, 0, st);
+}
+// s[...] += dtaps[k] (reference layout) where s is d loss / d pre-activation in our layout
+int inject_tap(const se_ctx* c, const float* const* dtaps, int k, float* s, int Bp, cudaStream_t st) {
+    if (dtaps == nullptr || dtaps[k] == nullptr) return 0;
+    Tap t;
+    if (tap_of(c, k, t)) return 1;
+    return launch_permute4(s, tap_ours(t), dtaps[k], tap_theirs(t), Bp, T, t.F, t.C, 1, st);
+}
+
 float* garena_of(const se_ctx* c, const void* w) {
     return c->garena + (reinterpret_cast<const float*>(w) - c->warena);
 }
@@ -2177,7 +2243,7 @@ int gln_bwd(se_ctx* c, const NormApplyParams& n, int B, int F, const float* y, c
     return launch_gln_bwd(p, st);
 }
 
-int train_backward(se_ctx* c, const float* dpred, float* grad_flat, cudaStream_t st) {
+int train_backward(se_ctx* c, const float* dpred, const float* const* dtaps, float* grad_flat, cudaStream_t st) {
     SE_REQUIRE(c->t_have_fwd, "se_crn_train_backward: no forward pass to differentiate");
     const int nb = c->t_nb, N = c->t_N, Bp = N * nb, H = c->H, L = c->L, feat = c->feat;
     SE_CUDA_OK(cudaMemsetAsync(c->garena, 0, c->warena_floats * sizeof(float), st));
@@ -2261,6 +2327,7 @@ int train_backward(se_ctx* c, const float* dpred, float* grad_flat, cudaStream_t
             // main norm backward fused with the ELU backward -> s1 = d loss / d deconv pre-activation
             const StridedRows os{(long long)T * r.Fy * C, (long long)r.Fy * C, C};
             if (gln_bwd(c, n, Bp, r.Fy, r.y, n.stats, n.count, n.w, s0, os, s1, C, 1, 0, 1, st)) return 1;
+            if (inject_tap(c, dtaps, 2 + j, s1, Bp, st)) return 1;
         }
         if (dense_bwd(c, dop, Bp, s1, ys, r.in->dbase, st)) return 1;
     }
@@ -2274,6 +2341,7 @@ int train_backward(se_ctx* c, const float* dpred, float* grad_flat, cudaStream_t
         if (gln_bwd(c, nop.n, Bp, c->Fg, c->fcraw, nop.n.stats, nop.n.count, nop.n.w, d0.dinterior(), gs, s1, c->Cg, 1, 0, 1,
                     st))
             return 1;
+        if (inject_tap(c, dtaps, 1, s1, Bp, st)) return 1;
         const StridedRows fs{(long long)T * feat, feat, 0};
         if (dense_bwd(c, fop, Bp, s1, fs, c->dH[1] + H, st)) return 1;
         const StridedRows g3{(long long)T * 3 * H, 3LL * H, 0};
@@ -2364,6 +2432,7 @@ int train_backward(se_ctx* c, const float* dpred, float* grad_flat, cudaStream_t
         const StridedRows g2{(long long)T * r.Fo * 2 * C, (long long)r.Fo * 2 * C, 2LL * C};
         if (dense_bwd(c, gop, Bp, s1, g2, s2, st)) return 1;
         if (launch_elu_bwd(s2, r.e, rows * C, st)) return 1;
+        if (i == (int)c->conv_recs.size() - 1 && inject_tap(c, dtaps, 0, s2, Bp, st)) return 1;
         const StridedRows g1{(long long)T * r.Fo * C, (long long)r.Fo * C, C};
         if (dense_bwd(c, cop, Bp, s2, g1, r.need_dgrad ? r.in->dbase : nullptr, st)) return 1;
     }
@@ -2830,7 +2899,33 @@ int se_crn_train_forward(se_ctx* c, const float* mixture, int B, int64_t L, int 
 int se_crn_train_backward(se_ctx* c, const float* dpred, float* grad_flat, void* stream) {
     if (check_ready(c, 0, true)) return 1;
     SE_REQUIRE(dpred != nullptr && grad_flat != nullptr, "se_crn_train_backward: null buffer");
-    return train_backward(c, dpred, grad_flat, (cudaStream_t)stream);
+    return train_backward(c, dpred, nullptr, grad_flat, (cudaStream_t)stream);
+}
+
+int se_crn_train_num_taps(const se_ctx* c) { return (c && c->train) ? c->L + 1 : 0; }
+
+int se_crn_train_tap_shape(const se_ctx* c, int tap, int* C_out, int* F_out, int* T_out) {
+    SE_REQUIRE(c != nullptr && C_out && F_out && T_out, "se_crn_train_tap_shape: null argument");
+    Tap t;
+    if (tap_of(c, tap, t)) return 1;
+    *C_out = t.C;
+    *F_out = t.F;
+    *T_out = T;
+    return 0;
+}
+
+int se_crn_train_tap(se_ctx* c, int tap, float* out, void* stream) {
+    if (check_ready(c, 0, true)) return 1;
+    SE_REQUIRE(out != nullptr, "se_crn_train_tap: null buffer");
+    return train_tap(c, tap, out, (cudaStream_t)stream);
+}
+
+int se_crn_train_backward_taps(se_ctx* c, const float* dpred, const float* const* dtaps, int n_taps, float* grad_flat,
+                               void* stream) {
+    if (check_ready(c, 0, true)) return 1;
+    SE_REQUIRE(dpred != nullptr && grad_flat != nullptr, "se_crn_train_backward_taps: null buffer");
+    SE_REQUIRE(dtaps == nullptr || n_taps == c->L + 1, "se_crn_train_backward_taps: one gradient slot per feature tap");
+    return train_backward(c, dpred, dtaps, grad_flat, (cudaStream_t)stream);
 }
 
 int se_crn_launches_per_chunk(const se_ctx* c) { return c ? count_launches(c) : 0; }

@@ -406,6 +406,13 @@ int launch_elu_bwd(float* de, const float* e, long long n, cudaStream_t st);
 // dst(b,t,f,c) += src(b,t,f,c) over [B][T][F][C] with independent strides (residual path of the pre-convolutions)
 int launch_add_strided(float* dst, StridedRows d, const float* src, StridedRows s, int B, int T, int F, int C,
                        cudaStream_t st);
+// dst(b,t,f,c) = [add ? dst(b,t,f,c) : 0] + src(b,t,f,c) over [B][T][F][C], every axis with its own stride on both sides
+// (feature taps of the distillation loss: channels-last activations <-> the reference's [B][C][F][T] tensors)
+struct Strides4 {
+    long long sB, sT, sF, sC;
+};
+int launch_permute4(float* dst, Strides4 d, const float* src, Strides4 s, int B, int T, int F, int C, int add,
+                    cudaStream_t st);
 // GRU cell backward for one step (PyTorch gate order r,z,n): dh = dH + dhrec; writes dgi, dgh (3H each) and dhrec := dh*z
 int launch_gru_bwd_pw(const float* gi, long long giB, const float* gh, long long ghB, const float* hprev, long long hB,
                       const float* dH, long long dHB, float* dhrec, float* dgi, float* dgh, long long dgB, int B, int H,

@@ -334,6 +334,36 @@ __global__ void __launch_bounds__(kThreads) add_strided_kernel(float* dst, Strid
     }
 }
 
+// destination-contiguous order when the destination is channels-last, i.e. c fastest (the injection direction); the
+// export direction (destination [C][F][T]) walks t fastest: the flag picks the index decomposition
+__global__ void __launch_bounds__(kThreads) permute4_kernel(float* __restrict__ dst, Strides4 d,
+                                                            const float* __restrict__ src, Strides4 s, int B, int T,
+                                                            int F, int C, int add, int t_fastest) {
+    const long long total = (long long)B * T * F * C;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int b, t, f, c;
+        if (t_fastest) {
+            t = (int)(i % T);
+            long long r = i / T;
+            f = (int)(r % F);
+            r /= F;
+            c = (int)(r % C);
+            b = (int)(r / C);
+        } else {
+            c = (int)(i % C);
+            long long r = i / C;
+            f = (int)(r % F);
+            r /= F;
+            t = (int)(r % T);
+            b = (int)(r / T);
+        }
+        const float v = src[b * s.sB + t * s.sT + f * s.sF + c * s.sC];
+        float* o = dst + b * d.sB + t * d.sT + f * d.sF + c * d.sC;
+        *o = add ? *o + v : v;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) gru_bwd_pw_kernel(const float* __restrict__ gi, long long giB,
                                                               const float* __restrict__ gh, long long ghB,
                                                               const float* __restrict__ hprev, long long hB,
@@ -466,6 +496,15 @@ int launch_add_strided(float* dst, StridedRows d, const float* src, StridedRows 
                        cudaStream_t st) {
     if (B <= 0) return 0;
     add_strided_kernel<<<grid_for((long long)B * T * F * C), kThreads, 0, st>>>(dst, d, src, s, B, T, F, C);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_permute4(float* dst, Strides4 d, const float* src, Strides4 s, int B, int T, int F, int C, int add,
+                    cudaStream_t st) {
+    if (B <= 0) return 0;
+    permute4_kernel<<<grid_for((long long)B * T * F * C), kThreads, 0, st>>>(dst, d, src, s, B, T, F, C, add,
+                                                                           d.sT == 1 ? 1 : 0);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -62,3 +62,30 @@ def rel_err(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+DISTILL_TEACHER = dict(num_channels=[16, 32, 32, 48], num_freqs=201, hidden=64, num_layers=2, num_inputs=3, kernel_size=3)
+
+
+def distill_weights():
+    """Teacher (seed 21) and student (seed 22) weights of tests/golden/distill.npz after the reference's parameter
+    aliasing (distillation_crn.py:527-529: parameters are zipped in registration order and a student parameter with the
+    teacher's shape SHARES its storage; the fixture loads the teacher first, so both end up with the student's values)."""
+    wt = synth.make_crn_weights(seed=21, **DISTILL_TEACHER)
+    ws = synth.make_crn_weights(seed=22, **STUDENT)
+    for kt, ks in zip(wt, ws):
+        if wt[kt].shape == ws[ks].shape:
+            wt[kt] = ws[ks].copy()
+    return wt, ws
+
+
+def distill_setup(g):
+    """Oracle teacher / student, the connector parameters stored in the fixture and the first piece's data."""
+    wt, ws = distill_weights()
+    teacher = CRNOracle({k: torch.from_numpy(v) for k, v in wt.items()}, segment_length=3200, student=True,
+                        **DISTILL_TEACHER)
+    student = CRNOracle({k: torch.from_numpy(v) for k, v in ws.items()}, segment_length=3200, student=True, **STUDENT)
+    connectors = [(torch.from_numpy(g[f"connector/{i}.0.weight"]), torch.from_numpy(g[f"connector/{i}.1.weight"]),
+                   torch.from_numpy(g[f"connector/{i}.1.bias"])) for i in range(5)]
+    mix, src = synth.make_mixture(2, 4000)
+    return teacher, student, connectors, (mix, src, [4000, 3300])
