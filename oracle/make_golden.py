@@ -198,6 +198,8 @@ def distill():
     res = {}
     for k, v in model.connectors.state_dict().items():
         res["connector/" + k] = v.detach().numpy().copy()
+    # the checkpoint surface predict_distillation.py:33-34 loads: every state_dict key with its shape
+    res["state_keys"] = np.array([f"{k}:{'x'.join(str(d) for d in v.shape)}" for k, v in model.state_dict().items()])
 
     # the same computation as DistillationCRN.forward (distillation_crn.py:560-565), unrolled only to keep the taps
     def step(mix, src, lens, flag, tag):

@@ -68,7 +68,7 @@ class Processor:
         self.name = args.name
         self.stage_dir = os.path.join(self.config["config"]["checkpoint_dir"], "denoise", args.user_defined_name)
         torch.manual_seed(self.config["config"]["seed"])
-        self.model = getattr(CRN_ELU, self.name)(**self.config[self.name])
+        self.model = self.build_model()
         self.epoch, self.train_step, self.dev_step, self.last_loss = -1, 0, 0, 1e8
         dn = self.config["denoise"]
         self.lr, self.accum = float(dn["lr"]), int(dn["gradient_accumulation"])
@@ -95,6 +95,15 @@ class Processor:
                                               betas=(0.9, 0.999))
         self.scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, mode="min", factor=0.5, patience=2,
                                                                     min_lr=1e-7)
+
+    def build_model(self):
+        return getattr(CRN_ELU, self.name)(**self.config[self.name])
+
+    def step_loss(self, mixture, source, length, flag):
+        """train.py:195-196 on the drop-in model (autograd engine and every dev pass): (loss, stoi, sisnr) tensors."""
+        pred = self.model.realtime_process(mixture, flag)
+        with contextlib.redirect_stdout(io.StringIO()):
+            return self.model.compute_loss(source[:, 0], pred, length)
 
     # ---- train.py:76-126 -----------------------------------------------------------------------------------------
     def save_modules(self, with_model):
@@ -140,9 +149,7 @@ class Processor:
                 loss, mae, sisnr = self.trainer.train_step(mixture, source[:, 0].contiguous(), length, data["flag"])
             elif mode == "train":
                 self.model.train()
-                pred = self.model.realtime_process(mixture, data["flag"])
-                with contextlib.redirect_stdout(io.StringIO()):
-                    loss_t, mae, sisnr = self.model.compute_loss(source[:, 0], pred, length)
+                loss_t, mae, sisnr = self.step_loss(mixture, source, length, data["flag"])
                 (loss_t / self.accum).backward()
                 if (n + 1) % self.accum == 0:
                     torch.nn.utils.clip_grad_norm_((p for p in self.model.parameters() if p.requires_grad),
@@ -151,11 +158,9 @@ class Processor:
                     self.optimizer.zero_grad()
                 loss = float(loss_t)
             else:
-                self.model.eval()
+                self.eval_mode()
                 with torch.no_grad():
-                    pred = self.model.realtime_process(mixture, data["flag"])
-                    with contextlib.redirect_stdout(io.StringIO()):
-                        loss_t, mae, sisnr = self.model.compute_loss(source[:, 0], pred, length)
+                    loss_t, mae, sisnr = self.step_loss(mixture, source, length, data["flag"])
                 loss = float(loss_t)
             total += loss
             n += 1
@@ -164,6 +169,9 @@ class Processor:
             else:
                 self.dev_step += 1
         return total / max(n, 1)
+
+    def eval_mode(self):
+        self.model.eval()
 
     def train(self, resume=False):
         if resume:

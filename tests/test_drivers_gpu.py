@@ -62,3 +62,36 @@ def test_native_and_autograd_engines_take_the_same_first_step(tmp_path):
     for k in out["native"]:
         a, b = out["native"][k], out["autograd"][k]
         assert (a - b).abs().max() <= 2e-5, k  # lr 3e-4: one Adam step moves every weight by at most 3e-4
+
+
+def test_distillation_driver_trains_and_serves_the_student(tmp_path):
+    """train_distillation.py:126-215 equivalent (teacher + student + connectors through the native autograd nodes), its
+    checkpoint, and the predict_distillation.py:32-38,84 flow: load with strict=False, move to the CPU, run
+    ``model.student.realtime_process`` on a CPU mixture in eval mode."""
+    from speech_enhancement_mi_b200 import distillation_crn, train_distillation
+    from speech_enhancement_mi_b200.data_synth import SyntheticPartyDataset
+    cfg = _config(tmp_path)
+    train_distillation.main(["DistillationCRN", cfg, "--steps", "4", "--items", "4", "--epochs", "1"])
+    stage = tmp_path / "modules" / "distillation" / "model"
+    for name in ("DistillationCRN.pth", "optimizer.pth", "scheduler.pth", "Epoch.pth"):
+        assert (stage / name).exists(), name
+    sd = torch.load(stage / "DistillationCRN.pth")
+    assert any(k.startswith("teacher.") for k in sd) and any(k.startswith("student.") for k in sd)
+    assert "connectors.0.0.weight" in sd and "connectors.4.1.running_mean" in sd
+    with open(cfg) as f:
+        full = yaml.safe_load(f)
+    kw = full["TemporalCRN"]
+    torch.manual_seed(full["config"]["seed"])  # the driver's initialisation (train.py:52)
+    before = {k: v.clone() for k, v in distillation_crn.DistillationCRN(**kw).student.state_dict().items()}
+    model = distillation_crn.DistillationCRN(**kw).cuda()
+    model.load_state_dict(sd, strict=False)
+    moved = sum(1 for k, v in model.student.state_dict().items()
+                if v.shape == before[k].shape and not torch.equal(v.cpu(), before[k]))
+    assert moved > 50  # the optimizer steps reached the student
+    model = model.cpu().eval()
+    data = SyntheticPartyDataset(size=2, max_length=30000, num_mic=3)
+    data.set_attribute("test")
+    mix = data[0]["mix"][None]
+    with torch.no_grad():
+        separated, feats = model.student.realtime_process(mix, flag=False)
+    assert feats == [] and separated.shape == (1, mix.shape[-1]) and bool(torch.isfinite(separated).all())
