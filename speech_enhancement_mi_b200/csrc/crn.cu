@@ -2539,6 +2539,7 @@ int64_t se_crn_state_bytes_per_stream(const se_ctx* c) {
 
 int se_crn_process_chunk(se_ctx* c, const float* in, int64_t in_stream_stride, int64_t in_mic_stride, float* out,
                          int64_t out_stream_stride, int B, void* stream) {
+    NvtxRange nvtx_range("se.chunk_step");
     if (check_ready(c, B)) return 1;
     SE_REQUIRE(in != nullptr && out != nullptr, "se_crn_process_chunk: null buffer");
     if (B == 0) return 0;
@@ -2556,6 +2557,7 @@ int se_chunk_grid(int64_t L, int K, int* gap, int* n_chunks) {
 }
 
 int se_crn_realtime_process(se_ctx* c, const float* mixture, int B, int64_t L, int flag, float* out, void* stream) {
+    NvtxRange nvtx_range("se.realtime_process");
     if (check_ready(c, B)) return 1;
     SE_REQUIRE(mixture != nullptr && out != nullptr, "se_crn_realtime_process: null buffer");
     SE_REQUIRE(L > 0, "se_crn_realtime_process: empty signal");
@@ -2589,6 +2591,7 @@ int se_crn_realtime_process(se_ctx* c, const float* mixture, int B, int64_t L, i
 }
 
 int se_crn_realtime_process_host(se_ctx* c, const float* mixture, int B, int64_t L, int flag, float* out) {
+    NvtxRange nvtx_range("se.realtime_process_host");
     if (check_ready(c, B)) return 1;
     const size_t nin = (size_t)B * 3 * L, nout = (size_t)B * L;
     if (c->h_in_floats < nin) {
@@ -2662,6 +2665,7 @@ int se_istft_trans(se_ctx* c, const float* spec, int R, float* out, void* stream
 }
 
 int se_crn_forward_chunk(se_ctx* c, const float* spec_in, float* spec_out, int B, void* stream) {
+    NvtxRange nvtx_range("se.forward_chunk");
     if (check_ready(c, B)) return 1;
     SE_REQUIRE(spec_in != nullptr && spec_out != nullptr, "se_crn_forward_chunk: null buffer");
     if (B == 0) return 0;
@@ -2890,6 +2894,7 @@ int se_crn_bind_weights_flat(se_ctx* c, const float* theta, void* stream) {
 }
 
 int se_crn_train_forward(se_ctx* c, const float* mixture, int B, int64_t L, int flag, float* pred, void* stream) {
+    NvtxRange nvtx_range("se.train_forward");
     if (check_ready(c, 0, true)) return 1;
     SE_REQUIRE(mixture != nullptr && pred != nullptr, "se_crn_train_forward: null buffer");
     SE_REQUIRE(B > 0 && L > 0, "se_crn_train_forward: empty batch");
@@ -2897,6 +2902,7 @@ int se_crn_train_forward(se_ctx* c, const float* mixture, int B, int64_t L, int 
 }
 
 int se_crn_train_backward(se_ctx* c, const float* dpred, float* grad_flat, void* stream) {
+    NvtxRange nvtx_range("se.train_backward");
     if (check_ready(c, 0, true)) return 1;
     SE_REQUIRE(dpred != nullptr && grad_flat != nullptr, "se_crn_train_backward: null buffer");
     return train_backward(c, dpred, nullptr, grad_flat, (cudaStream_t)stream);
@@ -2915,6 +2921,7 @@ int se_crn_train_tap_shape(const se_ctx* c, int tap, int* C_out, int* F_out, int
 }
 
 int se_crn_train_tap(se_ctx* c, int tap, float* out, void* stream) {
+    NvtxRange nvtx_range("se.train_tap");
     if (check_ready(c, 0, true)) return 1;
     SE_REQUIRE(out != nullptr, "se_crn_train_tap: null buffer");
     return train_tap(c, tap, out, (cudaStream_t)stream);
@@ -2922,6 +2929,7 @@ int se_crn_train_tap(se_ctx* c, int tap, float* out, void* stream) {
 
 int se_crn_train_backward_taps(se_ctx* c, const float* dpred, const float* const* dtaps, int n_taps, float* grad_flat,
                                void* stream) {
+    NvtxRange nvtx_range("se.train_backward_taps");
     if (check_ready(c, 0, true)) return 1;
     SE_REQUIRE(dpred != nullptr && grad_flat != nullptr, "se_crn_train_backward_taps: null buffer");
     SE_REQUIRE(dtaps == nullptr || n_taps == c->L + 1, "se_crn_train_backward_taps: one gradient slot per feature tap");
@@ -3012,6 +3020,8 @@ static int time_filter(se_ctx* c, int filter, int kernel, int B, int iters, floa
         if (scratch) cudaFree(scratch);
         SE_CUDA_OK(cudaMalloc(&scratch, need * sizeof(float)));
         SE_CUDA_OK(cudaMemset(scratch, 0, need * sizeof(float)));
+        // noise-like chunk content (the arithmetic of the STFT / feature kernel is not data independent: atan2 branches)
+        if (launch_fill_noise(scratch, (long long)B * 3 * KCHUNK, 0.3f, st)) return 1;
         scratch_floats = need;
     }
     IoDesc io{scratch, 3LL * KCHUNK, KCHUNK, 0, KCHUNK, scratch + (size_t)B * 3 * KCHUNK, PHOP, PHOP};

@@ -284,6 +284,16 @@ __global__ void __launch_bounds__(256) roll_kernel(RollTable tab, int first, int
 
 __global__ void set_io_kernel(IoDesc* dst, IoDesc v) { *dst = v; }
 
+__global__ void __launch_bounds__(256) fill_noise_kernel(float* __restrict__ x, long long n, float amp) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + (uint32_t)(i >> 32) * 40503u;
+        h ^= h >> 15;
+        h *= 2246822519u;
+        h ^= h >> 13;
+        x[i] = amp * ((float)(h >> 8) * (1.0f / 8388608.0f) - 1.0f);
+    }
+}
+
 // utility.py:339-370 -- chunk n of stream b is row b*N+n = padded[n*P : n*P+K], padded = [P zeros | x | gap | P zeros]
 __global__ void __launch_bounds__(256) segmentation_kernel(const float* __restrict__ x, int B, int C, long long L,
                                                            int K, int N, float* __restrict__ out) {
@@ -374,6 +384,15 @@ static int roll_or_zero(const RollTable& tab_in, int first, int B, int zero, cud
 }
 int launch_roll(const RollTable& tab, int first, int B, cudaStream_t st) { return roll_or_zero(tab, first, B, 0, st); }
 int launch_zero(const RollTable& tab, int first, int B, cudaStream_t st) { return roll_or_zero(tab, first, B, 1, st); }
+
+int launch_fill_noise(float* x, long long n, float amp, cudaStream_t st) {
+    if (n <= 0) return 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    fill_noise_kernel<<<(int)blocks, 256, 0, st>>>(x, n, amp);
+    SE_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 int launch_set_io(IoDesc* dst, const IoDesc& v, cudaStream_t st) {
     set_io_kernel<<<1, 1, 0, st>>>(dst, v);

@@ -757,6 +757,7 @@ int se_fsn_reset_state(se_fsn* c, int first, int count, void* stream) {
 }
 
 int se_fsn_forward_chunk(se_fsn* c, const float* x, float* out, int B, void* stream) {
+    NvtxRange nvtx_range("se.fsn_forward_chunk");
     SE_REQUIRE(c != nullptr && c->weights_bound, "se_fsn_forward_chunk: context without weights");
     SE_REQUIRE(x != nullptr && out != nullptr, "se_fsn_forward_chunk: null buffer");
     SE_REQUIRE(B >= 0 && B <= c->maxB, "se_fsn_forward_chunk: B exceeds max_streams");
@@ -769,6 +770,7 @@ int se_fsn_forward_chunk(se_fsn* c, const float* x, float* out, int B, void* str
 
 int se_fsn_realtime_process(se_fsn* c, const float* mixture, const float* source, int B, int64_t L, int flag, int train,
                             float* pred, float* crm_out, float* s_out, float* x0_out, void* stream) {
+    NvtxRange nvtx_range("se.fsn_realtime_process");
     SE_REQUIRE(c != nullptr && c->weights_bound, "se_fsn_realtime_process: context without weights");
     SE_REQUIRE(mixture != nullptr && pred != nullptr && L > 0, "se_fsn_realtime_process: null buffer");
     SE_REQUIRE(B >= 1 && B <= c->maxB, "se_fsn_realtime_process: B exceeds max_streams");

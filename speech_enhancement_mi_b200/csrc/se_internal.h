@@ -3,10 +3,21 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <nvtx3/nvToolsExt.h>  // header-only (the tools library is dlopen'ed when a profiler is attached)
 
 #include <string>
 
 namespace se {
+
+// NVTX range over a C-ABI call (nsys / ncu --nvtx time lines: "se.chunk_step", "se.train_forward", ...).  Costs a
+// few nanoseconds when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 
 constexpr int kFramesPerChunk = 21;  // T = 1 + K/hop for K=3200, hop=160 (reference: torch.stft center=True)
 
@@ -298,6 +309,8 @@ struct RollTable {
     int first_block[25];  // filled by the launcher: blocks [first_block[i], first_block[i+1]) serve entry i
 };
 int launch_roll(const RollTable& tab, int first, int B, cudaStream_t st);
+// x[i] = amp * u_i, u_i a hash of i in [-1, 1) (synthetic chunk content for the per-kernel timers)
+int launch_fill_noise(float* x, long long n, float amp, cudaStream_t st);
 int launch_zero(const RollTable& tab, int first, int B, cudaStream_t st);  // zero [dst_off, dst_off+count)
 
 // ---------------------------------------------------------------------------------------------------------------
