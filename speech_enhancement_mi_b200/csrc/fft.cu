@@ -32,9 +32,43 @@ constexpr int ROW = 21;             // padded row length (float2) of the 20x20 i
 __constant__ float2 c_w20[20];    // exp(-2 pi i j / 20)
 // tables indexed per thread live in global memory: a warp reading 32 different words of a __constant__ array is served
 // one word at a time (the constant cache broadcasts, it does not gather)
-__device__ float2 c_w400[400];  // exp(-2 pi i j / 400)
-__device__ float c_window[NFFT];
+__device__ __align__(16) float2 c_w400[400];  // exp(-2 pi i j / 400)  (16-byte aligned: cp.async source)
+__device__ __align__(16) float c_window[NFFT];
 __device__ float c_env[K];  // sum_t w^2 at output positions (istft window envelope, trimmed)
+
+// 16-byte asynchronous copy into shared memory; src_bytes < 16 zero-fills the rest (0: nothing is read)
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(src), "r"(src_bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all_groups() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+// Branch-free atan2 for the fp16 feature layout (the result is rounded to fp16, 11 significant bits: absolute error
+// >= 5e-4 for |phase| >= 1).  Odd minimax polynomial of degree 9 on [0, 1] (Hastings; |error| <= 1.1e-5 rad), octant
+// folding by selects.  atan2(+-0, x < 0) = +-pi and atan2(0, 0) = 0 as in the exact function.
+__device__ __forceinline__ float fast_atan2(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = __fdividef(mn, fmaxf(mx, 1e-37f));
+    const float q = a * a;
+    float r = fmaf(q, 0.0208351f, -0.0851330f);
+    r = fmaf(q, r, 0.1801410f);
+    r = fmaf(q, r, -0.3302995f);
+    r = fmaf(q, r, 0.9998660f);
+    r *= a;
+    r = ay > ax ? 1.57079632679f - r : r;
+    r = x < 0.f ? 3.14159265359f - r : r;
+    return copysignf(r, y);
+}
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -65,22 +99,38 @@ __global__ void __launch_bounds__(448, 2) stft_features_kernel(StftParams p) {
     const int t0 = blockIdx.y * GROUP;
     const int M = p.M;  // <= 3 per pass set (host guarantees M == 3 for the feature path)
 
-    for (int i = tid; i < NFFT; i += blockDim.x) {
-        s.win[i] = c_window[i];
-        s.w400[i] = c_w400[i];
-    }
+    // Everything the block needs arrives by cp.async (16-byte units, zero fill where the frame window leaves the chunk
+    // or the caller's signal) and is awaited ONCE: element-wise loads through registers exposed a DRAM round trip per
+    // loop iteration -- half of the kernel's time (profiles/r02_ncu_stft_before_cpasync.txt).
+    for (int i = tid; i < NFFT / 4; i += blockDim.x) cp_async16_zfill(&s.win[4 * i], &c_window[4 * i], 16u);
+    for (int i = tid; i < NFFT / 2; i += blockDim.x) cp_async16_zfill(&s.w400[2 * i], &c_w400[2 * i], 16u);
     if (tid < 20) s.w20[tid] = c_w20[tid];
     const int brow = p.nb > 0 ? b % p.nb : b;  // training layout: stream = chunk * nb + utterance
     const float* in = p.io->in + brow * p.io->in_stream_stride;
     const long long mic_stride = p.io->in_mic_stride;
     const long long in_off = p.io->in_offset + (p.nb > 0 ? (long long)(b / p.nb) * p.hop_chunk : 0), in_len = p.io->in_len;
-    for (int m = 0; m < M; ++m) {
-        for (int i = tid; i < SPAN; i += blockDim.x) {
-            const int n = t0 * HOP + i - NFFT / 2;  // sample index inside the chunk (center=True zero padding)
-            const long long j = in_off + n;         // index inside the caller's signal (segmentation zero padding)
-            s.xs[m][i] = (n >= 0 && n < K && j >= 0 && j < in_len) ? in[m * mic_stride + j] : 0.f;
+    // sample i of the span is chunk sample n = t0*HOP + i - NFFT/2 (center=True zero padding outside [0, K)) = signal
+    // sample j = in_off + n (segmentation zero padding outside [0, in_len)); n of a 4-sample unit starts at a multiple of 4
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)(mic_stride * 4) | (uintptr_t)(in_off * 4)) & 15) == 0;
+    if (vec_ok) {
+        for (int u = tid; u < M * (SPAN / 4); u += blockDim.x) {
+            const int m = u / (SPAN / 4), i = 4 * (u - m * (SPAN / 4));
+            const int n = t0 * HOP + i - NFFT / 2;
+            const long long j = in_off + n;
+            long long left = (n >= 0 && n < K && j >= 0) ? in_len - j : 0;  // valid samples from j on
+            left = left < 0 ? 0 : (left > 4 ? 4 : left);
+            cp_async16_zfill(&s.xs[m][i], in + m * mic_stride + (left > 0 ? j : 0), (uint32_t)left * 4u);
+        }
+    } else {
+        for (int m = 0; m < M; ++m) {
+            for (int i = tid; i < SPAN; i += blockDim.x) {
+                const int n = t0 * HOP + i - NFFT / 2;
+                const long long j = in_off + n;
+                s.xs[m][i] = (n >= 0 && n < K && j >= 0 && j < in_len) ? in[m * mic_stride + j] : 0.f;
+            }
         }
     }
+    cp_async_wait_all_groups();
     __syncthreads();
 
     // exp(-2 pi i j / 20) = (kC20[j], kS20[j]); both DFT stages are fully unrolled so that every twiddle is an immediate
@@ -174,12 +224,21 @@ __global__ void __launch_bounds__(448, 2) stft_features_kernel(StftParams p) {
             const int fr = o / NBIN;
             const int t = t0 + fr;
             float mag[3], ph[3];
+            if (p.feat_h8 != nullptr && !p.student) {  // fp16 feature layout: approximations far below the fp16 rounding
 #pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                const float2 v = s.spec[m][fr][k];
-                mag[m] = sqrtf(v.x * v.x + v.y * v.y + 1e-10f);  // CRN_ELU.py:372
-                ph[m] = p.student ? atanf(v.y / (v.x + 1e-8f) + 1e-8f)  // distillation_crn.py:340
-                                  : atan2f(v.y, v.x);                   // CRN_ELU.py:370
+                for (int m = 0; m < 3; ++m) {
+                    const float2 v = s.spec[m][fr][k];
+                    mag[m] = fast_sqrt(fmaf(v.x, v.x, fmaf(v.y, v.y, 1e-10f)));
+                    ph[m] = fast_atan2(v.y, v.x);
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 3; ++m) {
+                    const float2 v = s.spec[m][fr][k];
+                    mag[m] = sqrtf(v.x * v.x + v.y * v.y + 1e-10f);  // CRN_ELU.py:372
+                    ph[m] = p.student ? atanf(v.y / (v.x + 1e-8f) + 1e-8f)  // distillation_crn.py:340
+                                      : atan2f(v.y, v.x);                   // CRN_ELU.py:370
+                }
             }
             if (p.feat_h8 != nullptr) {
                 const __half2 h0 = __floats2half2_rn(mag[0], mag[1]), h1 = __floats2half2_rn(mag[2], ph[0] - ph[1]),
