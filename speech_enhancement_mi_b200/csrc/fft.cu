@@ -78,12 +78,14 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// STFT + features.  grid = (B, 3): block (b, g) handles frames [7g, 7g+7) of all microphones of stream b.
+// STFT + features.  Work item (b, g) = frames [7g, 7g+7) of all microphones of stream b; a persistent grid of two blocks
+// per SM walks the items, and the samples of a block's NEXT item are in flight (cp.async into the other half of a double
+// buffer) while it transforms the current one.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int SPAN = (GROUP - 1) * HOP + NFFT;  // 1360 padded samples cover 7 frames
 
 struct StftSmem {
-    float xs[3][SPAN];              // raw samples (zero outside the chunk), up to 3 mics per pass set
+    float xs[2][3][SPAN];           // raw samples (zero outside the chunk), up to 3 mics per pass set; double buffer
     float win[NFFT];
     float2 w20[20];
     float2 w400[400];
@@ -95,43 +97,55 @@ __global__ void __launch_bounds__(448, 2) stft_features_kernel(StftParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     StftSmem& s = *reinterpret_cast<StftSmem*>(smem_raw);
     const int tid = threadIdx.x;
-    const int b = blockIdx.x;
-    const int t0 = blockIdx.y * GROUP;
     const int M = p.M;  // <= 3 per pass set (host guarantees M == 3 for the feature path)
+    const int nitems = p.B * (T / GROUP);
 
-    // Everything the block needs arrives by cp.async (16-byte units, zero fill where the frame window leaves the chunk
-    // or the caller's signal) and is awaited ONCE: element-wise loads through registers exposed a DRAM round trip per
-    // loop iteration -- half of the kernel's time (profiles/r02_ncu_stft_before_cpasync.txt).
+    // Everything a block needs arrives by cp.async (16-byte units, zero fill where the frame window leaves the chunk or
+    // the caller's signal): element-wise loads through registers exposed a DRAM round trip per loop iteration -- half of
+    // the kernel's time in round 1 (profiles/r02_stft_regions.txt).
     for (int i = tid; i < NFFT / 4; i += blockDim.x) cp_async16_zfill(&s.win[4 * i], &c_window[4 * i], 16u);
     for (int i = tid; i < NFFT / 2; i += blockDim.x) cp_async16_zfill(&s.w400[2 * i], &c_w400[2 * i], 16u);
     if (tid < 20) s.w20[tid] = c_w20[tid];
-    const int brow = p.nb > 0 ? b % p.nb : b;  // training layout: stream = chunk * nb + utterance
-    const float* in = p.io->in + brow * p.io->in_stream_stride;
-    const long long mic_stride = p.io->in_mic_stride;
-    const long long in_off = p.io->in_offset + (p.nb > 0 ? (long long)(b / p.nb) * p.hop_chunk : 0), in_len = p.io->in_len;
+    const long long stream_stride = p.io->in_stream_stride, mic_stride = p.io->in_mic_stride, in_len = p.io->in_len;
+    const float* in_base = p.io->in;
+    const long long in_offset = p.io->in_offset;
     // sample i of the span is chunk sample n = t0*HOP + i - NFFT/2 (center=True zero padding outside [0, K)) = signal
     // sample j = in_off + n (segmentation zero padding outside [0, in_len)); n of a 4-sample unit starts at a multiple of 4
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)(mic_stride * 4) | (uintptr_t)(in_off * 4)) & 15) == 0;
-    if (vec_ok) {
-        for (int u = tid; u < M * (SPAN / 4); u += blockDim.x) {
-            const int m = u / (SPAN / 4), i = 4 * (u - m * (SPAN / 4));
-            const int n = t0 * HOP + i - NFFT / 2;
-            const long long j = in_off + n;
-            long long left = (n >= 0 && n < K && j >= 0) ? in_len - j : 0;  // valid samples from j on
-            left = left < 0 ? 0 : (left > 4 ? 4 : left);
-            cp_async16_zfill(&s.xs[m][i], in + m * mic_stride + (left > 0 ? j : 0), (uint32_t)left * 4u);
-        }
-    } else {
-        for (int m = 0; m < M; ++m) {
-            for (int i = tid; i < SPAN; i += blockDim.x) {
+    auto fetch = [&](int item, int buf) {
+        const int b = item / (T / GROUP), t0 = (item % (T / GROUP)) * GROUP;
+        const int brow = p.nb > 0 ? b % p.nb : b;  // training layout: stream = chunk * nb + utterance
+        const float* in = in_base + brow * stream_stride;
+        const long long in_off = in_offset + (p.nb > 0 ? (long long)(b / p.nb) * p.hop_chunk : 0);
+        const bool vec_ok =
+            ((reinterpret_cast<uintptr_t>(in) | (uintptr_t)(mic_stride * 4) | (uintptr_t)(in_off * 4)) & 15) == 0;
+        if (vec_ok) {
+            for (int u = tid; u < M * (SPAN / 4); u += blockDim.x) {
+                const int m = u / (SPAN / 4), i = 4 * (u - m * (SPAN / 4));
                 const int n = t0 * HOP + i - NFFT / 2;
                 const long long j = in_off + n;
-                s.xs[m][i] = (n >= 0 && n < K && j >= 0 && j < in_len) ? in[m * mic_stride + j] : 0.f;
+                long long left = (n >= 0 && n < K && j >= 0) ? in_len - j : 0;  // valid samples from j on
+                left = left < 0 ? 0 : (left > 4 ? 4 : left);
+                cp_async16_zfill(&s.xs[buf][m][i], in + m * mic_stride + (left > 0 ? j : 0), (uint32_t)left * 4u);
+            }
+        } else {
+            for (int m = 0; m < M; ++m) {
+                for (int i = tid; i < SPAN; i += blockDim.x) {
+                    const int n = t0 * HOP + i - NFFT / 2;
+                    const long long j = in_off + n;
+                    s.xs[buf][m][i] = (n >= 0 && n < K && j >= 0 && j < in_len) ? in[m * mic_stride + j] : 0.f;
+                }
             }
         }
-    }
+    };
+    if ((int)blockIdx.x < nitems) fetch(blockIdx.x, 0);
+    int buf = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, buf ^= 1) {
+    const int b = item / (T / GROUP), t0 = (item % (T / GROUP)) * GROUP;
+    // this item's samples have landed; every thread is past the previous item's output phase (s.spec, s.y reusable) and
+    // past its stage 1 (the other sample buffer is free for the prefetch)
     cp_async_wait_all_groups();
     __syncthreads();
+    if (item + (int)gridDim.x < nitems) fetch(item + gridDim.x, buf ^ 1);
 
     // exp(-2 pi i j / 20) = (kC20[j], kS20[j]); both DFT stages are fully unrolled so that every twiddle is an immediate
     constexpr float kC20[20] = {1.0f, 0.951056516f, 0.809016994f, 0.587785252f, 0.309016994f, 0.0f, -0.309016994f, -0.587785252f, -0.809016994f, -0.951056516f, -1.0f, -0.951056516f, -0.809016994f, -0.587785252f, -0.309016994f, 0.0f, 0.309016994f, 0.587785252f, 0.809016994f, 0.951056516f};
@@ -142,7 +156,7 @@ __global__ void __launch_bounds__(448, 2) stft_features_kernel(StftParams p) {
         const int n2 = u % 20;
         const int fr = (u / 20) % GROUP;
         const int m = u / (20 * GROUP);
-        const float* x = &s.xs[m][fr * HOP];
+        const float* x = &s.xs[buf][m][fr * HOP];
         float v[20];
 #pragma unroll
         for (int n1 = 0; n1 < 20; ++n1) v[n1] = x[20 * n1 + n2] * s.win[20 * n1 + n2];
@@ -260,6 +274,7 @@ __global__ void __launch_bounds__(448, 2) stft_features_kernel(StftParams p) {
             reinterpret_cast<float2*>(p.noisy)[((long long)b * T + t) * NBIN + k] = s.spec[0][fr][k];
         }
     }
+    }  // items
 }
 
 // features from a reference-layout spectrum (TemporalCRN.forward entry, CRN_ELU.py:369-373)
@@ -607,7 +622,13 @@ int launch_stft_features(const StftParams& p, cudaStream_t st) {
     SE_REQUIRE((p.feat == nullptr && p.feat_h8 == nullptr) || p.M == 3,
                "stft features need exactly 3 microphones (CRN_ELU.py:369-373)");
     if (p.B == 0) return 0;
-    stft_features_kernel<<<dim3(p.B, T / GROUP), 448, sizeof(StftSmem), st>>>(p);  // 420 (mic, frame, n2) units per stage: one round, 28 warps per SM
+    // 420 (mic, frame, n2) units per stage: one round of a block's 448 threads; two blocks per SM (28 warps) walk the
+    // B x 3 items, stream-major (the three frame groups of a stream share 240 + 240 input samples through L2)
+    int num_sms = 0;
+    if (num_sms_current_device(&num_sms)) return 1;
+    const int nitems = p.B * (T / GROUP);
+    const int grid = nitems < 2 * num_sms ? nitems : 2 * num_sms;
+    stft_features_kernel<<<grid, 448, sizeof(StftSmem), st>>>(p);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
