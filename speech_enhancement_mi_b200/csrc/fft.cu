@@ -85,10 +85,10 @@ __device__ __forceinline__ float2 cmul_conj(float2 a, float2 b) {  // a * conj(b
 constexpr int SPAN = (GROUP - 1) * HOP + NFFT;  // 1360 padded samples cover 7 frames
 
 struct StftSmem {
-    float xs[2][3][SPAN];           // raw samples (zero outside the chunk), up to 3 mics per pass set; double buffer
-    float win[NFFT];
+    alignas(16) float xs[2][3][SPAN];  // raw samples (zero outside the chunk), up to 3 mics per pass set; double buffer
+    alignas(16) float win[NFFT];
     float2 w20[20];
-    float2 w400[400];
+    alignas(16) float2 w400[400];
     float2 y[3][GROUP][11][ROW];    // stage-1 output rows k1 = 0..10 (the rest by Hermitian symmetry), before the twiddle
     float2 spec[3][GROUP][NBIN + 1];
 };
@@ -321,14 +321,22 @@ __global__ void __launch_bounds__(256) features_from_spec_kernel(const float* __
 // ------------------------------------------------------------------------------------------------------------
 // mask + iSTFT + overlap-add.  grid = B, one block per stream; frames processed in 3 groups of 7.
 // ------------------------------------------------------------------------------------------------------------
+constexpr int ISTFT_STAGE_UNITS = (GROUP * NBIN * 8 + 15) / 16 + 1;  // 16-byte units covering 7 frames of float2 bins from an 8-byte aligned start
 struct IstftSmem {
-    float2 spec[GROUP][NBIN + 1];
+    union {  // the spectrum is dead once stage A has produced z; the windowed frames are written after that
+        float2 spec[GROUP][NBIN + 1];
+        float frames[GROUP][NFFT];
+    };
     float2 z[GROUP][11][ROW];
-    float frames[GROUP][NFFT];
     float ola[NFFT + HOP * (T - 1)];  // 3600
-    float win[NFFT];
+    alignas(16) float win[NFFT];     // cp.async destinations: 16-byte aligned
     float2 w20[20];
-    float2 w400[400];
+    alignas(16) float2 w400[400];
+    // staging of one frame group of the mask pre-activation and of the noisy spectrum (cp.async; the next group is in
+    // flight while the current one is transformed), and of the carried half chunk
+    uint4 stage_y[ISTFT_STAGE_UNITS];
+    uint4 stage_x[ISTFT_STAGE_UNITS];
+    alignas(16) float carry[K / 2];
 };
 
 __device__ __forceinline__ float decompress_cirm(float m) {  // utility.py:439-442
@@ -347,9 +355,38 @@ __global__ void __launch_bounds__(256, 3) mask_istft_kernel(MaskIstftParams p) {
     const int tid = threadIdx.x;
     const int b = blockIdx.x;
 
-    for (int i = tid; i < NFFT; i += blockDim.x) {
-        s.win[i] = c_window[i];
-        s.w400[i] = c_w400[i];
+    // Global data arrives by cp.async and is awaited once per frame group: the per-bin loads of the mask / spectrum and
+    // the carried half chunk used to expose a DRAM round trip per loop iteration (55 % of the kernel's samples).
+    const bool staged = p.spec_in == nullptr;
+    const float2* gy = reinterpret_cast<const float2*>(p.y) + (long long)b * T * NBIN;
+    const float2* gx = reinterpret_cast<const float2*>(p.noisy) + (long long)b * T * NBIN;
+    // group g = float2 elements [g*7*201, (g+1)*7*201) of the stream: copied in 16-byte units from the aligned address
+    // at or below its first element (`skew` = 0 or 1 float2 of lead-in; the unit after the last element stays inside
+    // the stream's block or the next stream's -- the last stream of the buffer is clamped)
+    auto stage_group = [&](int g) {
+        const float2* y0 = gy + g * GROUP * NBIN;
+        const float2* x0 = gx + g * GROUP * NBIN;
+        const int sky = (int)((reinterpret_cast<uintptr_t>(y0) >> 3) & 1), skx = (int)((reinterpret_cast<uintptr_t>(x0) >> 3) & 1);
+        const int need_y = (GROUP * NBIN + sky + 1) / 2, need_x = (GROUP * NBIN + skx + 1) / 2;  // units holding data
+        for (int i = tid; i < need_y; i += blockDim.x) {
+            // the last unit may reach one float2 past the group: only past the END OF THE TENSOR is that out of bounds
+            const bool tail = (i == need_y - 1) && (((GROUP * NBIN + sky) & 1) != 0) && b == p.B - 1 && g == T / GROUP - 1;
+            cp_async16_zfill(&s.stage_y[i], reinterpret_cast<const uint4*>(y0 - sky) + i, tail ? 8u : 16u);
+        }
+        for (int i = tid; i < need_x; i += blockDim.x) {
+            const bool tail = (i == need_x - 1) && (((GROUP * NBIN + skx) & 1) != 0) && b == p.B - 1 && g == T / GROUP - 1;
+            cp_async16_zfill(&s.stage_x[i], reinterpret_cast<const uint4*>(x0 - skx) + i, tail ? 8u : 16u);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    for (int i = tid; i < NFFT / 4; i += blockDim.x) cp_async16_zfill(&s.win[4 * i], &c_window[4 * i], 16u);
+    for (int i = tid; i < NFFT / 2; i += blockDim.x) cp_async16_zfill(&s.w400[2 * i], &c_w400[2 * i], 16u);
+    if (staged) stage_group(0);
+    const bool carry_vec = p.carry != nullptr && (reinterpret_cast<uintptr_t>(p.carry) & 15) == 0;
+    if (carry_vec) {
+        const float* c = p.carry + (long long)b * (K / 2);
+        for (int i = tid; i < K / 8; i += blockDim.x) cp_async16_zfill(&s.carry[4 * i], c + 4 * i, 16u);
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
     if (tid < 20) s.w20[tid] = c_w20[tid];
     for (int i = tid; i < NFFT + HOP * (T - 1); i += blockDim.x) s.ola[i] = 0.f;
@@ -369,10 +406,15 @@ __global__ void __launch_bounds__(256, 3) mask_istft_kernel(MaskIstftParams p) {
         b0 = p.b[0];
         b1 = p.b[1];
     }
-    __syncthreads();
 
     for (int g = 0; g < T / GROUP; ++g) {
         const int t0 = g * GROUP;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // staged group g (and, the first time, tables / carry) visible; previous group's frames consumed
+        const float2* sy = reinterpret_cast<const float2*>(s.stage_y) +
+                           ((reinterpret_cast<uintptr_t>(gy + g * GROUP * NBIN) >> 3) & 1);
+        const float2* sx = reinterpret_cast<const float2*>(s.stage_x) +
+                           ((reinterpret_cast<uintptr_t>(gx + g * GROUP * NBIN) >> 3) & 1);
         // ---- enhanced spectrum of this frame group -----------------------------------------------------------
         for (int o = tid; o < GROUP * NBIN; o += blockDim.x) {
             const int k = o % NBIN;
@@ -382,9 +424,8 @@ __global__ void __launch_bounds__(256, 3) mask_istft_kernel(MaskIstftParams p) {
             if (p.spec_in != nullptr) {
                 e = reinterpret_cast<const float2*>(p.spec_in)[((long long)b * NBIN + k) * T + t];
             } else {
-                const long long idx = ((long long)b * T + t) * NBIN + k;
-                const float2 y = reinterpret_cast<const float2*>(p.y)[idx];
-                const float2 x = reinterpret_cast<const float2*>(p.noisy)[idx];
+                const float2 y = sy[o];  // element (t0 + fr, k) of the stream = o-th of the staged group
+                const float2 x = sx[o];
                 const float mr = decompress_cirm((y.x - mean) * inv * w0 + b0);
                 const float mi = decompress_cirm((y.y - mean) * inv * w1 + b1);
                 e = make_float2(mr * x.x - mi * x.y, mi * x.x + mr * x.y);  // CRN_ELU.py:402-403
@@ -394,7 +435,8 @@ __global__ void __launch_bounds__(256, 3) mask_istft_kernel(MaskIstftParams p) {
             if (k == 0 || k == NBIN - 1) e.y = 0.f;  // C2R: imaginary parts of DC / Nyquist are ignored
             s.spec[fr][k] = e;
         }
-        __syncthreads();
+        __syncthreads();  // spectrum complete; the staging buffers are free for the next group
+        if (staged && g + 1 < T / GROUP) stage_group(g + 1);
         if (p.spec_ref != nullptr && p.out_chunk == nullptr && p.carry == nullptr) continue;  // forward(): no iSTFT
 
         // exp(-2 pi i j / 20) = (kC20[j], kS20[j]); both stages are fully unrolled so that every twiddle is an immediate
@@ -481,13 +523,13 @@ __global__ void __launch_bounds__(256, 3) mask_istft_kernel(MaskIstftParams p) {
         }
         __syncthreads();
         // ---- overlap-add of this group's frames (deterministic order: ascending frame) ---------------------------
-        for (int pos = tid; pos < NFFT + HOP * (T - 1); pos += blockDim.x) {
+        // only the SPAN positions this group's frames reach, and per position only the <= 3 frames that cover it
+        for (int rel = tid; rel < SPAN; rel += blockDim.x) {
+            const int pos = t0 * HOP + rel;
             float acc = s.ola[pos];
-#pragma unroll
-            for (int fr = 0; fr < GROUP; ++fr) {
-                const int n = pos - (t0 + fr) * HOP;
-                if (n >= 0 && n < NFFT) acc += s.frames[fr][n];
-            }
+            const int hi = min(GROUP - 1, rel / HOP);
+            const int lo = rel < NFFT ? 0 : (rel - NFFT) / HOP + 1;
+            for (int fr = lo; fr <= hi; ++fr) acc += s.frames[fr][rel - fr * HOP];
             s.ola[pos] = acc;
         }
         __syncthreads();
@@ -506,7 +548,7 @@ __global__ void __launch_bounds__(256, 3) mask_istft_kernel(MaskIstftParams p) {
         for (int n = tid; n < P; n += blockDim.x) {
             const float first = s.ola[NFFT / 2 + n] / c_env[n];
             const float second = s.ola[NFFT / 2 + P + n] / c_env[P + n];
-            if (n < n_valid) out[n] = (first + carry[n]) / 2;  // utility.py:397-399
+            if (n < n_valid) out[n] = (first + (carry_vec ? s.carry[n] : carry[n])) / 2;  // utility.py:397-399
             carry[n] = second;
         }
     }
