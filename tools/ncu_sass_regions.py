@@ -7,11 +7,13 @@ region, a region being the code between two BAR.SYNC instructions (the phases of
 """
 import csv,collections,subprocess,sys,io
 rep=sys.argv[1]; kern=sys.argv[2]
-raw=subprocess.run(["ncu","-i",rep,"--page","source","--csv","--print-source","sass","-k","regex:"+kern],capture_output=True,text=True).stdout
+nth=int(sys.argv[3]) if len(sys.argv)>3 else 0   # which of the matching launches
+raw=subprocess.run(["ncu","-i",rep,"--page","source","--csv","--print-source","sass","-k","regex:"+kern.split("<")[0]],capture_output=True,text=True).stdout
 rows=list(csv.reader(io.StringIO(raw)))
-# may contain multiple kernels; take the first block
+# one block per captured launch of a matching kernel
 start=[i for i,r in enumerate(rows) if r and r[0]=="Kernel Name"]
-blk=rows[start[0]: start[1] if len(start)>1 else None]
+start=[i for i in start if kern.replace(" ","") in rows[i][1].replace(" ","").replace("(int)","")] or start
+blk=rows[start[nth]: ([j for j in [i for i,r in enumerate(rows) if r and r[0]=="Kernel Name"] if j>start[nth]]+[None])[0]]
 print(blk[0][1][:80])
 hdr=blk[1]; data=blk[2:]
 ix={h:i for i,h in enumerate(hdr)}
