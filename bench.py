@@ -503,7 +503,10 @@ def main():
     modes, latency, configs = None, None, None
     if not args.no_extras:
         from tools import bench_parts
+        model._destroy_ctx()  # release the headline context now (not whenever the cycle collector runs its destructor)
         del model
+        import gc
+        gc.collect()
         torch.cuda.empty_cache()
         short = max(3, min(K, 10))
         modes = {"fp16": {"ms_per_step": ms_per_step, "value": value, "unit": UNIT}}

@@ -35,8 +35,12 @@ def _world():
 
 
 def _barrier():
+    import gc
     import torch
     import torch.distributed as dist
+    # a model of an earlier sub-benchmark that is only reclaimed by the cycle collector would run its destructor
+    # (se_ctx_destroy: a device synchronisation and hundreds of cudaFree) inside the NEXT timed region
+    gc.collect()
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -102,6 +106,7 @@ def crn_stream(model_name, streams, precision, steps, warmup=3, latency_steps=0,
         lat = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(latency_steps))
         res.update(p50_chunk_latency_ms=lat[len(lat) // 2], p99_chunk_latency_ms=lat[min(len(lat) - 1, int(0.99 * len(lat)))],
                    latency_steps=latency_steps)
+    model._destroy_ctx()  # free the native context now, not when the collector gets to it
     del model
     return res
 
@@ -143,6 +148,7 @@ def fsn_utterances(streams, seconds=3.0, reps=2, precision="fp16", peak_tflops=N
            "algorithmic_tflop_per_s_per_gpu": tf, "precision": precision}
     if peak_tflops:
         res["roofline"] = {"bound": "tensor", "achieved": tf, "peak": peak_tflops, "unit": "TFLOP/s", "frac": tf / peak_tflops}
+    m._destroy()
     del m
     return res
 
@@ -194,5 +200,7 @@ def train_step(batch=1, seconds=2.0, steps=6, warmup=2, precision="tf32", graph=
            "collective": "NCCL all-reduce(sum) of the flat fp32 gradient" if _world() > 1 else "none (one rank)",
            "config": {"batch_per_rank": B, "piece_seconds": seconds, "precision": precision, "gradient_accumulation": 2,
                       "cuda_graph": bool(graph), "params": n_theta}}
-    del tr, model
+    del tr
+    model._destroy_ctx()
+    del model
     return res
