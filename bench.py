@@ -534,7 +534,7 @@ def main():
                                        dev=dev)
         r["workload"] = f"FullSubNet, {args.fsn_streams} synthetic 3 s utterances per GPU, train=False chunk loop (BASELINE.json configs[3])"
         configs["fsn_3s"] = r
-        r = bench_parts.train_step(batch=1, seconds=2.0, steps=5, warmup=2, precision="tf32", graph=True, dev=dev)
+        r = bench_parts.train_step(batch=1, seconds=2.0, steps=10, warmup=3, precision="tf32", graph=True, dev=dev)
         r["workload"] = ("CRN_ELU compute_loss training step, one 2 s piece per rank, grad-accum 2, gradient all-reduce over the "
                          "ranks of this run (BASELINE.json configs[4])")
         configs["train_step"] = r
