@@ -177,13 +177,13 @@ __global__ void __launch_bounds__(P3_THREADS, 1) preconv3_mma_kernel(Preconv3Par
             // j = 0, 1: taps kf = 2 j + tapsel; j = 2: tap 4 of this frame (tapsel 0) / of the next frame (tapsel 1)
             const int o0 = (tapsel - 2) * d * 16, o1 = tapsel * d * 16, o2 = 2 * d * 16 + tapsel * P3_ROW_BYTES;
             float psum = 0.f, psq = 0.f;
-            // ---- pass 1.  One warp owns a column of 16 bins (warps 13..15 only help with the copies and pass 2) and
+            // ---- pass 1.  A warp (0..11) owns a column of 16 bins (the 13th column: see the else branch) and
             // streams over the 25 input frames: the fragments of input frame u feed the output frames u - kt (kt = 0..4),
             // whose accumulators roll through five register slots; output frame u - 4 is complete after frame u: ELU, gate,
             // statistics, gated values -> Y.  3 ldmatrix and 15 mma per 16-row tile (13 + 15 with one fragment per tap
             // pair and no reuse).  The first and last five frames are peeled so that the steady state has no conditions:
             // the compiler interleaves the epilogue of frame u with the mma of frame u + 1 in one basic block.
-            if (warp < 13) {
+            if (warp < 12) {
                 const int ft = warp;
                 // rows 16 ft + g are always real bins (<= 199); rows + 8 run past bin 200 only in the last column
                 const float m1 = (ft < 12 || g == 0) ? 1.f : 0.f;
@@ -247,6 +247,73 @@ __global__ void __launch_bounds__(P3_THREADS, 1) preconv3_mma_kernel(Preconv3Par
 #pragma unroll 1
                 for (int ub = 5; ub < 20; ub += 5) frames5(std::integral_constant<int, 1>{}, ub);
                 frames5(std::integral_constant<int, 2>{}, 20);
+            } else {
+                // The 13th column (bins 192..200, 9 real rows) is shared by warps 12..15, a quarter of the output frames
+                // each.  The tensor pipe of an SM sub-partition is the bound of this pass (one HMMA per 16 cycles) and
+                // warp w issues on sub-partition w % 4: twelve full columns are three per sub-partition, and the four
+                // quarters (5 or 6 output frames + 4 frames of run-in each) add 0.4 of a column to every one of them
+                // instead of a whole fourth column to sub-partition 0.
+                const int q = warp - 12;
+                const int ta = 5 * q, tb = q == 3 ? T : 5 * q + 5;  // output frames [ta, tb)
+                constexpr int ft = 12;
+                const float m1 = g == 0 ? 1.f : 0.f;  // rows + 8 run past bin 200 except for g = 0
+                const uint32_t a_col = x_smem + (uint32_t)((P3_BORDER + 16 * ft + rowoff) * 16);
+                unsigned char* y_col = sy + (size_t)((16 * ft + g) * 16 + 4 * tg);
+                float acc[5][4];
+#pragma unroll
+                for (int i = 0; i < 5; ++i) {
+                    acc[i][0] = acc[i][2] = cb0;
+                    acc[i][1] = acc[i][3] = cb1;
+                }
+                // input frames ta .. tb + 3 in blocks of five (slot of output frame u - kt: (ui - kt) mod 5 as above);
+                // an output frame is live when it lies in [ta, tb)
+#pragma unroll 1
+                for (int ub = ta; ub < tb + 4; ub += 5) {
+                    const bool first = ub == ta;
+#pragma unroll
+                    for (int ui = 0; ui < 5; ++ui) {
+                        const int u = ub + ui;
+                        if (u < tb + 4) {  // warp-uniform
+                            uint32_t f0[4], f1[4], f2[4];
+                            const uint32_t arow = a_col + (uint32_t)(u * P3_ROW_BYTES);
+                            ldsm_x4_dep(arow + o0, epoch, f0);
+                            ldsm_x4_dep(arow + o1, epoch, f1);
+                            ldsm_x4_dep(arow + (u == T + 3 ? 2 * d * 16 : o2), epoch, f2);  // frame 24 has no successor
+#pragma unroll
+                            for (int kt = 0; kt < 5; ++kt) {
+                                const bool live = (!first || ui >= kt) && (u - kt < tb);
+                                if (live) {
+                                    float(&c)[4] = acc[(ui - kt + 5) % 5];
+                                    mma16816(c, f0, wr[2 * kt].x, wr[2 * kt].y);
+                                    mma16816(c, f1, wr[2 * kt + 1].x, wr[2 * kt + 1].y);
+                                    if ((kt & 1) == 0) mma16816(c, f2, wr[10 + kt / 2].x, wr[10 + kt / 2].y);
+                                }
+                            }
+                            if ((!first || ui == 4) && u - 4 < tb) {
+                                const int t = u - 4;
+                                float(&c)[4] = acc[(ui + 1) % 5];
+                                uint32_t a2[4];
+                                a2[0] = pack_h2(fast_elu(c[0]), fast_elu(c[1]));
+                                a2[1] = pack_h2(fast_elu(c[2]), fast_elu(c[3]));
+                                a2[2] = a2[3] = 0u;
+                                float gt[4] = {bt0, bt1, bt0, bt1}, gg4[4] = {bg0, bg1, bg0, bg1};
+                                mma16816(gt, a2, wgt.x, wgt.y);
+                                mma16816(gg4, a2, wgg.x, wgg.y);
+                                const float y0 = gt[0] * sigmoid_from_neg_log2(gg4[0]);
+                                const float y1 = gt[1] * sigmoid_from_neg_log2(gg4[1]);
+                                const float y2 = m1 * gt[2] * sigmoid_from_neg_log2(gg4[2]);
+                                const float y3 = m1 * gt[3] * sigmoid_from_neg_log2(gg4[3]);
+                                psum += (y0 + y1) + (y2 + y3);
+                                psq = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, psq))));
+                                unsigned char* yr = y_col + (size_t)t * (P3_YPITCH * 16);
+                                *reinterpret_cast<uint32_t*>(yr) = pack_h2(y0, y1);
+                                *reinterpret_cast<uint32_t*>(yr + 8 * 16) = pack_h2(y2, y3);
+                                c[0] = c[2] = cb0;
+                                c[1] = c[3] = cb1;
+                            }
+                        }
+                    }
+                }
             }
             __syncthreads();  // frames 0..3 of X are dead from here on
             if (l < 2) {      // carried state of the next layer -> frames 0..3 (overlaps the statistics and pass 2)
