@@ -128,10 +128,12 @@ __global__ void __launch_bounds__(kThreads, 1) dec_mma_kernel(DecMmaParams p) {
     const int sel = mi >> 1;
     const int dFp = p.d * Fp;
     const int MT = (T * Fp + 15) >> 4;     // deconv tiles (rows over the padded width)
-    const int mt_lo = (warp * MT) / kWarps, mt_hi = ((warp + 1) * MT) / kWarps;
+    int mt_lo, mt_hi;
+    warp_tile_range(warp, kWarps, MT, mt_lo, mt_hi);
     const int Fy = 2 * p.Fin - 1, Fs = p.Fs;
     const int MT2 = (T * Fs + 15) >> 4;    // skip tiles
-    const int st_lo = (warp * MT2) / kWarps, st_hi = ((warp + 1) * MT2) / kWarps;
+    int st_lo, st_hi;
+    warp_tile_range(warp, kWarps, MT2, st_lo, st_hi);
     constexpr int UPR = COUT / 8;
 
     __syncthreads();

@@ -526,7 +526,8 @@ __global__ void __launch_bounds__(kThreads, 1) enc_mma_kernel(EncMmaParams p) {
     const int sel = mi >> 1;
     const int dtJ = p.dt * Jp;
     const int MT = (T * Jp + 15) >> 4;
-    const int mt_lo = (warp * MT) / kWarps, mt_hi = ((warp + 1) * MT) / kWarps;  // the warp's contiguous tile range
+    int mt_lo, mt_hi;  // the warp's contiguous tile range
+    warp_tile_range(warp, kWarps, MT, mt_lo, mt_hi);
     const int Fo = p.Fo;
     const double count = (double)COUT * Fo * T;
     constexpr int UPR = COUT / 8;  // 16-byte units per output row

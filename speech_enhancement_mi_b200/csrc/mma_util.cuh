@@ -48,6 +48,17 @@ constexpr float kLog2e = 1.4426950408889634f;
 // gate: the caller passes z = -log2(e) * (pre-activation); the factor is folded into the gate weights and bias
 __device__ __forceinline__ float sigmoid_from_neg_log2(float z) { return rcp_ftz(1.0f + ex2_ftz(z)); }
 __device__ __forceinline__ float fast_elu(float x) { return x > 0.f ? x : ex2_ftz(x * kLog2e) - 1.0f; }
+// Contiguous tile range of a warp such that the four SM sub-partitions (warp w issues on sub-partition w % 4, and the
+// tensor pipe of a sub-partition is what bounds the mma.sync passes) get equal shares: sub-partition sp owns the sp-th
+// quarter of the tiles and its warps (w / 4 = 0 .. nwarps / 4 - 1) split that quarter.  Sizes differ by at most one tile
+// between sub-partitions and between the warps of one (warp * n / nwarps let one sub-partition collect all the
+// rounded-up ranges: 36 tiles against 32 in the first encoder level).
+__device__ __forceinline__ void warp_tile_range(int warp, int nwarps, int ntiles, int& lo, int& hi) {
+    const int sp = warp & 3, k = warp >> 2, per = nwarps >> 2;
+    const int s0 = (sp * ntiles) >> 2, n = (((sp + 1) * ntiles) >> 2) - s0;
+    lo = s0 + (k * n) / per;
+    hi = s0 + ((k + 1) * n) / per;
+}
 // exact quotient r / d for r < 65536 with magic = ceil(2^32 / d)
 __device__ __forceinline__ int div_magic(int r, uint32_t magic) { return (int)__umulhi((uint32_t)r, magic); }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
