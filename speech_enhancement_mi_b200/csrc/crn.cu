@@ -1965,6 +1965,7 @@ int enqueue_stream_step(se_ctx* c, int B, cudaStream_t st, int stage_filter = -1
         mp.b = c->b_last;
         mp.noisy = c->noisy;
         mp.carry = c->carry;
+        mp.fast = (c->half || c->tf32) ? 1 : 0;
         if (launch_mask_istft(mp, st)) return 1;
     }
     if (want(ST_ROLL)) {

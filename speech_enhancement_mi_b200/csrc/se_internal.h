@@ -360,6 +360,7 @@ struct MaskIstftParams {
     float* out_chunk;    // optional [B][K] full per-chunk iSTFT output
     float* spec_ref;     // optional enhanced spectrum in the reference layout [B][F][T][2] (forward()); skips iSTFT
     const float* spec_in;  // optional: take the enhanced spectrum [B][F][T][2] from here instead (se_istft_trans)
+    int fast;  // tensor-core precisions (tf32 / fp16): decompress_cIRM by two lg2.approx instead of an IEEE division + logf
 };
 int launch_mask_istft(const MaskIstftParams& p, cudaStream_t st);
 int init_fft_tables();  // uploads twiddles / window / envelope to constant memory of the current device
