@@ -3,9 +3,11 @@
 native clip + Adam step (se_clip_adam_step), against fixtures produced by the UNMODIFIED reference
 (tests/golden/train_grads.npz, oracle/make_golden.py train) and against the oracle's autograd.
 
-Stated tolerances (fp32 arithmetic, sums re-associated by tiling / atomics): pred 2e-4 of the peak, loss terms 2e-3,
-d loss / d pred 1e-2 of its peak, every parameter gradient 2e-2 of that tensor's peak (tf32 mode: 0.1 and cosine
-similarity >= 0.99 over all parameters)."""
+Stated tolerances (fp32 arithmetic, sums re-associated by tiling / atomics), about 5x the error measured on B200 in round
+2 (worst parameter gradient 1.4e-5 of the tensor's peak, d loss / d pred 8e-4): pred 2e-4 of the peak, loss terms 2e-3,
+d loss / d pred 4e-3 of its peak, every parameter gradient 1e-3 of that tensor's peak (tf32 mode: 0.1 and cosine
+similarity >= 0.99 over all parameters).  The student check runs against the oracle's autograd on the CPU (a second
+fp32 implementation, not the reference's own numbers) and keeps 1e-2 / 5e-3."""
 import contextlib
 import io
 import os
@@ -66,14 +68,14 @@ def test_small_train_step_matches_reference():
     pred, dpred, losses, grads = _step(model, mix, src, [8000, 6500], False)
     assert rel_err(pred, g["small_pred"]) < 2e-4
     assert np.allclose(losses, g["small_loss"], atol=2e-3)
-    assert rel_err(dpred, g["small_dpred"]) < 1e-2
-    _report(grads, g, "small_grad/", 2e-2)
+    assert rel_err(dpred, g["small_dpred"]) < 4e-3
+    _report(grads, g, "small_grad/", 1e-3)
     # flag=True: the next piece continues with the carried conv buffers / GRU state (CRN_ELU.py:474-481)
     mix2, src2 = synth.make_mixture(2, 4800, first_stream=100)
     pred, dpred, losses, grads = _step(model, mix2, src2, [4800, 4800], True)
     assert rel_err(pred, g["small_cont_pred"]) < 2e-4
     assert np.allclose(losses, g["small_cont_loss"], atol=2e-3)
-    _report(grads, g, "small_cont_grad/", 2e-2)
+    _report(grads, g, "small_cont_grad/", 1e-3)
 
 
 def test_teacher_train_step_matches_reference():
@@ -83,14 +85,14 @@ def test_teacher_train_step_matches_reference():
     pred, dpred, losses, grads = _step(model, mix, src, [6400], False)
     assert rel_err(pred, g["teacher_pred"]) < 2e-4
     assert np.allclose(losses, g["teacher_loss"], atol=2e-3)
-    assert rel_err(dpred, g["teacher_dpred"]) < 1e-2
+    assert rel_err(dpred, g["teacher_dpred"]) < 4e-3
     bad = []
     for k in [k[len("teacher_gnorm/"):] for k in g.files if k.startswith("teacher_gnorm/")]:
         gn = float(g["teacher_gnorm/" + k])
-        if abs(float(np.linalg.norm(grads[k].astype(np.float64))) - gn) > 2e-2 * gn + 1e-9:
+        if abs(float(np.linalg.norm(grads[k].astype(np.float64))) - gn) > 1e-3 * gn + 1e-9:
             bad.append((k, "norm"))
         head = g["teacher_ghead/" + k]
-        if np.abs(grads[k].reshape(-1)[:64] - head).max() > 2e-2 * (np.abs(grads[k]).max() + 1e-30):
+        if np.abs(grads[k].reshape(-1)[:64] - head).max() > 1e-3 * (np.abs(grads[k]).max() + 1e-30):
             bad.append((k, "head"))
     assert not bad, bad
 
@@ -112,7 +114,7 @@ def test_student_train_step_matches_oracle_autograd():
     assert abs(float(loss) - losses_ref[0]) < 2e-3
     assert rel_err(pred.grad.cpu().numpy(), dpred_ref.numpy()) < 1e-2
     bad = [(k, rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy())) for k, p in model.named_parameters()
-           if k in grads_ref and not rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy()) < 2e-2]
+           if k in grads_ref and not rel_err(p.grad.cpu().numpy(), grads_ref[k].numpy()) < 5e-3]
     assert not bad, bad
 
 
