@@ -243,6 +243,7 @@ struct se_ctx {
     // round-1 kernels (preconv_tc.cu per layer; back-to-back tcgen05 GEMM + separate GlobalLayerNorm pass).
     bool front_mma = true, enc_mma = true;
     bool enc_tc = true;  // SE_B200_ENC_TC=0: the 16 -> 32 / 32 -> 64 encoder levels on their round-2a kernels (mma.sync / b2b GEMM)
+    int bwd_mode = BWD_3XTF32;  // arithmetic of the backward contractions (train_kernels.cu), SE_B200_BWD_MMA
     bool dec_mma = true;  // SE_B200_DEC_MMA=0: small-channel decoder blocks as deconv GEMM + skip-pair kernel + blend kernel
     bool use_tma = true;  // SE_B200_TMA=0: every tcgen05 GEMM keeps the cp.async gather producers
     __half* feat_h = nullptr;     // features of the chunk [maxB][21][224][8] halves (borders stay zero)
@@ -1019,6 +1020,11 @@ int build_ctx(se_ctx* c) {
     c->enc_mma = c->enc_mma && c->half && !c->train;
     if (const char* e = getenv("SE_B200_DEC_MMA")) c->dec_mma = atoi(e) != 0;
     c->dec_mma = c->dec_mma && c->half && !c->train;
+    // backward contractions of the training step: fp32-accurate 3xTF32 beside the exact forward, one tf32 pass beside
+    // the tf32 forward; SE_B200_BWD_MMA=0 keeps them on the CUDA cores (1 / 2 force a tensor-core form)
+    c->bwd_mode = c->tf32 ? BWD_TF32 : BWD_3XTF32;
+    if (const char* e = getenv("SE_B200_BWD_MMA")) c->bwd_mode = atoi(e);
+    SE_REQUIRE(c->bwd_mode >= 0 && c->bwd_mode <= 2, "SE_B200_BWD_MMA must be 0, 1 or 2");
     for (int i = 0; i < c->L; ++i) {
         SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
         SE_REQUIRE(!c->half || g.num_channels[i] % 8 == 0, "fp16 mode: num_channels must be multiples of 8");
@@ -2210,8 +2216,8 @@ float* garena_of(const se_ctx* c, const void* w) {
 int dense_bwd(se_ctx* c, const Op& op, int B, const float* G, StridedRows gs, float* dA, cudaStream_t st) {
     GemmParams g = op.g;
     g.M = B * op.rows_per_stream;
-    if (launch_wgrad(g, G, gs, garena_of(c, g.W), garena_of(c, g.bias), st)) return 1;
-    if (dA != nullptr && launch_dgrad(g, G, gs, dA, st)) return 1;
+    if (launch_wgrad(g, G, gs, garena_of(c, g.W), garena_of(c, g.bias), st, c->bwd_mode)) return 1;
+    if (dA != nullptr && launch_dgrad(g, G, gs, dA, st, c->bwd_mode)) return 1;
     return 0;
 }
 
@@ -2397,11 +2403,11 @@ int train_backward(se_ctx* c, const float* dpred, const float* const* dtaps, flo
                                       H, st))
                     return 1;
                 if (t > 0 && launch_dgrad(rec, c->dgh + (long long)t * 3 * H, StridedRows{(long long)T * 3 * H, 0, 0},
-                                          c->dhrec, st))
+                                          c->dhrec, st, c->bwd_mode))
                     return 1;
             }
             gh.out = nullptr;
-            if (launch_wgrad(gh, c->dgh, g3, garena_of(c, gh.W), garena_of(c, gh.bias), st)) return 1;
+            if (launch_wgrad(gh, c->dgh, g3, garena_of(c, gh.W), garena_of(c, gh.bias), st, c->bwd_mode)) return 1;
             if (dense_bwd(c, iop, Bp, c->dgi, g3, l == 1 ? c->dH[0] + H : c->dxg, st)) return 1;
         }
     }

@@ -378,10 +378,15 @@ struct StridedRows {  // row m = (b*Tn + t)*Fo + f of a [B][Tn][Fo] grid lives a
 };
 // dW[n][k] += sum_m G(m,n) * A(m,k), dbias[n] += sum_m G(m,n)   (A gathered exactly like the forward GEMM `p`)
 // G(m,n) = G[b*g.sB + t*g.sT + f*g.sF + n], n < N (odd_tail as in the forward).  dW has the packed layout [Npad][K].
-int launch_wgrad(const GemmParams& p, const float* G, StridedRows g, float* dW, float* dbias, cudaStream_t st);
+// mode: which arithmetic carries the contraction (train_kernels.cu)
+enum { BWD_CUDA_CORES = 0,  // fp32 FMA
+       BWD_3XTF32 = 1,      // mma.sync tf32 with head / tail operands (fp32-accurate)
+       BWD_TF32 = 2 };      // mma.sync tf32, single pass
+int launch_wgrad(const GemmParams& p, const float* G, StridedRows g, float* dW, float* dbias, cudaStream_t st,
+                 int mode = BWD_3XTF32);
 // dA(m,k) = sum_n G(m,n) * W[n][k], scatter-added at dA + (same offsets as the forward gather); dA is a twin of the
 // forward operand buffer (zero-initialised by the caller; contributions of overlapping taps accumulate)
-int launch_dgrad(const GemmParams& p, const float* G, StridedRows g, float* dA, cudaStream_t st);
+int launch_dgrad(const GemmParams& p, const float* G, StridedRows g, float* dA, cudaStream_t st, int mode = BWD_3XTF32);
 
 struct GlnBwdParams {
     int B, T, F, C;       // y is compact [B][T][F][C]; statistics count = `count` real elements

@@ -161,6 +161,236 @@ __global__ void __launch_bounds__(kThreads) dgrad_kernel(GemmParams p, const flo
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Tensor-core forms of the two contractions above: warp-level mma.sync.m16n8k8 (tf32 operands, fp32 accumulation).
+// SPLIT = true is the error-compensated "3xTF32" product: every operand is stored in shared memory as a tf32 head and a
+// tf32 tail (x = hi + lo up to 2^-21 |x|) and a tile step issues lo*hi + hi*lo + hi*hi, which keeps the gradients at fp32
+// accuracy (the fp32 parity mode); SPLIT = false is the single-pass tf32 product used when the forward runs in tf32
+// too.  Same tiles, gather table and atomics as the CUDA-core kernels, so the two forms are interchangeable per launch
+// (SE_B200_BWD_MMA=0 selects the CUDA-core kernels).
+// Fragment roles (gq = lane / 4, tq = lane % 4): A (16 x 8): rows gq, gq + 8, columns tq, tq + 4; B (8 x 8): row tq,
+// tq + 4, column gq; C (16 x 8): rows gq, gq + 8, columns 2 tq, 2 tq + 1.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TM_BM = 32;   // rows (wgrad) / columns n (dgrad) per shared-memory stage
+constexpr int TM_LD8 = 72;  // row pitch = 8 mod 32 banks: the (tq, gq) fragment reads of a [k][m|n] tile are conflict free
+constexpr int TM_LD4 = 36;  // row pitch = 4 mod 32 banks: the (gq, tq) fragment reads of a [m][k] tile are conflict free
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void mma1688(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// four values -> tf32 heads (and tails) as one 16-byte shared-memory store each
+template <bool SPLIT>
+__device__ __forceinline__ void store_split4(uint32_t* hi, uint32_t* lo, const float (&v)[4]) {
+    uint4 h, l;
+    h.x = to_tf32(v[0]);
+    h.y = to_tf32(v[1]);
+    h.z = to_tf32(v[2]);
+    h.w = to_tf32(v[3]);
+    *reinterpret_cast<uint4*>(hi) = h;
+    if (SPLIT) {
+        l.x = to_tf32(v[0] - __uint_as_float(h.x));
+        l.y = to_tf32(v[1] - __uint_as_float(h.y));
+        l.z = to_tf32(v[2] - __uint_as_float(h.z));
+        l.w = to_tf32(v[3] - __uint_as_float(h.w));
+        *reinterpret_cast<uint4*>(lo) = l;
+    }
+}
+
+// C fragment {(gq, 2tq), (gq, 2tq+1), (gq+8, 2tq), (gq+8, 2tq+1)} of a lane pair -> four consecutive columns of one row:
+// even tq keeps row gq, odd tq row gq + 8
+__device__ __forceinline__ float4 pair_rows(const float (&c)[4], int tq) {
+    const bool odd = tq & 1;
+    const float s0 = odd ? c[0] : c[2], s1 = odd ? c[1] : c[3];  // what the partner needs
+    const float r0 = __shfl_xor_sync(0xffffffffu, s0, 1), r1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    return odd ? make_float4(r0, r1, c[2], c[3]) : make_float4(c[0], c[1], r0, r1);
+}
+
+// weight gradient: 64 (n) x 64 (k) tile per CTA; warp w owns output rows n0 + 16 (w % 4) and columns k0 + 32 (w / 4)
+// .. + 31 (four n8 tiles); the reduction runs over this CTA's slice of the rows in stages of TM_BM
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreads) wgrad_mma_kernel(GemmParams p, const float* __restrict__ G, StridedRows g,
+                                                             float* __restrict__ dW, float* __restrict__ dbias,
+                                                             int rows_per_cta) {
+    constexpr int NS = SPLIT ? 2 : 1;
+    __shared__ __align__(16) uint32_t Gs[NS][TM_BM][TM_LD8];  // [m][n]
+    __shared__ __align__(16) uint32_t As[NS][TM_BM][TM_LD8];  // [m][k]
+    __shared__ float s_bias[64];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int m_begin = blockIdx.z * rows_per_cta;
+    const int m_end = min(p.M, m_begin + rows_per_cta);
+    const int nt = (warp & 3) * 16, kh = (warp >> 2) * 32;
+    const int rps = p.Tn * p.Fo;
+    const float* A = reinterpret_cast<const float*>(p.A);
+    const bool want_bias = dbias != nullptr && blockIdx.x == 0;
+    float acc[4][4] = {};
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    if (tid < 64) s_bias[tid] = 0.f;
+    const int lr = tid >> 4, lu = tid & 15;  // loader role: row lr (+16), 16-byte unit lu
+    for (int m0 = m_begin; m0 < m_end; m0 += TM_BM) {
+#pragma unroll
+        for (int pass = 0; pass < TM_BM / 16; ++pass) {
+            const int r = lr + 16 * pass, m = m0 + r;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < m_end) {
+                int f;
+                const long long off = row_off(m, rps, p.Fo, g.sB, g.sT, g.sF, &f);
+                const int nlim = (p.odd_tail && f == p.Fo - 1) ? p.N / 2 : p.N;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n0 + 4 * lu + j < nlim) v[j] = G[off + n0 + 4 * lu + j];
+                const int k = k0 + 4 * lu;
+                if (k < p.K)
+                    a = *reinterpret_cast<const float4*>(A + row_off(m, rps, p.Fo, p.sB, p.sT, p.sF) +
+                                                         __ldg(p.koff + (k >> 2)));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bsum[j] += v[j];
+            store_split4<SPLIT>(&Gs[0][r][4 * lu], &Gs[NS - 1][r][4 * lu], v);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            store_split4<SPLIT>(&As[0][r][4 * lu], &As[NS - 1][r][4 * lu], av);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ms = 0; ms < TM_BM; ms += 8) {
+            uint32_t ah[4], al[4];
+            ah[0] = Gs[0][ms + tq][nt + gq];
+            ah[1] = Gs[0][ms + tq][nt + gq + 8];
+            ah[2] = Gs[0][ms + tq + 4][nt + gq];
+            ah[3] = Gs[0][ms + tq + 4][nt + gq + 8];
+            if (SPLIT) {
+                al[0] = Gs[NS - 1][ms + tq][nt + gq];
+                al[1] = Gs[NS - 1][ms + tq][nt + gq + 8];
+                al[2] = Gs[NS - 1][ms + tq + 4][nt + gq];
+                al[3] = Gs[NS - 1][ms + tq + 4][nt + gq + 8];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kc = kh + 8 * j + gq;
+                const uint32_t bh0 = As[0][ms + tq][kc], bh1 = As[0][ms + tq + 4][kc];
+                if (SPLIT) {
+                    const uint32_t bl0 = As[NS - 1][ms + tq][kc], bl1 = As[NS - 1][ms + tq + 4][kc];
+                    mma1688(acc[j], al, bh0, bh1);
+                    mma1688(acc[j], ah, bl0, bl1);
+                }
+                mma1688(acc[j], ah, bh0, bh1);
+            }
+        }
+        __syncthreads();
+    }
+    // a lane pair (tq even / odd) holds columns 4 (tq / 2) .. + 3 of rows gq and gq + 8: one exchange gives the even
+    // lane the four values of row gq and the odd lane those of row gq + 8 -> ONE 16-byte reduction per row and unit
+    // instead of four (the L2 reduction rate, not the arithmetic, bounds the scatter)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 v = pair_rows(acc[j], tq);
+        const int k = k0 + kh + 8 * j + 4 * (tq >> 1);
+        const int n = n0 + nt + gq + 8 * (tq & 1);
+        if (k < p.K && n < p.N && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f))
+            atomicAdd(reinterpret_cast<float4*>(dW + (long long)n * p.K + k), v);
+    }
+    if (want_bias) {  // the raw fp32 values, not their tf32 heads
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (bsum[j] != 0.f) atomicAdd(&s_bias[4 * lu + j], bsum[j]);
+        __syncthreads();
+        if (tid < 64 && n0 + tid < p.N && s_bias[tid] != 0.f) atomicAdd(dbias + n0 + tid, s_bias[tid]);
+    }
+}
+
+// data gradient: 64 (rows) x 64 (k) tile per CTA; warp w owns rows m0 + 16 (w % 4) and columns k0 + 32 (w / 4) .. + 31;
+// the reduction runs over the N columns of G in stages of TM_BM
+template <bool SPLIT>
+__global__ void __launch_bounds__(kThreads) dgrad_mma_kernel(GemmParams p, const float* __restrict__ G, StridedRows g,
+                                                             float* __restrict__ dA, int n_per_cta) {
+    constexpr int NS = SPLIT ? 2 : 1;
+    __shared__ __align__(16) uint32_t Gs[NS][64][TM_LD4];     // [m][n]
+    __shared__ __align__(16) uint32_t Ws[NS][TM_BM][TM_LD8];  // [n][k]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int m0 = blockIdx.x * 64, k0 = blockIdx.y * 64;
+    const int mt = (warp & 3) * 16, kh = (warp >> 2) * 32;
+    const int rps = p.Tn * p.Fo;
+    const float* W = reinterpret_cast<const float*>(p.W);
+    // loader role for G: row tid / 4, columns 8 (tid % 4) .. + 7 of every stage
+    const int lr = tid >> 2, lc = (tid & 3) * 8;
+    long long goff = -1;
+    int nlim_l = 0;
+    if (m0 + lr < p.M) {
+        int f;
+        goff = row_off(m0 + lr, rps, p.Fo, g.sB, g.sT, g.sF, &f);
+        nlim_l = (p.odd_tail && f == p.Fo - 1) ? p.N / 2 : p.N;
+    }
+    float acc[4][4] = {};
+    // blockIdx.z: slice of the reduction (few-row GEMMs such as the GRU projections would otherwise run on 64 CTAs)
+    const int n_begin = blockIdx.z * n_per_cta, n_end = min(p.N, n_begin + n_per_cta);
+    for (int n0 = n_begin; n0 < n_end; n0 += TM_BM) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int n = n0 + lc + 4 * half + j;
+                v[j] = (goff >= 0 && n < nlim_l && n < n_end) ? G[goff + n] : 0.f;
+            }
+            store_split4<SPLIT>(&Gs[0][lr][lc + 4 * half], &Gs[NS - 1][lr][lc + 4 * half], v);
+        }
+#pragma unroll
+        for (int pass = 0; pass < TM_BM / 16; ++pass) {
+            const int nr = (tid >> 4) + 16 * pass, n = n0 + nr, k = k0 + 4 * (tid & 15);
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < n_end && k < p.K) w = *reinterpret_cast<const float4*>(W + (long long)n * p.K + k);
+            const float wv[4] = {w.x, w.y, w.z, w.w};
+            store_split4<SPLIT>(&Ws[0][nr][4 * (tid & 15)], &Ws[NS - 1][nr][4 * (tid & 15)], wv);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ns = 0; ns < TM_BM; ns += 8) {
+            uint32_t ah[4], al[4];
+            ah[0] = Gs[0][mt + gq][ns + tq];
+            ah[1] = Gs[0][mt + gq + 8][ns + tq];
+            ah[2] = Gs[0][mt + gq][ns + tq + 4];
+            ah[3] = Gs[0][mt + gq + 8][ns + tq + 4];
+            if (SPLIT) {
+                al[0] = Gs[NS - 1][mt + gq][ns + tq];
+                al[1] = Gs[NS - 1][mt + gq + 8][ns + tq];
+                al[2] = Gs[NS - 1][mt + gq][ns + tq + 4];
+                al[3] = Gs[NS - 1][mt + gq + 8][ns + tq + 4];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int kc = kh + 8 * j + gq;
+                const uint32_t bh0 = Ws[0][ns + tq][kc], bh1 = Ws[0][ns + tq + 4][kc];
+                if (SPLIT) {
+                    const uint32_t bl0 = Ws[NS - 1][ns + tq][kc], bl1 = Ws[NS - 1][ns + tq + 4][kc];
+                    mma1688(acc[j], al, bh0, bh1);
+                    mma1688(acc[j], ah, bl0, bl1);
+                }
+                mma1688(acc[j], ah, bh0, bh1);
+            }
+        }
+        __syncthreads();
+    }
+    const int m = m0 + mt + gq + 8 * (tq & 1);
+    const long long roff = m < p.M ? row_off(m, rps, p.Fo, p.sB, p.sT, p.sF) : 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float4 v = pair_rows(acc[j], tq);  // row m, the whole 16-byte unit k .. k + 3 of the gather table
+        const int k = k0 + kh + 8 * j + 4 * (tq >> 1);
+        if (k < p.K && m < p.M && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f))
+            atomicAdd(reinterpret_cast<float4*>(dA + roff + __ldg(p.koff + (k >> 2))), v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // GlobalLayerNorm backward.  out = (y - mu) / D * w + b,  D = sqrt(var + eps) + eps (teacher) | sqrt(var) + eps (student)
 //   g = dout * w;  dy = (g - mean(g)) / D - (y - mu) * sum(g (y - mu)) / (N D^2 s),  s = dD/dvar^-1 / 2 = sqrt(var [+ eps])
 // ---------------------------------------------------------------------------------------------------------------
@@ -428,26 +658,48 @@ inline int grid_for(long long n) {
 
 }  // namespace
 
-int launch_wgrad(const GemmParams& p, const float* G, StridedRows g, float* dW, float* dbias, cudaStream_t st) {
+int launch_wgrad(const GemmParams& p, const float* G, StridedRows g, float* dW, float* dbias, cudaStream_t st, int mode) {
     if (p.M <= 0) return 0;
     SE_REQUIRE(!p.a_half, "wgrad: fp32 operands only");
+    const int bm = mode == BWD_CUDA_CORES ? WG_BM : TM_BM;
     const int kt = (p.K + 63) / 64, nt = (p.N + 63) / 64;
     int splits = (148 * 4 + kt * nt - 1) / (kt * nt);
-    const int max_splits = (p.M + 4 * WG_BM - 1) / (4 * WG_BM);
+    const int max_splits = (p.M + 4 * bm - 1) / (4 * bm);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     int rows = (p.M + splits - 1) / splits;
-    rows = (rows + WG_BM - 1) / WG_BM * WG_BM;
+    rows = (rows + bm - 1) / bm * bm;
     splits = (p.M + rows - 1) / rows;
-    wgrad_kernel<<<dim3(kt, nt, splits), kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
+    const dim3 grid(kt, nt, splits);
+    if (mode == BWD_CUDA_CORES)
+        wgrad_kernel<<<grid, kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
+    else if (mode == BWD_TF32)
+        wgrad_mma_kernel<false><<<grid, kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
+    else
+        wgrad_mma_kernel<true><<<grid, kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
-int launch_dgrad(const GemmParams& p, const float* G, StridedRows g, float* dA, cudaStream_t st) {
+int launch_dgrad(const GemmParams& p, const float* G, StridedRows g, float* dA, cudaStream_t st, int mode) {
     if (p.M <= 0) return 0;
     SE_REQUIRE(!p.a_half, "dgrad: fp32 operands only");
-    dgrad_kernel<<<dim3((p.M + 63) / 64, (p.K + 63) / 64), kThreads, 0, st>>>(p, G, g, dA);
+    dim3 grid((p.M + 63) / 64, (p.K + 63) / 64);
+    if (mode == BWD_CUDA_CORES) {
+        dgrad_kernel<<<grid, kThreads, 0, st>>>(p, G, g, dA);
+    } else {
+        // at least two CTAs per SM: split the reduction over N when the row / k tiles are few (results are scatter-added anyway)
+        const int tiles = grid.x * grid.y, stages = (p.N + TM_BM - 1) / TM_BM;
+        int nsplit = (2 * 148 + tiles - 1) / tiles;
+        if (nsplit > stages) nsplit = stages;
+        if (nsplit < 1) nsplit = 1;
+        const int n_per_cta = (stages + nsplit - 1) / nsplit * TM_BM;
+        grid.z = (p.N + n_per_cta - 1) / n_per_cta;
+        if (mode == BWD_TF32)
+            dgrad_mma_kernel<false><<<grid, kThreads, 0, st>>>(p, G, g, dA, n_per_cta);
+        else
+            dgrad_mma_kernel<true><<<grid, kThreads, 0, st>>>(p, G, g, dA, n_per_cta);
+    }
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }

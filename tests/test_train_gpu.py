@@ -118,6 +118,28 @@ def test_student_train_step_matches_oracle_autograd():
     assert not bad, bad
 
 
+@pytest.mark.parametrize("env", [{"SE_B200_BWD_MMA": "0"}, {"SE_B200_GRU_CLUSTER": "0"},
+                                 {"SE_B200_BWD_MMA": "0", "SE_B200_GRU_CLUSTER": "0"}, {"SE_B200_BWD_MMA": "2"}],
+                         ids=["bwd_cuda_cores", "gru_cooperative", "round1_backward", "bwd_single_tf32"])
+def test_backward_kernel_switches_match_reference(env, monkeypatch):
+    """Every form of the backward contractions (CUDA cores / 3xTF32 / one tf32 pass on mma.sync, train_kernels.cu) and of
+    the sequence GRU (cluster-resident / cooperative, gru_seq.cu) against the unmodified reference's gradients: the
+    fp32-accurate forms at the tolerance of the default path, the single tf32 pass at 2e-2 of each tensor's peak."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = np.load(os.path.join(GOLDEN, "train_grads.npz"))
+    model = make_model("crn_small", precision="fp32").cuda().train()
+    mix, src = synth.make_mixture(2, 8000)
+    pred, dpred, losses, grads = _step(model, mix, src, [8000, 6500], False)
+    assert rel_err(pred, g["small_pred"]) < 2e-4
+    assert rel_err(dpred, g["small_dpred"]) < 4e-3
+    _report(grads, g, "small_grad/", 2e-2 if env.get("SE_B200_BWD_MMA") == "2" else 1e-3)
+    mix2, src2 = synth.make_mixture(2, 4800, first_stream=100)
+    pred, dpred, losses, grads = _step(model, mix2, src2, [4800, 4800], True)
+    assert rel_err(pred, g["small_cont_pred"]) < 2e-4
+    _report(grads, g, "small_cont_grad/", 2e-2 if env.get("SE_B200_BWD_MMA") == "2" else 1e-3)
+
+
 def test_tf32_training_gradients_close():
     g = np.load(os.path.join(GOLDEN, "train_grads.npz"))
     model = make_model("crn_small", precision="tf32").cuda().train()
