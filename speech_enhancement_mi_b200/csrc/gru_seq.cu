@@ -9,6 +9,10 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "se_internal.h"
 
 namespace cg = cooperative_groups;
@@ -109,15 +113,28 @@ __global__ void __launch_bounds__(kWarps * 32) gru_seq_fwd_kernel(GruSeqParams p
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kClWarps = 16;  // x 2 units = 32 units per CTA
 
+// one lane of a converged warp; with the operands warp-uniform, ptxas issues the guarded instruction once from the
+// uniform datapath instead of wrapping it into a per-lane BRA.U.ANY loop (as it does behind `if (lane == 0)`)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t mbar, uint32_t parity) {
+// the plain form, as for any TMA-filled buffer: data and completion arrive through the async proxy; the
+// .acquire.cluster form only adds an L1 invalidation (CCTL.IVALL) per thread and step
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
     uint32_t done = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(mbar), "r"(parity)
@@ -125,22 +142,54 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t mbar, uint32_t parity
     }
 }
 
+// Sums of eight per-lane accumulators over the warp in 9 shuffles (instead of 8 x 5): each butterfly level halves the
+// number of live values, the kept half chosen by the lane's bit.  Returns in EVERY lane the total of accumulator lane / 4.
+__device__ __forceinline__ float fold8(float (&a)[8], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+    float b[4], c[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = b4 ? a[i] : a[i + 4];
+        b[i] = (b4 ? a[i + 4] : a[i]) + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = b3 ? b[i] : b[i + 2];
+        c[i] = (b3 ? b[i + 2] : b[i]) + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    float d = (b2 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, b2 ? c[0] : c[1], 4);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+
+// MUFU forms (ex2 / rcp, ~2 ulp): a dozen instructions for the three activations of a cell instead of ~150 for expf,
+// tanhf and two IEEE divisions -- the cell is the serial stretch of every step.  |error| < 3e-7 absolute.
+__device__ __forceinline__ float fast_sigmoid(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return r;
+}
+__device__ __forceinline__ float fast_tanh(float x) { return 2.0f * fast_sigmoid(2.0f * x) - 1.0f; }
+
 template <int KPL>  // H / 32 = CTAs per cluster
 __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_fwd_cluster_kernel(GruSeqParams p, int SG, int upc) {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) unsigned long long mbar[2];
     constexpr int H = 32 * KPL;
-    float* hb = sm;                       // [2][upc][H]
-    float* gst = sm + 2 * upc * H;        // [2][upc][kClWarps][8]: r0 r1 z0 z1 n0 n1 of the warp's two units
+    float* hb = sm;                          // [2][upc][H]   h of the step, every CTA holds all of it
+    float* gst = hb + 2 * upc * H;           // [2][upc][3][32] input projections (r, z, n) of the CTA's 32 units
+    float* dots = gst + 2 * upc * 96;        // [upc][3][32]  W_hh . h of the CTA's 32 units
+    float* outst = dots + upc * 96;          // [2][upc][32]  the CTA's new values, source of the bulk copies
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rank = blockIdx.x % KPL, sg = blockIdx.x / KPL;
-    const int j0 = rank * 32 + warp * 2;  // first hidden unit of this warp
+    const int j0 = rank * 32 + warp * 2;  // first hidden unit of this warp's dot products
     const int T = p.T;
-    int mine = 0;  // utterances of this cluster
+    int mine = 0;  // utterances of this cluster: sg, sg + SG, ...
     for (int u = 0; u < upc; ++u) mine += (sg + u * SG < p.nb) ? 1 : 0;
-    const uint32_t tx_bytes = (uint32_t)mine * (H - 32) * sizeof(float);  // the own 32 values are written in place
+    const uint32_t tx_bytes = (uint32_t)mine * H * sizeof(float);
     float w[6][KPL];  // rows r(j0) r(j0+1) z(j0) z(j0+1) n(j0) n(j0+1)
-    float bh = 0.f, bz = 0.f, bn = 0.f;  // lanes 0, 1: b_hh of the lane's unit
 #pragma unroll
     for (int gte = 0; gte < 3; ++gte)
 #pragma unroll
@@ -148,118 +197,159 @@ __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_fwd_cluster_kernel(G
 #pragma unroll
             for (int q = 0; q < KPL; ++q)
                 w[2 * gte + u][q] = p.Whh[(long long)(gte * H + j0 + u) * p.Kp + lane + 32 * q];
-    if (lane < 2) {
-        bh = p.bhh[j0 + lane];
-        bz = p.bhh[H + j0 + lane];
-        bn = p.bhh[2 * H + j0 + lane];
+    // warp u finishes the cell of utterance u for all 32 units of the CTA (lane = unit): the activations run once per CTA
+    // with full warps instead of in two lanes of every warp (which made the step issue-bound: 481 instructions per warp
+    // and step)
+    const int jc = rank * 32 + lane;
+    float bh = 0.f, bz = 0.f, bn = 0.f;
+    if (warp < mine) {
+        bh = p.bhh[jc];
+        bz = p.bhh[H + jc];
+        bn = p.bhh[2 * H + jc];
     }
     // state entering chunk 0 (slot 0 of hseq, written by the caller)
-    for (int u = 0; u < upc; ++u) {
+    for (int u = 0; u < mine; ++u) {
         const int i = sg + u * SG;
-        for (int k = threadIdx.x; k < H; k += blockDim.x)
-            hb[u * H + k] = i < p.nb ? p.hseq[(long long)i * p.hB + k] : 0.f;
+        for (int k = threadIdx.x; k < H; k += blockDim.x) hb[u * H + k] = p.hseq[(long long)i * p.hB + k];
     }
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar[b])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    auto stage_gi = [&](int buf, int n, int t) {
-        if (lane < 6) {
-            for (int u = 0; u < upc; ++u) {
-                const int i = sg + u * SG;
-                if (i >= p.nb) break;
-                const float* g = p.gi + ((long long)n * p.nb + i) * p.giB + (long long)t * 3 * H + (lane >> 1) * H + j0 + (lane & 1);
-                const uint32_t dst = smem_addr(gst + ((buf * upc + u) * kClWarps + warp) * 8 + lane);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g) : "memory");
-            }
+    auto stage_gi = [&](int buf, int step) {  // cell warps: the projections of utterance `warp` at `step`
+        const int n = step / T, t = step - n * T;
+        const float* g = p.gi + ((long long)n * p.nb + sg + warp * SG) * p.giB + (long long)t * 3 * H + jc;
+#pragma unroll
+        for (int gte = 0; gte < 3; ++gte) {
+            const uint32_t dst = smem_addr(gst + ((buf * upc + warp) * 3 + gte) * 32 + lane);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(g + gte * H) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    stage_gi(0, 0, 0);
+    if (warp < mine) stage_gi(0, 0);
     __syncthreads();
     cluster_arrive();  // every CTA of the cluster runs and has its mbarriers before anyone stores into it
     cluster_wait();
     const int steps = p.N * T;
     for (int step = 0; step < steps; ++step) {
-        const int n = step / T, t = step - n * T;
         const int cur = step & 1;
-        if (step > 0) mbar_wait_cluster(smem_addr(&mbar[cur]), ((step - 1) >> 1) & 1);
-        if (threadIdx.x == 0 && step + 1 < steps)  // the buffer filled during this step
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&mbar[cur ^ 1])), "r"(tx_bytes)
-                         : "memory");
-        // the projections of THIS step were committed one group earlier
-        if (step + 1 < steps) {
-            stage_gi(cur ^ 1, (step + 1) / T, (step + 1) % T);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncwarp();
-        for (int u = 0; u < upc; ++u) {
-            const int i = sg + u * SG;
-            if (i >= p.nb) break;
-            const long long s = (long long)n * p.nb + i;
+        if (step > 0) mbar_wait(smem_addr(&mbar[cur]), ((step - 1) >> 1) & 1);
+        for (int u = 0; u < mine; ++u) {
             const float* h = hb + (cur * upc + u) * H;
-            float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < KPL; ++q) {
                 const float hv = h[lane + 32 * q];
 #pragma unroll
                 for (int r = 0; r < 6; ++r) a[r] = fmaf(w[r][q], hv, a[r]);
             }
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1)
-#pragma unroll
-                for (int r = 0; r < 6; ++r) a[r] += __shfl_xor_sync(0xffffffffu, a[r], off);
-            float hnew = 0.f;
-            if (lane < 2) {
-                const float* gs = gst + ((cur * upc + u) * kClWarps + warp) * 8;
-                const float gr = gs[lane], gz = gs[2 + lane], gn = gs[4 + lane];
-                const float ar = lane ? a[1] : a[0], az = lane ? a[3] : a[2], an = lane ? a[5] : a[4];
-                const float hj = h[j0 + lane];
-                const float r = sigmoidf_(gr + ar + bh);
-                const float z = sigmoidf_(gz + az + bz);
-                const float c = tanhf(gn + r * (an + bn));
-                hnew = (1.0f - z) * c + z * hj;
-                p.hseq[s * p.hB + (long long)(t + 1) * H + j0 + lane] = hnew;
-                if (t == 0 && n > 0) p.hseq[s * p.hB + j0 + lane] = hj;  // slot 0 = state entering the chunk (backward reads it)
-                hb[((cur ^ 1) * upc + u) * H + j0 + lane] = hnew;
-            }
+            const float tot = fold8(a, lane);  // accumulator lane / 4 = 2 * gate + unit
+            if ((lane & 3) == 0 && lane < 24) dots[(u * 3 + (lane >> 3)) * 32 + warp * 2 + ((lane >> 2) & 1)] = tot;
         }
-        if (step + 1 == steps) break;
-        // the CTA's 32 new values are in place in its own copy; one 128-byte bulk copy per peer carries them (and their
-        // completion) into the others' copies -- 4-byte st.async's cost the receiver one mbarrier update each (512 per
-        // step: 1.7 us per step)
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
-        if (warp == 0 && lane < KPL && lane != rank) {
-            for (int u = 0; u < mine; ++u) {
-                const uint32_t src = smem_addr(hb + ((cur ^ 1) * upc + u) * H + rank * 32);
-                uint32_t remote, rbar;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(src), "r"(lane));
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_addr(&mbar[cur ^ 1])), "r"(lane));
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], 128, [%2];" ::"r"(remote),
-                    "r"(src), "r"(rbar)
-                    : "memory");
+        if (warp >= mine) continue;
+        // ---- cell of utterance `warp` (lane = unit).  This single-warp stretch is the critical path of the step (every
+        // other warp of the cluster waits for its result), so it is kept short: MUFU activations, 16-byte st.async sends
+        // straight from the lanes, and everything that can wait (next step's projections, the hseq stores) after them
+        const int u = warp;
+        if (warp == 0 && lane == 0 && step + 1 < steps)  // the buffer filled during this step
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&mbar[cur ^ 1])), "r"(tx_bytes)
+                         : "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");  // the projections of this step (staged one step earlier)
+        const float* gs = gst + (cur * upc + u) * 96;
+        const float* d = dots + u * 96;
+        const float hj = hb[(cur * upc + u) * H + jc];
+        const float r = fast_sigmoid(gs[lane] + d[lane] + bh);
+        const float z = fast_sigmoid(gs[32 + lane] + d[32 + lane] + bz);
+        const float c = fast_tanh(gs[64 + lane] + r * (d[64 + lane] + bn));
+        const float hnew = (1.0f - z) * c + z * hj;
+        if (step + 1 < steps) {
+            // lane L sends the 16-byte chunk L % 8 of the CTA's 32 new values to the CTAs L / 8 + 4 k (the own one
+            // included); every store carries its completion to the receiver's mbarrier
+            float* mine_out = outst + (cur * upc + u) * 32;
+            mine_out[lane] = hnew;
+            __syncwarp();
+            const float4 chunk = *reinterpret_cast<const float4*>(mine_out + 4 * (lane & 7));
+            const uint32_t dstl = smem_addr(hb + ((cur ^ 1) * upc + u) * H + rank * 32 + 4 * (lane & 7));
+            const uint32_t lbar = smem_addr(&mbar[cur ^ 1]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int peer = (lane >> 3) + 4 * k;
+                if (peer < KPL) {
+                    uint32_t remote, rbar;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(dstl), "r"(peer));
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(lbar), "r"(peer));
+                    asm volatile(
+                        "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                            remote),
+                        "r"(__float_as_uint(chunk.x)), "r"(__float_as_uint(chunk.y)), "r"(__float_as_uint(chunk.z)),
+                        "r"(__float_as_uint(chunk.w)), "r"(rbar)
+                        : "memory");
+                }
             }
+            stage_gi(cur ^ 1, step + 1);
         }
+        const int n = step / T, t = step - n * T;
+        const long long s = (long long)n * p.nb + sg + u * SG;
+        p.hseq[s * p.hB + (long long)(t + 1) * H + jc] = hnew;
+        if (t == 0 && n > 0) p.hseq[s * p.hB + jc] = hj;  // slot 0 = state entering the chunk (backward reads it)
     }
     cluster_arrive();  // nobody leaves while a peer may still address its shared memory
     cluster_wait();
+}
+
+// Co-resident clusters of `kernel` (cluster size KPL, `smem` dynamic bytes) on the current device; 0 = cannot be placed.
+// The occupancy query and the non-portable-size opt-in cost tens of milliseconds of host time: once per (device, kernel).
+template <typename K>
+int cluster_capacity(K kernel, int KPL, size_t smem, int* out) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, int> cache;
+    int dev = 0;
+    SE_CUDA_OK(cudaGetDevice(&dev));
+    const auto key = std::make_pair(reinterpret_cast<const void*>(kernel), dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+        *out = it->second;
+        return 0;
+    }
+    int ncl = 0;
+    bool ok = true;
+    if (KPL > 8 && cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = false;
+    if (ok && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) ok = false;
+    if (ok) {
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = KPL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cfg.blockDim = dim3(kClWarps * 32);
+        cfg.gridDim = dim3(KPL);
+        cfg.dynamicSmemBytes = smem;
+        if (cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg) != cudaSuccess) ncl = 0;
+    }
+    cudaGetLastError();
+    cache[key] = ncl;
+    *out = ncl;
+    return 0;
 }
 
 template <int KPL>
 int launch_cluster(const GruSeqParams& p, cudaStream_t st, bool* launched) {
     *launched = false;
     auto kernel = gru_seq_fwd_cluster_kernel<KPL>;
-    if (KPL > 8) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-    }
+    auto smem_of = [&](int upc) { return (size_t)(2 * upc * 32 * KPL + 2 * upc * 96 + upc * 96 + 2 * upc * 32) * sizeof(float); };
+    int ncl = 0;
+    if (cluster_capacity(kernel, KPL, smem_of(1), &ncl)) return 1;
+    if (ncl < 1) return 0;  // this device cannot place the cluster: the caller takes the cooperative kernel
+    int SG = p.nb < ncl ? p.nb : ncl;
+    int upc = (p.nb + SG - 1) / SG;
+    SG = (p.nb + upc - 1) / upc;
+    if (smem_of(upc) > 200 * 1024 || upc > kClWarps) return 0;  // one cell warp per utterance of the cluster
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -270,19 +360,6 @@ int launch_cluster(const GruSeqParams& p, cudaStream_t st, bool* launched) {
     cfg.numAttrs = 1;
     cfg.blockDim = dim3(kClWarps * 32);
     cfg.stream = st;
-    auto smem_of = [&](int upc) { return (size_t)(2 * upc * 32 * KPL + 2 * upc * kClWarps * 8) * sizeof(float); };
-    cfg.gridDim = dim3(KPL);
-    cfg.dynamicSmemBytes = smem_of(1);
-    int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg) != cudaSuccess || ncl < 1) {
-        cudaGetLastError();
-        return 0;  // this device cannot place the cluster: the caller takes the cooperative kernel
-    }
-    int SG = p.nb < ncl ? p.nb : ncl;
-    int upc = (p.nb + SG - 1) / SG;
-    SG = (p.nb + upc - 1) / upc;
-    if (smem_of(upc) > 200 * 1024) return 0;
-    SE_DYN_SMEM(kernel, smem_of(upc));
     cfg.gridDim = dim3(KPL * SG);
     cfg.dynamicSmemBytes = smem_of(upc);
     SE_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p, SG, upc));
@@ -362,10 +439,11 @@ __global__ void __launch_bounds__(kWarps * 32) gru_seq_bwd_kernel(GruSeqBwdParam
 // Cluster-resident backward.  The chunk-streams are independent sequences of T steps (the carried state is detached),
 // so nothing needs the whole grid: a cluster of H / 32 CTAs holds W_hh by columns in registers (a warp owns two
 // columns = two hidden units on the input side, same lane-strided order and butterfly as above: bit-identical) and walks
-// UP sequences at a time from t = T - 1 down to 0.  Per step: the cell adjoint of the warp's two units (lanes 0, 1; the
-// recurrent part of d loss / d h stays in a register of those lanes, it never leaves the warp), the 3H values of
-// d loss / d gh all-gathered into every CTA's shared memory by bulk copies with complete_tx (see the forward),
-// then the warp's two dot products over them.  The cell inputs of the next step arrive by cp.async.
+// UP sequences at a time from t = T - 1 down to 0.  Per step: the cell adjoint of the CTA's 32 units by one warp per
+// sequence (lane = unit), the 3H values of d loss / d gh all-gathered into every CTA's shared memory by bulk copies
+// with complete_tx (see the forward), then every warp's two dot products per sequence over them (one 9-shuffle fold
+// for all of them), handed back to the cell warps through shared memory.  The cell inputs of the next step arrive by
+// cp.async.
 // The cooperative kernel above spent two barriers over ~1000 CTAs per step and walked a group's streams one after
 // another: 0.44 ms per layer for 24 sequences, 2.3 ms for 192.
 // ---------------------------------------------------------------------------------------------------------------
@@ -374,13 +452,16 @@ constexpr int kBwdUP = 4;  // sequences in flight per cluster
 template <int KPL>
 __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_bwd_cluster_kernel(GruSeqBwdParams p, int NCL) {
     constexpr int H = 32 * KPL, H3 = 3 * H, UP = kBwdUP;
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) unsigned long long mbar[2];
-    float* gb = sm;                          // [2][UP][3H] d loss / d gh of the step
-    float* stg = sm + 2 * UP * H3;           // [2][UP][kClWarps][16]: per unit a_r a_z a_n h_r h_z h_n h_prev dH
+    float* gb = sm;                    // [2][UP][KPL][3][32] d loss / d gh of the step, every CTA holds all of it
+    float* stg = gb + 2 * UP * H3;     // [2][UP][8][32] cell inputs a_r a_z a_n h_r h_z h_n h_prev dH of the CTA's 32 units
+    float* accs = stg + 2 * UP * 256;  // [UP][32] W_hh^T . d gh of the CTA's 32 units
+    float* outst = accs + UP * 32;     // [2][UP][3][32] the CTA's part of d gh, source of the bulk copies
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rank = blockIdx.x % KPL, cl = blockIdx.x / KPL;
-    const int j0 = rank * 32 + warp * 2;
+    const int j0 = rank * 32 + warp * 2;  // columns of this warp's dot products
+    const int jc = rank * 32 + lane;      // unit of this lane in the cell phase (warps 0 .. UP-1, warp = sequence)
     const int T = p.T;
     const int nseq = cl < p.B ? (p.B - cl + NCL - 1) / NCL : 0;  // sequences cl, cl + NCL, ...
     const int ngroups = (nseq + UP - 1) / UP;
@@ -394,126 +475,111 @@ __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_bwd_cluster_kernel(G
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar[b])) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // cell inputs of step `it` (group it / T, t = T - 1 - it % T) into staging buffer it & 1
+    // cell inputs of step `it` (group it / T, t = T - 1 - it % T) of sequence `warp` of the group into staging buffer it & 1
     auto stage = [&](int it) {
         const int grp = it / T, t = T - 1 - (it - grp * T);
-        if (lane < 16) {
-            const int unit = lane >> 3, v = lane & 7, j = j0 + unit;
+        const int q = grp * UP + warp;
+        if (q < nseq) {
+            const long long s = cl + (long long)q * NCL;
+            const float* a = p.gi + s * p.gB + (long long)t * H3 + jc;
+            const float* h = p.gh + s * p.gB + (long long)t * H3 + jc;
+            const uint32_t dst = smem_addr(stg + (((it & 1) * UP + warp) * 8) * 32 + lane);
 #pragma unroll
-            for (int u = 0; u < UP; ++u) {
-                const int q = grp * UP + u;
-                if (q >= nseq) break;
-                const long long s = cl + (long long)q * NCL;
-                const float* src;
-                if (v < 3)
-                    src = p.gi + s * p.gB + (long long)t * H3 + v * H + j;
-                else if (v < 6)
-                    src = p.gh + s * p.gB + (long long)t * H3 + (v - 3) * H + j;
-                else if (v == 6)
-                    src = p.hseq + s * p.hB + (long long)t * H + j;
-                else
-                    src = p.dH + s * p.hB + (long long)(t + 1) * H + j;
-                const uint32_t dst = smem_addr(stg + ((((it & 1) * UP + u) * kClWarps + warp) * 16 + lane));
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+            for (int gte = 0; gte < 3; ++gte) {
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + gte * 128), "l"(a + gte * H) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + (3 + gte) * 128), "l"(h + gte * H) : "memory");
             }
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 6 * 128), "l"(p.hseq + s * p.hB + (long long)t * H + jc)
+                         : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 7 * 128),
+                         "l"(p.dH + s * p.hB + (long long)(t + 1) * H + jc)
+                         : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     const int iters = ngroups * T;
-    if (iters > 0) stage(0);
+    if (iters > 0 && warp < UP) stage(0);
     __syncthreads();
     cluster_arrive();
     cluster_wait();
-    float rec[UP];  // lanes 0, 1: d loss / d h_t of the lane's unit arriving through the recurrence
-    int x = 0;      // exchanges so far (steps with t > 0)
+    float keep = 0.f;  // cell warps: dh * z of the lane's unit
+    int x = 0;         // exchanges so far (steps with t > 0)
     for (int it = 0; it < iters; ++it) {
         const int grp = it / T, t = T - 1 - (it - grp * T);
         int act = nseq - grp * UP;
         if (act > UP) act = UP;
-        if (t == T - 1) {
-#pragma unroll
-            for (int u = 0; u < UP; ++u) rec[u] = 0.f;
-        }
-        if (threadIdx.x == 0 && t > 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&mbar[x & 1])),
-                         "r"((uint32_t)(act * (H3 - 96) * sizeof(float)))
-                         : "memory");
-        if (it + 1 < iters) {
-            stage(it + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncwarp();
-        float keep[UP];  // dh * z
-#pragma unroll
-        for (int u = 0; u < UP; ++u) {
-            keep[u] = 0.f;
-            if (u >= act) continue;
-            const long long s = cl + (long long)(grp * UP + u) * NCL;
-            float dar = 0.f, daz = 0.f, danr = 0.f;
-            if (lane < 2) {
-                const float* in = stg + ((((it & 1) * UP + u) * kClWarps + warp) * 16 + 8 * lane);
-                const float r = sigmoidf_(in[0] + in[3]);
-                const float z = sigmoidf_(in[1] + in[4]);
-                const float hn = in[5];
-                const float c = tanhf(in[2] + r * hn);
-                const float hp = in[6];
-                const float dh = in[7] + rec[u];
-                const float dan = dh * (1.f - z) * (1.f - c * c);
-                daz = dh * (hp - c) * z * (1.f - z);
-                dar = dan * hn * r * (1.f - r);
-                danr = dan * r;
-                keep[u] = dh * z;
-                const int j = j0 + lane;
-                float* o = p.dgi + s * p.gB + (long long)t * H3;
-                float* q = p.dgh + s * p.gB + (long long)t * H3;
-                o[j] = dar;
-                o[H + j] = daz;
-                o[2 * H + j] = dan;
-                q[j] = dar;
-                q[H + j] = daz;
-                q[2 * H + j] = danr;
-            }
-            if (t > 0 && lane < 2) {  // own segment of the gathered vector, layout [rank][gate][32]
-                float* own = gb + ((x & 1) * UP + u) * H3 + rank * 96 + warp * 2 + lane;
+        if (warp < act) {  // cell adjoint of sequence `warp` of the group, lane = unit
+            // d loss / d h_t arriving through the recurrence: dh_{t+1} z + W_hh^T d gh_{t+1} (the dot products of the
+            // previous step, behind its __syncthreads)
+            const float rec = t == T - 1 ? 0.f : keep + accs[warp * 32 + lane];
+            if (warp == 0 && lane == 0 && t > 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&mbar[x & 1])),
+                             "r"((uint32_t)(act * H3 * sizeof(float)))
+                             : "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");  // the cell inputs of this step (staged one step earlier)
+            const long long s = cl + (long long)(grp * UP + warp) * NCL;
+            const float* in = stg + (((it & 1) * UP + warp) * 8) * 32 + lane;
+            const float r = fast_sigmoid(in[0] + in[3 * 32]);
+            const float z = fast_sigmoid(in[32] + in[4 * 32]);
+            const float hn = in[5 * 32];
+            const float c = fast_tanh(in[2 * 32] + r * hn);
+            const float hp = in[6 * 32];
+            const float dh = in[7 * 32] + rec;
+            const float dan = dh * (1.f - z) * (1.f - c * c);
+            const float daz = dh * (hp - c) * z * (1.f - z);
+            const float dar = dan * hn * r * (1.f - r);
+            keep = dh * z;
+            if (t > 0) {  // all-gather: one 384-byte bulk copy per CTA of the cluster (the own one included); before the
+                          // global stores, which the fence would otherwise wait for
+                float* own = outst + ((x & 1) * UP + warp) * 96 + lane;
                 own[0] = dar;
                 own[32] = daz;
-                own[64] = danr;
+                own[64] = dan * r;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                const uint32_t src = smem_addr(outst + ((x & 1) * UP + warp) * 96);
+                const uint32_t dstl = smem_addr(gb + ((x & 1) * UP + warp) * H3 + rank * 96);
+                const uint32_t lbar = smem_addr(&mbar[x & 1]);
+#pragma unroll
+                for (int peer = 0; peer < KPL; ++peer) {
+                    uint32_t remote, rbar;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(dstl), "r"(peer));
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(lbar), "r"(peer));
+                    if (elect_one())
+                        asm volatile(
+                            "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], 384, [%2];" ::"r"(
+                                remote),
+                            "r"(src), "r"(rbar)
+                            : "memory");
+                }
             }
+            if (it + 1 < iters) stage(it + 1);  // after the sends: off the critical path of the step
+            float* o = p.dgi + s * p.gB + (long long)t * H3;
+            float* q = p.dgh + s * p.gB + (long long)t * H3;
+            o[jc] = dar;
+            o[H + jc] = daz;
+            o[2 * H + jc] = dan;
+            q[jc] = dar;
+            q[H + jc] = daz;
+            q[2 * H + jc] = dan * r;
         }
         if (t == 0) continue;  // the state entering the chunk is detached (CRN_ELU.py:185)
-        // all-gather: one 384-byte bulk copy per peer and sequence carries the CTA's 96 values and their completion
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-        if (warp == 0 && lane < KPL && lane != rank) {
-            for (int u = 0; u < act; ++u) {
-                const uint32_t src = smem_addr(gb + ((x & 1) * UP + u) * H3 + rank * 96);
-                uint32_t remote, rbar;
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(src), "r"(lane));
-                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_addr(&mbar[x & 1])), "r"(lane));
-                asm volatile(
-                    "cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], 384, [%2];" ::"r"(remote),
-                    "r"(src), "r"(rbar)
-                    : "memory");
-            }
-        }
-        mbar_wait_cluster(smem_addr(&mbar[x & 1]), (x >> 1) & 1);
+        mbar_wait(smem_addr(&mbar[x & 1]), (x >> 1) & 1);
+        float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // (sequence u, column c) at 2 u + c
 #pragma unroll
         for (int u = 0; u < UP; ++u) {
             if (u >= act) continue;
             const float* g = gb + ((x & 1) * UP + u) * H3;
-            float a0 = 0.f, a1 = 0.f;
 #pragma unroll
             for (int q = 0; q < 3 * KPL; ++q) {
                 const float gv = g[((q % KPL) * 3 + q / KPL) * 32 + lane];  // row n = lane + 32 q = gate (q / KPL), rank (q % KPL)
-                a0 = fmaf(wc[0][q], gv, a0);
-                a1 = fmaf(wc[1][q], gv, a1);
+                a[2 * u] = fmaf(wc[0][q], gv, a[2 * u]);
+                a[2 * u + 1] = fmaf(wc[1][q], gv, a[2 * u + 1]);
             }
-            a0 = warp_sum(a0);
-            a1 = warp_sum(a1);
-            rec[u] = keep[u] + (lane ? a1 : a0);
         }
+        const float tot = fold8(a, lane);
+        if ((lane & 3) == 0 && (lane >> 3) < act) accs[(lane >> 3) * 32 + warp * 2 + ((lane >> 2) & 1)] = tot;
+        __syncthreads();
         ++x;
     }
     cluster_arrive();  // nobody leaves while a peer may still address its shared memory
@@ -524,14 +590,11 @@ template <int KPL>
 int launch_cluster_bwd(const GruSeqBwdParams& p, cudaStream_t st, bool* launched) {
     *launched = false;
     auto kernel = gru_seq_bwd_cluster_kernel<KPL>;
-    if (KPL > 8) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-            cudaGetLastError();
-            return 0;
-        }
-    }
-    const size_t smem = (size_t)(2 * kBwdUP * 3 * 32 * KPL + 2 * kBwdUP * kClWarps * 16) * sizeof(float);
-    SE_DYN_SMEM(kernel, smem);
+    const size_t smem = (size_t)(2 * kBwdUP * 3 * 32 * KPL + 2 * kBwdUP * 256 + kBwdUP * 32 + 2 * kBwdUP * 96) * sizeof(float);
+    int ncl = 0;
+    if (cluster_capacity(kernel, KPL, smem, &ncl)) return 1;
+    if (ncl < 1) return 0;
+    const int NCL = p.B < ncl ? p.B : ncl;  // one wave of clusters, sequences cl, cl + NCL, ... each
     cudaLaunchConfig_t cfg{};
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -542,16 +605,8 @@ int launch_cluster_bwd(const GruSeqBwdParams& p, cudaStream_t st, bool* launched
     cfg.numAttrs = 1;
     cfg.blockDim = dim3(kClWarps * 32);
     cfg.stream = st;
-    cfg.gridDim = dim3(KPL);
-    cfg.dynamicSmemBytes = smem;
-    int ncl = 0;
-    if (cudaOccupancyMaxActiveClusters(&ncl, kernel, &cfg) != cudaSuccess || ncl < 1) {
-        cudaGetLastError();
-        return 0;
-    }
-    // one wave of clusters; fewer when that keeps kBwdUP sequences in flight per cluster would leave clusters idle
-    int NCL = p.B < ncl ? p.B : ncl;
     cfg.gridDim = dim3(KPL * NCL);
+    cfg.dynamicSmemBytes = smem;
     SE_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, p, NCL));
     *launched = true;
     return 0;

@@ -234,31 +234,44 @@ __global__ void __launch_bounds__(kThreads) wgrad_mma_kernel(GemmParams p, const
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
     if (tid < 64) s_bias[tid] = 0.f;
     const int lr = tid >> 4, lu = tid & 15;  // loader role: row lr (+16), 16-byte unit lu
-    for (int m0 = m_begin; m0 < m_end; m0 += TM_BM) {
+    const bool k_ok = k0 + 4 * lu < p.K;
+    const int koff_l = k_ok ? __ldg(p.koff + ((k0 + 4 * lu) >> 2)) : 0;
+    // the rows of a stage travel global -> registers -> shared memory; the loads of stage s + 1 are issued before the
+    // MMAs of stage s, so their latency is covered by arithmetic instead of by other CTAs only
+    float v[TM_BM / 16][4];
+    float4 a[TM_BM / 16];
+    auto load_stage = [&](int m0) {
 #pragma unroll
         for (int pass = 0; pass < TM_BM / 16; ++pass) {
-            const int r = lr + 16 * pass, m = m0 + r;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int m = m0 + lr + 16 * pass;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[pass][j] = 0.f;
+            a[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (m < m_end) {
                 int f;
                 const long long off = row_off(m, rps, p.Fo, g.sB, g.sT, g.sF, &f);
                 const int nlim = (p.odd_tail && f == p.Fo - 1) ? p.N / 2 : p.N;
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (n0 + 4 * lu + j < nlim) v[j] = G[off + n0 + 4 * lu + j];
-                const int k = k0 + 4 * lu;
-                if (k < p.K)
-                    a = *reinterpret_cast<const float4*>(A + row_off(m, rps, p.Fo, p.sB, p.sT, p.sF) +
-                                                         __ldg(p.koff + (k >> 2)));
+                    if (n0 + 4 * lu + j < nlim) v[pass][j] = G[off + n0 + 4 * lu + j];
+                if (k_ok)
+                    a[pass] = *reinterpret_cast<const float4*>(A + row_off(m, rps, p.Fo, p.sB, p.sT, p.sF) + koff_l);
             }
+        }
+    };
+    if (m_begin < m_end) load_stage(m_begin);
+    for (int m0 = m_begin; m0 < m_end; m0 += TM_BM) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bsum[j] += v[j];
-            store_split4<SPLIT>(&Gs[0][r][4 * lu], &Gs[NS - 1][r][4 * lu], v);
-            const float av[4] = {a.x, a.y, a.z, a.w};
+        for (int pass = 0; pass < TM_BM / 16; ++pass) {
+            const int r = lr + 16 * pass;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bsum[j] += v[pass][j];
+            store_split4<SPLIT>(&Gs[0][r][4 * lu], &Gs[NS - 1][r][4 * lu], v[pass]);
+            const float av[4] = {a[pass].x, a[pass].y, a[pass].z, a[pass].w};
             store_split4<SPLIT>(&As[0][r][4 * lu], &As[NS - 1][r][4 * lu], av);
         }
         __syncthreads();
+        if (m0 + TM_BM < m_end) load_stage(m0 + TM_BM);
 #pragma unroll
         for (int ms = 0; ms < TM_BM; ms += 8) {
             uint32_t ah[4], al[4];
@@ -332,26 +345,36 @@ __global__ void __launch_bounds__(kThreads) dgrad_mma_kernel(GemmParams p, const
     float acc[4][4] = {};
     // blockIdx.z: slice of the reduction (few-row GEMMs such as the GRU projections would otherwise run on 64 CTAs)
     const int n_begin = blockIdx.z * n_per_cta, n_end = min(p.N, n_begin + n_per_cta);
-    for (int n0 = n_begin; n0 < n_end; n0 += TM_BM) {
+    float gv[2][4];
+    float4 wv4[TM_BM / 16];
+    auto load_stage = [&](int n0) {  // next stage into registers, in flight during the MMAs of the current one
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            float v[4];
+        for (int half = 0; half < 2; ++half)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int n = n0 + lc + 4 * half + j;
-                v[j] = (goff >= 0 && n < nlim_l && n < n_end) ? G[goff + n] : 0.f;
+                gv[half][j] = (goff >= 0 && n < nlim_l && n < n_end) ? G[goff + n] : 0.f;
             }
-            store_split4<SPLIT>(&Gs[0][lr][lc + 4 * half], &Gs[NS - 1][lr][lc + 4 * half], v);
-        }
 #pragma unroll
         for (int pass = 0; pass < TM_BM / 16; ++pass) {
-            const int nr = (tid >> 4) + 16 * pass, n = n0 + nr, k = k0 + 4 * (tid & 15);
-            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (n < n_end && k < p.K) w = *reinterpret_cast<const float4*>(W + (long long)n * p.K + k);
-            const float wv[4] = {w.x, w.y, w.z, w.w};
+            const int n = n0 + (tid >> 4) + 16 * pass, k = k0 + 4 * (tid & 15);
+            wv4[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < n_end && k < p.K) wv4[pass] = *reinterpret_cast<const float4*>(W + (long long)n * p.K + k);
+        }
+    };
+    if (n_begin < n_end) load_stage(n_begin);
+    for (int n0 = n_begin; n0 < n_end; n0 += TM_BM) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+            store_split4<SPLIT>(&Gs[0][lr][lc + 4 * half], &Gs[NS - 1][lr][lc + 4 * half], gv[half]);
+#pragma unroll
+        for (int pass = 0; pass < TM_BM / 16; ++pass) {
+            const int nr = (tid >> 4) + 16 * pass;
+            const float wv[4] = {wv4[pass].x, wv4[pass].y, wv4[pass].z, wv4[pass].w};
             store_split4<SPLIT>(&Ws[0][nr][4 * (tid & 15)], &Ws[NS - 1][nr][4 * (tid & 15)], wv);
         }
         __syncthreads();
+        if (n0 + TM_BM < n_end) load_stage(n0 + TM_BM);
 #pragma unroll
         for (int ns = 0; ns < TM_BM; ns += 8) {
             uint32_t ah[4], al[4];
@@ -663,7 +686,7 @@ int launch_wgrad(const GemmParams& p, const float* G, StridedRows g, float* dW, 
     SE_REQUIRE(!p.a_half, "wgrad: fp32 operands only");
     const int bm = mode == BWD_CUDA_CORES ? WG_BM : TM_BM;
     const int kt = (p.K + 63) / 64, nt = (p.N + 63) / 64;
-    int splits = (148 * 4 + kt * nt - 1) / (kt * nt);
+    int splits = (148 * (mode == BWD_CUDA_CORES ? 4 : 6) + kt * nt - 1) / (kt * nt);
     const int max_splits = (p.M + 4 * bm - 1) / (4 * bm);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
