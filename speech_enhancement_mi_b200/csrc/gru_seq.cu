@@ -163,6 +163,18 @@ __device__ __forceinline__ float fold8(float (&a)[8], int lane) {
     return d;
 }
 
+// packed fp32 pairs for fma.rn.f32x2 (sm_100: two fp32 FMAs per issue slot)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float lo_f(unsigned long long v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float hi_f(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
+__device__ __forceinline__ void ffma2(unsigned long long& acc, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+
 // MUFU forms (ex2 / rcp, ~2 ulp): a dozen instructions for the three activations of a cell instead of ~150 for expf,
 // tanhf and two IEEE divisions -- the cell is the serial stretch of every step.  |error| < 3e-7 absolute.
 __device__ __forceinline__ float fast_sigmoid(float x) {
@@ -189,14 +201,30 @@ __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_fwd_cluster_kernel(G
     int mine = 0;  // utterances of this cluster: sg, sg + SG, ...
     for (int u = 0; u < upc; ++u) mine += (sg + u * SG < p.nb) ? 1 : 0;
     const uint32_t tx_bytes = (uint32_t)mine * H * sizeof(float);
-    float w[6][KPL];  // rows r(j0) r(j0+1) z(j0) z(j0+1) n(j0) n(j0+1)
+    // rows r(j0) r(j0+1) z(j0) z(j0+1) n(j0) n(j0+1) of W_hh.  H >= 128: the lane owns k = 128 q4 + 4 lane + {0..3}, held
+    // as (k, k + 1) pairs, so that h arrives by 16-byte loads and a packed fma.rn.f32x2 does two k of a row at once (the
+    // dot products were issue-bound: 16 LDS + 96 FFMA per warp and step become 4 LDS.128 + 48 FFMA2).  Smaller H: lane
+    // owns k = lane + 32 q, scalar.
+    constexpr bool PACK = KPL >= 4;
+    constexpr int NW = PACK ? KPL / 2 : KPL;
+    unsigned long long w2[6][PACK ? NW : 1];
+    float w[6][PACK ? 1 : KPL];
 #pragma unroll
     for (int gte = 0; gte < 3; ++gte)
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < 2; ++u) {
+            const float* row = p.Whh + (long long)(gte * H + j0 + u) * p.Kp;
+            if (PACK) {
 #pragma unroll
-            for (int q = 0; q < KPL; ++q)
-                w[2 * gte + u][q] = p.Whh[(long long)(gte * H + j0 + u) * p.Kp + lane + 32 * q];
+                for (int q = 0; q < NW; ++q) {
+                    const int k = 128 * (q >> 1) + 4 * lane + 2 * (q & 1);
+                    w2[2 * gte + u][q] = pack2(row[k], row[k + 1]);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < KPL; ++q) w[2 * gte + u][q] = row[lane + 32 * q];
+            }
+        }
     // warp u finishes the cell of utterance u for all 32 units of the CTA (lane = unit): the activations run once per CTA
     // with full warps instead of in two lanes of every warp (which made the step issue-bound: 481 instructions per warp
     // and step)
@@ -238,11 +266,26 @@ __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_fwd_cluster_kernel(G
         for (int u = 0; u < mine; ++u) {
             const float* h = hb + (cur * upc + u) * H;
             float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (PACK) {
+                unsigned long long acc[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull};  // (even k, odd k) partial sums
 #pragma unroll
-            for (int q = 0; q < KPL; ++q) {
-                const float hv = h[lane + 32 * q];
+                for (int q4 = 0; q4 < KPL / 4; ++q4) {
+                    const ulonglong2 hv = *reinterpret_cast<const ulonglong2*>(h + 128 * q4 + 4 * lane);
 #pragma unroll
-                for (int r = 0; r < 6; ++r) a[r] = fmaf(w[r][q], hv, a[r]);
+                    for (int r = 0; r < 6; ++r) {
+                        ffma2(acc[r], w2[r][2 * q4], hv.x);
+                        ffma2(acc[r], w2[r][2 * q4 + 1], hv.y);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 6; ++r) a[r] = lo_f(acc[r]) + hi_f(acc[r]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < KPL; ++q) {
+                    const float hv = h[lane + 32 * q];
+#pragma unroll
+                    for (int r = 0; r < 6; ++r) a[r] = fmaf(w[r][q], hv, a[r]);
+                }
             }
             const float tot = fold8(a, lane);  // accumulator lane / 4 = 2 * gate + unit
             if ((lane & 3) == 0 && lane < 24) dots[(u * 3 + (lane >> 3)) * 32 + warp * 2 + ((lane >> 2) & 1)] = tot;

@@ -211,69 +211,106 @@ __device__ __forceinline__ float4 pair_rows(const float (&c)[4], int tq) {
     return odd ? make_float4(r0, r1, c[2], c[3]) : make_float4(c[0], c[1], r0, r1);
 }
 
-// weight gradient: 64 (n) x 64 (k) tile per CTA; warp w owns output rows n0 + 16 (w % 4) and columns k0 + 32 (w / 4)
-// .. + 31 (four n8 tiles); the reduction runs over this CTA's slice of the rows in stages of TM_BM
-template <bool SPLIT>
+// weight gradient.  Two tile shapes: 64 (n) x 64 (k) per CTA -- warp w owns output rows n0 + 16 (w % 4) and columns
+// k0 + 32 (w / 4) .. + 31 (four n8 tiles) -- and, for the few-channel layers (N <= 16: pre-convolutions, first encoder and
+// last decoder level, where a 64-row tile multiplies zeros), 16 (n) x 256 (k): every warp owns 32 columns of the same 16
+// rows.  The reduction runs over this CTA's slice of the GEMM rows in stages of BM; the row offsets of a stage (two
+// integer divisions each) are computed once per row by the first BM threads, one stage ahead, and passed through
+// shared memory; the rows themselves travel global -> registers -> shared memory with the loads of stage s + 1 issued
+// before the MMAs of stage s.
+template <bool SPLIT, bool N16>
 __global__ void __launch_bounds__(kThreads) wgrad_mma_kernel(GemmParams p, const float* __restrict__ G, StridedRows g,
                                                              float* __restrict__ dW, float* __restrict__ dbias,
                                                              int rows_per_cta) {
     constexpr int NS = SPLIT ? 2 : 1;
-    __shared__ __align__(16) uint32_t Gs[NS][TM_BM][TM_LD8];  // [m][n]
-    __shared__ __align__(16) uint32_t As[NS][TM_BM][TM_LD8];  // [m][k]
-    __shared__ float s_bias[64];
+    constexpr int BN = N16 ? 16 : 64, BK = N16 ? 256 : 64, BM = (N16 && SPLIT) ? 16 : TM_BM;
+    constexpr int LDG = BN + 8, LDA = BK + 8;  // = 8 mod 32 banks (24 works as well: tq * 24 + gq are distinct banks)
+    constexpr int UA = BK / 4, RA = kThreads / UA, PA = BM / RA;               // A: units per row, rows per pass, passes
+    constexpr int UG = BN / 4, RG = kThreads / UG, PG = BM > RG ? BM / RG : 1;  // G likewise
+    __shared__ __align__(16) uint32_t Gs[NS][BM][LDG];  // [m][n]
+    __shared__ __align__(16) uint32_t As[NS][BM][LDA];  // [m][k]
+    __shared__ long long s_aoff[2][BM], s_goff[2][BM];
+    __shared__ int s_nlim[2][BM];
+    __shared__ float s_bias[BN];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gq = lane >> 2, tq = lane & 3;
-    const int k0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int k0 = blockIdx.x * BK, n0 = blockIdx.y * BN;
     const int m_begin = blockIdx.z * rows_per_cta;
     const int m_end = min(p.M, m_begin + rows_per_cta);
-    const int nt = (warp & 3) * 16, kh = (warp >> 2) * 32;
+    const int nt = N16 ? 0 : (warp & 3) * 16, kh = N16 ? warp * 32 : (warp >> 2) * 32;
     const int rps = p.Tn * p.Fo;
     const float* A = reinterpret_cast<const float*>(p.A);
     const bool want_bias = dbias != nullptr && blockIdx.x == 0;
     float acc[4][4] = {};
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-    if (tid < 64) s_bias[tid] = 0.f;
-    const int lr = tid >> 4, lu = tid & 15;  // loader role: row lr (+16), 16-byte unit lu
-    const bool k_ok = k0 + 4 * lu < p.K;
-    const int koff_l = k_ok ? __ldg(p.koff + ((k0 + 4 * lu) >> 2)) : 0;
-    // the rows of a stage travel global -> registers -> shared memory; the loads of stage s + 1 are issued before the
-    // MMAs of stage s, so their latency is covered by arithmetic instead of by other CTAs only
-    float v[TM_BM / 16][4];
-    float4 a[TM_BM / 16];
-    auto load_stage = [&](int m0) {
-#pragma unroll
-        for (int pass = 0; pass < TM_BM / 16; ++pass) {
-            const int m = m0 + lr + 16 * pass;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) v[pass][j] = 0.f;
-            a[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < BN) s_bias[tid] = 0.f;
+    const int au = tid % UA, ar = tid / UA, gu = tid % UG, gr = tid / UG;  // loader roles
+    const bool k_ok = k0 + 4 * au < p.K;
+    const int koff_l = k_ok ? __ldg(p.koff + ((k0 + 4 * au) >> 2)) : 0;
+    auto row_offsets = [&](int m0, int buf) {  // threads < BM: one row each
+        if (tid < BM) {
+            const int m = m0 + tid;
+            int f = 0;
+            long long go = 0, ao = 0;
+            int nl = 0;
             if (m < m_end) {
-                int f;
-                const long long off = row_off(m, rps, p.Fo, g.sB, g.sT, g.sF, &f);
-                const int nlim = (p.odd_tail && f == p.Fo - 1) ? p.N / 2 : p.N;
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (n0 + 4 * lu + j < nlim) v[pass][j] = G[off + n0 + 4 * lu + j];
-                if (k_ok)
-                    a[pass] = *reinterpret_cast<const float4*>(A + row_off(m, rps, p.Fo, p.sB, p.sT, p.sF) + koff_l);
+                go = row_off(m, rps, p.Fo, g.sB, g.sT, g.sF, &f);
+                ao = row_off(m, rps, p.Fo, p.sB, p.sT, p.sF);
+                nl = (p.odd_tail && f == p.Fo - 1) ? p.N / 2 : p.N;
             }
+            s_goff[buf][tid] = go;
+            s_aoff[buf][tid] = ao;
+            s_nlim[buf][tid] = nl;  // 0 beyond the slice: nothing is loaded
         }
     };
-    if (m_begin < m_end) load_stage(m_begin);
-    for (int m0 = m_begin; m0 < m_end; m0 += TM_BM) {
+    float v[PG][4];
+    float4 a[PA];
+    auto load_stage = [&](int buf) {
 #pragma unroll
-        for (int pass = 0; pass < TM_BM / 16; ++pass) {
-            const int r = lr + 16 * pass;
+        for (int pass = 0; pass < PG; ++pass) {
+            const int r = gr + RG * pass;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bsum[j] += v[pass][j];
-            store_split4<SPLIT>(&Gs[0][r][4 * lu], &Gs[NS - 1][r][4 * lu], v[pass]);
-            const float av[4] = {a[pass].x, a[pass].y, a[pass].z, a[pass].w};
-            store_split4<SPLIT>(&As[0][r][4 * lu], &As[NS - 1][r][4 * lu], av);
+            for (int j = 0; j < 4; ++j) v[pass][j] = 0.f;
+            if (r < BM) {
+                const int nlim = s_nlim[buf][r];
+                const long long off = s_goff[buf][r];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (n0 + 4 * gu + j < nlim) v[pass][j] = G[off + n0 + 4 * gu + j];
+            }
         }
-        __syncthreads();
-        if (m0 + TM_BM < m_end) load_stage(m0 + TM_BM);
 #pragma unroll
-        for (int ms = 0; ms < TM_BM; ms += 8) {
+        for (int pass = 0; pass < PA; ++pass) {
+            const int r = ar + RA * pass;
+            a[pass] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k_ok && s_nlim[buf][r] > 0) a[pass] = *reinterpret_cast<const float4*>(A + s_aoff[buf][r] + koff_l);
+        }
+    };
+    row_offsets(m_begin, 0);
+    __syncthreads();
+    if (m_begin < m_end) load_stage(0);
+    int buf = 0;
+    for (int m0 = m_begin; m0 < m_end; m0 += BM, buf ^= 1) {
+#pragma unroll
+        for (int pass = 0; pass < PG; ++pass) {
+            const int r = gr + RG * pass;
+            if (r < BM) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bsum[j] += v[pass][j];
+                store_split4<SPLIT>(&Gs[0][r][4 * gu], &Gs[NS - 1][r][4 * gu], v[pass]);
+            }
+        }
+#pragma unroll
+        for (int pass = 0; pass < PA; ++pass) {
+            const int r = ar + RA * pass;
+            const float av[4] = {a[pass].x, a[pass].y, a[pass].z, a[pass].w};
+            store_split4<SPLIT>(&As[0][r][4 * au], &As[NS - 1][r][4 * au], av);
+        }
+        if (m0 + BM < m_end) row_offsets(m0 + BM, buf ^ 1);
+        __syncthreads();
+        if (m0 + BM < m_end) load_stage(buf ^ 1);
+#pragma unroll
+        for (int ms = 0; ms < BM; ms += 8) {
             uint32_t ah[4], al[4];
             ah[0] = Gs[0][ms + tq][nt + gq];
             ah[1] = Gs[0][ms + tq][nt + gq + 8];
@@ -304,18 +341,20 @@ __global__ void __launch_bounds__(kThreads) wgrad_mma_kernel(GemmParams p, const
     // instead of four (the L2 reduction rate, not the arithmetic, bounds the scatter)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float4 v = pair_rows(acc[j], tq);
+        const float4 v4 = pair_rows(acc[j], tq);
         const int k = k0 + kh + 8 * j + 4 * (tq >> 1);
         const int n = n0 + nt + gq + 8 * (tq & 1);
-        if (k < p.K && n < p.N && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f))
-            atomicAdd(reinterpret_cast<float4*>(dW + (long long)n * p.K + k), v);
+        if (k < p.K && n < p.N && (v4.x != 0.f || v4.y != 0.f || v4.z != 0.f || v4.w != 0.f))
+            atomicAdd(reinterpret_cast<float4*>(dW + (long long)n * p.K + k), v4);
     }
     if (want_bias) {  // the raw fp32 values, not their tf32 heads
+        if (gr < BM) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (bsum[j] != 0.f) atomicAdd(&s_bias[4 * lu + j], bsum[j]);
+            for (int j = 0; j < 4; ++j)
+                if (bsum[j] != 0.f) atomicAdd(&s_bias[4 * gu + j], bsum[j]);
+        }
         __syncthreads();
-        if (tid < 64 && n0 + tid < p.N && s_bias[tid] != 0.f) atomicAdd(dbias + n0 + tid, s_bias[tid]);
+        if (tid < BN && n0 + tid < p.N && s_bias[tid] != 0.f) atomicAdd(dbias + n0 + tid, s_bias[tid]);
     }
 }
 
@@ -684,8 +723,10 @@ inline int grid_for(long long n) {
 int launch_wgrad(const GemmParams& p, const float* G, StridedRows g, float* dW, float* dbias, cudaStream_t st, int mode) {
     if (p.M <= 0) return 0;
     SE_REQUIRE(!p.a_half, "wgrad: fp32 operands only");
-    const int bm = mode == BWD_CUDA_CORES ? WG_BM : TM_BM;
-    const int kt = (p.K + 63) / 64, nt = (p.N + 63) / 64;
+    const bool n16 = mode != BWD_CUDA_CORES && p.N <= 16;  // few-channel layers: 16 x 256 tiles
+    const int bm = mode == BWD_CUDA_CORES ? WG_BM : (n16 && mode == BWD_3XTF32) ? 16 : TM_BM;
+    const int bk = n16 ? 256 : 64, bn = n16 ? 16 : 64;
+    const int kt = (p.K + bk - 1) / bk, nt = (p.N + bn - 1) / bn;
     int splits = (148 * (mode == BWD_CUDA_CORES ? 4 : 6) + kt * nt - 1) / (kt * nt);
     const int max_splits = (p.M + 4 * bm - 1) / (4 * bm);
     if (splits > max_splits) splits = max_splits;
@@ -696,10 +737,14 @@ int launch_wgrad(const GemmParams& p, const float* G, StridedRows g, float* dW, 
     const dim3 grid(kt, nt, splits);
     if (mode == BWD_CUDA_CORES)
         wgrad_kernel<<<grid, kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
+    else if (mode == BWD_TF32 && n16)
+        wgrad_mma_kernel<false, true><<<grid, kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
     else if (mode == BWD_TF32)
-        wgrad_mma_kernel<false><<<grid, kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
+        wgrad_mma_kernel<false, false><<<grid, kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
+    else if (n16)
+        wgrad_mma_kernel<true, true><<<grid, kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
     else
-        wgrad_mma_kernel<true><<<grid, kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
+        wgrad_mma_kernel<true, false><<<grid, kThreads, 0, st>>>(p, G, g, dW, dbias, rows);
     SE_CUDA_OK(cudaGetLastError());
     return 0;
 }

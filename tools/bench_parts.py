@@ -171,26 +171,27 @@ def train_step(batch=1, seconds=2.0, steps=6, warmup=2, precision="tf32", graph=
         mix, src = synth.make_mixture(B, L, first_stream=rank * B)
         mix, src = torch.from_numpy(mix).to(dev), torch.from_numpy(src).to(dev)
         lens = torch.full((B,), L, dtype=torch.int32, device=dev)
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        t_opt = 0.0
+        # no host synchronisation inside the timed region (the K steps are bracketed by a barrier + synchronize on both
+        # sides): a per-step synchronize left the GPU idle while the host -- and, data parallel, the slower rank's host --
+        # prepared the next step (2 ranks: 10.8 ms per step against 7.7 ms of device time)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         e0 = None
         for it in range(warmup + steps):
             if it == warmup:
                 _barrier()
                 e0 = torch.cuda.Event(enable_timing=True)
                 e0.record()
-            ev[0].record()
             for _ in range(2):
                 tr.micro_step(mix, src, lens, False, check_nan=False, graph=graph)
-            ev[1].record()
-            tr.optimizer_step()
-            ev[2].record()
             if it >= warmup:
-                torch.cuda.synchronize()
-                t_opt += ev[1].elapsed_time(ev[2])
+                ev[it - warmup][0].record()
+            tr.optimizer_step()
+            if it >= warmup:
+                ev[it - warmup][1].record()
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         _barrier()
+        t_opt = sum(a.elapsed_time(b) for a, b in ev)
         ms = _max_over_ranks(e0.elapsed_time(e1) / steps, dev)
         n_theta = int(tr.theta.numel())
     res = {"metric": "CRN_ELU training: optimizer steps/s (2 micro-steps of forward+loss+backward, all-reduce, clip, Adam)",
