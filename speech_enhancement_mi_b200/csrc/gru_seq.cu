@@ -508,11 +508,28 @@ __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_bwd_cluster_kernel(G
     const int T = p.T;
     const int nseq = cl < p.B ? (p.B - cl + NCL - 1) / NCL : 0;  // sequences cl, cl + NCL, ...
     const int ngroups = (nseq + UP - 1) / UP;
-    float wc[2][3 * KPL];  // columns j0, j0 + 1 of W_hh: rows n = lane + 32 q
+    // columns j0, j0 + 1 of W_hh.  The gathered vector lies in shared memory as [rank][gate][32] blocks; KPL even: the lane
+    // owns the element pair 2 (lane % 16), + 1 of the blocks 2 bb + lane / 16 (8-byte loads, packed fma.rn.f32x2 over the
+    // pair: 24 LDS.64 + 48 FFMA2 per sequence instead of 48 LDS + 96 FFMA); KPL = 1: rows n = lane + 32 q, scalar.
+    constexpr bool PACK = (KPL % 2) == 0;
+    constexpr int NP = 3 * KPL / 2;
+    unsigned long long wc2[2][PACK ? NP : 1];
+    float wc[2][PACK ? 1 : 3 * KPL];
+    const int half = lane >> 4, i0 = 2 * (lane & 15);
 #pragma unroll
-    for (int c = 0; c < 2; ++c)
+    for (int c = 0; c < 2; ++c) {
+        if (PACK) {
 #pragma unroll
-        for (int q = 0; q < 3 * KPL; ++q) wc[c][q] = p.Whh[(long long)(lane + 32 * q) * p.Kp + j0 + c];
+            for (int bb = 0; bb < NP; ++bb) {
+                const int b = 2 * bb + half;  // block = rank * 3 + gate
+                const long long n = (long long)(b % 3) * H + (b / 3) * 32 + i0;
+                wc2[c][bb] = pack2(p.Whh[n * p.Kp + j0 + c], p.Whh[(n + 1) * p.Kp + j0 + c]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 3 * KPL; ++q) wc[c][q] = p.Whh[(long long)(lane + 32 * q) * p.Kp + j0 + c];
+        }
+    }
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&mbar[b])) : "memory");
@@ -613,11 +630,23 @@ __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_bwd_cluster_kernel(G
         for (int u = 0; u < UP; ++u) {
             if (u >= act) continue;
             const float* g = gb + ((x & 1) * UP + u) * H3;
+            if (PACK) {
+                unsigned long long s0 = 0ull, s1 = 0ull;
 #pragma unroll
-            for (int q = 0; q < 3 * KPL; ++q) {
-                const float gv = g[((q % KPL) * 3 + q / KPL) * 32 + lane];  // row n = lane + 32 q = gate (q / KPL), rank (q % KPL)
-                a[2 * u] = fmaf(wc[0][q], gv, a[2 * u]);
-                a[2 * u + 1] = fmaf(wc[1][q], gv, a[2 * u + 1]);
+                for (int bb = 0; bb < NP; ++bb) {
+                    const unsigned long long gv = *reinterpret_cast<const unsigned long long*>(g + (2 * bb + half) * 32 + i0);
+                    ffma2(s0, wc2[0][bb], gv);
+                    ffma2(s1, wc2[1][bb], gv);
+                }
+                a[2 * u] = lo_f(s0) + hi_f(s0);
+                a[2 * u + 1] = lo_f(s1) + hi_f(s1);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 3 * KPL; ++q) {
+                    const float gv = g[((q % KPL) * 3 + q / KPL) * 32 + lane];  // row n = lane + 32 q = gate (q / KPL), rank (q % KPL)
+                    a[2 * u] = fmaf(wc[0][q], gv, a[2 * u]);
+                    a[2 * u + 1] = fmaf(wc[1][q], gv, a[2 * u + 1]);
+                }
             }
         }
         const float tot = fold8(a, lane);
