@@ -254,6 +254,11 @@ struct se_ctx {
     unsigned tc_mask = 0xffffffffu;  // SE_B200_TC_MASK: bit per Stage that may use the tensor-core GEMM (debug)
     std::map<int, cudaGraphExec_t> graphs;  // keyed by B
     cudaStream_t own_stream = nullptr;
+    // training forward: second branch for the layer-1 GRU (input projection + recurrence per chunk group) beside layer 0
+    cudaStream_t pipe_stream = nullptr;
+    cudaEvent_t pipe_ev[17] = {};
+    int gru_pipe = 1;  // SE_B200_GRU_PIPE=0: the two GRU layers one after the other
+    int bwd_overlap = 1;  // SE_B200_BWD_OVERLAP=0: weight gradient, then data gradient, on one stream
 
     // ---- training (se_crn_config.training): chunk-major batch, activations of every layer kept, gradient twins --------
     bool train = false;
@@ -1025,6 +1030,12 @@ int build_ctx(se_ctx* c) {
     c->bwd_mode = c->tf32 ? BWD_TF32 : BWD_3XTF32;
     if (const char* e = getenv("SE_B200_BWD_MMA")) c->bwd_mode = atoi(e);
     SE_REQUIRE(c->bwd_mode >= 0 && c->bwd_mode <= 2, "SE_B200_BWD_MMA must be 0, 1 or 2");
+    if (const char* e = getenv("SE_B200_GRU_PIPE")) c->gru_pipe = atoi(e);
+    if (const char* e = getenv("SE_B200_BWD_OVERLAP")) c->bwd_overlap = atoi(e);
+    if (c->train && (c->gru_pipe || c->bwd_overlap)) {  // created here, not at first use: the first use may sit inside a stream capture
+        SE_CUDA_OK(cudaStreamCreateWithFlags(&c->pipe_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : c->pipe_ev) SE_CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     for (int i = 0; i < c->L; ++i) {
         SE_REQUIRE(g.num_channels[i] % 4 == 0 && g.num_channels[i] > 0, "num_channels must be multiples of 4");
         SE_REQUIRE(!c->half || g.num_channels[i] % 8 == 0, "fp16 mode: num_channels must be multiples of 8");
@@ -2096,6 +2107,59 @@ int train_forward(se_ctx* c, const float* mixture, int nb, long long L, int flag
             i = j;
             continue;
         }
+        // Two GRU layers as a pipeline over chunk groups: layer 0 walks group g + 1 while the second branch runs the
+        // layer-1 input projection and recurrence of group g (each sequence kernel occupies one cluster = 16 SMs, the
+        // serial chain is what costs).  Streams are chunk-major, so a chunk group is a contiguous range of GEMM rows.
+        if (op.kind == OP_GRU_SEQ && op.gru_layer == 0 && c->gru_pipe && c->pipe_stream && N >= 4 && i + 2 < c->ops.size() &&
+            c->ops[i + 1].kind == OP_GEMM && !c->ops[i + 1].chunk_serial && c->ops[i + 1].state_entry < 0 &&
+            !c->ops[i + 1].g.a_half && !c->ops[i + 1].g.out_half && c->ops[i + 2].kind == OP_GRU_SEQ &&
+            c->ops[i + 2].gru_layer == 1) {
+            const Op& proj = c->ops[i + 1];
+            const Op& op1 = c->ops[i + 2];
+            const int groups = N >= 16 ? 8 : N >= 8 ? 4 : 2;
+            auto seq_params = [&](const Op& o, int n0, int n1) {
+                GruSeqParams gp{};
+                gp.Whh = reinterpret_cast<const float*>(o.g.W);
+                gp.Kp = o.g.K;
+                gp.bhh = o.g.bias;
+                gp.gi = c->gi_l[o.gru_layer];
+                gp.giB = (long long)T * 3 * c->H;
+                gp.hseq = c->hseq[o.gru_layer];
+                gp.hB = (long long)(T + 1) * c->H;
+                gp.H = c->H;
+                gp.T = T;
+                gp.nb = nb;
+                gp.N = n1 - n0;
+                gp.n0 = n0;
+                return gp;
+            };
+            for (int gidx = 0; gidx < groups; ++gidx) {
+                const int n0 = (int)((long long)N * gidx / groups), n1 = (int)((long long)N * (gidx + 1) / groups);
+                if (launch_gru_seq_fwd(seq_params(op, n0, n1), st)) return 1;
+                SE_CUDA_OK(cudaEventRecord(c->pipe_ev[gidx], st));
+                SE_CUDA_OK(cudaStreamWaitEvent(c->pipe_stream, c->pipe_ev[gidx], 0));
+                GemmParams g = proj.g;  // rows of the chunk group (whole streams: the tensor-core path keeps its alignment)
+                const int s0 = n0 * nb;
+                g.M = (n1 - n0) * nb * proj.rows_per_stream;
+                // the tensor-core kernel addresses rows as stream b0 + m / rows_per_stream itself; the CUDA-core kernel
+                // starts at the pointers it is given
+                const bool tc = c->tf32 && ((c->tc_mask >> proj.stage) & 1u) && gemm_tf32_supported(g);
+                if (tc) {
+                    g.b0 = s0;
+                    if (launch_gemm_tf32(g, c->pipe_stream)) return 1;
+                } else {
+                    g.A = reinterpret_cast<const float*>(g.A) + (long long)s0 * g.sB;
+                    g.out += (long long)s0 * g.oB;
+                    if (g.out2) g.out2 += (long long)s0 * g.o2B;
+                    if (launch_gemm_fp32(g, c->pipe_stream)) return 1;
+                }
+                if (launch_gru_seq_fwd(seq_params(op1, n0, n1), c->pipe_stream)) return 1;
+            }
+            SE_CUDA_OK(cudaEventRecord(c->pipe_ev[16], c->pipe_stream));
+            SE_CUDA_OK(cudaStreamWaitEvent(st, c->pipe_ev[16], 0));
+            i += 3;
+            continue;
+        }
         if (op.kind == OP_GRU_SEQ) {
             GruSeqParams gp{};
             gp.Whh = reinterpret_cast<const float*>(op.g.W);
@@ -2216,6 +2280,17 @@ float* garena_of(const se_ctx* c, const void* w) {
 int dense_bwd(se_ctx* c, const Op& op, int B, const float* G, StridedRows gs, float* dA, cudaStream_t st) {
     GemmParams g = op.g;
     g.M = B * op.rows_per_stream;
+    // weight and data gradient read the same G and write disjoint buffers: side by side on two branches, joined before
+    // anything downstream may overwrite G (at one piece per rank most of these launches leave SMs idle)
+    if (dA != nullptr && c->pipe_stream && c->bwd_overlap) {
+        SE_CUDA_OK(cudaEventRecord(c->pipe_ev[14], st));
+        SE_CUDA_OK(cudaStreamWaitEvent(c->pipe_stream, c->pipe_ev[14], 0));
+        if (launch_wgrad(g, G, gs, garena_of(c, g.W), garena_of(c, g.bias), c->pipe_stream, c->bwd_mode)) return 1;
+        if (launch_dgrad(g, G, gs, dA, st, c->bwd_mode)) return 1;
+        SE_CUDA_OK(cudaEventRecord(c->pipe_ev[15], c->pipe_stream));
+        SE_CUDA_OK(cudaStreamWaitEvent(st, c->pipe_ev[15], 0));
+        return 0;
+    }
     if (launch_wgrad(g, G, gs, garena_of(c, g.W), garena_of(c, g.bias), st, c->bwd_mode)) return 1;
     if (dA != nullptr && launch_dgrad(g, G, gs, dA, st, c->bwd_mode)) return 1;
     return 0;
@@ -2491,6 +2566,9 @@ int se_ctx_destroy(se_ctx* c) {
     cudaDeviceSynchronize();
     for (auto& kv : c->graphs) cudaGraphExecDestroy(kv.second);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->pipe_stream) cudaStreamDestroy(c->pipe_stream);
+    for (cudaEvent_t e : c->pipe_ev)
+        if (e) cudaEventDestroy(e);
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_in) cudaFree(c->h_in);
     if (c->h_out) cudaFree(c->h_out);

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(kWarps * 32) gru_seq_fwd_kernel(GruSeqParams p
         bz = p.bhh[H + j];
         bn = p.bhh[2 * H + j];
     }
-    for (int n = 0; n < p.N; ++n) {
+    for (int n = p.n0; n < p.n0 + p.N; ++n) {
         for (int t = 0; t < T; ++t) {
             if (active) {
                 for (int i = sg; i < p.nb; i += SG) {
@@ -238,7 +238,9 @@ __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_fwd_cluster_kernel(G
     // state entering chunk 0 (slot 0 of hseq, written by the caller)
     for (int u = 0; u < mine; ++u) {
         const int i = sg + u * SG;
-        for (int k = threadIdx.x; k < H; k += blockDim.x) hb[u * H + k] = p.hseq[(long long)i * p.hB + k];
+        const float* h0 = p.n0 == 0 ? p.hseq + (long long)i * p.hB  // slot 0 of chunk 0, or the last state of chunk n0 - 1
+                                    : p.hseq + ((long long)(p.n0 - 1) * p.nb + i) * p.hB + (long long)T * H;
+        for (int k = threadIdx.x; k < H; k += blockDim.x) hb[u * H + k] = h0[k];
     }
     if (threadIdx.x == 0) {
         for (int b = 0; b < 2; ++b)
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_fwd_cluster_kernel(G
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     auto stage_gi = [&](int buf, int step) {  // cell warps: the projections of utterance `warp` at `step`
-        const int n = step / T, t = step - n * T;
+        const int n = p.n0 + step / T, t = step % T;
         const float* g = p.gi + ((long long)n * p.nb + sg + warp * SG) * p.giB + (long long)t * 3 * H + jc;
 #pragma unroll
         for (int gte = 0; gte < 3; ++gte) {
@@ -333,7 +335,7 @@ __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_fwd_cluster_kernel(G
             }
             stage_gi(cur ^ 1, step + 1);
         }
-        const int n = step / T, t = step - n * T;
+        const int n = p.n0 + step / T, t = step % T;
         const long long s = (long long)n * p.nb + sg + u * SG;
         p.hseq[s * p.hB + (long long)(t + 1) * H + jc] = hnew;
         if (t == 0 && n > 0) p.hseq[s * p.hB + jc] = hj;  // slot 0 = state entering the chunk (backward reads it)

@@ -516,6 +516,7 @@ struct GruSeqParams {
     float* hseq;       // hseq[s*hB + t*H + j], t in [0, T]: slot 0 = state entering the chunk
     long long hB;
     int H, T, nb, N;   // streams s = n*nb + i (chunk n of utterance i); chunk n starts from the last state of chunk n-1
+    int n0;            // first chunk of this launch (chunks n0 .. n0 + N - 1; n0 > 0 continues from chunk n0 - 1)
 };
 struct GruSeqBwdParams {
     const float* Whh;

@@ -119,11 +119,13 @@ def test_student_train_step_matches_oracle_autograd():
 
 
 @pytest.mark.parametrize("env", [{"SE_B200_BWD_MMA": "0"}, {"SE_B200_GRU_CLUSTER": "0"},
-                                 {"SE_B200_BWD_MMA": "0", "SE_B200_GRU_CLUSTER": "0"}, {"SE_B200_BWD_MMA": "2"}],
-                         ids=["bwd_cuda_cores", "gru_cooperative", "round1_backward", "bwd_single_tf32"])
+                                 {"SE_B200_BWD_MMA": "0", "SE_B200_GRU_CLUSTER": "0"}, {"SE_B200_BWD_MMA": "2"},
+                                 {"SE_B200_GRU_PIPE": "0"}],
+                         ids=["bwd_cuda_cores", "gru_cooperative", "round1_backward", "bwd_single_tf32", "gru_layers_serial"])
 def test_backward_kernel_switches_match_reference(env, monkeypatch):
     """Every form of the backward contractions (CUDA cores / 3xTF32 / one tf32 pass on mma.sync, train_kernels.cu) and of
-    the sequence GRU (cluster-resident / cooperative, gru_seq.cu) against the unmodified reference's gradients: the
+    the sequence GRU (cluster-resident / cooperative, gru_seq.cu; the two layers pipelined over chunk groups / one after
+    the other, crn.cu train_forward) against the unmodified reference's gradients: the
     fp32-accurate forms at the tolerance of the default path, the single tf32 pass at 2e-2 of each tensor's peak."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
