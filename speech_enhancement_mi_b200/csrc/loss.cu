@@ -14,6 +14,8 @@
 #include <vector>
 
 #include "../../include/se_b200.h"
+#include <mutex>
+
 #include "se_internal.h"
 
 namespace cg = cooperative_groups;
@@ -483,6 +485,26 @@ int upload_tables() {
     return 0;
 }
 
+// The loss entry points take their scratch from the stream-ordered allocator.  The device's default pool releases unused
+// memory back to the OS at every synchronisation (release threshold 0), so a training loop that reads the loss on the host
+// after each micro-step (train.py:199-206) paid a fresh physical allocation -- milliseconds -- in the next step.  Keep the
+// pool's memory: once per device.
+int keep_pool_memory() {
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    SE_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+        cudaMemPool_t pool;
+        SE_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull;
+        SE_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        done[dev] = true;
+    }
+    return 0;
+}
+
 }  // namespace
 }  // namespace se
 
@@ -496,6 +518,7 @@ int se_cal_si_snr(const float* separated, const float* source, const int32_t* le
     SE_REQUIRE(B > 0 && L > 0, "se_cal_si_snr: empty batch");
     cudaStream_t st = (cudaStream_t)stream;
     float* per = nullptr;
+    if (keep_pool_memory()) return 1;
     SE_CUDA_OK(cudaMallocAsync(&per, sizeof(float) * B, st));
     si_snr_kernel<<<B, kThreads, 0, st>>>(separated, source, length_dev, L, 1e-8f, per, nullptr, 0.f);
     mean_kernel<<<1, 1, 0, st>>>(per, B, 1.0f, out);
@@ -518,6 +541,7 @@ int se_stoi_loss(const float* y_true, const float* y_pred, const int32_t* lens_d
     float* base = nullptr;
     const size_t n_r10 = (size_t)B * 2 * w.L10max, n_sil = (size_t)B * 2 * w.Lsmax, n_en = (size_t)B * w.NFmax,
                  n_oct = (size_t)B * 2 * 15 * w.NSmax;
+    if (keep_pool_memory()) return 1;
     SE_CUDA_OK(cudaMallocAsync(&base, sizeof(float) * (n_r10 + n_sil + n_en + n_oct + B) + sizeof(int) * n_en, st));
     w.r10 = base;
     w.sil = w.r10 + n_r10;
@@ -553,6 +577,7 @@ int se_loss_terms_grad(const float* source, const float* pred, const int32_t* le
     const size_t n_r10 = (size_t)B * 2 * w.L10max, n_sil = (size_t)B * 2 * w.Lsmax, n_en = (size_t)B * w.NFmax,
                  n_oct = (size_t)B * 2 * 15 * w.NSmax, n_spec = (size_t)B * w.NSmax * w.NBmax * 2,
                  n_doct = (size_t)B * 15 * w.NSmax, n_dsil = (size_t)B * w.Lsmax, n_dr10 = (size_t)B * w.L10max;
+    if (keep_pool_memory()) return 1;
     SE_CUDA_OK(cudaMallocAsync(&base,
                                sizeof(float) * (n_r10 + n_sil + n_en + n_oct + n_spec + n_doct + n_dsil + n_dr10 + 2 * B) +
                                    sizeof(int) * 2 * n_en,
@@ -630,6 +655,7 @@ int se_clip_adam_step(float* theta, float* grad, float* m, float* v, int64_t n, 
     SE_REQUIRE(n > 0 && step >= 1, "se_clip_adam_step: bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     double* sq = nullptr;
+    if (keep_pool_memory()) return 1;
     SE_CUDA_OK(cudaMallocAsync(&sq, sizeof(double), st));
     SE_CUDA_OK(cudaMemsetAsync(sq, 0, sizeof(double), st));
     long long g = (n + 511) / 512;
