@@ -98,18 +98,22 @@ __global__ void __launch_bounds__(kWarps * 32) gru_seq_fwd_kernel(GruSeqParams p
 // ---------------------------------------------------------------------------------------------------------------
 // Cluster-resident forward.  The chain above costs a grid-wide barrier plus an L2 round trip of h per step (~3 us x
 // N*T steps: 2.5 of the 3 ms of a training forward).  Here one thread-block CLUSTER of H / 32 CTAs owns a sequence:
-// 16 warps per CTA, a warp owns two hidden units (its six rows of W_hh in registers, same lane-strided order and the
-// same butterfly as above, so the results are bit-identical), every CTA keeps a full copy of h in shared memory
-// (double-buffered), and a step ends with the CTA's 32 new values (written in place into its own copy) going to every
-// peer's copy as ONE 128-byte bulk copy through distributed shared memory that carries its own completion
-// (cp.async.bulk ... complete_tx on the receiver's mbarrier), so a step needs no cluster barrier and no fence:
-// barrier.cluster.arrive.release made every warp wait for its hseq store to reach L2 (measured 2.05 us per step, no
-// better than the grid barrier), and 4-byte st.async's cost the receiver 512 mbarrier updates per step (1.7 us).  A
-// CTA proceeds to step t + 1 when its mbarrier has counted the H - 32 foreign values of step t; a peer can only
-// overwrite the buffer a warp is still reading after this CTA's output of the same step has arrived there, i.e. after
-// the __syncthreads that follows every warp's read.  The input projections of the next step arrive by
-// cp.async while the current one computes.  Utterances are spread over clusters (no dependence between them); a
-// cluster serves its utterances inside the same step.
+//   * 16 warps per CTA, a warp owns two hidden units: its six rows of W_hh stay in registers, h_{t-1} is read from the
+//     CTA's own full copy in shared memory (double-buffered), the six dot products are summed over the warp by a
+//     9-shuffle fold and left in shared memory;
+//   * after ONE __syncthreads a single warp per utterance finishes the cell for the CTA's 32 units (lane = unit) and
+//     sends the 32 new values into every CTA's copy of h -- the own one included -- through distributed shared memory
+//     with 16-byte st.async stores that carry their own completion (complete_tx on the receiver's mbarrier);
+//   * a CTA starts step t + 1 when its mbarrier has counted all H values of step t.  No grid barrier, no cluster barrier,
+//     no fence.  A peer can only overwrite the buffer a warp is still reading after this CTA's values of the same step
+//     have arrived there, and the cell warp sends them after every warp of the CTA has passed the __syncthreads behind
+//     its reads.
+// How it got there (profiles/r02_gru_seq_cluster_stalls.txt): barrier.cluster.arrive.release made every warp wait for its
+// hseq store to reach L2 (2.05 us per step, no better than the grid barrier); 4-byte st.async's cost the receiver 512
+// mbarrier updates per step; the cell in two lanes of every warp made the step issue-bound; a long single-warp cell
+// (expf / tanhf / divisions, 16 bulk copies issued one by one) left the other 15 warps waiting.  The input projections of
+// the next step arrive by cp.async behind the sends.  Utterances are spread over clusters (no dependence between
+// them); a cluster serves its utterances inside the same step, one cell warp each.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kClWarps = 16;  // x 2 units = 32 units per CTA
 
@@ -193,7 +197,7 @@ __global__ void __launch_bounds__(kClWarps * 32, 1) gru_seq_fwd_cluster_kernel(G
     float* hb = sm;                          // [2][upc][H]   h of the step, every CTA holds all of it
     float* gst = hb + 2 * upc * H;           // [2][upc][3][32] input projections (r, z, n) of the CTA's 32 units
     float* dots = gst + 2 * upc * 96;        // [upc][3][32]  W_hh . h of the CTA's 32 units
-    float* outst = dots + upc * 96;          // [2][upc][32]  the CTA's new values, source of the bulk copies
+    float* outst = dots + upc * 96;          // [2][upc][32]  the CTA's new values, re-read as 16-byte chunks by the sending lanes
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rank = blockIdx.x % KPL, sg = blockIdx.x / KPL;
     const int j0 = rank * 32 + warp * 2;  // first hidden unit of this warp's dot products
