@@ -142,6 +142,30 @@ def test_backward_kernel_switches_match_reference(env, monkeypatch):
     _report(grads, g, "small_cont_grad/", 2e-2 if env.get("SE_B200_BWD_MMA") == "2" else 1e-3)
 
 
+def test_cluster_gru_many_utterances_matches_cooperative(monkeypatch):
+    """More utterances than co-resident clusters (teacher, H = 512: 7 clusters of 16 CTAs on B200): the cluster-resident
+    sequence GRU then serves two utterances per cluster in the forward (one cell warp each, the last cluster a single
+    one) and walks several groups of four sequences per cluster in the backward.  Against the cooperative kernels with the
+    layers one after the other: same prediction and gradients up to the re-association of the dot products."""
+    mix, src = synth.make_mixture(9, 4800)
+    lens = [4800] * 9
+
+    def run(env):
+        for k in ("SE_B200_GRU_CLUSTER", "SE_B200_GRU_PIPE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        model = make_model("crn_teacher", precision="fp32").cuda().train()
+        return _step(model, mix, src, lens, False)
+
+    pred_a, dpred_a, loss_a, grads_a = run({})
+    pred_b, dpred_b, loss_b, grads_b = run({"SE_B200_GRU_CLUSTER": "0", "SE_B200_GRU_PIPE": "0"})
+    assert rel_err(pred_a, pred_b) < 2e-5
+    assert np.allclose(loss_a, loss_b, atol=1e-4)
+    bad = [(k, rel_err(grads_a[k], grads_b[k])) for k in grads_b if not rel_err(grads_a[k], grads_b[k]) < 2e-4]
+    assert not bad, bad
+
+
 def test_tf32_training_gradients_close():
     g = np.load(os.path.join(GOLDEN, "train_grads.npz"))
     model = make_model("crn_small", precision="tf32").cuda().train()
