@@ -1,8 +1,12 @@
-// Persistent GRU recurrence for small batches (training micro-step, CRN_ELU.py:173 through nn.GRU): ONE cooperative
-// launch walks all time steps of all chunks of a layer.  Each warp owns one hidden unit and keeps its three rows of
-// W_hh (forward) or its column of W_hh (backward) in registers for the whole sequence; the hidden state goes through
-// L2 (a few KB) and the steps are separated by grid-wide barriers.  The per-step GEMM launches this replaces spent
-// 44 us per step streaming 3 MB of weights out of L2 for a single row of output (profiles/r01_train_launches_*.csv).
+// Persistent GRU recurrence for small batches (training micro-step and whole-file forward, CRN_ELU.py:173 through
+// nn.GRU): one launch walks the time steps of a range of chunks of a layer with W_hh resident in registers.  Two forms:
+//   * cluster-resident (default; round 2): a thread-block cluster of H / 32 CTAs per sequence, the state exchanged
+//     through distributed shared memory with self-completing stores / bulk copies (gru_seq_*_cluster_kernel below);
+//   * cooperative (round 1; SE_B200_GRU_CLUSTER=0 or where a cluster cannot be placed): each warp owns one hidden unit
+//     and keeps its three rows of W_hh (forward) or its column of W_hh (backward) in registers, the hidden state goes
+//     through L2 (a few KB) and the steps are separated by grid-wide barriers.
+// The per-step GEMM launches these replace spent 44 us per step streaming 3 MB of weights out of L2 for a single row of
+// output (profiles/r01_train_launches_*.csv).
 //
 // Batch layout ("chunk-major"): stream s = n * nb + i is chunk n of utterance i; the state entering chunk n is the
 // state leaving chunk n-1 (CRN_ELU.py:173,183-185), detached for the backward (the gradient stops at chunk borders).

@@ -6,8 +6,10 @@
 //   * GlobalLayerNorm (CRN_ELU.py:37-56), gate (:240), ELU, gated skip blend (:297-306), GRU cell (:173).
 // The carried conv buffers and the GRU state are detached in the reference (CRN_ELU.py:185,243): the gradient of a
 // chunk never leaves the chunk, so the backward runs batched over all chunks of all utterances at once.
-// fp32 on CUDA cores: the training configuration of the reference is one utterance piece per step (config.yaml:92),
-// i.e. a few dozen chunk-streams -- these kernels are sized for that, not for the 1024-stream inference path.
+// The two contractions run on mma.sync.m16n8k8 tf32 (3xTF32 head / tail operands beside the exact fp32 forward, one pass
+// beside the tf32 forward; the fp32 CUDA-core forms stay selectable); everything else is fp32 on CUDA cores.  The
+// training configuration of the reference is one utterance piece per step (config.yaml:92), i.e. a few dozen
+// chunk-streams -- these kernels are sized for that, not for the 1024-stream inference path.
 #include "se_internal.h"
 
 namespace se {
